@@ -1,0 +1,665 @@
+// context.cu -- C ABI (include/amg_b200.h): context, hierarchy upload, per-op entry points,
+// synchronous cycles (Multadd / AFACx / BPX) and the outer solve loop, all enqueued on one CUDA
+// stream and replayed as a CUDA graph per iteration.
+//
+// Reference call paths replaced (host orchestration only; the arithmetic lives in kernels.cu):
+//   SMEM_Solve sync branch          src/SMEM_Solve.cpp:93-252
+//   SMEM_Sync_Add_Vcycle            src/SMEM_Sync_AMG.cpp:408-621  (meaning: src/SEQ_AMG.cpp:110-235)
+//   SMEM_Sync_Parfor_BPXcycle       src/SMEM_Sync_AMG.cpp:147-294
+//   SMEM_Sync_Parfor_AFACx_Vcycle   src/SMEM_Sync_AMG.cpp:296-406
+//   SMEM_Smooth dispatcher          src/SMEM_Solve.cpp:264-377
+#include "ctx.h"
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+int amgb_fail(amgb_ctx *c, int code, const char *fmt, ...)
+{
+   if (c) {
+      va_list ap;
+      va_start(ap, fmt);
+      vsnprintf(c->err, sizeof(c->err), fmt, ap);
+      va_end(ap);
+   }
+   return code;
+}
+
+// ---- device memory helpers ----------------------------------------------------------------------
+template <class T>
+static int dev_alloc(amgb_ctx *c, T **p, size_t n)
+{
+   *p = nullptr;
+   if (n == 0) n = 1;
+   cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
+   if (e != cudaSuccess) return amgb_fail(c, AMGB_ENOMEM, "cudaMalloc(%zu bytes): %s", n * sizeof(T), cudaGetErrorString(e));
+   c->allocs.push_back((void *)*p);
+   c->bytes_allocated += n * sizeof(T);
+   return AMGB_OK;
+}
+template <class T>
+static int dev_upload(amgb_ctx *c, T **p, const T *h, size_t n)
+{
+   int rc = dev_alloc(c, p, n);
+   if (rc) return rc;
+   if (n) CUDA_OK(c, cudaMemcpyAsync(*p, h, n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+   return AMGB_OK;
+}
+static int dev_zero(amgb_ctx *c, double **p, size_t n)
+{
+   int rc = dev_alloc(c, p, n);
+   if (rc) return rc;
+   CUDA_OK(c, cudaMemsetAsync(*p, 0, std::max<size_t>(n, 1) * sizeof(double), c->stream));
+   return AMGB_OK;
+}
+
+int amgb_dev_alloc_bytes(amgb_ctx *c, void **p, size_t bytes, bool zero)
+{
+   char *q = nullptr;
+   int rc = dev_alloc(c, &q, bytes);
+   if (rc) return rc;
+   if (zero) CUDA_OK(c, cudaMemsetAsync(q, 0, std::max<size_t>(bytes, 1), c->stream));
+   *p = q;
+   return AMGB_OK;
+}
+
+extern "C" {
+
+void amgb_default_options(amgb_options *o)
+{
+   // src/SMEM_Main.cpp:64-104
+   o->solver = AMGB_SOLVER_MULTADD;
+   o->smoother = AMGB_SMOOTH_JACOBI;
+   o->smooth_weight = 1.0;
+   o->num_pre_smooth_sweeps = 1;
+   o->num_post_smooth_sweeps = 1;
+   o->num_fine_smooth_sweeps = 1;
+   o->num_coarse_smooth_sweeps = 1;
+   o->jgs_block_rows = 8;
+   o->use_sell = 1;
+   o->l2_persist = 1;
+}
+
+int amgb_create(amgb_ctx **out, int device)
+{
+   if (!out) return AMGB_EINVAL;
+   *out = nullptr;
+   int ndev = 0;
+   cudaError_t e = cudaGetDeviceCount(&ndev);
+   if (e != cudaSuccess || ndev == 0) return AMGB_ECUDA;   // no CPU fallback by design
+   if (device < 0 || device >= ndev) return AMGB_EINVAL;
+   amgb_ctx *c = new amgb_ctx();
+   c->device = device;
+   if (cudaSetDevice(device) != cudaSuccess) { delete c; return AMGB_ECUDA; }
+   cudaDeviceProp prop;
+   cudaGetDeviceProperties(&prop, device);
+   c->cfg.num_sms = prop.multiProcessorCount;
+   c->cfg.ctas_per_sm = 8;
+   c->l2_bytes = prop.l2CacheSize;
+   c->max_window = prop.accessPolicyMaxWindowSize;
+   c->persist_max = prop.persistingL2CacheMaxSize;
+   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return AMGB_ECUDA; }
+   cudaEventCreate(&c->ev0);
+   cudaEventCreate(&c->ev1);
+   cudaMallocHost((void **)&c->h_scalars, 64 * sizeof(double));
+   amgb_default_options(&c->opt);
+   *out = c;
+   return AMGB_OK;
+}
+
+int amgb_destroy(amgb_ctx *c)
+{
+   if (!c) return AMGB_EINVAL;
+   cudaSetDevice(c->device);
+   cudaStreamSynchronize(c->stream);
+   amgb_dist_teardown(c);
+   if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+   for (void *p : c->allocs) cudaFree(p);
+   if (c->h_scalars) cudaFreeHost(c->h_scalars);
+   cudaEventDestroy(c->ev0);
+   cudaEventDestroy(c->ev1);
+   cudaStreamDestroy(c->stream);
+   delete c;
+   return AMGB_OK;
+}
+
+const char *amgb_last_error(const amgb_ctx *c) { return c ? c->err : "null context"; }
+long long amgb_launch_count(const amgb_ctx *c) { return c ? c->launches : 0; }
+
+int amgb_set_num_levels(amgb_ctx *c, int L)
+{
+   if (!c || L < 1 || L > AMGB_MAX_LEVELS) return amgb_fail(c, AMGB_EINVAL, "num_levels %d out of range", L);
+   if (c->L) return amgb_fail(c, AMGB_ESTATE, "hierarchy already defined");
+   c->L = L;
+   c->A.resize(L); c->P.resize(L); c->R.resize(L);
+   c->hA.resize(L);
+   return AMGB_OK;
+}
+
+int amgb_set_options(amgb_ctx *c, const amgb_options *o)
+{
+   if (!c || !o) return AMGB_EINVAL;
+   if (o->smooth_weight == 0.0 || o->jgs_block_rows < 1) return amgb_fail(c, AMGB_EINVAL, "bad options");
+   c->opt = *o;
+   return AMGB_OK;
+}
+
+// choose lanes per row for the CSR vector kernel from the mean row length
+static int pick_lpr(int nrows, int nnz)
+{
+   double avg = nrows > 0 ? (double)nnz / nrows : 0.0;
+   if (avg <= 2.5) return 2;
+   if (avg <= 5.0) return 4;
+   if (avg <= 12.0) return 8;
+   if (avg <= 28.0) return 16;
+   return 32;
+}
+
+// Build the sliced-ELL (C=32) copy on the host when padding stays below 15 %.
+static int build_sell(amgb_ctx *c, DevCSR &M, int nrows, const int *rp, const int *ci, const double *va)
+{
+   const int slices = (nrows + 31) / 32;
+   std::vector<int> off((size_t)slices + 1, 0);
+   long padded = 0;
+   for (int s = 0; s < slices; s++) {
+      int w = 0;
+      for (int r = s * 32; r < std::min(nrows, s * 32 + 32); r++) w = std::max(w, rp[r + 1] - rp[r]);
+      padded += (long)w * 32;
+      if (padded > 2147483000L) return AMGB_OK;   // keep CSR
+      off[s + 1] = (int)padded;
+   }
+   const long nnz = rp[nrows];
+   if (nnz == 0 || (double)padded > 1.15 * (double)nnz) return AMGB_OK;
+   std::vector<int> sci((size_t)padded);
+   std::vector<double> sva((size_t)padded, 0.0);
+#pragma omp parallel for schedule(static)
+   for (int s = 0; s < slices; s++) {
+      const int w = (off[s + 1] - off[s]) / 32;
+      for (int l = 0; l < 32; l++) {
+         const int r = s * 32 + l;
+         for (int k = 0; k < w; k++) {
+            const size_t d = (size_t)off[s] + (size_t)k * 32 + l;
+            if (r < nrows && rp[r] + k < rp[r + 1]) { sci[d] = ci[rp[r] + k]; sva[d] = va[rp[r] + k]; }
+            else { sci[d] = (r < nrows && rp[r + 1] > rp[r]) ? ci[rp[r]] : 0; sva[d] = 0.0; }   // padding: harmless gather, zero value
+         }
+      }
+   }
+   int *d_off, *d_ci; double *d_va;
+   int rc;
+   if ((rc = dev_upload(c, &d_off, off.data(), off.size()))) return rc;
+   if ((rc = dev_upload(c, &d_ci, sci.data(), sci.size()))) return rc;
+   if ((rc = dev_upload(c, &d_va, sva.data(), sva.size()))) return rc;
+   CUDA_OK(c, cudaStreamSynchronize(c->stream));   // host vectors go out of scope
+   M.sell_slices = slices; M.sell_off = d_off; M.sell_ci = d_ci; M.sell_va = d_va;
+   c->sell_entries[&M] = padded;
+   return AMGB_OK;
+}
+
+int amgb_set_matrix(amgb_ctx *c, int kind, int level, int nrows, int ncols, int nnz,
+                    const int *rp, const int *ci, const double *va)
+{
+   if (!c || !rp || (nnz > 0 && (!ci || !va))) return amgb_fail(c, AMGB_EINVAL, "null matrix arrays");
+   if (c->L == 0) return amgb_fail(c, AMGB_ESTATE, "call amgb_set_num_levels first");
+   if (level < 0 || level >= c->L || (kind != AMGB_MAT_A && level >= c->L - 1 && c->L > 1))
+      return amgb_fail(c, AMGB_EINVAL, "level %d out of range for kind %d", level, kind);
+   if (nrows < 0 || ncols < 0 || nnz < 0 || rp[0] != 0 || rp[nrows] != nnz) return amgb_fail(c, AMGB_EINVAL, "inconsistent CSR");
+   CUDA_OK(c, cudaSetDevice(c->device));
+   DevCSR &M = kind == AMGB_MAT_A ? c->A[level] : (kind == AMGB_MAT_P ? c->P[level] : c->R[level]);
+   if (M.rp) return amgb_fail(c, AMGB_ESTATE, "matrix (kind %d, level %d) already set", kind, level);
+   if (kind == AMGB_MAT_A) {
+      if (nrows != ncols) return amgb_fail(c, AMGB_EINVAL, "A must be square");
+      for (int r = 0; r < nrows; r++)
+         if (rp[r + 1] > rp[r] && ci[rp[r]] != r) return amgb_fail(c, AMGB_EINVAL, "A_%d row %d is not diagonal-first", level, r);
+   }
+   int *d_rp, *d_ci; double *d_va;
+   int rc;
+   if ((rc = dev_upload(c, &d_rp, rp, (size_t)nrows + 1))) return rc;
+   if ((rc = dev_upload(c, &d_ci, ci, (size_t)nnz))) return rc;
+   if ((rc = dev_upload(c, &d_va, va, (size_t)nnz))) return rc;
+   M.nrows = nrows; M.ncols = ncols; M.nnz = nnz;
+   M.rp = d_rp; M.ci = d_ci; M.va = d_va;
+   M.lpr = pick_lpr(nrows, nnz);
+   CUDA_OK(c, cudaStreamSynchronize(c->stream));
+   if (c->opt.use_sell && nrows >= 1024) {
+      if ((rc = build_sell(c, M, nrows, rp, ci, va))) return rc;
+   }
+   return AMGB_OK;
+}
+
+// ---- setup ----------------------------------------------------------------------------------------
+int amgb_setup(amgb_ctx *c)
+{
+   if (!c) return AMGB_EINVAL;
+   if (c->ready) return amgb_fail(c, AMGB_ESTATE, "setup already done");
+   const int L = c->L;
+   if (L == 0) return amgb_fail(c, AMGB_ESTATE, "no hierarchy");
+   for (int l = 0; l < L; l++) {
+      if (!c->A[l].rp) return amgb_fail(c, AMGB_ESTATE, "A_%d missing", l);
+      if (l < L - 1) {
+         if (!c->P[l].rp || !c->R[l].rp) return amgb_fail(c, AMGB_ESTATE, "P_%d / R_%d missing", l, l);
+         if (c->P[l].nrows != c->A[l].nrows || c->P[l].ncols != c->A[l + 1].nrows ||
+             c->R[l].nrows != c->A[l + 1].nrows || c->R[l].ncols != c->A[l].nrows)
+            return amgb_fail(c, AMGB_EINVAL, "transfer shapes at level %d do not match", l);
+      }
+   }
+   CUDA_OK(c, cudaSetDevice(c->device));
+   const amgb_options &o = c->opt;
+   const bool multadd = o.solver == AMGB_SOLVER_MULTADD || o.solver == AMGB_SOLVER_ASYNC_MULTADD;
+   c->symmetric = multadd && o.num_pre_smooth_sweeps > 0 && o.num_post_smooth_sweeps > 0 &&
+                  o.smoother != AMGB_SMOOTH_HYBRID_JGS;
+   int rc;
+   c->ws.assign(L, nullptr); c->dow.assign(L, nullptr); c->l1.assign(L, nullptr); c->inv_l1.assign(L, nullptr);
+   c->r.assign(L, nullptr); c->e.assign(L, nullptr); c->t.assign(L, nullptr); c->w.assign(L, nullptr);
+   int maxn = 0;
+   for (int l = 0; l < L; l++) {
+      const int n = c->A[l].nrows;
+      maxn = std::max(maxn, n);
+      if ((rc = dev_alloc(c, &c->ws[l], n))) return rc;
+      if ((rc = dev_alloc(c, &c->dow[l], n))) return rc;
+      if ((rc = dev_alloc(c, &c->l1[l], n))) return rc;
+      if ((rc = dev_alloc(c, &c->inv_l1[l], n))) return rc;
+      c->launches += launch_diag_scale(c->stream, c->A[l], o.smooth_weight, c->ws[l], c->dow[l]);
+      c->launches += launch_l1(c->stream, c->A[l], c->l1[l], c->inv_l1[l]);
+      // column-scaled copy of A's values for the one-pass symmetrised smoother
+      double *sv = nullptr;
+      if ((rc = dev_alloc(c, &sv, (size_t)c->A[l].nnz))) return rc;
+      const double *cs = (o.smoother == AMGB_SMOOTH_L1_JACOBI) ? c->inv_l1[l] : c->ws[l];
+      c->launches += launch_colscale(c->stream, c->A[l].nnz, c->A[l].ci, c->A[l].va, cs, sv);
+      c->A[l].sval = sv;
+      if (c->A[l].sell_slices > 0) {
+         long pe = c->sell_entries[&c->A[l]];
+         double *ssv = nullptr;
+         if ((rc = dev_alloc(c, &ssv, (size_t)pe))) return rc;
+         c->launches += launch_colscale(c->stream, (int)pe, c->A[l].sell_ci, c->A[l].sell_va, cs, ssv);
+         c->A[l].sell_sval = ssv;
+      }
+      if ((rc = dev_zero(c, &c->r[l], n))) return rc;
+      if ((rc = dev_zero(c, &c->e[l], n))) return rc;
+      if ((rc = dev_zero(c, &c->t[l], n))) return rc;
+      if ((rc = dev_zero(c, &c->w[l], n))) return rc;
+   }
+   const int n0 = c->A[0].nrows;
+   if ((rc = dev_zero(c, &c->f, n0))) return rc;
+   if ((rc = dev_zero(c, &c->u, n0))) return rc;
+   if ((rc = dev_zero(c, &c->cvec, n0))) return rc;
+   if ((rc = dev_zero(c, &c->u_outer, n0))) return rc;
+   if ((rc = dev_zero(c, &c->y_outer, n0))) return rc;
+   if ((rc = dev_zero(c, &c->io_a, maxn))) return rc;
+   if ((rc = dev_zero(c, &c->io_b, maxn))) return rc;
+   if ((rc = dev_zero(c, &c->io_c, maxn))) return rc;
+   c->npartials = c->cfg.num_sms * c->cfg.ctas_per_sm;
+   if ((rc = dev_zero(c, &c->partials, c->npartials))) return rc;
+   if ((rc = dev_zero(c, &c->d_scalars, 64))) return rc;
+   CUDA_OK(c, cudaStreamSynchronize(c->stream));
+   c->ready = true;
+   return AMGB_OK;
+}
+
+// ---- vectors --------------------------------------------------------------------------------------
+int amgb_set_rhs(amgb_ctx *c, const double *f)
+{
+   NEED_READY(c);
+   if (!f) return amgb_fail(c, AMGB_EINVAL, "null rhs");
+   CUDA_OK(c, cudaMemcpyAsync(c->f, f, sizeof(double) * c->A[0].nrows, cudaMemcpyHostToDevice, c->stream));
+   CUDA_OK(c, cudaStreamSynchronize(c->stream));
+   return AMGB_OK;
+}
+int amgb_set_solution(amgb_ctx *c, const double *u)
+{
+   NEED_READY(c);
+   if (u) CUDA_OK(c, cudaMemcpyAsync(c->u, u, sizeof(double) * c->A[0].nrows, cudaMemcpyHostToDevice, c->stream));
+   else CUDA_OK(c, cudaMemsetAsync(c->u, 0, sizeof(double) * c->A[0].nrows, c->stream));
+   CUDA_OK(c, cudaStreamSynchronize(c->stream));
+   return AMGB_OK;
+}
+int amgb_get_solution(amgb_ctx *c, double *u)
+{
+   NEED_READY(c);
+   CUDA_OK(c, cudaMemcpyAsync(u, c->u, sizeof(double) * c->A[0].nrows, cudaMemcpyDeviceToHost, c->stream));
+   CUDA_OK(c, cudaStreamSynchronize(c->stream));
+   return AMGB_OK;
+}
+int amgb_get_residual(amgb_ctx *c, double *r)
+{
+   NEED_READY(c);
+   CUDA_OK(c, cudaMemcpyAsync(r, c->r[0], sizeof(double) * c->A[0].nrows, cudaMemcpyDeviceToHost, c->stream));
+   CUDA_OK(c, cudaStreamSynchronize(c->stream));
+   return AMGB_OK;
+}
+
+}  // extern "C"
+
+// ---- enqueue helpers (no host synchronisation) ---------------------------------------------------
+static inline SpmvEpilogue epi(double alpha, double beta, const double *b, double gamma = 0.0, const double *cc = nullptr,
+                               const double *rs = nullptr)
+{
+   SpmvEpilogue e;
+   e.alpha = alpha; e.beta = beta; e.gamma = gamma; e.b = b; e.c = cc; e.rs = rs;
+   return e;
+}
+
+void enq_spmv(amgb_ctx *c, const DevCSR &M, bool sval, const double *x, double *y, const SpmvEpilogue &e, bool norm)
+{
+   int grid = 0;
+   c->launches += launch_spmv(c->cfg, c->stream, M, sval, x, y, e, norm ? c->partials : nullptr, &grid);
+   if (norm) c->launches += launch_reduce_partials(c->stream, c->partials, grid, c->d_scalars);
+}
+
+// r0 = f - A0 u, d_scalars[0] = ||r||^2     (SMEM_Sync_Residual + norm, src/SMEM_Solve.cpp:192-203)
+void enq_residual(amgb_ctx *c)
+{
+   enq_spmv(c, c->A[0], false, c->u, c->r[0], epi(-1.0, 1.0, c->f), true);
+}
+
+// e = S_l f from a zero initial guess, `sweeps` sweeps; scratch: t[l], w[l] are free to use.
+// Dispatch as SMEM_Smooth (src/SMEM_Solve.cpp:264-377).  parfor: the ONE_LEVEL branch (BPX).
+void enq_smooth_zero(amgb_ctx *c, int l, const double *f, double *e, int sweeps, bool symmetric, bool parfor,
+                     double *s1, double *s2)
+{
+   const DevCSR &A = c->A[l];
+   const int n = A.nrows;
+   const int sm = c->opt.smoother;
+   if (sweeps < 1) { cudaMemsetAsync(e, 0, sizeof(double) * n, c->stream); return; }
+   if (sm == AMGB_SMOOTH_HYBRID_JGS) {
+      const double *scale = parfor ? c->dow[l] : nullptr;
+      c->launches += launch_hybrid_jgs(c->cfg, c->stream, A, f, e, nullptr, scale, c->opt.jgs_block_rows, true);
+      for (int k = 1; k < sweeps; k++) {
+         cudaMemcpyAsync(s1, e, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream);
+         c->launches += launch_hybrid_jgs(c->cfg, c->stream, A, f, e, s1, scale, c->opt.jgs_block_rows, false);
+      }
+      return;
+   }
+   const double *rs = (sm == AMGB_SMOOTH_L1_JACOBI) ? c->inv_l1[l] : c->ws[l];
+   if (symmetric) {
+      // sweep 1: e = rs.*(2f - (A*diag(rs)) f)      (src/SMEM_Smooth.cpp:655-695 in one pass)
+      enq_spmv(c, A, true, f, e, epi(-1.0, 2.0, f, 0.0, nullptr, rs), false);
+      for (int k = 1; k < sweeps; k++) {
+         // reference: r = f - A u; then the same update with zero_flags still 1 -> u = S r (:685-701)
+         enq_spmv(c, A, false, e, s1, epi(-1.0, 1.0, f), false);
+         enq_spmv(c, A, true, s1, e, epi(-1.0, 2.0, s1, 0.0, nullptr, rs), false);
+      }
+      return;
+   }
+   // (L1-)Jacobi: sweep 1 from zero guess u = rs.*f (src/SMEM_Smooth.cpp:381-389,422-426); then
+   // u <- u + rs.*(f - A u_prev) with ping-pong buffers, arranged so that the result lands in e
+   double *cur = ((sweeps - 1) & 1) ? s1 : e;
+   double *oth = (cur == e) ? s1 : e;
+   c->launches += launch_scale(c->cfg, c->stream, n, rs, f, cur);
+   for (int k = 1; k < sweeps; k++) {
+      enq_spmv(c, A, false, cur, oth, epi(-1.0, 1.0, f, 1.0, cur, rs), false);
+      std::swap(cur, oth);
+   }
+   (void)s2;
+}
+
+// One additive cycle on residual r[0]:  target = gamma*target + B r.
+void enq_cycle(amgb_ctx *c, double *target, bool accumulate)
+{
+   const int L = c->L;
+   const amgb_options &o = c->opt;
+   const int n0 = c->A[0].nrows;
+   const int solver = o.solver;
+   const bool multadd = solver == AMGB_SOLVER_MULTADD || solver == AMGB_SOLVER_ASYNC_MULTADD;
+   const bool afacx = solver == AMGB_SOLVER_AFACX || solver == AMGB_SOLVER_ASYNC_AFACX;
+   const bool bpx = solver == AMGB_SOLVER_BPX;
+   if (L == 1) {
+      // single level: Multadd/AFACx coarsest contributes nothing; BPX smooths it
+      if (bpx) {
+         enq_smooth_zero(c, 0, c->r[0], c->e[0], o.num_pre_smooth_sweeps, false, true, c->t[0], c->w[0]);
+         if (accumulate) c->launches += launch_add(c->cfg, c->stream, n0, c->e[0], target);
+         else cudaMemcpyAsync(target, c->e[0], sizeof(double) * n0, cudaMemcpyDeviceToDevice, c->stream);
+      } else if (!accumulate) cudaMemsetAsync(target, 0, sizeof(double) * n0, c->stream);
+      return;
+   }
+   // restriction chain, shared by all levels (the reference repeats it per level group,
+   // src/SMEM_Sync_AMG.cpp:475-490; the result is identical)
+   const int last_r = multadd ? L - 2 : L - 1;   // Multadd never reads r_{L-1} (coarsest contributes 0)
+   for (int l = 0; l < last_r; l++) enq_spmv(c, c->R[l], false, c->r[l], c->r[l + 1], epi(1.0, 0.0, nullptr), false);
+   // per-level corrections e_l (levels are independent)
+   const int top = bpx ? L : L - 1;              // BPX also smooths the coarsest level (:217-236)
+   for (int l = 0; l < top; l++) {
+      if (multadd) enq_smooth_zero(c, l, c->r[l], c->e[l], o.num_fine_smooth_sweeps, c->symmetric, false, c->t[l], c->w[l]);
+      else if (bpx) enq_smooth_zero(c, l, c->r[l], c->e[l], o.num_pre_smooth_sweeps, false, true, c->t[l], c->w[l]);
+      else if (afacx) {
+         // src/SEQ_AMG.cpp:172-208: u_c = S_{l+1} r_{l+1}; e = P u_c; r_f = r_l - A_l e; u_f = S_l r_f
+         const int cl = l + 1;
+         double *uc = c->t[cl];
+         enq_smooth_zero(c, cl, c->r[cl], uc, o.num_coarse_smooth_sweeps, false, false, c->w[cl], c->e[cl]);
+         enq_spmv(c, c->P[l], false, uc, c->t[l], epi(1.0, 0.0, nullptr), false);
+         enq_spmv(c, c->A[l], false, c->t[l], c->w[l], epi(-1.0, 1.0, c->r[l]), false);
+         // scratch for the fine smooth must not alias its input w[l] nor the pending e[l+1]
+         enq_smooth_zero(c, l, c->w[l], c->e[l], o.num_fine_smooth_sweeps, false, false, c->t[l], c->t[l]);
+      }
+   }
+   // Horner prolongation: c = e_0 + P_0 (e_1 + P_1 (e_2 + ...)), same sum as the reference's
+   // per-level prolongation chains (src/SEQ_AMG.cpp:213-233)
+   for (int l = top - 2; l >= 1; l--) enq_spmv(c, c->P[l], false, c->e[l + 1], c->e[l], epi(1.0, 1.0, c->e[l]), false);
+   if (top >= 2) {
+      // target = [target +] e_0 + P_0 e_1   (u += e fused into the last prolongation)
+      enq_spmv(c, c->P[0], false, c->e[1], target, epi(1.0, 1.0, c->e[0], 1.0, accumulate ? target : nullptr), false);
+   } else {
+      if (accumulate) c->launches += launch_add(c->cfg, c->stream, n0, c->e[0], target);
+      else cudaMemcpyAsync(target, c->e[0], sizeof(double) * n0, cudaMemcpyDeviceToDevice, c->stream);
+   }
+}
+
+int amgb_fetch_scalar(amgb_ctx *c, double *out)
+{
+   CUDA_OK(c, cudaMemcpyAsync(c->h_scalars, c->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+   CUDA_OK(c, cudaStreamSynchronize(c->stream));
+   *out = c->h_scalars[0];
+   return AMGB_OK;
+}
+
+extern "C" {
+
+// ---- per-op entry points (host in / host out) ------------------------------------------------------
+int amgb_spgemv(amgb_ctx *c, int kind, int level, double alpha, const double *x, double beta, const double *b, double *y)
+{
+   NEED_READY(c);
+   if (level < 0 || level >= c->L || (kind != AMGB_MAT_A && level >= c->L - 1)) return amgb_fail(c, AMGB_EINVAL, "bad level");
+   const DevCSR &M = kind == AMGB_MAT_A ? c->A[level] : (kind == AMGB_MAT_P ? c->P[level] : c->R[level]);
+   if (!x || !y || (beta != 0.0 && !b)) return amgb_fail(c, AMGB_EINVAL, "null vector");
+   CUDA_OK(c, cudaMemcpyAsync(c->io_a, x, sizeof(double) * M.ncols, cudaMemcpyHostToDevice, c->stream));
+   if (beta != 0.0) CUDA_OK(c, cudaMemcpyAsync(c->io_b, b, sizeof(double) * M.nrows, cudaMemcpyHostToDevice, c->stream));
+   enq_spmv(c, M, false, c->io_a, c->io_c, epi(alpha, beta, beta != 0.0 ? c->io_b : nullptr), false);
+   CUDA_OK(c, cudaMemcpyAsync(y, c->io_c, sizeof(double) * M.nrows, cudaMemcpyDeviceToHost, c->stream));
+   CUDA_OK(c, cudaStreamSynchronize(c->stream));
+   CUDA_OK(c, cudaGetLastError());
+   return AMGB_OK;
+}
+
+int amgb_smooth(amgb_ctx *c, int level, int smoother, int symmetric, int sweeps, int zero_guess, const double *f, double *u)
+{
+   NEED_READY(c);
+   if (level < 0 || level >= c->L || !f || !u || sweeps < 1) return amgb_fail(c, AMGB_EINVAL, "bad smooth arguments");
+   if (smoother != c->opt.smoother) return amgb_fail(c, AMGB_EINVAL, "smoother %d differs from the one set up (%d)", smoother, c->opt.smoother);
+   const DevCSR &A = c->A[level];
+   const int n = A.nrows;
+   CUDA_OK(c, cudaMemcpyAsync(c->io_a, f, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+   if (zero_guess) {
+      enq_smooth_zero(c, level, c->io_a, c->io_b, sweeps, symmetric != 0, false, c->io_c, c->w[level]);
+   } else {
+      // general sweeps from a given u (src/SMEM_Smooth.cpp:391-402,428-439,565-581)
+      CUDA_OK(c, cudaMemcpyAsync(c->io_b, u, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+      if (symmetric) return amgb_fail(c, AMGB_EINVAL, "symmetrised smoother is only used from a zero guess");
+      double *cur = c->io_b, *oth = c->io_c;
+      for (int k = 0; k < sweeps; k++) {
+         if (smoother == AMGB_SMOOTH_HYBRID_JGS) {
+            CUDA_OK(c, cudaMemcpyAsync(oth, cur, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+            c->launches += launch_hybrid_jgs(c->cfg, c->stream, A, c->io_a, cur, oth, nullptr, c->opt.jgs_block_rows, false);
+         } else {
+            const double *rs = (smoother == AMGB_SMOOTH_L1_JACOBI) ? c->inv_l1[level] : c->ws[level];
+            enq_spmv(c, A, false, cur, oth, epi(-1.0, 1.0, c->io_a, 1.0, cur, rs), false);
+            std::swap(cur, oth);
+         }
+      }
+      if (cur != c->io_b) CUDA_OK(c, cudaMemcpyAsync(c->io_b, cur, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+   }
+   CUDA_OK(c, cudaMemcpyAsync(u, c->io_b, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+   CUDA_OK(c, cudaStreamSynchronize(c->stream));
+   CUDA_OK(c, cudaGetLastError());
+   return AMGB_OK;
+}
+
+int amgb_norm2(amgb_ctx *c, const double *x, int n, double *out)
+{
+   NEED_READY(c);
+   int maxn = 0;
+   for (auto &a : c->A) maxn = std::max(maxn, a.nrows);
+   if (!x || !out || n < 0 || n > maxn) return amgb_fail(c, AMGB_EINVAL, "bad norm2 arguments");
+   CUDA_OK(c, cudaMemcpyAsync(c->io_a, x, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+   int grid = 0;
+   c->launches += launch_sumsq(c->cfg, c->stream, n, c->io_a, c->partials, &grid);
+   c->launches += launch_reduce_partials(c->stream, c->partials, grid, c->d_scalars);
+   double ss;
+   int rc = amgb_fetch_scalar(c, &ss);
+   if (rc) return rc;
+   *out = sqrt(ss);
+   return AMGB_OK;
+}
+
+int amgb_cycle(amgb_ctx *c, const double *r_host, double *c_host)
+{
+   NEED_READY(c);
+   if (!r_host || !c_host) return amgb_fail(c, AMGB_EINVAL, "null vector");
+   const int n0 = c->A[0].nrows;
+   CUDA_OK(c, cudaMemcpyAsync(c->r[0], r_host, sizeof(double) * n0, cudaMemcpyHostToDevice, c->stream));
+   enq_cycle(c, c->cvec, false);
+   CUDA_OK(c, cudaMemcpyAsync(c_host, c->cvec, sizeof(double) * n0, cudaMemcpyDeviceToHost, c->stream));
+   CUDA_OK(c, cudaStreamSynchronize(c->stream));
+   CUDA_OK(c, cudaGetLastError());
+   return AMGB_OK;
+}
+
+// ---- SMEM_Solve, synchronous branch ----------------------------------------------------------------
+int amgb_solve_sync(amgb_ctx *c, double tol, int max_cycles, int cheby_flag, double mu, double delta,
+                    double *hist, int *n_cycles, double *solve_seconds)
+{
+   NEED_READY(c);
+   if (max_cycles < 0) return amgb_fail(c, AMGB_EINVAL, "max_cycles < 0");
+   const int n0 = c->A[0].nrows;
+   int rc;
+   // r0 (src/SMEM_Solve.cpp:60-70)
+   enq_residual(c);
+   double ss;
+   if ((rc = amgb_fetch_scalar(c, &ss))) return rc;
+   const double r0 = sqrt(ss);
+   if (hist) hist[0] = 1.0;
+   int done = 0;
+   double omega = 2.0;
+   const double mu24 = 4.0 * mu * mu;
+   if (cheby_flag) {
+      CUDA_OK(c, cudaMemsetAsync(c->u_outer, 0, sizeof(double) * n0, c->stream));
+      CUDA_OK(c, cudaMemsetAsync(c->y_outer, 0, sizeof(double) * n0, c->stream));
+   }
+   // one iteration = cycle + residual + norm; captured once, replayed as a graph
+   cudaGraphExec_t gexec = nullptr;
+   long long graph_nodes = 0;
+   if (!cheby_flag) {
+      if (!c->graph_exec) {
+         cudaGraph_t g;
+         long long before = c->launches;
+         CUDA_OK(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+         enq_cycle(c, c->u, true);
+         enq_residual(c);
+         cudaMemcpyAsync(c->h_scalars, c->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+         CUDA_OK(c, cudaStreamEndCapture(c->stream, &g));
+         c->graph_kernels = c->launches - before;
+         c->launches = before;
+         CUDA_OK(c, cudaGraphInstantiate(&c->graph_exec, g, 0));
+         cudaGraphDestroy(g);
+      }
+      gexec = c->graph_exec;
+      graph_nodes = c->graph_kernels;
+   }
+   CUDA_OK(c, cudaEventRecord(c->ev0, c->stream));
+   for (int k = 1; k <= max_cycles; k++) {
+      if (gexec) {
+         CUDA_OK(c, cudaGraphLaunch(gexec, c->stream));
+         c->launches += graph_nodes;
+         CUDA_OK(c, cudaStreamSynchronize(c->stream));
+         ss = c->h_scalars[0];
+      } else {
+         // Chebyshev acceleration (src/SMEM_Solve.cpp:169-188): cycle from a zero guess on the
+         // current residual, then the three-term recurrence
+         enq_cycle(c, c->cvec, false);
+         c->launches += launch_cheby(c->cfg, c->stream, n0, omega, delta, c->cvec, c->u_outer, c->y_outer, c->u);
+         omega = 1.0 / (1.0 - omega / mu24);
+         enq_residual(c);
+         if ((rc = amgb_fetch_scalar(c, &ss))) return rc;
+      }
+      done = k;
+      const double rel = sqrt(ss) / r0;
+      if (hist) hist[k] = rel;
+      if (rel < tol) break;
+   }
+   CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));
+   CUDA_OK(c, cudaEventSynchronize(c->ev1));
+   float ms = 0;
+   cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+   if (solve_seconds) *solve_seconds = ms * 1e-3;
+   if (n_cycles) *n_cycles = done;
+   c->r0_norm = r0;
+   CUDA_OK(c, cudaGetLastError());
+   return AMGB_OK;
+}
+
+int amgb_smem_solve(amgb_ctx *c, const double *f_host, double *u_host, double tol, int num_cycles,
+                    double *hist, int *n_cycles, int *corrections, double *final_relres, double *solve_seconds)
+{
+   NEED_READY(c);
+   if (!f_host || !u_host) return amgb_fail(c, AMGB_EINVAL, "null host buffers");
+   const int n0 = c->A[0].nrows;
+   int rc;
+   CUDA_OK(c, cudaMemcpyAsync(c->f, f_host, sizeof(double) * n0, cudaMemcpyHostToDevice, c->stream));
+   CUDA_OK(c, cudaMemsetAsync(c->u, 0, sizeof(double) * n0, c->stream));   // InitSolve: x0 = 0
+   const int solver = c->opt.solver;
+   int done = 0;
+   double rel = 0.0;
+   if (solver == AMGB_SOLVER_ASYNC_MULTADD || solver == AMGB_SOLVER_ASYNC_AFACX) {
+      if ((rc = amgb_solve_async(c, num_cycles, AMGB_CONVERGE_LOCAL, corrections, &rel, solve_seconds))) return rc;
+      done = num_cycles;
+   } else {
+      std::vector<double> h((size_t)num_cycles + 1, 0.0);
+      if ((rc = amgb_solve_sync(c, tol, num_cycles, 0, 1.0, 1.0, h.data(), &done, solve_seconds))) return rc;
+      if (hist) memcpy(hist, h.data(), sizeof(double) * ((size_t)done + 1));
+      if (corrections) for (int l = 0; l < c->L; l++) corrections[l] = done;   // src/SMEM_Solve.cpp:246-248
+      rel = h[done];
+   }
+   if (n_cycles) *n_cycles = done;
+   if (final_relres) *final_relres = rel;
+   CUDA_OK(c, cudaMemcpyAsync(u_host, c->u, sizeof(double) * n0, cudaMemcpyDeviceToHost, c->stream));
+   CUDA_OK(c, cudaStreamSynchronize(c->stream));
+   return AMGB_OK;
+}
+
+int amgb_time_residual(amgb_ctx *c, int reps, double *ms_per_launch)
+{
+   NEED_READY(c);
+   if (reps < 1 || !ms_per_launch) return amgb_fail(c, AMGB_EINVAL, "bad arguments");
+   CUDA_OK(c, cudaStreamSynchronize(c->stream));
+   CUDA_OK(c, cudaEventRecord(c->ev0, c->stream));
+   for (int k = 0; k < reps; k++) {
+      int grid;
+      c->launches += launch_spmv(c->cfg, c->stream, c->A[0], false, c->u, c->r[0], epi(-1.0, 1.0, c->f), c->partials, &grid);
+   }
+   CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));
+   CUDA_OK(c, cudaEventSynchronize(c->ev1));
+   float ms = 0;
+   cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+   *ms_per_launch = ms / reps;
+   return AMGB_OK;
+}
+
+int amgb_level_storage(amgb_ctx *c, int kind, int level, int *is_sell)
+{
+   if (!c || level < 0 || level >= c->L || !is_sell) return AMGB_EINVAL;
+   const DevCSR &M = kind == AMGB_MAT_A ? c->A[level] : (kind == AMGB_MAT_P ? c->P[level] : c->R[level]);
+   *is_sell = M.sell_slices > 0;
+   return AMGB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,72 @@
+// ctx.h -- internal context shared by context.cu / async.cu / dist.cu (not part of the C ABI).
+#pragma once
+#include "amg_b200.h"
+#include "launch.h"
+#include <map>
+#include <vector>
+
+struct DistState;
+
+struct amgb_ctx {
+   int device = 0;
+   cudaStream_t stream = nullptr;
+   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+   LaunchCfg cfg;
+   amgb_options opt;
+   int L = 0;
+   bool ready = false;
+   bool symmetric = false;
+   std::vector<DevCSR> A, P, R;
+   std::vector<int> hA;
+   std::map<const DevCSR *, long> sell_entries;
+   // per level: w/d, d/w, l1, 1/l1; residual chain, correction chain, two scratch vectors
+   std::vector<double *> ws, dow, l1, inv_l1, r, e, t, w;
+   double *f = nullptr, *u = nullptr, *cvec = nullptr, *u_outer = nullptr, *y_outer = nullptr;
+   double *io_a = nullptr, *io_b = nullptr, *io_c = nullptr;
+   double *partials = nullptr;
+   int npartials = 0;
+   double *d_scalars = nullptr;
+   double *h_scalars = nullptr;   // pinned
+   double r0_norm = 0.0;
+   cudaGraphExec_t graph_exec = nullptr;
+   long long graph_kernels = 0;
+   long long launches = 0;
+   size_t bytes_allocated = 0;
+   size_t l2_bytes = 0, max_window = 0, persist_max = 0;
+   std::vector<void *> allocs;
+   // async
+   void *async_params_dev = nullptr;
+   AsyncParams *async_host = nullptr;
+   cudaAccessPolicyWindow window = {};
+   bool window_valid = false;
+   bool async_ready = false;
+   int async_grid = 0;
+   std::vector<int> async_cta_begin;
+   // distributed
+   DistState *dist = nullptr;
+   char err[512] = {0};
+};
+
+int amgb_fail(amgb_ctx *c, int code, const char *fmt, ...);
+void amgb_dist_teardown(amgb_ctx *c);
+
+#define CUDA_OK(c, call)                                                                                   \
+   do {                                                                                                    \
+      cudaError_t e__ = (call);                                                                            \
+      if (e__ != cudaSuccess)                                                                              \
+         return amgb_fail((c), AMGB_ECUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e__)); \
+   } while (0)
+
+#define NEED_READY(c)                                                                      \
+   do {                                                                                    \
+      if (!(c)) return AMGB_EINVAL;                                                        \
+      if (!(c)->ready) return amgb_fail((c), AMGB_ESTATE, "amgb_setup not called");        \
+      CUDA_OK((c), cudaSetDevice((c)->device));                                            \
+   } while (0)
+
+// helpers exported by context.cu to async.cu / dist.cu
+int amgb_dev_alloc_bytes(amgb_ctx *c, void **p, size_t bytes, bool zero);
+void enq_spmv(amgb_ctx *c, const DevCSR &M, bool sval, const double *x, double *y, const SpmvEpilogue &e, bool norm);
+void enq_residual(amgb_ctx *c);
+void enq_cycle(amgb_ctx *c, double *target, bool accumulate);
+int amgb_fetch_scalar(amgb_ctx *c, double *out);

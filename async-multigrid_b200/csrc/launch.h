@@ -1,0 +1,67 @@
+// launch.h -- host-side launchers of the stand-alone kernels (kernels.cu) and of the persistent
+// asynchronous kernel (async.cu).  Every launcher returns the number of kernels it launched.
+#pragma once
+#include "common.cuh"
+
+struct LaunchCfg {
+   int num_sms = 148;
+   int ctas_per_sm = 8;
+};
+
+// y = gamma*c + rs.*(beta*b + alpha*M*x); optional sum of y_i^2 into partial sums (one per CTA,
+// `partials` must hold >= grid entries; *grid_out receives the grid used).
+int launch_spmv(const LaunchCfg &cfg, cudaStream_t st, const DevCSR &M, bool use_sval, const double *x, double *y,
+                const SpmvEpilogue &e, double *partials, int *grid_out);
+// out[0] = sum(partials[0..n)); if hist != nullptr: hist[k] = sqrt(out[0]) (and r0 handling on host)
+int launch_reduce_partials(cudaStream_t st, const double *partials, int n, double *out);
+// y = a.*x  (zero-guess Jacobi: u = (w/d).*f, src/SMEM_Smooth.cpp:381-389)
+int launch_scale(const LaunchCfg &cfg, cudaStream_t st, int n, const double *a, const double *x, double *y);
+// y += x
+int launch_add(const LaunchCfg &cfg, cudaStream_t st, int n, const double *x, double *y);
+// Chebyshev update (src/SMEM_Solve.cpp:179-187): uo_prev=uo; uo = yo + omega*(delta*c + uo - yo); yo = uo_prev; u = uo
+int launch_cheby(const LaunchCfg &cfg, cudaStream_t st, int n, double omega, double delta, const double *c,
+                 double *u_outer, double *y_outer, double *u);
+// partial sums of x_i^2
+int launch_sumsq(const LaunchCfg &cfg, cudaStream_t st, int n, const double *x, double *partials, int *grid_out);
+// hybrid JGS sweep
+int launch_hybrid_jgs(const LaunchCfg &cfg, cudaStream_t st, const DevCSR &A, const double *f, double *u,
+                      const double *u_prev, const double *scale, int block_rows, bool zero_guess);
+// setup helpers: ws = w/d (0 where d == 0), l1 = sum |a_ij|, sval = va .* cs[col]
+int launch_diag_scale(cudaStream_t st, const DevCSR &A, double w, double *ws, double *dow);
+int launch_l1(cudaStream_t st, const DevCSR &A, double *l1, double *inv_l1);
+int launch_colscale(cudaStream_t st, int nnz, const int *ci, const double *va, const double *cs, double *out);
+
+// ---- persistent asynchronous kernel (async.cu) ---------------------------------------------------
+#define AMGB_MAX_LEVELS 32
+struct AsyncLevelVecs {           // per CTA group (the reference's level_vector[k], src/SMEM_Setup.cpp:314-341)
+   double *r[AMGB_MAX_LEVELS];    // residual chain r_0 .. r_k
+   double *e[AMGB_MAX_LEVELS];    // correction chain e_k .. e_0
+   double *t[AMGB_MAX_LEVELS];    // scratch (u_prev / AFACx work)
+   double *w[AMGB_MAX_LEVELS];    // scratch (AFACx r_fine)
+   double *u_local;               // the group's private copy of the fine solution
+};
+struct AsyncParams {
+   int num_levels;
+   int solver;                    // AMGB_SOLVER_ASYNC_MULTADD / ASYNC_AFACX
+   int smoother;
+   int symmetric;
+   int fine_sweeps, coarse_sweeps;
+   int jgs_block_rows;
+   int num_cycles;
+   int converge_type;
+   DevCSR A[AMGB_MAX_LEVELS], P[AMGB_MAX_LEVELS], R[AMGB_MAX_LEVELS];
+   const double *ws[AMGB_MAX_LEVELS];       // w/d
+   const double *inv_l1[AMGB_MAX_LEVELS];   // 1/l1
+   AsyncLevelVecs g[AMGB_MAX_LEVELS];
+   int cta_begin[AMGB_MAX_LEVELS + 1];      // CTA range of every level's group
+   const double *f;
+   double *u;                               // shared fine solution (atomic adds)
+   unsigned int *barrier_count;             // [L] arrive counters
+   volatile unsigned int *barrier_gen;      // [L] generations
+   int *num_correct;                        // [L] local_num_correct
+   int *group_stop;                         // [L] the group root's stop decision (GLOBAL rule)
+   volatile int *converge_flag;             // thread.converge_flag
+};
+int launch_async(const LaunchCfg &cfg, cudaStream_t st, const AsyncParams *params_dev, int grid, int block,
+                 const cudaAccessPolicyWindow *window);
+int async_max_grid(int block);

@@ -1,0 +1,340 @@
+"""Host-side input provider: problem matrices, AMG hierarchy, smoothed transfers, RHS,
+thread-group (-> CTA-group) partition.  Mirrors what the reference's SMEM_Setup hands to
+the solve phase (/root/reference/src/SMEM_Setup.cpp:55-180, 182-276, 590-1036, 1038-1171).
+
+hypre-BoomerAMG is absent from this image; `libamg_host.so` (host/amg_host.cpp) supplies a
+classical AMG hierarchy of the same shape (diag-first CSR A_l, P_l).  All of this runs on
+the CPU and is NOT the accelerated path.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+from . import build as _build
+
+# enums shared with the reference (src/Main.hpp:47-75) ------------------------------------
+JACOBI = 0
+HYBRID_JACOBI_GAUSS_SEIDEL = 2
+L1_JACOBI = 6
+MULT, AFACX, MULTADD, BPX = 0, 1, 2, 3
+ASYNC_AFACX, ASYNC_MULTADD = 5, 6
+
+
+class _CSR(C.Structure):
+    _fields_ = [("nrows", C.c_int), ("ncols", C.c_int), ("nnz", C.c_int),
+                ("i", C.POINTER(C.c_int)), ("j", C.POINTER(C.c_int)), ("data", C.POINTER(C.c_double))]
+
+
+_lib = None
+
+
+def host_lib():
+    global _lib
+    if _lib is None:
+        path = _build.HOST_LIB
+        if not os.path.exists(path):
+            _build.build_host()
+        L = C.CDLL(path)
+        L.amgh_setup.restype = C.c_void_p
+        L.amgh_setup.argtypes = [C.POINTER(_CSR), C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.amgh_level_A.restype = C.POINTER(_CSR)
+        L.amgh_level_A.argtypes = [C.c_void_p, C.c_int]
+        L.amgh_level_P.restype = C.POINTER(_CSR)
+        L.amgh_level_P.argtypes = [C.c_void_p, C.c_int]
+        L.amgh_num_levels.argtypes = [C.c_void_p]
+        L.amgh_destroy.argtypes = [C.c_void_p]
+        L.amgh_rand_fill.argtypes = [C.c_void_p, C.c_long, C.c_double, C.c_double, C.c_uint]
+        L.amgh_rand_fill.restype = None
+        L.amgh_csr_free.argtypes = [C.POINTER(_CSR)]
+        L.amgh_csr_free.restype = None
+        L.amgh_smooth_transfer.argtypes = [C.POINTER(_CSR), C.POINTER(_CSR), C.c_int, C.c_double,
+                                           C.c_int, C.c_int, C.POINTER(_CSR), C.POINTER(_CSR)]
+        _lib = L
+    return _lib
+
+
+class CSR:
+    """Plain CSR triple (int32 indices, fp64 values) -- the layout of hypre_CSRMatrix
+    {i, j, data} the reference kernels index (src/SMEM_MatVec.cpp:311-322)."""
+
+    def __init__(self, nrows, ncols, indptr, indices, data):
+        self.nrows, self.ncols = int(nrows), int(ncols)
+        self.indptr = np.ascontiguousarray(indptr, dtype=np.int32)
+        self.indices = np.ascontiguousarray(indices, dtype=np.int32)
+        self.data = np.ascontiguousarray(data, dtype=np.float64)
+        self.nnz = int(self.indptr[-1])
+
+    @property
+    def shape(self):
+        return (self.nrows, self.ncols)
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        return sp.csr_matrix((self.data, self.indices, self.indptr), shape=self.shape)
+
+    @staticmethod
+    def from_scipy(m, diag_first=False):
+        m = m.tocsr()
+        m.sort_indices()
+        c = CSR(m.shape[0], m.shape[1], m.indptr, m.indices, m.data)
+        if diag_first:
+            c.make_diag_first()
+        return c
+
+    def make_diag_first(self):
+        ip, ix, dv = self.indptr, self.indices, self.data
+        rows = np.repeat(np.arange(self.nrows, dtype=np.int64), np.diff(ip))
+        isd = ix == rows
+        pos = np.nonzero(isd)[0]
+        for p in pos:  # small matrices only (tests); the C++ path does the big ones
+            r = rows[p]
+            s = ip[r]
+            if p != s:
+                ix[s + 1:p + 1], ix[s] = ix[s:p].copy(), ix[p]
+                dv[s + 1:p + 1], dv[s] = dv[s:p].copy(), dv[p]
+
+    def diagonal(self):
+        return self.data[self.indptr[:-1]].copy()
+
+    def _as_c(self):
+        s = _CSR()
+        s.nrows, s.ncols, s.nnz = self.nrows, self.ncols, self.nnz
+        s.i = self.indptr.ctypes.data_as(C.POINTER(C.c_int))
+        s.j = self.indices.ctypes.data_as(C.POINTER(C.c_int))
+        s.data = self.data.ctypes.data_as(C.POINTER(C.c_double))
+        return s
+
+
+def _take(cs, free=True):
+    """copy a C-side amgh_csr into numpy-owned arrays"""
+    n, nnz = cs.nrows, cs.nnz
+    ip = np.ctypeslib.as_array(cs.i, shape=(n + 1,)).copy()
+    ix = np.ctypeslib.as_array(cs.j, shape=(max(nnz, 1),))[:nnz].copy()
+    dv = np.ctypeslib.as_array(cs.data, shape=(max(nnz, 1),))[:nnz].copy()
+    out = CSR(n, cs.ncols, ip, ix, dv)
+    if free:
+        host_lib().amgh_csr_free(C.byref(cs))
+    return out
+
+
+def laplacian(problem, nx, ny=None, nz=None):
+    """'5pt' (n x n), '7pt', '27pt' (nx x ny x nz); diag-first CSR, natural ordering."""
+    L = host_lib()
+    out = _CSR()
+    ny = nx if ny is None else ny
+    nz = nx if nz is None else nz
+    if problem == "5pt":
+        rc = L.amgh_laplacian_5pt(C.c_int(nx), C.byref(out))
+    elif problem == "7pt":
+        rc = L.amgh_laplacian_7pt(C.c_int(nx), C.c_int(ny), C.c_int(nz), C.byref(out))
+    elif problem == "27pt":
+        rc = L.amgh_laplacian_27pt(C.c_int(nx), C.c_int(ny), C.c_int(nz), C.byref(out))
+    else:
+        raise ValueError("unknown problem %r" % problem)
+    if rc != 0:
+        raise ValueError("problem too large for int32 CSR")
+    return _take(out)
+
+
+def rand_rhs(n, lo=-1.0, hi=1.0, seed=0):
+    """SMEM RHS: srand(0); b_i = RandDouble(-1,1) (src/SMEM_Setup.cpp:1729-1742)."""
+    b = np.empty(n, dtype=np.float64)
+    host_lib().amgh_rand_fill(b.ctypes.data_as(C.c_void_p), C.c_long(n), lo, hi, C.c_uint(seed))
+    return b
+
+
+class Hierarchy:
+    """Per-level A (diag-first), P (plain), and the transfer operators the selected cycle
+    uses: for MULTADD P̄ = G P and R̄ = Pᵀ GT (SMEM_Setup.cpp:244-260,1173-1254); for
+    AFACX / BPX plain P and R = Pᵀ (SMEM_Setup.cpp:262-274)."""
+
+    def __init__(self, A, P):
+        self.A = A
+        self.P_plain = P
+        self.num_levels = len(A)
+        self.n = [a.nrows for a in A]
+        self.P = None
+        self.R = None
+        self.smooth_weight = None
+        self.l1 = None
+
+    def build_transfers(self, solver=MULTADD, smooth_weight=1.0, smooth_interp_type=JACOBI,
+                        num_pre=1, num_post=1):
+        L = host_lib()
+        self.P, self.R = [], []
+        self.smooth_weight = smooth_weight
+        for l in range(self.num_levels - 1):
+            a_c, p_c = self.A[l]._as_c(), self.P_plain[l]._as_c()
+            if solver in (MULTADD, ASYNC_MULTADD) and (num_pre > 0 or num_post > 0):
+                pb, rb = _CSR(), _CSR()
+                kind = 0 if smooth_interp_type in (JACOBI, HYBRID_JACOBI_GAUSS_SEIDEL) else 1
+                L.amgh_smooth_transfer(C.byref(a_c), C.byref(p_c), kind, smooth_weight,
+                                       int(num_post > 0), int(num_pre > 0), C.byref(pb), C.byref(rb))
+                self.P.append(_take(pb) if num_post > 0 else self.P_plain[l])
+                if num_pre > 0:
+                    self.R.append(_take(rb))
+                else:
+                    self.R.append(self._transpose(self.P_plain[l]))
+            else:
+                self.P.append(self.P_plain[l])
+                self.R.append(self._transpose(self.P_plain[l]))
+        return self
+
+    @staticmethod
+    def _transpose(p):
+        L = host_lib()
+        out = _CSR()
+        pc = p._as_c()
+        L.amgh_restriction_from_P(C.byref(pc), C.byref(out))
+        return _take(out)
+
+    def l1_norms(self):
+        if self.l1 is None:
+            self.l1 = []
+            for a in self.A:
+                rows = np.repeat(np.arange(a.nrows), np.diff(a.indptr))
+                self.l1.append(np.bincount(rows, weights=np.abs(a.data), minlength=a.nrows))
+        return self.l1
+
+    def operator_complexity(self):
+        return sum(a.nnz for a in self.A) / self.A[0].nnz
+
+
+def amg_setup(A, theta=0.25, max_levels=25, max_coarse=9, pmax=4, jacobi_interp_steps=1, verbose=False):
+    """Classical AMG hierarchy (stand-in for HYPRE_BoomerAMGSetup, SMEM_Setup.cpp:65)."""
+    L = host_lib()
+    a_c = A._as_c()
+    h = L.amgh_setup(C.byref(a_c), theta, max_levels, max_coarse, pmax, jacobi_interp_steps, int(verbose))
+    nl = L.amgh_num_levels(h)
+    As = [_take(L.amgh_level_A(h, l).contents, free=False) for l in range(nl)]
+    Ps = [_take(L.amgh_level_P(h, l).contents, free=False) for l in range(nl - 1)]
+    L.amgh_destroy(h)
+    return Hierarchy(As, Ps)
+
+
+# ---------------------------------------------------------------------------------------------
+# work model and group partition (src/SMEM_Setup.cpp:1038-1171, 770-854, 870-893, 945-979)
+# ---------------------------------------------------------------------------------------------
+def compute_work(h, solver=MULTADD, num_pre=1, num_post=1, fine_sweeps=1, coarse_sweeps=1):
+    """level_work / frac_level_work for res_compute_type == LOCAL."""
+    L = h.num_levels
+    work = [0] * L
+    multadd = solver in (MULTADD, ASYNC_MULTADD)
+    for level in range(L):
+        w = h.A[0].nnz + h.A[0].nrows
+        coarsest = level if multadd else level + 1
+        for inner in range(coarsest):
+            if inner >= L - 1:
+                continue
+            if multadd:
+                w += h.R[inner].nnz
+            elif level < L - 1:
+                w += inner * h.R[inner].nnz
+        if level == L - 1:
+            w += h.A[level].nnz
+        elif multadd:
+            if num_post > 0 and num_pre > 0:
+                w += fine_sweeps * (h.A[level].nnz + h.A[level].nrows)
+            else:
+                w += h.A[level].nrows
+        else:
+            w += ((coarse_sweeps - 1) * h.A[level + 1].nnz + h.P[level].nnz + h.A[level].nnz
+                  + (fine_sweeps - 1) * h.A[level].nnz)
+        for inner in range(level):
+            w += h.P[inner].nnz
+        work[level] = w
+    tot = float(sum(work))
+    return work, [x / tot for x in work]
+
+
+def balanced_threads(frac, num_threads):
+    """BALANCED_THREADS distribution of src/SMEM_Setup.cpp:770-854: deal threads round-robin,
+    then move one thread at a time from the most over- to the most under-provisioned level."""
+    L = len(frac)
+    tpl = [0] * L
+    lvl = 0
+    for _ in range(num_threads):
+        tpl[lvl] += 1
+        lvl = lvl + 1 if lvl < L - 1 else 0
+    prev = float("inf")
+    while True:
+        max_diff, k_max = 0.0, 0
+        for k in range(L):
+            diff = frac[k] - tpl[k] / num_threads
+            if abs(diff) > abs(max_diff):
+                if max_diff < 0.0 and tpl[k] == 1:
+                    pass
+                else:
+                    max_diff, k_max = diff, k
+        min_diff, k_min, not_found = float("inf"), 0, True
+        for k in range(L):
+            if k == k_max:
+                continue
+            diff = frac[k] - tpl[k] / num_threads
+            if max_diff > 0.0:
+                if diff < 0.0 and tpl[k] > 1 and abs(diff) < abs(min_diff):
+                    min_diff, k_min, not_found = diff, k, False
+            else:
+                if diff > 0.0 and abs(diff) < abs(min_diff):
+                    min_diff, k_min, not_found = diff, k, False
+        if abs(max_diff) >= abs(prev) or not_found:
+            break
+        prev = max_diff
+        if max_diff > 0.0:
+            tpl[k_min] -= 1
+            tpl[k_max] += 1
+        else:
+            tpl[k_min] += 1
+            tpl[k_max] -= 1
+    return tpl
+
+
+def nnz_balanced_bounds(indptr, nparts):
+    """[ns,ne) per part from the nnz-balanced split (hypre_LowerBound on the row pointer),
+    src/SMEM_Setup.cpp:870-893."""
+    n = len(indptr) - 1
+    nnz = int(indptr[-1])
+    per = (nnz + nparts - 1) // nparts
+    b = [0]
+    for t in range(1, nparts):
+        b.append(int(np.searchsorted(indptr[:n], per * t, side="left")))
+    b.append(n)
+    return np.asarray(b, dtype=np.int32)
+
+
+def uniform_blocks(n, block_rows):
+    """hybrid-JGS block list used on the GPU: contiguous blocks of `block_rows` rows."""
+    b = np.arange(0, n + block_rows, block_rows, dtype=np.int64)
+    b[-1] = n
+    if len(b) >= 2 and b[-2] >= n:
+        b = b[:-1]
+        b[-1] = n
+    return b.astype(np.int32)
+
+
+# ---------------------------------------------------------------------------------------------
+# algorithmic byte model (SURVEY.md 8d / BASELINE.md 3)
+# ---------------------------------------------------------------------------------------------
+def bytes_spmv(m, with_b):
+    return 12 * m.nnz + 4 * (m.nrows + 1) + 8 * m.ncols + 8 * m.nrows + (8 * m.nrows if with_b else 0)
+
+
+def bytes_sync_multadd_cycle(h, symmetric=True):
+    L = h.num_levels
+    tot = bytes_spmv(h.A[0], True)
+    for l in range(L - 1):
+        tot += bytes_spmv(h.R[l], False)
+        tot += (bytes_spmv(h.A[l], False) + 8 * h.n[l]) if symmetric else 24 * h.n[l]
+        tot += bytes_spmv(h.P[l], True)
+    tot += 8 * h.n[0]
+    return tot
+
+
+def bytes_async_chain(h, k, symmetric=True):
+    tot = 0
+    for l in range(min(k, h.num_levels - 1)):
+        tot += bytes_spmv(h.R[l], False) + bytes_spmv(h.P[l], False)
+    if k < h.num_levels - 1:
+        tot += (bytes_spmv(h.A[k], False) + 8 * h.n[k]) if symmetric else 24 * h.n[k]
+    tot += bytes_spmv(h.A[0], True) + 32 * h.n[0]
+    return tot

@@ -1,0 +1,599 @@
+// amg_host.cpp -- host-side INPUT PROVIDER for the B200 additive-AMG solve phase.
+//
+// The reference builds its hierarchy on the host with hypre-BoomerAMG
+// (/root/reference/src/SMEM_Setup.cpp:55-180) and hands per-level diag-first CSR
+// matrices A_l, P_l, R_l to the solve phase (SMEM_Setup.cpp:217-276).  hypre is an
+// un-vendored third-party dependency that is not present in this image, so this
+// file supplies the same *kind* of input with a self-contained classical AMG setup:
+//
+//   strength (theta)  ->  PMIS C/F splitting  ->  direct interpolation
+//   -> one Jacobi improvement step + truncation (P_max_elmts)  ->  Galerkin RAP
+//
+// plus restatements of the pieces of the reference's own setup that define the
+// hot path's input layout:
+//   * stencil generators  (src/Laplacian.cpp:3-69, src/BuildHypreMatrix.cpp:250-289)
+//   * RHS generator       (src/SMEM_Setup.cpp:1729-1742, src/Misc.cpp:282-285)
+//   * smoothed transfers  P̄ = G P, R̄ = Pᵀ GT   (src/SMEM_Setup.cpp:1173-1254)
+//   * diag-first, reverse-sorted row layout of products (src/SMEM_Setup.cpp:1382-1423)
+//
+// Everything here runs on the CPU (OpenMP) and is outside the accelerated path; it
+// exists so that tests and bench.py can build the 256^3 problem on the GPU box in
+// seconds.  C ABI, consumed from Python through ctypes (hierarchy.py).
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <vector>
+#include <omp.h>
+
+extern "C" {
+
+typedef struct {
+   int nrows, ncols, nnz;
+   int *i;        // [nrows+1]
+   int *j;        // [nnz]
+   double *data;  // [nnz]
+} amgh_csr;
+
+void amgh_csr_free(amgh_csr *m)
+{
+   if (!m) return;
+   free(m->i); free(m->j); free(m->data);
+   m->i = nullptr; m->j = nullptr; m->data = nullptr;
+   m->nrows = m->ncols = m->nnz = 0;
+}
+
+int amgh_max_threads(void) { return omp_get_max_threads(); }
+
+}  // extern "C"
+
+namespace {
+
+int g_threads() { return std::max(1, std::min(omp_get_max_threads(), 32)); }
+
+void csr_alloc(amgh_csr *m, int nrows, int ncols, int nnz)
+{
+   m->nrows = nrows; m->ncols = ncols; m->nnz = nnz;
+   m->i = (int *)malloc(sizeof(int) * ((size_t)nrows + 1));
+   m->j = (int *)malloc(sizeof(int) * (size_t)std::max(nnz, 1));
+   m->data = (double *)malloc(sizeof(double) * (size_t)std::max(nnz, 1));
+}
+
+// exclusive prefix sum of per-row counts into row pointer (counts in ptr[1..n])
+void prefix(int *ptr, int n)
+{
+   ptr[0] = 0;
+   for (int r = 0; r < n; r++) ptr[r + 1] += ptr[r];
+}
+
+// ---- generic row-wise Gustavson SpGEMM, C = A*B, rows sorted ascending ------------------
+void spgemm(const amgh_csr &A, const amgh_csr &B, amgh_csr *C)
+{
+   const int n = A.nrows, m = B.ncols;
+   int *ci = (int *)calloc((size_t)n + 1, sizeof(int));
+   const int T = g_threads();
+#pragma omp parallel num_threads(T)
+   {
+      std::vector<int> mark(m, -1);
+#pragma omp for schedule(dynamic, 1024)
+      for (int r = 0; r < n; r++) {
+         int cnt = 0;
+         for (int p = A.i[r]; p < A.i[r + 1]; p++) {
+            int k = A.j[p];
+            for (int q = B.i[k]; q < B.i[k + 1]; q++) {
+               int c = B.j[q];
+               if (mark[c] != r) { mark[c] = r; cnt++; }
+            }
+         }
+         ci[r + 1] = cnt;
+      }
+   }
+   prefix(ci, n);
+   C->nrows = n; C->ncols = m; C->nnz = ci[n];
+   C->i = ci;
+   C->j = (int *)malloc(sizeof(int) * (size_t)std::max(C->nnz, 1));
+   C->data = (double *)malloc(sizeof(double) * (size_t)std::max(C->nnz, 1));
+#pragma omp parallel num_threads(T)
+   {
+      std::vector<int> mark(m, -1);
+      std::vector<double> acc(m, 0.0);
+#pragma omp for schedule(dynamic, 1024)
+      for (int r = 0; r < n; r++) {
+         int base = ci[r], cnt = 0;
+         for (int p = A.i[r]; p < A.i[r + 1]; p++) {
+            int k = A.j[p];
+            double a = A.data[p];
+            for (int q = B.i[k]; q < B.i[k + 1]; q++) {
+               int c = B.j[q];
+               if (mark[c] != r) { mark[c] = r; acc[c] = a * B.data[q]; C->j[base + cnt++] = c; }
+               else acc[c] += a * B.data[q];
+            }
+         }
+         std::sort(C->j + base, C->j + base + cnt);
+         for (int t = 0; t < cnt; t++) C->data[base + t] = acc[C->j[base + t]];
+      }
+   }
+}
+
+void transpose(const amgh_csr &A, amgh_csr *AT)
+{
+   const int n = A.nrows, m = A.ncols;
+   csr_alloc(AT, m, n, A.nnz);
+   std::fill(AT->i, AT->i + m + 1, 0);
+   for (int p = 0; p < A.nnz; p++) AT->i[A.j[p] + 1]++;
+   prefix(AT->i, m);
+   std::vector<int> fill(AT->i, AT->i + m);
+   for (int r = 0; r < n; r++)
+      for (int p = A.i[r]; p < A.i[r + 1]; p++) {
+         int c = A.j[p];
+         int d = fill[c]++;
+         AT->j[d] = r;
+         AT->data[d] = A.data[p];
+      }
+}
+
+// put a_ii first in every row (rows otherwise keep their order)
+void diag_first(amgh_csr *A)
+{
+#pragma omp parallel for schedule(static)
+   for (int r = 0; r < A->nrows; r++) {
+      int s = A->i[r], e = A->i[r + 1];
+      for (int p = s; p < e; p++)
+         if (A->j[p] == r) {
+            int jt = A->j[p]; double dt = A->data[p];
+            for (int q = p; q > s; q--) { A->j[q] = A->j[q - 1]; A->data[q] = A->data[q - 1]; }
+            A->j[s] = jt; A->data[s] = dt;
+            break;
+         }
+   }
+}
+
+// Row layout the reference gives to every Eigen product (SMEM_Setup.cpp:1382-1423):
+// the sorted row is reversed (descending column), then the entry with column == row
+// is swapped into the first slot.
+void reference_product_layout(amgh_csr *A)
+{
+#pragma omp parallel for schedule(static)
+   for (int r = 0; r < A->nrows; r++) {
+      int s = A->i[r], e = A->i[r + 1];
+      std::reverse(A->j + s, A->j + e);
+      std::reverse(A->data + s, A->data + e);
+      for (int p = s; p < e; p++)
+         if (A->j[p] == r) {
+            std::swap(A->j[s], A->j[p]);
+            std::swap(A->data[s], A->data[p]);
+            break;
+         }
+   }
+}
+
+inline uint32_t hash32(uint32_t x)
+{
+   x = ((x >> 16) ^ x) * 0x45d9f3bu;
+   x = ((x >> 16) ^ x) * 0x45d9f3bu;
+   x = (x >> 16) ^ x;
+   return x;
+}
+
+// classical strength of connection: j strongly influences i iff
+// -a_ij >= theta * max_k(-a_ik), k != i.   Returns S with the pattern only (data = a_ij).
+void strength(const amgh_csr &A, double theta, amgh_csr *S)
+{
+   const int n = A.nrows;
+   int *si = (int *)calloc((size_t)n + 1, sizeof(int));
+#pragma omp parallel for schedule(static)
+   for (int r = 0; r < n; r++) {
+      double mx = 0.0;
+      for (int p = A.i[r]; p < A.i[r + 1]; p++)
+         if (A.j[p] != r) mx = std::max(mx, -A.data[p]);
+      int cnt = 0;
+      if (mx > 0.0)
+         for (int p = A.i[r]; p < A.i[r + 1]; p++)
+            if (A.j[p] != r && -A.data[p] >= theta * mx) cnt++;
+      si[r + 1] = cnt;
+   }
+   prefix(si, n);
+   S->nrows = n; S->ncols = n; S->nnz = si[n]; S->i = si;
+   S->j = (int *)malloc(sizeof(int) * (size_t)std::max(S->nnz, 1));
+   S->data = (double *)malloc(sizeof(double) * (size_t)std::max(S->nnz, 1));
+#pragma omp parallel for schedule(static)
+   for (int r = 0; r < n; r++) {
+      double mx = 0.0;
+      for (int p = A.i[r]; p < A.i[r + 1]; p++)
+         if (A.j[p] != r) mx = std::max(mx, -A.data[p]);
+      int d = si[r];
+      if (mx > 0.0)
+         for (int p = A.i[r]; p < A.i[r + 1]; p++)
+            if (A.j[p] != r && -A.data[p] >= theta * mx) { S->j[d] = A.j[p]; S->data[d] = A.data[p]; d++; }
+   }
+}
+
+// PMIS splitting (De Sterck, Yang, Heys 2006).  cf[i] = 1 (C), -1 (F).
+void pmis(const amgh_csr &S, std::vector<int> &cf)
+{
+   const int n = S.nrows;
+   amgh_csr ST; transpose(S, &ST);
+   std::vector<double> w(n);
+   cf.assign(n, 0);
+#pragma omp parallel for schedule(static)
+   for (int r = 0; r < n; r++) {
+      w[r] = (double)(ST.i[r + 1] - ST.i[r]) + (double)hash32((uint32_t)r) / 4294967296.0;
+      if (S.i[r + 1] == S.i[r] && ST.i[r + 1] == ST.i[r]) cf[r] = -1;   // isolated point
+      else if (ST.i[r + 1] == ST.i[r]) cf[r] = -1;                       // influences nobody: F
+   }
+   // a point that influences nobody but has no strong C neighbour later is fixed up below
+   std::vector<int> newc(n);
+   long undecided = 1;
+   while (undecided) {
+#pragma omp parallel for schedule(static)
+      for (int r = 0; r < n; r++) {
+         newc[r] = 0;
+         if (cf[r] != 0) continue;
+         bool top = true;
+         for (int p = S.i[r]; p < S.i[r + 1] && top; p++) { int c = S.j[p]; if (cf[c] == 0 && w[c] >= w[r]) top = false; }
+         for (int p = ST.i[r]; p < ST.i[r + 1] && top; p++) { int c = ST.j[p]; if (cf[c] == 0 && w[c] >= w[r]) top = false; }
+         if (top) newc[r] = 1;
+      }
+#pragma omp parallel for schedule(static)
+      for (int r = 0; r < n; r++) if (newc[r]) cf[r] = 1;
+      undecided = 0;
+#pragma omp parallel for schedule(static) reduction(+ : undecided)
+      for (int r = 0; r < n; r++) {
+         if (cf[r] != 0) continue;
+         bool hasC = false;
+         for (int p = S.i[r]; p < S.i[r + 1]; p++) if (cf[S.j[p]] == 1) { hasC = true; break; }
+         if (hasC) cf[r] = -1; else undecided++;
+      }
+   }
+   // F points without any strong C neighbour (only possible for the pre-marked ones): promote to C
+#pragma omp parallel for schedule(static)
+   for (int r = 0; r < n; r++) {
+      if (cf[r] != -1) continue;
+      if (S.i[r + 1] == S.i[r]) continue;   // no strong connections: stays F with empty row
+      bool hasC = false;
+      for (int p = S.i[r]; p < S.i[r + 1]; p++) if (cf[S.j[p]] == 1) { hasC = true; break; }
+      if (!hasC) newc[r] = 2; else newc[r] = 0;
+   }
+   for (int r = 0; r < n; r++) if (cf[r] == -1 && newc[r] == 2 && S.i[r + 1] != S.i[r]) cf[r] = 1;
+   amgh_csr_free(&ST);
+}
+
+// direct interpolation on strong C neighbours (Stueben), sign-separated.
+void direct_interp(const amgh_csr &A, const amgh_csr &S, const std::vector<int> &cf,
+                   const std::vector<int> &cidx, int nc, amgh_csr *P)
+{
+   const int n = A.nrows;
+   int *pi = (int *)calloc((size_t)n + 1, sizeof(int));
+#pragma omp parallel for schedule(static)
+   for (int r = 0; r < n; r++) {
+      if (cf[r] == 1) { pi[r + 1] = 1; continue; }
+      int cnt = 0;
+      for (int p = S.i[r]; p < S.i[r + 1]; p++) if (cf[S.j[p]] == 1) cnt++;
+      pi[r + 1] = cnt;
+   }
+   prefix(pi, n);
+   P->nrows = n; P->ncols = nc; P->nnz = pi[n]; P->i = pi;
+   P->j = (int *)malloc(sizeof(int) * (size_t)std::max(P->nnz, 1));
+   P->data = (double *)malloc(sizeof(double) * (size_t)std::max(P->nnz, 1));
+#pragma omp parallel for schedule(static)
+   for (int r = 0; r < n; r++) {
+      int d = pi[r];
+      if (cf[r] == 1) { P->j[d] = cidx[r]; P->data[d] = 1.0; continue; }
+      double diag = 0, neg_all = 0, pos_all = 0, neg_c = 0, pos_c = 0;
+      for (int p = A.i[r]; p < A.i[r + 1]; p++) {
+         if (A.j[p] == r) diag += A.data[p];
+         else if (A.data[p] < 0) neg_all += A.data[p];
+         else pos_all += A.data[p];
+      }
+      for (int p = S.i[r]; p < S.i[r + 1]; p++)
+         if (cf[S.j[p]] == 1) { if (S.data[p] < 0) neg_c += S.data[p]; else pos_c += S.data[p]; }
+      double alpha = neg_c != 0 ? neg_all / neg_c : 0.0;
+      double beta = pos_c != 0 ? pos_all / pos_c : 0.0;
+      if (pos_c == 0) diag += pos_all;
+      for (int p = S.i[r]; p < S.i[r + 1]; p++)
+         if (cf[S.j[p]] == 1) {
+            double a = S.data[p];
+            P->j[d] = cidx[S.j[p]];
+            P->data[d] = -(a < 0 ? alpha : beta) * a / diag;
+            d++;
+         }
+   }
+}
+
+// keep the pmax largest-magnitude entries of every row, rescale to preserve the row sum
+void truncate_rows(amgh_csr *P, int pmax)
+{
+   if (pmax <= 0) return;
+   const int n = P->nrows;
+   int *ni = (int *)calloc((size_t)n + 1, sizeof(int));
+   for (int r = 0; r < n; r++) ni[r + 1] = std::min(pmax, P->i[r + 1] - P->i[r]);
+   prefix(ni, n);
+   int *nj = (int *)malloc(sizeof(int) * (size_t)std::max(ni[n], 1));
+   double *nd = (double *)malloc(sizeof(double) * (size_t)std::max(ni[n], 1));
+#pragma omp parallel
+   {
+      std::vector<int> ord;
+#pragma omp for schedule(static)
+      for (int r = 0; r < n; r++) {
+         int s = P->i[r], len = P->i[r + 1] - s, keep = ni[r + 1] - ni[r];
+         int d = ni[r];
+         if (keep == len) {
+            for (int t = 0; t < len; t++) { nj[d + t] = P->j[s + t]; nd[d + t] = P->data[s + t]; }
+            continue;
+         }
+         ord.resize(len);
+         std::iota(ord.begin(), ord.end(), 0);
+         // deterministic: larger |v| first, ties by smaller column
+         std::sort(ord.begin(), ord.end(), [&](int a, int b) {
+            double va = std::fabs(P->data[s + a]), vb = std::fabs(P->data[s + b]);
+            if (va != vb) return va > vb;
+            return P->j[s + a] < P->j[s + b];
+         });
+         double all = 0, kept = 0;
+         for (int t = 0; t < len; t++) all += P->data[s + t];
+         std::sort(ord.begin(), ord.begin() + keep, [&](int a, int b) { return P->j[s + a] < P->j[s + b]; });
+         for (int t = 0; t < keep; t++) kept += P->data[s + ord[t]];
+         double sc = kept != 0 ? all / kept : 1.0;
+         for (int t = 0; t < keep; t++) { nj[d + t] = P->j[s + ord[t]]; nd[d + t] = P->data[s + ord[t]] * sc; }
+      }
+   }
+   free(P->i); free(P->j); free(P->data);
+   P->i = ni; P->j = nj; P->data = nd; P->nnz = ni[n];
+}
+
+struct Hierarchy {
+   std::vector<amgh_csr> A;   // diag-first
+   std::vector<amgh_csr> P;   // n_l x n_{l+1}, sorted rows
+};
+
+}  // namespace
+
+extern "C" {
+
+// ---- stencil generators (diag first, then ascending columns) ---------------------------------
+// 2-D 5-point: diag 4, off -1, natural ordering  (src/Laplacian.cpp:30-64)
+int amgh_laplacian_5pt(int n, amgh_csr *out)
+{
+   const int N = n * n;
+   std::vector<int> cnt((size_t)N + 1, 0);
+   for (int r = 0; r < N; r++) {
+      int c = 1;
+      if (r - n >= 0) c++;
+      if (r % n) c++;
+      if ((r + 1) % n) c++;
+      if (r + n < N) c++;
+      cnt[r + 1] = c;
+   }
+   for (int r = 0; r < N; r++) cnt[r + 1] += cnt[r];
+   csr_alloc(out, N, N, cnt[N]);
+   memcpy(out->i, cnt.data(), sizeof(int) * ((size_t)N + 1));
+#pragma omp parallel for schedule(static)
+   for (int r = 0; r < N; r++) {
+      int d = out->i[r];
+      out->j[d] = r; out->data[d++] = 4.0;
+      if (r - n >= 0) { out->j[d] = r - n; out->data[d++] = -1.0; }
+      if (r % n) { out->j[d] = r - 1; out->data[d++] = -1.0; }
+      if ((r + 1) % n) { out->j[d] = r + 1; out->data[d++] = -1.0; }
+      if (r + n < N) { out->j[d] = r + n; out->data[d++] = -1.0; }
+   }
+   return 0;
+}
+
+// 3-D 7-point: diag 2cx+2cy+2cz (=6), off -1  (src/BuildHypreMatrix.cpp:250-269, "7pt": c=1, a=0)
+int amgh_laplacian_7pt(int nx, int ny, int nz, amgh_csr *out)
+{
+   const long N = (long)nx * ny * nz;
+   if (N * 7 > 2147483000L) return 1;
+   std::vector<int> ptr((size_t)N + 1);
+   ptr[0] = 0;
+   for (int z = 0; z < nz; z++)
+      for (int y = 0; y < ny; y++)
+         for (int x = 0; x < nx; x++) {
+            long r = x + (long)nx * (y + (long)ny * z);
+            int c = 1 + (x > 0) + (x < nx - 1) + (y > 0) + (y < ny - 1) + (z > 0) + (z < nz - 1);
+            ptr[r + 1] = c;
+         }
+   for (long r = 0; r < N; r++) ptr[r + 1] += ptr[r];
+   csr_alloc(out, (int)N, (int)N, ptr[N]);
+   memcpy(out->i, ptr.data(), sizeof(int) * ((size_t)N + 1));
+   double diag = 0.0;
+   if (nx > 1) diag += 2.0;
+   if (ny > 1) diag += 2.0;
+   if (nz > 1) diag += 2.0;
+#pragma omp parallel for collapse(2) schedule(static)
+   for (int z = 0; z < nz; z++)
+      for (int y = 0; y < ny; y++)
+         for (int x = 0; x < nx; x++) {
+            int r = x + nx * (y + ny * z);
+            int d = out->i[r];
+            out->j[d] = r; out->data[d++] = diag;
+            if (z > 0) { out->j[d] = r - nx * ny; out->data[d++] = -1.0; }
+            if (y > 0) { out->j[d] = r - nx; out->data[d++] = -1.0; }
+            if (x > 0) { out->j[d] = r - 1; out->data[d++] = -1.0; }
+            if (x < nx - 1) { out->j[d] = r + 1; out->data[d++] = -1.0; }
+            if (y < ny - 1) { out->j[d] = r + nx; out->data[d++] = -1.0; }
+            if (z < nz - 1) { out->j[d] = r + nx * ny; out->data[d++] = -1.0; }
+         }
+   return 0;
+}
+
+// 3-D 27-point: diag 26 (8 / 2 for degenerate dims), off -1  (src/BuildHypreMatrix.cpp:277-286)
+int amgh_laplacian_27pt(int nx, int ny, int nz, amgh_csr *out)
+{
+   const long N = (long)nx * ny * nz;
+   std::vector<int> ptr((size_t)N + 1);
+   ptr[0] = 0;
+   long tot = 0;
+   for (int z = 0; z < nz; z++)
+      for (int y = 0; y < ny; y++)
+         for (int x = 0; x < nx; x++) {
+            long r = x + (long)nx * (y + (long)ny * z);
+            int cx = 1 + (x > 0) + (x < nx - 1), cy = 1 + (y > 0) + (y < ny - 1), cz = 1 + (z > 0) + (z < nz - 1);
+            ptr[r + 1] = cx * cy * cz;
+            tot += cx * cy * cz;
+         }
+   if (tot > 2147483000L) return 1;
+   for (long r = 0; r < N; r++) ptr[r + 1] += ptr[r];
+   csr_alloc(out, (int)N, (int)N, ptr[N]);
+   memcpy(out->i, ptr.data(), sizeof(int) * ((size_t)N + 1));
+   double diag = 26.0;
+   if (nx == 1 || ny == 1 || nz == 1) diag = 8.0;
+   if (nx * ny == 1 || nx * nz == 1 || ny * nz == 1) diag = 2.0;
+#pragma omp parallel for collapse(2) schedule(static)
+   for (int z = 0; z < nz; z++)
+      for (int y = 0; y < ny; y++)
+         for (int x = 0; x < nx; x++) {
+            int r = x + nx * (y + ny * z);
+            int d = out->i[r];
+            out->j[d] = r; out->data[d++] = diag;
+            for (int dz = -1; dz <= 1; dz++) {
+               if (z + dz < 0 || z + dz >= nz) continue;
+               for (int dy = -1; dy <= 1; dy++) {
+                  if (y + dy < 0 || y + dy >= ny) continue;
+                  for (int dx = -1; dx <= 1; dx++) {
+                     if (x + dx < 0 || x + dx >= nx) continue;
+                     if (!dx && !dy && !dz) continue;
+                     out->j[d] = r + dx + nx * (dy + ny * dz);
+                     out->data[d++] = -1.0;
+                  }
+               }
+            }
+         }
+   return 0;
+}
+
+// b_i = lo + (hi-lo) * rand()/RAND_MAX after srand(seed), i ascending
+// (RandDouble src/Misc.cpp:282-285; SMEM RHS src/SMEM_Setup.cpp:1729-1742).  Uses the C
+// library's own rand() so the sequence is the one the reference would draw on this box.
+void amgh_rand_fill(double *b, long n, double lo, double hi, unsigned seed)
+{
+   srand(seed);
+   for (long k = 0; k < n; k++) b[k] = lo + (hi - lo) * ((double)rand() / RAND_MAX);
+}
+
+int amgh_transpose(const amgh_csr *A, amgh_csr *AT) { transpose(*A, AT); return 0; }
+int amgh_spgemm(const amgh_csr *A, const amgh_csr *B, amgh_csr *C) { spgemm(*A, *B, C); return 0; }
+int amgh_diag_first(amgh_csr *A) { diag_first(A); return 0; }
+
+// ---- hierarchy --------------------------------------------------------------------------------
+void *amgh_setup(const amgh_csr *A0, double theta, int max_levels, int max_coarse, int pmax,
+                 int jacobi_interp_steps, int verbose)
+{
+   Hierarchy *H = new Hierarchy();
+   amgh_csr A;
+   csr_alloc(&A, A0->nrows, A0->ncols, A0->nnz);
+   memcpy(A.i, A0->i, sizeof(int) * ((size_t)A0->nrows + 1));
+   memcpy(A.j, A0->j, sizeof(int) * (size_t)A0->nnz);
+   memcpy(A.data, A0->data, sizeof(double) * (size_t)A0->nnz);
+   diag_first(&A);
+   H->A.push_back(A);
+   while ((int)H->A.size() < max_levels && H->A.back().nrows > max_coarse) {
+      const amgh_csr &Af = H->A.back();
+      const int n = Af.nrows;
+      double t0 = omp_get_wtime();
+      amgh_csr S; strength(Af, theta, &S);
+      std::vector<int> cf; pmis(S, cf);
+      std::vector<int> cidx(n, -1);
+      int nc = 0;
+      for (int r = 0; r < n; r++) if (cf[r] == 1) cidx[r] = nc++;
+      if (nc == 0 || nc == n) { amgh_csr_free(&S); break; }
+      amgh_csr P; direct_interp(Af, S, cf, cidx, nc, &P);
+      amgh_csr_free(&S);
+      for (int it = 0; it < jacobi_interp_steps; it++) {
+         // P <- M P with M = -D^{-1}(A-D) on F rows, identity on C rows
+         amgh_csr M;
+         csr_alloc(&M, n, n, Af.nnz);
+         int *mi = M.i; mi[0] = 0;
+         for (int r = 0; r < n; r++) mi[r + 1] = mi[r] + (cf[r] == 1 ? 1 : (Af.i[r + 1] - Af.i[r] - 1));
+         M.nnz = mi[n];
+#pragma omp parallel for schedule(static)
+         for (int r = 0; r < n; r++) {
+            int d = mi[r];
+            if (cf[r] == 1) { M.j[d] = r; M.data[d] = 1.0; continue; }
+            double diag = Af.data[Af.i[r]];
+            for (int p = Af.i[r] + 1; p < Af.i[r + 1]; p++) { M.j[d] = Af.j[p]; M.data[d] = -Af.data[p] / diag; d++; }
+         }
+         amgh_csr P1; spgemm(M, P, &P1);
+         amgh_csr_free(&M); amgh_csr_free(&P);
+         truncate_rows(&P1, pmax);
+         P = P1;
+      }
+      amgh_csr R, AP, Ac;
+      transpose(P, &R);
+      spgemm(Af, P, &AP);
+      spgemm(R, AP, &Ac);
+      amgh_csr_free(&R); amgh_csr_free(&AP);
+      diag_first(&Ac);
+      if (verbose)
+         printf("[amgh_setup] level %d: n=%d nnz=%d -> nc=%d nnz(P)=%d nnz(Ac)=%d  (%.2fs)\n",
+                (int)H->A.size() - 1, n, Af.nnz, nc, P.nnz, Ac.nnz, omp_get_wtime() - t0);
+      H->P.push_back(P);
+      H->A.push_back(Ac);
+   }
+   return H;
+}
+
+int amgh_num_levels(void *h) { return (int)((Hierarchy *)h)->A.size(); }
+const amgh_csr *amgh_level_A(void *h, int l) { return &((Hierarchy *)h)->A[l]; }
+const amgh_csr *amgh_level_P(void *h, int l) { return &((Hierarchy *)h)->P[l]; }
+void amgh_destroy(void *h)
+{
+   Hierarchy *H = (Hierarchy *)h;
+   for (auto &m : H->A) amgh_csr_free(&m);
+   for (auto &m : H->P) amgh_csr_free(&m);
+   delete H;
+}
+
+// Smoothed transfers (src/SMEM_Setup.cpp:1173-1254).  kind 0: weighted Jacobi
+//   G_ii = 1-w, G_ij = -w a_ij/d_i ;  GT_ij = -w a_ij/d_j
+// kind 1: L1   G_ii = 1 - a_ii/l1_i, G_ij = -a_ij/l1_i ; GT_ij = -a_ij/l1_j
+// want_P: Pbar = G*P (else not produced); want_R: Rbar = P^T*GT.  A must be diag-first.
+int amgh_smooth_transfer(const amgh_csr *A, const amgh_csr *P, int kind, double w,
+                         int want_P, int want_R, amgh_csr *Pbar, amgh_csr *Rbar)
+{
+   const int n = A->nrows;
+   std::vector<double> s(n);
+   for (int r = 0; r < n; r++) {
+      if (kind == 0) s[r] = A->data[A->i[r]];
+      else { double l1 = 0; for (int p = A->i[r]; p < A->i[r + 1]; p++) l1 += std::fabs(A->data[p]); s[r] = l1; }
+   }
+   amgh_csr G;
+   csr_alloc(&G, n, n, A->nnz);
+   memcpy(G.i, A->i, sizeof(int) * ((size_t)n + 1));
+   memcpy(G.j, A->j, sizeof(int) * (size_t)A->nnz);
+   if (want_P) {
+#pragma omp parallel for schedule(static)
+      for (int r = 0; r < n; r++) {
+         int d = A->i[r];
+         G.data[d] = kind == 0 ? 1.0 - w : 1.0 - A->data[d] / s[r];
+         for (int p = d + 1; p < A->i[r + 1]; p++)
+            G.data[p] = kind == 0 ? -w * A->data[p] / s[r] : -A->data[p] / s[r];
+      }
+      spgemm(G, *P, Pbar);
+      reference_product_layout(Pbar);
+   }
+   if (want_R) {
+#pragma omp parallel for schedule(static)
+      for (int r = 0; r < n; r++) {
+         int d = A->i[r];
+         G.data[d] = kind == 0 ? 1.0 - w : 1.0 - A->data[d] / s[r];
+         for (int p = d + 1; p < A->i[r + 1]; p++)
+            G.data[p] = kind == 0 ? -w * A->data[p] / s[A->j[p]] : -A->data[p] / s[A->j[p]];
+      }
+      amgh_csr PT; transpose(*P, &PT);
+      spgemm(PT, G, Rbar);
+      reference_product_layout(Rbar);
+      amgh_csr_free(&PT);
+   }
+   amgh_csr_free(&G);
+   return 0;
+}
+
+// plain R = P^T in the reference's layout (hypre_CSRMatrixTranspose keeps ascending rows)
+int amgh_restriction_from_P(const amgh_csr *P, amgh_csr *R) { transpose(*P, R); return 0; }
+
+}  // extern "C"

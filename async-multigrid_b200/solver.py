@@ -1,0 +1,233 @@
+"""Host-side mirror of the reference's solve-phase interface on top of the C ABI
+(include/amg_b200.h, libamg_b200.so).  Python only marshals pointers; all arithmetic runs in
+the sm_100a kernels.  There is no CPU fallback: constructing a solver without a CUDA device
+(or without the built extension) raises.
+
+Names follow the reference: SMEM_Solve, SMEM_Sync_Add_Vcycle (-> cycle), SMEM_Async_Add_AMG,
+SMEM_MatVec/SMEM_Residual (-> spgemv), SMEM_Smooth (-> smooth)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+from . import hierarchy as H
+
+DP = C.POINTER(C.c_double)
+IP = C.POINTER(C.c_int)
+
+MAT_A, MAT_P, MAT_R = 0, 1, 2
+CONVERGE_LOCAL, CONVERGE_GLOBAL = 0, 1
+
+ABI_SYMBOLS = [
+    "amgb_default_options", "amgb_create", "amgb_destroy", "amgb_last_error", "amgb_launch_count",
+    "amgb_set_num_levels", "amgb_set_matrix", "amgb_set_options", "amgb_setup",
+    "amgb_set_rhs", "amgb_set_solution", "amgb_get_solution", "amgb_get_residual",
+    "amgb_spgemv", "amgb_smooth", "amgb_norm2", "amgb_cycle", "amgb_solve_sync", "amgb_solve_async",
+    "amgb_smem_solve", "amgb_time_residual", "amgb_level_storage",
+    "amgb_dist_unique_id", "amgb_dist_init", "amgb_dist_set_partition", "amgb_dist_solve_sync",
+]
+
+
+class Options(C.Structure):
+    _fields_ = [("solver", C.c_int), ("smoother", C.c_int), ("smooth_weight", C.c_double),
+                ("num_pre_smooth_sweeps", C.c_int), ("num_post_smooth_sweeps", C.c_int),
+                ("num_fine_smooth_sweeps", C.c_int), ("num_coarse_smooth_sweeps", C.c_int),
+                ("jgs_block_rows", C.c_int), ("use_sell", C.c_int), ("l2_persist", C.c_int)]
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen libamg_b200.so (building it in-tree if the sources are newer)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.CUDA_LIB
+    if not os.path.exists(path):
+        _build.build_cuda()
+    L = C.CDLL(path)
+    L.amgb_last_error.restype = C.c_char_p
+    L.amgb_last_error.argtypes = [C.c_void_p]
+    L.amgb_launch_count.restype = C.c_longlong
+    L.amgb_launch_count.argtypes = [C.c_void_p]
+    L.amgb_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+    L.amgb_destroy.argtypes = [C.c_void_p]
+    L.amgb_default_options.argtypes = [C.POINTER(Options)]
+    L.amgb_default_options.restype = None
+    L.amgb_set_num_levels.argtypes = [C.c_void_p, C.c_int]
+    L.amgb_set_matrix.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, IP, IP, DP]
+    L.amgb_set_options.argtypes = [C.c_void_p, C.POINTER(Options)]
+    L.amgb_setup.argtypes = [C.c_void_p]
+    L.amgb_set_rhs.argtypes = [C.c_void_p, DP]
+    L.amgb_set_solution.argtypes = [C.c_void_p, DP]
+    L.amgb_get_solution.argtypes = [C.c_void_p, DP]
+    L.amgb_get_residual.argtypes = [C.c_void_p, DP]
+    L.amgb_spgemv.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, DP, C.c_double, DP, DP]
+    L.amgb_smooth.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, DP, DP]
+    L.amgb_norm2.argtypes = [C.c_void_p, DP, C.c_int, DP]
+    L.amgb_cycle.argtypes = [C.c_void_p, DP, DP]
+    L.amgb_solve_sync.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, DP, IP, DP]
+    L.amgb_solve_async.argtypes = [C.c_void_p, C.c_int, C.c_int, IP, DP, DP]
+    L.amgb_smem_solve.argtypes = [C.c_void_p, DP, DP, C.c_double, C.c_int, DP, IP, IP, DP, DP]
+    L.amgb_time_residual.argtypes = [C.c_void_p, C.c_int, DP]
+    L.amgb_level_storage.argtypes = [C.c_void_p, C.c_int, C.c_int, IP]
+    L.amgb_async_groups.argtypes = [C.c_void_p, IP, IP]
+    _lib = L
+    return L
+
+
+def _dp(a):
+    return a.ctypes.data_as(DP)
+
+
+def _ip(a):
+    return a.ctypes.data_as(IP)
+
+
+class AmgError(RuntimeError):
+    pass
+
+
+class Solver:
+    """One hierarchy resident on one B200.  `h` is a hierarchy.Hierarchy whose transfers were
+    built for `solver` (build_transfers)."""
+
+    def __init__(self, h, solver=H.MULTADD, smoother=H.JACOBI, smooth_weight=1.0, num_pre=1, num_post=1,
+                 fine_sweeps=1, coarse_sweeps=1, jgs_block_rows=8, use_sell=True, l2_persist=True, device=0):
+        self.L = load_library()
+        self.h = h
+        self.ctx = C.c_void_p()
+        rc = self.L.amgb_create(C.byref(self.ctx), device)
+        if rc != 0:
+            raise AmgError("amgb_create failed (%d): no CUDA device / driver -- there is no CPU fallback" % rc)
+        o = Options()
+        self.L.amgb_default_options(C.byref(o))
+        o.solver, o.smoother, o.smooth_weight = solver, smoother, smooth_weight
+        o.num_pre_smooth_sweeps, o.num_post_smooth_sweeps = num_pre, num_post
+        o.num_fine_smooth_sweeps, o.num_coarse_smooth_sweeps = fine_sweeps, coarse_sweeps
+        o.jgs_block_rows, o.use_sell, o.l2_persist = jgs_block_rows, int(use_sell), int(l2_persist)
+        self.options = o
+        self._ck(self.L.amgb_set_options(self.ctx, C.byref(o)))
+        self._ck(self.L.amgb_set_num_levels(self.ctx, h.num_levels))
+        for l in range(h.num_levels):
+            self._set(MAT_A, l, h.A[l])
+            if l < h.num_levels - 1:
+                self._set(MAT_P, l, h.P[l])
+                self._set(MAT_R, l, h.R[l])
+        self._ck(self.L.amgb_setup(self.ctx))
+        self.n0 = h.n[0]
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise AmgError("amg_b200 error %d: %s" % (rc, self.L.amgb_last_error(self.ctx).decode()))
+
+    def _set(self, kind, l, m):
+        self._ck(self.L.amgb_set_matrix(self.ctx, kind, l, m.nrows, m.ncols, m.nnz, _ip(m.indptr), _ip(m.indices), _dp(m.data)))
+
+    def close(self):
+        if self.ctx:
+            self.L.amgb_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- vectors -------------------------------------------------------------------------------
+    def set_rhs(self, f):
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        assert f.shape[0] == self.n0
+        self._ck(self.L.amgb_set_rhs(self.ctx, _dp(f)))
+
+    def set_solution(self, u=None):
+        if u is None:
+            self._ck(self.L.amgb_set_solution(self.ctx, None))
+        else:
+            u = np.ascontiguousarray(u, dtype=np.float64)
+            self._ck(self.L.amgb_set_solution(self.ctx, _dp(u)))
+
+    def get_solution(self):
+        u = np.empty(self.n0)
+        self._ck(self.L.amgb_get_solution(self.ctx, _dp(u)))
+        return u
+
+    # -- per-op ----------------------------------------------------------------------------------
+    def spgemv(self, kind, level, alpha, x, beta=0.0, b=None):
+        m = (self.h.A, self.h.P, self.h.R)[kind][level]
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty(m.nrows)
+        bb = None if b is None else np.ascontiguousarray(b, dtype=np.float64)
+        self._ck(self.L.amgb_spgemv(self.ctx, kind, level, alpha, _dp(x), beta, None if bb is None else _dp(bb), _dp(y)))
+        return y
+
+    def smooth(self, level, f, sweeps=1, symmetric=False, zero_guess=True, u0=None):
+        n = self.h.n[level]
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        u = np.zeros(n) if u0 is None else np.array(u0, dtype=np.float64)
+        self._ck(self.L.amgb_smooth(self.ctx, level, self.options.smoother, int(symmetric), sweeps, int(zero_guess), _dp(f), _dp(u)))
+        return u
+
+    def norm2(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = C.c_double(0)
+        self._ck(self.L.amgb_norm2(self.ctx, _dp(x), len(x), C.byref(out)))
+        return out.value
+
+    # -- cycles / solves ---------------------------------------------------------------------------
+    def cycle(self, r):
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        c = np.empty(self.n0)
+        self._ck(self.L.amgb_cycle(self.ctx, _dp(r), _dp(c)))
+        return c
+
+    def solve_sync(self, tol=1e-9, max_cycles=100, cheby=None):
+        """resident f,u -> (relres history, seconds)"""
+        hist = np.zeros(max_cycles + 1)
+        n = C.c_int(0)
+        secs = C.c_double(0)
+        mu, delta = cheby if cheby else (1.0, 1.0)
+        self._ck(self.L.amgb_solve_sync(self.ctx, tol, max_cycles, 1 if cheby else 0, mu, delta, _dp(hist), C.byref(n), C.byref(secs)))
+        return hist[:n.value + 1], secs.value
+
+    def solve_async(self, num_cycles, converge=CONVERGE_LOCAL):
+        corr = np.zeros(self.h.num_levels, dtype=np.int32)
+        rel, secs = C.c_double(0), C.c_double(0)
+        self._ck(self.L.amgb_solve_async(self.ctx, num_cycles, converge, _ip(corr), C.byref(rel), C.byref(secs)))
+        return corr, rel.value, secs.value
+
+    def SMEM_Solve(self, f_host, tol=1e-9, num_cycles=100):
+        """Drop-in for one SMEM_Solve call with host buffers (src/SMEM_Main.cpp:694-757):
+        returns dict(u, hist, cycles, corrections, relres, seconds)."""
+        f = np.ascontiguousarray(f_host, dtype=np.float64)
+        u = np.empty(self.n0)
+        hist = np.zeros(num_cycles + 1)
+        n = C.c_int(0)
+        corr = np.zeros(self.h.num_levels, dtype=np.int32)
+        rel, secs = C.c_double(0), C.c_double(0)
+        self._ck(self.L.amgb_smem_solve(self.ctx, _dp(f), _dp(u), tol, num_cycles, _dp(hist), C.byref(n), _ip(corr),
+                                        C.byref(rel), C.byref(secs)))
+        return dict(u=u, hist=hist[:n.value + 1], cycles=n.value, corrections=corr, relres=rel.value, seconds=secs.value)
+
+    # -- introspection --------------------------------------------------------------------------------
+    def launch_count(self):
+        return int(self.L.amgb_launch_count(self.ctx))
+
+    def time_residual(self, reps=20):
+        ms = C.c_double(0)
+        self._ck(self.L.amgb_time_residual(self.ctx, reps, C.byref(ms)))
+        return ms.value
+
+    def is_sell(self, kind, level):
+        v = C.c_int(0)
+        self._ck(self.L.amgb_level_storage(self.ctx, kind, level, C.byref(v)))
+        return bool(v.value)
+
+    def async_groups(self):
+        cb = np.zeros(self.h.num_levels + 1, dtype=np.int32)
+        g = C.c_int(0)
+        self._ck(self.L.amgb_async_groups(self.ctx, _ip(cb), C.byref(g)))
+        return cb, g.value

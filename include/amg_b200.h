@@ -1,0 +1,140 @@
+/* amg_b200.h -- C ABI of the B200-native solve phase for async-multigrid's additive AMG cycles.
+ *
+ * The reference has no plugin/FFI API; its solve-phase boundary is a set of free C++ functions
+ * called SPMD from inside one OpenMP parallel region.  A GPU backend cannot sit at
+ * the per-thread kernel signature, so the seam is one level up: per cycle and per solve, called
+ * from a single host thread.  Every entry point below names the reference interface it replaces.
+ *
+ * Conventions: plain pointers and sizes only; all matrices are CSR with int32 indices and fp64
+ * values, A_l diag-first (the reference's assumption, src/SMEM_Smooth.cpp:385-386); host pointers
+ * unless a name ends in _dev; every function returns 0 on success and a negative AMGB_E* code
+ * otherwise (never exit()s, unlike src/SMEM_Setup.cpp:1613-1615); amgb_last_error() gives text.
+ * There is no CPU fallback: if no sm_100-class device / driver is present amgb_create fails.
+ */
+#ifndef AMG_B200_H
+#define AMG_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct amgb_ctx amgb_ctx;
+
+enum {
+   AMGB_OK = 0,
+   AMGB_EINVAL = -1,   /* bad argument / call order */
+   AMGB_ECUDA = -2,    /* CUDA runtime error (text in amgb_last_error) */
+   AMGB_ENOMEM = -3,
+   AMGB_ENCCL = -4,
+   AMGB_ESTATE = -5    /* hierarchy incomplete / setup not called */
+};
+
+/* enumerators keep the reference's numeric values (src/Main.hpp:47-75) */
+enum { AMGB_SMOOTH_JACOBI = 0, AMGB_SMOOTH_HYBRID_JGS = 2, AMGB_SMOOTH_L1_JACOBI = 6 };
+enum { AMGB_SOLVER_MULT = 0, AMGB_SOLVER_AFACX = 1, AMGB_SOLVER_MULTADD = 2, AMGB_SOLVER_BPX = 3,
+       AMGB_SOLVER_ASYNC_AFACX = 5, AMGB_SOLVER_ASYNC_MULTADD = 6 };
+enum { AMGB_CONVERGE_LOCAL = 0, AMGB_CONVERGE_GLOBAL = 1 };       /* src/Main.hpp LOCAL/GLOBAL */
+enum { AMGB_MAT_A = 0, AMGB_MAT_P = 1, AMGB_MAT_R = 2 };
+
+/* InputData fields the solve phase reads (src/Main.hpp:187-235; defaults src/SMEM_Main.cpp:64-104) */
+typedef struct {
+   int solver;                  /* AMGB_SOLVER_*                                   (-solver)            */
+   int smoother;                /* AMGB_SMOOTH_*                                   (-smoother)          */
+   double smooth_weight;        /* omega                                           (-smooth_weight)     */
+   int num_pre_smooth_sweeps;   /* >0 with post>0 selects the symmetrised smoother (src/SMEM_Solve.cpp:305-317) */
+   int num_post_smooth_sweeps;
+   int num_fine_smooth_sweeps;
+   int num_coarse_smooth_sweeps;
+   int jgs_block_rows;          /* hybrid JGS: Gauss-Seidel inside contiguous blocks of this many rows, Jacobi
+                                   across blocks (the reference's block is a thread's row range,
+                                   src/SMEM_Smooth.cpp:567-581) */
+   int use_sell;                /* 1: sliced-ELL (C=32) storage for low-variance levels, 0: CSR only */
+   int l2_persist;              /* 1: pin the coarse hierarchy in L2 with an access-policy window */
+} amgb_options;
+
+void amgb_default_options(amgb_options *opt);
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+int amgb_create(amgb_ctx **ctx, int device);
+int amgb_destroy(amgb_ctx *ctx);
+const char *amgb_last_error(const amgb_ctx *ctx);
+/* number of kernels this context has launched so far (graph replays counted per node) */
+long long amgb_launch_count(const amgb_ctx *ctx);
+
+/* ---- hierarchy upload: replaces the pointers SMEM_Setup/InitAlgebra hand to the solve phase
+ *      (all_data->matrix.A/P/R[l], src/SMEM_Setup.cpp:217-276).  Arrays are copied to HBM. ----- */
+int amgb_set_num_levels(amgb_ctx *ctx, int num_levels);
+int amgb_set_matrix(amgb_ctx *ctx, int kind /*AMGB_MAT_**/, int level, int nrows, int ncols, int nnz,
+                    const int *row_ptr, const int *col_idx, const double *values);
+int amgb_set_options(amgb_ctx *ctx, const amgb_options *opt);
+/* allocates work vectors, scale arrays (A_diag = d/omega, L1 norms: src/SMEM_Setup.cpp:225-238),
+ * optional SELL copies, CUDA graphs.  Must follow the uploads. */
+int amgb_setup(amgb_ctx *ctx);
+
+/* ---- vectors (all_data->vector.f[0] / u[0]) ----------------------------------------------- */
+int amgb_set_rhs(amgb_ctx *ctx, const double *f_host);
+int amgb_set_solution(amgb_ctx *ctx, const double *u_host /* NULL = zero */);
+int amgb_get_solution(amgb_ctx *ctx, double *u_host);
+int amgb_get_residual(amgb_ctx *ctx, double *r_host);
+
+/* ---- per-op entry points (unit parity; ChebySetup/BPXCycle callers) --------------------- */
+/* y = alpha*M*x + beta*b  -- SMEM_MatVec / SMEM_SpGEMV / SMEM_Residual / SMEM_Restrict
+ * (src/SMEM_MatVec.cpp:123-259,302-378,394-408).  b may be NULL when beta == 0. */
+int amgb_spgemv(amgb_ctx *ctx, int kind, int level, double alpha, const double *x, double beta,
+                const double *b, double *y);
+/* SMEM_Smooth dispatcher (src/SMEM_Solve.cpp:264-377) on level `level`: u is in/out (ignored on
+ * input when zero_guess != 0).  symmetric != 0 selects SMEM_Sync_Symmetric{,L1}Jacobi. */
+int amgb_smooth(amgb_ctx *ctx, int level, int smoother, int symmetric, int sweeps, int zero_guess,
+                const double *f, double *u);
+/* sqrt(sum x_i^2) -- Parfor_Norm2 (src/Misc.cpp:296-309) */
+int amgb_norm2(amgb_ctx *ctx, const double *x, int n, double *out);
+
+/* ---- cycles ------------------------------------------------------------------------------- */
+/* one application of the selected additive cycle to a residual, zero initial guess: c = B r.
+ * SMEM_Sync_Add_Vcycle (Multadd/AFACx, src/SMEM_Sync_AMG.cpp:408-621, sequential meaning
+ * src/SEQ_AMG.cpp:110-235) or SMEM_Sync_Parfor_BPXcycle (src/SMEM_Sync_AMG.cpp:147-294). */
+int amgb_cycle(amgb_ctx *ctx, const double *r_host, double *c_host);
+
+/* SMEM_Solve, synchronous branch (src/SMEM_Solve.cpp:93-252) on the resident f,u: cycles until
+ * ||r||/||r0|| < tol or max_cycles.  relres_hist[0..*n_cycles] (caller provides max_cycles+1
+ * doubles, may be NULL).  cheby_flag: Chebyshev acceleration of the cycle (:169-188) with mu,
+ * delta from ChebySetup (src/SMEM_Cheby.cpp:48-49).  solve_seconds: device time of the loop. */
+int amgb_solve_sync(amgb_ctx *ctx, double tol, int max_cycles, int cheby_flag, double mu, double delta,
+                    double *relres_hist, int *n_cycles, double *solve_seconds);
+
+/* SMEM_Async_Add_AMG (src/SMEM_Async_AMG.cpp:7-437) as ONE persistent cooperative kernel: each
+ * level's correction chain owns a CTA group; groups share u through fp64 global atomics, no grid
+ * barrier.  Stop rule: LOCAL = every group stops after num_cycles own corrections; GLOBAL = all
+ * stop once every level has done >= num_cycles (CheckConverge, src/Misc.cpp:418-442).
+ * corrections_per_level[num_levels] = local_num_correct; relres = final ||f-Au||/||r0||. */
+int amgb_solve_async(amgb_ctx *ctx, int num_cycles, int converge_type, int *corrections_per_level,
+                     double *relres, double *solve_seconds);
+
+/* Drop-in for one whole SMEM_Solve call with HOST buffers (what SMEM_Main's run loop would call,
+ * src/SMEM_Main.cpp:694-757): uploads f, zeroes u (InitSolve), runs the sync or async solve named
+ * by opt.solver, downloads u. */
+int amgb_smem_solve(amgb_ctx *ctx, const double *f_host, double *u_host, double tol, int num_cycles,
+                    double *relres_hist, int *n_cycles, int *corrections_per_level, double *final_relres,
+                    double *solve_seconds);
+
+/* ---- introspection used by bench.py ------------------------------------------------------- */
+/* event-timed duration (ms) of `reps` back-to-back launches of the fine-level residual kernel
+ * r = f - A_0 u (the dominant kernel), on the context's stream */
+int amgb_time_residual(amgb_ctx *ctx, int reps, double *ms_per_launch);
+int amgb_level_storage(amgb_ctx *ctx, int kind, int level, int *is_sell);
+
+/* ---- multi-GPU (DMEM replacement; one process per GPU) ------------------------------------ */
+/* rank 0 obtains a 128-byte NCCL unique id and distributes it (e.g. torch.distributed broadcast) */
+int amgb_dist_unique_id(unsigned char id128[128]);
+/* row-partitioned hierarchy: this rank owns rows [row_start[l], row_start[l]+nrows_local) of every
+ * level; matrices passed to amgb_set_matrix are then the LOCAL row blocks with GLOBAL column
+ * indices.  Replaces hypre's ParCSR comm_pkg + DMEM_Comm (src/DMEM_Comm.cpp:81-382). */
+int amgb_dist_init(amgb_ctx *ctx, const unsigned char id128[128], int rank, int nranks);
+int amgb_dist_set_partition(amgb_ctx *ctx, int level, const int *row_starts /* nranks+1 */);
+int amgb_dist_solve_sync(amgb_ctx *ctx, double tol, int max_cycles, double *relres_hist, int *n_cycles,
+                         double *solve_seconds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

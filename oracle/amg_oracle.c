@@ -1,0 +1,453 @@
+/* amg_oracle.c -- CPU ORACLE for the additive-AMG solve phase.  TEST INFRASTRUCTURE ONLY.
+ *
+ * A plain-C restatement of the reference's solve-phase loops.  Every function cites the
+ * reference file:line it follows.  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load this library; the product (libamg_b200.so)
+ * never links, imports or calls it.
+ *
+ * Parity status: PINNED against the reference's own object code -- oracle/_ref compiles the
+ * unmodified reference translation units SMEM_MatVec.cpp, SMEM_Smooth.cpp, SMEM_Sync_AMG.cpp,
+ * SMEM_Async_AMG.cpp, SMEM_Solve.cpp, SEQ_*.cpp against a hypre stub shim and
+ * tests/test_oracle_vs_ref.py compares both on the same inputs; the outputs are also
+ * committed as fixtures under tests/golden/.  The reference ships no golden vectors of its
+ * own.  The hierarchy (A_l, P_l) is an INPUT here -- hypre's setup is an
+ * un-vendored third-party dependency and is not restated.
+ *
+ * Semantics chosen where the reference is ambiguous:
+ *   - additive cycles follow the race-free sequential specification SEQ_Add_Vcycle
+ *     (src/SEQ_AMG.cpp:110-235), smoothers dispatched as SMEM_Smooth does
+ *     (src/SMEM_Solve.cpp:264-377);
+ *   - the coarsest level contributes nothing in SMEM additive cycles (5.9c);
+ *   - hybrid Jacobi/Gauss-Seidel takes the block list as an input (5.9e).
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <omp.h>
+
+typedef struct {
+   int nrows, ncols, nnz;
+   const int *i;
+   const int *j;
+   const double *data;
+} orc_csr;
+
+/* enums: src/Main.hpp:47-75 */
+#define ORC_JACOBI 0
+#define ORC_HYBRID_JGS 2
+#define ORC_L1_JACOBI 6
+#define ORC_AFACX 1
+#define ORC_MULTADD 2
+#define ORC_BPX 3
+
+typedef struct {
+   int num_levels;
+   const orc_csr *A;        /* [L]   diag-first */
+   const orc_csr *P;        /* [L-1] (smoothed for MULTADD) */
+   const orc_csr *R;        /* [L-1] explicit restriction */
+   const double *const *l1; /* [L] L1 row norms or NULL */
+   int solver, smoother;
+   double smooth_weight;
+   int num_pre, num_post, fine_sweeps, coarse_sweeps;
+   const int *const *jgs_blocks; /* [L] block boundaries (nblocks+1 ints) for hybrid JGS, or NULL */
+   const int *jgs_nblocks;       /* [L] */
+   int jgs_parfor_scale;         /* 1: divide by a_ii/w (Parfor variant, SMEM_Smooth.cpp:253-263) */
+} orc_problem;
+
+/* ---- SpMV family ------------------------------------------------------------------------ */
+/* src/SMEM_MatVec.cpp:302-323 (SMEM_MatVec), src/SEQ_MatVec.cpp:3-24 */
+void orc_matvec(const orc_csr *A, const double *x, double *y, int ns, int ne)
+{
+#pragma omp parallel for schedule(static)
+   for (int i = ns; i < ne; i++) {
+      double Axi = 0.0;
+      for (int jj = A->i[i]; jj < A->i[i + 1]; jj++) Axi += A->data[jj] * x[A->j[jj]];
+      y[i] = Axi;
+   }
+}
+
+/* y = alpha*A*x + beta*b   (src/SMEM_MatVec.cpp:123-259; the 12 alpha/beta special cases
+ * there are algebraically this expression; residual is alpha=-1, beta=1 as at :95-103) */
+void orc_spgemv(const orc_csr *A, const double *x, const double *b, double alpha, double beta, double *y)
+{
+#pragma omp parallel for schedule(static)
+   for (int i = 0; i < A->nrows; i++) {
+      double Axi = 0.0;
+      for (int jj = A->i[i]; jj < A->i[i + 1]; jj++) Axi += A->data[jj] * x[A->j[jj]];
+      double v;
+      if (alpha == -1.0 && beta == 1.0) v = b[i] - Axi;
+      else if (alpha == 1.0 && beta == 1.0) v = b[i] + Axi;
+      else if (beta == 0.0) v = alpha * Axi;
+      else v = alpha * Axi + beta * b[i];
+      y[i] = v;
+   }
+}
+
+/* src/SMEM_MatVec.cpp:362-378 */
+void orc_residual(const orc_csr *A, const double *b, const double *x, double *r)
+{
+   orc_spgemv(A, x, b, -1.0, 1.0, r);
+}
+
+/* y = A^T x   (src/SEQ_MatVec.cpp:26-45) */
+void orc_matvecT(const orc_csr *A, const double *x, double *y)
+{
+   for (int i = 0; i < A->ncols; i++) y[i] = 0;
+   for (int i = 0; i < A->nrows; i++)
+      for (int jj = A->i[i]; jj < A->i[i + 1]; jj++) y[A->j[jj]] += A->data[jj] * x[i];
+}
+
+/* sqrt(sum r_i^2)  (src/SMEM_Solve.cpp:199-203; src/Misc.cpp:296-309) */
+double orc_norm2(const double *x, int n)
+{
+   double s = 0;
+#pragma omp parallel for reduction(+ : s) schedule(static)
+   for (int i = 0; i < n; i++) s += x[i] * x[i];
+   return sqrt(s);
+}
+
+/* ---- smoothers ---------------------------------------------------------------------------- */
+/* src/SMEM_Smooth.cpp:365-407 (SMEM_Sync_Jacobi) / src/SEQ_Smooth.cpp:4-44 */
+void orc_jacobi(const orc_csr *A, const double *f, double *u, double *u_prev, double w, int sweeps, int zero_flag)
+{
+   const int n = A->nrows;
+   for (int k = 0; k < sweeps; k++) {
+      if (k == 0 && zero_flag) {
+#pragma omp parallel for schedule(static)
+         for (int i = 0; i < n; i++)
+            if (A->data[A->i[i]] != 0.0) u[i] = w * f[i] / A->data[A->i[i]];
+      } else {
+         memcpy(u_prev, u, sizeof(double) * (size_t)n);
+#pragma omp parallel for schedule(static)
+         for (int i = 0; i < n; i++)
+            if (A->data[A->i[i]] != 0.0) {
+               double res = f[i];
+               for (int jj = A->i[i]; jj < A->i[i + 1]; jj++) res -= A->data[jj] * u_prev[A->j[jj]];
+               u[i] += w * res / A->data[A->i[i]];
+            }
+      }
+   }
+}
+
+/* src/SMEM_Smooth.cpp:409-443 (SMEM_Sync_L1Jacobi) */
+void orc_l1_jacobi(const orc_csr *A, const double *f, double *u, double *u_prev, const double *l1, int sweeps, int zero_flag)
+{
+   const int n = A->nrows;
+   for (int k = 0; k < sweeps; k++) {
+      if (k == 0 && zero_flag) {
+#pragma omp parallel for schedule(static)
+         for (int i = 0; i < n; i++) u[i] = f[i] / l1[i];
+      } else {
+         memcpy(u_prev, u, sizeof(double) * (size_t)n);
+#pragma omp parallel for schedule(static)
+         for (int i = 0; i < n; i++) {
+            double res = f[i];
+            for (int jj = A->i[i]; jj < A->i[i + 1]; jj++) res -= A->data[jj] * u_prev[A->j[jj]];
+            u[i] += res / l1[i];
+         }
+      }
+   }
+}
+
+/* src/SMEM_Smooth.cpp:533-586 (SMEM_Sync_HybridJacobiGaussSeidel): Gauss-Seidel inside each
+ * block [ns,ne), Jacobi across blocks; weight forced to 1.  `scale`, when non-NULL, replaces
+ * a_ii as the divisor (Parfor variant, src/SMEM_Smooth.cpp:253-263,276,297). */
+void orc_hybrid_jgs(const orc_csr *A, const double *f, double *u, double *u_prev,
+                    const int *blocks, int nblocks, const double *scale, int sweeps, int zero_flag)
+{
+   const int n = A->nrows;
+   for (int k = 0; k < sweeps; k++) {
+      if (k == 0 && zero_flag) {
+#pragma omp parallel for schedule(dynamic, 16)
+         for (int b = 0; b < nblocks; b++) {
+            int ns = blocks[b], ne = blocks[b + 1];
+            for (int i = ns; i < ne; i++) u[i] = 0.0;
+            for (int i = ns; i < ne; i++)
+               if (A->data[A->i[i]] != 0.0) {
+                  double res = f[i];
+                  for (int jj = A->i[i]; jj < A->i[i + 1]; jj++) {
+                     int ii = A->j[jj];
+                     if (ii >= ns && ii < ne) res -= A->data[jj] * u[ii];
+                  }
+                  u[i] = res / (scale ? scale[i] : A->data[A->i[i]]);
+               }
+         }
+      } else {
+         memcpy(u_prev, u, sizeof(double) * (size_t)n);
+#pragma omp parallel for schedule(dynamic, 16)
+         for (int b = 0; b < nblocks; b++) {
+            int ns = blocks[b], ne = blocks[b + 1];
+            for (int i = ns; i < ne; i++)
+               if (A->data[A->i[i]] != 0.0) {
+                  double res = f[i];
+                  for (int jj = A->i[i]; jj < A->i[i + 1]; jj++) {
+                     int ii = A->j[jj];
+                     if (ii >= ns && ii < ne) res -= A->data[jj] * u[ii];
+                     else res -= A->data[jj] * u_prev[ii];
+                  }
+                  u[i] += res / (scale ? scale[i] : A->data[A->i[i]]);
+               }
+         }
+      }
+   }
+}
+
+/* src/SMEM_Smooth.cpp:643-702 (SMEM_Sync_SymmetricJacobi) / src/SEQ_Smooth.cpp:119-155:
+ * u (+)= (2 M^-1 - M^-1 A M^-1) r,  M = D/w.  The arithmetic order of the reference lines
+ * :663,:682-683 is kept. */
+void orc_symmetric_jacobi(const orc_csr *A, const double *f, double *u, double *y, double *r,
+                          double w, int sweeps, int zero_flag)
+{
+   const int n = A->nrows;
+   int k = 0;
+   if (zero_flag) memcpy(r, f, sizeof(double) * (size_t)n);
+   else orc_residual(A, f, u, r);
+   while (1) {
+#pragma omp parallel for schedule(static)
+      for (int i = 0; i < n; i++) r[i] *= w / A->data[A->i[i]];
+      orc_matvec(A, r, y, 0, n);
+#pragma omp parallel for schedule(static)
+      for (int i = 0; i < n; i++) {
+         double d = A->data[A->i[i]];
+         r[i] = (2.0 * d * r[i] / w) - y[i];
+         r[i] *= w / d;
+         if (zero_flag) u[i] = r[i]; else u[i] += r[i];
+      }
+      k++;
+      if (k == sweeps) break;
+      orc_residual(A, f, u, r);
+      /* the reference keeps zero_flags[level]==1 for later sweeps as well (:685-694), so a
+       * second sweep overwrites u; mirrored. */
+   }
+}
+
+/* src/SMEM_Smooth.cpp:704-762 (SMEM_Sync_SymmetricL1Jacobi) */
+void orc_symmetric_l1_jacobi(const orc_csr *A, const double *f, double *u, double *y, double *r,
+                             const double *l1, int sweeps, int zero_flag)
+{
+   const int n = A->nrows;
+   int k = 0;
+   if (zero_flag) memcpy(r, f, sizeof(double) * (size_t)n);
+   else orc_residual(A, f, u, r);
+   while (1) {
+#pragma omp parallel for schedule(static)
+      for (int i = 0; i < n; i++) r[i] /= l1[i];
+      orc_matvec(A, r, y, 0, n);
+#pragma omp parallel for schedule(static)
+      for (int i = 0; i < n; i++) {
+         r[i] = (2.0 * l1[i] * r[i]) - y[i];
+         r[i] /= l1[i];
+         if (zero_flag) u[i] = r[i]; else u[i] += r[i];
+      }
+      k++;
+      if (k == sweeps) break;
+      orc_residual(A, f, u, r);
+   }
+}
+
+/* smoother dispatch: src/SMEM_Solve.cpp:264-377, thread_part_type == ALL_LEVELS branch
+ * (:277-323) for MULTADD/AFACX, Parfor branch (:324-345) for BPX.  zero_flags[level]==1
+ * everywhere in additive cycles (src/SEQ_AMG.cpp:121, src/SMEM_Sync_AMG.cpp:217,457). */
+static void orc_smooth(const orc_problem *pb, int level, const double *f, double *u,
+                       double *scratch_y, double *scratch_r, int sweeps)
+{
+   const orc_csr *A = &pb->A[level];
+   const int symm = (pb->solver == ORC_MULTADD) && pb->num_pre > 0 && pb->num_post > 0;
+   if (pb->smoother == ORC_HYBRID_JGS) {
+      double *scale = NULL;
+      if (pb->jgs_parfor_scale || pb->solver == ORC_BPX) {
+         scale = (double *)malloc(sizeof(double) * (size_t)A->nrows);
+         for (int i = 0; i < A->nrows; i++) scale[i] = A->data[A->i[i]] / pb->smooth_weight;
+      }
+      orc_hybrid_jgs(A, f, u, scratch_y, pb->jgs_blocks[level], pb->jgs_nblocks[level], scale, sweeps, 1);
+      free(scale);
+   } else if (pb->smoother == ORC_L1_JACOBI) {
+      if (symm) orc_symmetric_l1_jacobi(A, f, u, scratch_y, scratch_r, pb->l1[level], sweeps, 1);
+      else orc_l1_jacobi(A, f, u, scratch_y, pb->l1[level], sweeps, 1);
+   } else {
+      if (symm) orc_symmetric_jacobi(A, f, u, scratch_y, scratch_r, pb->smooth_weight, sweeps, 1);
+      else orc_jacobi(A, f, u, scratch_y, pb->smooth_weight, sweeps, 1);
+   }
+}
+
+/* ---- cycles --------------------------------------------------------------------------------- */
+typedef struct {
+   double **r, **e, **y, **s, **uc, **rf;
+   int L;
+} orc_work;
+
+static orc_work *work_alloc(const orc_problem *pb)
+{
+   orc_work *w = (orc_work *)calloc(1, sizeof(orc_work));
+   int L = pb->num_levels;
+   w->L = L;
+   double ***arr[6] = {&w->r, &w->e, &w->y, &w->s, &w->uc, &w->rf};
+   for (int a = 0; a < 6; a++) {
+      *arr[a] = (double **)calloc((size_t)L, sizeof(double *));
+      for (int l = 0; l < L; l++) (*arr[a])[l] = (double *)calloc((size_t)pb->A[l].nrows, sizeof(double));
+   }
+   return w;
+}
+
+static void work_free(orc_work *w)
+{
+   double **arr[6] = {w->r, w->e, w->y, w->s, w->uc, w->rf};
+   for (int a = 0; a < 6; a++) {
+      for (int l = 0; l < w->L; l++) free(arr[a][l]);
+      free(arr[a]);
+   }
+   free(w);
+}
+
+/* One additive cycle applied to residual w->r[0]; adds every level's correction into u.
+ * Multadd / AFACx: src/SEQ_AMG.cpp:110-235 (sequential specification of
+ * src/SMEM_Sync_AMG.cpp:408-621).  levels_done[l]++ mirrors local_num_correct. */
+static void orc_add_vcycle(const orc_problem *pb, orc_work *w, double *u, int *levels_done)
+{
+   const int L = pb->num_levels;
+   for (int l = 0; l < L - 1; l++) orc_matvec(&pb->R[l], w->r[l], w->r[l + 1], 0, pb->R[l].nrows);
+   for (int level = 0; level < L; level++) {
+      double *uf = w->uc[level]; /* u_fine of this level */
+      if (level == L - 1) {
+         /* coarsest: solve commented out / result unused -> contributes 0 */
+         memset(w->e[level], 0, sizeof(double) * (size_t)pb->A[level].nrows);
+      } else if (pb->solver == ORC_MULTADD) {
+         memset(w->e[level], 0, sizeof(double) * (size_t)pb->A[level].nrows);
+         orc_smooth(pb, level, w->r[level], w->e[level], w->y[level], w->s[level], pb->fine_sweeps);
+      } else { /* AFACx: src/SEQ_AMG.cpp:172-208 */
+         int c = level + 1;
+         double *ucoarse = w->rf[c];
+         memset(ucoarse, 0, sizeof(double) * (size_t)pb->A[c].nrows);
+         orc_smooth(pb, c, w->r[c], ucoarse, w->y[c], w->s[c], pb->coarse_sweeps);
+         orc_matvec(&pb->P[level], ucoarse, w->e[level], 0, pb->P[level].nrows);
+         /* r_fine = r - A e */
+         orc_spgemv(&pb->A[level], w->e[level], w->r[level], -1.0, 1.0, w->y[level]);
+         double *rfine = (double *)malloc(sizeof(double) * (size_t)pb->A[level].nrows);
+         memcpy(rfine, w->y[level], sizeof(double) * (size_t)pb->A[level].nrows);
+         memset(uf, 0, sizeof(double) * (size_t)pb->A[level].nrows);
+         orc_smooth(pb, level, rfine, uf, w->y[level], w->s[level], pb->fine_sweeps);
+         memcpy(w->e[level], uf, sizeof(double) * (size_t)pb->A[level].nrows);
+         free(rfine);
+      }
+      if (levels_done) levels_done[level]++;
+      /* prolong this level's correction to level 0 (src/SEQ_AMG.cpp:213-228) */
+      for (int inner = level; inner > 0; inner--)
+         orc_matvec(&pb->P[inner - 1], w->e[inner], w->e[inner - 1], 0, pb->P[inner - 1].nrows);
+      const int n0 = pb->A[0].nrows;
+#pragma omp parallel for schedule(static)
+      for (int i = 0; i < n0; i++) u[i] += w->e[0][i];
+   }
+}
+
+/* BPX: src/SMEM_Sync_AMG.cpp:147-294 (non-PAR_BPX branch): restrict with R = P^T, e_l = S_l r_l on
+ * EVERY level incl. the coarsest (zero guess, num_pre sweeps, Parfor smoothers), e_l += P_l e_{l+1}
+ * upward, u += e_0. */
+static void orc_bpx_cycle(const orc_problem *pb, orc_work *w, double *u)
+{
+   const int L = pb->num_levels;
+   for (int l = 0; l < L - 1; l++) orc_matvec(&pb->R[l], w->r[l], w->r[l + 1], 0, pb->R[l].nrows);
+   for (int l = 0; l < L; l++) {
+      memset(w->e[l], 0, sizeof(double) * (size_t)pb->A[l].nrows);
+      orc_smooth(pb, l, w->r[l], w->e[l], w->y[l], w->s[l], pb->num_pre);
+   }
+   for (int l = L - 2; l >= 0; l--) orc_spgemv(&pb->P[l], w->e[l + 1], w->e[l], 1.0, 1.0, w->e[l]);
+   const int n0 = pb->A[0].nrows;
+#pragma omp parallel for schedule(static)
+   for (int i = 0; i < n0; i++) u[i] += w->e[0][i];
+}
+
+/* One application of the selected cycle to residual r (length n0): u += B r.  Exposed for
+ * per-cycle parity tests. */
+void orc_cycle(const orc_problem *pb, const double *r, double *u)
+{
+   orc_work *w = work_alloc(pb);
+   memcpy(w->r[0], r, sizeof(double) * (size_t)pb->A[0].nrows);
+   if (pb->solver == ORC_BPX) orc_bpx_cycle(pb, w, u);
+   else orc_add_vcycle(pb, w, u, NULL);
+   work_free(w);
+}
+
+/* Outer loop: src/SMEM_Solve.cpp:60-70 (r0), :128-240 (cycle, Chebyshev :169-188, residual
+ * :192-197, norm :199-203, stop :222).  relres[0]=1, relres[k] after cycle k.  Returns the
+ * number of cycles done.  cheby: 0 off; else mu, delta as from ChebySetup
+ * (src/SMEM_Cheby.cpp:48-49). */
+int orc_solve_sync(const orc_problem *pb, const double *f, double *u, double tol, int num_cycles,
+                   int cheby_flag, double mu, double delta, double *relres, double *seconds)
+{
+   const int n0 = pb->A[0].nrows;
+   orc_work *w = work_alloc(pb);
+   double *r = w->r[0];
+   double *u_outer = NULL, *y_outer = NULL, *c = NULL;
+   double omega = 2.0, mu24 = 4.0 * mu * mu;
+   orc_residual(&pb->A[0], f, u, r);
+   const double r0 = orc_norm2(r, n0);
+   relres[0] = 1.0;
+   if (cheby_flag) {
+      u_outer = (double *)calloc((size_t)n0, sizeof(double));
+      y_outer = (double *)calloc((size_t)n0, sizeof(double));
+      c = (double *)calloc((size_t)n0, sizeof(double));
+   }
+   int k, done = 0;
+   double t0 = omp_get_wtime();
+   for (k = 1; k <= num_cycles; k++) {
+      if (cheby_flag) {
+         /* precond form: cycle from zero guess on the current residual (src/SMEM_Sync_AMG.cpp:281-286
+          * precond_flag branch), then the three-term recurrence src/SMEM_Solve.cpp:179-187 */
+         memset(c, 0, sizeof(double) * (size_t)n0);
+         if (pb->solver == ORC_BPX) orc_bpx_cycle(pb, w, c);
+         else orc_add_vcycle(pb, w, c, NULL);
+#pragma omp parallel for schedule(static)
+         for (int i = 0; i < n0; i++) {
+            double u_outer_prev = u_outer[i];
+            u_outer[i] = y_outer[i] + omega * (delta * c[i] + u_outer[i] - y_outer[i]);
+            y_outer[i] = u_outer_prev;
+            u[i] = u_outer[i];
+         }
+         omega = 1.0 / (1.0 - omega / mu24);
+      } else {
+         if (pb->solver == ORC_BPX) orc_bpx_cycle(pb, w, u);
+         else orc_add_vcycle(pb, w, u, NULL);
+      }
+      orc_residual(&pb->A[0], f, u, r);
+      double rn = orc_norm2(r, n0);
+      relres[k] = rn / r0;
+      done = k;
+      if (rn / r0 < tol) break;
+   }
+   if (seconds) *seconds = omp_get_wtime() - t0;
+   free(u_outer); free(y_outer); free(c);
+   work_free(w);
+   return done;
+}
+
+/* Sequential model of the asynchronous additive solve with no staleness: every level applies
+ * its chain to the residual of the CURRENT shared u, one level after the other (the
+ * num_threads-independent limit of src/SMEM_Async_AMG.cpp:79-352 when groups never overlap).
+ * Used only to sanity-check the async GPU path's convergence; counts[l] = corrections. */
+int orc_solve_async_sequential(const orc_problem *pb, const double *f, double *u, int num_cycles,
+                               int *counts, double *final_relres)
+{
+   const int L = pb->num_levels, n0 = pb->A[0].nrows;
+   orc_work *w = work_alloc(pb);
+   orc_residual(&pb->A[0], f, u, w->r[0]);
+   const double r0 = orc_norm2(w->r[0], n0);
+   for (int k = 0; k < num_cycles; k++)
+      for (int q = 0; q < L; q++) {
+         for (int l = 0; l < q && l < L - 1; l++) orc_matvec(&pb->R[l], w->r[l], w->r[l + 1], 0, pb->R[l].nrows);
+         if (q < L - 1) {
+            memset(w->e[q], 0, sizeof(double) * (size_t)pb->A[q].nrows);
+            orc_smooth(pb, q, w->r[q], w->e[q], w->y[q], w->s[q], pb->fine_sweeps);
+         } else memset(w->e[q], 0, sizeof(double) * (size_t)pb->A[q].nrows);
+         for (int inner = q; inner > 0; inner--)
+            orc_matvec(&pb->P[inner - 1], w->e[inner], w->e[inner - 1], 0, pb->P[inner - 1].nrows);
+         for (int i = 0; i < n0; i++) u[i] += w->e[0][i];
+         counts[q]++;
+         orc_residual(&pb->A[0], f, u, w->r[0]);
+      }
+   *final_relres = orc_norm2(w->r[0], n0) / r0;
+   work_free(w);
+   return 0;
+}
+
+int orc_max_threads(void) { return omp_get_max_threads(); }
+void orc_set_threads(int t) { omp_set_num_threads(t); }

@@ -1,0 +1,262 @@
+"""ctypes front-end of the CPU oracle (oracle/amg_oracle.c) and of the compiled reference
+objects (oracle/_ref/libref_smem.so).  TEST INFRASTRUCTURE ONLY: imported by tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs, never by the
+product package."""
+import ctypes as C
+import importlib
+import os
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+if _ROOT not in sys.path:
+    sys.path.insert(0, _ROOT)
+_pkg = importlib.import_module("async-multigrid_b200")
+from oracle import build as _build  # noqa: E402
+
+DP = C.POINTER(C.c_double)
+IP = C.POINTER(C.c_int)
+
+
+class OrcCSR(C.Structure):
+    _fields_ = [("nrows", C.c_int), ("ncols", C.c_int), ("nnz", C.c_int),
+                ("i", IP), ("j", IP), ("data", DP)]
+
+
+class OrcProblem(C.Structure):
+    _fields_ = [("num_levels", C.c_int),
+                ("A", C.POINTER(OrcCSR)), ("P", C.POINTER(OrcCSR)), ("R", C.POINTER(OrcCSR)),
+                ("l1", C.POINTER(DP)),
+                ("solver", C.c_int), ("smoother", C.c_int), ("smooth_weight", C.c_double),
+                ("num_pre", C.c_int), ("num_post", C.c_int), ("fine_sweeps", C.c_int), ("coarse_sweeps", C.c_int),
+                ("jgs_blocks", C.POINTER(IP)), ("jgs_nblocks", IP), ("jgs_parfor_scale", C.c_int)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = _build.ORACLE_LIB
+        if not os.path.exists(path):
+            _build.build_oracle()
+        L = C.CDLL(path)
+        L.orc_norm2.restype = C.c_double
+        L.orc_norm2.argtypes = [DP, C.c_int]
+        L.orc_solve_sync.restype = C.c_int
+        L.orc_solve_sync.argtypes = [C.POINTER(OrcProblem), DP, DP, C.c_double, C.c_int, C.c_int,
+                                     C.c_double, C.c_double, DP, DP]
+        L.orc_cycle.argtypes = [C.POINTER(OrcProblem), DP, DP]
+        L.orc_spgemv.argtypes = [C.POINTER(OrcCSR), DP, DP, C.c_double, C.c_double, DP]
+        L.orc_matvec.argtypes = [C.POINTER(OrcCSR), DP, DP, C.c_int, C.c_int]
+        L.orc_jacobi.argtypes = [C.POINTER(OrcCSR), DP, DP, DP, C.c_double, C.c_int, C.c_int]
+        L.orc_l1_jacobi.argtypes = [C.POINTER(OrcCSR), DP, DP, DP, DP, C.c_int, C.c_int]
+        L.orc_hybrid_jgs.argtypes = [C.POINTER(OrcCSR), DP, DP, DP, IP, C.c_int, DP, C.c_int, C.c_int]
+        L.orc_symmetric_jacobi.argtypes = [C.POINTER(OrcCSR), DP, DP, DP, DP, C.c_double, C.c_int, C.c_int]
+        L.orc_symmetric_l1_jacobi.argtypes = [C.POINTER(OrcCSR), DP, DP, DP, DP, DP, C.c_int, C.c_int]
+        L.orc_solve_async_sequential.argtypes = [C.POINTER(OrcProblem), DP, DP, C.c_int, IP, DP]
+        _lib = L
+    return _lib
+
+
+def dptr(a):
+    return a.ctypes.data_as(DP)
+
+
+def iptr(a):
+    return a.ctypes.data_as(IP)
+
+
+def c_csr(m):
+    s = OrcCSR()
+    s.nrows, s.ncols, s.nnz = m.nrows, m.ncols, m.nnz
+    s.i, s.j, s.data = iptr(m.indptr), iptr(m.indices), dptr(m.data)
+    return s
+
+
+class Problem:
+    """Keeps the numpy arrays alive and exposes an orc_problem for the C side."""
+
+    def __init__(self, h, solver, smoother, smooth_weight=1.0, num_pre=1, num_post=1,
+                 fine_sweeps=1, coarse_sweeps=1, jgs_blocks=None, jgs_parfor_scale=0):
+        L = h.num_levels
+        self.h = h
+        self._A = (OrcCSR * L)(*[c_csr(a) for a in h.A])
+        self._P = (OrcCSR * max(L - 1, 1))(*[c_csr(p) for p in h.P])
+        self._R = (OrcCSR * max(L - 1, 1))(*[c_csr(r) for r in h.R])
+        self._l1arrs = h.l1_norms()
+        self._l1 = (DP * L)(*[dptr(a) for a in self._l1arrs])
+        if jgs_blocks is None:
+            jgs_blocks = [np.asarray([0, a.nrows], dtype=np.int32) for a in h.A]
+        self._blocks = [np.ascontiguousarray(b, dtype=np.int32) for b in jgs_blocks]
+        self._bptr = (IP * L)(*[iptr(b) for b in self._blocks])
+        self._nb = np.asarray([len(b) - 1 for b in self._blocks], dtype=np.int32)
+        p = OrcProblem()
+        p.num_levels = L
+        p.A, p.P, p.R = self._A, self._P, self._R
+        p.l1 = self._l1
+        p.solver, p.smoother, p.smooth_weight = solver, smoother, smooth_weight
+        p.num_pre, p.num_post, p.fine_sweeps, p.coarse_sweeps = num_pre, num_post, fine_sweeps, coarse_sweeps
+        p.jgs_blocks = self._bptr
+        p.jgs_nblocks = iptr(self._nb)
+        p.jgs_parfor_scale = jgs_parfor_scale
+        self.c = p
+
+    def solve_sync(self, f, tol=1e-9, num_cycles=100, cheby=None, u0=None):
+        n = self.h.n[0]
+        u = np.zeros(n) if u0 is None else np.array(u0, dtype=np.float64)
+        hist = np.zeros(num_cycles + 1)
+        secs = C.c_double(0)
+        mu, delta = (cheby if cheby else (0.0, 0.0))
+        k = lib().orc_solve_sync(C.byref(self.c), dptr(np.ascontiguousarray(f)), dptr(u), tol, num_cycles,
+                                 1 if cheby else 0, mu, delta, dptr(hist), C.byref(secs))
+        return u, hist[:k + 1], secs.value
+
+    def cycle(self, r):
+        u = np.zeros(self.h.n[0])
+        lib().orc_cycle(C.byref(self.c), dptr(np.ascontiguousarray(r)), dptr(u))
+        return u
+
+    def solve_async_sequential(self, f, num_cycles):
+        u = np.zeros(self.h.n[0])
+        counts = np.zeros(self.h.num_levels, dtype=np.int32)
+        rr = C.c_double(0)
+        lib().orc_solve_async_sequential(C.byref(self.c), dptr(np.ascontiguousarray(f)), dptr(u), num_cycles,
+                                         iptr(counts), C.byref(rr))
+        return u, counts, rr.value
+
+
+def spgemv(m, x, b, alpha, beta):
+    y = np.zeros(m.nrows)
+    s = c_csr(m)
+    bb = b if b is not None else np.zeros(m.nrows)
+    lib().orc_spgemv(C.byref(s), dptr(np.ascontiguousarray(x)), dptr(np.ascontiguousarray(bb)), alpha, beta, dptr(y))
+    return y
+
+
+def norm2(x):
+    x = np.ascontiguousarray(x)
+    return lib().orc_norm2(dptr(x), len(x))
+
+
+def smooth(kind, m, f, w=1.0, sweeps=1, zero_flag=1, u0=None, l1=None, blocks=None, scale=None):
+    """kind in jacobi | l1_jacobi | hybrid_jgs | symmetric_jacobi | symmetric_l1_jacobi"""
+    n = m.nrows
+    s = c_csr(m)
+    f = np.ascontiguousarray(f)
+    u = np.zeros(n) if u0 is None else np.array(u0, dtype=np.float64)
+    y, r = np.zeros(n), np.zeros(n)
+    L = lib()
+    if kind == "jacobi":
+        L.orc_jacobi(C.byref(s), dptr(f), dptr(u), dptr(y), w, sweeps, zero_flag)
+    elif kind == "l1_jacobi":
+        L.orc_l1_jacobi(C.byref(s), dptr(f), dptr(u), dptr(y), dptr(l1), sweeps, zero_flag)
+    elif kind == "hybrid_jgs":
+        blocks = np.ascontiguousarray(blocks, dtype=np.int32)
+        sp = dptr(scale) if scale is not None else None
+        L.orc_hybrid_jgs(C.byref(s), dptr(f), dptr(u), dptr(y), iptr(blocks), len(blocks) - 1, sp, sweeps, zero_flag)
+    elif kind == "symmetric_jacobi":
+        L.orc_symmetric_jacobi(C.byref(s), dptr(f), dptr(u), dptr(y), dptr(r), w, sweeps, zero_flag)
+    elif kind == "symmetric_l1_jacobi":
+        L.orc_symmetric_l1_jacobi(C.byref(s), dptr(f), dptr(u), dptr(y), dptr(r), dptr(l1), sweeps, zero_flag)
+    else:
+        raise ValueError(kind)
+    return u
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's own object code (oracle/_ref/libref_smem.so, built by oracle/build_ref.sh)
+# ------------------------------------------------------------------------------------------------
+_ref = None
+
+
+def ref_lib():
+    """None when oracle/_ref is absent (it is built only where /root/reference is mounted and
+    travels to the GPU box as a prebuilt file)."""
+    global _ref
+    if _ref is None:
+        path = _build.REF_LIB
+        if not os.path.exists(path):
+            try:
+                _build.build_ref()
+            except Exception:
+                return None
+        if not os.path.exists(path):
+            return None
+        L = C.CDLL(path)
+        L.ref_create.restype = C.c_void_p
+        L.ref_create.argtypes = [C.c_int, C.POINTER(OrcCSR), C.POINTER(OrcCSR), C.POINTER(OrcCSR), C.POINTER(DP),
+                                 C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
+                                 C.c_int, IP, DP]
+        L.ref_solve.restype = C.c_int
+        L.ref_solve.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double,
+                                C.c_int, DP, DP, IP, DP, DP]
+        L.ref_destroy.argtypes = [C.c_void_p]
+        L.ref_solve_sync_det.restype = C.c_int
+        L.ref_solve_sync_det.argtypes = [C.c_void_p, C.c_int, C.c_double, DP, DP]
+        L.ref_matvec.argtypes = [C.POINTER(OrcCSR), DP, DP]
+        L.ref_seq_symmetric_jacobi.argtypes = [C.POINTER(OrcCSR), DP, DP, C.c_double, C.c_int]
+        L.ref_seq_jacobi.argtypes = [C.POINTER(OrcCSR), DP, DP, C.c_double, C.c_int, C.c_int]
+        _ref = L
+    return _ref
+
+
+class RefSolver:
+    """SMEM_Solve of the reference on a given hierarchy.  num_threads >= num_levels is required
+    for the thread-group-per-level cycles."""
+
+    def __init__(self, h, solver, smoother, f, smooth_weight=1.0, num_pre=1, num_post=1,
+                 fine_sweeps=1, coarse_sweeps=1, num_threads=None, one_thread_per_level=False):
+        hier = _pkg.hierarchy
+        L = h.num_levels
+        self.h = h
+        self.L = ref_lib()
+        if self.L is None:
+            raise RuntimeError("oracle/_ref/libref_smem.so not available")
+        if num_threads is None:
+            num_threads = max(L, min(self.L.ref_max_threads(), 64))
+        self.num_threads = num_threads
+        self._A = (OrcCSR * L)(*[c_csr(a) for a in h.A])
+        self._P = (OrcCSR * max(L - 1, 1))(*[c_csr(p) for p in h.P])
+        self._R = (OrcCSR * max(L - 1, 1))(*[c_csr(r) for r in h.R])
+        self._l1arrs = h.l1_norms()
+        self._l1 = (DP * L)(*[dptr(a) for a in self._l1arrs])
+        _, frac = hier.compute_work(h, solver, num_pre, num_post, fine_sweeps, coarse_sweeps)
+        if one_thread_per_level:
+            num_threads = L
+            self.threads_per_level = np.ones(L, dtype=np.int32)
+        else:
+            self.threads_per_level = np.asarray(hier.balanced_threads(frac, num_threads), dtype=np.int32)
+        self.num_threads = num_threads
+        self._f = np.ascontiguousarray(f, dtype=np.float64)
+        self.handle = self.L.ref_create(L, self._A, self._P, self._R, self._l1, solver, smoother, smooth_weight,
+                                        num_pre, num_post, fine_sweeps, coarse_sweeps, num_threads,
+                                        iptr(self.threads_per_level), dptr(self._f))
+
+    def solve(self, num_cycles, tol=1e-9, async_type=1, cheby=None, precond=0):
+        """async_type=1 (SEMI_ASYNC) takes the lock around the u update in the sync additive cycle
+        (src/SMEM_Sync_AMG.cpp:598-610), i.e. the race-free meaning."""
+        n = self.h.n[0]
+        u = np.zeros(n)
+        hist = np.zeros(num_cycles + 1)
+        corr = np.zeros(self.h.num_levels, dtype=np.int32)
+        secs, rr = C.c_double(0), C.c_double(0)
+        mu, delta = cheby if cheby else (1.0, 1.0)
+        k = self.L.ref_solve(self.handle, num_cycles, tol, async_type, 1 if cheby else 0, mu, delta, precond,
+                             dptr(u), dptr(hist), iptr(corr), C.byref(secs), C.byref(rr))
+        return dict(u=u, hist=hist[:k + 1], cycles=k, corrections=corr, seconds=secs.value, relres=rr.value)
+
+    def solve_sync_det(self, num_cycles, tol=1e-9):
+        """race-free run of the reference's grouped additive cycle (see ref_driver.cpp)"""
+        u = np.zeros(self.h.n[0])
+        hist = np.zeros(num_cycles + 1)
+        k = self.L.ref_solve_sync_det(self.handle, num_cycles, tol, dptr(u), dptr(hist))
+        return dict(u=u, hist=hist[:k + 1], cycles=k)
+
+    def close(self):
+        if self.handle:
+            self.L.ref_destroy(self.handle)
+            self.handle = None

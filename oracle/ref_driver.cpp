@@ -1,0 +1,378 @@
+// ref_driver.cpp -- TEST INFRASTRUCTURE.  Drives the reference's own, UNMODIFIED solve-phase
+// object code (SMEM_Solve, SMEM_Sync_Add_Vcycle, SMEM_Sync_Parfor_{BPX,AFACx}cycle,
+// SMEM_Async_Add_AMG, SMEM_Smooth*, SMEM_MatVec*, SEQ_*, Misc.cpp barriers/norms), compiled by
+// oracle/build_ref.sh from /root/reference/src into oracle/_ref/libref_smem.so.
+//
+// What this file does is the part of SMEM_Setup the solve phase needs but that cannot be
+// compiled here (it calls hypre / Eigen): it fills `AllData` from a hierarchy handed in as
+// flat CSR arrays, following InitAlgebra's allocations (src/SMEM_Setup.cpp:280-419) and
+// PartitionLevels / PartitionGrids' final assignment loops (src/SMEM_Setup.cpp:855-868,
+// 940-1036).  The per-level thread counts come from the caller (hierarchy.balanced_threads
+// restates src/SMEM_Setup.cpp:770-854).  It then calls the reference's InitSolve + SMEM_Solve.
+//
+// The per-iteration residual history is captured at full precision by routing SMEM_Solve.cpp's
+// printf (only that TU, -Dprintf=ref_hook_printf) to a hook that reads all_data->output.
+#include "ref_prelude.hpp"
+#include "Misc.hpp"
+#include "SMEM_Solve.hpp"
+#include "SMEM_MatVec.hpp"
+#include "SEQ_Smooth.hpp"
+#include "SMEM_Sync_AMG.hpp"
+#include <cstdarg>
+
+static AllData *g_all = nullptr;
+static double *g_hist = nullptr;
+static int g_hist_cap = 0;
+
+extern "C" int ref_hook_printf(const char *fmt, ...)
+{
+   // SMEM_Solve.cpp:232-239 prints "%d\t%e\t\t%e\n" with (k, r_norm2/r0_norm2, rate)
+   if (g_all && g_hist && strncmp(fmt, "%d\t%e", 5) == 0) {
+      va_list ap;
+      va_start(ap, fmt);
+      int k = va_arg(ap, int);
+      va_end(ap);
+      if (k >= 0 && k < g_hist_cap) g_hist[k] = (k == 0) ? 1.0 : g_all->output.r_norm2 / g_all->output.r0_norm2;
+   }
+   return 0;
+}
+
+// ---- the few hypre entry points the solve phase calls -------------------------------------------
+HYPRE_Int *hypre_LowerBound(HYPRE_Int *first, HYPRE_Int *last, HYPRE_Int value)
+{
+   return std::lower_bound(first, last, value);
+}
+// hypre csr_matrix.c: hypre_CSRMatrixGetLoadBalancedPartitionBoundary (published algorithm)
+static HYPRE_Int lb_boundary(hypre_CSRMatrix *A, HYPRE_Int idx)
+{
+   HYPRE_Int nnz = A->num_nonzeros, n = A->num_rows, T = omp_get_num_threads();
+   HYPRE_Int per = (nnz + T - 1) / T;
+   if (idx <= 0) return 0;
+   if (idx >= T) return n;
+   return (HYPRE_Int)(hypre_LowerBound(A->i, A->i + n, per * idx) - A->i);
+}
+HYPRE_Int hypre_CSRMatrixGetLoadBalancedPartitionBegin(hypre_CSRMatrix *A) { return lb_boundary(A, omp_get_thread_num()); }
+HYPRE_Int hypre_CSRMatrixGetLoadBalancedPartitionEnd(hypre_CSRMatrix *A) { return lb_boundary(A, omp_get_thread_num() + 1); }
+// SMEM additive cycles call this on hypre's own F/U arrays, which the cycle never reads
+// (SURVEY.md 5.9c): a no-op reproduces the reference result exactly.
+HYPRE_Int hypre_GaussElimSolve(hypre_ParAMGData *, HYPRE_Int, HYPRE_Int) { return 0; }
+HYPRE_Int HYPRE_BoomerAMGSetPrintLevel(HYPRE_Solver, HYPRE_Int) { return 0; }
+HYPRE_Int HYPRE_BoomerAMGSetMaxIter(HYPRE_Solver, HYPRE_Int) { return 0; }
+HYPRE_Int hypre_ParVectorSetConstantValues(hypre_ParVector *, HYPRE_Complex) { return 0; }
+HYPRE_Int HYPRE_IJMatrixCreate(MPI_Comm, HYPRE_BigInt, HYPRE_BigInt, HYPRE_BigInt, HYPRE_BigInt, HYPRE_IJMatrix *) { return 1; }
+HYPRE_Int HYPRE_IJMatrixSetObjectType(HYPRE_IJMatrix, HYPRE_Int) { return 1; }
+HYPRE_Int HYPRE_IJMatrixInitialize(HYPRE_IJMatrix) { return 1; }
+HYPRE_Int HYPRE_IJMatrixSetValues(HYPRE_IJMatrix, HYPRE_Int, HYPRE_Int *, const HYPRE_BigInt *, const HYPRE_BigInt *, const HYPRE_Complex *) { return 1; }
+HYPRE_Int HYPRE_IJMatrixAssemble(HYPRE_IJMatrix) { return 1; }
+HYPRE_Int HYPRE_IJMatrixGetObject(HYPRE_IJMatrix, void **) { return 1; }
+
+// referenced by SMEM_Solve.cpp (async with one thread) but defined in a TU that is compiled too
+// (SEQ_AMG.cpp); nothing else is missing.
+
+struct RefCSR { int nrows, ncols, nnz; int *i; int *j; double *data; };
+
+struct RefHandle {
+   AllData all;
+   std::vector<hypre_CSRMatrix> A, P, R;
+   hypre_ParAMGData amg;
+   std::vector<hypre_ParVector> pv;
+   std::vector<hypre_Vector> lv;
+   std::vector<hypre_ParVector *> Farr, Uarr;
+   std::vector<hypre_ParCSRMatrix> parA;
+   std::vector<hypre_ParCSRMatrix *> Aarr;
+   std::vector<std::vector<double>> store;
+   double *vec(size_t n) { store.emplace_back(n, 0.0); return store.back().data(); }
+};
+
+static void fill(hypre_CSRMatrix *m, const RefCSR &s)
+{
+   m->i = s.i; m->j = s.j; m->data = s.data;
+   m->num_rows = s.nrows; m->num_cols = s.ncols; m->num_nonzeros = s.nnz;
+   m->rownnz = nullptr; m->num_rownnz = s.nrows;
+}
+
+extern "C" {
+
+// threads_per_level[L]: BALANCED_THREADS result (caller).  thread_part_type is chosen as
+// SMEM_Main.cpp:641-649 does (ONE_LEVEL for BPX/MULT, ALL_LEVELS otherwise).
+void *ref_create(int L, const RefCSR *A, const RefCSR *P, const RefCSR *R, double *const *l1,
+                 int solver, int smoother, double smooth_weight, int num_pre, int num_post,
+                 int fine_sweeps, int coarse_sweeps, int num_threads, const int *threads_per_level,
+                 const double *f)
+{
+   RefHandle *H = new RefHandle();
+   AllData *ad = &H->all;
+   memset((void *)&ad->input, 0, sizeof(ad->input));
+   memset((void *)&ad->output, 0, sizeof(ad->output));
+   memset((void *)&ad->matrix, 0, sizeof(ad->matrix));
+   memset((void *)&ad->cheby, 0, sizeof(ad->cheby));
+   // defaults of src/SMEM_Main.cpp:64-104
+   ad->input.tol = 1e-9;
+   ad->input.async_flag = (solver == ASYNC_MULTADD || solver == ASYNC_AFACX);
+   ad->input.async_type = FULL_ASYNC;
+   ad->input.check_resnorm_flag = 1;
+   ad->input.converge_test_type = LOCAL;
+   ad->input.res_compute_type = LOCAL;
+   ad->input.thread_part_distr_type = BALANCED_THREADS;
+   ad->input.num_pre_smooth_sweeps = num_pre;
+   ad->input.num_post_smooth_sweeps = num_post;
+   ad->input.num_fine_smooth_sweeps = fine_sweeps;
+   ad->input.num_coarse_smooth_sweeps = coarse_sweeps;
+   ad->input.num_threads = num_threads;
+   ad->input.smooth_weight = smooth_weight;
+   ad->input.smoother = smoother;
+   ad->input.smooth_interp_type = JACOBI;
+   ad->input.solver = solver;
+   ad->input.read_type = READ_SOL;
+   ad->input.delay_type = DELAY_NONE;
+   ad->input.construct_R_flag = 1;
+   ad->input.print_reshist_flag = 1;
+   ad->input.format_output_flag = 1;
+   ad->input.thread_part_type = (solver == MULT || solver == BPX || solver == PAR_BPX) ? ONE_LEVEL : ALL_LEVELS;
+   ad->cheby.mu = 1.0; ad->cheby.delta = 1.0;
+
+   ad->grid.num_levels = L;
+   ad->grid.n = (int *)malloc(sizeof(int) * L);
+   H->A.resize(L); H->P.resize(L); H->R.resize(L);
+   ad->matrix.A = (hypre_CSRMatrix **)malloc(sizeof(void *) * L);
+   ad->matrix.P = (hypre_CSRMatrix **)malloc(sizeof(void *) * L);
+   ad->matrix.R = (hypre_CSRMatrix **)malloc(sizeof(void *) * L);
+   ad->matrix.L1_row_norm = (double **)malloc(sizeof(double *) * L);
+   ad->matrix.A_diag = (double **)malloc(sizeof(double *) * L);
+   for (int l = 0; l < L; l++) {
+      fill(&H->A[l], A[l]);
+      ad->matrix.A[l] = &H->A[l];
+      ad->grid.n[l] = A[l].nrows;
+      ad->matrix.L1_row_norm[l] = l1[l];
+      // src/SMEM_Setup.cpp:233-238
+      ad->matrix.A_diag[l] = H->vec(A[l].nrows);
+      for (int i = 0; i < A[l].nrows; i++) ad->matrix.A_diag[l][i] = A[l].data[A[l].i[i]] / smooth_weight;
+      if (l < L - 1) {
+         fill(&H->P[l], P[l]); fill(&H->R[l], R[l]);
+         ad->matrix.P[l] = &H->P[l]; ad->matrix.R[l] = &H->R[l];
+      }
+   }
+   // hypre solver object: only the arrays SMEM_Solve.cpp:21-28 dereferences
+   H->lv.resize(3); H->pv.resize(3);
+   for (int k = 0; k < 3; k++) { H->lv[k].data = H->vec(A[0].nrows); H->lv[k].size = A[0].nrows; H->pv[k].local_vector = &H->lv[k]; }
+   H->Farr.assign(L, &H->pv[0]); H->Uarr.assign(L, &H->pv[1]);
+   H->parA.resize(L); H->Aarr.resize(L);
+   for (int l = 0; l < L; l++) { H->parA[l].diag = &H->A[l]; H->parA[l].global_num_rows = A[l].nrows; H->Aarr[l] = &H->parA[l]; }
+   H->amg.A_array = H->Aarr.data(); H->amg.P_array = nullptr; H->amg.R_array = nullptr;
+   H->amg.F_array = H->Farr.data(); H->amg.U_array = H->Uarr.data();
+   H->amg.Vtemp = &H->pv[2]; H->amg.Ztemp = &H->pv[2]; H->amg.l1_norms = (HYPRE_Real **)l1;
+   ad->hypre.solver = (HYPRE_Solver)&H->amg;
+
+   // vectors (src/SMEM_Setup.cpp:280-419)
+   VectorData *v = &ad->vector;
+   HYPRE_Real ***arrs[] = {&v->f, &v->u, &v->u_prev, &v->u_fine, &v->u_fine_prev, &v->u_coarse, &v->u_coarse_prev,
+                           &v->y, &v->r, &v->r_fine, &v->r_coarse, &v->e, &v->z};
+   for (auto a : arrs) {
+      *a = (HYPRE_Real **)calloc(L, sizeof(HYPRE_Real *));
+      for (int l = 0; l < L; l++) (*a)[l] = H->vec(A[l].nrows);
+   }
+   v->y_expand = (HYPRE_Real **)calloc(L, sizeof(HYPRE_Real *));
+   v->i.resize(L, vector<int>(0));
+   memcpy(v->f[0], f, sizeof(double) * A[0].nrows);
+   if (ad->input.thread_part_type == ALL_LEVELS) {
+      ad->level_vector = (VectorData *)calloc(L, sizeof(VectorData));
+      for (int level = 0; level < L; level++) {
+         VectorData *lv = &ad->level_vector[level];
+         HYPRE_Real ***la[] = {&lv->f, &lv->u, &lv->u_prev, &lv->u_coarse, &lv->u_coarse_prev, &lv->u_fine, &lv->u_fine_prev,
+                               &lv->y, &lv->r, &lv->r_coarse, &lv->r_fine, &lv->e, &lv->z, &lv->z1, &lv->z2};
+         for (auto a : la) {
+            *a = (HYPRE_Real **)calloc(L, sizeof(HYPRE_Real *));
+            for (int inner = 0; inner < level + 2 && inner < L; inner++) (*a)[inner] = H->vec(A[inner].nrows);
+         }
+      }
+   }
+   // src/SMEM_Setup.cpp:103-134
+   ad->barrier.local_sense = (int *)calloc(num_threads, sizeof(int));
+   ad->grid.global_smooth_flags = (int *)calloc(num_threads, sizeof(int));
+   int **gi[] = {&ad->grid.zero_flags, &ad->grid.num_smooth_wait, &ad->grid.finest_num_res_compute,
+                 &ad->grid.local_num_res_compute, &ad->grid.local_num_correct, &ad->grid.local_cycle_num_correct,
+                 &ad->grid.last_read_correct, &ad->grid.last_read_cycle_correct};
+   for (auto g : gi) *g = (int *)calloc(L, sizeof(int));
+   ad->grid.mean_grid_wait = (double *)calloc(L, sizeof(double));
+   ad->grid.max_grid_wait = (double *)calloc(L, sizeof(double));
+   ad->grid.min_grid_wait = (double *)calloc(L, sizeof(double));
+   double **od[] = {&ad->output.smooth_wtime, &ad->output.residual_wtime, &ad->output.restrict_wtime,
+                    &ad->output.prolong_wtime, &ad->output.A_matvec_wtime, &ad->output.vec_wtime, &ad->output.innerprod_wtime};
+   for (auto o : od) *o = (double *)calloc(num_threads, sizeof(double));
+   ad->output.smooth_sweeps = (int *)calloc(num_threads, sizeof(int));
+
+   // PartitionLevels, final assignment (src/SMEM_Setup.cpp:855-868 / 870-880)
+   ThreadData *th = &ad->thread;
+   th->thread_levels.resize(num_threads, vector<int>(0));
+   th->level_threads.resize(L, vector<int>(0));
+   th->barrier_flags = (int **)malloc(L * sizeof(int *));
+   th->barrier_root = (int *)malloc(L * sizeof(int));
+   th->global_barrier_flags = (int *)calloc(num_threads, sizeof(int));
+   th->loc_sum = (double *)malloc(num_threads * sizeof(double));
+   th->converge_flag = 0;
+   for (int l = 0; l < L; l++) th->barrier_flags[l] = (int *)calloc(num_threads, sizeof(int));
+   if (ad->input.thread_part_type == ALL_LEVELS) {
+      int t = 0;
+      for (int k = 0; k < L; k++) {
+         th->barrier_root[k] = t;
+         for (int tt = 0; tt < threads_per_level[k]; tt++) {
+            th->thread_levels[t].push_back(k);
+            th->level_threads[k].push_back(t);
+            th->barrier_flags[k][t] = 0;
+            if (t < num_threads - 1) t++;
+         }
+      }
+   } else {
+      for (int l = 0; l < L; l++) {
+         for (int t = 0; t < num_threads; t++) { th->thread_levels[t].push_back(l); th->level_threads[l].push_back(t); }
+         th->barrier_root[l] = 0;
+      }
+   }
+   // PartitionGrids (src/SMEM_Setup.cpp:895-1036)
+   int ***pa[] = {&th->A_ns, &th->A_ne, &th->R_ns, &th->R_ne, &th->P_ns, &th->P_ne, &th->row_ns, &th->row_ne};
+   for (auto p : pa) {
+      *p = (int **)malloc(L * sizeof(int *));
+      for (int l = 0; l < L; l++) (*p)[l] = (int *)calloc(num_threads, sizeof(int));
+   }
+   auto bound = [](hypre_CSRMatrix *M, int per, int nt, int t, int *ns, int *ne) {
+      int n = M->num_rows;
+      *ns = (t == 0) ? 0 : (int)(hypre_LowerBound(M->i, M->i + n, per * t) - M->i);
+      *ne = (t == nt - 1) ? n : (int)(hypre_LowerBound(M->i, M->i + n, per * (t + 1)) - M->i);
+   };
+   if (ad->input.thread_part_type == ALL_LEVELS) {
+      for (int level = 0; level < L; level++) {
+         int nlt = (int)th->level_threads[level].size();
+         if (nlt == 0) continue;
+         for (int inner = 0; inner < L; inner++)
+            for (int i = 0; i < nlt; i++) {
+               int t = th->level_threads[level][i];
+               int st = t - th->level_threads[level][0];
+               hypre_CSRMatrix *M = ad->matrix.A[inner];
+               bound(M, (M->num_nonzeros + nlt - 1) / nlt, nlt, st, &th->A_ns[inner][t], &th->A_ne[inner][t]);
+               if (inner < L - 1) {
+                  M = ad->matrix.P[inner];
+                  bound(M, (M->num_nonzeros + nlt - 1) / nlt, nlt, st, &th->P_ns[inner][t], &th->P_ne[inner][t]);
+                  M = ad->matrix.R[inner];
+                  bound(M, (M->num_nonzeros + nlt - 1) / nlt, nlt, st, &th->R_ns[inner][t], &th->R_ne[inner][t]);
+               }
+            }
+      }
+   } else {
+      for (int l = 0; l < L; l++) {
+         int n = ad->grid.n[l];
+         for (int t = 0; t < num_threads; t++) {
+            int size = n / num_threads, rest = n - size * num_threads;
+            if (t < rest) { th->A_ns[l][t] = t * size + t; th->A_ne[l][t] = (t + 1) * size + t + 1; }
+            else { th->A_ns[l][t] = t * size + rest; th->A_ne[l][t] = (t + 1) * size + rest; }
+         }
+      }
+   }
+   return H;
+}
+
+// Runs InitSolve + SMEM_Solve of the reference.  hist[0..num_cycles] receives the relative
+// residual after every cycle (sync); returns cycles done.  corrections[L] = local_num_correct.
+int ref_solve(void *h, int num_cycles, double tol, int async_type, int cheby_flag, double mu, double delta,
+              int precond_flag, double *u_out, double *hist, int *corrections, double *solve_seconds,
+              double *final_relres)
+{
+   RefHandle *H = (RefHandle *)h;
+   AllData *ad = &H->all;
+   ad->input.num_cycles = num_cycles;
+   ad->input.tol = tol;
+   ad->input.async_type = async_type;
+   ad->input.cheby_flag = cheby_flag;
+   ad->input.precond_flag = precond_flag;
+   ad->cheby.mu = mu; ad->cheby.delta = delta;
+   omp_set_num_threads(ad->input.num_threads);
+   InitSolve(ad);
+   g_all = ad; g_hist = hist; g_hist_cap = num_cycles + 1;
+   if (hist) for (int k = 0; k <= num_cycles; k++) hist[k] = -1.0;
+   SMEM_Solve(ad);
+   g_all = nullptr; g_hist = nullptr;
+   int done = ad->output.num_cycles;
+   if (hist && !ad->input.async_flag) { hist[0] = 1.0; hist[done] = ad->output.r_norm2 / ad->output.r0_norm2; }
+   if (u_out) memcpy(u_out, ad->vector.u[0], sizeof(double) * ad->grid.n[0]);
+   if (corrections) for (int l = 0; l < ad->grid.num_levels; l++) corrections[l] = ad->grid.local_num_correct[l];
+   if (solve_seconds) *solve_seconds = ad->output.solve_wtime;
+   if (final_relres) *final_relres = ad->output.r_norm2 / ad->output.r0_norm2;
+   return done;
+}
+
+// Deterministic (race-free) run of the reference's grouped additive cycle.  SMEM_Solve's own
+// loop (src/SMEM_Solve.cpp:128-240) starts the residual of iteration k without waiting for the
+// other level groups to finish adding their corrections of iteration k (there is no barrier
+// between SMEM_Sync_Add_Vcycle's "u += e" at src/SMEM_Sync_AMG.cpp:611-616 and
+// SMEM_Sync_Residual at src/SMEM_Solve.cpp:192), and different groups add into the same u[i]
+// without atomics.  This loop is SMEM_Solve's with ONE added "omp barrier"
+// after the cycle and async_type = SEMI_ASYNC (the reference's own lock around the update);
+// with one thread per level it is exactly the sequential specification.  The cycle, residual
+// and smoothers executed are the reference's object code.
+int ref_solve_sync_det(void *h, int num_cycles, double tol, double *u_out, double *hist)
+{
+   RefHandle *H = (RefHandle *)h;
+   AllData *ad = &H->all;
+   ad->input.num_cycles = num_cycles;
+   ad->input.tol = tol;
+   ad->input.async_type = SEMI_ASYNC;
+   ad->input.cheby_flag = 0;
+   ad->input.precond_flag = 0;
+   omp_set_num_threads(ad->input.num_threads);
+   InitSolve(ad);
+   HYPRE_Real *r = ad->vector.r[0];
+   const int n0 = ad->grid.n[0];
+#pragma omp parallel
+   {
+      SMEM_Sync_Residual(ad, ad->matrix.A[0], ad->vector.f[0], ad->vector.u[0], ad->vector.y[0], r);
+   }
+   ad->output.r0_norm2 = Parfor_Norm2(r, n0);
+   hist[0] = 1.0;
+   omp_init_lock(&ad->thread.lock);
+   double r_inner_prod = 0;
+   int done = 0;
+#pragma omp parallel
+   {
+      int tid = omp_get_thread_num();
+      for (int k = 1; k <= num_cycles; k++) {
+         SMEM_Sync_Add_Vcycle(ad);
+#pragma omp barrier
+         if (tid == 0) r_inner_prod = 0;
+         SMEM_Sync_Residual(ad, ad->matrix.A[0], ad->vector.f[0], ad->vector.u[0], ad->vector.y[0], r);
+#pragma omp for reduction(+ : r_inner_prod)
+         for (int i = 0; i < n0; i++) r_inner_prod += r[i] * r[i];
+         double r_norm2 = sqrt(r_inner_prod);
+         if (tid == 0) { done = k; hist[k] = r_norm2 / ad->output.r0_norm2; }
+#pragma omp barrier
+         if (r_norm2 / ad->output.r0_norm2 < tol) break;
+      }
+   }
+   omp_destroy_lock(&ad->thread.lock);
+   if (u_out) memcpy(u_out, ad->vector.u[0], sizeof(double) * n0);
+   return done;
+}
+
+void ref_destroy(void *h) { delete (RefHandle *)h; }
+
+// direct kernel entry points for unit parity (called SPMD over one [ns,ne) = all rows)
+void ref_matvec(const RefCSR *A, double *x, double *y)
+{
+   hypre_CSRMatrix m; fill(&m, *A);
+   SMEM_MatVec(nullptr, &m, x, y, 0, A->nrows);
+}
+void ref_seq_symmetric_jacobi(const RefCSR *A, double *f, double *u, double w, int sweeps)
+{
+   hypre_CSRMatrix m; fill(&m, *A);
+   AllData ad; ad.input.smooth_weight = w;
+   std::vector<double> y(A->nrows), r(A->nrows);
+   SEQ_SymmetricJacobi(&ad, &m, f, u, y.data(), r.data(), sweeps, 0);
+}
+void ref_seq_jacobi(const RefCSR *A, double *f, double *u, double w, int sweeps, int zero_flag)
+{
+   hypre_CSRMatrix m; fill(&m, *A);
+   AllData ad; ad.input.smooth_weight = w;
+   int zf = zero_flag; ad.grid.zero_flags = &zf;
+   std::vector<double> up(A->nrows);
+   SEQ_Jacobi(&ad, &m, f, u, up.data(), sweeps, 0);
+}
+int ref_max_threads(void) { return omp_get_max_threads(); }
+}

@@ -1,0 +1,1 @@
+#include "hypre_stub.h"

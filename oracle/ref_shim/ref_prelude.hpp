@@ -1,0 +1,21 @@
+/* ref_prelude.hpp -- force-included (-include) before every reference translation unit.
+ * src/Main.hpp is stale relative to the SMEM sources: the solve phase names
+ * matrix.A_diag, L1_HYBRID_JACOBI_GAUSS_SEIDEL and CYCLE_PHASE_DOWN/UP, none of which it
+ * declares.  The reference sources are compiled UNMODIFIED; this prelude injects the missing
+ * member through the preprocessor (the token A_diag_ext in the struct body expands to
+ * "A_diag_ext; double **A_diag") and supplies the three missing enumerators. */
+#ifndef AMG_REF_PRELUDE_HPP
+#define AMG_REF_PRELUDE_HPP
+#define A_diag_ext A_diag_ext; double **A_diag
+#include "Main.hpp"
+#undef A_diag_ext
+#define L1_HYBRID_JACOBI_GAUSS_SEIDEL 12
+#define CYCLE_PHASE_DOWN 0
+#define CYCLE_PHASE_UP 1
+/* src/SMEM_Solve.hpp:8-16 declares SMEM_Smooth with 10 parameters; the definition
+ * (src/SMEM_Solve.cpp:264-273) and every caller use 11.  Pre-empt the stale header. */
+#define SMEM_SOLVE_HPP
+void SMEM_Solve(AllData *all_data);
+void SMEM_Smooth(AllData *all_data, hypre_CSRMatrix *A, HYPRE_Real *f, HYPRE_Real *u, HYPRE_Real *y,
+                 HYPRE_Real *r, int num_sweeps, int level, int cycle_phase, int ns, int ne);
+#endif

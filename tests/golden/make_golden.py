@@ -1,0 +1,93 @@
+"""Generates tests/golden/*.npz: small hierarchies together with outputs of the REFERENCE's own
+object code (oracle/_ref/libref_smem.so, built from /root/reference/src by oracle/build_ref.sh).
+Run in the build container (needs /root/reference); the fixtures are committed so that the GPU
+box -- which has no /root/reference -- can check the oracle and the CUDA path against them.
+
+    python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import async_multigrid_b200 as amg  # noqa: E402
+from async_multigrid_b200 import hierarchy as H  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def pack(h):
+    d = {"num_levels": np.asarray(h.num_levels)}
+    for l in range(h.num_levels):
+        for nm, m in (("A", h.A[l]),) + ((("Pp", h.P_plain[l]),) if l < h.num_levels - 1 else ()):
+            d["%s%d_shape" % (nm, l)] = np.asarray(m.shape)
+            d["%s%d_indptr" % (nm, l)] = m.indptr
+            d["%s%d_indices" % (nm, l)] = m.indices
+            d["%s%d_data" % (nm, l)] = m.data
+    return d
+
+
+def main():
+    from oracle import build as obuild
+    amg.build.build_host(); obuild.build_oracle(); obuild.build_ref()
+    assert O.ref_lib() is not None, "oracle/_ref not available"
+    for name, prob, n, w in (("lap5pt_n32", "5pt", 32, 0.9), ("lap7pt_n12", "7pt", 12, 0.9)):
+        A = H.laplacian(prob, n)
+        h = H.amg_setup(A)
+        b = H.rand_rhs(A.nrows)
+        d = pack(h)
+        d["b"] = b
+        d["smooth_weight"] = np.asarray(w)
+        # reference: synchronous Multadd, symmetrised Jacobi (defaults pre=post=1), race-free run
+        h.build_transfers(H.MULTADD, w)
+        rs = O.RefSolver(h, H.MULTADD, H.JACOBI, b, w, one_thread_per_level=True)
+        out = rs.solve_sync_det(100, 1e-9)
+        d["multadd_symj_hist"] = out["hist"]
+        d["multadd_symj_u"] = out["u"]
+        rs.close()
+        # reference: Multadd with plain Jacobi (post sweeps = 0: only R is smoothed)
+        h.build_transfers(H.MULTADD, w, num_pre=1, num_post=0)
+        rs = O.RefSolver(h, H.MULTADD, H.JACOBI, b, w, num_pre=1, num_post=0, one_thread_per_level=True)
+        out = rs.solve_sync_det(60, 1e-9)
+        d["multadd_j_hist"] = out["hist"]
+        rs.close()
+        # reference: L1-Jacobi symmetrised
+        h.build_transfers(H.MULTADD, w, smooth_interp_type=H.L1_JACOBI)
+        rs = O.RefSolver(h, H.MULTADD, H.L1_JACOBI, b, w, one_thread_per_level=True)
+        out = rs.solve_sync_det(100, 1e-9)
+        d["multadd_syml1_hist"] = out["hist"]
+        rs.close()
+        # reference: AFACx (grouped cycle), weight 0.6
+        h.build_transfers(H.AFACX, 0.6)
+        rs = O.RefSolver(h, H.AFACX, H.JACOBI, b, 0.6, one_thread_per_level=True)
+        out = rs.solve_sync_det(40, 1e-9)
+        d["afacx_j_hist"] = out["hist"]
+        rs.close()
+        # reference: BPX through SMEM_Solve itself (omp-for cycle, deterministic), 4 threads, 10 cycles
+        rs = O.RefSolver(h, H.BPX, H.JACOBI, b, 0.6, num_threads=4)
+        out = rs.solve(10, 1e-30, async_type=0)
+        d["bpx_j_hist"] = out["hist"]
+        rs.close()
+        # reference kernels: SMEM_MatVec and the sequential smoothers on level 0
+        x = np.cos(np.arange(A.nrows) * 0.37)
+        y = np.zeros(A.nrows)
+        import ctypes as C
+        s = O.c_csr(h.A[0])
+        O.ref_lib().ref_matvec(C.byref(s), O.dptr(x), O.dptr(y))
+        d["x"] = x
+        d["matvec_A0_x"] = y
+        u = np.zeros(A.nrows)
+        O.ref_lib().ref_seq_symmetric_jacobi(C.byref(s), O.dptr(b.copy()), O.dptr(u), w, 1)
+        d["seq_symj_b"] = u
+        u = np.zeros(A.nrows)
+        O.ref_lib().ref_seq_jacobi(C.byref(s), O.dptr(b.copy()), O.dptr(u), w, 3, 1)
+        d["seq_j3_b"] = u
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+        print(name, {k: (v.shape if hasattr(v, "shape") else v) for k, v in d.items() if "hist" in k})
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,345 @@
+"""GPU parity tests: the sm_100a kernels, called through the C ABI (libamg_b200.so via
+async-multigrid_b200/solver.py), against the CPU oracle on the same seeded inputs and against the
+committed reference-object fixtures.  fp64 everywhere.
+
+Tolerances (stated per test):
+  * single operators (SpMV, smoothers, one cycle): summation order differs from the CPU loop, so
+    results agree to a few ulp of the accumulated magnitude: |gpu - cpu| <= 1e-13 * scale;
+  * synchronous solve history: |relres_gpu[k] - relres_ref[k]| <= 1e-10 (conftest.HIST_TOL) and the
+    same iteration count;
+  * asynchronous solves: ||f - A u|| / ||r0|| < 1e-9 checked with the ORACLE's residual on the
+    returned u, per-level correction counts reported.
+"""
+import numpy as np
+import pytest
+
+import async_multigrid_b200 as amg
+from async_multigrid_b200 import hierarchy as H
+from conftest import HIST_TOL, hierarchy_from_golden
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+MAT_A, MAT_P, MAT_R = 0, 1, 2
+
+
+def _problem(prob, n, solver=H.MULTADD, w=0.9, **kw):
+    A = H.laplacian(prob, n)
+    h = H.amg_setup(A)
+    h.build_transfers(solver, w, **kw)
+    return h, H.rand_rhs(A.nrows)
+
+
+def _rel(a, b, scale=None):
+    scale = np.max(np.abs(b)) if scale is None else scale
+    return np.max(np.abs(a - b)) / max(scale, 1e-300)
+
+
+# ---- SpGEMV -----------------------------------------------------------------------------------
+@pytest.mark.parametrize("prob,n", [("5pt", 40), ("7pt", 14), ("27pt", 9)])
+@pytest.mark.parametrize("use_sell", [True, False])
+def test_spgemv_matches_oracle(prob, n, use_sell):
+    h, b = _problem(prob, n)
+    s = amg.Solver(h, H.MULTADD, H.JACOBI, 0.9, use_sell=use_sell)
+    rng = np.random.default_rng(1)
+    for kind, mats in ((MAT_A, h.A), (MAT_P, h.P), (MAT_R, h.R)):
+        for l, m in enumerate(mats):
+            x = rng.uniform(-1, 1, m.ncols)
+            bb = rng.uniform(-1, 1, m.nrows)
+            for alpha, beta in ((1.0, 0.0), (-1.0, 1.0), (1.0, 1.0), (2.5, -0.5)):
+                got = s.spgemv(kind, l, alpha, x, beta, bb if beta != 0 else None)
+                want = O.spgemv(m, x, bb, alpha, beta)
+                mag = O.spgemv(H.CSR(m.nrows, m.ncols, m.indptr, m.indices, np.abs(m.data)), np.abs(x), np.abs(bb), abs(alpha), abs(beta))
+                assert np.max(np.abs(got - want) / np.maximum(mag, 1e-300)) <= 1e-13, (kind, l, alpha, beta)
+    if use_sell and h.n[0] >= 1024:
+        assert s.is_sell(MAT_A, 0)
+    s.close()
+
+
+def test_spgemv_ragged_and_empty_rows():
+    """rows of very different length, empty rows, one dense row: the vector-per-row kernel's tail paths"""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(3)
+    n = 1500
+    M = sp.random(n, n, density=0.004, random_state=4, format="lil")
+    M[7, :] = rng.uniform(-1, 1, n)          # dense row
+    M[11, :] = 0                              # empty row (no diagonal either)
+    M = (M + sp.eye(n)).tolil()
+    M[11, 11] = 0
+    M = M.tocsr()
+    M.eliminate_zeros()
+    A = H.CSR.from_scipy(M)
+    # upload as a transfer operator (no diag-first requirement) of a 2-level dummy hierarchy
+    A0 = H.laplacian("5pt", 40)               # 1600 rows
+    P = H.CSR.from_scipy(sp.random(1600, n, density=0.002, random_state=5, format="csr") + sp.eye(1600, n))
+    h = H.Hierarchy([A0, H.CSR.from_scipy(sp.eye(n, format="csr") * 2.0, diag_first=True)], [P])
+    h.P, h.R = [P], [A]                       # "R" carries the ragged matrix (n x 1600 needed)
+    R = H.CSR.from_scipy(sp.hstack([M, sp.csr_matrix((n, 100))]).tocsr())
+    h.R = [R]
+    s = amg.Solver(h, H.AFACX, H.JACOBI, 1.0)
+    x = rng.uniform(-1, 1, 1600)
+    got = s.spgemv(MAT_R, 0, 1.0, x)
+    want = O.spgemv(R, x, None, 1.0, 0.0)
+    assert _rel(got, want) <= 1e-13
+    assert got[11] == 0.0
+    s.close()
+
+
+# ---- smoothers -------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prob,n", [("5pt", 40), ("7pt", 13)])
+def test_jacobi_family_matches_oracle(prob, n):
+    h, b = _problem(prob, n)
+    l1 = h.l1_norms()
+    for smoother, kind in ((H.JACOBI, "jacobi"), (H.L1_JACOBI, "l1_jacobi")):
+        s = amg.Solver(h, H.MULTADD, smoother, 0.9)
+        for l in range(min(3, h.num_levels)):
+            f = H.rand_rhs(h.n[l], seed=l + 1)
+            for sweeps in (1, 2, 3):
+                got = s.smooth(l, f, sweeps=sweeps, symmetric=False, zero_guess=True)
+                want = O.smooth(kind, h.A[l], f, w=0.9, sweeps=sweeps, zero_flag=1, l1=l1[l])
+                assert _rel(got, want) <= 1e-13, (kind, l, sweeps)
+            got = s.smooth(l, f, sweeps=1, symmetric=True, zero_guess=True)
+            want = O.smooth("symmetric_" + kind, h.A[l], f, w=0.9, sweeps=1, zero_flag=1, l1=l1[l])
+            assert _rel(got, want) <= 1e-13, ("symmetric", kind, l)
+            got = s.smooth(l, f, sweeps=2, symmetric=True, zero_guess=True)
+            want = O.smooth("symmetric_" + kind, h.A[l], f, w=0.9, sweeps=2, zero_flag=1, l1=l1[l])
+            assert _rel(got, want) <= 1e-13, ("symmetric x2", kind, l)
+            u0 = np.sin(np.arange(h.n[l]))
+            got = s.smooth(l, f, sweeps=2, symmetric=False, zero_guess=False, u0=u0)
+            want = O.smooth(kind, h.A[l], f, w=0.9, sweeps=2, zero_flag=0, u0=u0, l1=l1[l])
+            assert _rel(got, want) <= 1e-13, ("general", kind, l)
+        s.close()
+
+
+@pytest.mark.parametrize("block_rows", [1, 8, 37])
+def test_hybrid_jgs_matches_oracle(block_rows):
+    h, b = _problem("7pt", 13)
+    s = amg.Solver(h, H.MULTADD, H.HYBRID_JACOBI_GAUSS_SEIDEL, 0.9, jgs_block_rows=block_rows)
+    for l in range(min(3, h.num_levels)):
+        f = H.rand_rhs(h.n[l], seed=7)
+        blocks = H.uniform_blocks(h.n[l], block_rows)
+        for sweeps in (1, 2):
+            got = s.smooth(l, f, sweeps=sweeps, zero_guess=True)
+            want = O.smooth("hybrid_jgs", h.A[l], f, sweeps=sweeps, zero_flag=1, blocks=blocks)
+            assert _rel(got, want) <= 1e-13, (l, sweeps)
+        u0 = np.cos(np.arange(h.n[l]))
+        got = s.smooth(l, f, sweeps=1, zero_guess=False, u0=u0)
+        want = O.smooth("hybrid_jgs", h.A[l], f, sweeps=1, zero_flag=0, u0=u0, blocks=blocks)
+        assert _rel(got, want) <= 1e-13
+    s.close()
+
+
+def test_norm2():
+    h, b = _problem("5pt", 40)
+    s = amg.Solver(h)
+    assert abs(s.norm2(b) - O.norm2(b)) <= 1e-13 * O.norm2(b)
+    assert s.norm2(np.zeros(5)) == 0.0
+    s.close()
+
+
+# ---- one cycle ------------------------------------------------------------------------------------------
+CYCLES = [
+    (H.MULTADD, H.JACOBI, dict()),                                  # symmetrised Jacobi, smoothed P and R
+    (H.MULTADD, H.JACOBI, dict(num_pre=1, num_post=0)),             # plain Jacobi, only R smoothed
+    (H.MULTADD, H.L1_JACOBI, dict(smooth_interp_type=H.L1_JACOBI)),
+    (H.MULTADD, H.HYBRID_JACOBI_GAUSS_SEIDEL, dict()),
+    (H.AFACX, H.JACOBI, dict()),
+    (H.AFACX, H.HYBRID_JACOBI_GAUSS_SEIDEL, dict()),
+    (H.BPX, H.JACOBI, dict()),
+    (H.BPX, H.L1_JACOBI, dict()),
+]
+
+
+@pytest.mark.parametrize("solver,smoother,kw", CYCLES)
+@pytest.mark.parametrize("prob,n", [("5pt", 48), ("7pt", 14)])
+def test_cycle_matches_oracle(prob, n, solver, smoother, kw):
+    w = 0.8
+    h, b = _problem(prob, n, solver, w, **kw)
+    pre, post = kw.get("num_pre", 1), kw.get("num_post", 1)
+    blocks = [H.uniform_blocks(m, 8) for m in h.n]
+    pb = O.Problem(h, solver, smoother, w, num_pre=pre, num_post=post, jgs_blocks=blocks)
+    s = amg.Solver(h, solver, smoother, w, num_pre=pre, num_post=post, jgs_block_rows=8)
+    want = pb.cycle(b)
+    got = s.cycle(b)
+    assert _rel(got, want) <= 1e-12
+    # linearity of the cycle operator: B(a r1 + c r2) = a B r1 + c B r2
+    r2 = np.cos(np.arange(h.n[0]) * 0.1)
+    lhs = s.cycle(2.0 * b - 3.0 * r2)
+    rhs = 2.0 * got - 3.0 * s.cycle(r2)
+    assert _rel(lhs, rhs) <= 1e-12
+    s.close()
+
+
+def test_two_sweeps_and_single_level():
+    h, b = _problem("5pt", 40)
+    for fs in (2, 3):
+        pb = O.Problem(h, H.MULTADD, H.JACOBI, 0.9, num_pre=1, num_post=0, fine_sweeps=fs)
+        h.build_transfers(H.MULTADD, 0.9, num_pre=1, num_post=0)
+        s = amg.Solver(h, H.MULTADD, H.JACOBI, 0.9, num_pre=1, num_post=0, fine_sweeps=fs)
+        assert _rel(s.cycle(b), pb.cycle(b)) <= 1e-12
+        s.close()
+    # a one-level "hierarchy": additive cycles contribute nothing, BPX smooths the only level
+    A = H.laplacian("5pt", 8)
+    h1 = H.Hierarchy([A], [])
+    h1.P, h1.R = [], []
+    s = amg.Solver(h1, H.MULTADD, H.JACOBI, 0.9)
+    f = H.rand_rhs(A.nrows)
+    assert np.all(s.cycle(f) == 0.0)
+    s.close()
+    s = amg.Solver(h1, H.BPX, H.JACOBI, 0.9)
+    assert _rel(s.cycle(f), 0.9 * f / 4.0) <= 1e-15
+    s.close()
+
+
+# ---- synchronous solves: per-iteration relative-residual history -----------------------------------------
+def _check_hist(got, want):
+    assert len(got) == len(want), (len(got), len(want))
+    assert np.max(np.abs(got - want)) <= HIST_TOL, np.max(np.abs(got - want))
+
+
+@pytest.mark.parametrize("name", ["lap5pt_n32", "lap7pt_n12"])
+def test_sync_history_matches_reference_fixture(name):
+    """histories recorded from the reference's own object code (tests/golden/make_golden.py)"""
+    h, d = hierarchy_from_golden(name)
+    w = float(d["smooth_weight"])
+    h.build_transfers(H.MULTADD, w)
+    s = amg.Solver(h, H.MULTADD, H.JACOBI, w)
+    out = s.SMEM_Solve(d["b"], 1e-9, 100)
+    _check_hist(out["hist"], d["multadd_symj_hist"])
+    assert _rel(out["u"], d["multadd_symj_u"]) <= 1e-12
+    assert list(out["corrections"]) == [out["cycles"]] * h.num_levels
+    s.close()
+    h.build_transfers(H.MULTADD, w, num_pre=1, num_post=0)
+    s = amg.Solver(h, H.MULTADD, H.JACOBI, w, num_pre=1, num_post=0)
+    _check_hist(s.SMEM_Solve(d["b"], 1e-9, 60)["hist"], d["multadd_j_hist"])
+    s.close()
+    h.build_transfers(H.MULTADD, w, smooth_interp_type=H.L1_JACOBI)
+    s = amg.Solver(h, H.MULTADD, H.L1_JACOBI, w)
+    _check_hist(s.SMEM_Solve(d["b"], 1e-9, 100)["hist"], d["multadd_syml1_hist"])
+    s.close()
+    h.build_transfers(H.AFACX, 0.6)
+    s = amg.Solver(h, H.AFACX, H.JACOBI, 0.6)
+    _check_hist(s.SMEM_Solve(d["b"], 1e-9, 40)["hist"], d["afacx_j_hist"])
+    s.close()
+    s = amg.Solver(h, H.BPX, H.JACOBI, 0.6)
+    got = s.SMEM_Solve(d["b"], 1e-30, 10)["hist"]
+    assert np.max(np.abs(got - d["bpx_j_hist"]) / d["bpx_j_hist"]) <= 1e-10
+    s.close()
+
+
+@pytest.mark.parametrize("prob,n,solver,smoother,w", [
+    ("5pt", 128, H.MULTADD, H.JACOBI, 0.9),          # config 1 family (2-D 5-pt, weighted Jacobi)
+    ("7pt", 32, H.MULTADD, H.JACOBI, 0.9),
+    ("7pt", 32, H.MULTADD, H.HYBRID_JACOBI_GAUSS_SEIDEL, 1.0),
+    ("27pt", 20, H.MULTADD, H.JACOBI, 0.9),
+    ("7pt", 24, H.AFACX, H.JACOBI, 0.6),
+])
+def test_sync_history_matches_oracle(prob, n, solver, smoother, w):
+    h, b = _problem(prob, n, solver, w)
+    blocks = [H.uniform_blocks(m, 8) for m in h.n]
+    _, want, _ = O.Problem(h, solver, smoother, w, jgs_blocks=blocks).solve_sync(b, 1e-9, 120)
+    s = amg.Solver(h, solver, smoother, w, jgs_block_rows=8)
+    s.set_rhs(b)
+    s.set_solution(None)
+    got, secs = s.solve_sync(1e-9, 120)
+    _check_hist(got, want)
+    if solver == H.MULTADD:
+        assert got[-1] < 1e-9
+    # the reported residual is the true one: recompute ||f - A u|| with the oracle on the returned u
+    u = s.get_solution()
+    true = O.norm2(O.spgemv(h.A[0], u, b, -1.0, 1.0)) / O.norm2(b)
+    assert abs(true - got[-1]) <= 1e-12
+    s.close()
+
+
+def test_chebyshev_accelerated_bpx_matches_oracle():
+    h, b = _problem("7pt", 20, H.BPX, 0.8)
+    # eigenvalue bounds of the BPX-preconditioned operator are an INPUT (ChebySetup is host-side)
+    alpha, beta = 0.3, 6.0
+    mu, delta = (beta + alpha) / (beta - alpha), 2.0 / (beta + alpha)
+    _, want, _ = O.Problem(h, H.BPX, H.JACOBI, 0.8).solve_sync(b, 1e-9, 60, cheby=(mu, delta))
+    s = amg.Solver(h, H.BPX, H.JACOBI, 0.8)
+    s.set_rhs(b)
+    s.set_solution(None)
+    got, _ = s.solve_sync(1e-9, 60, cheby=(mu, delta))
+    assert len(got) == len(want)
+    assert np.max(np.abs(got - want) / want) <= 1e-9
+    s.close()
+
+
+# ---- asynchronous solves --------------------------------------------------------------------------------
+@pytest.mark.parametrize("solver,smoother,w,cycles", [
+    (H.ASYNC_MULTADD, H.JACOBI, 0.9, 80),
+    (H.ASYNC_MULTADD, H.HYBRID_JACOBI_GAUSS_SEIDEL, 1.0, 80),
+    (H.ASYNC_AFACX, H.JACOBI, 0.5, 150),
+])
+def test_async_reaches_tolerance(solver, smoother, w, cycles):
+    h, b = _problem("7pt", 32, H.MULTADD if solver == H.ASYNC_MULTADD else H.AFACX, w)
+    s = amg.Solver(h, solver, smoother, w, jgs_block_rows=8)
+    out = s.SMEM_Solve(b, 1e-9, cycles)
+    # LOCAL stop rule: every level did exactly num_cycles corrections (src/SMEM_Async_AMG.cpp:317-322)
+    assert list(out["corrections"]) == [cycles] * h.num_levels
+    true = O.norm2(O.spgemv(h.A[0], out["u"], b, -1.0, 1.0)) / O.norm2(b)
+    assert abs(true - out["relres"]) <= 1e-12
+    assert true < 1e-9, true
+    print("async", solver, smoother, "relres", true, "corrections", list(out["corrections"]), "s", out["seconds"])
+    s.close()
+
+
+def test_async_global_stop_rule_and_groups():
+    h, b = _problem("7pt", 32, H.MULTADD, 0.9)
+    s = amg.Solver(h, H.ASYNC_MULTADD, H.JACOBI, 0.9)
+    cb, grid = s.async_groups()
+    assert cb[0] == 0 and cb[-1] == grid and np.all(np.diff(cb) >= 1)
+    s.set_rhs(b)
+    s.set_solution(None)
+    corr, rel, secs = s.solve_async(60, amg.solver.CONVERGE_GLOBAL)
+    assert np.all(corr >= 60)
+    assert rel < 1e-9
+    s.close()
+
+
+def test_async_single_group_equals_sequential_model():
+    """with ONE level below the coarsest (2-level hierarchy) there is a single working group, so the
+    asynchronous iteration is deterministic and equals the sequential model"""
+    A = H.laplacian("5pt", 24)
+    h = H.amg_setup(A, max_levels=2)
+    h.build_transfers(H.MULTADD, 0.9)
+    b = H.rand_rhs(A.nrows)
+    s = amg.Solver(h, H.ASYNC_MULTADD, H.JACOBI, 0.9)
+    out = s.SMEM_Solve(b, 1e-9, 25)
+    u, counts, rel = O.Problem(h, H.MULTADD, H.JACOBI, 0.9).solve_async_sequential(b, 25)
+    assert _rel(out["u"], u) <= 1e-11
+    assert abs(out["relres"] - rel) <= 1e-10
+    s.close()
+
+
+# ---- API behaviour ----------------------------------------------------------------------------------------
+def test_error_codes():
+    import ctypes as C
+    lib = amg.solver.load_library()
+    ctx = C.c_void_p()
+    assert lib.amgb_create(C.byref(ctx), 0) == 0
+    assert lib.amgb_setup(ctx) != 0                       # no hierarchy yet
+    assert lib.amgb_set_num_levels(ctx, 0) != 0
+    assert lib.amgb_set_num_levels(ctx, 2) == 0
+    A = H.laplacian("5pt", 4)
+    bad = A.indices.copy()
+    bad[0], bad[1] = bad[1], bad[0]                       # not diagonal-first
+    rc = lib.amgb_set_matrix(ctx, 0, 0, A.nrows, A.ncols, A.nnz, A.indptr.ctypes.data_as(amg.solver.IP),
+                             bad.ctypes.data_as(amg.solver.IP), A.data.ctypes.data_as(amg.solver.DP))
+    assert rc != 0 and b"diagonal-first" in lib.amgb_last_error(ctx)
+    assert lib.amgb_set_rhs(ctx, None) != 0               # setup not done
+    assert lib.amgb_destroy(ctx) == 0
+    assert lib.amgb_create(C.byref(ctx), 999) != 0
+
+
+def test_launch_counter_counts_graph_replays():
+    h, b = _problem("5pt", 40)
+    s = amg.Solver(h, H.MULTADD, H.JACOBI, 0.9)
+    n0 = s.launch_count()
+    out = s.SMEM_Solve(b, 1e-9, 100)
+    per_iter = (s.launch_count() - n0 - 2) / out["cycles"]
+    # restrictions + smoothers + Horner prolongations + residual + reduce
+    assert per_iter >= 2 * (h.num_levels - 2) + 2
+    s.close()

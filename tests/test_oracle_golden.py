@@ -1,0 +1,118 @@
+"""CPU: the oracle restatement (oracle/amg_oracle.c) against outputs of the reference's own object
+code (committed fixtures, and live oracle/_ref when it is present)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import HIST_TOL
+from async_multigrid_b200 import hierarchy as H
+from oracle import oracle as O
+
+
+def _close_hist(a, b):
+    assert len(a) == len(b), (len(a), len(b))
+    assert np.max(np.abs(np.asarray(a) - np.asarray(b))) <= HIST_TOL
+
+
+def test_multadd_symmetric_jacobi_history(golden):
+    h, d = golden
+    w = float(d["smooth_weight"])
+    h.build_transfers(H.MULTADD, w)
+    u, hist, _ = O.Problem(h, H.MULTADD, H.JACOBI, w).solve_sync(d["b"], 1e-9, 100)
+    _close_hist(hist, d["multadd_symj_hist"])
+    assert np.max(np.abs(u - d["multadd_symj_u"])) <= 1e-12 * np.max(np.abs(u))
+
+
+def test_multadd_plain_jacobi_history(golden):
+    h, d = golden
+    w = float(d["smooth_weight"])
+    h.build_transfers(H.MULTADD, w, num_pre=1, num_post=0)
+    _, hist, _ = O.Problem(h, H.MULTADD, H.JACOBI, w, num_pre=1, num_post=0).solve_sync(d["b"], 1e-9, 60)
+    _close_hist(hist, d["multadd_j_hist"])
+
+
+def test_multadd_symmetric_l1_history(golden):
+    h, d = golden
+    w = float(d["smooth_weight"])
+    h.build_transfers(H.MULTADD, w, smooth_interp_type=H.L1_JACOBI)
+    _, hist, _ = O.Problem(h, H.MULTADD, H.L1_JACOBI, w).solve_sync(d["b"], 1e-9, 100)
+    _close_hist(hist, d["multadd_syml1_hist"])
+
+
+def test_afacx_history(golden):
+    h, d = golden
+    h.build_transfers(H.AFACX, 0.6)
+    _, hist, _ = O.Problem(h, H.AFACX, H.JACOBI, 0.6).solve_sync(d["b"], 1e-9, 40)
+    _close_hist(hist, d["afacx_j_hist"])
+
+
+def test_bpx_history(golden):
+    h, d = golden
+    h.build_transfers(H.AFACX, 0.6)
+    _, hist, _ = O.Problem(h, H.BPX, H.JACOBI, 0.6).solve_sync(d["b"], 1e-30, 10)
+    ref = d["bpx_j_hist"]
+    assert len(hist) == len(ref)
+    # BPX is not a convergent stationary iteration: compare relative to the growing residual
+    assert np.max(np.abs(hist - ref) / ref) <= 1e-10
+
+
+def test_kernels_against_reference_objects(golden):
+    h, d = golden
+    w = float(d["smooth_weight"])
+    y = O.spgemv(h.A[0], d["x"], None, 1.0, 0.0)
+    assert np.max(np.abs(y - d["matvec_A0_x"])) == 0.0      # same loop order -> bit-identical
+    u = O.smooth("symmetric_jacobi", h.A[0], d["b"], w=w, sweeps=1, zero_flag=1)
+    assert np.max(np.abs(u - d["seq_symj_b"])) <= 1e-15 * np.max(np.abs(u))
+    u = O.smooth("jacobi", h.A[0], d["b"], w=w, sweeps=3, zero_flag=1)
+    assert np.max(np.abs(u - d["seq_j3_b"])) <= 1e-15 * np.max(np.abs(u))
+
+
+@pytest.mark.skipif(O.ref_lib() is None, reason="oracle/_ref not built (needs /root/reference)")
+def test_live_reference_objects_match_oracle():
+    A = H.laplacian("5pt", 24)
+    h = H.amg_setup(A)
+    b = H.rand_rhs(A.nrows)
+    h.build_transfers(H.MULTADD, 0.8)
+    rs = O.RefSolver(h, H.MULTADD, H.JACOBI, b, 0.8, one_thread_per_level=True)
+    if rs.num_threads > O.ref_lib().ref_max_threads():
+        pytest.skip("more levels than cores: the reference's spin barriers would oversubscribe")
+    out = rs.solve_sync_det(50, 1e-9)
+    rs.close()
+    _, hist, _ = O.Problem(h, H.MULTADD, H.JACOBI, 0.8).solve_sync(b, 1e-9, 50)
+    _close_hist(hist, out["hist"])
+
+
+def test_hybrid_jgs_block_semantics():
+    """block GS == plain Gauss-Seidel when one block covers everything; == Jacobi (w=1) for 1-row blocks"""
+    A = H.laplacian("7pt", 6)
+    f = H.rand_rhs(A.nrows)
+    n = A.nrows
+    gs = O.smooth("hybrid_jgs", A, f, sweeps=1, zero_flag=1, blocks=np.asarray([0, n], dtype=np.int32))
+    S = A.to_scipy()
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as sla
+    ref = sla.spsolve_triangular(sp.tril(S).tocsr(), f)
+    assert np.max(np.abs(gs - ref)) <= 1e-13
+    jac = O.smooth("hybrid_jgs", A, f, sweeps=1, zero_flag=1, blocks=np.arange(n + 1, dtype=np.int32))
+    assert np.max(np.abs(jac - f / A.diagonal())) <= 1e-15
+    # second sweep, 4-row blocks, against a direct numpy transcription
+    blocks = H.uniform_blocks(n, 4)
+    got = O.smooth("hybrid_jgs", A, f, sweeps=2, zero_flag=1, blocks=blocks)
+    D = S.toarray()
+    u = np.zeros(n)
+    for k in range(2):
+        up = u.copy()
+        for b in range(len(blocks) - 1):
+            ns, ne = blocks[b], blocks[b + 1]
+            if k == 0:
+                u[ns:ne] = 0
+            for i in range(ns, ne):
+                res = f[i]
+                for j in np.nonzero(D[i])[0]:
+                    if ns <= j < ne:
+                        res -= D[i, j] * u[j]
+                    elif k > 0:
+                        res -= D[i, j] * up[j]
+                u[i] = res / D[i, i] if k == 0 else u[i] + res / D[i, i]
+    assert np.max(np.abs(got - u)) <= 1e-13
