@@ -24,7 +24,13 @@ struct DevCSR {
    const double *sell_va = nullptr;
    const double *sell_sval = nullptr;
    int lpr = 8;                      // lanes per row chosen for the CSR vector kernel
+   // CSR-stream row blocks: CTA b owns rows [blk[b], blk[b+1]) whose entries (<= AMGB_STREAM_CAP,
+   // counted from the 4-aligned start) are streamed with 128-bit loads into shared memory and then
+   // reduced per row; a block made of ONE longer row is reduced by the whole CTA.
+   int nblk = 0;
+   const int *blk = nullptr;
 };
+#define AMGB_STREAM_CAP 2048
 
 // y_i = gamma*c_i + rs_i * (beta*b_i + alpha * sum_j M_ij x_j)       (rs == nullptr -> 1)
 // covers: MatVec (alpha=1), Residual (alpha=-1,beta=1,b=f), prolong-and-add (beta=1,b=y),
@@ -48,6 +54,19 @@ __device__ __forceinline__ int ld_stream(const int *p)
 {
    int v;
    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+   return v;
+}
+// 128-bit streaming loads (4 column indices / 2 values per instruction), 16-byte aligned
+__device__ __forceinline__ int4 ld_stream4(const int *p)
+{
+   int4 v;
+   asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+   return v;
+}
+__device__ __forceinline__ double2 ld_stream2(const double *p)
+{
+   double2 v;
+   asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
    return v;
 }
 // coherent (L2) load for vectors that other CTA groups update concurrently inside the persistent

@@ -32,7 +32,7 @@ template <class T>
 static int dev_alloc(amgb_ctx *c, T **p, size_t n)
 {
    *p = nullptr;
-   if (n == 0) n = 1;
+   n += 8;   // slack: the 128-bit group loads of the CSR-stream kernel may touch up to 3 elements past the end
    cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
    if (e != cudaSuccess) return amgb_fail(c, AMGB_ENOMEM, "cudaMalloc(%zu bytes): %s", n * sizeof(T), cudaGetErrorString(e));
    c->allocs.push_back((void *)*p);
@@ -80,6 +80,7 @@ void amgb_default_options(amgb_options *o)
    o->jgs_block_rows = 8;
    o->use_sell = 1;
    o->l2_persist = 1;
+   o->use_stream = 1;
 }
 
 int amgb_create(amgb_ctx **out, int device)
@@ -197,6 +198,31 @@ static int build_sell(amgb_ctx *c, DevCSR &M, int nrows, const int *rp, const in
    return AMGB_OK;
 }
 
+// Row blocks of the CSR-stream kernel: consecutive rows whose entries, counted from the 4-aligned
+// start of the block, fit AMGB_STREAM_CAP (and at most AMGB_STREAM_CAP rows); a longer row is a
+// block of its own.
+static int build_stream_blocks(amgb_ctx *c, DevCSR &M, int nrows, const int *rp)
+{
+   std::vector<int> blk;
+   blk.reserve((size_t)rp[nrows] / 1024 + 16);
+   blk.push_back(0);
+   int r = 0;
+   while (r < nrows) {
+      const int start = r;
+      const long q0 = rp[start] & ~3;
+      while (r < nrows && r - start < AMGB_STREAM_CAP && (long)rp[r + 1] - q0 <= AMGB_STREAM_CAP) r++;
+      if (r == start) r++;
+      blk.push_back(r);
+   }
+   int *d_blk;
+   int rc;
+   if ((rc = dev_upload(c, &d_blk, blk.data(), blk.size()))) return rc;
+   CUDA_OK(c, cudaStreamSynchronize(c->stream));
+   M.nblk = (int)blk.size() - 1;
+   M.blk = d_blk;
+   return AMGB_OK;
+}
+
 int amgb_set_matrix(amgb_ctx *c, int kind, int level, int nrows, int ncols, int nnz,
                     const int *rp, const int *ci, const double *va)
 {
@@ -224,6 +250,9 @@ int amgb_set_matrix(amgb_ctx *c, int kind, int level, int nrows, int ncols, int 
    CUDA_OK(c, cudaStreamSynchronize(c->stream));
    if (c->opt.use_sell && nrows >= 1024) {
       if ((rc = build_sell(c, M, nrows, rp, ci, va))) return rc;
+   }
+   if (c->opt.use_stream && M.sell_slices == 0 && nrows > 0) {
+      if ((rc = build_stream_blocks(c, M, nrows, rp))) return rc;
    }
    return AMGB_OK;
 }

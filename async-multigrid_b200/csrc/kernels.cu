@@ -12,13 +12,21 @@ namespace {
 
 constexpr int kBlock = 256;
 
-template <bool SVAL>
+// One kernel per storage scheme (separate register budgets): MODE 0 = vector-per-row CSR,
+// 1 = sliced ELL (stencil levels), 2 = CSR-stream (row blocks through shared memory).
+template <int MODE, bool SVAL>
 __global__ void __launch_bounds__(kBlock) k_spmv(DevCSR M, const double *x, double *y, SpmvEpilogue e, double *partials)
 {
    const int tid = blockIdx.x * kBlock + threadIdx.x;
    const int tsz = gridDim.x * kBlock;
-   double ss = spmv_team<true, SVAL>(M, x, y, e, tid, tsz, partials != nullptr);
-   if (partials) {
+   const bool norm = partials != nullptr;
+   double ss;
+   if (MODE == 1) ss = sell_rows_team<true, SVAL>(M, x, y, e, tid, tsz, norm);
+   else if (MODE == 2) {
+      __shared__ __align__(16) double sprod[AMGB_STREAM_CAP];
+      ss = stream_rows_team<true, SVAL>(M, x, y, e, blockIdx.x, gridDim.x, sprod, norm);
+   } else ss = csr_rows_dispatch<true, SVAL>(M, x, y, e, tid, tsz, norm);
+   if (norm) {
       ss = block_sum(ss);
       if (threadIdx.x == 0) partials[blockIdx.x] = ss;
    }
@@ -102,14 +110,37 @@ inline int grid_for(const LaunchCfg &cfg, long work_threads)
 
 }  // namespace
 
+template <int MODE, bool SVAL>
+static int resident_grid(const LaunchCfg &cfg)
+{
+   static int per_sm = 0;   // co-resident CTAs per SM of this instantiation: grids are sized to exactly one wave
+   if (per_sm == 0) {
+      int v = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_spmv<MODE, SVAL>, kBlock, 0) != cudaSuccess || v < 1) v = 4;
+      per_sm = v;
+   }
+   return cfg.num_sms * per_sm;
+}
+
+template <int MODE>
+static int launch_spmv_mode(const LaunchCfg &cfg, cudaStream_t st, const DevCSR &M, bool use_sval, const double *x, double *y,
+                            const SpmvEpilogue &e, double *partials, long ctas_of_work)
+{
+   const int cap = use_sval ? resident_grid<MODE, true>(cfg) : resident_grid<MODE, false>(cfg);
+   const int grid = (int)std::max(1L, std::min(ctas_of_work, (long)cap));
+   if (use_sval) k_spmv<MODE, true><<<grid, kBlock, 0, st>>>(M, x, y, e, partials);
+   else k_spmv<MODE, false><<<grid, kBlock, 0, st>>>(M, x, y, e, partials);
+   return grid;
+}
+
 int launch_spmv(const LaunchCfg &cfg, cudaStream_t st, const DevCSR &M, bool use_sval, const double *x, double *y,
                 const SpmvEpilogue &e, double *partials, int *grid_out)
 {
-   long threads = M.sell_slices > 0 ? (long)M.sell_slices * 32 : (long)M.nrows * M.lpr;
-   int grid = grid_for(cfg, threads);
+   int grid;
+   if (M.sell_slices > 0) grid = launch_spmv_mode<1>(cfg, st, M, use_sval, x, y, e, partials, ((long)M.sell_slices * 32 + kBlock - 1) / kBlock);
+   else if (M.nblk > 0) grid = launch_spmv_mode<2>(cfg, st, M, use_sval, x, y, e, partials, (long)M.nblk);
+   else grid = launch_spmv_mode<0>(cfg, st, M, use_sval, x, y, e, partials, ((long)M.nrows * M.lpr + kBlock - 1) / kBlock);
    if (grid_out) *grid_out = grid;
-   if (use_sval) k_spmv<true><<<grid, kBlock, 0, st>>>(M, x, y, e, partials);
-   else k_spmv<false><<<grid, kBlock, 0, st>>>(M, x, y, e, partials);
    return 1;
 }
 

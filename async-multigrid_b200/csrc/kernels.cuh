@@ -71,12 +71,104 @@ __device__ __forceinline__ double sell_rows_team(const DevCSR &M, const double *
    return sumsq;
 }
 
-// dispatch on storage + lanes per row
+// ---- CSR-stream: one CTA per row block --------------------------------------------------------
+// Phase 1 streams the block's (col,val) pairs with 128-bit coalesced loads -- every lane busy and
+// two independent 48-byte groups in flight per thread regardless of the row lengths -- multiplies
+// by the gathered x and parks the products in shared memory.  Phase 2 sums each row's products
+// with a sub-warp sized to the block's row count and applies the fused epilogue.  `sprod` holds
+// AMGB_STREAM_CAP doubles.  Must be called by all threads of a 256-thread CTA.
 template <bool RO, bool SVAL>
-__device__ __forceinline__ double spmv_team(const DevCSR &M, const double *x, double *y, const SpmvEpilogue &e,
-                                            int team_tid, int team_size, bool want_sumsq)
+__device__ __forceinline__ double stream_block(const DevCSR &M, int b, const double *__restrict__ x, double *y,
+                                               const SpmvEpilogue &e, double *sprod, bool want_sumsq)
 {
-   if (M.sell_slices > 0) return sell_rows_team<RO, SVAL>(M, x, y, e, team_tid, team_size, want_sumsq);
+   const int tid = threadIdx.x;
+   const int r0 = __ldg(M.blk + b), r1 = __ldg(M.blk + b + 1);
+   const int p0 = __ldg(M.rp + r0), p1 = __ldg(M.rp + r1);
+   const int q0 = p0 & ~3;
+   const double *__restrict__ va = SVAL ? M.sval : M.va;
+   double sumsq = 0.0;
+   if (p1 - q0 > AMGB_STREAM_CAP) {
+      // a single long row: the whole CTA strides over it
+      double acc = 0.0;
+      for (int p = p0 + tid; p < p1; p += 256) acc += ld_stream(va + p) * ld_x<RO>(x + ld_stream(M.ci + p));
+      acc = block_sum(acc);
+      if (tid == 0) {
+         const double v = epilogue_apply<RO>(e, r0, acc);
+         y[r0] = v;
+         if (want_sumsq) sumsq = v * v;
+      }
+      return sumsq;
+   }
+   const int ngroups = (p1 - q0 + 3) >> 2;            // <= 512: at most two groups per thread
+   {
+      const int g0 = tid, g1 = tid + 256;
+      const bool h0 = g0 < ngroups, h1 = g1 < ngroups;
+      int4 c0 = make_int4(0, 0, 0, 0), c1 = c0;
+      double2 a0 = make_double2(0, 0), a1 = a0, b0 = a0, b1 = a0;
+      if (h0) { const int p = q0 + 4 * g0; c0 = ld_stream4(M.ci + p); a0 = ld_stream2(va + p); a1 = ld_stream2(va + p + 2); }
+      if (h1) { const int p = q0 + 4 * g1; c1 = ld_stream4(M.ci + p); b0 = ld_stream2(va + p); b1 = ld_stream2(va + p + 2); }
+      if (h0) {
+         const int p = q0 + 4 * g0;
+         double2 o0, o1;
+         o0.x = (p >= p0 && p < p1) ? a0.x * ld_x<RO>(x + c0.x) : 0.0;
+         o0.y = (p + 1 >= p0 && p + 1 < p1) ? a0.y * ld_x<RO>(x + c0.y) : 0.0;
+         o1.x = (p + 2 >= p0 && p + 2 < p1) ? a1.x * ld_x<RO>(x + c0.z) : 0.0;
+         o1.y = (p + 3 >= p0 && p + 3 < p1) ? a1.y * ld_x<RO>(x + c0.w) : 0.0;
+         *reinterpret_cast<double2 *>(sprod + 4 * g0) = o0;
+         *reinterpret_cast<double2 *>(sprod + 4 * g0 + 2) = o1;
+      }
+      if (h1) {
+         const int p = q0 + 4 * g1;
+         double2 o0, o1;
+         o0.x = (p < p1) ? b0.x * ld_x<RO>(x + c1.x) : 0.0;
+         o0.y = (p + 1 < p1) ? b0.y * ld_x<RO>(x + c1.y) : 0.0;
+         o1.x = (p + 2 < p1) ? b1.x * ld_x<RO>(x + c1.z) : 0.0;
+         o1.y = (p + 3 < p1) ? b1.y * ld_x<RO>(x + c1.w) : 0.0;
+         *reinterpret_cast<double2 *>(sprod + 4 * g1) = o0;
+         *reinterpret_cast<double2 *>(sprod + 4 * g1 + 2) = o1;
+      }
+   }
+   __syncthreads();
+   const int nr = r1 - r0;
+   // lanes per row: the largest power of two (<= 32) such that all rows fit in one pass
+   int lpr = 1;
+   while (lpr < 32 && nr * (lpr << 1) <= 256) lpr <<= 1;
+   const int lane = tid & (lpr - 1);
+   const int rows_per_pass = 256 / lpr;
+   for (int base = 0; base < nr; base += rows_per_pass) {
+      const int row = r0 + base + tid / lpr;
+      const bool ok = row < r1;
+      const int s = ok ? __ldg(M.rp + row) - q0 : 0, t = ok ? __ldg(M.rp + row + 1) - q0 : 0;
+      double acc = 0.0;
+      for (int i = s + lane; i < t; i += lpr) acc += sprod[i];
+      for (int o = lpr >> 1; o > 0; o >>= 1) acc += __shfl_down_sync(AMGB_FULL, acc, o, 32);
+      if (lane == 0 && ok) {
+         const double v = epilogue_apply<RO>(e, row, acc);
+         y[row] = v;
+         if (want_sumsq) sumsq += v * v;
+      }
+   }
+   return sumsq;
+}
+
+// all row blocks of M, dealt round-robin to the CTAs of a team; returns the thread's sum of y_i^2
+template <bool RO, bool SVAL>
+__device__ __forceinline__ double stream_rows_team(const DevCSR &M, const double *x, double *y, const SpmvEpilogue &e,
+                                                   int team_cta, int team_nctas, double *sprod, bool want_sumsq)
+{
+   double sumsq = 0.0;
+   for (int b = team_cta; b < M.nblk; b += team_nctas) {
+      sumsq += stream_block<RO, SVAL>(M, b, x, y, e, sprod, want_sumsq);
+      __syncthreads();                                 // sprod is reused by the next block
+   }
+   return sumsq;
+}
+
+// vector-per-row CSR with the lanes-per-row chosen at upload time
+template <bool RO, bool SVAL>
+__device__ __forceinline__ double csr_rows_dispatch(const DevCSR &M, const double *x, double *y, const SpmvEpilogue &e,
+                                                    int team_tid, int team_size, bool want_sumsq)
+{
    switch (M.lpr) {
       case 2: return csr_rows_team<2, RO, SVAL>(M, x, y, e, team_tid, team_size, want_sumsq);
       case 4: return csr_rows_team<4, RO, SVAL>(M, x, y, e, team_tid, team_size, want_sumsq);
@@ -84,6 +176,19 @@ __device__ __forceinline__ double spmv_team(const DevCSR &M, const double *x, do
       case 16: return csr_rows_team<16, RO, SVAL>(M, x, y, e, team_tid, team_size, want_sumsq);
       default: return csr_rows_team<32, RO, SVAL>(M, x, y, e, team_tid, team_size, want_sumsq);
    }
+}
+
+
+// dispatch on storage + lanes per row
+// (team_tid, team_size) = (team_cta * 256 + threadIdx.x, team_nctas * 256); sprod: AMGB_STREAM_CAP doubles
+// of shared memory
+template <bool RO, bool SVAL>
+__device__ __forceinline__ double spmv_team(const DevCSR &M, const double *x, double *y, const SpmvEpilogue &e,
+                                            int team_tid, int team_size, bool want_sumsq, double *sprod)
+{
+   if (M.sell_slices > 0) return sell_rows_team<RO, SVAL>(M, x, y, e, team_tid, team_size, want_sumsq);
+   if (M.nblk > 0) return stream_rows_team<RO, SVAL>(M, x, y, e, team_tid >> 8, team_size >> 8, sprod, want_sumsq);
+   return csr_rows_dispatch<RO, SVAL>(M, x, y, e, team_tid, team_size, want_sumsq);
 }
 
 // ---- hybrid Jacobi / Gauss-Seidel (src/SMEM_Smooth.cpp:533-586) ----------------------------------

@@ -33,7 +33,7 @@ class Options(C.Structure):
     _fields_ = [("solver", C.c_int), ("smoother", C.c_int), ("smooth_weight", C.c_double),
                 ("num_pre_smooth_sweeps", C.c_int), ("num_post_smooth_sweeps", C.c_int),
                 ("num_fine_smooth_sweeps", C.c_int), ("num_coarse_smooth_sweeps", C.c_int),
-                ("jgs_block_rows", C.c_int), ("use_sell", C.c_int), ("l2_persist", C.c_int)]
+                ("jgs_block_rows", C.c_int), ("use_sell", C.c_int), ("l2_persist", C.c_int), ("use_stream", C.c_int)]
 
 
 _lib = None
@@ -95,7 +95,8 @@ class Solver:
     built for `solver` (build_transfers)."""
 
     def __init__(self, h, solver=H.MULTADD, smoother=H.JACOBI, smooth_weight=1.0, num_pre=1, num_post=1,
-                 fine_sweeps=1, coarse_sweeps=1, jgs_block_rows=8, use_sell=True, l2_persist=True, device=0):
+                 fine_sweeps=1, coarse_sweeps=1, jgs_block_rows=8, use_sell=True, l2_persist=True, use_stream=True,
+                 device=0):
         self.L = load_library()
         self.h = h
         self.ctx = C.c_void_p()
@@ -108,6 +109,7 @@ class Solver:
         o.num_pre_smooth_sweeps, o.num_post_smooth_sweeps = num_pre, num_post
         o.num_fine_smooth_sweeps, o.num_coarse_smooth_sweeps = fine_sweeps, coarse_sweeps
         o.jgs_block_rows, o.use_sell, o.l2_persist = jgs_block_rows, int(use_sell), int(l2_persist)
+        o.use_stream = int(use_stream)
         self.options = o
         self._ck(self.L.amgb_set_options(self.ctx, C.byref(o)))
         self._ck(self.L.amgb_set_num_levels(self.ctx, h.num_levels))
@@ -199,11 +201,13 @@ class Solver:
         self._ck(self.L.amgb_solve_async(self.ctx, num_cycles, converge, _ip(corr), C.byref(rel), C.byref(secs)))
         return corr, rel.value, secs.value
 
-    def SMEM_Solve(self, f_host, tol=1e-9, num_cycles=100):
+    def SMEM_Solve(self, f_host, tol=1e-9, num_cycles=100, u_out=None):
         """Drop-in for one SMEM_Solve call with host buffers (src/SMEM_Main.cpp:694-757):
-        returns dict(u, hist, cycles, corrections, relres, seconds)."""
+        returns dict(u, hist, cycles, corrections, relres, seconds).  u_out: optional caller-owned
+        (e.g. pinned) result buffer."""
         f = np.ascontiguousarray(f_host, dtype=np.float64)
-        u = np.empty(self.n0)
+        u = np.empty(self.n0) if u_out is None else u_out
+        assert u.dtype == np.float64 and u.shape[0] == self.n0 and u.flags["C_CONTIGUOUS"]
         hist = np.zeros(num_cycles + 1)
         n = C.c_int(0)
         corr = np.zeros(self.h.num_levels, dtype=np.int32)

@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline measurement on B200: fp64 additive-AMG (Multadd) solve of the
+3-D 7-point Laplacian to 1e-9 relative residual, solve seconds + achieved HBM GB/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--n 256] [--solver ...]
+
+One "step" = one complete solve (x0 = 0 -> ||r||/||r0|| < 1e-9) of the same synthetic problem
+(srand(0) right-hand side, the reference's SMEM convention).  `value` = device-timed seconds of the
+cycle loop with f, u and the hierarchy resident in HBM (the reference times exactly this loop,
+src/SMEM_Solve.cpp:107,245); `e2e` = the same solve through the drop-in C-ABI call amgb_smem_solve
+with HOST buffers (pinned f in, u out), copies inside the timed region.  The hierarchy (A_l, P_l, R_l)
+is built on the host before the timed region, as the reference's SMEM_Setup does.
+
+--impl reference times the reference's own OpenMP solve phase (oracle/_ref/libref_smem.so: the
+unmodified translation units of /root/reference/src compiled by oracle/build_ref.sh) on the host
+cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "fp64 Multadd solve sec to 1e-9 rel resid, 3D 7pt Laplacian; SpMV HBM GB/s"
+TOL = 1e-9
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device=0):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power)}
+
+
+SOLVERS = {"multadd": 2, "afacx": 1, "bpx": 3, "async_multadd": 6, "async_afacx": 5}
+SMOOTHERS = {"j": 0, "hybrid_jgs": 2, "L1j": 6}
+
+
+def build_problem(args, H):
+    t0 = time.time()
+    A = H.laplacian("7pt", args.n, args.n, args.nz or args.n)
+    h = H.amg_setup(A, theta=args.theta)
+    sv = SOLVERS[args.solver]
+    base = H.MULTADD if sv in (H.MULTADD, H.ASYNC_MULTADD) else sv
+    if sv == H.ASYNC_AFACX:
+        base = H.AFACX
+    h.build_transfers(base, args.smooth_weight, num_pre=1, num_post=args.num_post)
+    b = H.rand_rhs(A.nrows)
+    log("[bench] hierarchy: %d levels, n=%s, nnz(A)=%s, opcx=%.2f, host setup %.1fs" %
+        (h.num_levels, h.n, [a.nnz for a in h.A], h.operator_complexity(), time.time() - t0))
+    return h, b
+
+
+def pinned(n):
+    import torch
+    t = torch.empty(n, dtype=torch.float64).pin_memory()
+    return t, t.numpy()
+
+
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import async_multigrid_b200 as amg
+    from async_multigrid_b200 import hierarchy as H
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
+    if world > 1:
+        from async_multigrid_b200 import dist_bench
+        return dist_bench.run(args, rank, world, local)
+    torch.cuda.set_device(local)
+    peak, peak_src = load_peaks()
+    h, b = build_problem(args, H)
+    sv, sm = SOLVERS[args.solver], SMOOTHERS[args.smoother]
+    is_async = sv in (H.ASYNC_MULTADD, H.ASYNC_AFACX)
+    t0 = time.time()
+    s = amg.Solver(h, sv, sm, args.smooth_weight, num_pre=1, num_post=args.num_post, jgs_block_rows=args.jgs_block_rows,
+                   use_sell=not args.no_sell)
+    log("[bench] upload + device setup %.1fs" % (time.time() - t0))
+    f_t, f_host = pinned(h.n[0])
+    u_t, u_host = pinned(h.n[0])
+    f_host[:] = b
+    max_cycles = args.max_cycles
+
+    # async: the stop rule is a correction count (src/SMEM_Async_AMG.cpp:317-322); find the smallest count
+    # (multiple of 5) that reaches the tolerance, untimed
+    num_cycles = max_cycles
+    if is_async:
+        for nc in range(10, max_cycles + 1, 5):
+            out = s.SMEM_Solve(f_host, TOL, nc)
+            log("[bench] async calibration: %d corrections/level -> relres %.3e (%.4fs)" % (nc, out["relres"], out["seconds"]))
+            if out["relres"] < TOL * 0.5:
+                num_cycles = nc
+                break
+
+    def one_solve_resident():
+        s.set_solution(None)
+        if is_async:
+            corr, rel, secs = s.solve_async(num_cycles)
+            return secs, num_cycles, rel, corr
+        hist, secs = s.solve_sync(TOL, max_cycles)
+        return secs, len(hist) - 1, hist[-1], None
+
+    s.set_rhs(f_host)
+    for _ in range(args.warmup):
+        one_solve_resident()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = s.launch_count()
+    torch.cuda.synchronize()
+    secs_list, cycles, rel = [], 0, 0.0
+    for _ in range(args.steps):
+        secs, cycles, rel, corr = one_solve_resident()
+        secs_list.append(secs)
+    torch.cuda.synchronize()
+    launches = s.launch_count() - launches0
+    solve_s = float(np.mean(secs_list))
+
+    # end to end through the drop-in call with host buffers
+    s.SMEM_Solve(f_host, TOL, num_cycles if is_async else max_cycles, u_out=u_host)
+    e2e_list = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        out = s.SMEM_Solve(f_host, TOL, num_cycles if is_async else max_cycles, u_out=u_host)
+        e2e_list.append(time.perf_counter() - t0)
+    e2e_s = float(np.mean(e2e_list))
+
+    # dominant kernel: fine-level residual r = f - A_0 u (k_spmv on A_0), event-timed on the solver's stream
+    res_ms = s.time_residual(50)
+    clocks = sampler.stop()
+    res_bytes = H.bytes_spmv(h.A[0], True)
+    achieved = res_bytes / (res_ms * 1e-3) / 1e9
+    symmetric = sm != H.HYBRID_JACOBI_GAUSS_SEIDEL and args.num_post > 0
+    if is_async:
+        cyc_bytes = sum(H.bytes_async_chain(h, k, symmetric) for k in range(h.num_levels))
+    else:
+        cyc_bytes = H.bytes_sync_multadd_cycle(h, symmetric)
+    solve_bytes = cyc_bytes * cycles
+    true_rel = float(out["relres"])
+    line = {
+        "metric": METRIC, "value": solve_s, "unit": "s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": solve_s * 1e3, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "3D 7-pt Laplacian %d^3 (n=%d, nnz=%d), %s, smoother %s w=%.2f, tol 1e-9, x0=0, b=srand(0) RandDouble(-1,1)"
+                   % (args.n, h.n[0], h.A[0].nnz, args.solver, args.smoother, args.smooth_weight),
+                   "levels": h.num_levels, "operator_complexity": round(h.operator_complexity(), 3),
+                   "cycles_to_tol": int(cycles), "final_relres": float(rel),
+                   "l2": "inputs (A_0 alone %.2f GB) exceed the 126 MB L2; no explicit flush" % (12e-9 * h.A[0].nnz),
+                   "hierarchy": "host classical AMG stand-in for hypre BoomerAMG (PMIS, direct interp + 1 Jacobi step, Pmax 4)"},
+        "e2e": {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": int(8 * h.n[0]), "d2h_bytes_per_step": int(8 * h.n[0]),
+                "final_relres": true_rel},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "k_spmv (r = f - A_0 u, fine level)", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "frac_of_8000_spec": achieved / 8000.0,
+                     "peak_source": peak_src, "bytes_per_launch": int(res_bytes), "ms_per_launch": res_ms,
+                     "traffic": None},
+        "solve_roofline": {"bytes_per_cycle": int(cyc_bytes), "cycles": int(cycles),
+                           "achieved": solve_bytes / solve_s / 1e9, "frac": solve_bytes / solve_s / 1e9 / peak, "unit": "GB/s"},
+    }
+    if corr is not None:
+        line["config"]["corrections_per_level"] = [int(x) for x in corr]
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args, h, b, cycles if not is_async else num_cycles)
+    s.close()
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline(args, h, b, cycles_to_tol, sample_cycles=None, full=False):
+    """The reference's own OpenMP solve phase (oracle/_ref) -- or the oracle port when _ref is absent --
+    on the host cores, on a bounded sample: `sample_cycles` cycles, scaled to the cycle count of the full
+    solve (every cycle costs the same)."""
+    from async_multigrid_b200 import hierarchy as H
+    from oracle import oracle as O
+    sv, sm = SOLVERS[args.solver], SMOOTHERS[args.smoother]
+    cores = os.cpu_count() or 1
+    threads = max(h.num_levels, min(cores, args.cpu_threads or cores))
+    sample = sample_cycles or args.cpu_sample_cycles
+    if full:
+        sample = args.max_cycles
+    use_ref = O.ref_lib() is not None and not args.cpu_port
+    t0 = time.time()
+    if use_ref:
+        rs = O.RefSolver(h, sv, sm, b, args.smooth_weight, num_pre=1, num_post=args.num_post, num_threads=threads)
+        if sv in (H.ASYNC_MULTADD, H.ASYNC_AFACX):
+            out = rs.solve(sample, TOL if full else 1e-300)
+            secs, done, rel = out["seconds"], sample, out["relres"]
+        elif sv in (H.MULTADD, H.AFACX):
+            # SMEM_Solve's loop with ONE added barrier between the cycle's "u += e" and the residual
+            # (oracle/ref_driver.cpp ref_solve_sync_det): as shipped, the grouped synchronous cycle races on u
+            #  and does not reach 1e-9; cycle, smoothers and SpMV are the reference's object code
+            t1 = time.perf_counter()
+            out = rs.solve_sync_det(sample, TOL if full else 1e-300)
+            secs, done, rel = time.perf_counter() - t1, out["cycles"], out["hist"][-1]
+        else:
+            out = rs.solve(sample, TOL if full else 1e-300, async_type=0)
+            secs, done, rel = out["seconds"], out["cycles"], out["relres"]
+        rs.close()
+        kind = "reference"
+    else:
+        O.lib().orc_set_threads(threads)
+        base = {H.ASYNC_MULTADD: H.MULTADD, H.ASYNC_AFACX: H.AFACX}.get(sv, sv)
+        pb = O.Problem(h, base, sm, args.smooth_weight, num_pre=1, num_post=args.num_post, jgs_blocks=[H.uniform_blocks(m, args.jgs_block_rows) for m in h.n])
+        _, hist, secs = pb.solve_sync(b, TOL if full else 1e-300, sample)
+        done, rel = len(hist) - 1, hist[-1]
+        kind = "port"
+    per_cycle = secs / max(done, 1)
+    total = cycles_to_tol if cycles_to_tol else done
+    log("[bench] cpu %s: %d cycles in %.2fs (%d threads, wall incl. setup %.1fs), relres after sample %.3e" %
+        (kind, done, secs, threads, time.time() - t0, rel))
+    return {"value": per_cycle * total, "unit": "s", "cores": threads, "kind": kind,
+            "sample": "%d cycles of the same %d^3 solve timed (%.3fs, %.4fs/cycle), scaled to the %d cycles of the full solve"
+                      % (done, args.n, secs, per_cycle, total),
+            "seconds_per_cycle": per_cycle, "cycles": int(total), "relres_after_sample": float(rel)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from async_multigrid_b200 import hierarchy as H
+    h, b = build_problem(args, H)
+    sv = SOLVERS[args.solver]
+    # warm-up 1: the full solve to the tolerance (gives the cycle count); further warm-ups and the timed
+    # steps: a bounded sample of cycles each
+    full = cpu_baseline(args, h, b, None, full=True)
+    cycles = int(full["cycles"])
+    for _ in range(max(0, args.warmup - 1)):
+        cpu_baseline(args, h, b, cycles)
+    vals = [cpu_baseline(args, h, b, cycles) for _ in range(args.steps)]
+    v = float(np.mean([x["value"] for x in vals]))
+    cb = dict(vals[-1])
+    cb["value"] = v
+    cb["full_solve_seconds_measured_once"] = full["value"]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": v * 1e3, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "3D 7-pt Laplacian %d^3 (n=%d, nnz=%d), %s, smoother %s w=%.2f, tol 1e-9, x0=0, b=srand(0) RandDouble(-1,1)"
+                   % (args.n, h.n[0], h.A[0].nnz, args.solver, args.smoother, args.smooth_weight),
+                   "levels": h.num_levels, "cycles_to_tol": cycles},
+        "cpu_baseline": cb,
+        "e2e": {"value": v, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=256)
+    ap.add_argument("--nz", type=int, default=0)
+    ap.add_argument("--solver", default="multadd", choices=sorted(SOLVERS))
+    ap.add_argument("--smoother", default="j", choices=sorted(SMOOTHERS))
+    ap.add_argument("--smooth-weight", type=float, default=0.9)
+    ap.add_argument("--theta", type=float, default=0.25)
+    ap.add_argument("--num-post", type=int, default=1, help="-num_post_smooth_sweeps: 0 = plain P + non-symmetrised smoother")
+    ap.add_argument("--max-cycles", type=int, default=200)
+    ap.add_argument("--jgs-block-rows", type=int, default=8)
+    ap.add_argument("--no-sell", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-port", action="store_true", help="time the oracle port instead of oracle/_ref")
+    ap.add_argument("--cpu-sample-cycles", type=int, default=3)
+    ap.add_argument("--cpu-threads", type=int, default=0)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        log("[bench] note: fewer than 3 warm-up steps requested")
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

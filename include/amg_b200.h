@@ -50,6 +50,8 @@ typedef struct {
                                    src/SMEM_Smooth.cpp:567-581) */
    int use_sell;                /* 1: sliced-ELL (C=32) storage for low-variance levels, 0: CSR only */
    int l2_persist;              /* 1: pin the coarse hierarchy in L2 with an access-policy window */
+   int use_stream;              /* 1: CSR-stream kernel (row blocks staged through shared memory with 128-bit
+                                   loads) for every matrix not stored as sliced ELL; 0: vector-per-row CSR */
 } amgb_options;
 
 void amgb_default_options(amgb_options *opt);

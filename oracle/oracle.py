@@ -84,6 +84,7 @@ class Problem:
                  fine_sweeps=1, coarse_sweeps=1, jgs_blocks=None, jgs_parfor_scale=0):
         L = h.num_levels
         self.h = h
+        self._keep = (list(h.A), list(h.P), list(h.R))   # the C structs borrow these arrays
         self._A = (OrcCSR * L)(*[c_csr(a) for a in h.A])
         self._P = (OrcCSR * max(L - 1, 1))(*[c_csr(p) for p in h.P])
         self._R = (OrcCSR * max(L - 1, 1))(*[c_csr(r) for r in h.R])
@@ -219,6 +220,7 @@ class RefSolver:
         if num_threads is None:
             num_threads = max(L, min(self.L.ref_max_threads(), 64))
         self.num_threads = num_threads
+        self._keep = (list(h.A), list(h.P), list(h.R))   # the C structs borrow these arrays
         self._A = (OrcCSR * L)(*[c_csr(a) for a in h.A])
         self._P = (OrcCSR * max(L - 1, 1))(*[c_csr(p) for p in h.P])
         self._R = (OrcCSR * max(L - 1, 1))(*[c_csr(r) for r in h.R])
@@ -229,7 +231,15 @@ class RefSolver:
             num_threads = L
             self.threads_per_level = np.ones(L, dtype=np.int32)
         else:
-            self.threads_per_level = np.asarray(hier.balanced_threads(frac, num_threads), dtype=np.int32)
+            tpl = hier.balanced_threads(frac, num_threads)
+            # the reference's balancing loop can leave a level with 0 threads, which is then silently never
+            # corrected (the `max_diff < 0.0 && threads == 1` guard at
+            # src/SMEM_Setup.cpp:788 tests the running maximum, not the candidate).  A converging run needs
+            # every level served: move one thread from the best-provisioned level to each empty one.
+            while min(tpl) == 0:
+                tpl[int(np.argmax(tpl))] -= 1
+                tpl[tpl.index(0)] += 1
+            self.threads_per_level = np.asarray(tpl, dtype=np.int32)
         self.num_threads = num_threads
         self._f = np.ascontiguousarray(f, dtype=np.float64)
         self.handle = self.L.ref_create(L, self._A, self._P, self._R, self._l1, solver, smoother, smooth_weight,
