@@ -27,7 +27,7 @@ struct Team {
    int cta, nctas;         // CTA index / count within the group
    unsigned int *count;
    volatile unsigned int *gen;
-   double *sprod;          // AMGB_STREAM_CAP doubles of shared memory (CSR-stream staging)
+   unsigned char *smem;    // AMGB_STREAM_SMEM bytes of shared memory (CSR-stream staging)
 };
 
 // barrier among the CTAs of one group (the reference's SMEM_LevelBarrier)
@@ -80,12 +80,12 @@ __device__ void team_smooth_zero(const AsyncParams &p, const Team &tm, int l, co
    }
    const double *rs = (p.smoother == AMGB_SMOOTH_L1_JACOBI) ? p.inv_l1[l] : p.ws[l];
    if (symmetric) {
-      spmv_team<false, true>(A, f, e, mk(-1.0, 2.0, f, 0.0, nullptr, rs), tm.tid, tm.size, false, tm.sprod);
+      spmv_team<false, true>(A, f, e, mk(-1.0, 2.0, f, 0.0, nullptr, rs), tm.tid, tm.size, false, tm.smem);
       group_barrier(tm);
       for (int k = 1; k < sweeps; k++) {
-         spmv_team<false, false>(A, e, s1, mk(-1.0, 1.0, f), tm.tid, tm.size, false, tm.sprod);
+         spmv_team<false, false>(A, e, s1, mk(-1.0, 1.0, f), tm.tid, tm.size, false, tm.smem);
          group_barrier(tm);
-         spmv_team<false, true>(A, s1, e, mk(-1.0, 2.0, s1, 0.0, nullptr, rs), tm.tid, tm.size, false, tm.sprod);
+         spmv_team<false, true>(A, s1, e, mk(-1.0, 2.0, s1, 0.0, nullptr, rs), tm.tid, tm.size, false, tm.smem);
          group_barrier(tm);
       }
       return;
@@ -95,13 +95,13 @@ __device__ void team_smooth_zero(const AsyncParams &p, const Team &tm, int l, co
    for (int i = tm.tid; i < n; i += tm.size) cur[i] = __ldg(rs + i) * ld_cg(f + i);
    group_barrier(tm);
    for (int k = 1; k < sweeps; k++) {
-      spmv_team<false, false>(A, cur, oth, mk(-1.0, 1.0, f, 1.0, cur, rs), tm.tid, tm.size, false, tm.sprod);
+      spmv_team<false, false>(A, cur, oth, mk(-1.0, 1.0, f, 1.0, cur, rs), tm.tid, tm.size, false, tm.smem);
       group_barrier(tm);
       double *tmp = cur; cur = oth; oth = tmp;
    }
 }
 
-__global__ void __launch_bounds__(kABlock) k_async_amg(const AsyncParams *__restrict__ pp)
+__global__ void __launch_bounds__(kABlock, 3) k_async_amg(const AsyncParams *__restrict__ pp)
 {
    const AsyncParams &p = *pp;
    const int L = p.num_levels;
@@ -120,8 +120,8 @@ __global__ void __launch_bounds__(kABlock) k_async_amg(const AsyncParams *__rest
    const bool multadd = p.solver == AMGB_SOLVER_ASYNC_MULTADD;
    const int n0 = p.A[0].nrows;
    __shared__ int s_stop;
-   __shared__ __align__(16) double s_prod[AMGB_STREAM_CAP];
-   tm.sprod = s_prod;
+   extern __shared__ __align__(128) unsigned char dyn_smem[];
+   tm.smem = dyn_smem;
 
    // The coarsest level's correction is identically zero in the reference (direct solve commented
    // out, :112-131): its restrict / prolong / residual work adds exactly 0.0 to u, so this group only
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(kABlock) k_async_amg(const AsyncParams *__rest
       const int coarsest = idle ? 0 : (multadd ? q : q + 1);
       for (int l = 0; l < coarsest; l++) {
          if (l < L - 1) {
-            spmv_team<false, false>(p.R[l], v.r[l], v.r[l + 1], mk(1.0, 0.0, nullptr), tm.tid, tm.size, false, tm.sprod);
+            spmv_team<false, false>(p.R[l], v.r[l], v.r[l + 1], mk(1.0, 0.0, nullptr), tm.tid, tm.size, false, tm.smem);
             group_barrier(tm);
          }
       }
@@ -147,15 +147,15 @@ __global__ void __launch_bounds__(kABlock) k_async_amg(const AsyncParams *__rest
          // AFACx (:153-206): u_c = S_{q+1} r_{q+1}; e = P u_c; r_f = r_q - A_q e; u_f = S_q r_f
          const int cl = q + 1;
          team_smooth_zero(p, tm, cl, v.r[cl], v.t[cl], v.w[cl], p.coarse_sweeps, false);
-         spmv_team<false, false>(p.P[q], v.t[cl], v.t[q], mk(1.0, 0.0, nullptr), tm.tid, tm.size, false, tm.sprod);
+         spmv_team<false, false>(p.P[q], v.t[cl], v.t[q], mk(1.0, 0.0, nullptr), tm.tid, tm.size, false, tm.smem);
          group_barrier(tm);
-         spmv_team<false, false>(p.A[q], v.t[q], v.w[q], mk(-1.0, 1.0, v.r[q]), tm.tid, tm.size, false, tm.sprod);
+         spmv_team<false, false>(p.A[q], v.t[q], v.w[q], mk(-1.0, 1.0, v.r[q]), tm.tid, tm.size, false, tm.smem);
          group_barrier(tm);
          team_smooth_zero(p, tm, q, v.w[q], v.e[q], v.t[q], p.fine_sweeps, false);
       }
       // ---- prolongation chain (:211-224)
       for (int l = idle ? -1 : q - 1; l >= 0; l--) {
-         spmv_team<false, false>(p.P[l], v.e[l + 1], v.e[l], mk(1.0, 0.0, nullptr), tm.tid, tm.size, false, tm.sprod);
+         spmv_team<false, false>(p.P[l], v.e[l + 1], v.e[l], mk(1.0, 0.0, nullptr), tm.tid, tm.size, false, tm.smem);
          group_barrier(tm);
       }
       // ---- u += e (atomic), private copy (:285-301)
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(kABlock) k_async_amg(const AsyncParams *__rest
       __syncthreads();
       const int stop = s_stop;
       // ---- private residual from the private copy (:338-351)
-      if (!idle) spmv_team<false, false>(p.A[0], v.u_local, v.r[0], mk(-1.0, 1.0, p.f), tm.tid, tm.size, false, tm.sprod);
+      if (!idle) spmv_team<false, false>(p.A[0], v.u_local, v.r[0], mk(-1.0, 1.0, p.f), tm.tid, tm.size, false, tm.smem);
       group_barrier(tm);
       if (stop) break;
    }
@@ -207,7 +207,8 @@ int async_max_grid(int block)
    int dev = 0, sms = 0, per_sm = 0;
    cudaGetDevice(&dev);
    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_async_amg, block, 0);
+   cudaFuncSetAttribute(k_async_amg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AMGB_STREAM_SMEM);
+   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_async_amg, block, AMGB_STREAM_SMEM);
    return sms * per_sm;
 }
 
@@ -217,7 +218,7 @@ int launch_async(const LaunchCfg &, cudaStream_t st, const AsyncParams *params_d
    cudaLaunchConfig_t cfg = {};
    cfg.gridDim = dim3(grid);
    cfg.blockDim = dim3(block);
-   cfg.dynamicSmemBytes = 0;
+   cfg.dynamicSmemBytes = AMGB_STREAM_SMEM;
    cfg.stream = st;
    cudaLaunchAttribute attrs[2];
    int na = 0;

@@ -28,9 +28,13 @@ struct DevCSR {
    // counted from the 4-aligned start) are streamed with 128-bit loads into shared memory and then
    // reduced per row; a block made of ONE longer row is reduced by the whole CTA.
    int nblk = 0;
-   const int *blk = nullptr;
+   const int4 *blk = nullptr;        // per block {first row, end row, first entry, end entry}
 };
 #define AMGB_STREAM_CAP 2048
+#define AMGB_STREAM_STAGES 3
+// dynamic shared memory of a CTA running the CSR-stream path: per stage CAP column indices + CAP values
+// (products overwrite the values in place), then one mbarrier per stage
+#define AMGB_STREAM_SMEM (AMGB_STREAM_STAGES * AMGB_STREAM_CAP * 12 + 64)
 
 // y_i = gamma*c_i + rs_i * (beta*b_i + alpha * sum_j M_ij x_j)       (rs == nullptr -> 1)
 // covers: MatVec (alpha=1), Residual (alpha=-1,beta=1,b=f), prolong-and-add (beta=1,b=y),
@@ -87,6 +91,42 @@ __device__ __forceinline__ void red_add_f64(double *p, double v)
    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
 
+// ---- TMA bulk copy + mbarrier (sm_90+/sm_100a): global -> shared without register staging -----------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_inval(uint32_t bar) { asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+   uint32_t done;
+   do {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+   } while (!done);
+}
+// generic-proxy accesses to shared memory (the in-place products) are ordered before the next bulk copy
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint64_t l2_evict_first_policy()
+{
+   uint64_t pol;
+   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+   return pol;
+}
+// bytes: multiple of 16; src and dst 16-byte aligned.  The matrix streams are read once: evict_first keeps
+// the gathered vectors resident in L2.
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t pol)
+{
+   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
+
 template <int W>
 __device__ __forceinline__ double subwarp_sum(double v)
 {
@@ -104,6 +144,26 @@ __device__ __forceinline__ double epilogue_apply(const SpmvEpilogue &e, int row,
    if (e.b) t += e.beta * (RO ? e.b[row] : ld_cg(e.b + row));
    if (e.rs) t *= __ldg(e.rs + row);
    if (e.c) t += e.gamma * (RO ? e.c[row] : ld_cg(e.c + row));
+   return t;
+}
+
+// epilogue with the row operands loaded ahead of the reduction (latency off the critical path)
+struct EpiOps { double b, c, rs; };
+template <bool RO>
+__device__ __forceinline__ EpiOps epilogue_load(const SpmvEpilogue &e, int row)
+{
+   EpiOps o;
+   o.b = e.b ? (RO ? e.b[row] : ld_cg(e.b + row)) : 0.0;
+   o.rs = e.rs ? __ldg(e.rs + row) : 1.0;
+   o.c = e.c ? (RO ? e.c[row] : ld_cg(e.c + row)) : 0.0;
+   return o;
+}
+__device__ __forceinline__ double epilogue_finish(const SpmvEpilogue &e, const EpiOps &o, double ax)
+{
+   double t = e.alpha * ax;
+   if (e.b) t += e.beta * o.b;
+   if (e.rs) t *= o.rs;
+   if (e.c) t += e.gamma * o.c;
    return t;
 }
 

@@ -203,22 +203,21 @@ static int build_sell(amgb_ctx *c, DevCSR &M, int nrows, const int *rp, const in
 // block of its own.
 static int build_stream_blocks(amgb_ctx *c, DevCSR &M, int nrows, const int *rp)
 {
-   std::vector<int> blk;
+   std::vector<int4> blk;
    blk.reserve((size_t)rp[nrows] / 1024 + 16);
-   blk.push_back(0);
    int r = 0;
    while (r < nrows) {
       const int start = r;
       const long q0 = rp[start] & ~3;
       while (r < nrows && r - start < AMGB_STREAM_CAP && (long)rp[r + 1] - q0 <= AMGB_STREAM_CAP) r++;
       if (r == start) r++;
-      blk.push_back(r);
+      blk.push_back(make_int4(start, r, rp[start], rp[r]));
    }
-   int *d_blk;
+   int4 *d_blk;
    int rc;
    if ((rc = dev_upload(c, &d_blk, blk.data(), blk.size()))) return rc;
    CUDA_OK(c, cudaStreamSynchronize(c->stream));
-   M.nblk = (int)blk.size() - 1;
+   M.nblk = (int)blk.size();
    M.blk = d_blk;
    return AMGB_OK;
 }

@@ -23,8 +23,8 @@ __global__ void __launch_bounds__(kBlock) k_spmv(DevCSR M, const double *x, doub
    double ss;
    if (MODE == 1) ss = sell_rows_team<true, SVAL>(M, x, y, e, tid, tsz, norm);
    else if (MODE == 2) {
-      __shared__ __align__(16) double sprod[AMGB_STREAM_CAP];
-      ss = stream_rows_team<true, SVAL>(M, x, y, e, blockIdx.x, gridDim.x, sprod, norm);
+      extern __shared__ __align__(128) unsigned char dyn_smem[];
+      ss = stream_rows_team<true, SVAL>(M, x, y, e, blockIdx.x, gridDim.x, dyn_smem, norm);
    } else ss = csr_rows_dispatch<true, SVAL>(M, x, y, e, tid, tsz, norm);
    if (norm) {
       ss = block_sum(ss);
@@ -116,7 +116,9 @@ static int resident_grid(const LaunchCfg &cfg)
    static int per_sm = 0;   // co-resident CTAs per SM of this instantiation: grids are sized to exactly one wave
    if (per_sm == 0) {
       int v = 0;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_spmv<MODE, SVAL>, kBlock, 0) != cudaSuccess || v < 1) v = 4;
+      const size_t dyn = MODE == 2 ? AMGB_STREAM_SMEM : 0;
+      if (dyn) cudaFuncSetAttribute(k_spmv<MODE, SVAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_spmv<MODE, SVAL>, kBlock, dyn) != cudaSuccess || v < 1) v = 2;
       per_sm = v;
    }
    return cfg.num_sms * per_sm;
@@ -128,8 +130,9 @@ static int launch_spmv_mode(const LaunchCfg &cfg, cudaStream_t st, const DevCSR 
 {
    const int cap = use_sval ? resident_grid<MODE, true>(cfg) : resident_grid<MODE, false>(cfg);
    const int grid = (int)std::max(1L, std::min(ctas_of_work, (long)cap));
-   if (use_sval) k_spmv<MODE, true><<<grid, kBlock, 0, st>>>(M, x, y, e, partials);
-   else k_spmv<MODE, false><<<grid, kBlock, 0, st>>>(M, x, y, e, partials);
+   const size_t dyn = MODE == 2 ? AMGB_STREAM_SMEM : 0;
+   if (use_sval) k_spmv<MODE, true><<<grid, kBlock, dyn, st>>>(M, x, y, e, partials);
+   else k_spmv<MODE, false><<<grid, kBlock, dyn, st>>>(M, x, y, e, partials);
    return grid;
 }
 

@@ -71,96 +71,138 @@ __device__ __forceinline__ double sell_rows_team(const DevCSR &M, const double *
    return sumsq;
 }
 
-// ---- CSR-stream: one CTA per row block --------------------------------------------------------
-// Phase 1 streams the block's (col,val) pairs with 128-bit coalesced loads -- every lane busy and
-// two independent 48-byte groups in flight per thread regardless of the row lengths -- multiplies
-// by the gathered x and parks the products in shared memory.  Phase 2 sums each row's products
-// with a sub-warp sized to the block's row count and applies the fused epilogue.  `sprod` holds
-// AMGB_STREAM_CAP doubles.  Must be called by all threads of a 256-thread CTA.
+// ---- CSR-stream: row blocks staged through shared memory by TMA bulk copies ---------------------
+// A CTA owns every team_nctas-th row block.  One thread keeps AMGB_STREAM_STAGES blocks in flight:
+// per block two cp.async.bulk copies (column indices, values; contiguous, 16-byte aligned segments of
+// the CSR arrays) that complete on the stage's mbarrier -- no register staging, the HBM stream never
+// stalls on the row structure.  Per block all 256 threads then (1) multiply the staged values by the
+// gathered x in place, (2) sum each row's products with a sub-warp sized to the block's row count and
+// apply the fused epilogue, whose row operands were loaded before the barrier wait.  A block made of
+// ONE row longer than AMGB_STREAM_CAP is read straight from global memory by the whole CTA.
+// `smem`: AMGB_STREAM_SMEM bytes, 16-byte aligned.  Must be called by all threads of a 256-thread CTA.
 template <bool RO, bool SVAL>
-__device__ __forceinline__ double stream_block(const DevCSR &M, int b, const double *__restrict__ x, double *y,
-                                               const SpmvEpilogue &e, double *sprod, bool want_sumsq)
+__device__ __forceinline__ double stream_rows_team(const DevCSR &M, const double *__restrict__ x, double *y,
+                                                   const SpmvEpilogue &e, int team_cta, int team_nctas,
+                                                   unsigned char *smem, bool want_sumsq)
 {
+   constexpr int CAP = AMGB_STREAM_CAP, ST = AMGB_STREAM_STAGES;
    const int tid = threadIdx.x;
-   const int r0 = __ldg(M.blk + b), r1 = __ldg(M.blk + b + 1);
-   const int p0 = __ldg(M.rp + r0), p1 = __ldg(M.rp + r1);
-   const int q0 = p0 & ~3;
    const double *__restrict__ va = SVAL ? M.sval : M.va;
+   int *scol = reinterpret_cast<int *>(smem);                                    // [ST][CAP]
+   double *sval = reinterpret_cast<double *>(smem + (size_t)ST * CAP * 4);        // [ST][CAP]
+   const uint32_t bar0 = smem_u32(smem + (size_t)ST * CAP * 12);
+   const int nmine = team_cta < M.nblk ? (M.nblk - team_cta + team_nctas - 1) / team_nctas : 0;
    double sumsq = 0.0;
-   if (p1 - q0 > AMGB_STREAM_CAP) {
-      // a single long row: the whole CTA strides over it
-      double acc = 0.0;
-      for (int p = p0 + tid; p < p1; p += 256) acc += ld_stream(va + p) * ld_x<RO>(x + ld_stream(M.ci + p));
-      acc = block_sum(acc);
-      if (tid == 0) {
-         const double v = epilogue_apply<RO>(e, r0, acc);
-         y[r0] = v;
-         if (want_sumsq) sumsq = v * v;
-      }
-      return sumsq;
-   }
-   const int ngroups = (p1 - q0 + 3) >> 2;            // <= 512: at most two groups per thread
-   {
-      const int g0 = tid, g1 = tid + 256;
-      const bool h0 = g0 < ngroups, h1 = g1 < ngroups;
-      int4 c0 = make_int4(0, 0, 0, 0), c1 = c0;
-      double2 a0 = make_double2(0, 0), a1 = a0, b0 = a0, b1 = a0;
-      if (h0) { const int p = q0 + 4 * g0; c0 = ld_stream4(M.ci + p); a0 = ld_stream2(va + p); a1 = ld_stream2(va + p + 2); }
-      if (h1) { const int p = q0 + 4 * g1; c1 = ld_stream4(M.ci + p); b0 = ld_stream2(va + p); b1 = ld_stream2(va + p + 2); }
-      if (h0) {
-         const int p = q0 + 4 * g0;
-         double2 o0, o1;
-         o0.x = (p >= p0 && p < p1) ? a0.x * ld_x<RO>(x + c0.x) : 0.0;
-         o0.y = (p + 1 >= p0 && p + 1 < p1) ? a0.y * ld_x<RO>(x + c0.y) : 0.0;
-         o1.x = (p + 2 >= p0 && p + 2 < p1) ? a1.x * ld_x<RO>(x + c0.z) : 0.0;
-         o1.y = (p + 3 >= p0 && p + 3 < p1) ? a1.y * ld_x<RO>(x + c0.w) : 0.0;
-         *reinterpret_cast<double2 *>(sprod + 4 * g0) = o0;
-         *reinterpret_cast<double2 *>(sprod + 4 * g0 + 2) = o1;
-      }
-      if (h1) {
-         const int p = q0 + 4 * g1;
-         double2 o0, o1;
-         o0.x = (p < p1) ? b0.x * ld_x<RO>(x + c1.x) : 0.0;
-         o0.y = (p + 1 < p1) ? b0.y * ld_x<RO>(x + c1.y) : 0.0;
-         o1.x = (p + 2 < p1) ? b1.x * ld_x<RO>(x + c1.z) : 0.0;
-         o1.y = (p + 3 < p1) ? b1.y * ld_x<RO>(x + c1.w) : 0.0;
-         *reinterpret_cast<double2 *>(sprod + 4 * g1) = o0;
-         *reinterpret_cast<double2 *>(sprod + 4 * g1 + 2) = o1;
-      }
+   uint64_t pol = 0;
+
+   auto issue = [&](const int4 d, int stage) {       // thread 0 only
+      const int q0 = d.z & ~3;
+      if (d.w - q0 > CAP || d.w == d.z) return;       // long row / no entries: not staged
+      const uint32_t n4 = (uint32_t)((d.w - q0 + 3) & ~3);
+      const uint32_t bar = bar0 + 8u * stage;
+      mbar_expect_tx(bar, n4 * 12u);
+      tma_bulk_g2s(smem_u32(scol + stage * CAP), M.ci + q0, n4 * 4u, bar, pol);
+      tma_bulk_g2s(smem_u32(sval + stage * CAP), va + q0, n4 * 8u, bar, pol);
+   };
+
+   __syncthreads();                                   // previous users of smem (and of the barriers) are done
+   if (tid == 0) {
+      pol = l2_evict_first_policy();
+      for (int s = 0; s < ST; s++) mbar_init(bar0 + 8u * s, 1);
+      mbar_init_fence();
+      fence_proxy_async();
+      for (int s = 0; s < ST && s < nmine; s++) issue(__ldg(M.blk + team_cta + s * team_nctas), s);
    }
    __syncthreads();
-   const int nr = r1 - r0;
-   // lanes per row: the largest power of two (<= 32) such that all rows fit in one pass
-   int lpr = 1;
-   while (lpr < 32 && nr * (lpr << 1) <= 256) lpr <<= 1;
-   const int lane = tid & (lpr - 1);
-   const int rows_per_pass = 256 / lpr;
-   for (int base = 0; base < nr; base += rows_per_pass) {
-      const int row = r0 + base + tid / lpr;
-      const bool ok = row < r1;
-      const int s = ok ? __ldg(M.rp + row) - q0 : 0, t = ok ? __ldg(M.rp + row + 1) - q0 : 0;
-      double acc = 0.0;
-      for (int i = s + lane; i < t; i += lpr) acc += sprod[i];
-      for (int o = lpr >> 1; o > 0; o >>= 1) acc += __shfl_down_sync(AMGB_FULL, acc, o, 32);
-      if (lane == 0 && ok) {
-         const double v = epilogue_apply<RO>(e, row, acc);
-         y[row] = v;
-         if (want_sumsq) sumsq += v * v;
+   uint32_t phase = 0;                                // bit s: parity to wait for on stage s
+   int4 d = nmine > 0 ? __ldg(M.blk + team_cta) : make_int4(0, 0, 0, 0);
+   for (int i = 0; i < nmine; i++) {
+      const int b = team_cta + i * team_nctas;
+      const int stage = i % ST;
+      const int r0 = d.x, r1 = d.y, p0 = d.z, p1 = d.w, q0 = p0 & ~3, nr = r1 - r0;
+      int4 dn = make_int4(0, 0, 0, 0), dp = dn;
+      if (i + 1 < nmine) dn = __ldg(M.blk + b + team_nctas);
+      if (tid == 0 && i + ST < nmine) dp = __ldg(M.blk + b + ST * team_nctas);
+      if (p1 - q0 > CAP) {
+         double acc = 0.0;
+         for (int p = p0 + tid; p < p1; p += 256) acc += ld_stream(va + p) * ld_x<RO>(x + ld_stream(M.ci + p));
+         acc = block_sum(acc);
+         if (tid == 0) {
+            const double v = epilogue_apply<RO>(e, r0, acc);
+            y[r0] = v;
+            if (want_sumsq) sumsq += v * v;
+         }
+         __syncthreads();
+      } else {
+         // lanes per row: the largest power of two (<= 32) such that all rows fit in one pass
+         int lpr = 1;
+         while (lpr < 32 && nr * (lpr << 1) <= 256) lpr <<= 1;
+         const int lane = tid & (lpr - 1);
+         const int rows_per_pass = 256 / lpr;
+         // first pass: row pointers and epilogue operands loaded before the barrier wait
+         const int row_a = r0 + tid / lpr;
+         const bool ok_a = row_a < r1;
+         int s_a = 0, t_a = 0;
+         EpiOps o_a = {0.0, 0.0, 1.0};
+         if (ok_a) {
+            s_a = __ldg(M.rp + row_a) - q0;
+            t_a = __ldg(M.rp + row_a + 1) - q0;
+            if (lane == 0) o_a = epilogue_load<RO>(e, row_a);
+         }
+         if (p1 > p0) {
+            mbar_wait(bar0 + 8u * stage, (phase >> stage) & 1u);
+            phase ^= 1u << stage;
+         }
+         const int *cs = scol + stage * CAP;
+         double *vs = sval + stage * CAP;
+         // products in place.  Consecutive lanes take consecutive entries: neighbouring entries of a row
+         // mostly point at neighbouring x, so one gather instruction touches few 128-byte lines (the
+         // L1 wavefront count per gather, not HBM, is what limits a scattered mapping).
+         const int first = p0 - q0, cnt = p1 - q0;
+         double xv[AMGB_STREAM_CAP / 256];
+#pragma unroll
+         for (int k = 0; k < AMGB_STREAM_CAP / 256; k++) {
+            const int q = tid + 256 * k;
+            xv[k] = (q >= first && q < cnt) ? ld_x<RO>(x + cs[q]) : 0.0;
+         }
+#pragma unroll
+         for (int k = 0; k < AMGB_STREAM_CAP / 256; k++) {
+            const int q = tid + 256 * k;
+            if (q < cnt) vs[q] = (q >= first) ? vs[q] * xv[k] : 0.0;
+         }
+         __syncthreads();
+         {
+            double acc = 0.0;
+            for (int q = s_a + lane; q < t_a; q += lpr) acc += vs[q];
+            for (int o = lpr >> 1; o > 0; o >>= 1) acc += __shfl_down_sync(AMGB_FULL, acc, o, 32);
+            if (lane == 0 && ok_a) {
+               const double v = epilogue_finish(e, o_a, acc);
+               y[row_a] = v;
+               if (want_sumsq) sumsq += v * v;
+            }
+         }
+         for (int base = rows_per_pass; base < nr; base += rows_per_pass) {   // only when lpr == 1
+            const int row = r0 + base + tid;
+            if (row < r1) {
+               const int s1 = __ldg(M.rp + row) - q0, t1 = __ldg(M.rp + row + 1) - q0;
+               double acc = 0.0;
+               for (int q = s1; q < t1; q++) acc += vs[q];
+               const double v = epilogue_apply<RO>(e, row, acc);
+               y[row] = v;
+               if (want_sumsq) sumsq += v * v;
+            }
+         }
+         __syncthreads();                              // the stage is free again
       }
+      if (tid == 0 && i + ST < nmine) {
+         fence_proxy_async();
+         issue(dp, stage);
+      }
+      d = dn;
    }
-   return sumsq;
-}
-
-// all row blocks of M, dealt round-robin to the CTAs of a team; returns the thread's sum of y_i^2
-template <bool RO, bool SVAL>
-__device__ __forceinline__ double stream_rows_team(const DevCSR &M, const double *x, double *y, const SpmvEpilogue &e,
-                                                   int team_cta, int team_nctas, double *sprod, bool want_sumsq)
-{
-   double sumsq = 0.0;
-   for (int b = team_cta; b < M.nblk; b += team_nctas) {
-      sumsq += stream_block<RO, SVAL>(M, b, x, y, e, sprod, want_sumsq);
-      __syncthreads();                                 // sprod is reused by the next block
-   }
+   __syncthreads();
+   if (tid == 0)
+      for (int s = 0; s < ST; s++) mbar_inval(bar0 + 8u * s);   // the memory may be re-initialised by the next call
    return sumsq;
 }
 
@@ -180,14 +222,14 @@ __device__ __forceinline__ double csr_rows_dispatch(const DevCSR &M, const doubl
 
 
 // dispatch on storage + lanes per row
-// (team_tid, team_size) = (team_cta * 256 + threadIdx.x, team_nctas * 256); sprod: AMGB_STREAM_CAP doubles
-// of shared memory
+// (team_tid, team_size) = (team_cta * 256 + threadIdx.x, team_nctas * 256); smem: AMGB_STREAM_SMEM bytes
+// of 16-byte aligned shared memory
 template <bool RO, bool SVAL>
 __device__ __forceinline__ double spmv_team(const DevCSR &M, const double *x, double *y, const SpmvEpilogue &e,
-                                            int team_tid, int team_size, bool want_sumsq, double *sprod)
+                                            int team_tid, int team_size, bool want_sumsq, unsigned char *smem)
 {
    if (M.sell_slices > 0) return sell_rows_team<RO, SVAL>(M, x, y, e, team_tid, team_size, want_sumsq);
-   if (M.nblk > 0) return stream_rows_team<RO, SVAL>(M, x, y, e, team_tid >> 8, team_size >> 8, sprod, want_sumsq);
+   if (M.nblk > 0) return stream_rows_team<RO, SVAL>(M, x, y, e, team_tid >> 8, team_size >> 8, smem, want_sumsq);
    return csr_rows_dispatch<RO, SVAL>(M, x, y, e, team_tid, team_size, want_sumsq);
 }
 

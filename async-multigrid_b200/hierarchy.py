@@ -43,6 +43,8 @@ def host_lib():
         L.amgh_level_P.argtypes = [C.c_void_p, C.c_int]
         L.amgh_num_levels.argtypes = [C.c_void_p]
         L.amgh_destroy.argtypes = [C.c_void_p]
+        L.amgh_level_cpts.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.amgh_level_cpts.restype = None
         L.amgh_rand_fill.argtypes = [C.c_void_p, C.c_long, C.c_double, C.c_double, C.c_uint]
         L.amgh_rand_fill.restype = None
         L.amgh_csr_free.argtypes = [C.POINTER(_CSR)]
@@ -157,6 +159,7 @@ class Hierarchy:
         self.R = None
         self.smooth_weight = None
         self.l1 = None
+        self.cpts = None      # cpts[l][j]: level-l index of coarse point j of level l+1 (row partitions follow it)
 
     def build_transfers(self, solver=MULTADD, smooth_weight=1.0, smooth_interp_type=JACOBI,
                         num_pre=1, num_post=1):
@@ -208,8 +211,15 @@ def amg_setup(A, theta=0.25, max_levels=25, max_coarse=9, pmax=4, jacobi_interp_
     nl = L.amgh_num_levels(h)
     As = [_take(L.amgh_level_A(h, l).contents, free=False) for l in range(nl)]
     Ps = [_take(L.amgh_level_P(h, l).contents, free=False) for l in range(nl - 1)]
+    cpts = []
+    for l in range(nl - 1):
+        c = np.empty(As[l + 1].nrows, dtype=np.int32)
+        L.amgh_level_cpts(h, l, c.ctypes.data_as(C.c_void_p))
+        cpts.append(c)
     L.amgh_destroy(h)
-    return Hierarchy(As, Ps)
+    hh = Hierarchy(As, Ps)
+    hh.cpts = cpts
+    return hh
 
 
 # ---------------------------------------------------------------------------------------------

@@ -348,6 +348,7 @@ void truncate_rows(amgh_csr *P, int pmax)
 struct Hierarchy {
    std::vector<amgh_csr> A;   // diag-first
    std::vector<amgh_csr> P;   // n_l x n_{l+1}, sorted rows
+   std::vector<std::vector<int>> cpts;   // cpts[l][j] = level-l index of coarse point j of level l+1 (ascending)
 };
 
 }  // namespace
@@ -501,6 +502,8 @@ void *amgh_setup(const amgh_csr *A0, double theta, int max_levels, int max_coars
       int nc = 0;
       for (int r = 0; r < n; r++) if (cf[r] == 1) cidx[r] = nc++;
       if (nc == 0 || nc == n) { amgh_csr_free(&S); break; }
+      std::vector<int> cp(nc);
+      for (int r = 0; r < n; r++) if (cf[r] == 1) cp[cidx[r]] = r;
       amgh_csr P; direct_interp(Af, S, cf, cidx, nc, &P);
       amgh_csr_free(&S);
       for (int it = 0; it < jacobi_interp_steps; it++) {
@@ -533,6 +536,7 @@ void *amgh_setup(const amgh_csr *A0, double theta, int max_levels, int max_coars
                 (int)H->A.size() - 1, n, Af.nnz, nc, P.nnz, Ac.nnz, omp_get_wtime() - t0);
       H->P.push_back(P);
       H->A.push_back(Ac);
+      H->cpts.push_back(std::move(cp));
    }
    return H;
 }
@@ -540,6 +544,12 @@ void *amgh_setup(const amgh_csr *A0, double theta, int max_levels, int max_coars
 int amgh_num_levels(void *h) { return (int)((Hierarchy *)h)->A.size(); }
 const amgh_csr *amgh_level_A(void *h, int l) { return &((Hierarchy *)h)->A[l]; }
 const amgh_csr *amgh_level_P(void *h, int l) { return &((Hierarchy *)h)->P[l]; }
+// fine-level indices of the coarse points chosen on level l (length = rows of level l+1, ascending)
+void amgh_level_cpts(void *h, int l, int *out)
+{
+   const std::vector<int> &c = ((Hierarchy *)h)->cpts[l];
+   memcpy(out, c.data(), sizeof(int) * c.size());
+}
 void amgh_destroy(void *h)
 {
    Hierarchy *H = (Hierarchy *)h;

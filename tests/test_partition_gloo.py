@@ -1,0 +1,109 @@
+"""Host logic of the multi-GPU (DMEM replacement) path, on CPU: the row partition / extended numbering /
+halo plan of async-multigrid_b200/partition.py executed by the numpy emulator over torch.distributed
+(gloo, world_size 2 and 3) must reproduce the GLOBAL oracle cycle and solve history.  csrc/dist.cu executes
+the same plan with the sm_100a kernels over NCCL."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, prob, n, min_rows, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    os.environ["OMP_NUM_THREADS"] = "1"
+    import torch.distributed as dist
+    import async_multigrid_b200 as amg  # noqa: F401
+    from async_multigrid_b200 import hierarchy as H, partition as PT
+    from oracle import oracle as O
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        w = 0.9
+        A = H.laplacian(prob, n)
+        h = H.amg_setup(A)
+        h.build_transfers(H.MULTADD, w)
+        b = H.rand_rhs(A.nrows)
+        plane = n * n if prob != "5pt" else n
+        plan = PT.RankPlan(h, world, rank, plane=plane, min_rows_per_rank=min_rows)
+        lay0 = plan.layouts[0]
+        em = PT.DistEmulator(plan, PT.TorchComm(), w)
+        # one cycle on the right-hand side vs the global oracle
+        r0 = em.new_vec(0)
+        em.owned(0, r0)[:] = b[lay0.row_start:lay0.row_start + lay0.n_owned]
+        c = em.owned(0, em.cycle(r0))
+        pb = O.Problem(h, H.MULTADD, H.JACOBI, w)
+        want = pb.cycle(b)[lay0.row_start:lay0.row_start + lay0.n_owned]
+        err_cycle = float(np.max(np.abs(c - want)) / np.max(np.abs(want)))
+        # whole solve: history vs the global oracle
+        u, hist = em.solve(b[lay0.row_start:lay0.row_start + lay0.n_owned], 1e-9, 100)
+        _, want_hist, _ = pb.solve_sync(b, 1e-9, 100)
+        ok_len = len(hist) == len(want_hist)
+        err_hist = float(np.max(np.abs(hist - want_hist))) if ok_len else 1.0
+        q.put((rank, plan.num_dist, err_cycle, err_hist, ok_len, [l.n_owned for l in plan.layouts],
+               [(l.halo_lo, l.halo_hi) for l in plan.layouts]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,prob,n,min_rows", [(2, "7pt", 16, 64), (3, "7pt", 18, 32), (2, "5pt", 48, 100)])
+def test_distributed_plan_reproduces_global_cycle(world, prob, n, min_rows):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, prob, n, min_rows, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, num_dist, err_cycle, err_hist, ok_len, owned, halos in res:
+        assert num_dist >= 2, (num_dist, owned)          # at least two levels are really partitioned
+        assert num_dist < len(owned)                      # and the coarse tail is replicated
+        assert err_cycle <= 1e-12, err_cycle
+        assert ok_len and err_hist <= 1e-10, err_hist
+
+
+def test_partition_layout_properties():
+    sys.path.insert(0, ROOT)
+    import async_multigrid_b200 as amg  # noqa: F401
+    from async_multigrid_b200 import hierarchy as H, partition as PT
+    A = H.laplacian("7pt", 16)
+    h = H.amg_setup(A)
+    h.build_transfers(H.MULTADD, 0.9)
+    for world in (1, 2, 4):
+        starts, num_dist, halos = PT.plan_layouts(h, world, plane=256, min_rows_per_rank=64)
+        for l, s in enumerate(starts):
+            assert s[0] == 0 and s[-1] == h.n[l] and np.all(np.diff(s) >= 0)
+        if world == 1:
+            assert num_dist == 0
+            continue
+        assert np.all(starts[0] % 256 == 0)                # whole z-planes on level 0
+        for rank in range(world):
+            plan = PT.RankPlan(h, world, rank, plan=(starts, num_dist, halos))
+            for l, lay in enumerate(plan.layouts):
+                if lay.distributed:
+                    # every column of the local blocks lands inside the extended range; the diagonal sits at halo_lo + i
+                    a = plan.A[l]
+                    assert a.ncols == lay.n_ext
+                    assert np.all(a.indices[a.indptr[:-1]] == lay.halo_lo + np.arange(lay.n_owned))
+                    # what I send is what my neighbour expects
+                    if rank > 0:
+                        assert lay.send_lo == halos[l][rank - 1][1]
+                    if rank < world - 1:
+                        assert lay.send_hi == halos[l][rank + 1][0]
+                else:
+                    assert plan.A[l].nrows == h.n[l]
