@@ -9,5 +9,5 @@ Importable as ``importlib.import_module("async-multigrid_b200")`` or through the
              (include/amg_b200.h -> libamg_b200.so, hand-written sm_100a kernels)
   build      in-tree nvcc / g++ builds
 """
-from . import build, hierarchy, solver  # noqa: F401
-from .solver import Solver, AmgError  # noqa: F401
+from . import build, hierarchy, partition, solver  # noqa: F401
+from .solver import Solver, DistSolver, AmgError  # noqa: F401

@@ -66,6 +66,8 @@ def build_cuda(force=False, verbose=False):
     if inc:
         cmd += ["-DAMG_HAVE_NCCL=1", "-I", inc]
     cmd += srcs + ["-o", CUDA_LIB, "-lcudart", "-lgomp"]
+    if inc:
+        cmd += ["-L", lib, "-l:libnccl.so.2", "-Xlinker", "-rpath=" + lib]
     out = _run(cmd)
     if verbose:
         print(out)

@@ -234,9 +234,10 @@ int amgb_set_matrix(amgb_ctx *c, int kind, int level, int nrows, int ncols, int 
    DevCSR &M = kind == AMGB_MAT_A ? c->A[level] : (kind == AMGB_MAT_P ? c->P[level] : c->R[level]);
    if (M.rp) return amgb_fail(c, AMGB_ESTATE, "matrix (kind %d, level %d) already set", kind, level);
    if (kind == AMGB_MAT_A) {
-      if (nrows != ncols) return amgb_fail(c, AMGB_EINVAL, "A must be square");
+      if (nrows != ncols && !c->dist) return amgb_fail(c, AMGB_EINVAL, "A must be square");
+      const int doff = amgb_dist_diag_offset(c, level);   // local row block of a partitioned level: extended numbering
       for (int r = 0; r < nrows; r++)
-         if (rp[r + 1] > rp[r] && ci[rp[r]] != r) return amgb_fail(c, AMGB_EINVAL, "A_%d row %d is not diagonal-first", level, r);
+         if (rp[r + 1] > rp[r] && ci[rp[r]] != r + doff) return amgb_fail(c, AMGB_EINVAL, "A_%d row %d is not diagonal-first", level, r);
    }
    int *d_rp, *d_ci; double *d_va;
    int rc;
@@ -267,8 +268,8 @@ int amgb_setup(amgb_ctx *c)
       if (!c->A[l].rp) return amgb_fail(c, AMGB_ESTATE, "A_%d missing", l);
       if (l < L - 1) {
          if (!c->P[l].rp || !c->R[l].rp) return amgb_fail(c, AMGB_ESTATE, "P_%d / R_%d missing", l, l);
-         if (c->P[l].nrows != c->A[l].nrows || c->P[l].ncols != c->A[l + 1].nrows ||
-             c->R[l].nrows != c->A[l + 1].nrows || c->R[l].ncols != c->A[l].nrows)
+         if (!c->dist && (c->P[l].nrows != c->A[l].nrows || c->P[l].ncols != c->A[l + 1].nrows ||
+                          c->R[l].nrows != c->A[l + 1].nrows || c->R[l].ncols != c->A[l].nrows))
             return amgb_fail(c, AMGB_EINVAL, "transfer shapes at level %d do not match", l);
       }
    }
@@ -294,13 +295,15 @@ int amgb_setup(amgb_ctx *c)
       double *sv = nullptr;
       if ((rc = dev_alloc(c, &sv, (size_t)c->A[l].nnz))) return rc;
       const double *cs = (o.smoother == AMGB_SMOOTH_L1_JACOBI) ? c->inv_l1[l] : c->ws[l];
-      c->launches += launch_colscale(c->stream, c->A[l].nnz, c->A[l].ci, c->A[l].va, cs, sv);
+      // (a partitioned level's columns are in the rank's extended numbering: amgb_dist_setup fills sval there)
+      const bool part = amgb_dist_level_distributed(c, l);
+      if (!part) c->launches += launch_colscale(c->stream, c->A[l].nnz, c->A[l].ci, c->A[l].va, cs, sv);
       c->A[l].sval = sv;
       if (c->A[l].sell_slices > 0) {
          long pe = c->sell_entries[&c->A[l]];
          double *ssv = nullptr;
          if ((rc = dev_alloc(c, &ssv, (size_t)pe))) return rc;
-         c->launches += launch_colscale(c->stream, (int)pe, c->A[l].sell_ci, c->A[l].sell_va, cs, ssv);
+         if (!part) c->launches += launch_colscale(c->stream, (int)pe, c->A[l].sell_ci, c->A[l].sell_va, cs, ssv);
          c->A[l].sell_sval = ssv;
       }
       if ((rc = dev_zero(c, &c->r[l], n))) return rc;

@@ -49,6 +49,8 @@ struct amgb_ctx {
 
 int amgb_fail(amgb_ctx *c, int code, const char *fmt, ...);
 void amgb_dist_teardown(amgb_ctx *c);
+int amgb_dist_diag_offset(const amgb_ctx *c, int level);          // position of the diagonal in a local row block
+bool amgb_dist_level_distributed(const amgb_ctx *c, int level);
 
 #define CUDA_OK(c, call)                                                                                   \
    do {                                                                                                    \

@@ -1,38 +1,363 @@
-// dist.cu -- multi-GPU (DMEM replacement) entry points.  Round-1 state: the row-partitioned
-// NCCL path is declared in include/amg_b200.h; until it lands these report AMGB_ESTATE so a
-// caller can never mistake a missing implementation for a result.
+// dist.cu -- multi-GPU synchronous additive solve: one process per GPU, rows of every level partitioned
+// contiguously, NCCL over NVLink for the halo exchange, the coarse all-gather and the norms.
+//
+// Replaces, for the synchronous Multadd cycle, the reference's DMEM path: DMEM_Add / DMEM_SyncAdd
+// (src/DMEM_Add.cpp:20-178, src/DMEM_Mult.cpp:263-450), whose distributed SpMVs are hypre ParCSR matvecs
+// (halo exchange through hypre's comm_pkg, src/DMEM_Add.cpp:230-249,277-308) and whose vector traffic
+// goes through DMEM_Comm's MPI engine (src/DMEM_Comm.cpp:81-382); the residual norm is an Allreduce
+// (src/DMEM_Misc.cpp:398-433).
+//
+// Layout (host logic in async-multigrid_b200/partition.py): a DISTRIBUTED level's vectors live in the
+// rank's extended index space [ghost_lo | owned | ghost_hi]; the local row blocks of A_l, P_l, R_l carry
+// column indices in that space, so the SpMV kernels are the single-GPU ones and a halo exchange is two
+// contiguous ncclSend/ncclRecv pairs with the immediate neighbours, no packing.  REPLICATED levels (the
+// small coarse tail) hold full vectors and matrices on every rank; the first replicated level's
+// residual is all-gathered, everything coarser is computed redundantly with no communication.
 #include "ctx.h"
+#include <algorithm>
+#include <cmath>
 #include <cstring>
+#include <vector>
 #ifdef AMG_HAVE_NCCL
 #include <nccl.h>
 #endif
 
-struct DistState { int rank = 0, nranks = 1; };
+struct DistLevel {
+   int n_global = 0, row_start = 0, n_owned = 0, halo_lo = 0, halo_hi = 0, distributed = 0, send_lo = 0, send_hi = 0;
+   bool set = false;
+   std::vector<int> all_owned;   // n_owned of every rank (all-gather counts)
+   int n_ext() const { return distributed ? halo_lo + n_owned + halo_hi : n_global; }
+   int off() const { return distributed ? halo_lo : 0; }   // position of the first owned entry
+};
+
+struct DistState {
+   int rank = 0, nranks = 1;
+#ifdef AMG_HAVE_NCCL
+   ncclComm_t comm = nullptr;
+#endif
+   std::vector<DistLevel> lv;
+   std::vector<double *> ws, r, e;   // level layout
+   double *u = nullptr, *f = nullptr;   // u: level-0 layout; f: owned rows
+   bool ready = false;
+   long long halo_bytes = 0, collectives = 0;
+};
 
 void amgb_dist_teardown(amgb_ctx *c)
 {
-   if (c && c->dist) { delete c->dist; c->dist = nullptr; }
+   if (c && c->dist) {
+#ifdef AMG_HAVE_NCCL
+      if (c->dist->comm) ncclCommDestroy(c->dist->comm);
+#endif
+      delete c->dist;
+      c->dist = nullptr;
+   }
 }
 
+int amgb_dist_diag_offset(const amgb_ctx *c, int level)
+{
+   if (!c->dist || level >= (int)c->dist->lv.size() || !c->dist->lv[level].set) return 0;
+   return c->dist->lv[level].off();
+}
+bool amgb_dist_level_distributed(const amgb_ctx *c, int level)
+{
+   return c->dist && level < (int)c->dist->lv.size() && c->dist->lv[level].set && c->dist->lv[level].distributed;
+}
+
+#ifdef AMG_HAVE_NCCL
+#define NCCL_OK(c, call)                                                                                    \
+   do {                                                                                                     \
+      ncclResult_t r__ = (call);                                                                            \
+      if (r__ != ncclSuccess)                                                                               \
+         return amgb_fail((c), AMGB_ENCCL, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, ncclGetErrorString(r__)); \
+   } while (0)
+
+static inline SpmvEpilogue epi(double alpha, double beta, const double *b, double gamma = 0.0, const double *cc = nullptr,
+                               const double *rs = nullptr)
+{
+   SpmvEpilogue e;
+   e.alpha = alpha; e.beta = beta; e.gamma = gamma; e.b = b; e.c = cc; e.rs = rs;
+   return e;
+}
+
+// ghosts of v (level layout) <- neighbours' boundary entries
+static int halo(amgb_ctx *c, int l, double *v)
+{
+   DistState *d = c->dist;
+   const DistLevel &L = d->lv[l];
+   if (!L.distributed) return AMGB_OK;
+   double *own = v + L.halo_lo;
+   NCCL_OK(c, ncclGroupStart());
+   if (d->rank > 0) {
+      if (L.send_lo) NCCL_OK(c, ncclSend(own, (size_t)L.send_lo, ncclDouble, d->rank - 1, d->comm, c->stream));
+      if (L.halo_lo) NCCL_OK(c, ncclRecv(v, (size_t)L.halo_lo, ncclDouble, d->rank - 1, d->comm, c->stream));
+   }
+   if (d->rank < d->nranks - 1) {
+      if (L.send_hi) NCCL_OK(c, ncclSend(own + L.n_owned - L.send_hi, (size_t)L.send_hi, ncclDouble, d->rank + 1, d->comm, c->stream));
+      if (L.halo_hi) NCCL_OK(c, ncclRecv(own + L.n_owned, (size_t)L.halo_hi, ncclDouble, d->rank + 1, d->comm, c->stream));
+   }
+   NCCL_OK(c, ncclGroupEnd());
+   d->halo_bytes += 8LL * (L.send_lo + L.send_hi);
+   d->collectives++;
+   return AMGB_OK;
+}
+
+// every rank's owned slice of a replicated vector -> everybody (in place)
+static int allgather_level(amgb_ctx *c, int l, double *v)
+{
+   DistState *d = c->dist;
+   const DistLevel &L = d->lv[l];
+   NCCL_OK(c, ncclGroupStart());
+   size_t off = 0;
+   for (int p = 0; p < d->nranks; p++) {
+      const size_t cnt = (size_t)L.all_owned[p];
+      if (cnt) NCCL_OK(c, ncclBroadcast(v + off, v + off, cnt, ncclDouble, p, d->comm, c->stream));
+      off += cnt;
+   }
+   NCCL_OK(c, ncclGroupEnd());
+   d->collectives++;
+   return AMGB_OK;
+}
+
+// r_0 = f - A_0 u on the owned rows, d_scalars[0] = global ||r||^2
+static int dist_residual(amgb_ctx *c)
+{
+   DistState *d = c->dist;
+   int rc;
+   if ((rc = halo(c, 0, d->u))) return rc;
+   enq_spmv(c, c->A[0], false, d->u, d->r[0] + d->lv[0].off(), epi(-1.0, 1.0, d->f), true);
+   NCCL_OK(c, ncclAllReduce(c->d_scalars, c->d_scalars, 1, ncclDouble, ncclSum, d->comm, c->stream));
+   d->collectives++;
+   return AMGB_OK;
+}
+
+// one synchronous Multadd cycle on r[0]; u += B r   (SMEM_Sync_Add_Vcycle semantics, src/SEQ_AMG.cpp:110-235;
+// DMEM analogue DMEM_SyncAddCycle, src/DMEM_Mult.cpp:322-450, with the SMEM convention that the coarsest
+// level contributes nothing)
+static int dist_cycle(amgb_ctx *c)
+{
+   DistState *d = c->dist;
+   const int L = c->L;
+   int rc;
+   if (L == 1) return AMGB_OK;
+   for (int l = 0; l < L - 2; l++) {
+      if ((rc = halo(c, l, d->r[l]))) return rc;
+      const DistLevel &nx = d->lv[l + 1];
+      const bool gather = d->lv[l].distributed && !nx.distributed;
+      double *out = d->r[l + 1] + (gather ? nx.row_start : nx.off());
+      enq_spmv(c, c->R[l], false, d->r[l], out, epi(1.0, 0.0, nullptr), false);
+      if (gather && (rc = allgather_level(c, l + 1, d->r[l + 1]))) return rc;
+   }
+   if ((rc = halo(c, L - 2, d->r[L - 2]))) return rc;
+   for (int l = 0; l < L - 1; l++) {
+      const DistLevel &lv = d->lv[l];
+      const double *rown = d->r[l] + lv.off();
+      const double *ws = d->ws[l] + lv.off();
+      if (c->symmetric)   // e = (w/d) o (2 r - (A diag(w/d)) r)
+         enq_spmv(c, c->A[l], true, d->r[l], d->e[l] + lv.off(), epi(-1.0, 2.0, rown, 0.0, nullptr, ws), false);
+      else
+         c->launches += launch_scale(c->cfg, c->stream, c->A[l].nrows, ws, rown, d->e[l] + lv.off());
+   }
+   for (int l = L - 3; l >= 1; l--) {
+      if ((rc = halo(c, l + 1, d->e[l + 1]))) return rc;
+      double *eo = d->e[l] + d->lv[l].off();
+      enq_spmv(c, c->P[l], false, d->e[l + 1], eo, epi(1.0, 1.0, eo), false);
+   }
+   double *uo = d->u + d->lv[0].off();
+   if (L >= 3) {
+      if ((rc = halo(c, 1, d->e[1]))) return rc;
+      enq_spmv(c, c->P[0], false, d->e[1], uo, epi(1.0, 1.0, d->e[0] + d->lv[0].off(), 1.0, uo), false);
+   } else {
+      c->launches += launch_add(c->cfg, c->stream, c->A[0].nrows, d->e[0] + d->lv[0].off(), uo);
+   }
+   return AMGB_OK;
+}
+#endif   // AMG_HAVE_NCCL
+
 extern "C" {
+
 int amgb_dist_unique_id(unsigned char id128[128])
 {
+#ifdef AMG_HAVE_NCCL
+   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+   ncclUniqueId id;
+   if (ncclGetUniqueId(&id) != ncclSuccess) return AMGB_ENCCL;
+   memcpy(id128, &id, 128);
+   return AMGB_OK;
+#else
    (void)id128;
-   return AMGB_ESTATE;
+   return AMGB_ENCCL;
+#endif
 }
+
 int amgb_dist_init(amgb_ctx *c, const unsigned char id128[128], int rank, int nranks)
 {
-   (void)id128; (void)rank; (void)nranks;
-   return amgb_fail(c, AMGB_ESTATE, "distributed path not implemented in this build");
+   if (!c || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return amgb_fail(c, AMGB_EINVAL, "bad rank / nranks");
+   if (c->dist) return amgb_fail(c, AMGB_ESTATE, "amgb_dist_init called twice");
+   if (c->L) return amgb_fail(c, AMGB_ESTATE, "amgb_dist_init must precede the hierarchy upload");
+#ifdef AMG_HAVE_NCCL
+   CUDA_OK(c, cudaSetDevice(c->device));
+   DistState *d = new DistState();
+   d->rank = rank; d->nranks = nranks;
+   ncclUniqueId id;
+   memcpy(&id, id128, 128);
+   ncclResult_t r = ncclCommInitRank(&d->comm, nranks, id, rank);
+   if (r != ncclSuccess) { delete d; return amgb_fail(c, AMGB_ENCCL, "ncclCommInitRank: %s", ncclGetErrorString(r)); }
+   c->dist = d;
+   return AMGB_OK;
+#else
+   return amgb_fail(c, AMGB_ENCCL, "library built without NCCL");
+#endif
 }
-int amgb_dist_set_partition(amgb_ctx *c, int level, const int *row_starts)
+
+int amgb_dist_set_level(amgb_ctx *c, int level, int n_global, int row_start, int n_owned, int halo_lo, int halo_hi,
+                        int distributed, int send_lo, int send_hi, const int *all_owned)
 {
-   (void)level; (void)row_starts;
-   return amgb_fail(c, AMGB_ESTATE, "distributed path not implemented in this build");
+   if (!c || !c->dist) return amgb_fail(c, AMGB_ESTATE, "amgb_dist_init not called");
+   if (c->L == 0) return amgb_fail(c, AMGB_ESTATE, "call amgb_set_num_levels first");
+   if (level < 0 || level >= c->L || n_global < 0 || n_owned < 0 || row_start < 0 || row_start + n_owned > n_global ||
+       halo_lo < 0 || halo_hi < 0 || send_lo < 0 || send_hi < 0 || send_lo > n_owned || send_hi > n_owned || !all_owned)
+      return amgb_fail(c, AMGB_EINVAL, "bad level layout");
+   DistState *d = c->dist;
+   if ((int)d->lv.size() != c->L) d->lv.resize(c->L);
+   if (c->A[level].rp) return amgb_fail(c, AMGB_ESTATE, "amgb_dist_set_level must precede amgb_set_matrix for level %d", level);
+   DistLevel &L = d->lv[level];
+   L.n_global = n_global; L.row_start = row_start; L.n_owned = n_owned;
+   L.distributed = distributed ? 1 : 0;
+   L.halo_lo = distributed ? halo_lo : 0; L.halo_hi = distributed ? halo_hi : 0;
+   L.send_lo = distributed ? send_lo : 0; L.send_hi = distributed ? send_hi : 0;
+   L.all_owned.assign(all_owned, all_owned + d->nranks);
+   long tot = 0;
+   for (int v : L.all_owned) tot += v;
+   if (tot != n_global || L.all_owned[d->rank] != n_owned) return amgb_fail(c, AMGB_EINVAL, "owned counts of level %d do not add up", level);
+   if (level > 0 && L.distributed && !d->lv[level - 1].distributed) return amgb_fail(c, AMGB_EINVAL, "a distributed level below a replicated one");
+   L.set = true;
+   return AMGB_OK;
 }
-int amgb_dist_solve_sync(amgb_ctx *c, double tol, int max_cycles, double *relres_hist, int *n_cycles, double *solve_seconds)
+
+int amgb_dist_setup(amgb_ctx *c)
 {
-   (void)tol; (void)max_cycles; (void)relres_hist; (void)n_cycles; (void)solve_seconds;
-   return amgb_fail(c, AMGB_ESTATE, "distributed path not implemented in this build");
+   NEED_READY(c);
+#ifdef AMG_HAVE_NCCL
+   DistState *d = c->dist;
+   if (!d) return amgb_fail(c, AMGB_ESTATE, "amgb_dist_init not called");
+   if (d->ready) return amgb_fail(c, AMGB_ESTATE, "amgb_dist_setup already done");
+   const int L = c->L;
+   const amgb_options &o = c->opt;
+   if (o.solver != AMGB_SOLVER_MULTADD || o.smoother != AMGB_SMOOTH_JACOBI)
+      return amgb_fail(c, AMGB_EINVAL, "the distributed path implements synchronous Multadd with (symmetrised) weighted Jacobi");
+   if ((int)d->lv.size() != L) return amgb_fail(c, AMGB_ESTATE, "level layouts missing");
+   int rc;
+   for (int l = 0; l < L; l++) {
+      const DistLevel &lv = d->lv[l];
+      if (!lv.set) return amgb_fail(c, AMGB_ESTATE, "layout of level %d missing", l);
+      const int rows = lv.distributed ? lv.n_owned : lv.n_global;
+      if (c->A[l].nrows != rows || c->A[l].ncols != lv.n_ext()) return amgb_fail(c, AMGB_EINVAL, "A_%d block shape does not match its layout", l);
+      if (l < L - 1) {
+         const DistLevel &nx = d->lv[l + 1];
+         const int prow = rows, pcol = nx.n_ext();
+         const int rrow = lv.distributed ? nx.n_owned : nx.n_global, rcol = lv.n_ext();
+         if (c->P[l].nrows != prow || c->P[l].ncols != pcol || c->R[l].nrows != rrow || c->R[l].ncols != rcol)
+            return amgb_fail(c, AMGB_EINVAL, "transfer block shapes at level %d do not match the layouts", l);
+      }
+   }
+   d->ws.assign(L, nullptr); d->r.assign(L, nullptr); d->e.assign(L, nullptr);
+   for (int l = 0; l < L; l++) {
+      const DistLevel &lv = d->lv[l];
+      const size_t bytes = sizeof(double) * (size_t)lv.n_ext();
+      if ((rc = amgb_dev_alloc_bytes(c, (void **)&d->ws[l], bytes, true))) return rc;
+      if ((rc = amgb_dev_alloc_bytes(c, (void **)&d->r[l], bytes, true))) return rc;
+      if ((rc = amgb_dev_alloc_bytes(c, (void **)&d->e[l], bytes, true))) return rc;
+      // w/d of the owned rows, ghosts from the neighbours, then the column-scaled values of the one-pass
+      // symmetrised smoother (on replicated levels amgb_setup already did this)
+      CUDA_OK(c, cudaMemcpyAsync(d->ws[l] + lv.off(), c->ws[l], sizeof(double) * c->A[l].nrows, cudaMemcpyDeviceToDevice, c->stream));
+      if (lv.distributed) {
+         if ((rc = halo(c, l, d->ws[l]))) return rc;
+         c->launches += launch_colscale(c->stream, c->A[l].nnz, c->A[l].ci, c->A[l].va, d->ws[l], const_cast<double *>(c->A[l].sval));
+         if (c->A[l].sell_slices > 0)
+            c->launches += launch_colscale(c->stream, (int)c->sell_entries[&c->A[l]], c->A[l].sell_ci, c->A[l].sell_va, d->ws[l],
+                                           const_cast<double *>(c->A[l].sell_sval));
+      }
+   }
+   if ((rc = amgb_dev_alloc_bytes(c, (void **)&d->u, sizeof(double) * (size_t)d->lv[0].n_ext(), true))) return rc;
+   if ((rc = amgb_dev_alloc_bytes(c, (void **)&d->f, sizeof(double) * (size_t)std::max(1, c->A[0].nrows), true))) return rc;
+   CUDA_OK(c, cudaStreamSynchronize(c->stream));
+   d->halo_bytes = 0; d->collectives = 0;
+   d->ready = true;
+   return AMGB_OK;
+#else
+   return amgb_fail(c, AMGB_ENCCL, "library built without NCCL");
+#endif
 }
+
+int amgb_dist_set_rhs(amgb_ctx *c, const double *f_owned)
+{
+   NEED_READY(c);
+   if (!c->dist || !c->dist->ready) return amgb_fail(c, AMGB_ESTATE, "amgb_dist_setup not called");
+   if (!f_owned) return amgb_fail(c, AMGB_EINVAL, "null rhs");
+   CUDA_OK(c, cudaMemcpyAsync(c->dist->f, f_owned, sizeof(double) * c->A[0].nrows, cudaMemcpyHostToDevice, c->stream));
+   CUDA_OK(c, cudaStreamSynchronize(c->stream));
+   return AMGB_OK;
 }
+
+int amgb_dist_get_solution(amgb_ctx *c, double *u_owned)
+{
+   NEED_READY(c);
+   if (!c->dist || !c->dist->ready) return amgb_fail(c, AMGB_ESTATE, "amgb_dist_setup not called");
+   if (!u_owned) return amgb_fail(c, AMGB_EINVAL, "null buffer");
+   CUDA_OK(c, cudaMemcpyAsync(u_owned, c->dist->u + c->dist->lv[0].off(), sizeof(double) * c->A[0].nrows, cudaMemcpyDeviceToHost, c->stream));
+   CUDA_OK(c, cudaStreamSynchronize(c->stream));
+   return AMGB_OK;
+}
+
+// DMEM_Add's loop (src/DMEM_Add.cpp:101-130) for the synchronous Multadd cycle: x0 = 0; cycle; residual;
+// global norm; stop test -- the same on every rank (the norm is all-reduced), so all ranks leave together.
+int amgb_dist_solve_sync(amgb_ctx *c, double tol, int max_cycles, double *hist, int *n_cycles, double *solve_seconds)
+{
+   NEED_READY(c);
+#ifdef AMG_HAVE_NCCL
+   DistState *d = c->dist;
+   if (!d || !d->ready) return amgb_fail(c, AMGB_ESTATE, "amgb_dist_setup not called");
+   if (max_cycles < 0) return amgb_fail(c, AMGB_EINVAL, "max_cycles < 0");
+   int rc;
+   CUDA_OK(c, cudaMemsetAsync(d->u, 0, sizeof(double) * (size_t)d->lv[0].n_ext(), c->stream));
+   if ((rc = dist_residual(c))) return rc;
+   double ss;
+   if ((rc = amgb_fetch_scalar(c, &ss))) return rc;
+   const double r0 = sqrt(ss);
+   if (hist) hist[0] = 1.0;
+   int done = 0;
+   CUDA_OK(c, cudaEventRecord(c->ev0, c->stream));
+   for (int k = 1; k <= max_cycles; k++) {
+      if ((rc = dist_cycle(c))) return rc;
+      if ((rc = dist_residual(c))) return rc;
+      if ((rc = amgb_fetch_scalar(c, &ss))) return rc;
+      done = k;
+      const double rel = sqrt(ss) / r0;
+      if (hist) hist[k] = rel;
+      if (rel < tol) break;
+   }
+   CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));
+   CUDA_OK(c, cudaEventSynchronize(c->ev1));
+   float ms = 0;
+   cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+   if (solve_seconds) *solve_seconds = ms * 1e-3;
+   if (n_cycles) *n_cycles = done;
+   c->r0_norm = r0;
+   CUDA_OK(c, cudaGetLastError());
+   return AMGB_OK;
+#else
+   (void)tol; (void)max_cycles; (void)hist; (void)n_cycles; (void)solve_seconds;
+   return amgb_fail(c, AMGB_ENCCL, "library built without NCCL");
+#endif
+}
+
+// halo bytes sent and NCCL operations enqueued by this rank since amgb_dist_setup
+int amgb_dist_stats(amgb_ctx *c, long long *halo_bytes, long long *collectives)
+{
+   if (!c || !c->dist) return AMGB_EINVAL;
+   if (halo_bytes) *halo_bytes = c->dist->halo_bytes;
+   if (collectives) *collectives = c->dist->collectives;
+   return AMGB_OK;
+}
+
+}   // extern "C"

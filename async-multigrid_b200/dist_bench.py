@@ -1,0 +1,209 @@
+"""bench.py's multi-GPU leg: the row-partitioned synchronous Multadd solve (DMEM_Add replacement,
+csrc/dist.cu) on N GPUs of one box, one process per GPU (torchrun), NCCL for the data path.
+
+Workload (BASELINE.json configs[4] family): 3-D 7-pt Laplacian on an n x n x (n*N) grid cut into N z-slabs of
+n^3 rows -- per-GPU work is fixed ("weak" scaling; N = 8, n = 256 is the 512^3-sized problem: 134 M rows).
+Rank 0 builds the global hierarchy on the host (as DMEM_Setup's hypre does on all ranks), cuts it into
+per-rank row blocks and hands them over through /dev/shm; the timed region is the solve only.
+"""
+import json
+import os
+import shutil
+import sys
+import time
+
+import numpy as np
+
+from . import hierarchy as H
+from . import partition as PT
+from . import solver as S
+
+
+def _log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def _save_csr(d, name, m):
+    np.save(os.path.join(d, name + "_ip.npy"), m.indptr)
+    np.save(os.path.join(d, name + "_ix.npy"), m.indices)
+    np.save(os.path.join(d, name + "_dv.npy"), m.data)
+    np.save(os.path.join(d, name + "_sh.npy"), np.asarray([m.nrows, m.ncols], dtype=np.int64))
+
+
+def _load_csr(d, name):
+    sh = np.load(os.path.join(d, name + "_sh.npy"))
+    ip = np.load(os.path.join(d, name + "_ip.npy"), mmap_mode="r")
+    ix = np.load(os.path.join(d, name + "_ix.npy"), mmap_mode="r")
+    dv = np.load(os.path.join(d, name + "_dv.npy"), mmap_mode="r")
+    m = H.CSR.__new__(H.CSR)
+    m.nrows, m.ncols = int(sh[0]), int(sh[1])
+    m.indptr, m.indices, m.data = np.ascontiguousarray(ip), ix, dv   # indices / data stay memory-mapped (no copy)
+    m.nnz = int(m.indptr[-1])
+    return m
+
+
+class _PlanFromDisk:
+    """RankPlan look-alike rebuilt from the files rank 0 wrote"""
+
+    def __init__(self, d, rank, nranks):
+        meta = json.load(open(os.path.join(d, "meta.json")))
+        self.rank, self.nranks = rank, nranks
+        self.num_levels = meta["num_levels"]
+        self.num_dist = meta["num_dist"]
+        self.all_counts = [np.asarray(c, dtype=np.int64) for c in meta["all_counts"]]
+        self.layouts = [PT.LevelLayout(*x) for x in meta["layouts"][rank]]
+        rd = os.path.join(d, "rank%d" % rank)
+        sd = os.path.join(d, "shared")
+        self.A, self.P, self.R = [], [], []
+        for l in range(self.num_levels):
+            src = rd if self.layouts[l].distributed else sd
+            self.A.append(_load_csr(src, "A%d" % l))
+            if l < self.num_levels - 1:
+                self.P.append(_load_csr(src, "P%d" % l))
+                self.R.append(_load_csr(src, "R%d" % l))
+        self.b = np.load(os.path.join(rd, "b.npy"))
+        self.info = meta["info"]
+
+
+def _build_and_scatter(args, world, d):
+    """rank 0: global problem -> plan -> per-rank blocks on /dev/shm (freed level by level)"""
+    t0 = time.time()
+    n = args.n
+    A = H.laplacian("7pt", n, n, n * world)
+    h = H.amg_setup(A, theta=args.theta)
+    h.build_transfers(H.MULTADD, args.smooth_weight, num_pre=1, num_post=args.num_post)
+    b = H.rand_rhs(A.nrows)
+    info = {"levels": h.num_levels, "n": [int(x) for x in h.n], "nnz_A": [int(a.nnz) for a in h.A],
+            "operator_complexity": round(h.operator_complexity(), 3),
+            "bytes_per_cycle": int(H.bytes_sync_multadd_cycle(h, args.num_post > 0)), "host_setup_s": round(time.time() - t0, 1)}
+    _log("[bench] global hierarchy: %d levels, n=%s, host setup %.1fs" % (h.num_levels, h.n, time.time() - t0))
+    starts, num_dist, halos = PT.plan_layouts(h, world, plane=n * n, min_rows_per_rank=args.min_rows_per_rank)
+    layouts = [PT.rank_layouts(h, world, r, starts, num_dist, halos) for r in range(world)]
+    os.makedirs(os.path.join(d, "shared"), exist_ok=True)
+    for r in range(world):
+        os.makedirs(os.path.join(d, "rank%d" % r), exist_ok=True)
+        l0 = layouts[r][0]
+        np.save(os.path.join(d, "rank%d" % r, "b.npy"), b[l0.row_start:l0.row_start + l0.n_owned])
+    L = h.num_levels
+    for l in range(L):
+        if l < num_dist:
+            for r in range(world):
+                lay, rd = layouts[r][l], os.path.join(d, "rank%d" % r)
+                _save_csr(rd, "A%d" % l, PT._block(h.A[l], lay.row_start, lay.row_start + lay.n_owned, lay.base, lay.n_ext))
+                if l < L - 1:
+                    nxt = layouts[r][l + 1]
+                    _save_csr(rd, "P%d" % l, PT._block(h.P[l], lay.row_start, lay.row_start + lay.n_owned, nxt.base, nxt.n_ext))
+                    _save_csr(rd, "R%d" % l, PT._block(h.R[l], nxt.row_start, nxt.row_start + nxt.n_owned, lay.base, lay.n_ext))
+        else:
+            sd = os.path.join(d, "shared")
+            _save_csr(sd, "A%d" % l, h.A[l])
+            if l < L - 1:
+                _save_csr(sd, "P%d" % l, h.P[l])
+                _save_csr(sd, "R%d" % l, h.R[l])
+        # free the global copies of this level as soon as they are on /dev/shm
+        h.A[l] = None
+        if l < L - 1:
+            h.P[l] = h.R[l] = None
+            h.P_plain[l] = None
+    meta = {"num_levels": L, "num_dist": num_dist, "all_counts": [[int(x) for x in np.diff(s)] for s in starts],
+            "layouts": [[[x.n_global, x.row_start, x.n_owned, x.halo_lo, x.halo_hi, x.distributed, x.send_lo, x.send_hi]
+                         for x in layouts[r]] for r in range(world)], "info": info}
+    json.dump(meta, open(os.path.join(d, "meta.json"), "w"))
+    _log("[bench] plan: %d distributed + %d replicated levels, blocks on %s after %.1fs" % (num_dist, L - num_dist, d, time.time() - t0))
+
+
+def run(args, rank, world, local):
+    import torch
+    import torch.distributed as dist
+    from bench import ClockSampler, METRIC, TOL, load_peaks
+    torch.cuda.set_device(local)
+    dist.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world)
+    if args.solver != "multadd" or args.smoother != "j":
+        raise SystemExit("bench.py --gpus N>1 runs the synchronous Multadd / weighted-Jacobi path")
+    tag = os.environ.get("MASTER_PORT", "0")
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+    d = os.path.join(base, "amgb_plan_%s" % tag)
+    if rank == 0:
+        shutil.rmtree(d, ignore_errors=True)
+        _build_and_scatter(args, world, d)
+    dist.barrier()
+    plan = _PlanFromDisk(d, rank, world)
+    uid = [S.dist_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    t0 = time.time()
+    s = S.DistSolver(plan, uid[0], args.smooth_weight, num_pre=1, num_post=args.num_post, use_sell=not args.no_sell, device=local)
+    _log("[bench] rank %d: upload + device setup %.1fs, owned rows per level %s" % (rank, time.time() - t0, [x.n_owned for x in plan.layouts]))
+    dist.barrier()
+    if rank == 0:
+        shutil.rmtree(d, ignore_errors=True)
+    f_t = torch.empty(plan.layouts[0].n_owned, dtype=torch.float64).pin_memory()
+    u_t = torch.empty_like(f_t).pin_memory()
+    f_host, u_host = f_t.numpy(), u_t.numpy()
+    f_host[:] = plan.b
+    s.set_rhs(f_host)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        dist.barrier()
+
+    for _ in range(args.warmup):
+        hist, secs = s.solve_sync(TOL, args.max_cycles)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = s.launch_count()
+    sync_all()
+    times = []
+    for _ in range(args.steps):
+        hist, secs = s.solve_sync(TOL, args.max_cycles)
+        times.append(secs)
+    sync_all()
+    launches = s.launch_count() - launches0
+    t = torch.tensor([float(np.mean(times))], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    solve_s = float(t.item())
+    # end to end: host f slice in, host u slice out, per rank; wall clock, max over ranks
+    e2e = []
+    for _ in range(args.steps + 1):
+        sync_all()
+        w0 = time.perf_counter()
+        s.set_rhs(f_host)
+        s.solve_sync(TOL, args.max_cycles)
+        s.get_solution(u_host)
+        e2e.append(time.perf_counter() - w0)
+    t = torch.tensor([float(np.mean(e2e[1:]))], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    hb, ops = s.stats()
+    hbt = torch.tensor([float(hb)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(hbt)
+    clocks = sampler.stop() if rank == 0 else None
+    cycles = len(hist) - 1
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        info = plan.info
+        solve_bytes = info["bytes_per_cycle"] * cycles
+        n0 = info["n"][0]
+        line = {
+            "metric": METRIC, "value": solve_s, "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": solve_s * 1e3, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "3D 7-pt Laplacian %dx%dx%d (n=%d) in %d z-slabs of %d^3 rows, sync Multadd, smoother j w=%.2f, tol 1e-9"
+                       % (args.n, args.n, args.n * world, n0, world, args.n, args.smooth_weight),
+                       "levels": info["levels"], "distributed_levels": plan.num_dist, "operator_complexity": info["operator_complexity"],
+                       "cycles_to_tol": int(cycles), "final_relres": float(hist[-1]), "rows_per_s": n0 / solve_s,
+                       "l2": "per-GPU inputs exceed the 126 MB L2; no explicit flush",
+                       "exchange": "NCCL send/recv halo with row-neighbours per SpMV input, all-gather of the first replicated level, all-reduce of the norm",
+                       "host_setup_s": info["host_setup_s"]},
+            "e2e": {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": int(8 * n0), "d2h_bytes_per_step": int(8 * n0)},
+            "gpu_launches": int(launches) * world,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "whole cycle (all k_spmv launches), aggregate over ranks", "achieved": solve_bytes / solve_s / 1e9,
+                         "peak": peak * world, "unit": "GB/s", "frac": solve_bytes / solve_s / 1e9 / (peak * world),
+                         "peak_source": peak_src + " x n_gpus", "traffic": None},
+            "comm": {"halo_bytes_sent_all_ranks": float(hbt.item()), "nccl_ops_per_rank": int(ops)},
+        }
+        print(json.dumps(line), flush=True)
+    s.close()
+    dist.barrier()
+    dist.destroy_process_group()

@@ -25,7 +25,8 @@ ABI_SYMBOLS = [
     "amgb_set_rhs", "amgb_set_solution", "amgb_get_solution", "amgb_get_residual",
     "amgb_spgemv", "amgb_smooth", "amgb_norm2", "amgb_cycle", "amgb_solve_sync", "amgb_solve_async",
     "amgb_smem_solve", "amgb_time_residual", "amgb_level_storage",
-    "amgb_dist_unique_id", "amgb_dist_init", "amgb_dist_set_partition", "amgb_dist_solve_sync",
+    "amgb_dist_unique_id", "amgb_dist_init", "amgb_dist_set_level", "amgb_dist_setup", "amgb_dist_set_rhs",
+    "amgb_dist_get_solution", "amgb_dist_solve_sync", "amgb_dist_stats",
 ]
 
 
@@ -74,6 +75,14 @@ def load_library():
     L.amgb_time_residual.argtypes = [C.c_void_p, C.c_int, DP]
     L.amgb_level_storage.argtypes = [C.c_void_p, C.c_int, C.c_int, IP]
     L.amgb_async_groups.argtypes = [C.c_void_p, IP, IP]
+    L.amgb_dist_unique_id.argtypes = [C.c_char_p]
+    L.amgb_dist_init.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
+    L.amgb_dist_set_level.argtypes = [C.c_void_p] + [C.c_int] * 9 + [IP]
+    L.amgb_dist_setup.argtypes = [C.c_void_p]
+    L.amgb_dist_set_rhs.argtypes = [C.c_void_p, DP]
+    L.amgb_dist_get_solution.argtypes = [C.c_void_p, DP]
+    L.amgb_dist_solve_sync.argtypes = [C.c_void_p, C.c_double, C.c_int, DP, IP, DP]
+    L.amgb_dist_stats.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     _lib = L
     return L
 
@@ -235,3 +244,79 @@ class Solver:
         g = C.c_int(0)
         self._ck(self.L.amgb_async_groups(self.ctx, _ip(cb), C.byref(g)))
         return cb, g.value
+
+
+def dist_unique_id():
+    """128-byte NCCL unique id (rank 0 creates it, everybody receives it through the launcher's channel)"""
+    L = load_library()
+    buf = C.create_string_buffer(128)
+    rc = L.amgb_dist_unique_id(buf)
+    if rc != 0:
+        raise AmgError("amgb_dist_unique_id failed (%d)" % rc)
+    return buf.raw
+
+
+class DistSolver:
+    """One rank of the row-partitioned synchronous Multadd solve (DMEM_Add replacement).  `plan` is a
+    partition.RankPlan; `uid` the 128-byte id from dist_unique_id() of rank 0."""
+
+    def __init__(self, plan, uid, smooth_weight=1.0, num_pre=1, num_post=1, use_sell=True, use_stream=True, device=0):
+        self.L = load_library()
+        self.plan = plan
+        self.ctx = C.c_void_p()
+        rc = self.L.amgb_create(C.byref(self.ctx), device)
+        if rc != 0:
+            raise AmgError("amgb_create failed (%d): no CUDA device / driver -- there is no CPU fallback" % rc)
+        self._ck(self.L.amgb_dist_init(self.ctx, uid, plan.rank, plan.nranks))
+        o = Options()
+        self.L.amgb_default_options(C.byref(o))
+        o.solver, o.smoother, o.smooth_weight = H.MULTADD, H.JACOBI, smooth_weight
+        o.num_pre_smooth_sweeps, o.num_post_smooth_sweeps = num_pre, num_post
+        o.use_sell, o.use_stream = int(use_sell), int(use_stream)
+        self._ck(self.L.amgb_set_options(self.ctx, C.byref(o)))
+        nl = plan.num_levels
+        self._ck(self.L.amgb_set_num_levels(self.ctx, nl))
+        for l in range(nl):
+            lay = plan.layouts[l]
+            counts = np.ascontiguousarray(plan.all_counts[l], dtype=np.int32)
+            self._ck(self.L.amgb_dist_set_level(self.ctx, l, lay.n_global, lay.row_start, lay.n_owned, lay.halo_lo,
+                                                lay.halo_hi, int(lay.distributed), lay.send_lo, lay.send_hi, _ip(counts)))
+            self._set(MAT_A, l, plan.A[l])
+            if l < nl - 1:
+                self._set(MAT_P, l, plan.P[l])
+                self._set(MAT_R, l, plan.R[l])
+        self._ck(self.L.amgb_setup(self.ctx))
+        self._ck(self.L.amgb_dist_setup(self.ctx))
+        self.n_owned = plan.layouts[0].n_owned
+
+    _ck = Solver._ck
+    _set = Solver._set
+    close = Solver.close
+    launch_count = Solver.launch_count
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_rhs(self, f_owned):
+        f = np.ascontiguousarray(f_owned, dtype=np.float64)
+        assert f.shape[0] == self.n_owned
+        self._ck(self.L.amgb_dist_set_rhs(self.ctx, _dp(f)))
+
+    def get_solution(self, out=None):
+        u = np.empty(self.n_owned) if out is None else out
+        self._ck(self.L.amgb_dist_get_solution(self.ctx, _dp(u)))
+        return u
+
+    def solve_sync(self, tol=1e-9, max_cycles=100):
+        hist = np.zeros(max_cycles + 1)
+        n, secs = C.c_int(0), C.c_double(0)
+        self._ck(self.L.amgb_dist_solve_sync(self.ctx, tol, max_cycles, _dp(hist), C.byref(n), C.byref(secs)))
+        return hist[:n.value + 1], secs.value
+
+    def stats(self):
+        hb, ops = C.c_longlong(0), C.c_longlong(0)
+        self._ck(self.L.amgb_dist_stats(self.ctx, C.byref(hb), C.byref(ops)))
+        return hb.value, ops.value

@@ -330,6 +330,8 @@ def main():
     ap.add_argument("--max-cycles", type=int, default=200)
     ap.add_argument("--jgs-block-rows", type=int, default=8)
     ap.add_argument("--no-sell", action="store_true")
+    ap.add_argument("--min-rows-per-rank", type=int, default=16384,
+                    help="multi-GPU: levels with fewer owned rows per rank are replicated, not partitioned")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-port", action="store_true", help="time the oracle port instead of oracle/_ref")
     ap.add_argument("--cpu-sample-cycles", type=int, default=3)

@@ -125,16 +125,31 @@ int amgb_smem_solve(amgb_ctx *ctx, const double *f_host, double *u_host, double 
 int amgb_time_residual(amgb_ctx *ctx, int reps, double *ms_per_launch);
 int amgb_level_storage(amgb_ctx *ctx, int kind, int level, int *is_sell);
 
-/* ---- multi-GPU (DMEM replacement; one process per GPU) ------------------------------------ */
-/* rank 0 obtains a 128-byte NCCL unique id and distributes it (e.g. torch.distributed broadcast) */
+/* ---- multi-GPU (DMEM replacement; one process per GPU) ------------------------------------
+ * Replaces DMEM_Add / DMEM_SyncAdd (src/DMEM_Add.cpp:20-178, src/DMEM_Mult.cpp:263-450) for the synchronous
+ * Multadd cycle: hypre's ParCSR halo exchange and DMEM_Comm (src/DMEM_Comm.cpp:81-382) become NCCL
+ * send/recv between row-neighbours, the residual norm an ncclAllReduce (src/DMEM_Misc.cpp:398-433).
+ * Call order: amgb_create, amgb_dist_init, amgb_set_options, amgb_set_num_levels, then per level
+ * amgb_dist_set_level followed by that level's amgb_set_matrix calls (LOCAL row blocks whose column
+ * indices are in the rank's extended numbering [ghost_lo | owned | ghost_hi] on distributed levels, full
+ * matrices on replicated levels), amgb_setup, amgb_dist_setup. */
+/* rank 0 obtains a 128-byte NCCL unique id and distributes it (MPI_Bcast / torch.distributed broadcast) */
 int amgb_dist_unique_id(unsigned char id128[128]);
-/* row-partitioned hierarchy: this rank owns rows [row_start[l], row_start[l]+nrows_local) of every
- * level; matrices passed to amgb_set_matrix are then the LOCAL row blocks with GLOBAL column
- * indices.  Replaces hypre's ParCSR comm_pkg + DMEM_Comm (src/DMEM_Comm.cpp:81-382). */
 int amgb_dist_init(amgb_ctx *ctx, const unsigned char id128[128], int rank, int nranks);
-int amgb_dist_set_partition(amgb_ctx *ctx, int level, const int *row_starts /* nranks+1 */);
+/* vector layout of one level on this rank: owned rows [row_start, row_start + n_owned) of n_global;
+ * distributed != 0: halo_lo / halo_hi ghost entries come from rank-1 / rank+1, and this rank sends its
+ * first send_lo / last send_hi owned entries to them; distributed == 0: the level is replicated (full
+ * vectors, redundant computation), row_start / n_owned then name the slice this rank contributes to the
+ * all-gather of the first replicated level.  all_owned[nranks] = n_owned of every rank. */
+int amgb_dist_set_level(amgb_ctx *ctx, int level, int n_global, int row_start, int n_owned, int halo_lo, int halo_hi,
+                        int distributed, int send_lo, int send_hi, const int *all_owned);
+int amgb_dist_setup(amgb_ctx *ctx);
+int amgb_dist_set_rhs(amgb_ctx *ctx, const double *f_owned);        /* this rank's rows of f */
+int amgb_dist_get_solution(amgb_ctx *ctx, double *u_owned);
+/* x0 = 0; cycles until ||r||/||r0|| < tol (global norms) or max_cycles; identical history on every rank */
 int amgb_dist_solve_sync(amgb_ctx *ctx, double tol, int max_cycles, double *relres_hist, int *n_cycles,
                          double *solve_seconds);
+int amgb_dist_stats(amgb_ctx *ctx, long long *halo_bytes_sent, long long *nccl_ops);
 
 #ifdef __cplusplus
 }
