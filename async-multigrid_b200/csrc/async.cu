@@ -27,7 +27,7 @@ struct Team {
    int cta, nctas;         // CTA index / count within the group
    unsigned int *count;
    volatile unsigned int *gen;
-   unsigned char *smem;    // AMGB_STREAM_SMEM bytes of shared memory (CSR-stream staging)
+   unsigned char *smem;    // AMGB_TEAM_SMEM bytes of shared memory (CSR-stream staging)
 };
 
 // barrier among the CTAs of one group (the reference's SMEM_LevelBarrier)
@@ -207,8 +207,8 @@ int async_max_grid(int block)
    int dev = 0, sms = 0, per_sm = 0;
    cudaGetDevice(&dev);
    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-   cudaFuncSetAttribute(k_async_amg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AMGB_STREAM_SMEM);
-   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_async_amg, block, AMGB_STREAM_SMEM);
+   cudaFuncSetAttribute(k_async_amg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AMGB_TEAM_SMEM);
+   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_async_amg, block, AMGB_TEAM_SMEM);
    return sms * per_sm;
 }
 
@@ -218,7 +218,7 @@ int launch_async(const LaunchCfg &, cudaStream_t st, const AsyncParams *params_d
    cudaLaunchConfig_t cfg = {};
    cfg.gridDim = dim3(grid);
    cfg.blockDim = dim3(block);
-   cfg.dynamicSmemBytes = AMGB_STREAM_SMEM;
+   cfg.dynamicSmemBytes = AMGB_TEAM_SMEM;
    cfg.stream = st;
    cudaLaunchAttribute attrs[2];
    int na = 0;

@@ -29,12 +29,22 @@ struct DevCSR {
    // reduced per row; a block made of ONE longer row is reduced by the whole CTA.
    int nblk = 0;
    const int4 *blk = nullptr;        // per block {first row, end row, first entry, end entry}
+   // staged-x form of a block: the columns its entries touch are covered by <= 32 contiguous windows of x
+   // (total <= AMGB_STREAM_XCAP entries) that are bulk-copied into shared memory next to the block; `li`
+   // then holds, per entry, the 16-bit position of its column inside that window buffer.
+   const int4 *blkx = nullptr;       // per block {offset into win, #windows (0 = gather from global memory), 0, 0}
+   const int2 *win = nullptr;        // {first column (even), length (even)} per window
+   const unsigned short *li = nullptr;
+   int wept = 0;                     // > 0: the blocks are WARP chunks of <= 32*wept entries (warp_stream_rows_team)
+   // second block list for the persistent asynchronous kernel: CTA blocks of <= AMGB_STREAM_CAP entries
+   int ncblk = 0;
+   const int4 *cblk = nullptr;
 };
-#define AMGB_STREAM_CAP 2048
-#define AMGB_STREAM_STAGES 3
-// dynamic shared memory of a CTA running the CSR-stream path: per stage CAP column indices + CAP values
-// (products overwrite the values in place), then one mbarrier per stage
-#define AMGB_STREAM_SMEM (AMGB_STREAM_STAGES * AMGB_STREAM_CAP * 12 + 64)
+#define AMGB_STREAM_CAP 2048          // largest row block any variant uses (and the persistent kernel's)
+#define AMGB_TEAM_STAGES 3
+// dynamic shared memory of a CTA of the persistent kernel: per stage CAP values (products overwrite them in
+// place) + CAP column indices, then one mbarrier per stage
+#define AMGB_TEAM_SMEM (AMGB_TEAM_STAGES * AMGB_STREAM_CAP * 12 + 64)
 
 // y_i = gamma*c_i + rs_i * (beta*b_i + alpha * sum_j M_ij x_j)       (rs == nullptr -> 1)
 // covers: MatVec (alpha=1), Residual (alpha=-1,beta=1,b=f), prolong-and-add (beta=1,b=y),
@@ -117,6 +127,12 @@ __device__ __forceinline__ uint64_t l2_evict_first_policy()
 {
    uint64_t pol;
    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+   return pol;
+}
+__device__ __forceinline__ uint64_t l2_evict_last_policy()
+{
+   uint64_t pol;
+   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
    return pol;
 }
 // bytes: multiple of 16; src and dst 16-byte aligned.  The matrix streams are read once: evict_first keeps

@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstring>
 #include <vector>
+#include <omp.h>
 
 int amgb_fail(amgb_ctx *c, int code, const char *fmt, ...)
 {
@@ -32,7 +33,7 @@ template <class T>
 static int dev_alloc(amgb_ctx *c, T **p, size_t n)
 {
    *p = nullptr;
-   n += 8;   // slack: the 128-bit group loads of the CSR-stream kernel may touch up to 3 elements past the end
+   n += 64 / sizeof(T) + 8;   // slack: 16-byte granular bulk copies may touch a few elements past the end
    cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
    if (e != cudaSuccess) return amgb_fail(c, AMGB_ENOMEM, "cudaMalloc(%zu bytes): %s", n * sizeof(T), cudaGetErrorString(e));
    c->allocs.push_back((void *)*p);
@@ -81,6 +82,7 @@ void amgb_default_options(amgb_options *o)
    o->use_sell = 1;
    o->l2_persist = 1;
    o->use_stream = 1;
+   o->stream_variant = 8;
 }
 
 int amgb_create(amgb_ctx **out, int device)
@@ -98,6 +100,7 @@ int amgb_create(amgb_ctx **out, int device)
    cudaGetDeviceProperties(&prop, device);
    c->cfg.num_sms = prop.multiProcessorCount;
    c->cfg.ctas_per_sm = 8;
+   c->host_threads = std::max(1, std::min(16, omp_get_num_procs()));
    c->l2_bytes = prop.l2CacheSize;
    c->max_window = prop.accessPolicyMaxWindowSize;
    c->persist_max = prop.persistingL2CacheMaxSize;
@@ -142,8 +145,11 @@ int amgb_set_num_levels(amgb_ctx *c, int L)
 int amgb_set_options(amgb_ctx *c, const amgb_options *o)
 {
    if (!c || !o) return AMGB_EINVAL;
-   if (o->smooth_weight == 0.0 || o->jgs_block_rows < 1) return amgb_fail(c, AMGB_EINVAL, "bad options");
+   if (o->smooth_weight == 0.0 || o->jgs_block_rows < 1 || o->stream_variant < 0 || o->stream_variant >= AMGB_NUM_STREAM_VARIANTS)
+      return amgb_fail(c, AMGB_EINVAL, "bad options");
+   if (c->L) return amgb_fail(c, AMGB_ESTATE, "amgb_set_options must precede the hierarchy upload");
    c->opt = *o;
+   c->cfg.stream_variant = o->stream_variant;
    return AMGB_OK;
 }
 
@@ -201,30 +207,113 @@ static int build_sell(amgb_ctx *c, DevCSR &M, int nrows, const int *rp, const in
 // Row blocks of the CSR-stream kernel: consecutive rows whose entries, counted from the 4-aligned
 // start of the block, fit AMGB_STREAM_CAP (and at most AMGB_STREAM_CAP rows); a longer row is a
 // block of its own.
-static int build_stream_blocks(amgb_ctx *c, DevCSR &M, int nrows, const int *rp)
+static int build_stream_blocks(amgb_ctx *c, DevCSR &M, int nrows, int ncols, const int *rp, const int *ci)
 {
+   const StreamVariant &sv = kStreamVariants[c->cfg.stream_variant];
+   const int CAPV = sv.cap, XCAPV = sv.xcap;
    std::vector<int4> blk;
    blk.reserve((size_t)rp[nrows] / 1024 + 16);
    int r = 0;
    while (r < nrows) {
       const int start = r;
-      const long q0 = rp[start] & ~3;
-      while (r < nrows && r - start < AMGB_STREAM_CAP && (long)rp[r + 1] - q0 <= AMGB_STREAM_CAP) r++;
+      const long q0 = sv.stages == 0 ? rp[start] : (rp[start] & ~7);   // bulk copies start 8-entry aligned
+      while (r < nrows && r - start < CAPV && (long)rp[r + 1] - q0 <= CAPV) r++;
       if (r == start) r++;
       blk.push_back(make_int4(start, r, rp[start], rp[r]));
    }
-   int4 *d_blk;
+   const int nb = (int)blk.size();
+   // x windows per block (see DevCSR): built in parallel, then concatenated
+   std::vector<int4> blkx((size_t)nb, make_int4(0, 0, 0, 0));
+   std::vector<std::vector<int2>> wins((size_t)nb);
+   std::vector<unsigned short> li((size_t)rp[nrows] + 16, 0);
+   long staged = 0;
+#pragma omp parallel reduction(+ : staged)
+   {
+      std::vector<int> u;
+      std::vector<int2> w;
+      std::vector<int> wbase;
+#pragma omp for schedule(dynamic, 64)
+      for (int b = 0; b < nb; b++) {
+         const int p0 = blk[b].z, p1 = blk[b].w;
+         if (XCAPV == 0 || p1 <= p0 || p1 - (p0 & ~7) > CAPV) continue;   // no staging / empty / long-row block
+         u.assign(ci + p0, ci + p1);
+         std::sort(u.begin(), u.end());
+         u.erase(std::unique(u.begin(), u.end()), u.end());
+         bool ok = false;
+         for (int gap = 8; gap <= 512 && !ok; gap *= 4) {
+            w.clear();
+            int ws = u[0] & ~1, we = (u[0] + 2) & ~1;
+            for (size_t k = 1; k < u.size(); k++) {
+               if (u[k] < we + gap) we = (u[k] + 2) & ~1;
+               else { w.push_back(make_int2(ws, we - ws)); ws = u[k] & ~1; we = (u[k] + 2) & ~1; }
+            }
+            w.push_back(make_int2(ws, we - ws));
+            long tot = 0;
+            for (auto &x : w) tot += x.y;
+            if (tot > XCAPV) break;                       // larger gaps only add entries
+            ok = (int)w.size() <= 32;
+         }
+         if (!ok) continue;
+         (void)ncols;   // a window may end one entry past ncols: vectors are allocated with slack
+         wbase.resize(w.size());
+         int acc = 0;
+         for (size_t k = 0; k < w.size(); k++) { wbase[k] = acc; acc += w[k].y; }
+         for (int p = p0; p < p1; p++) {
+            const int col = ci[p];
+            size_t lo = 0, hi = w.size();                 // last window with start <= col
+            while (hi - lo > 1) { size_t mid = (lo + hi) / 2; if (w[mid].x <= col) lo = mid; else hi = mid; }
+            li[p] = (unsigned short)(wbase[lo] + (col - w[lo].x));
+         }
+         wins[b] = w;
+         blkx[b].y = (int)w.size();
+         staged++;
+      }
+   }
+   std::vector<int2> win;
+   for (int b = 0; b < nb; b++) {
+      blkx[b].x = (int)win.size();
+      win.insert(win.end(), wins[b].begin(), wins[b].end());
+   }
+   int4 *d_blk, *d_blkx;
+   int2 *d_win;
+   unsigned short *d_li;
    int rc;
    if ((rc = dev_upload(c, &d_blk, blk.data(), blk.size()))) return rc;
+   if ((rc = dev_upload(c, &d_blkx, blkx.data(), blkx.size()))) return rc;
+   if ((rc = dev_upload(c, &d_win, win.data(), win.size()))) return rc;
+   if ((rc = dev_upload(c, &d_li, li.data(), li.size()))) return rc;
    CUDA_OK(c, cudaStreamSynchronize(c->stream));
-   M.nblk = (int)blk.size();
-   M.blk = d_blk;
+   M.nblk = nb;
+   M.blk = d_blk; M.blkx = d_blkx; M.win = d_win; M.li = d_li;
+   M.wept = sv.stages == 0 ? sv.cap / 32 : 0;
+   const int solver = c->opt.solver;
+   if (solver == AMGB_SOLVER_ASYNC_MULTADD || solver == AMGB_SOLVER_ASYNC_AFACX) {
+      // the persistent kernel streams CTA-sized blocks (bulk copies start 8-entry aligned)
+      std::vector<int4> cb;
+      int rr = 0;
+      while (rr < nrows) {
+         const int start = rr;
+         const long q0 = rp[start] & ~7;
+         while (rr < nrows && rr - start < AMGB_STREAM_CAP && (long)rp[rr + 1] - q0 <= AMGB_STREAM_CAP) rr++;
+         if (rr == start) rr++;
+         cb.push_back(make_int4(start, rr, rp[start], rp[rr]));
+      }
+      int4 *d_cb;
+      if ((rc = dev_upload(c, &d_cb, cb.data(), cb.size()))) return rc;
+      CUDA_OK(c, cudaStreamSynchronize(c->stream));
+      M.ncblk = (int)cb.size();
+      M.cblk = d_cb;
+   }
+   c->stream_blocks += nb;
+   c->stream_blocks_staged_x += staged;
    return AMGB_OK;
 }
 
 int amgb_set_matrix(amgb_ctx *c, int kind, int level, int nrows, int ncols, int nnz,
                     const int *rp, const int *ci, const double *va)
 {
+   // layout conversion below is OpenMP-parallel; launchers such as torchrun export OMP_NUM_THREADS=1
+   if (omp_get_max_threads() < c->host_threads) omp_set_num_threads(c->host_threads);
    if (!c || !rp || (nnz > 0 && (!ci || !va))) return amgb_fail(c, AMGB_EINVAL, "null matrix arrays");
    if (c->L == 0) return amgb_fail(c, AMGB_ESTATE, "call amgb_set_num_levels first");
    if (level < 0 || level >= c->L || (kind != AMGB_MAT_A && level >= c->L - 1 && c->L > 1))
@@ -251,8 +340,12 @@ int amgb_set_matrix(amgb_ctx *c, int kind, int level, int nrows, int ncols, int 
    if (c->opt.use_sell && nrows >= 1024) {
       if ((rc = build_sell(c, M, nrows, rp, ci, va))) return rc;
    }
-   if (c->opt.use_stream && M.sell_slices == 0 && nrows > 0) {
-      if ((rc = build_stream_blocks(c, M, nrows, rp))) return rc;
+   // long rows (restrictions on coarse levels: 150-300 entries) are served best by one warp per row; everything
+   // shorter goes through the stream kernel (measured per matrix with tools/spmv_sweep.py, profiles/)
+   const bool long_rows = nrows > 0 && (double)nnz / nrows >= 96.0;
+   if (long_rows) M.lpr = 32;
+   if (c->opt.use_stream && M.sell_slices == 0 && nrows > 0 && !(long_rows && c->opt.stream_variant == 8)) {
+      if ((rc = build_stream_blocks(c, M, nrows, ncols, rp, ci))) return rc;
    }
    return AMGB_OK;
 }
@@ -682,6 +775,39 @@ int amgb_time_residual(amgb_ctx *c, int reps, double *ms_per_launch)
    float ms = 0;
    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
    *ms_per_launch = ms / reps;
+   return AMGB_OK;
+}
+
+// event-timed y = M x (plain epilogue) for one matrix of the hierarchy: the tuning harness's probe
+int amgb_time_spmv(amgb_ctx *c, int kind, int level, int use_sval, int reps, double *ms_per_launch)
+{
+   NEED_READY(c);
+   if (level < 0 || level >= c->L || (kind != AMGB_MAT_A && level >= c->L - 1) || reps < 1 || !ms_per_launch)
+      return amgb_fail(c, AMGB_EINVAL, "bad arguments");
+   const DevCSR &M = kind == AMGB_MAT_A ? c->A[level] : (kind == AMGB_MAT_P ? c->P[level] : c->R[level]);
+   if (use_sval && !M.sval) return amgb_fail(c, AMGB_EINVAL, "no scaled values for this matrix");
+   const double *x = kind == AMGB_MAT_A ? c->r[level] : (kind == AMGB_MAT_P ? c->e[level + 1] : c->r[level]);
+   double *y = kind == AMGB_MAT_A ? c->e[level] : (kind == AMGB_MAT_P ? c->t[level] : c->t[level + 1]);
+   int grid;
+   for (int k = 0; k < 3; k++) c->launches += launch_spmv(c->cfg, c->stream, M, use_sval != 0, x, y, epi(1.0, 0.0, nullptr), nullptr, &grid);
+   CUDA_OK(c, cudaStreamSynchronize(c->stream));
+   CUDA_OK(c, cudaEventRecord(c->ev0, c->stream));
+   for (int k = 0; k < reps; k++) c->launches += launch_spmv(c->cfg, c->stream, M, use_sval != 0, x, y, epi(1.0, 0.0, nullptr), nullptr, &grid);
+   CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));
+   CUDA_OK(c, cudaEventSynchronize(c->ev1));
+   float ms = 0;
+   cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+   *ms_per_launch = ms / reps;
+   CUDA_OK(c, cudaGetLastError());
+   return AMGB_OK;
+}
+
+// CSR-stream row blocks over the whole hierarchy and how many of them carry staged x windows
+int amgb_stream_stats(amgb_ctx *c, long long *blocks, long long *blocks_staged_x)
+{
+   if (!c) return AMGB_EINVAL;
+   if (blocks) *blocks = c->stream_blocks;
+   if (blocks_staged_x) *blocks_staged_x = c->stream_blocks_staged_x;
    return AMGB_OK;
 }
 

@@ -32,6 +32,8 @@ struct amgb_ctx {
    long long graph_kernels = 0;
    long long launches = 0;
    size_t bytes_allocated = 0;
+   int host_threads = 1;   // threads for the upload-time layout conversions (set in amgb_create)
+   long stream_blocks = 0, stream_blocks_staged_x = 0;   // CSR-stream row blocks / those with staged x windows
    size_t l2_bytes = 0, max_window = 0, persist_max = 0;
    std::vector<void *> allocs;
    // async

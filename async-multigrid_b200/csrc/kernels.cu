@@ -13,7 +13,7 @@ namespace {
 constexpr int kBlock = 256;
 
 // One kernel per storage scheme (separate register budgets): MODE 0 = vector-per-row CSR,
-// 1 = sliced ELL (stencil levels), 2 = CSR-stream (row blocks through shared memory).
+// 1 = sliced ELL (stencil levels); the CSR-stream kernel (row blocks through shared memory) is k_spmv_stream.
 template <int MODE, bool SVAL>
 __global__ void __launch_bounds__(kBlock) k_spmv(DevCSR M, const double *x, double *y, SpmvEpilogue e, double *partials)
 {
@@ -22,10 +22,19 @@ __global__ void __launch_bounds__(kBlock) k_spmv(DevCSR M, const double *x, doub
    const bool norm = partials != nullptr;
    double ss;
    if (MODE == 1) ss = sell_rows_team<true, SVAL>(M, x, y, e, tid, tsz, norm);
-   else if (MODE == 2) {
-      extern __shared__ __align__(128) unsigned char dyn_smem[];
-      ss = stream_rows_team<true, SVAL>(M, x, y, e, blockIdx.x, gridDim.x, dyn_smem, norm);
-   } else ss = csr_rows_dispatch<true, SVAL>(M, x, y, e, tid, tsz, norm);
+   else ss = csr_rows_dispatch<true, SVAL>(M, x, y, e, tid, tsz, norm);
+   if (norm) {
+      ss = block_sum(ss);
+      if (threadIdx.x == 0) partials[blockIdx.x] = ss;
+   }
+}
+
+template <int NT, int CAP, int XCAP, int ST, bool SVAL>
+__global__ void __launch_bounds__(NT) k_spmv_stream(DevCSR M, const double *x, double *y, SpmvEpilogue e, double *partials)
+{
+   extern __shared__ __align__(128) unsigned char dyn_smem[];
+   const bool norm = partials != nullptr;
+   double ss = stream_rows_team<true, SVAL, NT, CAP, XCAP, ST>(M, x, y, e, blockIdx.x, gridDim.x, dyn_smem, norm, M.blk, M.nblk);
    if (norm) {
       ss = block_sum(ss);
       if (threadIdx.x == 0) partials[blockIdx.x] = ss;
@@ -110,29 +119,71 @@ inline int grid_for(const LaunchCfg &cfg, long work_threads)
 
 }  // namespace
 
-template <int MODE, bool SVAL>
-static int resident_grid(const LaunchCfg &cfg)
+template <int EPT, bool SVAL>
+__global__ void __launch_bounds__(kBlock) k_spmv_wstream(DevCSR M, const double *x, double *y, SpmvEpilogue e, double *partials)
 {
-   static int per_sm = 0;   // co-resident CTAs per SM of this instantiation: grids are sized to exactly one wave
-   if (per_sm == 0) {
-      int v = 0;
-      const size_t dyn = MODE == 2 ? AMGB_STREAM_SMEM : 0;
-      if (dyn) cudaFuncSetAttribute(k_spmv<MODE, SVAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_spmv<MODE, SVAL>, kBlock, dyn) != cudaSuccess || v < 1) v = 2;
-      per_sm = v;
+   __shared__ __align__(16) double swarp[(kBlock / 32) * EPT * 32];
+   const bool norm = partials != nullptr;
+   const int warp = threadIdx.x >> 5;
+   double ss = warp_stream_rows_team<true, SVAL, EPT>(M, x, y, e, blockIdx.x * (kBlock / 32) + warp, gridDim.x * (kBlock / 32),
+                                                      swarp + warp * EPT * 32, norm);
+   if (norm) {
+      ss = block_sum(ss);
+      if (threadIdx.x == 0) partials[blockIdx.x] = ss;
    }
-   return cfg.num_sms * per_sm;
+}
+
+template <class K>
+static int resident_ctas(K kernel, int block, size_t dyn, int num_sms, int *cache)
+{
+   // co-resident CTAs of this kernel on the device: grids are sized to exactly one wave
+   if (*cache == 0) {
+      int v = 0;
+      if (dyn) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, block, dyn) != cudaSuccess || v < 1) v = 1;
+      *cache = v;
+   }
+   return num_sms * *cache;
 }
 
 template <int MODE>
 static int launch_spmv_mode(const LaunchCfg &cfg, cudaStream_t st, const DevCSR &M, bool use_sval, const double *x, double *y,
                             const SpmvEpilogue &e, double *partials, long ctas_of_work)
 {
-   const int cap = use_sval ? resident_grid<MODE, true>(cfg) : resident_grid<MODE, false>(cfg);
+   static int occ[2] = {0, 0};
+   const int cap = use_sval ? resident_ctas(k_spmv<MODE, true>, kBlock, 0, cfg.num_sms, &occ[1])
+                            : resident_ctas(k_spmv<MODE, false>, kBlock, 0, cfg.num_sms, &occ[0]);
    const int grid = (int)std::max(1L, std::min(ctas_of_work, (long)cap));
-   const size_t dyn = MODE == 2 ? AMGB_STREAM_SMEM : 0;
-   if (use_sval) k_spmv<MODE, true><<<grid, kBlock, dyn, st>>>(M, x, y, e, partials);
-   else k_spmv<MODE, false><<<grid, kBlock, dyn, st>>>(M, x, y, e, partials);
+   if (use_sval) k_spmv<MODE, true><<<grid, kBlock, 0, st>>>(M, x, y, e, partials);
+   else k_spmv<MODE, false><<<grid, kBlock, 0, st>>>(M, x, y, e, partials);
+   return grid;
+}
+
+template <int NT, int CAP, int XCAP, int ST>
+static int launch_stream_variant(const LaunchCfg &cfg, cudaStream_t st, const DevCSR &M, bool use_sval, const double *x, double *y,
+                                 const SpmvEpilogue &e, double *partials)
+{
+   static int occ[2] = {0, 0};
+   constexpr size_t dyn = stream_smem_bytes(CAP, XCAP, ST);
+   const int cap = use_sval ? resident_ctas(k_spmv_stream<NT, CAP, XCAP, ST, true>, NT, dyn, cfg.num_sms, &occ[1])
+                            : resident_ctas(k_spmv_stream<NT, CAP, XCAP, ST, false>, NT, dyn, cfg.num_sms, &occ[0]);
+   const int grid = (int)std::max(1L, std::min((long)M.nblk, (long)cap));
+   if (use_sval) k_spmv_stream<NT, CAP, XCAP, ST, true><<<grid, NT, dyn, st>>>(M, x, y, e, partials);
+   else k_spmv_stream<NT, CAP, XCAP, ST, false><<<grid, NT, dyn, st>>>(M, x, y, e, partials);
+   return grid;
+}
+
+template <int EPT>
+static int launch_wstream(const LaunchCfg &cfg, cudaStream_t st, const DevCSR &M, bool use_sval, const double *x, double *y,
+                          const SpmvEpilogue &e, double *partials)
+{
+   static int occ[2] = {0, 0};
+   const int cap = use_sval ? resident_ctas(k_spmv_wstream<EPT, true>, kBlock, 0, cfg.num_sms, &occ[1])
+                            : resident_ctas(k_spmv_wstream<EPT, false>, kBlock, 0, cfg.num_sms, &occ[0]);
+   const long want = ((long)M.nblk + kBlock / 32 - 1) / (kBlock / 32);
+   const int grid = (int)std::max(1L, std::min(want, (long)cap));
+   if (use_sval) k_spmv_wstream<EPT, true><<<grid, kBlock, 0, st>>>(M, x, y, e, partials);
+   else k_spmv_wstream<EPT, false><<<grid, kBlock, 0, st>>>(M, x, y, e, partials);
    return grid;
 }
 
@@ -141,8 +192,22 @@ int launch_spmv(const LaunchCfg &cfg, cudaStream_t st, const DevCSR &M, bool use
 {
    int grid;
    if (M.sell_slices > 0) grid = launch_spmv_mode<1>(cfg, st, M, use_sval, x, y, e, partials, ((long)M.sell_slices * 32 + kBlock - 1) / kBlock);
-   else if (M.nblk > 0) grid = launch_spmv_mode<2>(cfg, st, M, use_sval, x, y, e, partials, (long)M.nblk);
-   else grid = launch_spmv_mode<0>(cfg, st, M, use_sval, x, y, e, partials, ((long)M.nrows * M.lpr + kBlock - 1) / kBlock);
+   else if (M.nblk > 0 && M.wept > 0) {
+      if (M.wept <= 4) grid = launch_wstream<4>(cfg, st, M, use_sval, x, y, e, partials);
+      else if (M.wept <= 8) grid = launch_wstream<8>(cfg, st, M, use_sval, x, y, e, partials);
+      else grid = launch_wstream<16>(cfg, st, M, use_sval, x, y, e, partials);
+   } else if (M.nblk > 0) {
+      switch (cfg.stream_variant) {   // keep in step with kStreamVariants (launch.h)
+         case 1: grid = launch_stream_variant<128, 1024, 0, 2>(cfg, st, M, use_sval, x, y, e, partials); break;
+         case 2: grid = launch_stream_variant<128, 1024, 0, 3>(cfg, st, M, use_sval, x, y, e, partials); break;
+         case 3: grid = launch_stream_variant<256, 2048, 1536, 2>(cfg, st, M, use_sval, x, y, e, partials); break;
+         case 4: grid = launch_stream_variant<128, 1024, 1024, 2>(cfg, st, M, use_sval, x, y, e, partials); break;
+         case 5: grid = launch_stream_variant<256, 1024, 0, 2>(cfg, st, M, use_sval, x, y, e, partials); break;
+         case 6: grid = launch_stream_variant<128, 1024, 1024, 3>(cfg, st, M, use_sval, x, y, e, partials); break;
+         case 7: grid = launch_stream_variant<128, 2048, 0, 2>(cfg, st, M, use_sval, x, y, e, partials); break;
+         default: grid = launch_stream_variant<256, 2048, 0, 3>(cfg, st, M, use_sval, x, y, e, partials); break;
+      }
+   } else grid = launch_spmv_mode<0>(cfg, st, M, use_sval, x, y, e, partials, ((long)M.nrows * M.lpr + kBlock - 1) / kBlock);
    if (grid_out) *grid_out = grid;
    return 1;
 }

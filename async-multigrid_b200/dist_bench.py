@@ -69,6 +69,7 @@ def _build_and_scatter(args, world, d):
     """rank 0: global problem -> plan -> per-rank blocks on /dev/shm (freed level by level)"""
     t0 = time.time()
     n = args.n
+    H.set_host_threads(os.cpu_count() or 1)      # the other ranks idle at the barrier meanwhile
     A = H.laplacian("7pt", n, n, n * world)
     h = H.amg_setup(A, theta=args.theta)
     h.build_transfers(H.MULTADD, args.smooth_weight, num_pre=1, num_post=args.num_post)

@@ -119,6 +119,11 @@ def _take(cs, free=True):
     return out
 
 
+def set_host_threads(n):
+    """OpenMP threads of the host input provider (torchrun exports OMP_NUM_THREADS=1)"""
+    host_lib().amgh_set_num_threads(C.c_int(int(n)))
+
+
 def laplacian(problem, nx, ny=None, nz=None):
     """'5pt' (n x n), '7pt', '27pt' (nx x ny x nz); diag-first CSR, natural ordering."""
     L = host_lib()

@@ -48,6 +48,8 @@ void amgh_csr_free(amgh_csr *m)
 }
 
 int amgh_max_threads(void) { return omp_get_max_threads(); }
+// launchers such as torchrun export OMP_NUM_THREADS=1; the setup rank overrides it explicitly
+void amgh_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 
 }  // extern "C"
 

@@ -24,7 +24,7 @@ ABI_SYMBOLS = [
     "amgb_set_num_levels", "amgb_set_matrix", "amgb_set_options", "amgb_setup",
     "amgb_set_rhs", "amgb_set_solution", "amgb_get_solution", "amgb_get_residual",
     "amgb_spgemv", "amgb_smooth", "amgb_norm2", "amgb_cycle", "amgb_solve_sync", "amgb_solve_async",
-    "amgb_smem_solve", "amgb_time_residual", "amgb_level_storage",
+    "amgb_smem_solve", "amgb_time_residual", "amgb_level_storage", "amgb_time_spmv", "amgb_stream_stats",
     "amgb_dist_unique_id", "amgb_dist_init", "amgb_dist_set_level", "amgb_dist_setup", "amgb_dist_set_rhs",
     "amgb_dist_get_solution", "amgb_dist_solve_sync", "amgb_dist_stats",
 ]
@@ -34,7 +34,8 @@ class Options(C.Structure):
     _fields_ = [("solver", C.c_int), ("smoother", C.c_int), ("smooth_weight", C.c_double),
                 ("num_pre_smooth_sweeps", C.c_int), ("num_post_smooth_sweeps", C.c_int),
                 ("num_fine_smooth_sweeps", C.c_int), ("num_coarse_smooth_sweeps", C.c_int),
-                ("jgs_block_rows", C.c_int), ("use_sell", C.c_int), ("l2_persist", C.c_int), ("use_stream", C.c_int)]
+                ("jgs_block_rows", C.c_int), ("use_sell", C.c_int), ("l2_persist", C.c_int), ("use_stream", C.c_int),
+                ("stream_variant", C.c_int)]
 
 
 _lib = None
@@ -74,6 +75,8 @@ def load_library():
     L.amgb_smem_solve.argtypes = [C.c_void_p, DP, DP, C.c_double, C.c_int, DP, IP, IP, DP, DP]
     L.amgb_time_residual.argtypes = [C.c_void_p, C.c_int, DP]
     L.amgb_level_storage.argtypes = [C.c_void_p, C.c_int, C.c_int, IP]
+    L.amgb_time_spmv.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, DP]
+    L.amgb_stream_stats.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     L.amgb_async_groups.argtypes = [C.c_void_p, IP, IP]
     L.amgb_dist_unique_id.argtypes = [C.c_char_p]
     L.amgb_dist_init.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
@@ -105,7 +108,7 @@ class Solver:
 
     def __init__(self, h, solver=H.MULTADD, smoother=H.JACOBI, smooth_weight=1.0, num_pre=1, num_post=1,
                  fine_sweeps=1, coarse_sweeps=1, jgs_block_rows=8, use_sell=True, l2_persist=True, use_stream=True,
-                 device=0):
+                 stream_variant=None, device=0):
         self.L = load_library()
         self.h = h
         self.ctx = C.c_void_p()
@@ -119,6 +122,10 @@ class Solver:
         o.num_fine_smooth_sweeps, o.num_coarse_smooth_sweeps = fine_sweeps, coarse_sweeps
         o.jgs_block_rows, o.use_sell, o.l2_persist = jgs_block_rows, int(use_sell), int(l2_persist)
         o.use_stream = int(use_stream)
+        if stream_variant is not None:
+            o.stream_variant = int(stream_variant)
+        elif "AMGB_STREAM_VARIANT" in os.environ:
+            o.stream_variant = int(os.environ["AMGB_STREAM_VARIANT"])
         self.options = o
         self._ck(self.L.amgb_set_options(self.ctx, C.byref(o)))
         self._ck(self.L.amgb_set_num_levels(self.ctx, h.num_levels))
@@ -233,6 +240,16 @@ class Solver:
         ms = C.c_double(0)
         self._ck(self.L.amgb_time_residual(self.ctx, reps, C.byref(ms)))
         return ms.value
+
+    def time_spmv(self, kind, level, use_sval=False, reps=20):
+        ms = C.c_double(0)
+        self._ck(self.L.amgb_time_spmv(self.ctx, kind, level, int(use_sval), reps, C.byref(ms)))
+        return ms.value
+
+    def stream_stats(self):
+        a, b = C.c_longlong(0), C.c_longlong(0)
+        self._ck(self.L.amgb_stream_stats(self.ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def is_sell(self, kind, level):
         v = C.c_int(0)

@@ -320,7 +320,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=256)
+    ap.add_argument("--n", "--grid", dest="n", type=int, default=256, help="grid points per dimension (per GPU slab)")
     ap.add_argument("--nz", type=int, default=0)
     ap.add_argument("--solver", default="multadd", choices=sorted(SOLVERS))
     ap.add_argument("--smoother", default="j", choices=sorted(SMOOTHERS))

@@ -52,6 +52,7 @@ typedef struct {
    int l2_persist;              /* 1: pin the coarse hierarchy in L2 with an access-policy window */
    int use_stream;              /* 1: CSR-stream kernel (row blocks staged through shared memory with 128-bit
                                    loads) for every matrix not stored as sliced ELL; 0: vector-per-row CSR */
+   int stream_variant;          /* geometry of the CSR-stream kernel (csrc/launch.h kStreamVariants; default 8 = warp-granular, 256-entry chunks) */
 } amgb_options;
 
 void amgb_default_options(amgb_options *opt);
@@ -124,6 +125,9 @@ int amgb_smem_solve(amgb_ctx *ctx, const double *f_host, double *u_host, double 
  * r = f - A_0 u (the dominant kernel), on the context's stream */
 int amgb_time_residual(amgb_ctx *ctx, int reps, double *ms_per_launch);
 int amgb_level_storage(amgb_ctx *ctx, int kind, int level, int *is_sell);
+/* event-timed y = M x for one matrix of the hierarchy (tools/spmv_sweep.py) and CSR-stream block statistics */
+int amgb_time_spmv(amgb_ctx *ctx, int kind, int level, int use_scaled_values, int reps, double *ms_per_launch);
+int amgb_stream_stats(amgb_ctx *ctx, long long *blocks, long long *blocks_with_staged_x);
 
 /* ---- multi-GPU (DMEM replacement; one process per GPU) ------------------------------------
  * Replaces DMEM_Add / DMEM_SyncAdd (src/DMEM_Add.cpp:20-178, src/DMEM_Mult.cpp:263-450) for the synchronous
