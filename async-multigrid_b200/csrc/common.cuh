@@ -36,6 +36,14 @@ struct DevCSR {
    const int2 *win = nullptr;        // {first column (even), length (even)} per window
    const unsigned short *li = nullptr;
    int wept = 0;                     // > 0: the blocks are WARP chunks of <= 32*wept entries (warp_stream_rows_team)
+   // column-sorted copy of the warp chunks (wept > 0, DevCSR::pos != nullptr): inside every chunk the entries
+   // are stored in ascending column order (pci / pva / psval) and pos[k] is the entry's original position
+   // within the chunk, so consecutive lanes gather neighbouring x (few L1 tag look-ups per instruction) and
+   // the products are scattered back to row order in shared memory.
+   const int *pci = nullptr;
+   const double *pva = nullptr;
+   const double *psval = nullptr;
+   const unsigned char *pos = nullptr;
    // second block list for the persistent asynchronous kernel: CTA blocks of <= AMGB_STREAM_CAP entries
    int ncblk = 0;
    const int4 *cblk = nullptr;
@@ -69,6 +77,12 @@ __device__ __forceinline__ int ld_stream(const int *p)
    int v;
    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
    return v;
+}
+__device__ __forceinline__ int ld_stream(const unsigned char *p)
+{
+   unsigned int v;
+   asm volatile("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(v) : "l"(p));
+   return (int)v;
 }
 // 128-bit streaming loads (4 column indices / 2 values per instruction), 16-byte aligned
 __device__ __forceinline__ int4 ld_stream4(const int *p)

@@ -207,7 +207,7 @@ static int build_sell(amgb_ctx *c, DevCSR &M, int nrows, const int *rp, const in
 // Row blocks of the CSR-stream kernel: consecutive rows whose entries, counted from the 4-aligned
 // start of the block, fit AMGB_STREAM_CAP (and at most AMGB_STREAM_CAP rows); a longer row is a
 // block of its own.
-static int build_stream_blocks(amgb_ctx *c, DevCSR &M, int nrows, int ncols, const int *rp, const int *ci)
+static int build_stream_blocks(amgb_ctx *c, DevCSR &M, int nrows, int ncols, const int *rp, const int *ci, const double *va)
 {
    const StreamVariant &sv = kStreamVariants[c->cfg.stream_variant];
    const int CAPV = sv.cap, XCAPV = sv.xcap;
@@ -216,7 +216,7 @@ static int build_stream_blocks(amgb_ctx *c, DevCSR &M, int nrows, int ncols, con
    int r = 0;
    while (r < nrows) {
       const int start = r;
-      const long q0 = sv.stages == 0 ? rp[start] : (rp[start] & ~7);   // bulk copies start 8-entry aligned
+      const long q0 = sv.stages <= 0 ? rp[start] : (rp[start] & ~7);   // bulk copies start 8-entry aligned
       while (r < nrows && r - start < CAPV && (long)rp[r + 1] - q0 <= CAPV) r++;
       if (r == start) r++;
       blk.push_back(make_int4(start, r, rp[start], rp[r]));
@@ -285,7 +285,40 @@ static int build_stream_blocks(amgb_ctx *c, DevCSR &M, int nrows, int ncols, con
    CUDA_OK(c, cudaStreamSynchronize(c->stream));
    M.nblk = nb;
    M.blk = d_blk; M.blkx = d_blkx; M.win = d_win; M.li = d_li;
-   M.wept = sv.stages == 0 ? sv.cap / 32 : 0;
+   M.wept = sv.stages <= 0 ? sv.cap / 32 : 0;
+   if (sv.stages < 0) {
+      // column-sorted copy of every warp chunk (see DevCSR::pos)
+      const size_t nnz = (size_t)rp[nrows];
+      std::vector<int> pci(nnz);
+      std::vector<double> pva(nnz);
+      std::vector<unsigned char> pos(nnz + 16, 0);
+#pragma omp parallel
+      {
+         std::vector<int> idx;
+#pragma omp for schedule(dynamic, 256)
+         for (int b = 0; b < nb; b++) {
+            const int p0 = blk[b].z, p1 = blk[b].w, cnt = p1 - p0;
+            if (cnt > CAPV || cnt > 256) {      // long row: read unsorted by the whole warp
+               for (int p = p0; p < p1; p++) { pci[p] = ci[p]; pva[p] = va[p]; }
+               continue;
+            }
+            idx.resize(cnt);
+            for (int k = 0; k < cnt; k++) idx[k] = k;
+            std::stable_sort(idx.begin(), idx.end(), [&](int a, int bb) { return ci[p0 + a] < ci[p0 + bb]; });
+            for (int k = 0; k < cnt; k++) {
+               pci[p0 + k] = ci[p0 + idx[k]];
+               pva[p0 + k] = va[p0 + idx[k]];
+               pos[p0 + k] = (unsigned char)idx[k];
+            }
+         }
+      }
+      int *d_pci; double *d_pva; unsigned char *d_pos;
+      if ((rc = dev_upload(c, &d_pci, pci.data(), pci.size()))) return rc;
+      if ((rc = dev_upload(c, &d_pva, pva.data(), pva.size()))) return rc;
+      if ((rc = dev_upload(c, &d_pos, pos.data(), pos.size()))) return rc;
+      CUDA_OK(c, cudaStreamSynchronize(c->stream));
+      M.pci = d_pci; M.pva = d_pva; M.pos = d_pos;
+   }
    const int solver = c->opt.solver;
    if (solver == AMGB_SOLVER_ASYNC_MULTADD || solver == AMGB_SOLVER_ASYNC_AFACX) {
       // the persistent kernel streams CTA-sized blocks (bulk copies start 8-entry aligned)
@@ -344,8 +377,8 @@ int amgb_set_matrix(amgb_ctx *c, int kind, int level, int nrows, int ncols, int 
    // shorter goes through the stream kernel (measured per matrix with tools/spmv_sweep.py, profiles/)
    const bool long_rows = nrows > 0 && (double)nnz / nrows >= 96.0;
    if (long_rows) M.lpr = 32;
-   if (c->opt.use_stream && M.sell_slices == 0 && nrows > 0 && !(long_rows && c->opt.stream_variant == 8)) {
-      if ((rc = build_stream_blocks(c, M, nrows, ncols, rp, ci))) return rc;
+   if (c->opt.use_stream && M.sell_slices == 0 && nrows > 0 && !(long_rows && kStreamVariants[c->opt.stream_variant].stages <= 0)) {
+      if ((rc = build_stream_blocks(c, M, nrows, ncols, rp, ci, va))) return rc;
    }
    return AMGB_OK;
 }
@@ -392,6 +425,12 @@ int amgb_setup(amgb_ctx *c)
       const bool part = amgb_dist_level_distributed(c, l);
       if (!part) c->launches += launch_colscale(c->stream, c->A[l].nnz, c->A[l].ci, c->A[l].va, cs, sv);
       c->A[l].sval = sv;
+      if (c->A[l].pos) {   // scaled values of the column-sorted chunk copy
+         double *psv = nullptr;
+         if ((rc = dev_alloc(c, &psv, (size_t)c->A[l].nnz))) return rc;
+         if (!part) c->launches += launch_colscale(c->stream, c->A[l].nnz, c->A[l].pci, c->A[l].pva, cs, psv);
+         c->A[l].psval = psv;
+      }
       if (c->A[l].sell_slices > 0) {
          long pe = c->sell_entries[&c->A[l]];
          double *ssv = nullptr;

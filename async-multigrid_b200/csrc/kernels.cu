@@ -119,14 +119,14 @@ inline int grid_for(const LaunchCfg &cfg, long work_threads)
 
 }  // namespace
 
-template <int EPT, bool SVAL>
+template <int EPT, bool SVAL, bool SORTED>
 __global__ void __launch_bounds__(kBlock) k_spmv_wstream(DevCSR M, const double *x, double *y, SpmvEpilogue e, double *partials)
 {
    __shared__ __align__(16) double swarp[(kBlock / 32) * EPT * 32];
    const bool norm = partials != nullptr;
    const int warp = threadIdx.x >> 5;
-   double ss = warp_stream_rows_team<true, SVAL, EPT>(M, x, y, e, blockIdx.x * (kBlock / 32) + warp, gridDim.x * (kBlock / 32),
-                                                      swarp + warp * EPT * 32, norm);
+   double ss = warp_stream_rows_team<true, SVAL, EPT, SORTED>(M, x, y, e, blockIdx.x * (kBlock / 32) + warp, gridDim.x * (kBlock / 32),
+                                                              swarp + warp * EPT * 32, norm);
    if (norm) {
       ss = block_sum(ss);
       if (threadIdx.x == 0) partials[blockIdx.x] = ss;
@@ -173,17 +173,17 @@ static int launch_stream_variant(const LaunchCfg &cfg, cudaStream_t st, const De
    return grid;
 }
 
-template <int EPT>
+template <int EPT, bool SORTED>
 static int launch_wstream(const LaunchCfg &cfg, cudaStream_t st, const DevCSR &M, bool use_sval, const double *x, double *y,
                           const SpmvEpilogue &e, double *partials)
 {
    static int occ[2] = {0, 0};
-   const int cap = use_sval ? resident_ctas(k_spmv_wstream<EPT, true>, kBlock, 0, cfg.num_sms, &occ[1])
-                            : resident_ctas(k_spmv_wstream<EPT, false>, kBlock, 0, cfg.num_sms, &occ[0]);
+   const int cap = use_sval ? resident_ctas(k_spmv_wstream<EPT, true, SORTED>, kBlock, 0, cfg.num_sms, &occ[1])
+                            : resident_ctas(k_spmv_wstream<EPT, false, SORTED>, kBlock, 0, cfg.num_sms, &occ[0]);
    const long want = ((long)M.nblk + kBlock / 32 - 1) / (kBlock / 32);
    const int grid = (int)std::max(1L, std::min(want, (long)cap));
-   if (use_sval) k_spmv_wstream<EPT, true><<<grid, kBlock, 0, st>>>(M, x, y, e, partials);
-   else k_spmv_wstream<EPT, false><<<grid, kBlock, 0, st>>>(M, x, y, e, partials);
+   if (use_sval) k_spmv_wstream<EPT, true, SORTED><<<grid, kBlock, 0, st>>>(M, x, y, e, partials);
+   else k_spmv_wstream<EPT, false, SORTED><<<grid, kBlock, 0, st>>>(M, x, y, e, partials);
    return grid;
 }
 
@@ -193,9 +193,12 @@ int launch_spmv(const LaunchCfg &cfg, cudaStream_t st, const DevCSR &M, bool use
    int grid;
    if (M.sell_slices > 0) grid = launch_spmv_mode<1>(cfg, st, M, use_sval, x, y, e, partials, ((long)M.sell_slices * 32 + kBlock - 1) / kBlock);
    else if (M.nblk > 0 && M.wept > 0) {
-      if (M.wept <= 4) grid = launch_wstream<4>(cfg, st, M, use_sval, x, y, e, partials);
-      else if (M.wept <= 8) grid = launch_wstream<8>(cfg, st, M, use_sval, x, y, e, partials);
-      else grid = launch_wstream<16>(cfg, st, M, use_sval, x, y, e, partials);
+      if (M.pos) {
+         if (M.wept <= 4) grid = launch_wstream<4, true>(cfg, st, M, use_sval, x, y, e, partials);
+         else grid = launch_wstream<8, true>(cfg, st, M, use_sval, x, y, e, partials);
+      } else if (M.wept <= 4) grid = launch_wstream<4, false>(cfg, st, M, use_sval, x, y, e, partials);
+      else if (M.wept <= 8) grid = launch_wstream<8, false>(cfg, st, M, use_sval, x, y, e, partials);
+      else grid = launch_wstream<16, false>(cfg, st, M, use_sval, x, y, e, partials);
    } else if (M.nblk > 0) {
       switch (cfg.stream_variant) {   // keep in step with kStreamVariants (launch.h)
          case 1: grid = launch_stream_variant<128, 1024, 0, 2>(cfg, st, M, use_sval, x, y, e, partials); break;

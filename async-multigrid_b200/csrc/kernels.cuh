@@ -267,7 +267,7 @@ __device__ __forceinline__ double stream_rows_team(const DevCSR &M, const double
 // for each other, so the load / gather / reduce phases of the 32-64 resident warps of an SM overlap
 // freely -- the CTA-synchronous variant above spends ~20 % of its issue slots in barrier stalls and ~45 %
 // waiting on gathers with only 3-5 CTAs to hide them (profiles/).  swarp: EPT*32 doubles per warp.
-template <bool RO, bool SVAL, int EPT>
+template <bool RO, bool SVAL, int EPT, bool SORTED = false>
 __device__ __forceinline__ double warp_stream_rows_team(const DevCSR &M, const double *__restrict__ x, double *y,
                                                         const SpmvEpilogue &e, int team_warp, int team_nwarps,
                                                         double *swarp, bool want_sumsq)
@@ -292,13 +292,19 @@ __device__ __forceinline__ double warp_stream_rows_team(const DevCSR &M, const d
          }
          continue;
       }
-      int cc[EPT];
+      int cc[EPT], pp[EPT];
       double vv[EPT];
+      const int *__restrict__ cip = SORTED ? M.pci : M.ci;
+      const double *__restrict__ vap = SORTED ? (SVAL ? M.psval : M.pva) : va;
 #pragma unroll
       for (int k = 0; k < EPT; k++) {
          const int q = lane + 32 * k;
-         cc[k] = 0; vv[k] = 0.0;
-         if (q < cnt) { cc[k] = ld_stream(M.ci + p0 + q); vv[k] = ld_stream(va + p0 + q); }
+         cc[k] = 0; vv[k] = 0.0; pp[k] = q;
+         if (q < cnt) {
+            cc[k] = ld_stream(cip + p0 + q);
+            vv[k] = ld_stream(vap + p0 + q);
+            if (SORTED) pp[k] = ld_stream(M.pos + p0 + q);
+         }
       }
       // lanes per row: the largest power of two such that all rows fit in one pass
       int lpr = 1;
@@ -322,7 +328,7 @@ __device__ __forceinline__ double warp_stream_rows_team(const DevCSR &M, const d
 #pragma unroll
       for (int k = 0; k < EPT; k++) {
          const int q = lane + 32 * k;
-         if (q < cnt) swarp[q] = vv[k];
+         if (q < cnt) swarp[pp[k]] = vv[k];
       }
       __syncwarp();
       {

@@ -14,11 +14,12 @@ struct LaunchCfg {
 // selects one; the row blocks are built for its cap / xcap at upload time.
 struct StreamVariant { int nt, cap, xcap, stages; };
 // stages == 0: the warp-granular variant (warp_stream_rows_team), cap = entries per warp chunk
-#define AMGB_NUM_STREAM_VARIANTS 11
+// stages == -1: warp-granular with column-sorted chunks (DevCSR::pci/pva/pos)
+#define AMGB_NUM_STREAM_VARIANTS 13
 static const StreamVariant kStreamVariants[AMGB_NUM_STREAM_VARIANTS] = {
    {256, 2048, 0, 3}, {128, 1024, 0, 2}, {128, 1024, 0, 3}, {256, 2048, 1536, 2},
    {128, 1024, 1024, 2}, {256, 1024, 0, 2}, {128, 1024, 1024, 3}, {128, 2048, 0, 2},
-   {256, 256, 0, 0}, {256, 128, 0, 0}, {256, 512, 0, 0},
+   {256, 256, 0, 0}, {256, 128, 0, 0}, {256, 512, 0, 0}, {256, 256, 0, -1}, {256, 128, 0, -1},
 };
 
 // y = gamma*c + rs.*(beta*b + alpha*M*x); optional sum of y_i^2 into partial sums (one per CTA,
