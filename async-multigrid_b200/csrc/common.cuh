@@ -23,6 +23,7 @@ struct DevCSR {
    const int *sell_ci = nullptr;
    const double *sell_va = nullptr;
    const double *sell_sval = nullptr;
+   const int *sell_perm = nullptr;   // SELL-C-sigma: slot (32*slice + lane) -> row, -1 for padding slots; nullptr = identity
    int lpr = 8;                      // lanes per row chosen for the CSR vector kernel
    // CSR-stream row blocks: CTA b owns rows [blk[b], blk[b+1]) whose entries (<= AMGB_STREAM_CAP,
    // counted from the 4-aligned start) are streamed with 128-bit loads into shared memory and then

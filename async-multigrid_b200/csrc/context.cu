@@ -83,6 +83,7 @@ void amgb_default_options(amgb_options *o)
    o->l2_persist = 1;
    o->use_stream = 1;
    o->stream_variant = 8;
+   o->sell_sigma = 128;
 }
 
 int amgb_create(amgb_ctx **out, int device)
@@ -164,32 +165,52 @@ static int pick_lpr(int nrows, int nnz)
    return 32;
 }
 
-// Build the sliced-ELL (C=32) copy on the host when padding stays below 15 %.
-static int build_sell(amgb_ctx *c, DevCSR &M, int nrows, const int *rp, const int *ci, const double *va)
+// Build the sliced-ELL (C = 32) copy on the host.  sigma == 1: rows in natural order, accepted when padding
+// <= 2 % (stencil levels).  sigma > 1 (SELL-C-sigma): inside every window of `sigma` consecutive rows the rows are
+// ordered by decreasing length before being cut into slices (sell_perm records slot -> row), which brings the
+// padding of the Galerkin / transfer operators from 35-58 % down to ~11-15 % (sigma = 128) while the 32 rows of
+// a slice stay within 128 rows of each other, so that one gather instruction still touches few lines of x.
+static int build_sell(amgb_ctx *c, DevCSR &M, int nrows, const int *rp, const int *ci, const double *va, int sigma,
+                      double max_padding)
 {
    const int slices = (nrows + 31) / 32;
+   std::vector<int> perm;
+   if (sigma > 1) {
+      perm.resize((size_t)slices * 32, -1);
+      for (int r = 0; r < nrows; r++) perm[r] = r;
+#pragma omp parallel for schedule(static)
+      for (int w0 = 0; w0 < nrows; w0 += sigma) {
+         const int w1 = std::min(nrows, w0 + sigma);
+         std::stable_sort(perm.begin() + w0, perm.begin() + w1,
+                          [&](int a, int b) { return rp[a + 1] - rp[a] > rp[b + 1] - rp[b]; });
+      }
+   }
+   auto row_of = [&](int slot) { return sigma > 1 ? perm[slot] : (slot < nrows ? slot : -1); };
    std::vector<int> off((size_t)slices + 1, 0);
    long padded = 0;
    for (int s = 0; s < slices; s++) {
       int w = 0;
-      for (int r = s * 32; r < std::min(nrows, s * 32 + 32); r++) w = std::max(w, rp[r + 1] - rp[r]);
+      for (int l = 0; l < 32; l++) {
+         const int r = row_of(s * 32 + l);
+         if (r >= 0) w = std::max(w, rp[r + 1] - rp[r]);
+      }
       padded += (long)w * 32;
       if (padded > 2147483000L) return AMGB_OK;   // keep CSR
       off[s + 1] = (int)padded;
    }
    const long nnz = rp[nrows];
-   if (nnz == 0 || (double)padded > 1.15 * (double)nnz) return AMGB_OK;
+   if (nnz == 0 || (double)padded > (1.0 + max_padding) * (double)nnz) return AMGB_OK;
    std::vector<int> sci((size_t)padded);
    std::vector<double> sva((size_t)padded, 0.0);
 #pragma omp parallel for schedule(static)
    for (int s = 0; s < slices; s++) {
       const int w = (off[s + 1] - off[s]) / 32;
       for (int l = 0; l < 32; l++) {
-         const int r = s * 32 + l;
+         const int r = row_of(s * 32 + l);
          for (int k = 0; k < w; k++) {
             const size_t d = (size_t)off[s] + (size_t)k * 32 + l;
-            if (r < nrows && rp[r] + k < rp[r + 1]) { sci[d] = ci[rp[r] + k]; sva[d] = va[rp[r] + k]; }
-            else { sci[d] = (r < nrows && rp[r + 1] > rp[r]) ? ci[rp[r]] : 0; sva[d] = 0.0; }   // padding: harmless gather, zero value
+            if (r >= 0 && rp[r] + k < rp[r + 1]) { sci[d] = ci[rp[r] + k]; sva[d] = va[rp[r] + k]; }
+            else { sci[d] = (r >= 0 && rp[r + 1] > rp[r]) ? ci[rp[r]] : 0; sva[d] = 0.0; }   // padding: harmless gather, zero value
          }
       }
    }
@@ -198,6 +219,11 @@ static int build_sell(amgb_ctx *c, DevCSR &M, int nrows, const int *rp, const in
    if ((rc = dev_upload(c, &d_off, off.data(), off.size()))) return rc;
    if ((rc = dev_upload(c, &d_ci, sci.data(), sci.size()))) return rc;
    if ((rc = dev_upload(c, &d_va, sva.data(), sva.size()))) return rc;
+   if (sigma > 1) {
+      int *d_perm;
+      if ((rc = dev_upload(c, &d_perm, perm.data(), perm.size()))) return rc;
+      M.sell_perm = d_perm;
+   }
    CUDA_OK(c, cudaStreamSynchronize(c->stream));   // host vectors go out of scope
    M.sell_slices = slices; M.sell_off = d_off; M.sell_ci = d_ci; M.sell_va = d_va;
    c->sell_entries[&M] = padded;
@@ -371,7 +397,10 @@ int amgb_set_matrix(amgb_ctx *c, int kind, int level, int nrows, int ncols, int 
    M.lpr = pick_lpr(nrows, nnz);
    CUDA_OK(c, cudaStreamSynchronize(c->stream));
    if (c->opt.use_sell && nrows >= 1024) {
-      if ((rc = build_sell(c, M, nrows, rp, ci, va))) return rc;
+      if ((rc = build_sell(c, M, nrows, rp, ci, va, 1, 0.02))) return rc;
+      if (M.sell_slices == 0 && c->opt.sell_sigma > 1 && (double)nnz / nrows < 96.0) {
+         if ((rc = build_sell(c, M, nrows, rp, ci, va, c->opt.sell_sigma, 0.25))) return rc;
+      }
    }
    // long rows (restrictions on coarse levels: 150-300 entries) are served best by one warp per row; everything
    // shorter goes through the stream kernel (measured per matrix with tools/spmv_sweep.py, profiles/)

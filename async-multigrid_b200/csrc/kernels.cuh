@@ -56,13 +56,14 @@ __device__ __forceinline__ double sell_rows_team(const DevCSR &M, const double *
    for (int sl = team_tid >> 5; sl < M.sell_slices; sl += nwarp) {
       const int off = __ldg(M.sell_off + sl);
       const int width = (__ldg(M.sell_off + sl + 1) - off) >> 5;
-      const int row = (sl << 5) + lane;
+      int row = (sl << 5) + lane;
+      if (M.sell_perm) row = __ldg(M.sell_perm + row);
       const int *__restrict__ cp = M.sell_ci + off + lane;
       const double *__restrict__ vp = va + off + lane;
       double acc = 0.0;
 #pragma unroll 4
       for (int k = 0; k < width; k++) acc += ld_stream(vp + (k << 5)) * ld_x<RO>(x + ld_stream(cp + (k << 5)));
-      if (row < M.nrows) {
+      if (row >= 0 && row < M.nrows) {
          double v = epilogue_apply<RO>(e, row, acc);
          y[row] = v;
          if (want_sumsq) sumsq += v * v;

@@ -35,7 +35,7 @@ class Options(C.Structure):
                 ("num_pre_smooth_sweeps", C.c_int), ("num_post_smooth_sweeps", C.c_int),
                 ("num_fine_smooth_sweeps", C.c_int), ("num_coarse_smooth_sweeps", C.c_int),
                 ("jgs_block_rows", C.c_int), ("use_sell", C.c_int), ("l2_persist", C.c_int), ("use_stream", C.c_int),
-                ("stream_variant", C.c_int)]
+                ("sell_sigma", C.c_int), ("stream_variant", C.c_int)]
 
 
 _lib = None
@@ -108,7 +108,7 @@ class Solver:
 
     def __init__(self, h, solver=H.MULTADD, smoother=H.JACOBI, smooth_weight=1.0, num_pre=1, num_post=1,
                  fine_sweeps=1, coarse_sweeps=1, jgs_block_rows=8, use_sell=True, l2_persist=True, use_stream=True,
-                 stream_variant=None, device=0):
+                 stream_variant=None, sell_sigma=None, device=0):
         self.L = load_library()
         self.h = h
         self.ctx = C.c_void_p()
@@ -126,6 +126,10 @@ class Solver:
             o.stream_variant = int(stream_variant)
         elif "AMGB_STREAM_VARIANT" in os.environ:
             o.stream_variant = int(os.environ["AMGB_STREAM_VARIANT"])
+        if sell_sigma is not None:
+            o.sell_sigma = int(sell_sigma)
+        elif "AMGB_SELL_SIGMA" in os.environ:
+            o.sell_sigma = int(os.environ["AMGB_SELL_SIGMA"])
         self.options = o
         self._ck(self.L.amgb_set_options(self.ctx, C.byref(o)))
         self._ck(self.L.amgb_set_num_levels(self.ctx, h.num_levels))

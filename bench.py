@@ -218,10 +218,12 @@ def run_b200(args):
                 "final_relres": true_rel},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "k_spmv (r = f - A_0 u, fine level)", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": "k_spmv<1,0> sliced-ELL SpGEMV, r = f - A_0 u on the fine level", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "frac_of_8000_spec": achieved / 8000.0,
                      "peak_source": peak_src, "bytes_per_launch": int(res_bytes), "ms_per_launch": res_ms,
-                     "traffic": None},
+                     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full capture at 256^3
+                     # (profiles/r1_ncu_full_final_kernels.csv: 1.677 GB + 0.115 GB); only valid for the default size
+                     "traffic": 1.792e9 if (args.n == 256 and not args.nz) else None},
         "solve_roofline": {"bytes_per_cycle": int(cyc_bytes), "cycles": int(cycles),
                            "achieved": solve_bytes / solve_s / 1e9, "frac": solve_bytes / solve_s / 1e9 / peak, "unit": "GB/s"},
     }

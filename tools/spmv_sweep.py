@@ -28,7 +28,12 @@ def main():
         mats += [("A%d" % l, 0, l, False), ("A%d*" % l, 0, l, True), ("P%d" % l, 1, l, False), ("R%d" % l, 2, l, False)]
     rows = {}
     for v in args.variants.split(","):
-        kw = dict(use_stream=False) if v == "csr" else dict(stream_variant=int(v))
+        if v == "csr":
+            kw = dict(use_stream=False, sell_sigma=0)
+        elif v.startswith("sell"):
+            kw = dict(sell_sigma=int(v[4:]))
+        else:
+            kw = dict(stream_variant=int(v), sell_sigma=0)
         s = amg.Solver(h, H.MULTADD, H.JACOBI, 0.9, **kw)
         blocks, staged = s.stream_stats()
         out = {}
