@@ -398,7 +398,11 @@ int amgb_set_matrix(amgb_ctx *c, int kind, int level, int nrows, int ncols, int 
    CUDA_OK(c, cudaStreamSynchronize(c->stream));
    if (c->opt.use_sell && nrows >= 1024) {
       if ((rc = build_sell(c, M, nrows, rp, ci, va, 1, 0.02))) return rc;
-      if (M.sell_slices == 0 && c->opt.sell_sigma > 1 && (double)nnz / nrows < 96.0) {
+      // (the persistent asynchronous kernel runs few warps per SM: there the TMA-fed CTA blocks are faster
+      //  than any gather-per-lane layout -- 1.6 s vs 3.0 s for the 256^3 solve -- so SELL-C-sigma is skipped)
+      const bool persistent = c->opt.solver == AMGB_SOLVER_ASYNC_MULTADD || c->opt.solver == AMGB_SOLVER_ASYNC_AFACX;
+      // small levels stay on the warp-stream kernel: with few slices the one-row-per-lane loop is latency bound
+      if (M.sell_slices == 0 && c->opt.sell_sigma > 1 && !persistent && nrows >= 262144 && (double)nnz / nrows < 96.0) {
          if ((rc = build_sell(c, M, nrows, rp, ci, va, c->opt.sell_sigma, 0.25))) return rc;
       }
    }

@@ -348,3 +348,30 @@ def test_launch_counter_counts_graph_replays():
     # restrictions + smoothers + Horner prolongations + residual + reduce
     assert per_iter >= 2 * (h.num_levels - 2) + 2
     s.close()
+
+
+# ---- BASELINE.json's full size (3-D 7-pt, 256^3): size-independent properties + the first cycles vs the oracle ----
+def test_full_size_256_properties():
+    w = 0.9
+    h, b = _problem("7pt", 256, H.MULTADD, w)
+    s = amg.Solver(h, H.MULTADD, H.JACOBI, w)
+    # (1) linearity of the cycle operator at full size
+    r2 = np.cos(np.arange(h.n[0]) * 0.01)
+    c1, c2 = s.cycle(b), s.cycle(r2)
+    lhs = s.cycle(2.0 * b - 3.0 * r2)
+    assert _rel(lhs, 2.0 * c1 - 3.0 * c2) <= 1e-12
+    # (2) the first two cycles of the history against the CPU oracle (each oracle cycle streams ~15 GB)
+    _, want, _ = O.Problem(h, H.MULTADD, H.JACOBI, w).solve_sync(b, 1e-9, 2)
+    out = s.SMEM_Solve(b, 1e-9, 100)
+    hist = out["hist"]
+    assert np.max(np.abs(hist[:3] - want[:3])) <= HIST_TOL
+    # (3) monotone convergence to the tolerance, every level credited with every cycle
+    assert hist[-1] < 1e-9 and np.all(np.diff(hist) < 0) and out["cycles"] <= 40
+    assert list(out["corrections"]) == [out["cycles"]] * h.num_levels
+    # (4) the reported residual is the true one: recomputed by the oracle from the returned u
+    true = O.norm2(O.spgemv(h.A[0], out["u"], b, -1.0, 1.0)) / O.norm2(b)
+    assert abs(true - hist[-1]) <= 1e-12
+    # (5) idempotence of the stop rule: solving again from x0 = 0 reproduces the history bit for bit
+    again = s.SMEM_Solve(b, 1e-9, 100)["hist"]
+    assert np.array_equal(again, hist)
+    s.close()
