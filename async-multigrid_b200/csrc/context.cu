@@ -166,7 +166,7 @@ static int pick_lpr(int nrows, int nnz)
 }
 
 // Build the sliced-ELL (C = 32) copy on the host.  sigma == 1: rows in natural order, accepted when padding
-// <= 2 % (stencil levels).  sigma > 1 (SELL-C-sigma): inside every window of `sigma` consecutive rows the rows are
+// <= 15 % (stencil levels).  sigma > 1 (SELL-C-sigma): inside every window of `sigma` consecutive rows the rows are
 // ordered by decreasing length before being cut into slices (sell_perm records slot -> row), which brings the
 // padding of the Galerkin / transfer operators from 35-58 % down to ~11-15 % (sigma = 128) while the 32 rows of
 // a slice stay within 128 rows of each other, so that one gather instruction still touches few lines of x.
@@ -397,7 +397,7 @@ int amgb_set_matrix(amgb_ctx *c, int kind, int level, int nrows, int ncols, int 
    M.lpr = pick_lpr(nrows, nnz);
    CUDA_OK(c, cudaStreamSynchronize(c->stream));
    if (c->opt.use_sell && nrows >= 1024) {
-      if ((rc = build_sell(c, M, nrows, rp, ci, va, 1, 0.02))) return rc;
+      if ((rc = build_sell(c, M, nrows, rp, ci, va, 1, 0.15))) return rc;
       // (the persistent asynchronous kernel runs few warps per SM: there the TMA-fed CTA blocks are faster
       //  than any gather-per-lane layout -- 1.6 s vs 3.0 s for the 256^3 solve -- so SELL-C-sigma is skipped)
       const bool persistent = c->opt.solver == AMGB_SOLVER_ASYNC_MULTADD || c->opt.solver == AMGB_SOLVER_ASYNC_AFACX;

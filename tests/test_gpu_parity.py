@@ -274,7 +274,7 @@ def test_chebyshev_accelerated_bpx_matches_oracle():
 # ---- asynchronous solves --------------------------------------------------------------------------------
 @pytest.mark.parametrize("solver,smoother,w,cycles,post", [
     (H.ASYNC_MULTADD, H.JACOBI, 0.9, 80, 1),
-    (H.ASYNC_MULTADD, H.HYBRID_JACOBI_GAUSS_SEIDEL, 0.7, 400, 0),   # w = 1 diverges asynchronously, also in the reference
+    (H.ASYNC_MULTADD, H.HYBRID_JACOBI_GAUSS_SEIDEL, 0.7, 600, 0),   # w = 1 diverges asynchronously, also in the reference
     (H.ASYNC_AFACX, H.JACOBI, 0.5, 150, 1),
 ])
 def test_async_reaches_tolerance(solver, smoother, w, cycles, post):
