@@ -317,6 +317,15 @@ static int async_prepare(amgb_ctx *c)
    int *flag;
    if ((rc = amgb_dev_alloc_bytes(c, (void **)&flag, sizeof(int) * 4, true))) return rc;
    hp.converge_flag = flag;
+   if (o.l2_persist && c->arena_used > 0) {
+      // pin the coarse hierarchy in L2 for the persistent kernel (launch attribute, see launch_async)
+      c->window.base_ptr = c->arena;
+      c->window.num_bytes = std::min(c->arena_used, c->max_window);
+      c->window.hitRatio = 1.0f;
+      c->window.hitProp = cudaAccessPropertyPersisting;
+      c->window.missProp = cudaAccessPropertyStreaming;
+      c->window_valid = true;
+   }
    c->async_host = new AsyncParams(hp);
    if ((rc = amgb_dev_alloc_bytes(c, &c->async_params_dev, sizeof(AsyncParams), false))) return rc;
    CUDA_OK(c, cudaStreamSynchronize(c->stream));

@@ -34,6 +34,14 @@ static int dev_alloc(amgb_ctx *c, T **p, size_t n)
 {
    *p = nullptr;
    n += 64 / sizeof(T) + 8;   // slack: 16-byte granular bulk copies may touch a few elements past the end
+   if (c->alloc_in_arena && c->arena) {
+      const size_t bytes = (n * sizeof(T) + 255) & ~(size_t)255;
+      if (c->arena_used + bytes <= c->arena_size) {
+         *p = reinterpret_cast<T *>(c->arena + c->arena_used);
+         c->arena_used += bytes;
+         return AMGB_OK;
+      }
+   }
    cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
    if (e != cudaSuccess) return amgb_fail(c, AMGB_ENOMEM, "cudaMalloc(%zu bytes): %s", n * sizeof(T), cudaGetErrorString(e));
    c->allocs.push_back((void *)*p);
@@ -106,6 +114,17 @@ int amgb_create(amgb_ctx **out, int device)
    c->max_window = prop.accessPolicyMaxWindowSize;
    c->persist_max = prop.persistingL2CacheMaxSize;
    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return AMGB_ECUDA; }
+   // L2 persistence for the coarse hierarchy: at most half of what the device lets us set aside
+   if (c->persist_max > 0 && c->max_window > 0) {
+      const size_t want = std::min<size_t>(std::min(c->persist_max, c->max_window), (size_t)48 << 20);
+      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess && cudaMalloc((void **)&c->arena, want) == cudaSuccess) {
+         c->arena_size = want;
+         c->allocs.push_back(c->arena);
+      } else {
+         c->arena = nullptr;
+         cudaGetLastError();
+      }
+   }
    cudaEventCreate(&c->ev0);
    cudaEventCreate(&c->ev1);
    cudaMallocHost((void **)&c->h_scalars, 64 * sizeof(double));
@@ -389,6 +408,9 @@ int amgb_set_matrix(amgb_ctx *c, int kind, int level, int nrows, int ncols, int 
    }
    int *d_rp, *d_ci; double *d_va;
    int rc;
+   // coarse levels (level >= 2, everything of the matrix fits in what is left of the arena) live in the L2-pinned arena
+   c->alloc_in_arena = c->opt.l2_persist && level >= 2 && (size_t)nnz * 40 + (size_t)nrows * 16 + 65536 <= c->arena_size - c->arena_used;
+   struct ArenaOff { amgb_ctx *c; ~ArenaOff() { c->alloc_in_arena = false; } } arena_off{c};
    if ((rc = dev_upload(c, &d_rp, rp, (size_t)nrows + 1))) return rc;
    if ((rc = dev_upload(c, &d_ci, ci, (size_t)nnz))) return rc;
    if ((rc = dev_upload(c, &d_va, va, (size_t)nnz))) return rc;
@@ -880,6 +902,15 @@ int amgb_stream_stats(amgb_ctx *c, long long *blocks, long long *blocks_staged_x
    if (!c) return AMGB_EINVAL;
    if (blocks) *blocks = c->stream_blocks;
    if (blocks_staged_x) *blocks_staged_x = c->stream_blocks_staged_x;
+   return AMGB_OK;
+}
+
+// bytes of coarse-hierarchy data placed in the L2-pinned arena (the access-policy window of the persistent kernel)
+int amgb_l2_arena_bytes(amgb_ctx *c, long long *used, long long *capacity)
+{
+   if (!c) return AMGB_EINVAL;
+   if (used) *used = (long long)c->arena_used;
+   if (capacity) *capacity = (long long)c->arena_size;
    return AMGB_OK;
 }
 

@@ -39,6 +39,11 @@ struct amgb_ctx {
    // async
    void *async_params_dev = nullptr;
    AsyncParams *async_host = nullptr;
+   // one contiguous arena for the coarse hierarchy, so that ONE access-policy window can pin it in L2 for the
+   // persistent asynchronous kernel (every level group re-reads it once per correction)
+   char *arena = nullptr;
+   size_t arena_size = 0, arena_used = 0;
+   bool alloc_in_arena = false;
    cudaAccessPolicyWindow window = {};
    bool window_valid = false;
    bool async_ready = false;

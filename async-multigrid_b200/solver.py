@@ -24,7 +24,7 @@ ABI_SYMBOLS = [
     "amgb_set_num_levels", "amgb_set_matrix", "amgb_set_options", "amgb_setup",
     "amgb_set_rhs", "amgb_set_solution", "amgb_get_solution", "amgb_get_residual",
     "amgb_spgemv", "amgb_smooth", "amgb_norm2", "amgb_cycle", "amgb_solve_sync", "amgb_solve_async",
-    "amgb_smem_solve", "amgb_time_residual", "amgb_level_storage", "amgb_time_spmv", "amgb_stream_stats",
+    "amgb_smem_solve", "amgb_time_residual", "amgb_level_storage", "amgb_time_spmv", "amgb_stream_stats", "amgb_l2_arena_bytes",
     "amgb_dist_unique_id", "amgb_dist_init", "amgb_dist_set_level", "amgb_dist_setup", "amgb_dist_set_rhs",
     "amgb_dist_get_solution", "amgb_dist_solve_sync", "amgb_dist_stats",
 ]
@@ -77,6 +77,7 @@ def load_library():
     L.amgb_level_storage.argtypes = [C.c_void_p, C.c_int, C.c_int, IP]
     L.amgb_time_spmv.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, DP]
     L.amgb_stream_stats.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+    L.amgb_l2_arena_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     L.amgb_async_groups.argtypes = [C.c_void_p, IP, IP]
     L.amgb_dist_unique_id.argtypes = [C.c_char_p]
     L.amgb_dist_init.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
@@ -253,6 +254,11 @@ class Solver:
     def stream_stats(self):
         a, b = C.c_longlong(0), C.c_longlong(0)
         self._ck(self.L.amgb_stream_stats(self.ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def l2_arena_bytes(self):
+        a, b = C.c_longlong(0), C.c_longlong(0)
+        self._ck(self.L.amgb_l2_arena_bytes(self.ctx, C.byref(a), C.byref(b)))
         return a.value, b.value
 
     def is_sell(self, kind, level):

@@ -103,7 +103,7 @@ SMOOTHERS = {"j": 0, "hybrid_jgs": 2, "L1j": 6}
 
 def build_problem(args, H):
     t0 = time.time()
-    A = H.laplacian("7pt", args.n, args.n, args.nz or args.n)
+    A = H.laplacian(args.problem, args.n, args.n, args.nz or args.n)
     h = H.amg_setup(A, theta=args.theta)
     sv = SOLVERS[args.solver]
     base = H.MULTADD if sv in (H.MULTADD, H.ASYNC_MULTADD) else sv
@@ -208,8 +208,8 @@ def run_b200(args):
         "metric": METRIC, "value": solve_s, "unit": "s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": solve_s * 1e3, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "3D 7-pt Laplacian %d^3 (n=%d, nnz=%d), %s, smoother %s w=%.2f, tol 1e-9, x0=0, b=srand(0) RandDouble(-1,1)"
-                   % (args.n, h.n[0], h.A[0].nnz, args.solver, args.smoother, args.smooth_weight),
+        "config": {"workload": "3D %s Laplacian %d^3 (n=%d, nnz=%d), %s, smoother %s w=%.2f, tol 1e-9, x0=0, b=srand(0) RandDouble(-1,1)"
+                   % (args.problem, args.n, h.n[0], h.A[0].nnz, args.solver, args.smoother, args.smooth_weight),
                    "levels": h.num_levels, "operator_complexity": round(h.operator_complexity(), 3),
                    "cycles_to_tol": int(cycles), "final_relres": float(rel),
                    "l2": "inputs (A_0 alone %.2f GB) exceed the 126 MB L2; no explicit flush" % (12e-9 * h.A[0].nnz),
@@ -223,12 +223,14 @@ def run_b200(args):
                      "peak_source": peak_src, "bytes_per_launch": int(res_bytes), "ms_per_launch": res_ms,
                      # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full capture at 256^3
                      # (profiles/r1_ncu_full_final_kernels.csv: 1.677 GB + 0.115 GB); only valid for the default size
-                     "traffic": 1.792e9 if (args.n == 256 and not args.nz) else None},
+                     "traffic": 1.792e9 if (args.n == 256 and not args.nz and args.problem == "7pt") else None},
         "solve_roofline": {"bytes_per_cycle": int(cyc_bytes), "cycles": int(cycles),
                            "achieved": solve_bytes / solve_s / 1e9, "frac": solve_bytes / solve_s / 1e9 / peak, "unit": "GB/s"},
     }
     if corr is not None:
         line["config"]["corrections_per_level"] = [int(x) for x in corr]
+        used, cap = s.l2_arena_bytes()
+        line["config"]["l2_persisting_window_bytes"] = int(used)
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, h, b, cycles if not is_async else num_cycles)
     s.close()
@@ -324,6 +326,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", "--grid", dest="n", type=int, default=256, help="grid points per dimension (per GPU slab)")
     ap.add_argument("--nz", type=int, default=0)
+    ap.add_argument("--problem", default="7pt", choices=["7pt", "27pt"], help="stencil (BASELINE.json configs[1] / configs[2])")
     ap.add_argument("--solver", default="multadd", choices=sorted(SOLVERS))
     ap.add_argument("--smoother", default="j", choices=sorted(SMOOTHERS))
     ap.add_argument("--smooth-weight", type=float, default=0.9)

@@ -130,6 +130,8 @@ int amgb_level_storage(amgb_ctx *ctx, int kind, int level, int *is_sell);
 /* event-timed y = M x for one matrix of the hierarchy (tools/spmv_sweep.py) and CSR-stream block statistics */
 int amgb_time_spmv(amgb_ctx *ctx, int kind, int level, int use_scaled_values, int reps, double *ms_per_launch);
 int amgb_stream_stats(amgb_ctx *ctx, long long *blocks, long long *blocks_with_staged_x);
+/* coarse-hierarchy bytes living in the L2-pinned arena (cudaAccessPolicyWindow of the persistent kernel) */
+int amgb_l2_arena_bytes(amgb_ctx *ctx, long long *used, long long *capacity);
 
 /* ---- multi-GPU (DMEM replacement; one process per GPU) ------------------------------------
  * Replaces DMEM_Add / DMEM_SyncAdd (src/DMEM_Add.cpp:20-178, src/DMEM_Mult.cpp:263-450) for the synchronous

@@ -296,6 +296,8 @@ def test_async_global_stop_rule_and_groups():
     s = amg.Solver(h, H.ASYNC_MULTADD, H.JACOBI, 0.9)
     cb, grid = s.async_groups()
     assert cb[0] == 0 and cb[-1] == grid and np.all(np.diff(cb) >= 1)
+    used, cap = s.l2_arena_bytes()
+    assert 0 < used <= cap          # the coarse levels (>= 2) sit in the arena the access-policy window pins in L2
     s.set_rhs(b)
     s.set_solution(None)
     corr, rel, secs = s.solve_async(60, amg.solver.CONVERGE_GLOBAL)
