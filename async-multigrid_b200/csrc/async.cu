@@ -285,6 +285,9 @@ static int async_prepare(amgb_ctx *c)
       else w += (double)(o.num_coarse_smooth_sweeps - 1) * c->A[k + 1].nnz + c->P[k].nnz + c->A[k].nnz +
                 (double)(o.num_fine_smooth_sweeps - 1) * c->A[k].nnz;
       for (int l = 0; l < k; l++) w += c->P[l].nnz;
+      // the coarsest level's correction is identically zero (see k_async_amg): its group only keeps the count
+      // and the stop protocol, so it gets the mandatory single CTA and no share of the rest
+      if (k == L - 1 && L > 1) w = 0.0;
       work[k] = w;
       tot += w;
    }
@@ -301,7 +304,10 @@ static int async_prepare(amgb_ctx *c)
       ctas[k] += extra;
       left -= extra;
    }
-   for (int k = 0; left > 0; k = (k + 1) % L) { ctas[k]++; left--; }
+   for (int k = 0; left > 0; k = (k + 1) % L) {
+      if (work[k] == 0.0 && L > 1) continue;          // never hand spare CTAs to the idle coarsest group
+      ctas[k]++; left--;
+   }
    hp.cta_begin[0] = 0;
    for (int k = 0; k < L; k++) hp.cta_begin[k + 1] = hp.cta_begin[k] + ctas[k];
    c->async_cta_begin.assign(hp.cta_begin, hp.cta_begin + L + 1);

@@ -23,6 +23,7 @@ struct DevCSR {
    const int *sell_ci = nullptr;
    const double *sell_va = nullptr;
    const double *sell_sval = nullptr;
+   int sell_base = 0;                // index of the first slice of this view (row-range launches of the multi-GPU path)
    const int *sell_perm = nullptr;   // SELL-C-sigma: slot (32*slice + lane) -> row, -1 for padding slots; nullptr = identity
    int lpr = 8;                      // lanes per row chosen for the CSR vector kernel
    // CSR-stream row blocks: CTA b owns rows [blk[b], blk[b+1]) whose entries (<= AMGB_STREAM_CAP,
@@ -48,6 +49,9 @@ struct DevCSR {
    // second block list for the persistent asynchronous kernel: CTA blocks of <= AMGB_STREAM_CAP entries
    int ncblk = 0;
    const int4 *cblk = nullptr;
+   // multi-GPU: launch units (slices / chunks / rows) [ulo, uhi) read only OWNED entries of the input vector, so
+   // they can run while the halo exchange is in flight; the units outside wait for it.  uhi <= ulo: no split.
+   int ulo = 0, uhi = 0;
 };
 #define AMGB_STREAM_CAP 2048          // largest row block any variant uses (and the persistent kernel's)
 #define AMGB_TEAM_STAGES 3

@@ -238,6 +238,7 @@ static int build_sell(amgb_ctx *c, DevCSR &M, int nrows, const int *rp, const in
    if ((rc = dev_upload(c, &d_off, off.data(), off.size()))) return rc;
    if ((rc = dev_upload(c, &d_ci, sci.data(), sci.size()))) return rc;
    if ((rc = dev_upload(c, &d_va, sva.data(), sva.size()))) return rc;
+   c->last_perm = perm;
    if (sigma > 1) {
       int *d_perm;
       if ((rc = dev_upload(c, &d_perm, perm.data(), perm.size()))) return rc;
@@ -267,6 +268,7 @@ static int build_stream_blocks(amgb_ctx *c, DevCSR &M, int nrows, int ncols, con
       blk.push_back(make_int4(start, r, rp[start], rp[r]));
    }
    const int nb = (int)blk.size();
+   c->last_blk = blk;
    // x windows per block (see DevCSR): built in parallel, then concatenated
    std::vector<int4> blkx((size_t)nb, make_int4(0, 0, 0, 0));
    std::vector<std::vector<int2>> wins((size_t)nb);
@@ -434,6 +436,37 @@ int amgb_set_matrix(amgb_ctx *c, int kind, int level, int nrows, int ncols, int 
    if (long_rows) M.lpr = 32;
    if (c->opt.use_stream && M.sell_slices == 0 && nrows > 0 && !(long_rows && kStreamVariants[c->opt.stream_variant].stages <= 0)) {
       if ((rc = build_stream_blocks(c, M, nrows, ncols, rp, ci, va))) return rc;
+   }
+   // multi-GPU: which launch units touch only owned entries of the input vector (see DevCSR::ulo/uhi)
+   int c0 = 0, c1 = 0;
+   if (amgb_dist_owned_cols(c, kind, level, &c0, &c1) && nrows > 0) {
+      std::vector<char> rint((size_t)nrows, 1);
+#pragma omp parallel for schedule(static)
+      for (int r = 0; r < nrows; r++)
+         for (int p = rp[r]; p < rp[r + 1]; p++)
+            if (ci[p] < c0 || ci[p] >= c1) { rint[r] = 0; break; }
+      const int nu = spmv_units(M);
+      std::vector<char> uint_((size_t)nu, 1);
+      if (M.sell_slices > 0) {
+         for (int u = 0; u < nu; u++)
+            for (int l = 0; l < 32; l++) {
+               const int slot = u * 32 + l;
+               const int r = M.sell_perm ? c->last_perm[slot] : (slot < nrows ? slot : -1);
+               if (r >= 0 && !rint[r]) { uint_[u] = 0; break; }
+            }
+      } else if (M.nblk > 0) {
+         for (int u = 0; u < nu; u++)
+            for (int r = c->last_blk[u].x; r < c->last_blk[u].y; r++)
+               if (!rint[r]) { uint_[u] = 0; break; }
+      } else {
+         for (int u = 0; u < nu; u++) uint_[u] = rint[u];
+      }
+      int lo = 0, hi = nu;
+      while (lo < nu && !uint_[lo]) lo++;
+      while (hi > lo && !uint_[hi - 1]) hi--;
+      bool contiguous = true;
+      for (int u = lo; u < hi; u++) if (!uint_[u]) { contiguous = false; break; }
+      if (contiguous && hi > lo) { M.ulo = lo; M.uhi = hi; }
    }
    return AMGB_OK;
 }

@@ -19,6 +19,8 @@ struct amgb_ctx {
    std::vector<DevCSR> A, P, R;
    std::vector<int> hA;
    std::map<const DevCSR *, long> sell_entries;
+   std::vector<int> last_perm;      // host copies of the last built SELL permutation / block list (unit classification)
+   std::vector<int4> last_blk;
    // per level: w/d, d/w, l1, 1/l1; residual chain, correction chain, two scratch vectors
    std::vector<double *> ws, dow, l1, inv_l1, r, e, t, w;
    double *f = nullptr, *u = nullptr, *cvec = nullptr, *u_outer = nullptr, *y_outer = nullptr;
@@ -55,6 +57,9 @@ struct amgb_ctx {
 };
 
 int amgb_fail(amgb_ctx *c, int code, const char *fmt, ...);
+// owned column range [c0, c1) of the input vector of matrix (kind, level) on a partitioned level; false if the
+// input vector is not partitioned (nothing to overlap)
+bool amgb_dist_owned_cols(const amgb_ctx *c, int kind, int level, int *c0, int *c1);
 void amgb_dist_teardown(amgb_ctx *c);
 int amgb_dist_diag_offset(const amgb_ctx *c, int level);          // position of the diagonal in a local row block
 bool amgb_dist_level_distributed(const amgb_ctx *c, int level);

@@ -16,6 +16,7 @@
 #include "ctx.h"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #ifdef AMG_HAVE_NCCL
@@ -38,6 +39,11 @@ struct DistState {
    std::vector<DistLevel> lv;
    std::vector<double *> ws, r, e;   // level layout
    double *u = nullptr, *f = nullptr;   // u: level-0 layout; f: owned rows
+   // halo exchange on its own stream, overlapped with the interior launch units of the SpMV that needs it
+   cudaStream_t comm_stream = nullptr;
+   cudaEvent_t ev_x = nullptr, ev_h = nullptr;
+   double *partials3 = nullptr;          // 3 x npartials: interior / low boundary / high boundary launches
+   bool overlap = true;
    bool ready = false;
    long long halo_bytes = 0, collectives = 0;
 };
@@ -48,6 +54,9 @@ void amgb_dist_teardown(amgb_ctx *c)
 #ifdef AMG_HAVE_NCCL
       if (c->dist->comm) ncclCommDestroy(c->dist->comm);
 #endif
+      if (c->dist->comm_stream) cudaStreamDestroy(c->dist->comm_stream);
+      if (c->dist->ev_x) cudaEventDestroy(c->dist->ev_x);
+      if (c->dist->ev_h) cudaEventDestroy(c->dist->ev_h);
       delete c->dist;
       c->dist = nullptr;
    }
@@ -58,6 +67,19 @@ int amgb_dist_diag_offset(const amgb_ctx *c, int level)
    if (!c->dist || level >= (int)c->dist->lv.size() || !c->dist->lv[level].set) return 0;
    return c->dist->lv[level].off();
 }
+bool amgb_dist_owned_cols(const amgb_ctx *c, int kind, int level, int *c0, int *c1)
+{
+   if (!c->dist) return false;
+   const int in = kind == AMGB_MAT_P ? level + 1 : level;      // level of the matrix's input vector
+   if (in >= (int)c->dist->lv.size() || !c->dist->lv[in].set || !c->dist->lv[in].distributed) return false;
+   // the rows must be partitioned too (a replicated matrix has nothing to overlap)
+   const int out = kind == AMGB_MAT_R ? level + 1 : level;
+   if (kind != AMGB_MAT_R && !c->dist->lv[out].distributed) return false;
+   *c0 = c->dist->lv[in].halo_lo;
+   *c1 = c->dist->lv[in].halo_lo + c->dist->lv[in].n_owned;
+   return true;
+}
+
 bool amgb_dist_level_distributed(const amgb_ctx *c, int level)
 {
    return c->dist && level < (int)c->dist->lv.size() && c->dist->lv[level].set && c->dist->lv[level].distributed;
@@ -80,20 +102,21 @@ static inline SpmvEpilogue epi(double alpha, double beta, const double *b, doubl
 }
 
 // ghosts of v (level layout) <- neighbours' boundary entries
-static int halo(amgb_ctx *c, int l, double *v)
+static int halo(amgb_ctx *c, int l, double *v, cudaStream_t st = nullptr)
 {
    DistState *d = c->dist;
    const DistLevel &L = d->lv[l];
    if (!L.distributed) return AMGB_OK;
+   if (!st) st = c->stream;
    double *own = v + L.halo_lo;
    NCCL_OK(c, ncclGroupStart());
    if (d->rank > 0) {
-      if (L.send_lo) NCCL_OK(c, ncclSend(own, (size_t)L.send_lo, ncclDouble, d->rank - 1, d->comm, c->stream));
-      if (L.halo_lo) NCCL_OK(c, ncclRecv(v, (size_t)L.halo_lo, ncclDouble, d->rank - 1, d->comm, c->stream));
+      if (L.send_lo) NCCL_OK(c, ncclSend(own, (size_t)L.send_lo, ncclDouble, d->rank - 1, d->comm, st));
+      if (L.halo_lo) NCCL_OK(c, ncclRecv(v, (size_t)L.halo_lo, ncclDouble, d->rank - 1, d->comm, st));
    }
    if (d->rank < d->nranks - 1) {
-      if (L.send_hi) NCCL_OK(c, ncclSend(own + L.n_owned - L.send_hi, (size_t)L.send_hi, ncclDouble, d->rank + 1, d->comm, c->stream));
-      if (L.halo_hi) NCCL_OK(c, ncclRecv(own + L.n_owned, (size_t)L.halo_hi, ncclDouble, d->rank + 1, d->comm, c->stream));
+      if (L.send_hi) NCCL_OK(c, ncclSend(own + L.n_owned - L.send_hi, (size_t)L.send_hi, ncclDouble, d->rank + 1, d->comm, st));
+      if (L.halo_hi) NCCL_OK(c, ncclRecv(own + L.n_owned, (size_t)L.halo_hi, ncclDouble, d->rank + 1, d->comm, st));
    }
    NCCL_OK(c, ncclGroupEnd());
    d->halo_bytes += 8LL * (L.send_lo + L.send_hi);
@@ -118,13 +141,43 @@ static int allgather_level(amgb_ctx *c, int l, double *v)
    return AMGB_OK;
 }
 
+// y = epilogue(M x) where x (level `lin` layout, owned part final on the main stream) still needs its ghosts:
+// the exchange runs on the communication stream while the launch units that read only owned entries run on
+// the main stream; the boundary units follow once the ghosts have landed.  (The reference overlaps the same
+// way inside hypre's ParCSR matvec: diag block while the comm_pkg exchange is in flight, then the offd block;
+// its own attempt is at src/DMEM_Smooth.cpp:205-214.)
+static int dist_spmv(amgb_ctx *c, const DevCSR &M, bool sval, int lin, double *x, double *y, const SpmvEpilogue &e, bool norm)
+{
+   DistState *d = c->dist;
+   int rc;
+   const bool split = d->overlap && d->lv[lin].distributed && M.uhi > M.ulo;
+   if (!split) {
+      if ((rc = halo(c, lin, x))) return rc;
+      enq_spmv(c, M, sval, x, y, e, norm);
+      return AMGB_OK;
+   }
+   CUDA_OK(c, cudaEventRecord(d->ev_x, c->stream));
+   CUDA_OK(c, cudaStreamWaitEvent(d->comm_stream, d->ev_x, 0));
+   if ((rc = halo(c, lin, x, d->comm_stream))) return rc;
+   CUDA_OK(c, cudaEventRecord(d->ev_h, d->comm_stream));
+   const int nu = spmv_units(M), np = c->npartials;
+   int g0 = 0, g1 = 0, g2 = 0;
+   if (norm) CUDA_OK(c, cudaMemsetAsync(d->partials3, 0, sizeof(double) * 3 * np, c->stream));
+   c->launches += launch_spmv_units(c->cfg, c->stream, M, M.ulo, M.uhi, sval, x, y, e, norm ? d->partials3 : nullptr, &g0);
+   CUDA_OK(c, cudaStreamWaitEvent(c->stream, d->ev_h, 0));
+   c->launches += launch_spmv_units(c->cfg, c->stream, M, 0, M.ulo, sval, x, y, e, norm ? d->partials3 + np : nullptr, &g1);
+   c->launches += launch_spmv_units(c->cfg, c->stream, M, M.uhi, nu, sval, x, y, e, norm ? d->partials3 + 2 * np : nullptr, &g2);
+   if (norm) c->launches += launch_reduce_partials(c->stream, d->partials3, 3 * np, c->d_scalars);
+   (void)g0; (void)g1; (void)g2;
+   return AMGB_OK;
+}
+
 // r_0 = f - A_0 u on the owned rows, d_scalars[0] = global ||r||^2
 static int dist_residual(amgb_ctx *c)
 {
    DistState *d = c->dist;
    int rc;
-   if ((rc = halo(c, 0, d->u))) return rc;
-   enq_spmv(c, c->A[0], false, d->u, d->r[0] + d->lv[0].off(), epi(-1.0, 1.0, d->f), true);
+   if ((rc = dist_spmv(c, c->A[0], false, 0, d->u, d->r[0] + d->lv[0].off(), epi(-1.0, 1.0, d->f), true))) return rc;
    NCCL_OK(c, ncclAllReduce(c->d_scalars, c->d_scalars, 1, ncclDouble, ncclSum, d->comm, c->stream));
    d->collectives++;
    return AMGB_OK;
@@ -140,11 +193,10 @@ static int dist_cycle(amgb_ctx *c)
    int rc;
    if (L == 1) return AMGB_OK;
    for (int l = 0; l < L - 2; l++) {
-      if ((rc = halo(c, l, d->r[l]))) return rc;
       const DistLevel &nx = d->lv[l + 1];
       const bool gather = d->lv[l].distributed && !nx.distributed;
       double *out = d->r[l + 1] + (gather ? nx.row_start : nx.off());
-      enq_spmv(c, c->R[l], false, d->r[l], out, epi(1.0, 0.0, nullptr), false);
+      if ((rc = dist_spmv(c, c->R[l], false, l, d->r[l], out, epi(1.0, 0.0, nullptr), false))) return rc;
       if (gather && (rc = allgather_level(c, l + 1, d->r[l + 1]))) return rc;
    }
    if ((rc = halo(c, L - 2, d->r[L - 2]))) return rc;
@@ -158,14 +210,12 @@ static int dist_cycle(amgb_ctx *c)
          c->launches += launch_scale(c->cfg, c->stream, c->A[l].nrows, ws, rown, d->e[l] + lv.off());
    }
    for (int l = L - 3; l >= 1; l--) {
-      if ((rc = halo(c, l + 1, d->e[l + 1]))) return rc;
       double *eo = d->e[l] + d->lv[l].off();
-      enq_spmv(c, c->P[l], false, d->e[l + 1], eo, epi(1.0, 1.0, eo), false);
+      if ((rc = dist_spmv(c, c->P[l], false, l + 1, d->e[l + 1], eo, epi(1.0, 1.0, eo), false))) return rc;
    }
    double *uo = d->u + d->lv[0].off();
    if (L >= 3) {
-      if ((rc = halo(c, 1, d->e[1]))) return rc;
-      enq_spmv(c, c->P[0], false, d->e[1], uo, epi(1.0, 1.0, d->e[0] + d->lv[0].off(), 1.0, uo), false);
+      if ((rc = dist_spmv(c, c->P[0], false, 1, d->e[1], uo, epi(1.0, 1.0, d->e[0] + d->lv[0].off(), 1.0, uo), false))) return rc;
    } else {
       c->launches += launch_add(c->cfg, c->stream, c->A[0].nrows, d->e[0] + d->lv[0].off(), uo);
    }
@@ -280,6 +330,11 @@ int amgb_dist_setup(amgb_ctx *c)
                                            const_cast<double *>(c->A[l].sell_sval));
       }
    }
+   if ((rc = amgb_dev_alloc_bytes(c, (void **)&d->partials3, sizeof(double) * 3 * (size_t)c->npartials, true))) return rc;
+   CUDA_OK(c, cudaStreamCreateWithFlags(&d->comm_stream, cudaStreamNonBlocking));
+   CUDA_OK(c, cudaEventCreateWithFlags(&d->ev_x, cudaEventDisableTiming));
+   CUDA_OK(c, cudaEventCreateWithFlags(&d->ev_h, cudaEventDisableTiming));
+   if (const char *ov = getenv("AMGB_DIST_OVERLAP")) d->overlap = atoi(ov) != 0;
    if ((rc = amgb_dev_alloc_bytes(c, (void **)&d->u, sizeof(double) * (size_t)d->lv[0].n_ext(), true))) return rc;
    if ((rc = amgb_dev_alloc_bytes(c, (void **)&d->f, sizeof(double) * (size_t)std::max(1, c->A[0].nrows), true))) return rc;
    CUDA_OK(c, cudaStreamSynchronize(c->stream));

@@ -215,6 +215,28 @@ int launch_spmv(const LaunchCfg &cfg, cudaStream_t st, const DevCSR &M, bool use
    return 1;
 }
 
+int spmv_units(const DevCSR &M) { return M.sell_slices > 0 ? M.sell_slices : (M.nblk > 0 ? M.nblk : M.nrows); }
+
+// the same product restricted to launch units [u0, u1) (slices / chunks / rows, whichever the storage uses)
+int launch_spmv_units(const LaunchCfg &cfg, cudaStream_t st, const DevCSR &M, int u0, int u1, bool use_sval, const double *x,
+                      double *y, const SpmvEpilogue &e, double *partials, int *grid_out)
+{
+   if (grid_out) *grid_out = 0;
+   if (u1 <= u0) return 0;
+   DevCSR V = M;
+   SpmvEpilogue ev = e;
+   double *yv = y;
+   if (M.sell_slices > 0) { V.sell_off += u0; V.sell_base += u0; V.sell_slices = u1 - u0; }
+   else if (M.nblk > 0) { V.blk += u0; if (V.blkx) V.blkx += u0; V.nblk = u1 - u0; }
+   else {
+      V.rp += u0; V.nrows = u1 - u0; yv += u0;
+      if (ev.b) ev.b += u0;
+      if (ev.c) ev.c += u0;
+      if (ev.rs) ev.rs += u0;
+   }
+   return launch_spmv(cfg, st, V, use_sval, x, yv, ev, partials, grid_out);
+}
+
 int launch_reduce_partials(cudaStream_t st, const double *partials, int n, double *out)
 {
    k_reduce_partials<<<1, 1024, 0, st>>>(partials, n, out);

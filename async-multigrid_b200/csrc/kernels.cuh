@@ -56,7 +56,7 @@ __device__ __forceinline__ double sell_rows_team(const DevCSR &M, const double *
    for (int sl = team_tid >> 5; sl < M.sell_slices; sl += nwarp) {
       const int off = __ldg(M.sell_off + sl);
       const int width = (__ldg(M.sell_off + sl + 1) - off) >> 5;
-      int row = (sl << 5) + lane;
+      int row = ((sl + M.sell_base) << 5) + lane;
       if (M.sell_perm) row = __ldg(M.sell_perm + row);
       const int *__restrict__ cp = M.sell_ci + off + lane;
       const double *__restrict__ vp = va + off + lane;

@@ -26,6 +26,9 @@ static const StreamVariant kStreamVariants[AMGB_NUM_STREAM_VARIANTS] = {
 // `partials` must hold >= grid entries; *grid_out receives the grid used).
 int launch_spmv(const LaunchCfg &cfg, cudaStream_t st, const DevCSR &M, bool use_sval, const double *x, double *y,
                 const SpmvEpilogue &e, double *partials, int *grid_out);
+int spmv_units(const DevCSR &M);
+int launch_spmv_units(const LaunchCfg &cfg, cudaStream_t st, const DevCSR &M, int u0, int u1, bool use_sval, const double *x,
+                      double *y, const SpmvEpilogue &e, double *partials, int *grid_out);
 // out[0] = sum(partials[0..n)); if hist != nullptr: hist[k] = sqrt(out[0]) (and r0 handling on host)
 int launch_reduce_partials(cudaStream_t st, const double *partials, int n, double *out);
 // y = a.*x  (zero-guess Jacobi: u = (w/d).*f, src/SMEM_Smooth.cpp:381-389)

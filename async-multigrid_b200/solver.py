@@ -303,11 +303,12 @@ class DistSolver:
         self._ck(self.L.amgb_set_options(self.ctx, C.byref(o)))
         nl = plan.num_levels
         self._ck(self.L.amgb_set_num_levels(self.ctx, nl))
-        for l in range(nl):
+        for l in range(nl):      # all layouts first: a matrix's interior / boundary split needs its input level's layout
             lay = plan.layouts[l]
             counts = np.ascontiguousarray(plan.all_counts[l], dtype=np.int32)
             self._ck(self.L.amgb_dist_set_level(self.ctx, l, lay.n_global, lay.row_start, lay.n_owned, lay.halo_lo,
                                                 lay.halo_hi, int(lay.distributed), lay.send_lo, lay.send_hi, _ip(counts)))
+        for l in range(nl):
             self._set(MAT_A, l, plan.A[l])
             if l < nl - 1:
                 self._set(MAT_P, l, plan.P[l])

@@ -137,8 +137,8 @@ int amgb_l2_arena_bytes(amgb_ctx *ctx, long long *used, long long *capacity);
  * Replaces DMEM_Add / DMEM_SyncAdd (src/DMEM_Add.cpp:20-178, src/DMEM_Mult.cpp:263-450) for the synchronous
  * Multadd cycle: hypre's ParCSR halo exchange and DMEM_Comm (src/DMEM_Comm.cpp:81-382) become NCCL
  * send/recv between row-neighbours, the residual norm an ncclAllReduce (src/DMEM_Misc.cpp:398-433).
- * Call order: amgb_create, amgb_dist_init, amgb_set_options, amgb_set_num_levels, then per level
- * amgb_dist_set_level followed by that level's amgb_set_matrix calls (LOCAL row blocks whose column
+ * Call order: amgb_create, amgb_dist_init, amgb_set_options, amgb_set_num_levels, amgb_dist_set_level for
+ * EVERY level, then the amgb_set_matrix calls (LOCAL row blocks whose column
  * indices are in the rank's extended numbering [ghost_lo | owned | ghost_hi] on distributed levels, full
  * matrices on replicated levels), amgb_setup, amgb_dist_setup. */
 /* rank 0 obtains a 128-byte NCCL unique id and distributes it (MPI_Bcast / torch.distributed broadcast) */
