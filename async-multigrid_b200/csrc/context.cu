@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include <omp.h>
@@ -461,12 +462,23 @@ int amgb_set_matrix(amgb_ctx *c, int kind, int level, int nrows, int ncols, int 
       } else {
          for (int u = 0; u < nu; u++) uint_[u] = rint[u];
       }
-      int lo = 0, hi = nu;
-      while (lo < nu && !uint_[lo]) lo++;
-      while (hi > lo && !uint_[hi - 1]) hi--;
-      bool contiguous = true;
-      for (int u = lo; u < hi; u++) if (!uint_[u]) { contiguous = false; break; }
-      if (contiguous && hi > lo) { M.ulo = lo; M.uhi = hi; }
+      // the longest run of interior units (near the slab faces interior and boundary units interleave; the units
+      // outside the run simply wait for the exchange)
+      int lo = 0, hi = 0;
+      for (int u = 0; u < nu;) {
+         if (!uint_[u]) { u++; continue; }
+         int v = u;
+         while (v < nu && uint_[v]) v++;
+         if (v - u > hi - lo) { lo = u; hi = v; }
+         u = v;
+      }
+      const bool contiguous = hi > lo;
+      if (contiguous) { M.ulo = lo; M.uhi = hi; }
+      if (getenv("AMGB_DEBUG"))
+         fprintf(stderr, "[amgb] kind %d level %d: %d units (%s), owned cols [%d,%d), interior units [%d,%d) contiguous=%d\n", kind, level, nu,
+                 M.sell_slices > 0 ? (M.sell_perm ? "sell-sigma" : "sell") : (M.nblk > 0 ? "chunks" : "rows"), c0, c1, lo, hi, (int)contiguous);
+   } else if (getenv("AMGB_DEBUG") && c->dist) {
+      fprintf(stderr, "[amgb] kind %d level %d: input vector not partitioned, no split\n", kind, level);
    }
    return AMGB_OK;
 }
