@@ -261,6 +261,10 @@ def cpu_baseline(args, h, b, cycles_to_tol, sample_cycles=None, full=False):
             # SMEM_Solve's loop with ONE added barrier between the cycle's "u += e" and the residual
             # (oracle/ref_driver.cpp ref_solve_sync_det): as shipped, the grouped synchronous cycle races on u
             #  and does not reach 1e-9; cycle, smoothers and SpMV are the reference's object code
+            if not full:
+                # untimed pass first, as the reference's own -warmup run does (src/SMEM_Main.cpp:691-693): the first
+                # touch of the ~20 GB of per-group vectors would otherwise be charged to the sample
+                rs.solve_sync_det(sample, 1e-300)
             t1 = time.perf_counter()
             out = rs.solve_sync_det(sample, TOL if full else 1e-300)
             secs, done, rel = time.perf_counter() - t1, out["cycles"], out["hist"][-1]
