@@ -797,6 +797,44 @@ int amgb_cycle(amgb_ctx *c, const double *r_host, double *c_host)
    return AMGB_OK;
 }
 
+// ---- EigsPower (src/SMEM_Cheby.cpp:410-518) --------------------------------------------------------
+// Extreme eigenvalues of B*A by power iteration on the device, B = one application of the selected cycle
+// from a zero guess.  Start vector all ones, `iters` normalise / apply steps, eig_max = <v, BAv>; a second
+// pass deflated with u <- BAv - eig_max*v gives eig_min.  ChebySetup's mu = (beta+alpha)/(beta-alpha),
+// delta = 2/(beta+alpha) (:48-49) are left to the caller.  Scratch: u_outer, y_outer, cvec.
+int amgb_eigs_power(amgb_ctx *c, int iters, double *eig_min, double *eig_max)
+{
+   NEED_READY(c);
+   if (iters < 1 || !eig_min || !eig_max) return amgb_fail(c, AMGB_EINVAL, "bad arguments");
+   const int n0 = c->A[0].nrows;
+   double *u = c->u_outer, *e = c->y_outer;
+   double lam[2] = {0.0, 0.0};
+   int rc, grid;
+   for (int pass = 0; pass < 2; pass++) {
+      std::vector<double> ones((size_t)n0, 1.0);
+      CUDA_OK(c, cudaMemcpyAsync(u, ones.data(), sizeof(double) * n0, cudaMemcpyHostToDevice, c->stream));
+      CUDA_OK(c, cudaStreamSynchronize(c->stream));
+      for (int it = 1;; it++) {
+         double ss;
+         c->launches += launch_sumsq(c->cfg, c->stream, n0, u, c->partials, &grid);
+         c->launches += launch_reduce_partials(c->stream, c->partials, grid, c->d_scalars);
+         if ((rc = amgb_fetch_scalar(c, &ss))) return rc;
+         c->launches += launch_axpby(c->cfg, c->stream, n0, 1.0 / sqrt(ss), u, 0.0, u, e);        // u /= |u|; e = u
+         enq_spmv(c, c->A[0], false, u, c->r[0], epi(1.0, 0.0, nullptr), false);                   // f = A u
+         enq_cycle(c, u, false);                                                                   // u = B f
+         if (it == iters) break;
+         if (pass == 1) c->launches += launch_axpby(c->cfg, c->stream, n0, -lam[0], e, 1.0, u, nullptr);
+      }
+      c->launches += launch_dot(c->cfg, c->stream, n0, e, u, c->partials, &grid);
+      c->launches += launch_reduce_partials(c->stream, c->partials, grid, c->d_scalars);
+      if ((rc = amgb_fetch_scalar(c, &lam[pass]))) return rc;
+   }
+   *eig_max = lam[0];
+   *eig_min = lam[1];
+   CUDA_OK(c, cudaGetLastError());
+   return AMGB_OK;
+}
+
 // ---- SMEM_Solve, synchronous branch ----------------------------------------------------------------
 int amgb_solve_sync(amgb_ctx *c, double tol, int max_cycles, int cheby_flag, double mu, double delta,
                     double *hist, int *n_cycles, double *solve_seconds)

@@ -79,6 +79,24 @@ __global__ void __launch_bounds__(kBlock) k_sumsq(int n, const double *__restric
    if (threadIdx.x == 0) partials[blockIdx.x] = s;
 }
 
+// y = a*x + b*y (b == 0: y is not read); optional copy of the result into z
+__global__ void __launch_bounds__(kBlock) k_axpby(int n, double a, const double *x, double b, double *y, double *z)
+{
+   for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+      const double v = b == 0.0 ? a * x[i] : a * x[i] + b * y[i];
+      y[i] = v;
+      if (z) z[i] = v;
+   }
+}
+
+__global__ void __launch_bounds__(kBlock) k_dot(int n, const double *__restrict__ x, const double *__restrict__ y, double *partials)
+{
+   double s = 0.0;
+   for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) s += x[i] * y[i];
+   s = block_sum(s);
+   if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+
 __global__ void __launch_bounds__(kBlock) k_hybrid_jgs(DevCSR A, const double *f, double *u, const double *u_prev,
                                                         const double *scale, int B, int zero_guess)
 {
@@ -259,6 +277,20 @@ int launch_cheby(const LaunchCfg &cfg, cudaStream_t st, int n, double omega, dou
                  double *u_outer, double *y_outer, double *u)
 {
    k_cheby<<<grid_for(cfg, n), kBlock, 0, st>>>(n, omega, delta, c, u_outer, y_outer, u);
+   return 1;
+}
+
+int launch_axpby(const LaunchCfg &cfg, cudaStream_t st, int n, double a, const double *x, double b, double *y, double *z)
+{
+   k_axpby<<<grid_for(cfg, n), kBlock, 0, st>>>(n, a, x, b, y, z);
+   return 1;
+}
+
+int launch_dot(const LaunchCfg &cfg, cudaStream_t st, int n, const double *x, const double *y, double *partials, int *grid_out)
+{
+   int grid = grid_for(cfg, n);
+   if (grid_out) *grid_out = grid;
+   k_dot<<<grid, kBlock, 0, st>>>(n, x, y, partials);
    return 1;
 }
 

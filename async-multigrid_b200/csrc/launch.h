@@ -38,6 +38,9 @@ int launch_add(const LaunchCfg &cfg, cudaStream_t st, int n, const double *x, do
 // Chebyshev update (src/SMEM_Solve.cpp:179-187): uo_prev=uo; uo = yo + omega*(delta*c + uo - yo); yo = uo_prev; u = uo
 int launch_cheby(const LaunchCfg &cfg, cudaStream_t st, int n, double omega, double delta, const double *c,
                  double *u_outer, double *y_outer, double *u);
+// y = a*x + b*y [, z = y]; partial sums of x_i*y_i
+int launch_axpby(const LaunchCfg &cfg, cudaStream_t st, int n, double a, const double *x, double b, double *y, double *z);
+int launch_dot(const LaunchCfg &cfg, cudaStream_t st, int n, const double *x, const double *y, double *partials, int *grid_out);
 // partial sums of x_i^2
 int launch_sumsq(const LaunchCfg &cfg, cudaStream_t st, int n, const double *x, double *partials, int *grid_out);
 // hybrid JGS sweep

@@ -23,7 +23,7 @@ ABI_SYMBOLS = [
     "amgb_default_options", "amgb_create", "amgb_destroy", "amgb_last_error", "amgb_launch_count",
     "amgb_set_num_levels", "amgb_set_matrix", "amgb_set_options", "amgb_setup",
     "amgb_set_rhs", "amgb_set_solution", "amgb_get_solution", "amgb_get_residual",
-    "amgb_spgemv", "amgb_smooth", "amgb_norm2", "amgb_cycle", "amgb_solve_sync", "amgb_solve_async",
+    "amgb_spgemv", "amgb_smooth", "amgb_norm2", "amgb_cycle", "amgb_eigs_power", "amgb_solve_sync", "amgb_solve_async",
     "amgb_smem_solve", "amgb_time_residual", "amgb_level_storage", "amgb_time_spmv", "amgb_stream_stats", "amgb_l2_arena_bytes",
     "amgb_dist_unique_id", "amgb_dist_init", "amgb_dist_set_level", "amgb_dist_setup", "amgb_dist_set_rhs",
     "amgb_dist_get_solution", "amgb_dist_solve_sync", "amgb_dist_stats",
@@ -70,6 +70,7 @@ def load_library():
     L.amgb_smooth.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, DP, DP]
     L.amgb_norm2.argtypes = [C.c_void_p, DP, C.c_int, DP]
     L.amgb_cycle.argtypes = [C.c_void_p, DP, DP]
+    L.amgb_eigs_power.argtypes = [C.c_void_p, C.c_int, DP, DP]
     L.amgb_solve_sync.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, DP, IP, DP]
     L.amgb_solve_async.argtypes = [C.c_void_p, C.c_int, C.c_int, IP, DP, DP]
     L.amgb_smem_solve.argtypes = [C.c_void_p, DP, DP, C.c_double, C.c_int, DP, IP, IP, DP, DP]
@@ -173,8 +174,8 @@ class Solver:
             u = np.ascontiguousarray(u, dtype=np.float64)
             self._ck(self.L.amgb_set_solution(self.ctx, _dp(u)))
 
-    def get_solution(self):
-        u = np.empty(self.n0)
+    def get_solution(self, out=None):
+        u = np.empty(self.n0) if out is None else out
         self._ck(self.L.amgb_get_solution(self.ctx, _dp(u)))
         return u
 
@@ -206,6 +207,13 @@ class Solver:
         c = np.empty(self.n0)
         self._ck(self.L.amgb_cycle(self.ctx, _dp(r), _dp(c)))
         return c
+
+    def ChebySetup(self, iters=20):
+        """EigsPower + ChebySetup (src/SMEM_Cheby.cpp:28-60,410-518): returns (mu, delta, alpha, beta)"""
+        a, b = C.c_double(0), C.c_double(0)
+        self._ck(self.L.amgb_eigs_power(self.ctx, iters, C.byref(a), C.byref(b)))
+        alpha, beta = a.value, b.value
+        return (beta + alpha) / (beta - alpha), 2.0 / (beta + alpha), alpha, beta
 
     def solve_sync(self, tol=1e-9, max_cycles=100, cheby=None):
         """resident f,u -> (relres history, seconds)"""

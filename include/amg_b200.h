@@ -107,6 +107,11 @@ int amgb_cycle(amgb_ctx *ctx, const double *r_host, double *c_host);
 int amgb_solve_sync(amgb_ctx *ctx, double tol, int max_cycles, int cheby_flag, double mu, double delta,
                     double *relres_hist, int *n_cycles, double *solve_seconds);
 
+/* EigsPower (src/SMEM_Cheby.cpp:410-518): extreme eigenvalues of B*A by `iters` steps of power iteration (second,
+ * deflated pass for the minimum), B = the selected cycle from a zero guess.  ChebySetup then takes
+ * mu = (max+min)/(max-min), delta = 2/(max+min) (src/SMEM_Cheby.cpp:48-49) -> amgb_solve_sync(cheby_flag = 1). */
+int amgb_eigs_power(amgb_ctx *ctx, int iters, double *eig_min, double *eig_max);
+
 /* SMEM_Async_Add_AMG (src/SMEM_Async_AMG.cpp:7-437) as ONE persistent cooperative kernel: each
  * level's correction chain owns a CTA group; groups share u through fp64 global atomics, no grid
  * barrier.  Stop rule: LOCAL = every group stops after num_cycles own corrections; GLOBAL = all

@@ -449,5 +449,35 @@ int orc_solve_async_sequential(const orc_problem *pb, const double *f, double *u
    return 0;
 }
 
+/* EigsPower (src/SMEM_Cheby.cpp:410-518): extreme eigenvalues of B*A by power iteration, B = one application of
+ * the selected cycle from a zero guess (the reference hard-wires its hypre-vector BPXCycle for every solver other
+ * than MULT; here B is the cycle `pb` names, identical for BPX).  Start vector all ones; `iters` normalise /
+ * apply steps; eig_max = <v, BAv>; second pass deflated with u <- BAv - eig_max v; eig_min = <v, BAv>. */
+void orc_eigs_power(const orc_problem *pb, int iters, double *eig_min, double *eig_max)
+{
+   const int n = pb->A[0].nrows;
+   double *u = (double *)malloc(sizeof(double) * n), *e = (double *)malloc(sizeof(double) * n);
+   double *f = (double *)malloc(sizeof(double) * n);
+   double lam[2] = {0.0, 0.0};
+   for (int pass = 0; pass < 2; pass++) {
+      for (int i = 0; i < n; i++) u[i] = 1.0;
+      for (int it = 1;; it++) {
+         const double nu = orc_norm2(u, n);
+         for (int i = 0; i < n; i++) { u[i] /= nu; e[i] = u[i]; }
+         orc_matvec(&pb->A[0], u, f, 0, n);
+         orc_cycle(pb, f, u);
+         if (it == iters) break;
+         if (pass == 1)
+            for (int i = 0; i < n; i++) u[i] -= lam[0] * e[i];
+      }
+      double d = 0.0;
+      for (int i = 0; i < n; i++) d += e[i] * u[i];
+      lam[pass] = d;
+   }
+   *eig_max = lam[0];
+   *eig_min = lam[1];
+   free(u); free(e); free(f);
+}
+
 int orc_max_threads(void) { return omp_get_max_threads(); }
 void orc_set_threads(int t) { omp_set_num_threads(t); }

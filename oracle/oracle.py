@@ -58,6 +58,8 @@ def lib():
         L.orc_symmetric_jacobi.argtypes = [C.POINTER(OrcCSR), DP, DP, DP, DP, C.c_double, C.c_int, C.c_int]
         L.orc_symmetric_l1_jacobi.argtypes = [C.POINTER(OrcCSR), DP, DP, DP, DP, DP, C.c_int, C.c_int]
         L.orc_solve_async_sequential.argtypes = [C.POINTER(OrcProblem), DP, DP, C.c_int, IP, DP]
+        L.orc_eigs_power.argtypes = [C.POINTER(OrcProblem), C.c_int, DP, DP]
+        L.orc_eigs_power.restype = None
         _lib = L
     return _lib
 
@@ -120,6 +122,12 @@ class Problem:
         u = np.zeros(self.h.n[0])
         lib().orc_cycle(C.byref(self.c), dptr(np.ascontiguousarray(r)), dptr(u))
         return u
+
+    def eigs_power(self, iters=20):
+        """(alpha, beta) = (eig_min, eig_max) of B*A as EigsPower estimates them"""
+        a, b = C.c_double(0), C.c_double(0)
+        lib().orc_eigs_power(C.byref(self.c), iters, C.byref(a), C.byref(b))
+        return a.value, b.value
 
     def solve_async_sequential(self, f, num_cycles):
         u = np.zeros(self.h.n[0])

@@ -271,6 +271,24 @@ def test_chebyshev_accelerated_bpx_matches_oracle():
     s.close()
 
 
+@pytest.mark.parametrize("solver,w", [(H.BPX, 0.8), (H.MULTADD, 0.9)])
+def test_chebysetup_power_iteration_matches_oracle(solver, w):
+    """EigsPower on the device (amgb_eigs_power) vs its restatement, then the accelerated solve with those bounds"""
+    h, b = _problem("7pt", 20, solver, w)
+    pb = O.Problem(h, solver, H.JACOBI, w)
+    alpha, beta = pb.eigs_power(20)
+    s = amg.Solver(h, solver, H.JACOBI, w)
+    s.set_rhs(b)
+    mu, delta, a2, b2 = s.ChebySetup(20)
+    assert abs(a2 - alpha) <= 1e-9 * abs(alpha) and abs(b2 - beta) <= 1e-9 * abs(beta), (a2, alpha, b2, beta)
+    _, want, _ = pb.solve_sync(b, 1e-9, 200, cheby=((beta + alpha) / (beta - alpha), 2.0 / (beta + alpha)))
+    s.set_solution(None)
+    got, _ = s.solve_sync(1e-9, 200, cheby=(mu, delta))
+    assert len(got) == len(want) and got[-1] < 1e-9
+    assert np.max(np.abs(got - want)) <= HIST_TOL
+    s.close()
+
+
 # ---- asynchronous solves --------------------------------------------------------------------------------
 @pytest.mark.parametrize("solver,smoother,w,cycles,post", [
     (H.ASYNC_MULTADD, H.JACOBI, 0.9, 80, 1),
