@@ -465,6 +465,7 @@ void orc_eigs_power(const orc_problem *pb, int iters, double *eig_min, double *e
          const double nu = orc_norm2(u, n);
          for (int i = 0; i < n; i++) { u[i] /= nu; e[i] = u[i]; }
          orc_matvec(&pb->A[0], u, f, 0, n);
+         memset(u, 0, sizeof(double) * (size_t)n);      /* hypre_ParVectorSetConstantValues(u, 0.0), :452 */
          orc_cycle(pb, f, u);
          if (it == iters) break;
          if (pass == 1)
