@@ -708,6 +708,49 @@ void enq_cycle(amgb_ctx *c, double *target, bool accumulate)
    }
 }
 
+// `sweeps` general (L1-)Jacobi sweeps u <- u + rs o (f - A u) in place (ping-pong through `scratch`)
+static void enq_jacobi_sweeps(amgb_ctx *c, int l, const double *f, double *u, int sweeps, double *scratch)
+{
+   const DevCSR &A = c->A[l];
+   const double *rs = (c->opt.smoother == AMGB_SMOOTH_L1_JACOBI) ? c->inv_l1[l] : c->ws[l];
+   double *cur = u, *oth = scratch;
+   for (int k = 0; k < sweeps; k++) {
+      enq_spmv(c, A, false, cur, oth, epi(-1.0, 1.0, f, 1.0, cur, rs), false);
+      std::swap(cur, oth);
+   }
+   if (cur != u) cudaMemcpyAsync(u, cur, sizeof(double) * A.nrows, cudaMemcpyDeviceToDevice, c->stream);
+}
+
+// One multiplicative V-cycle on (f, u) of level 0 -- SMEM_Sync_Parfor_Vcycle, src/SMEM_Sync_AMG.cpp:8-145 (the
+// reference's comparator for the additive cycles).  Level right-hand sides live in r[l], level
+// solutions in e[l] (l >= 1).  As in the reference the first sweep on levels 1..L-2 starts from zero
+// (zero_flags = 1 on the way down), and the coarsest level's num_pre + num_post sweeps continue from the
+// value the previous cycle left there (its zero flag is never raised; e[L-1] is cleared at the start of a solve).
+void enq_vcycle(amgb_ctx *c)
+{
+   const int L = c->L;
+   const amgb_options &o = c->opt;
+   for (int l = 0; l < L - 1; l++) {
+      const double *fl = l == 0 ? c->f : c->r[l];
+      double *ul = l == 0 ? c->u : c->e[l];
+      if (l == 0) enq_jacobi_sweeps(c, 0, fl, ul, o.num_pre_smooth_sweeps, c->t[0]);
+      else enq_smooth_zero(c, l, fl, ul, o.num_pre_smooth_sweeps, false, true, c->t[l], c->w[l]);
+      enq_spmv(c, c->A[l], false, ul, c->w[l], epi(-1.0, 1.0, fl), false);                 // r_fine = f - A u
+      enq_spmv(c, c->R[l], false, c->w[l], c->r[l + 1], epi(1.0, 0.0, nullptr), false);    // f_{l+1} = R r_fine
+   }
+   {
+      const int cl = L - 1;
+      enq_jacobi_sweeps(c, cl, cl == 0 ? c->f : c->r[cl], cl == 0 ? c->u : c->e[cl],
+                        o.num_pre_smooth_sweeps + o.num_post_smooth_sweeps, c->t[cl]);
+   }
+   for (int l = L - 2; l >= 0; l--) {
+      const double *fl = l == 0 ? c->f : c->r[l];
+      double *ul = l == 0 ? c->u : c->e[l];
+      enq_spmv(c, c->P[l], false, c->e[l + 1], ul, epi(1.0, 1.0, ul), false);              // u += P u_c
+      enq_jacobi_sweeps(c, l, fl, ul, o.num_post_smooth_sweeps, c->t[l]);
+   }
+}
+
 int amgb_fetch_scalar(amgb_ctx *c, double *out)
 {
    CUDA_OK(c, cudaMemcpyAsync(c->h_scalars, c->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -843,6 +886,11 @@ int amgb_solve_sync(amgb_ctx *c, double tol, int max_cycles, int cheby_flag, dou
    if (max_cycles < 0) return amgb_fail(c, AMGB_EINVAL, "max_cycles < 0");
    const int n0 = c->A[0].nrows;
    int rc;
+   if (c->opt.solver == AMGB_SOLVER_MULT) {
+      if (cheby_flag) return amgb_fail(c, AMGB_EINVAL, "Chebyshev acceleration is wired for the additive cycles");
+      if (c->opt.smoother == AMGB_SMOOTH_HYBRID_JGS) return amgb_fail(c, AMGB_EINVAL, "MULT runs with (L1-)Jacobi smoothing");
+      CUDA_OK(c, cudaMemsetAsync(c->e[c->L - 1], 0, sizeof(double) * c->A[c->L - 1].nrows, c->stream));   // InitVectors
+   }
    // r0 (src/SMEM_Solve.cpp:60-70)
    enq_residual(c);
    double ss;
@@ -864,7 +912,8 @@ int amgb_solve_sync(amgb_ctx *c, double tol, int max_cycles, int cheby_flag, dou
          cudaGraph_t g;
          long long before = c->launches;
          CUDA_OK(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-         enq_cycle(c, c->u, true);
+         if (c->opt.solver == AMGB_SOLVER_MULT) enq_vcycle(c);
+         else enq_cycle(c, c->u, true);
          enq_residual(c);
          cudaMemcpyAsync(c->h_scalars, c->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, c->stream);
          CUDA_OK(c, cudaStreamEndCapture(c->stream, &g));

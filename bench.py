@@ -97,7 +97,7 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max(power)}
 
 
-SOLVERS = {"multadd": 2, "afacx": 1, "bpx": 3, "async_multadd": 6, "async_afacx": 5}
+SOLVERS = {"mult": 0, "multadd": 2, "afacx": 1, "bpx": 3, "async_multadd": 6, "async_afacx": 5}
 SMOOTHERS = {"j": 0, "hybrid_jgs": 2, "L1j": 6}
 
 

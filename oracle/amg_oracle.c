@@ -36,6 +36,7 @@ typedef struct {
 #define ORC_JACOBI 0
 #define ORC_HYBRID_JGS 2
 #define ORC_L1_JACOBI 6
+#define ORC_MULT 0
 #define ORC_AFACX 1
 #define ORC_MULTADD 2
 #define ORC_BPX 3
@@ -358,6 +359,40 @@ static void orc_bpx_cycle(const orc_problem *pb, orc_work *w, double *u)
 
 /* One application of the selected cycle to residual r (length n0): u += B r.  Exposed for
  * per-cycle parity tests. */
+/* Multiplicative V-cycle: SMEM_Sync_Parfor_Vcycle, src/SMEM_Sync_AMG.cpp:8-145 (non-preconditioner form).
+ * u is level 0's solution (in/out), f its right-hand side.  w->e[l] (l >= 1) are the level solutions, w->r[l]
+ * (l >= 1) the level right-hand sides.  Quirks mirrored: zero_flags is 1 on levels 1..L-2 on the way down (the
+ * first sweep overwrites u_l), 0 on level 0 and on the way up; the coarsest level's zero flag is never raised, so its
+ * num_pre + num_post sweeps start from whatever the previous cycle left in u_{L-1} (0 on the first cycle). */
+static void orc_mult_vcycle(const orc_problem *pb, orc_work *w, const double *f, double *u)
+{
+   const int L = pb->num_levels;
+   const double om = pb->smooth_weight;
+   for (int l = 0; l < L - 1; l++) {
+      const double *fl = l == 0 ? f : w->r[l];
+      double *ul = l == 0 ? u : w->e[l];
+      if (pb->smoother == ORC_L1_JACOBI) orc_l1_jacobi(&pb->A[l], fl, ul, w->y[l], pb->l1[l], pb->num_pre, l > 0);
+      else orc_jacobi(&pb->A[l], fl, ul, w->y[l], om, pb->num_pre, l > 0);
+      orc_residual(&pb->A[l], fl, ul, w->rf[l]);
+      orc_matvec(&pb->R[l], w->rf[l], w->r[l + 1], 0, pb->R[l].nrows);
+   }
+   {
+      const int c = L - 1;
+      const double *fc = c == 0 ? f : w->r[c];
+      double *ucs = c == 0 ? u : w->e[c];
+      if (pb->smoother == ORC_L1_JACOBI) orc_l1_jacobi(&pb->A[c], fc, ucs, w->y[c], pb->l1[c], pb->num_pre + pb->num_post, 0);
+      else orc_jacobi(&pb->A[c], fc, ucs, w->y[c], om, pb->num_pre + pb->num_post, 0);
+   }
+   for (int l = L - 2; l >= 0; l--) {
+      const double *fl = l == 0 ? f : w->r[l];
+      double *ul = l == 0 ? u : w->e[l];
+      orc_spgemv(&pb->P[l], w->e[l + 1], ul, 1.0, 1.0, w->s[l]);
+      memcpy(ul, w->s[l], sizeof(double) * (size_t)pb->A[l].nrows);
+      if (pb->smoother == ORC_L1_JACOBI) orc_l1_jacobi(&pb->A[l], fl, ul, w->y[l], pb->l1[l], pb->num_post, 0);
+      else orc_jacobi(&pb->A[l], fl, ul, w->y[l], om, pb->num_post, 0);
+   }
+}
+
 void orc_cycle(const orc_problem *pb, const double *r, double *u)
 {
    orc_work *w = work_alloc(pb);
@@ -405,7 +440,8 @@ int orc_solve_sync(const orc_problem *pb, const double *f, double *u, double tol
          }
          omega = 1.0 / (1.0 - omega / mu24);
       } else {
-         if (pb->solver == ORC_BPX) orc_bpx_cycle(pb, w, u);
+         if (pb->solver == ORC_MULT) orc_mult_vcycle(pb, w, f, u);
+         else if (pb->solver == ORC_BPX) orc_bpx_cycle(pb, w, u);
          else orc_add_vcycle(pb, w, u, NULL);
       }
       orc_residual(&pb->A[0], f, u, r);

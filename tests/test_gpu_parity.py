@@ -255,6 +255,29 @@ def test_sync_history_matches_oracle(prob, n, solver, smoother, w, post):
     s.close()
 
 
+@pytest.mark.parametrize("prob,n,smoother,pre,post", [("7pt", 20, H.JACOBI, 1, 1), ("5pt", 64, H.JACOBI, 2, 1),
+                                                      ("7pt", 16, H.L1_JACOBI, 1, 1)])
+def test_multiplicative_vcycle_matches_oracle(prob, n, smoother, pre, post):
+    """MULT (SMEM_Sync_Parfor_Vcycle), the comparator of the additive cycles.  The oracle restates
+    src/SMEM_Sync_AMG.cpp:8-145; the reference's own MULT path does not run under the stub driver (it needs hypre's
+    solver object), so this row is pinned by the restatement plus the properties below."""
+    w = 0.8
+    h, b = _problem(prob, n, H.MULT, w)
+    _, want, _ = O.Problem(h, H.MULT, smoother, w, num_pre=pre, num_post=post).solve_sync(b, 1e-9, 100)
+    s = amg.Solver(h, H.MULT, smoother, w, num_pre=pre, num_post=post)
+    out = s.SMEM_Solve(b, 1e-9, 100)
+    _check_hist(out["hist"], want)
+    assert out["hist"][-1] < 1e-9
+    # consistency: with f = A x* and x0 = x* the cycle must leave x* (nearly) untouched -- the coarse corrections vanish
+    xs = np.sin(np.arange(h.n[0]) * 0.3)
+    fs = O.spgemv(h.A[0], xs, None, 1.0, 0.0)
+    s.set_rhs(fs)
+    s.set_solution(xs)
+    hist, _ = s.solve_sync(1e-30, 1)
+    assert _rel(s.get_solution(), xs) <= 1e-13
+    s.close()
+
+
 def test_chebyshev_accelerated_bpx_matches_oracle():
     h, b = _problem("7pt", 20, H.BPX, 0.8)
     # eigenvalue bounds of the BPX-preconditioned operator are an INPUT (ChebySetup is host-side)
