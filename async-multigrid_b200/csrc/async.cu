@@ -344,6 +344,7 @@ extern "C" int amgb_solve_async(amgb_ctx *c, int num_cycles, int converge_type, 
 {
    NEED_READY(c);
    if (num_cycles < 1) return amgb_fail(c, AMGB_EINVAL, "num_cycles < 1");
+   if (c->opt.coarse_solve) return amgb_fail(c, AMGB_EINVAL, "coarse_solve (DMEM convention) is implemented for the synchronous cycles");
    int rc;
    if ((rc = async_prepare(c))) return rc;
    AsyncParams &hp = *c->async_host;

@@ -91,6 +91,7 @@ void amgb_default_options(amgb_options *o)
    o->use_sell = 1;
    o->l2_persist = 1;
    o->use_stream = 1;
+   o->coarse_solve = 0;
    o->stream_variant = 8;
    o->sell_sigma = 128;
 }
@@ -438,6 +439,46 @@ int amgb_set_matrix(amgb_ctx *c, int kind, int level, int nrows, int ncols, int 
    if (c->opt.use_stream && M.sell_slices == 0 && nrows > 0 && !(long_rows && kStreamVariants[c->opt.stream_variant].stages <= 0)) {
       if ((rc = build_stream_blocks(c, M, nrows, ncols, rp, ci, va))) return rc;
    }
+   // DMEM convention: dense inverse of the coarsest operator (hypre_GaussElimSetup, src/DMEM_Setup.cpp:385-388),
+   // applied later as one full SpMV
+   if (kind == AMGB_MAT_A && level == c->L - 1 && c->opt.coarse_solve && c->L > 1) {
+      const int n = nrows;
+      if (n > 2048) return amgb_fail(c, AMGB_EINVAL, "coarsest level has %d rows: too large for the dense direct solve", n);
+      std::vector<double> Mx((size_t)n * 2 * n, 0.0);         // [A | I]
+      for (int i = 0; i < n; i++) {
+         for (int p = rp[i]; p < rp[i + 1]; p++) Mx[(size_t)i * 2 * n + ci[p]] += va[p];
+         Mx[(size_t)i * 2 * n + n + i] = 1.0;
+      }
+      for (int k = 0; k < n; k++) {                            // Gauss-Jordan, partial pivoting
+         int piv = k;
+         for (int i = k + 1; i < n; i++)
+            if (fabs(Mx[(size_t)i * 2 * n + k]) > fabs(Mx[(size_t)piv * 2 * n + k])) piv = i;
+         if (Mx[(size_t)piv * 2 * n + k] == 0.0) return amgb_fail(c, AMGB_EINVAL, "coarsest operator is singular");
+         if (piv != k)
+            for (int j = 0; j < 2 * n; j++) std::swap(Mx[(size_t)k * 2 * n + j], Mx[(size_t)piv * 2 * n + j]);
+         const double d = 1.0 / Mx[(size_t)k * 2 * n + k];
+         for (int j = 0; j < 2 * n; j++) Mx[(size_t)k * 2 * n + j] *= d;
+         for (int i = 0; i < n; i++) {
+            if (i == k) continue;
+            const double fct = Mx[(size_t)i * 2 * n + k];
+            if (fct != 0.0)
+               for (int j = 0; j < 2 * n; j++) Mx[(size_t)i * 2 * n + j] -= fct * Mx[(size_t)k * 2 * n + j];
+         }
+      }
+      std::vector<int> irp((size_t)n + 1), ici((size_t)n * n);
+      std::vector<double> iva((size_t)n * n);
+      for (int i = 0; i <= n; i++) irp[i] = i * n;
+      for (int i = 0; i < n; i++)
+         for (int j = 0; j < n; j++) { ici[(size_t)i * n + j] = j; iva[(size_t)i * n + j] = Mx[(size_t)i * 2 * n + n + j]; }
+      int *d_irp, *d_ici; double *d_iva;
+      if ((rc = dev_upload(c, &d_irp, irp.data(), irp.size()))) return rc;
+      if ((rc = dev_upload(c, &d_ici, ici.data(), ici.size()))) return rc;
+      if ((rc = dev_upload(c, &d_iva, iva.data(), iva.size()))) return rc;
+      CUDA_OK(c, cudaStreamSynchronize(c->stream));
+      c->Ainv = DevCSR();
+      c->Ainv.nrows = n; c->Ainv.ncols = n; c->Ainv.nnz = n * n;
+      c->Ainv.rp = d_irp; c->Ainv.ci = d_ici; c->Ainv.va = d_iva; c->Ainv.lpr = 32;
+   }
    // multi-GPU: which launch units touch only owned entries of the input vector (see DevCSR::ulo/uhi)
    int c0 = 0, c1 = 0;
    if (amgb_dist_owned_cols(c, kind, level, &c0, &c1) && nrows > 0) {
@@ -678,12 +719,14 @@ void enq_cycle(amgb_ctx *c, double *target, bool accumulate)
    }
    // restriction chain, shared by all levels (the reference repeats it per level group,
    // src/SMEM_Sync_AMG.cpp:475-490; the result is identical)
-   const int last_r = multadd ? L - 2 : L - 1;   // Multadd never reads r_{L-1} (coarsest contributes 0)
+   const bool direct = o.coarse_solve && c->Ainv.rp != nullptr;   // DMEM convention: e_{L-1} = A_{L-1}^{-1} r_{L-1}
+   const int last_r = (multadd && !direct) ? L - 2 : L - 1;   // SMEM Multadd never reads r_{L-1} (coarsest contributes 0)
    for (int l = 0; l < last_r; l++) enq_spmv(c, c->R[l], false, c->r[l], c->r[l + 1], epi(1.0, 0.0, nullptr), false);
    // per-level corrections e_l (levels are independent)
-   const int top = bpx ? L : L - 1;              // BPX also smooths the coarsest level (:217-236)
+   const int top = (bpx || direct) ? L : L - 1;  // BPX also smooths the coarsest level (:217-236)
    for (int l = 0; l < top; l++) {
-      if (multadd) enq_smooth_zero(c, l, c->r[l], c->e[l], o.num_fine_smooth_sweeps, c->symmetric, false, c->t[l], c->w[l]);
+      if (direct && l == L - 1) enq_spmv(c, c->Ainv, false, c->r[l], c->e[l], epi(1.0, 0.0, nullptr), false);
+      else if (multadd) enq_smooth_zero(c, l, c->r[l], c->e[l], o.num_fine_smooth_sweeps, c->symmetric, false, c->t[l], c->w[l]);
       else if (bpx) enq_smooth_zero(c, l, c->r[l], c->e[l], o.num_pre_smooth_sweeps, false, true, c->t[l], c->w[l]);
       else if (afacx) {
          // src/SEQ_AMG.cpp:172-208: u_c = S_{l+1} r_{l+1}; e = P u_c; r_f = r_l - A_l e; u_f = S_l r_f

@@ -17,6 +17,7 @@ struct amgb_ctx {
    bool ready = false;
    bool symmetric = false;
    std::vector<DevCSR> A, P, R;
+   DevCSR Ainv;                     // dense inverse of the coarsest operator (coarse_solve), stored as a full CSR
    std::vector<int> hA;
    std::map<const DevCSR *, long> sell_entries;
    std::vector<int> last_perm;      // host copies of the last built SELL permutation / block list (unit classification)

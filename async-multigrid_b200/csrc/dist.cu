@@ -192,14 +192,17 @@ static int dist_cycle(amgb_ctx *c)
    const int L = c->L;
    int rc;
    if (L == 1) return AMGB_OK;
-   for (int l = 0; l < L - 2; l++) {
+   const bool direct = c->opt.coarse_solve && c->Ainv.rp != nullptr;   // DMEM: direct solve on the (replicated) coarsest level
+   const int top = direct ? L : L - 1;                                  // levels that contribute a correction
+   for (int l = 0; l < top - 1; l++) {
       const DistLevel &nx = d->lv[l + 1];
       const bool gather = d->lv[l].distributed && !nx.distributed;
       double *out = d->r[l + 1] + (gather ? nx.row_start : nx.off());
       if ((rc = dist_spmv(c, c->R[l], false, l, d->r[l], out, epi(1.0, 0.0, nullptr), false))) return rc;
       if (gather && (rc = allgather_level(c, l + 1, d->r[l + 1]))) return rc;
    }
-   if ((rc = halo(c, L - 2, d->r[L - 2]))) return rc;
+   if (!direct && (rc = halo(c, L - 2, d->r[L - 2]))) return rc;
+   if (direct) enq_spmv(c, c->Ainv, false, d->r[L - 1], d->e[L - 1], epi(1.0, 0.0, nullptr), false);
    for (int l = 0; l < L - 1; l++) {
       const DistLevel &lv = d->lv[l];
       const double *rown = d->r[l] + lv.off();
@@ -209,12 +212,12 @@ static int dist_cycle(amgb_ctx *c)
       else
          c->launches += launch_scale(c->cfg, c->stream, c->A[l].nrows, ws, rown, d->e[l] + lv.off());
    }
-   for (int l = L - 3; l >= 1; l--) {
+   for (int l = top - 2; l >= 1; l--) {
       double *eo = d->e[l] + d->lv[l].off();
       if ((rc = dist_spmv(c, c->P[l], false, l + 1, d->e[l + 1], eo, epi(1.0, 1.0, eo), false))) return rc;
    }
    double *uo = d->u + d->lv[0].off();
-   if (L >= 3) {
+   if (top >= 2) {
       if ((rc = dist_spmv(c, c->P[0], false, 1, d->e[1], uo, epi(1.0, 1.0, d->e[0] + d->lv[0].off(), 1.0, uo), false))) return rc;
    } else {
       c->launches += launch_add(c->cfg, c->stream, c->A[0].nrows, d->e[0] + d->lv[0].off(), uo);

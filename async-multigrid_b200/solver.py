@@ -35,7 +35,7 @@ class Options(C.Structure):
                 ("num_pre_smooth_sweeps", C.c_int), ("num_post_smooth_sweeps", C.c_int),
                 ("num_fine_smooth_sweeps", C.c_int), ("num_coarse_smooth_sweeps", C.c_int),
                 ("jgs_block_rows", C.c_int), ("use_sell", C.c_int), ("l2_persist", C.c_int), ("use_stream", C.c_int),
-                ("sell_sigma", C.c_int), ("stream_variant", C.c_int)]
+                ("coarse_solve", C.c_int), ("sell_sigma", C.c_int), ("stream_variant", C.c_int)]
 
 
 _lib = None
@@ -110,7 +110,7 @@ class Solver:
 
     def __init__(self, h, solver=H.MULTADD, smoother=H.JACOBI, smooth_weight=1.0, num_pre=1, num_post=1,
                  fine_sweeps=1, coarse_sweeps=1, jgs_block_rows=8, use_sell=True, l2_persist=True, use_stream=True,
-                 stream_variant=None, sell_sigma=None, device=0):
+                 stream_variant=None, sell_sigma=None, coarse_solve=False, device=0):
         self.L = load_library()
         self.h = h
         self.ctx = C.c_void_p()
@@ -124,6 +124,7 @@ class Solver:
         o.num_fine_smooth_sweeps, o.num_coarse_smooth_sweeps = fine_sweeps, coarse_sweeps
         o.jgs_block_rows, o.use_sell, o.l2_persist = jgs_block_rows, int(use_sell), int(l2_persist)
         o.use_stream = int(use_stream)
+        o.coarse_solve = int(coarse_solve)
         if stream_variant is not None:
             o.stream_variant = int(stream_variant)
         elif "AMGB_STREAM_VARIANT" in os.environ:
@@ -295,7 +296,8 @@ class DistSolver:
     """One rank of the row-partitioned synchronous Multadd solve (DMEM_Add replacement).  `plan` is a
     partition.RankPlan; `uid` the 128-byte id from dist_unique_id() of rank 0."""
 
-    def __init__(self, plan, uid, smooth_weight=1.0, num_pre=1, num_post=1, use_sell=True, use_stream=True, device=0):
+    def __init__(self, plan, uid, smooth_weight=1.0, num_pre=1, num_post=1, use_sell=True, use_stream=True,
+                 coarse_solve=False, device=0):
         self.L = load_library()
         self.plan = plan
         self.ctx = C.c_void_p()
@@ -308,6 +310,7 @@ class DistSolver:
         o.solver, o.smoother, o.smooth_weight = H.MULTADD, H.JACOBI, smooth_weight
         o.num_pre_smooth_sweeps, o.num_post_smooth_sweeps = num_pre, num_post
         o.use_sell, o.use_stream = int(use_sell), int(use_stream)
+        o.coarse_solve = int(coarse_solve)
         self._ck(self.L.amgb_set_options(self.ctx, C.byref(o)))
         nl = plan.num_levels
         self._ck(self.L.amgb_set_num_levels(self.ctx, nl))

@@ -52,6 +52,9 @@ typedef struct {
    int l2_persist;              /* 1: pin the coarse hierarchy in L2 with an access-policy window */
    int use_stream;              /* 1: CSR-stream kernel (row blocks staged through shared memory with 128-bit
                                    loads) for every matrix not stored as sliced ELL; 0: vector-per-row CSR */
+   int coarse_solve;            /* 0: SMEM convention, the coarsest level contributes nothing to Multadd/AFACx (the reference's
+                                   hypre_GaussElimSolve result is never used there); 1: DMEM convention, direct solve
+                                   on the coarsest level (src/DMEM_Add.cpp:262-264, src/DMEM_Mult.cpp:393) applied as a dense inverse */
    int sell_sigma;              /* > 1: SELL-C-sigma (rows sorted by length inside windows of sigma rows) for the
                                    non-stencil matrices whose padding then stays <= 25 %; 0/1: off */
    int stream_variant;          /* geometry of the CSR-stream kernel (csrc/launch.h kStreamVariants; default 8 = warp-granular, 256-entry chunks) */

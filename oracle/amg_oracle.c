@@ -53,6 +53,8 @@ typedef struct {
    const int *const *jgs_blocks; /* [L] block boundaries (nblocks+1 ints) for hybrid JGS, or NULL */
    const int *jgs_nblocks;       /* [L] */
    int jgs_parfor_scale;         /* 1: divide by a_ii/w (Parfor variant, SMEM_Smooth.cpp:253-263) */
+   int coarse_solve;             /* 1: DMEM convention -- direct solve on the coarsest level (hypre_GaussElimSolve,
+                                    src/DMEM_Add.cpp:262-264, src/DMEM_Mult.cpp:393); 0: SMEM (contributes nothing) */
 } orc_problem;
 
 /* ---- SpMV family ------------------------------------------------------------------------ */
@@ -271,6 +273,37 @@ static void orc_smooth(const orc_problem *pb, int level, const double *f, double
    }
 }
 
+/* dense Gaussian elimination with partial pivoting on the coarsest operator: x = A^{-1} b (what
+ * hypre_GaussElimSetup / hypre_GaussElimSolve, relax type 9, do -- third-party, restated) */
+static void orc_dense_solve(const orc_csr *A, const double *b, double *x)
+{
+   const int n = A->nrows;
+   double *M = (double *)calloc((size_t)n * (n + 1), sizeof(double));
+   for (int i = 0; i < n; i++) {
+      for (int p = A->i[i]; p < A->i[i + 1]; p++) M[(size_t)i * (n + 1) + A->j[p]] += A->data[p];
+      M[(size_t)i * (n + 1) + n] = b[i];
+   }
+   for (int k = 0; k < n; k++) {
+      int piv = k;
+      for (int i = k + 1; i < n; i++)
+         if (fabs(M[(size_t)i * (n + 1) + k]) > fabs(M[(size_t)piv * (n + 1) + k])) piv = i;
+      if (piv != k)
+         for (int j = 0; j <= n; j++) { double t = M[(size_t)k * (n + 1) + j]; M[(size_t)k * (n + 1) + j] = M[(size_t)piv * (n + 1) + j]; M[(size_t)piv * (n + 1) + j] = t; }
+      const double d = M[(size_t)k * (n + 1) + k];
+      for (int i = k + 1; i < n; i++) {
+         const double fct = M[(size_t)i * (n + 1) + k] / d;
+         if (fct != 0.0)
+            for (int j = k; j <= n; j++) M[(size_t)i * (n + 1) + j] -= fct * M[(size_t)k * (n + 1) + j];
+      }
+   }
+   for (int i = n - 1; i >= 0; i--) {
+      double sum = M[(size_t)i * (n + 1) + n];
+      for (int j = i + 1; j < n; j++) sum -= M[(size_t)i * (n + 1) + j] * x[j];
+      x[i] = sum / M[(size_t)i * (n + 1) + i];
+   }
+   free(M);
+}
+
 /* ---- cycles --------------------------------------------------------------------------------- */
 typedef struct {
    double **r, **e, **y, **s, **uc, **rf;
@@ -309,7 +342,9 @@ static void orc_add_vcycle(const orc_problem *pb, orc_work *w, double *u, int *l
    for (int l = 0; l < L - 1; l++) orc_matvec(&pb->R[l], w->r[l], w->r[l + 1], 0, pb->R[l].nrows);
    for (int level = 0; level < L; level++) {
       double *uf = w->uc[level]; /* u_fine of this level */
-      if (level == L - 1) {
+      if (level == L - 1 && pb->coarse_solve && L > 1) {
+         orc_dense_solve(&pb->A[level], w->r[level], w->e[level]);
+      } else if (level == L - 1) {
          /* coarsest: solve commented out / result unused -> contributes 0 */
          memset(w->e[level], 0, sizeof(double) * (size_t)pb->A[level].nrows);
       } else if (pb->solver == ORC_MULTADD) {

@@ -31,7 +31,8 @@ class OrcProblem(C.Structure):
                 ("l1", C.POINTER(DP)),
                 ("solver", C.c_int), ("smoother", C.c_int), ("smooth_weight", C.c_double),
                 ("num_pre", C.c_int), ("num_post", C.c_int), ("fine_sweeps", C.c_int), ("coarse_sweeps", C.c_int),
-                ("jgs_blocks", C.POINTER(IP)), ("jgs_nblocks", IP), ("jgs_parfor_scale", C.c_int)]
+                ("jgs_blocks", C.POINTER(IP)), ("jgs_nblocks", IP), ("jgs_parfor_scale", C.c_int),
+                ("coarse_solve", C.c_int)]
 
 
 _lib = None
@@ -83,7 +84,7 @@ class Problem:
     """Keeps the numpy arrays alive and exposes an orc_problem for the C side."""
 
     def __init__(self, h, solver, smoother, smooth_weight=1.0, num_pre=1, num_post=1,
-                 fine_sweeps=1, coarse_sweeps=1, jgs_blocks=None, jgs_parfor_scale=0):
+                 fine_sweeps=1, coarse_sweeps=1, jgs_blocks=None, jgs_parfor_scale=0, coarse_solve=0):
         L = h.num_levels
         self.h = h
         self._keep = (list(h.A), list(h.P), list(h.R))   # the C structs borrow these arrays
@@ -106,6 +107,7 @@ class Problem:
         p.jgs_blocks = self._bptr
         p.jgs_nblocks = iptr(self._nb)
         p.jgs_parfor_scale = jgs_parfor_scale
+        p.coarse_solve = int(coarse_solve)
         self.c = p
 
     def solve_sync(self, f, tol=1e-9, num_cycles=100, cheby=None, u0=None):

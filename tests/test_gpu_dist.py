@@ -24,15 +24,15 @@ def _setup(prob, n, w, post=1):
     return h, H.rand_rhs(A.nrows)
 
 
-@pytest.mark.parametrize("post", [1, 0])
-def test_single_rank_communicator_matches_oracle(post):
+@pytest.mark.parametrize("post,direct", [(1, 0), (0, 0), (1, 1)])
+def test_single_rank_communicator_matches_oracle(post, direct):
     w = 0.9
     h, b = _setup("7pt", 20, w, post)
     plan = PT.RankPlan(h, 1, 0)
-    s = amg.DistSolver(plan, amg.solver.dist_unique_id(), w, num_pre=1, num_post=post)
+    s = amg.DistSolver(plan, amg.solver.dist_unique_id(), w, num_pre=1, num_post=post, coarse_solve=bool(direct))
     s.set_rhs(b)
     hist, secs = s.solve_sync(1e-9, 100)
-    _, want, _ = O.Problem(h, H.MULTADD, H.JACOBI, w, num_pre=1, num_post=post).solve_sync(b, 1e-9, 100)
+    _, want, _ = O.Problem(h, H.MULTADD, H.JACOBI, w, num_pre=1, num_post=post, coarse_solve=direct).solve_sync(b, 1e-9, 100)
     assert len(hist) == len(want)
     assert np.max(np.abs(hist - want)) <= HIST_TOL
     u = s.get_solution()

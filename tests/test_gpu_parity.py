@@ -278,6 +278,26 @@ def test_multiplicative_vcycle_matches_oracle(prob, n, smoother, pre, post):
     s.close()
 
 
+@pytest.mark.parametrize("solver,w", [(H.MULTADD, 0.9), (H.AFACX, 0.6)])
+def test_dmem_convention_coarse_direct_solve_matches_oracle(solver, w):
+    """coarse_solve = 1: the coarsest level is solved directly (hypre_GaussElimSolve in DMEM's AddCycle,
+    src/DMEM_Add.cpp:262-264) instead of contributing nothing (SMEM)"""
+    A = H.laplacian("7pt", 20)
+    h = H.amg_setup(A, max_coarse=40)            # a coarsest level with a few dozen rows
+    assert 8 < h.n[-1] <= 2048
+    h.build_transfers(solver, w)
+    b = H.rand_rhs(A.nrows)
+    pb = O.Problem(h, solver, H.JACOBI, w, coarse_solve=1)
+    s = amg.Solver(h, solver, H.JACOBI, w, coarse_solve=True)
+    assert _rel(s.cycle(b), pb.cycle(b)) <= 1e-12
+    base = amg.Solver(h, solver, H.JACOBI, w)
+    assert _rel(s.cycle(b), base.cycle(b)) > 1e-6          # the coarse correction really is there
+    base.close()
+    _, want, _ = pb.solve_sync(b, 1e-9, 100)
+    _check_hist(s.SMEM_Solve(b, 1e-9, 100)["hist"], want)
+    s.close()
+
+
 def test_chebyshev_accelerated_bpx_matches_oracle():
     h, b = _problem("7pt", 20, H.BPX, 0.8)
     # eigenvalue bounds of the BPX-preconditioned operator are an INPUT (ChebySetup is host-side)
