@@ -246,7 +246,7 @@ class RefSolver:
             # corrected (the `max_diff < 0.0 && threads == 1` guard at
             # src/SMEM_Setup.cpp:788 tests the running maximum, not the candidate).  A converging run needs
             # every level served: move one thread from the best-provisioned level to each empty one.
-            while min(tpl) == 0:
+            while min(tpl) == 0 and num_threads >= L:    # (ONE_LEVEL solvers -- MULT, BPX -- ignore the assignment)
                 tpl[int(np.argmax(tpl))] -= 1
                 tpl[tpl.index(0)] += 1
             self.threads_per_level = np.asarray(tpl, dtype=np.int32)

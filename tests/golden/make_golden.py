@@ -71,6 +71,12 @@ def main():
         out = rs.solve(10, 1e-30, async_type=0)
         d["bpx_j_hist"] = out["hist"]
         rs.close()
+        # reference: multiplicative V(1,1) cycle through SMEM_Solve itself (omp-for cycle, deterministic), weight 0.8
+        h.build_transfers(H.MULT, 0.8)
+        rs = O.RefSolver(h, H.MULT, H.JACOBI, b, 0.8, num_threads=4)
+        out = rs.solve(100, 1e-9, async_type=0)
+        d["mult_j_hist"] = out["hist"]
+        rs.close()
         # reference kernels: SMEM_MatVec and the sequential smoothers on level 0
         x = np.cos(np.arange(A.nrows) * 0.37)
         y = np.zeros(A.nrows)

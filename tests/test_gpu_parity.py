@@ -221,6 +221,11 @@ def test_sync_history_matches_reference_fixture(name):
     s = amg.Solver(h, H.AFACX, H.JACOBI, 0.6)
     _check_hist(s.SMEM_Solve(d["b"], 1e-9, 40)["hist"], d["afacx_j_hist"])
     s.close()
+    h.build_transfers(H.MULT, 0.8)
+    s = amg.Solver(h, H.MULT, H.JACOBI, 0.8)
+    _check_hist(s.SMEM_Solve(d["b"], 1e-9, 100)["hist"], d["mult_j_hist"])
+    s.close()
+    h.build_transfers(H.AFACX, 0.6)
     s = amg.Solver(h, H.BPX, H.JACOBI, 0.6)
     got = s.SMEM_Solve(d["b"], 1e-30, 10)["hist"]
     assert np.max(np.abs(got - d["bpx_j_hist"]) / d["bpx_j_hist"]) <= 1e-10
@@ -259,8 +264,8 @@ def test_sync_history_matches_oracle(prob, n, solver, smoother, w, post):
                                                       ("7pt", 16, H.L1_JACOBI, 1, 1)])
 def test_multiplicative_vcycle_matches_oracle(prob, n, smoother, pre, post):
     """MULT (SMEM_Sync_Parfor_Vcycle), the comparator of the additive cycles.  The oracle restates
-    src/SMEM_Sync_AMG.cpp:8-145; the reference's own MULT path does not run under the stub driver (it needs hypre's
-    solver object), so this row is pinned by the restatement plus the properties below."""
+    src/SMEM_Sync_AMG.cpp:8-145 and is pinned by the reference's own object code (tests/golden mult_j_hist,
+    tests/test_oracle_golden.py: identical histories to 6e-17)."""
     w = 0.8
     h, b = _problem(prob, n, H.MULT, w)
     _, want, _ = O.Problem(h, H.MULT, smoother, w, num_pre=pre, num_post=post).solve_sync(b, 1e-9, 100)

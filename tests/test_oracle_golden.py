@@ -47,6 +47,14 @@ def test_afacx_history(golden):
     _close_hist(hist, d["afacx_j_hist"])
 
 
+def test_multiplicative_vcycle_history(golden):
+    """MULT: SMEM_Sync_Parfor_Vcycle run by the reference's own SMEM_Solve (fixture), V(1,1), weight 0.8"""
+    h, d = golden
+    h.build_transfers(H.MULT, 0.8)
+    _, hist, _ = O.Problem(h, H.MULT, H.JACOBI, 0.8).solve_sync(d["b"], 1e-9, 100)
+    _close_hist(hist, d["mult_j_hist"])
+
+
 def test_bpx_history(golden):
     h, d = golden
     h.build_transfers(H.AFACX, 0.6)
