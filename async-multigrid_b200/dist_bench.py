@@ -86,15 +86,20 @@ def _build_and_scatter(args, world, d):
         l0 = layouts[r][0]
         np.save(os.path.join(d, "rank%d" % r, "b.npy"), b[l0.row_start:l0.row_start + l0.n_owned])
     L = h.num_levels
+    from concurrent.futures import ThreadPoolExecutor
+
+    def cut(l, r):
+        lay, rd = layouts[r][l], os.path.join(d, "rank%d" % r)
+        _save_csr(rd, "A%d" % l, PT._block(h.A[l], lay.row_start, lay.row_start + lay.n_owned, lay.base, lay.n_ext))
+        if l < L - 1:
+            nxt = layouts[r][l + 1]
+            _save_csr(rd, "P%d" % l, PT._block(h.P[l], lay.row_start, lay.row_start + lay.n_owned, nxt.base, nxt.n_ext))
+            _save_csr(rd, "R%d" % l, PT._block(h.R[l], nxt.row_start, nxt.row_start + nxt.n_owned, lay.base, lay.n_ext))
+
     for l in range(L):
         if l < num_dist:
-            for r in range(world):
-                lay, rd = layouts[r][l], os.path.join(d, "rank%d" % r)
-                _save_csr(rd, "A%d" % l, PT._block(h.A[l], lay.row_start, lay.row_start + lay.n_owned, lay.base, lay.n_ext))
-                if l < L - 1:
-                    nxt = layouts[r][l + 1]
-                    _save_csr(rd, "P%d" % l, PT._block(h.P[l], lay.row_start, lay.row_start + lay.n_owned, nxt.base, nxt.n_ext))
-                    _save_csr(rd, "R%d" % l, PT._block(h.R[l], nxt.row_start, nxt.row_start + nxt.n_owned, lay.base, lay.n_ext))
+            with ThreadPoolExecutor(max_workers=min(world, 8)) as ex:      # numpy slicing / np.save release the GIL
+                list(ex.map(lambda r: cut(l, r), range(world)))
         else:
             sd = os.path.join(d, "shared")
             _save_csr(sd, "A%d" % l, h.A[l])
