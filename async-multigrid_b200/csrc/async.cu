@@ -67,6 +67,20 @@ __device__ void team_smooth_zero(const AsyncParams &p, const Team &tm, int l, co
 {
    const DevCSR &A = p.A[l];
    const int n = A.nrows;
+   if (p.smoother == AMGB_SMOOTH_ASYNC_GS || p.smoother == AMGB_SMOOTH_SEMI_ASYNC_GS) {
+      for (int i = tm.tid; i < n; i += tm.size) st_cg(e + i, 0.0);
+      group_barrier(tm);
+      if (p.smoother == AMGB_SMOOTH_ASYNC_GS) {
+         async_gs_team<false>(A, f, e, p.jgs_block_rows, sweeps, tm.tid, tm.size);
+         group_barrier(tm);
+      } else {
+         for (int k = 0; k < sweeps; k++) {
+            async_gs_team<false>(A, f, e, p.jgs_block_rows, 1, tm.tid, tm.size);
+            group_barrier(tm);
+         }
+      }
+      return;
+   }
    if (p.smoother == AMGB_SMOOTH_HYBRID_JGS) {
       hybrid_jgs_team<false>(A, f, e, nullptr, nullptr, p.jgs_block_rows, true, tm.tid, tm.size);
       group_barrier(tm);

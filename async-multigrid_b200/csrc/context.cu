@@ -544,7 +544,7 @@ int amgb_setup(amgb_ctx *c)
    const amgb_options &o = c->opt;
    const bool multadd = o.solver == AMGB_SOLVER_MULTADD || o.solver == AMGB_SOLVER_ASYNC_MULTADD;
    c->symmetric = multadd && o.num_pre_smooth_sweeps > 0 && o.num_post_smooth_sweeps > 0 &&
-                  o.smoother != AMGB_SMOOTH_HYBRID_JGS;
+                  (o.smoother == AMGB_SMOOTH_JACOBI || o.smoother == AMGB_SMOOTH_L1_JACOBI);
    int rc;
    c->ws.assign(L, nullptr); c->dow.assign(L, nullptr); c->l1.assign(L, nullptr); c->inv_l1.assign(L, nullptr);
    c->r.assign(L, nullptr); c->e.assign(L, nullptr); c->t.assign(L, nullptr); c->w.assign(L, nullptr);
@@ -666,6 +666,12 @@ void enq_smooth_zero(amgb_ctx *c, int l, const double *f, double *e, int sweeps,
    const int n = A.nrows;
    const int sm = c->opt.smoother;
    if (sweeps < 1) { cudaMemsetAsync(e, 0, sizeof(double) * n, c->stream); return; }
+   if (sm == AMGB_SMOOTH_ASYNC_GS || sm == AMGB_SMOOTH_SEMI_ASYNC_GS) {
+      // chaotic Gauss-Seidel from the zero guess the additive cycles give it (src/SMEM_Smooth.cpp:445-502)
+      cudaMemsetAsync(e, 0, sizeof(double) * n, c->stream);
+      c->launches += launch_async_gs(c->cfg, c->stream, A, f, e, c->opt.jgs_block_rows, sweeps, sm == AMGB_SMOOTH_SEMI_ASYNC_GS);
+      return;
+   }
    if (sm == AMGB_SMOOTH_HYBRID_JGS) {
       const double *scale = parfor ? c->dow[l] : nullptr;
       c->launches += launch_hybrid_jgs(c->cfg, c->stream, A, f, e, nullptr, scale, c->opt.jgs_block_rows, true);
@@ -820,6 +826,23 @@ int amgb_spgemv(amgb_ctx *c, int kind, int level, double alpha, const double *x,
    return AMGB_OK;
 }
 
+int amgb_spgemv_transpose(amgb_ctx *c, int kind, int level, const double *x, double *y)
+{
+   NEED_READY(c);
+   if (level < 0 || level >= c->L || (kind != AMGB_MAT_A && level >= c->L - 1)) return amgb_fail(c, AMGB_EINVAL, "bad level");
+   const DevCSR &M = kind == AMGB_MAT_A ? c->A[level] : (kind == AMGB_MAT_P ? c->P[level] : c->R[level]);
+   if (!x || !y) return amgb_fail(c, AMGB_EINVAL, "null vector");
+   int maxn = 0;
+   for (auto &a : c->A) maxn = std::max(maxn, a.nrows);
+   if (M.nrows > maxn || M.ncols > maxn) return amgb_fail(c, AMGB_EINVAL, "matrix larger than the staging vectors");
+   CUDA_OK(c, cudaMemcpyAsync(c->io_a, x, sizeof(double) * M.nrows, cudaMemcpyHostToDevice, c->stream));
+   c->launches += launch_spmv_transpose(c->cfg, c->stream, M, c->io_a, c->io_c);
+   CUDA_OK(c, cudaMemcpyAsync(y, c->io_c, sizeof(double) * M.ncols, cudaMemcpyDeviceToHost, c->stream));
+   CUDA_OK(c, cudaStreamSynchronize(c->stream));
+   CUDA_OK(c, cudaGetLastError());
+   return AMGB_OK;
+}
+
 int amgb_smooth(amgb_ctx *c, int level, int smoother, int symmetric, int sweeps, int zero_guess, const double *f, double *u)
 {
    NEED_READY(c);
@@ -836,7 +859,9 @@ int amgb_smooth(amgb_ctx *c, int level, int smoother, int symmetric, int sweeps,
       if (symmetric) return amgb_fail(c, AMGB_EINVAL, "symmetrised smoother is only used from a zero guess");
       double *cur = c->io_b, *oth = c->io_c;
       for (int k = 0; k < sweeps; k++) {
-         if (smoother == AMGB_SMOOTH_HYBRID_JGS) {
+         if (smoother == AMGB_SMOOTH_ASYNC_GS || smoother == AMGB_SMOOTH_SEMI_ASYNC_GS) {
+            c->launches += launch_async_gs(c->cfg, c->stream, A, c->io_a, cur, c->opt.jgs_block_rows, 1, true);
+         } else if (smoother == AMGB_SMOOTH_HYBRID_JGS) {
             CUDA_OK(c, cudaMemcpyAsync(oth, cur, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
             c->launches += launch_hybrid_jgs(c->cfg, c->stream, A, c->io_a, cur, oth, nullptr, c->opt.jgs_block_rows, false);
          } else {

@@ -103,6 +103,16 @@ __global__ void __launch_bounds__(kBlock) k_hybrid_jgs(DevCSR A, const double *f
    hybrid_jgs_team<true>(A, f, u, u_prev, scale, B, zero_guess != 0, blockIdx.x * kBlock + threadIdx.x, gridDim.x * kBlock);
 }
 
+__global__ void __launch_bounds__(kBlock) k_async_gs(DevCSR A, const double *f, double *u, int B, int sweeps)
+{
+   async_gs_team<true>(A, f, u, B, sweeps, blockIdx.x * kBlock + threadIdx.x, gridDim.x * kBlock);
+}
+
+__global__ void __launch_bounds__(kBlock) k_spmv_transpose(DevCSR M, const double *x, double *y)
+{
+   csr_transpose_rows_team<8>(M, x, y, blockIdx.x * kBlock + threadIdx.x, gridDim.x * kBlock);
+}
+
 __global__ void __launch_bounds__(kBlock) k_diag_scale(DevCSR A, double w, double *ws, double *dow)
 {
    for (int i = blockIdx.x * kBlock + threadIdx.x; i < A.nrows; i += gridDim.x * kBlock) {
@@ -307,6 +317,23 @@ int launch_hybrid_jgs(const LaunchCfg &cfg, cudaStream_t st, const DevCSR &A, co
 {
    long nblocks = ((long)A.nrows + block_rows - 1) / block_rows;
    k_hybrid_jgs<<<grid_for(cfg, nblocks), kBlock, 0, st>>>(A, f, u, u_prev, scale, block_rows, zero_guess ? 1 : 0);
+   return 1;
+}
+
+int launch_async_gs(const LaunchCfg &cfg, cudaStream_t st, const DevCSR &A, const double *f, double *u, int block_rows,
+                    int sweeps, bool semi)
+{
+   const long nblocks = ((long)A.nrows + block_rows - 1) / block_rows;
+   const int grid = grid_for(cfg, nblocks);
+   if (!semi) { k_async_gs<<<grid, kBlock, 0, st>>>(A, f, u, block_rows, sweeps); return 1; }
+   for (int k = 0; k < sweeps; k++) k_async_gs<<<grid, kBlock, 0, st>>>(A, f, u, block_rows, 1);
+   return sweeps;
+}
+
+int launch_spmv_transpose(const LaunchCfg &cfg, cudaStream_t st, const DevCSR &M, const double *x, double *y)
+{
+   cudaMemsetAsync(y, 0, sizeof(double) * (size_t)M.ncols, st);
+   k_spmv_transpose<<<grid_for(cfg, (long)M.nrows * 8), kBlock, 0, st>>>(M, x, y);
    return 1;
 }
 

@@ -424,3 +424,42 @@ __device__ __forceinline__ void hybrid_jgs_team(const DevCSR &A, const double *_
       }
    }
 }
+
+// ---- (semi-)asynchronous Gauss-Seidel (src/SMEM_Smooth.cpp:445-502) -------------------------------
+// Every thread sweeps its blocks of `B` consecutive rows in order, reading whatever the other threads have
+// written to u so far (chaotic relaxation): u_i += (f_i - sum_j a_ij u_j) / a_ii.  The asynchronous variant
+// runs all `sweeps` without synchronising; the semi-asynchronous one is launched once per sweep (the kernel
+// boundary is its barrier).  u is read and written through L2 (ld.cg / st.cg) so that updates become visible.
+template <bool RO>
+__device__ __forceinline__ void async_gs_team(const DevCSR &A, const double *__restrict__ f, double *u, int B, int sweeps,
+                                              int team_tid, int team_size)
+{
+   const int nblocks = (A.nrows + B - 1) / B;
+   for (int k = 0; k < sweeps; k++)
+      for (int blk = team_tid; blk < nblocks; blk += team_size) {
+         const int ns = blk * B, ne = min(ns + B, A.nrows);
+         for (int i = ns; i < ne; i++) {
+            const int s = A.rp[i], t = A.rp[i + 1];
+            const double d = A.va[s];
+            if (d != 0.0) {
+               double res = ld_x<RO>(f + i);
+               for (int p = s; p < t; p++) res -= A.va[p] * ld_cg(u + A.ci[p]);
+               st_cg(u + i, ld_cg(u + i) + res / d);
+            }
+         }
+      }
+}
+
+// ---- y += M^T x (SMEM_MatVecT / SMEM_Restrict with -no_construct_R, src/SMEM_MatVec.cpp:325-408) --------
+// LPR lanes walk one row of M and scatter its contributions with fp64 reductions; y must be zeroed first.
+template <int LPR>
+__device__ __forceinline__ void csr_transpose_rows_team(const DevCSR &M, const double *__restrict__ x, double *y,
+                                                        int team_tid, int team_size)
+{
+   const int lane = team_tid & (LPR - 1);
+   for (int row = team_tid / LPR; row < M.nrows; row += team_size / LPR) {
+      const double xr = __ldg(x + row);
+      const int s = __ldg(M.rp + row), t = __ldg(M.rp + row + 1);
+      for (int p = s + lane; p < t; p += LPR) red_add_f64(y + ld_stream(M.ci + p), ld_stream(M.va + p) * xr);
+   }
+}

@@ -46,6 +46,10 @@ int launch_sumsq(const LaunchCfg &cfg, cudaStream_t st, int n, const double *x, 
 // hybrid JGS sweep
 int launch_hybrid_jgs(const LaunchCfg &cfg, cudaStream_t st, const DevCSR &A, const double *f, double *u,
                       const double *u_prev, const double *scale, int block_rows, bool zero_guess);
+// (semi-)asynchronous Gauss-Seidel sweeps on u (in place); y = M^T x
+int launch_async_gs(const LaunchCfg &cfg, cudaStream_t st, const DevCSR &A, const double *f, double *u, int block_rows,
+                    int sweeps, bool semi);
+int launch_spmv_transpose(const LaunchCfg &cfg, cudaStream_t st, const DevCSR &M, const double *x, double *y);
 // setup helpers: ws = w/d (0 where d == 0), l1 = sum |a_ij|, sval = va .* cs[col]
 int launch_diag_scale(cudaStream_t st, const DevCSR &A, double w, double *ws, double *dow);
 int launch_l1(cudaStream_t st, const DevCSR &A, double *l1, double *inv_l1);

@@ -15,6 +15,8 @@ from . import build as _build
 # enums shared with the reference (src/Main.hpp:47-75) ------------------------------------
 JACOBI = 0
 HYBRID_JACOBI_GAUSS_SEIDEL = 2
+SEMI_ASYNC_GAUSS_SEIDEL = 4
+ASYNC_GAUSS_SEIDEL = 5
 L1_JACOBI = 6
 MULT, AFACX, MULTADD, BPX = 0, 1, 2, 3
 ASYNC_AFACX, ASYNC_MULTADD = 5, 6

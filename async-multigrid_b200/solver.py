@@ -23,7 +23,7 @@ ABI_SYMBOLS = [
     "amgb_default_options", "amgb_create", "amgb_destroy", "amgb_last_error", "amgb_launch_count",
     "amgb_set_num_levels", "amgb_set_matrix", "amgb_set_options", "amgb_setup",
     "amgb_set_rhs", "amgb_set_solution", "amgb_get_solution", "amgb_get_residual",
-    "amgb_spgemv", "amgb_smooth", "amgb_norm2", "amgb_cycle", "amgb_eigs_power", "amgb_solve_sync", "amgb_solve_async",
+    "amgb_spgemv", "amgb_spgemv_transpose", "amgb_smooth", "amgb_norm2", "amgb_cycle", "amgb_eigs_power", "amgb_solve_sync", "amgb_solve_async",
     "amgb_smem_solve", "amgb_time_residual", "amgb_level_storage", "amgb_time_spmv", "amgb_stream_stats", "amgb_l2_arena_bytes",
     "amgb_dist_unique_id", "amgb_dist_init", "amgb_dist_set_level", "amgb_dist_setup", "amgb_dist_set_rhs",
     "amgb_dist_get_solution", "amgb_dist_solve_sync", "amgb_dist_stats",
@@ -67,6 +67,7 @@ def load_library():
     L.amgb_get_solution.argtypes = [C.c_void_p, DP]
     L.amgb_get_residual.argtypes = [C.c_void_p, DP]
     L.amgb_spgemv.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, DP, C.c_double, DP, DP]
+    L.amgb_spgemv_transpose.argtypes = [C.c_void_p, C.c_int, C.c_int, DP, DP]
     L.amgb_smooth.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, DP, DP]
     L.amgb_norm2.argtypes = [C.c_void_p, DP, C.c_int, DP]
     L.amgb_cycle.argtypes = [C.c_void_p, DP, DP]
@@ -187,6 +188,14 @@ class Solver:
         y = np.empty(m.nrows)
         bb = None if b is None else np.ascontiguousarray(b, dtype=np.float64)
         self._ck(self.L.amgb_spgemv(self.ctx, kind, level, alpha, _dp(x), beta, None if bb is None else _dp(bb), _dp(y)))
+        return y
+
+    def spgemv_transpose(self, kind, level, x):
+        """y = M^T x (SMEM_MatVecT; restriction through P with -no_construct_R)"""
+        m = (self.h.A, self.h.P, self.h.R)[kind][level]
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty(m.ncols)
+        self._ck(self.L.amgb_spgemv_transpose(self.ctx, kind, level, _dp(x), _dp(y)))
         return y
 
     def smooth(self, level, f, sweeps=1, symmetric=False, zero_guess=True, u0=None):

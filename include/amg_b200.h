@@ -30,7 +30,8 @@ enum {
 };
 
 /* enumerators keep the reference's numeric values (src/Main.hpp:47-75) */
-enum { AMGB_SMOOTH_JACOBI = 0, AMGB_SMOOTH_HYBRID_JGS = 2, AMGB_SMOOTH_L1_JACOBI = 6 };
+enum { AMGB_SMOOTH_JACOBI = 0, AMGB_SMOOTH_HYBRID_JGS = 2, AMGB_SMOOTH_SEMI_ASYNC_GS = 4, AMGB_SMOOTH_ASYNC_GS = 5,
+       AMGB_SMOOTH_L1_JACOBI = 6 };
 enum { AMGB_SOLVER_MULT = 0, AMGB_SOLVER_AFACX = 1, AMGB_SOLVER_MULTADD = 2, AMGB_SOLVER_BPX = 3,
        AMGB_SOLVER_ASYNC_AFACX = 5, AMGB_SOLVER_ASYNC_MULTADD = 6 };
 enum { AMGB_CONVERGE_LOCAL = 0, AMGB_CONVERGE_GLOBAL = 1 };       /* src/Main.hpp LOCAL/GLOBAL */
@@ -90,6 +91,9 @@ int amgb_get_residual(amgb_ctx *ctx, double *r_host);
  * (src/SMEM_MatVec.cpp:123-259,302-378,394-408).  b may be NULL when beta == 0. */
 int amgb_spgemv(amgb_ctx *ctx, int kind, int level, double alpha, const double *x, double beta,
                 const double *b, double *y);
+/* y = M^T x -- SMEM_MatVecT / SMEM_Restrict with -no_construct_R (src/SMEM_MatVec.cpp:325-408): restriction through
+ * the interpolation matrix itself; x has M.nrows entries, y M.ncols. */
+int amgb_spgemv_transpose(amgb_ctx *ctx, int kind, int level, const double *x, double *y);
 /* SMEM_Smooth dispatcher (src/SMEM_Solve.cpp:264-377) on level `level`: u is in/out (ignored on
  * input when zero_guess != 0).  symmetric != 0 selects SMEM_Sync_Symmetric{,L1}Jacobi. */
 int amgb_smooth(amgb_ctx *ctx, int level, int smoother, int symmetric, int sweeps, int zero_guess,

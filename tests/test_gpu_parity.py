@@ -129,6 +129,46 @@ def test_hybrid_jgs_matches_oracle(block_rows):
     s.close()
 
 
+def test_transpose_spmv_matches_explicit_restriction():
+    """SMEM_MatVecT (-no_construct_R): restriction through P itself equals the explicit R = P^T product"""
+    h, b = _problem("7pt", 14, H.AFACX, 0.9)            # AFACx keeps plain P and R = P^T
+    s = amg.Solver(h, H.AFACX, H.JACOBI, 0.9)
+    rng = np.random.default_rng(5)
+    for l in range(h.num_levels - 1):
+        x = rng.uniform(-1, 1, h.n[l])
+        got = s.spgemv_transpose(MAT_P, l, x)
+        want = O.spgemv(h.R[l], x, None, 1.0, 0.0)
+        mag = O.spgemv(H.CSR(h.R[l].nrows, h.R[l].ncols, h.R[l].indptr, h.R[l].indices, np.abs(h.R[l].data)), np.abs(x), None, 1.0, 0.0)
+        assert np.max(np.abs(got - want) / np.maximum(mag, 1e-300)) <= 1e-13      # atomics: order differs, value does not
+    s.close()
+
+
+@pytest.mark.parametrize("smoother", [H.ASYNC_GAUSS_SEIDEL, H.SEMI_ASYNC_GAUSS_SEIDEL])
+def test_async_gauss_seidel_smoothers(smoother):
+    """SMEM_Async_GaussSeidel / SMEM_SemiAsync_GaussSeidel (src/SMEM_Smooth.cpp:445-502).  With ONE block the chaotic
+    sweep is plain Gauss-Seidel (deterministic: equals the oracle); with many blocks it must still contract."""
+    h, b = _problem("7pt", 13, H.MULTADD, 0.9, num_pre=1, num_post=0)
+    n = h.n[0]
+    f = H.rand_rhs(n, seed=3)
+    s = amg.Solver(h, H.MULTADD, smoother, 0.9, num_pre=1, num_post=0, jgs_block_rows=n)
+    for sweeps in (1, 2):
+        got = s.smooth(0, f, sweeps=sweeps, zero_guess=True)
+        want = O.smooth("hybrid_jgs", h.A[0], f, sweeps=sweeps, zero_flag=1, blocks=np.asarray([0, n], dtype=np.int32))
+        assert _rel(got, want) <= 1e-13
+    s.close()
+    s = amg.Solver(h, H.MULTADD, smoother, 0.9, num_pre=1, num_post=0, jgs_block_rows=4)
+    res = []
+    for sweeps in (2, 8, 32):
+        u = s.smooth(0, f, sweeps=sweeps, zero_guess=True)
+        res.append(O.norm2(O.spgemv(h.A[0], u, f, -1.0, 1.0)) / O.norm2(f))
+    assert res[0] < 1.0 and res[1] < res[0] and res[2] < 0.5 * res[1], res
+    # as the level smoother of a synchronous Multadd solve (plain P, smoothed R)
+    out = s.SMEM_Solve(b, 1e-9, 150)
+    true = O.norm2(O.spgemv(h.A[0], out["u"], b, -1.0, 1.0)) / O.norm2(b)
+    assert abs(true - out["relres"]) <= 1e-12 and true < 1e-9, (true, out["cycles"])
+    s.close()
+
+
 def test_norm2():
     h, b = _problem("5pt", 40)
     s = amg.Solver(h)
