@@ -44,3 +44,26 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.lower(), f
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/amg_b200.h compiles as C99 and a C program links against libamg_b200.so -- the binding a
+    maintainer of the (C-style C++) reference would write needs nothing else."""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text('#include "amg_b200.h"\n#include <stdio.h>\n'
+                   'int main(void){ amgb_ctx *c = 0; amgb_options o; amgb_default_options(&o);\n'
+                   '  int rc = amgb_create(&c, 0);\n'
+                   '  printf("%d %d %d\\n", rc, o.solver, o.num_pre_smooth_sweeps);\n'
+                   '  if (rc == AMGB_OK) amgb_destroy(c);\n'
+                   '  return 0; }\n')
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(amg.build.CUDA_LIB)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                        "-L", libdir, "-lamg_b200", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    rc, solver, pre = [int(x) for x in out.stdout.split()]
+    assert solver == 2 and pre == 1                       # MULTADD, the reference's defaults
+    assert (rc == 0) == has_gpu()                         # no device -> an error code, never a CPU fallback

@@ -107,3 +107,33 @@ def test_partition_layout_properties():
                         assert lay.send_hi == halos[l][rank + 1][0]
                 else:
                     assert plan.A[l].nrows == h.n[l]
+
+
+def test_bench_plan_roundtrip_through_disk(tmp_path):
+    """bench.py's multi-GPU leg hands the per-rank blocks over through files: what a rank loads must be what
+    RankPlan builds in memory"""
+    sys.path.insert(0, ROOT)
+    import types
+    import async_multigrid_b200 as amg  # noqa: F401
+    from async_multigrid_b200 import hierarchy as H, partition as PT, dist_bench as DB
+    args = types.SimpleNamespace(n=12, theta=0.25, smooth_weight=0.9, num_post=1, min_rows_per_rank=64)
+    world = 2
+    d = str(tmp_path / "plan")
+    DB._build_and_scatter(args, world, d)
+    A = H.laplacian("7pt", 12, 12, 12 * world)
+    h = H.amg_setup(A)
+    h.build_transfers(H.MULTADD, 0.9)
+    b = H.rand_rhs(A.nrows)
+    for rank in range(world):
+        got = DB._PlanFromDisk(d, rank, world)
+        want = PT.RankPlan(h, world, rank, plane=144, min_rows_per_rank=64)
+        assert got.num_dist == want.num_dist and got.num_levels == want.num_levels
+        for l in range(want.num_levels):
+            a, bb = got.layouts[l], want.layouts[l]
+            assert (a.n_global, a.row_start, a.n_owned, a.halo_lo, a.halo_hi, a.distributed, a.send_lo, a.send_hi) == \
+                   (bb.n_global, bb.row_start, bb.n_owned, bb.halo_lo, bb.halo_hi, bb.distributed, bb.send_lo, bb.send_hi)
+            for mg, mw in ((got.A[l], want.A[l]),) + (((got.P[l], want.P[l]), (got.R[l], want.R[l])) if l < want.num_levels - 1 else ()):
+                assert mg.shape == mw.shape and np.array_equal(mg.indptr, mw.indptr)
+                assert np.array_equal(mg.indices, mw.indices) and np.array_equal(mg.data, mw.data)
+        l0 = want.layouts[0]
+        assert np.array_equal(got.b, b[l0.row_start:l0.row_start + l0.n_owned])
