@@ -207,7 +207,7 @@ def ref_lib():
                                 C.c_int, DP, DP, IP, DP, DP]
         L.ref_destroy.argtypes = [C.c_void_p]
         L.ref_solve_sync_det.restype = C.c_int
-        L.ref_solve_sync_det.argtypes = [C.c_void_p, C.c_int, C.c_double, DP, DP]
+        L.ref_solve_sync_det.argtypes = [C.c_void_p, C.c_int, C.c_double, DP, DP, DP]
         L.ref_matvec.argtypes = [C.POINTER(OrcCSR), DP, DP]
         L.ref_seq_symmetric_jacobi.argtypes = [C.POINTER(OrcCSR), DP, DP, C.c_double, C.c_int]
         L.ref_seq_jacobi.argtypes = [C.POINTER(OrcCSR), DP, DP, C.c_double, C.c_int, C.c_int]
@@ -273,8 +273,9 @@ class RefSolver:
         """race-free run of the reference's grouped additive cycle (see ref_driver.cpp)"""
         u = np.zeros(self.h.n[0])
         hist = np.zeros(num_cycles + 1)
-        k = self.L.ref_solve_sync_det(self.handle, num_cycles, tol, dptr(u), dptr(hist))
-        return dict(u=u, hist=hist[:k + 1], cycles=k)
+        secs = C.c_double(0)
+        k = self.L.ref_solve_sync_det(self.handle, num_cycles, tol, dptr(u), dptr(hist), C.byref(secs))
+        return dict(u=u, hist=hist[:k + 1], cycles=k, seconds=secs.value)
 
     def close(self):
         if self.handle:

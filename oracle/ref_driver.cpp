@@ -308,7 +308,7 @@ int ref_solve(void *h, int num_cycles, double tol, int async_type, int cheby_fla
 // after the cycle and async_type = SEMI_ASYNC (the reference's own lock around the update);
 // with one thread per level it is exactly the sequential specification.  The cycle, residual
 // and smoothers executed are the reference's object code.
-int ref_solve_sync_det(void *h, int num_cycles, double tol, double *u_out, double *hist)
+int ref_solve_sync_det(void *h, int num_cycles, double tol, double *u_out, double *hist, double *solve_seconds)
 {
    RefHandle *H = (RefHandle *)h;
    AllData *ad = &H->all;
@@ -330,6 +330,7 @@ int ref_solve_sync_det(void *h, int num_cycles, double tol, double *u_out, doubl
    omp_init_lock(&ad->thread.lock);
    double r_inner_prod = 0;
    int done = 0;
+   const double t_start = omp_get_wtime();      // the reference times exactly this loop (src/SMEM_Solve.cpp:107,245)
 #pragma omp parallel
    {
       int tid = omp_get_thread_num();
@@ -346,6 +347,7 @@ int ref_solve_sync_det(void *h, int num_cycles, double tol, double *u_out, doubl
          if (r_norm2 / ad->output.r0_norm2 < tol) break;
       }
    }
+   if (solve_seconds) *solve_seconds = omp_get_wtime() - t_start;
    omp_destroy_lock(&ad->thread.lock);
    if (u_out) memcpy(u_out, ad->vector.u[0], sizeof(double) * n0);
    return done;

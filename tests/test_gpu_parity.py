@@ -379,11 +379,11 @@ def test_chebysetup_power_iteration_matches_oracle(solver, w):
 
 # ---- asynchronous solves --------------------------------------------------------------------------------
 @pytest.mark.parametrize("solver,smoother,w,cycles,post", [
-    (H.ASYNC_MULTADD, H.JACOBI, 0.9, 80, 1),
+    (H.ASYNC_MULTADD, H.JACOBI, 0.9, 160, 1),      # chaotic iteration: generous counts, the check is the true residual
     # hybrid JGS: w = 1 diverges asynchronously, also in the reference's own object code; w = 0.7 converges, slowly and
     # with a run-to-run spread of an order of magnitude (chaotic iteration), so this case is held to 1e-6
     (H.ASYNC_MULTADD, H.HYBRID_JACOBI_GAUSS_SEIDEL, 0.7, 300, 0),
-    (H.ASYNC_AFACX, H.JACOBI, 0.5, 150, 1),
+    (H.ASYNC_AFACX, H.JACOBI, 0.5, 300, 1),
 ])
 def test_async_reaches_tolerance(solver, smoother, w, cycles, post):
     h, b = _problem("7pt", 32, H.MULTADD if solver == H.ASYNC_MULTADD else H.AFACX, w, num_pre=1, num_post=post)
@@ -408,8 +408,8 @@ def test_async_global_stop_rule_and_groups():
     assert 0 < used <= cap          # the coarse levels (>= 2) sit in the arena the access-policy window pins in L2
     s.set_rhs(b)
     s.set_solution(None)
-    corr, rel, secs = s.solve_async(60, amg.solver.CONVERGE_GLOBAL)
-    assert np.all(corr >= 60)
+    corr, rel, secs = s.solve_async(120, amg.solver.CONVERGE_GLOBAL)
+    assert np.all(corr >= 120)
     assert rel < 1e-9
     s.close()
 
