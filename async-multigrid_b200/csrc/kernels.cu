@@ -103,6 +103,15 @@ __global__ void __launch_bounds__(kBlock) k_hybrid_jgs(DevCSR A, const double *f
    hybrid_jgs_team<true>(A, f, u, u_prev, scale, B, zero_guess != 0, blockIdx.x * kBlock + threadIdx.x, gridDim.x * kBlock);
 }
 
+template <int LPB>
+__global__ void __launch_bounds__(kBlock) k_hybrid_jgs_sw(DevCSR A, const double *f, double *u, const double *u_prev,
+                                                           const double *scale, int B, int zero_guess)
+{
+   __shared__ double ub[(kBlock / LPB) * AMGB_JGS_BMAX];
+   hybrid_jgs_subwarp_team<true, LPB>(A, f, u, u_prev, scale, B, zero_guess != 0, blockIdx.x * kBlock + threadIdx.x,
+                                      gridDim.x * kBlock, ub);
+}
+
 __global__ void __launch_bounds__(kBlock) k_async_gs(DevCSR A, const double *f, double *u, int B, int sweeps)
 {
    async_gs_team<true>(A, f, u, B, sweeps, blockIdx.x * kBlock + threadIdx.x, gridDim.x * kBlock);
@@ -316,6 +325,16 @@ int launch_hybrid_jgs(const LaunchCfg &cfg, cudaStream_t st, const DevCSR &A, co
                       const double *u_prev, const double *scale, int block_rows, bool zero_guess)
 {
    long nblocks = ((long)A.nrows + block_rows - 1) / block_rows;
+   if (block_rows <= AMGB_JGS_BMAX && A.nrows > 0) {
+      // lanes per block from the mean row length; one sub-warp per block
+      const double avg = (double)A.nnz / A.nrows;
+      const int z = zero_guess ? 1 : 0;
+      if (avg <= 5.0) k_hybrid_jgs_sw<4><<<grid_for(cfg, nblocks * 4), kBlock, 0, st>>>(A, f, u, u_prev, scale, block_rows, z);
+      else if (avg <= 10.0) k_hybrid_jgs_sw<8><<<grid_for(cfg, nblocks * 8), kBlock, 0, st>>>(A, f, u, u_prev, scale, block_rows, z);
+      else if (avg <= 20.0) k_hybrid_jgs_sw<16><<<grid_for(cfg, nblocks * 16), kBlock, 0, st>>>(A, f, u, u_prev, scale, block_rows, z);
+      else k_hybrid_jgs_sw<32><<<grid_for(cfg, nblocks * 32), kBlock, 0, st>>>(A, f, u, u_prev, scale, block_rows, z);
+      return 1;
+   }
    k_hybrid_jgs<<<grid_for(cfg, nblocks), kBlock, 0, st>>>(A, f, u, u_prev, scale, block_rows, zero_guess ? 1 : 0);
    return 1;
 }
