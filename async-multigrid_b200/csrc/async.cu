@@ -82,12 +82,22 @@ __device__ void team_smooth_zero(const AsyncParams &p, const Team &tm, int l, co
       return;
    }
    if (p.smoother == AMGB_SMOOTH_HYBRID_JGS) {
-      hybrid_jgs_team<false>(A, f, e, nullptr, nullptr, p.jgs_block_rows, true, tm.tid, tm.size);
+      auto sweep = [&](const double *uprev, bool zero) {
+         double *su = reinterpret_cast<double *>(tm.smem);
+         switch (p.jgs_lpb[l]) {   // sub-warp per block (see hybrid_jgs_subwarp_team); 0: block longer than the staging slice
+            case 4: hybrid_jgs_subwarp_team<false, 4>(A, f, e, uprev, nullptr, p.jgs_block_rows, zero, tm.tid, tm.size, su); break;
+            case 8: hybrid_jgs_subwarp_team<false, 8>(A, f, e, uprev, nullptr, p.jgs_block_rows, zero, tm.tid, tm.size, su); break;
+            case 16: hybrid_jgs_subwarp_team<false, 16>(A, f, e, uprev, nullptr, p.jgs_block_rows, zero, tm.tid, tm.size, su); break;
+            case 32: hybrid_jgs_subwarp_team<false, 32>(A, f, e, uprev, nullptr, p.jgs_block_rows, zero, tm.tid, tm.size, su); break;
+            default: hybrid_jgs_team<false>(A, f, e, uprev, nullptr, p.jgs_block_rows, zero, tm.tid, tm.size);
+         }
+      };
+      sweep(nullptr, true);
       group_barrier(tm);
       for (int k = 1; k < sweeps; k++) {
          for (int i = tm.tid; i < n; i += tm.size) s1[i] = ld_cg(e + i);
          group_barrier(tm);
-         hybrid_jgs_team<false>(A, f, e, s1, nullptr, p.jgs_block_rows, false, tm.tid, tm.size);
+         sweep(s1, false);
          group_barrier(tm);
       }
       return;
@@ -266,6 +276,10 @@ static int async_prepare(amgb_ctx *c)
    hp.fine_sweeps = o.num_fine_smooth_sweeps;
    hp.coarse_sweeps = o.num_coarse_smooth_sweeps;
    hp.jgs_block_rows = o.jgs_block_rows;
+   for (int l = 0; l < L; l++) {
+      const double avg = c->A[l].nrows > 0 ? (double)c->A[l].nnz / c->A[l].nrows : 0.0;
+      hp.jgs_lpb[l] = o.jgs_block_rows > AMGB_JGS_BMAX ? 0 : (avg <= 5.0 ? 4 : (avg <= 10.0 ? 8 : (avg <= 20.0 ? 16 : 32)));
+   }
    int rc;
    for (int l = 0; l < L; l++) {
       hp.A[l] = c->A[l];

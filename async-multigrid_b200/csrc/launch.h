@@ -71,6 +71,7 @@ struct AsyncParams {
    int symmetric;
    int fine_sweeps, coarse_sweeps;
    int jgs_block_rows;
+   int jgs_lpb[AMGB_MAX_LEVELS];  // lanes per hybrid-JGS block on every level (4/8/16/32 from the mean row length; 0: one thread per block)
    int num_cycles;
    int converge_type;
    DevCSR A[AMGB_MAX_LEVELS], P[AMGB_MAX_LEVELS], R[AMGB_MAX_LEVELS];
