@@ -274,6 +274,9 @@ def run_b200(args):
 
 
 # ------------------------------------------------------------------------------------------------
+_REF = {}
+
+
 def cpu_baseline(args, h, b, cycles_to_tol, sample_cycles=None, full=False):
     """The reference's own OpenMP solve phase (oracle/_ref) -- or the oracle port when _ref is absent --
     on the host cores, on a bounded sample: `sample_cycles` cycles, scaled to the cycle count of the full
@@ -289,7 +292,10 @@ def cpu_baseline(args, h, b, cycles_to_tol, sample_cycles=None, full=False):
     use_ref = O.ref_lib() is not None and not args.cpu_port
     t0 = time.time()
     if use_ref:
-        rs = O.RefSolver(h, sv, sm, b, args.smooth_weight, num_pre=1, num_post=args.num_post, num_threads=threads)
+        # one driver object per process: its setup (allocating and zeroing ~20 GB of per-group vectors) is not the solve phase
+        rs = _REF.get("rs")
+        if rs is None:
+            rs = _REF["rs"] = O.RefSolver(h, sv, sm, b, args.smooth_weight, num_pre=1, num_post=args.num_post, num_threads=threads)
         if sv in (H.ASYNC_MULTADD, H.ASYNC_AFACX):
             out = rs.solve(sample, TOL if full else 1e-300)
             secs, done, rel = out["seconds"], sample, out["relres"]
@@ -306,7 +312,6 @@ def cpu_baseline(args, h, b, cycles_to_tol, sample_cycles=None, full=False):
         else:
             out = rs.solve(sample, TOL if full else 1e-300, async_type=0)
             secs, done, rel = out["seconds"], out["cycles"], out["relres"]
-        rs.close()
         kind = "reference"
     else:
         O.lib().orc_set_threads(threads)
