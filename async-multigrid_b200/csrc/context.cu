@@ -141,6 +141,7 @@ int amgb_destroy(amgb_ctx *c)
    cudaSetDevice(c->device);
    cudaStreamSynchronize(c->stream);
    amgb_dist_teardown(c);
+   for (double *p : c->peer_u) cudaIpcCloseMemHandle(p);
    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
    for (void *p : c->allocs) cudaFree(p);
    if (c->h_scalars) cudaFreeHost(c->h_scalars);
@@ -905,6 +906,81 @@ int amgb_cycle(amgb_ctx *c, const double *r_host, double *c_host)
    CUDA_OK(c, cudaMemcpyAsync(c_host, c->cvec, sizeof(double) * n0, cudaMemcpyDeviceToHost, c->stream));
    CUDA_OK(c, cudaStreamSynchronize(c->stream));
    CUDA_OK(c, cudaGetLastError());
+   return AMGB_OK;
+}
+
+// ---- asynchronous additive solve ACROSS GPUs (DMEM async Multadd, src/DMEM_Add.cpp:101-130,391-458) ----------
+// The reference assigns MPI ranks to grids: every grid's rank group holds the hierarchy down to its level and
+// full-length fine vectors, runs its own restrict -> smooth -> prolong chain on its private residual, and sends
+// the fine-level correction to the other grids, which accumulate it whenever it arrives.  Here a GPU plays a
+// grid's rank group: amgb_async_dist_correct(level) is one pass of AddCycle + DMEM_AddCorrect_LocalRes +
+// DMEM_AddResidual_LocalRes for that level -- private copy of u, r = f - A_0 u, chain, and the correction is
+// added into this GPU's u and into every peer's u with fp64 reductions over NVLink (k_push_correction).
+// Nothing ever waits for a peer.
+int amgb_ipc_export_solution(amgb_ctx *c, unsigned char handle64[64])
+{
+   NEED_READY(c);
+   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+   cudaIpcMemHandle_t h;
+   CUDA_OK(c, cudaIpcGetMemHandle(&h, c->u));
+   memcpy(handle64, &h, 64);
+   return AMGB_OK;
+}
+
+int amgb_ipc_open_peers(amgb_ctx *c, int npeers, const unsigned char *handles)
+{
+   NEED_READY(c);
+   if (npeers < 0 || npeers > AMGB_MAX_PEERS || (npeers > 0 && !handles)) return amgb_fail(c, AMGB_EINVAL, "bad peer list");
+   for (int p = 0; p < npeers; p++) {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, handles + 64 * (size_t)p, 64);
+      void *ptr = nullptr;
+      CUDA_OK(c, cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+      c->peer_u.push_back((double *)ptr);
+   }
+   return AMGB_OK;
+}
+
+int amgb_async_dist_correct(amgb_ctx *c, int level)
+{
+   NEED_READY(c);
+   const int L = c->L, n0 = c->A[0].nrows;
+   if (level < 0 || level >= L) return amgb_fail(c, AMGB_EINVAL, "bad level");
+   const amgb_options &o = c->opt;
+   if (o.solver != AMGB_SOLVER_MULTADD || (o.smoother != AMGB_SMOOTH_JACOBI && o.smoother != AMGB_SMOOTH_L1_JACOBI))
+      return amgb_fail(c, AMGB_EINVAL, "the cross-GPU asynchronous solve runs Multadd with (L1-)Jacobi smoothing");
+   if (level == L - 1 && L > 1) return AMGB_OK;           // SMEM convention: the coarsest level contributes nothing
+   double *ul = c->u_outer;                                // private copy of the solution (level_vector[k].u)
+   CUDA_OK(c, cudaMemcpyAsync(ul, c->u, sizeof(double) * n0, cudaMemcpyDeviceToDevice, c->stream));
+   enq_spmv(c, c->A[0], false, ul, c->r[0], epi(-1.0, 1.0, c->f), false);
+   for (int l = 0; l < level; l++) enq_spmv(c, c->R[l], false, c->r[l], c->r[l + 1], epi(1.0, 0.0, nullptr), false);
+   enq_smooth_zero(c, level, c->r[level], c->e[level], o.num_fine_smooth_sweeps, c->symmetric, false, c->t[level], c->w[level]);
+   for (int l = level - 1; l >= 0; l--) enq_spmv(c, c->P[l], false, c->e[l + 1], c->e[l], epi(1.0, 0.0, nullptr), false);
+   PeerPtrs pp;
+   pp.n = (int)c->peer_u.size();
+   for (int p = 0; p < pp.n; p++) pp.p[p] = c->peer_u[p];
+   c->launches += launch_push_correction(c->cfg, c->stream, n0, c->e[0], c->u, pp);
+   CUDA_OK(c, cudaGetLastError());
+   return AMGB_OK;
+}
+
+// ||f - A_0 u||_2 of the resident vectors (waits for everything enqueued on the context's stream)
+int amgb_residual_norm(amgb_ctx *c, double *norm)
+{
+   NEED_READY(c);
+   if (!norm) return amgb_fail(c, AMGB_EINVAL, "null output");
+   enq_residual(c);
+   double ss;
+   int rc = amgb_fetch_scalar(c, &ss);
+   if (rc) return rc;
+   *norm = sqrt(ss);
+   return AMGB_OK;
+}
+
+int amgb_stream_synchronize(amgb_ctx *c)
+{
+   NEED_READY(c);
+   CUDA_OK(c, cudaStreamSynchronize(c->stream));
    return AMGB_OK;
 }
 

@@ -54,6 +54,8 @@ struct amgb_ctx {
    std::vector<int> async_cta_begin;
    // distributed
    DistState *dist = nullptr;
+   // asynchronous solve across GPUs: IPC-mapped solution vectors of the peer ranks (fp64 reductions over NVLink)
+   std::vector<double *> peer_u;
    char err[512] = {0};
 };
 

@@ -97,6 +97,18 @@ __global__ void __launch_bounds__(kBlock) k_dot(int n, const double *__restrict_
    if (threadIdx.x == 0) partials[blockIdx.x] = s;
 }
 
+// u += e on this GPU and on every peer GPU (their u mapped through CUDA IPC): the `#pragma omp atomic` of
+// src/SMEM_Async_AMG.cpp:297 / the accumulate-on-receive of src/DMEM_Comm.cpp:267-330 as fire-and-forget
+// red.global.add.f64 over NVLink -- no message queues, no in-flight accounting, nobody waits for anybody
+__global__ void __launch_bounds__(kBlock) k_push_correction(int n, const double *__restrict__ e, double *u, PeerPtrs peers)
+{
+   for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+      const double v = e[i];
+      red_add_f64(u + i, v);
+      for (int p = 0; p < peers.n; p++) red_add_f64(peers.p[p] + i, v);
+   }
+}
+
 __global__ void __launch_bounds__(kBlock) k_hybrid_jgs(DevCSR A, const double *f, double *u, const double *u_prev,
                                                         const double *scale, int B, int zero_guess)
 {
@@ -310,6 +322,12 @@ int launch_dot(const LaunchCfg &cfg, cudaStream_t st, int n, const double *x, co
    int grid = grid_for(cfg, n);
    if (grid_out) *grid_out = grid;
    k_dot<<<grid, kBlock, 0, st>>>(n, x, y, partials);
+   return 1;
+}
+
+int launch_push_correction(const LaunchCfg &cfg, cudaStream_t st, int n, const double *e, double *u, const PeerPtrs &peers)
+{
+   k_push_correction<<<grid_for(cfg, n), kBlock, 0, st>>>(n, e, u, peers);
    return 1;
 }
 

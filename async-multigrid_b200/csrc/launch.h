@@ -41,6 +41,10 @@ int launch_cheby(const LaunchCfg &cfg, cudaStream_t st, int n, double omega, dou
 // y = a*x + b*y [, z = y]; partial sums of x_i*y_i
 int launch_axpby(const LaunchCfg &cfg, cudaStream_t st, int n, double a, const double *x, double b, double *y, double *z);
 int launch_dot(const LaunchCfg &cfg, cudaStream_t st, int n, const double *x, const double *y, double *partials, int *grid_out);
+// u += e here and on every peer GPU (IPC-mapped pointers)
+#define AMGB_MAX_PEERS 15
+struct PeerPtrs { double *p[AMGB_MAX_PEERS]; int n; };
+int launch_push_correction(const LaunchCfg &cfg, cudaStream_t st, int n, const double *e, double *u, const PeerPtrs &peers);
 // partial sums of x_i^2
 int launch_sumsq(const LaunchCfg &cfg, cudaStream_t st, int n, const double *x, double *partials, int *grid_out);
 // hybrid JGS sweep

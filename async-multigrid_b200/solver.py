@@ -27,6 +27,7 @@ ABI_SYMBOLS = [
     "amgb_smem_solve", "amgb_time_residual", "amgb_level_storage", "amgb_time_spmv", "amgb_stream_stats", "amgb_l2_arena_bytes",
     "amgb_dist_unique_id", "amgb_dist_init", "amgb_dist_set_level", "amgb_dist_setup", "amgb_dist_set_rhs",
     "amgb_dist_get_solution", "amgb_dist_solve_sync", "amgb_dist_stats",
+    "amgb_ipc_export_solution", "amgb_ipc_open_peers", "amgb_async_dist_correct", "amgb_residual_norm", "amgb_stream_synchronize",
 ]
 
 
@@ -81,6 +82,11 @@ def load_library():
     L.amgb_stream_stats.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     L.amgb_l2_arena_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     L.amgb_async_groups.argtypes = [C.c_void_p, IP, IP]
+    L.amgb_ipc_export_solution.argtypes = [C.c_void_p, C.c_char_p]
+    L.amgb_ipc_open_peers.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
+    L.amgb_async_dist_correct.argtypes = [C.c_void_p, C.c_int]
+    L.amgb_residual_norm.argtypes = [C.c_void_p, DP]
+    L.amgb_stream_synchronize.argtypes = [C.c_void_p]
     L.amgb_dist_unique_id.argtypes = [C.c_char_p]
     L.amgb_dist_init.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
     L.amgb_dist_set_level.argtypes = [C.c_void_p] + [C.c_int] * 9 + [IP]
@@ -254,6 +260,28 @@ class Solver:
         self._ck(self.L.amgb_smem_solve(self.ctx, _dp(f), _dp(u), tol, num_cycles, _dp(hist), C.byref(n), _ip(corr),
                                         C.byref(rel), C.byref(secs)))
         return dict(u=u, hist=hist[:n.value + 1], cycles=n.value, corrections=corr, relres=rel.value, seconds=secs.value)
+
+    # -- asynchronous solve across GPUs (a GPU plays one grid's rank group of DMEM_Add) ------------------
+    def ipc_export_solution(self):
+        buf = C.create_string_buffer(64)
+        self._ck(self.L.amgb_ipc_export_solution(self.ctx, buf))
+        return buf.raw
+
+    def ipc_open_peers(self, handles):
+        """handles: list of 64-byte IPC handles of the OTHER ranks' solution vectors"""
+        blob = b"".join(handles)
+        self._ck(self.L.amgb_ipc_open_peers(self.ctx, len(handles), blob if handles else None))
+
+    def async_dist_correct(self, level):
+        self._ck(self.L.amgb_async_dist_correct(self.ctx, level))
+
+    def residual_norm(self):
+        v = C.c_double(0)
+        self._ck(self.L.amgb_residual_norm(self.ctx, C.byref(v)))
+        return v.value
+
+    def synchronize(self):
+        self._ck(self.L.amgb_stream_synchronize(self.ctx))
 
     # -- introspection --------------------------------------------------------------------------------
     def launch_count(self):

@@ -134,6 +134,8 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
     if world > 1:
         from async_multigrid_b200 import dist_bench
+        if args.solver == "async_multadd":
+            return dist_bench.run_async(args, rank, world, local)     # BASELINE.json configs[4]: asynchronous across GPUs
         return dist_bench.run(args, rank, world, local)
     torch.cuda.set_device(local)
     peak, peak_src = load_peaks()

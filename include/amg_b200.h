@@ -171,6 +171,22 @@ int amgb_dist_solve_sync(amgb_ctx *ctx, double tol, int max_cycles, double *relr
                          double *solve_seconds);
 int amgb_dist_stats(amgb_ctx *ctx, long long *halo_bytes_sent, long long *nccl_ops);
 
+/* ---- asynchronous additive solve across GPUs (DMEM async Multadd; one process per GPU) --------------------------
+ * The reference assigns ranks to grids (src/DMEM_Setup.cpp:1638-1759): every grid's rank group holds the hierarchy
+ * down to its level and full-length fine vectors, runs its own chain on a private residual and sends fine-level
+ * corrections to the other grids, which accumulate them on arrival (src/DMEM_Add.cpp:101-130,391-458;
+ * src/DMEM_Comm.cpp:267-330).  Here a GPU plays a grid's rank group; every context holds the whole hierarchy
+ * (amgb_set_matrix as for one GPU) and the same f.  amgb_ipc_export_solution / amgb_ipc_open_peers map the peers'
+ * solution vectors through CUDA IPC; amgb_async_dist_correct(level) enqueues ONE correction of `level`: private copy
+ * of u, r = f - A_0 u, restrict chain, smooth, prolong chain, then u += e on this GPU and on every peer with fp64
+ * reductions over NVLink.  No call ever waits for a peer.  amgb_residual_norm = ||f - A_0 u||_2 (synchronises the
+ * context's stream). */
+int amgb_ipc_export_solution(amgb_ctx *ctx, unsigned char handle64[64]);
+int amgb_ipc_open_peers(amgb_ctx *ctx, int npeers, const unsigned char *handles /* npeers x 64 bytes */);
+int amgb_async_dist_correct(amgb_ctx *ctx, int level);
+int amgb_residual_norm(amgb_ctx *ctx, double *norm);
+int amgb_stream_synchronize(amgb_ctx *ctx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -89,3 +89,88 @@ def test_two_gpus_match_global_oracle():
         assert len(hist) == len(want) and np.max(np.abs(hist - want)) <= HIST_TOL
     true = O.norm2(O.spgemv(h.A[0], u, b, -1.0, 1.0)) / O.norm2(b)
     assert abs(true - want[-1]) <= 1e-11
+
+
+# ---- asynchronous solve across GPUs: a GPU plays one grid's rank group of DMEM_Add -----------------------------
+def test_async_dist_single_gpu_equals_sequential_model():
+    """with one GPU the level corrections are applied one after the other, each from the fresh residual: exactly the
+    oracle's sequential model of the asynchronous additive iteration"""
+    w = 0.9
+    h, b = _setup("7pt", 16, w)
+    s = amg.Solver(h, H.MULTADD, H.JACOBI, w)
+    s.set_rhs(b)
+    s.set_solution(None)
+    s.ipc_open_peers([])
+    cycles = 12
+    for _ in range(cycles):
+        for q in range(h.num_levels):
+            s.async_dist_correct(q)
+    rel = s.residual_norm() / O.norm2(b)
+    u_want, counts, rel_want = O.Problem(h, H.MULTADD, H.JACOBI, w).solve_async_sequential(b, cycles)
+    u = s.get_solution()
+    assert np.max(np.abs(u - u_want)) <= 1e-11 * np.max(np.abs(u_want))
+    assert abs(rel - rel_want) <= 1e-10
+    s.close()
+
+
+def _async_worker(rank, world, q_in, q_out, q_res):
+    sys.path.insert(0, ROOT)
+    import async_multigrid_b200 as amg2
+    from async_multigrid_b200 import hierarchy as H2
+    w = 0.9
+    A = H2.laplacian("7pt", 24)
+    h = H2.amg_setup(A)
+    h.build_transfers(H2.MULTADD, w)
+    b = H2.rand_rhs(A.nrows)
+    s = amg2.Solver(h, H2.MULTADD, H2.JACOBI, w, device=rank)
+    s.set_rhs(b)
+    s.set_solution(None)
+    q_out.put((rank, s.ipc_export_solution()))
+    handles = q_in.get(timeout=120)                      # the other ranks' handles, from the parent
+    s.ipc_open_peers(handles)
+    q_out.put((rank, "ready"))
+    assert q_in.get(timeout=120) == "go"
+    levels = [q for q in range(h.num_levels - 1) if q % world == rank]
+    for _ in range(80):
+        for q in levels:
+            s.async_dist_correct(q)
+    s.synchronize()
+    q_out.put((rank, "done"))
+    assert q_in.get(timeout=120) == "all done"            # every peer's reductions have landed
+    q_res.put((rank, s.residual_norm(), s.get_solution(), levels))
+    assert q_in.get(timeout=120) == "close"
+    s.close()
+
+
+def test_async_dist_two_gpus_converge():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    world = 2
+    q_in = [ctx.Queue() for _ in range(world)]
+    q_out, q_res = ctx.Queue(), ctx.Queue()
+    procs = [ctx.Process(target=_async_worker, args=(r, world, q_in[r], q_out, q_res)) for r in range(world)]
+    for p in procs:
+        p.start()
+    handles = dict(q_out.get(timeout=300) for _ in range(world))
+    for r in range(world):
+        q_in[r].put([handles[o] for o in range(world) if o != r])
+    for phase, reply in (("ready", "go"), ("done", "all done")):
+        got = [q_out.get(timeout=300) for _ in range(world)]
+        assert all(g[1] == phase for g in got)
+        for r in range(world):
+            q_in[r].put(reply)
+    res = sorted([q_res.get(timeout=300) for _ in range(world)], key=lambda x: x[0])
+    for r in range(world):
+        q_in[r].put("close")
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    h, b = _setup("7pt", 24, 0.9)
+    assert sorted(res[0][3] + res[1][3]) == list(range(h.num_levels - 1))       # every working level has an owner
+    assert np.array_equal(res[0][2], res[1][2]) or np.max(np.abs(res[0][2] - res[1][2])) <= 1e-12    # the same u everywhere
+    true = O.norm2(O.spgemv(h.A[0], res[0][2], b, -1.0, 1.0)) / O.norm2(b)
+    assert true < 1e-9, true
+    assert abs(res[0][1] / O.norm2(b) - true) <= 1e-12
