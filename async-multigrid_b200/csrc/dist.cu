@@ -192,8 +192,9 @@ static int dist_cycle(amgb_ctx *c)
    const int L = c->L;
    int rc;
    if (L == 1) return AMGB_OK;
+   const bool bpx = c->opt.solver == AMGB_SOLVER_BPX;                   // SYNC_BPX of DMEM_SyncAddCycle (src/DMEM_Mult.cpp:346-349)
    const bool direct = c->opt.coarse_solve && c->Ainv.rp != nullptr;   // DMEM: direct solve on the (replicated) coarsest level
-   const int top = direct ? L : L - 1;                                  // levels that contribute a correction
+   const int top = (direct || bpx) ? L : L - 1;                         // levels that contribute a correction
    for (int l = 0; l < top - 1; l++) {
       const DistLevel &nx = d->lv[l + 1];
       const bool gather = d->lv[l].distributed && !nx.distributed;
@@ -201,9 +202,9 @@ static int dist_cycle(amgb_ctx *c)
       if ((rc = dist_spmv(c, c->R[l], false, l, d->r[l], out, epi(1.0, 0.0, nullptr), false))) return rc;
       if (gather && (rc = allgather_level(c, l + 1, d->r[l + 1]))) return rc;
    }
-   if (!direct && (rc = halo(c, L - 2, d->r[L - 2]))) return rc;
+   if (top == L - 1 && (rc = halo(c, L - 2, d->r[L - 2]))) return rc;
    if (direct) enq_spmv(c, c->Ainv, false, d->r[L - 1], d->e[L - 1], epi(1.0, 0.0, nullptr), false);
-   for (int l = 0; l < L - 1; l++) {
+   for (int l = 0; l < (direct ? L - 1 : top); l++) {
       const DistLevel &lv = d->lv[l];
       const double *rown = d->r[l] + lv.off();
       const double *ws = d->ws[l] + lv.off();
@@ -296,8 +297,10 @@ int amgb_dist_setup(amgb_ctx *c)
    if (d->ready) return amgb_fail(c, AMGB_ESTATE, "amgb_dist_setup already done");
    const int L = c->L;
    const amgb_options &o = c->opt;
-   if (o.solver != AMGB_SOLVER_MULTADD || o.smoother != AMGB_SMOOTH_JACOBI)
-      return amgb_fail(c, AMGB_EINVAL, "the distributed path implements synchronous Multadd with (symmetrised) weighted Jacobi");
+   if ((o.solver != AMGB_SOLVER_MULTADD && o.solver != AMGB_SOLVER_BPX) || o.smoother != AMGB_SMOOTH_JACOBI)
+      return amgb_fail(c, AMGB_EINVAL, "the partitioned path implements synchronous Multadd and BPX with weighted Jacobi");
+   if (o.solver == AMGB_SOLVER_BPX && o.num_pre_smooth_sweeps != 1)
+      return amgb_fail(c, AMGB_EINVAL, "partitioned BPX runs one Jacobi sweep per level");
    if ((int)d->lv.size() != L) return amgb_fail(c, AMGB_ESTATE, "level layouts missing");
    int rc;
    for (int l = 0; l < L; l++) {

@@ -334,7 +334,7 @@ class DistSolver:
     partition.RankPlan; `uid` the 128-byte id from dist_unique_id() of rank 0."""
 
     def __init__(self, plan, uid, smooth_weight=1.0, num_pre=1, num_post=1, use_sell=True, use_stream=True,
-                 coarse_solve=False, device=0):
+                 coarse_solve=False, solver=H.MULTADD, device=0):
         self.L = load_library()
         self.plan = plan
         self.ctx = C.c_void_p()
@@ -344,7 +344,7 @@ class DistSolver:
         self._ck(self.L.amgb_dist_init(self.ctx, uid, plan.rank, plan.nranks))
         o = Options()
         self.L.amgb_default_options(C.byref(o))
-        o.solver, o.smoother, o.smooth_weight = H.MULTADD, H.JACOBI, smooth_weight
+        o.solver, o.smoother, o.smooth_weight = solver, H.JACOBI, smooth_weight
         o.num_pre_smooth_sweeps, o.num_post_smooth_sweeps = num_pre, num_post
         o.use_sell, o.use_stream = int(use_sell), int(use_stream)
         o.coarse_solve = int(coarse_solve)

@@ -41,6 +41,22 @@ def test_single_rank_communicator_matches_oracle(post, direct):
     s.close()
 
 
+def test_single_rank_bpx_matches_oracle():
+    """SYNC_BPX in the partitioned path (plain P, R = P^T, one Jacobi sweep on every level incl. the coarsest)"""
+    w = 0.6
+    A = H.laplacian("7pt", 16)
+    h = H.amg_setup(A)
+    h.build_transfers(H.BPX, w)
+    b = H.rand_rhs(A.nrows)
+    s = amg.DistSolver(PT.RankPlan(h, 1, 0), amg.solver.dist_unique_id(), w, solver=H.BPX)
+    s.set_rhs(b)
+    hist, _ = s.solve_sync(1e-30, 10)
+    _, want, _ = O.Problem(h, H.BPX, H.JACOBI, w).solve_sync(b, 1e-30, 10)
+    assert len(hist) == len(want)
+    assert np.max(np.abs(hist - want) / want) <= 1e-10        # BPX alone is not convergent: relative to the growing residual
+    s.close()
+
+
 def _worker(rank, world, port, uid_q, res_q):
     sys.path.insert(0, ROOT)
     import async_multigrid_b200 as amg2
