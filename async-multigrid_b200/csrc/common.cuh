@@ -63,11 +63,16 @@ struct DevCSR {
 // covers: MatVec (alpha=1), Residual (alpha=-1,beta=1,b=f), prolong-and-add (beta=1,b=y),
 // general Jacobi sweep (rs=w/d, alpha=-1, beta=1, b=f, gamma=1, c=u_prev),
 // symmetrised Jacobi from zero guess with M = A*diag(w/d) (rs=w/d, alpha=-1, beta=2, b=r).
+// optional extras (level-0 factorised transfers): a second vector inside the scaled bracket and the input's own
+// entry outside it:  y_i = gamma*c_i + rs_i*(beta*b_i + beta2*b2_i + alpha*sum_j M_ij x_j) + xself*xs_i
 struct SpmvEpilogue {
    double alpha, beta, gamma;
    const double *b;
    const double *c;
    const double *rs;
+   double beta2 = 0.0, xself = 0.0;
+   const double *b2 = nullptr;
+   const double *xs = nullptr;
 };
 
 __device__ __forceinline__ double ld_stream(const double *p)
@@ -177,13 +182,15 @@ __device__ __forceinline__ double epilogue_apply(const SpmvEpilogue &e, int row,
 {
    double t = e.alpha * ax;
    if (e.b) t += e.beta * (RO ? e.b[row] : ld_cg(e.b + row));
+   if (e.b2) t += e.beta2 * (RO ? e.b2[row] : ld_cg(e.b2 + row));
    if (e.rs) t *= __ldg(e.rs + row);
    if (e.c) t += e.gamma * (RO ? e.c[row] : ld_cg(e.c + row));
+   if (e.xs) t += e.xself * (RO ? e.xs[row] : ld_cg(e.xs + row));
    return t;
 }
 
 // epilogue with the row operands loaded ahead of the reduction (latency off the critical path)
-struct EpiOps { double b, c, rs; };
+struct EpiOps { double b, c, rs, b2 = 0.0, xs = 0.0; };
 template <bool RO>
 __device__ __forceinline__ EpiOps epilogue_load(const SpmvEpilogue &e, int row)
 {
@@ -191,14 +198,18 @@ __device__ __forceinline__ EpiOps epilogue_load(const SpmvEpilogue &e, int row)
    o.b = e.b ? (RO ? e.b[row] : ld_cg(e.b + row)) : 0.0;
    o.rs = e.rs ? __ldg(e.rs + row) : 1.0;
    o.c = e.c ? (RO ? e.c[row] : ld_cg(e.c + row)) : 0.0;
+   o.b2 = e.b2 ? (RO ? e.b2[row] : ld_cg(e.b2 + row)) : 0.0;
+   o.xs = e.xs ? (RO ? e.xs[row] : ld_cg(e.xs + row)) : 0.0;
    return o;
 }
 __device__ __forceinline__ double epilogue_finish(const SpmvEpilogue &e, const EpiOps &o, double ax)
 {
    double t = e.alpha * ax;
    if (e.b) t += e.beta * o.b;
+   if (e.b2) t += e.beta2 * o.b2;
    if (e.rs) t *= o.rs;
    if (e.c) t += e.gamma * o.c;
+   if (e.xs) t += e.xself * o.xs;
    return t;
 }
 

@@ -91,6 +91,7 @@ void amgb_default_options(amgb_options *o)
    o->use_sell = 1;
    o->l2_persist = 1;
    o->use_stream = 1;
+   o->factor_level0 = 0;
    o->coarse_solve = 0;
    o->stream_variant = 8;
    o->sell_sigma = 128;
@@ -546,6 +547,9 @@ int amgb_setup(amgb_ctx *c)
    const bool multadd = o.solver == AMGB_SOLVER_MULTADD || o.solver == AMGB_SOLVER_ASYNC_MULTADD;
    c->symmetric = multadd && o.num_pre_smooth_sweeps > 0 && o.num_post_smooth_sweeps > 0 &&
                   (o.smoother == AMGB_SMOOTH_JACOBI || o.smoother == AMGB_SMOOTH_L1_JACOBI);
+   if (o.factor_level0 && !(o.solver == AMGB_SOLVER_MULTADD && c->symmetric))
+      return amgb_fail(c, AMGB_EINVAL, "factor_level0 applies to synchronous Multadd with the symmetrised (L1-)Jacobi smoother");
+   if (o.factor_level0 && c->dist) return amgb_fail(c, AMGB_EINVAL, "factor_level0 is not wired into the partitioned path");
    int rc;
    c->ws.assign(L, nullptr); c->dow.assign(L, nullptr); c->l1.assign(L, nullptr); c->inv_l1.assign(L, nullptr);
    c->r.assign(L, nullptr); c->e.assign(L, nullptr); c->t.assign(L, nullptr); c->w.assign(L, nullptr);
@@ -728,10 +732,21 @@ void enq_cycle(amgb_ctx *c, double *target, bool accumulate)
    // src/SMEM_Sync_AMG.cpp:475-490; the result is identical)
    const bool direct = o.coarse_solve && c->Ainv.rp != nullptr;   // DMEM convention: e_{L-1} = A_{L-1}^{-1} r_{L-1}
    const int last_r = (multadd && !direct) ? L - 2 : L - 1;   // SMEM Multadd never reads r_{L-1} (coarsest contributes 0)
-   for (int l = 0; l < last_r; l++) enq_spmv(c, c->R[l], false, c->r[l], c->r[l + 1], epi(1.0, 0.0, nullptr), false);
+   // level-0 transfers in factorised form (amgb_options.factor_level0): t_0 = r_0 - A_0 diag(w/d) r_0 serves both
+   // Rbar_0 r_0 = R_0 t_0 and the symmetrised smoother e_0 = (w/d) o (r_0 + t_0); on the way up
+   // u += e_0 + Pbar_0 e_1 = (w/d) o (r_0 + t_0 - A_0 v) + v with v = P_0 e_1.  Two passes over A_0 (sliced ELL, HBM
+   // speed) and two over the plain P_0 / R_0 replace A_0 + Pbar_0 + Rbar_0 (3.5x the entries of P_0, L1-bound).
+   const bool fact0 = o.factor_level0 && multadd && c->symmetric && last_r >= 1;
+   for (int l = 0; l < last_r; l++) {
+      if (fact0 && l == 0) {
+         enq_spmv(c, c->A[0], true, c->r[0], c->t[0], epi(-1.0, 1.0, c->r[0]), false);        // t_0
+         enq_spmv(c, c->R[0], false, c->t[0], c->r[1], epi(1.0, 0.0, nullptr), false);       // r_1 = R_0 t_0
+      } else enq_spmv(c, c->R[l], false, c->r[l], c->r[l + 1], epi(1.0, 0.0, nullptr), false);
+   }
    // per-level corrections e_l (levels are independent)
    const int top = (bpx || direct) ? L : L - 1;  // BPX also smooths the coarsest level (:217-236)
    for (int l = 0; l < top; l++) {
+      if (fact0 && l == 0) continue;                  // e_0 is folded into the last launch of the cycle
       if (direct && l == L - 1) enq_spmv(c, c->Ainv, false, c->r[l], c->e[l], epi(1.0, 0.0, nullptr), false);
       else if (multadd) enq_smooth_zero(c, l, c->r[l], c->e[l], o.num_fine_smooth_sweeps, c->symmetric, false, c->t[l], c->w[l]);
       else if (bpx) enq_smooth_zero(c, l, c->r[l], c->e[l], o.num_pre_smooth_sweeps, false, true, c->t[l], c->w[l]);
@@ -749,7 +764,15 @@ void enq_cycle(amgb_ctx *c, double *target, bool accumulate)
    // Horner prolongation: c = e_0 + P_0 (e_1 + P_1 (e_2 + ...)), same sum as the reference's
    // per-level prolongation chains (src/SEQ_AMG.cpp:213-233)
    for (int l = top - 2; l >= 1; l--) enq_spmv(c, c->P[l], false, c->e[l + 1], c->e[l], epi(1.0, 1.0, c->e[l]), false);
-   if (top >= 2) {
+   if (fact0) {
+      // v = P_0 e_1;  target = [target +] v + (w/d) o (r_0 + t_0 - A_0 v)
+      enq_spmv(c, c->P[0], false, c->e[1], c->w[0], epi(1.0, 0.0, nullptr), false);
+      const double *rs0 = (o.smoother == AMGB_SMOOTH_L1_JACOBI) ? c->inv_l1[0] : c->ws[0];
+      SpmvEpilogue fe = epi(-1.0, 1.0, c->r[0], 1.0, accumulate ? target : nullptr, rs0);
+      fe.b2 = c->t[0]; fe.beta2 = 1.0;
+      fe.xs = c->w[0]; fe.xself = 1.0;
+      enq_spmv(c, c->A[0], false, c->w[0], target, fe, false);
+   } else if (top >= 2) {
       // target = [target +] e_0 + P_0 e_1   (u += e fused into the last prolongation)
       enq_spmv(c, c->P[0], false, c->e[1], target, epi(1.0, 1.0, c->e[0], 1.0, accumulate ? target : nullptr), false);
    } else {

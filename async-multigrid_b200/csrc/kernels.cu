@@ -282,6 +282,8 @@ int launch_spmv_units(const LaunchCfg &cfg, cudaStream_t st, const DevCSR &M, in
       if (ev.b) ev.b += u0;
       if (ev.c) ev.c += u0;
       if (ev.rs) ev.rs += u0;
+      if (ev.b2) ev.b2 += u0;
+      if (ev.xs) ev.xs += u0;
    }
    return launch_spmv(cfg, st, V, use_sval, x, yv, ev, partials, grid_out);
 }

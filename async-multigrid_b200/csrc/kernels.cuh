@@ -187,7 +187,8 @@ __device__ __forceinline__ double stream_rows_team(const DevCSR &M, const double
          const int row_a = r0 + tid / lpr;
          const bool ok_a = row_a < r1;
          int s_a = 0, t_a = 0;
-         EpiOps o_a = {0.0, 0.0, 1.0};
+         EpiOps o_a;
+         o_a.b = 0.0; o_a.c = 0.0; o_a.rs = 1.0;
          if (ok_a) {
             s_a = __ldg(M.rp + row_a) - q0;
             t_a = __ldg(M.rp + row_a + 1) - q0;
@@ -314,7 +315,8 @@ __device__ __forceinline__ double warp_stream_rows_team(const DevCSR &M, const d
       const int row_a = r0 + lane / lpr;
       const bool ok_a = row_a < r1;
       int s_a = 0, t_a = 0;
-      EpiOps o_a = {0.0, 0.0, 1.0};
+      EpiOps o_a;
+         o_a.b = 0.0; o_a.c = 0.0; o_a.rs = 1.0;
       if (ok_a) {
          s_a = __ldg(M.rp + row_a) - p0;
          t_a = __ldg(M.rp + row_a + 1) - p0;

@@ -169,13 +169,14 @@ class Hierarchy:
         self.cpts = None      # cpts[l][j]: level-l index of coarse point j of level l+1 (row partitions follow it)
 
     def build_transfers(self, solver=MULTADD, smooth_weight=1.0, smooth_interp_type=JACOBI,
-                        num_pre=1, num_post=1):
+                        num_pre=1, num_post=1, factor_level0=False):
+        """factor_level0: leave P_0 / R_0 plain (amgb_options.factor_level0 applies the smoothing factors on the fly)"""
         L = host_lib()
         self.P, self.R = [], []
         self.smooth_weight = smooth_weight
         for l in range(self.num_levels - 1):
             a_c, p_c = self.A[l]._as_c(), self.P_plain[l]._as_c()
-            if solver in (MULTADD, ASYNC_MULTADD) and (num_pre > 0 or num_post > 0):
+            if solver in (MULTADD, ASYNC_MULTADD) and (num_pre > 0 or num_post > 0) and not (factor_level0 and l == 0):
                 pb, rb = _CSR(), _CSR()
                 kind = 0 if smooth_interp_type in (JACOBI, HYBRID_JACOBI_GAUSS_SEIDEL) else 1
                 L.amgh_smooth_transfer(C.byref(a_c), C.byref(p_c), kind, smooth_weight,
@@ -344,6 +345,20 @@ def bytes_sync_multadd_cycle(h, symmetric=True):
         tot += (bytes_spmv(h.A[l], False) + 8 * h.n[l]) if symmetric else 24 * h.n[l]
         tot += bytes_spmv(h.P[l], True)
     tot += 8 * h.n[0]
+    return tot
+
+
+def bytes_sync_multadd_cycle_factored(h):
+    """the same cycle with the level-0 transfers in factorised form (amgb_options.factor_level0; h.P[0] / h.R[0] plain):
+    residual on A_0, t_0 pass on A_0 (reads r_0, writes t_0), R_0, P_0, final pass on A_0 (reads v, r_0, t_0, w/d, u; writes u)"""
+    L = h.num_levels
+    n0 = h.n[0]
+    tot = bytes_spmv(h.A[0], True)                                  # r = f - A u
+    tot += bytes_spmv(h.A[0], True)                                 # t_0 = r_0 - A_0 diag(w/d) r_0
+    tot += bytes_spmv(h.R[0], False) + bytes_spmv(h.P[0], False)    # plain transfers
+    tot += bytes_spmv(h.A[0], True) + 3 * 8 * n0                    # u += v + (w/d) o (r_0 + t_0 - A_0 v): extra reads t_0, w/d, u
+    for l in range(1, L - 1):                                       # coarser levels as in bytes_sync_multadd_cycle
+        tot += bytes_spmv(h.R[l], False) + bytes_spmv(h.A[l], False) + 8 * h.n[l] + bytes_spmv(h.P[l], True)
     return tot
 
 

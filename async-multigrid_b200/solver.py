@@ -36,7 +36,7 @@ class Options(C.Structure):
                 ("num_pre_smooth_sweeps", C.c_int), ("num_post_smooth_sweeps", C.c_int),
                 ("num_fine_smooth_sweeps", C.c_int), ("num_coarse_smooth_sweeps", C.c_int),
                 ("jgs_block_rows", C.c_int), ("use_sell", C.c_int), ("l2_persist", C.c_int), ("use_stream", C.c_int),
-                ("coarse_solve", C.c_int), ("sell_sigma", C.c_int), ("stream_variant", C.c_int)]
+                ("factor_level0", C.c_int), ("coarse_solve", C.c_int), ("sell_sigma", C.c_int), ("stream_variant", C.c_int)]
 
 
 _lib = None
@@ -117,7 +117,7 @@ class Solver:
 
     def __init__(self, h, solver=H.MULTADD, smoother=H.JACOBI, smooth_weight=1.0, num_pre=1, num_post=1,
                  fine_sweeps=1, coarse_sweeps=1, jgs_block_rows=8, use_sell=True, l2_persist=True, use_stream=True,
-                 stream_variant=None, sell_sigma=None, coarse_solve=False, device=0):
+                 stream_variant=None, sell_sigma=None, coarse_solve=False, factor_level0=False, device=0):
         self.L = load_library()
         self.h = h
         self.ctx = C.c_void_p()
@@ -132,6 +132,7 @@ class Solver:
         o.jgs_block_rows, o.use_sell, o.l2_persist = jgs_block_rows, int(use_sell), int(l2_persist)
         o.use_stream = int(use_stream)
         o.coarse_solve = int(coarse_solve)
+        o.factor_level0 = int(factor_level0)
         if stream_variant is not None:
             o.stream_variant = int(stream_variant)
         elif "AMGB_STREAM_VARIANT" in os.environ:

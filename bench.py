@@ -101,6 +101,12 @@ SOLVERS = {"mult": 0, "multadd": 2, "afacx": 1, "bpx": 3, "async_multadd": 6, "a
 SMOOTHERS = {"j": 0, "hybrid_jgs": 2, "L1j": 6}
 
 
+def factor_level0(args):
+    """level-0 transfers in factorised form (amgb_options.factor_level0): synchronous Multadd, symmetrised Jacobi, one GPU"""
+    return (not args.no_factor_level0 and args.solver == "multadd" and args.smoother in ("j", "L1j") and args.num_post > 0
+            and args.impl == "b200" and int(os.environ.get("WORLD_SIZE", "1")) == 1)
+
+
 def build_problem(args, H):
     t0 = time.time()
     A = H.laplacian(args.problem, args.n, args.n, args.nz or args.n)
@@ -109,7 +115,7 @@ def build_problem(args, H):
     base = H.MULTADD if sv in (H.MULTADD, H.ASYNC_MULTADD) else sv
     if sv == H.ASYNC_AFACX:
         base = H.AFACX
-    h.build_transfers(base, args.smooth_weight, num_pre=1, num_post=args.num_post)
+    h.build_transfers(base, args.smooth_weight, num_pre=1, num_post=args.num_post, factor_level0=factor_level0(args))
     b = H.rand_rhs(A.nrows)
     log("[bench] hierarchy: %d levels, n=%s, nnz(A)=%s, opcx=%.2f, host setup %.1fs" %
         (h.num_levels, h.n, [a.nnz for a in h.A], h.operator_complexity(), time.time() - t0))
@@ -142,9 +148,10 @@ def run_b200(args):
     h, b = build_problem(args, H)
     sv, sm = SOLVERS[args.solver], SMOOTHERS[args.smoother]
     is_async = sv in (H.ASYNC_MULTADD, H.ASYNC_AFACX)
+    fact0 = factor_level0(args)
     t0 = time.time()
     s = amg.Solver(h, sv, sm, args.smooth_weight, num_pre=1, num_post=args.num_post, jgs_block_rows=args.jgs_block_rows,
-                   use_sell=not args.no_sell)
+                   use_sell=not args.no_sell, factor_level0=factor_level0(args))
     log("[bench] upload + device setup %.1fs" % (time.time() - t0))
     f_t, f_host = pinned(h.n[0])
     u_t, u_host = pinned(h.n[0])
@@ -220,7 +227,7 @@ def run_b200(args):
     if is_async:
         cyc_bytes = sum(H.bytes_async_chain(h, k, symmetric) for k in range(h.num_levels))
     else:
-        cyc_bytes = H.bytes_sync_multadd_cycle(h, symmetric)
+        cyc_bytes = H.bytes_sync_multadd_cycle_factored(h) if fact0 else H.bytes_sync_multadd_cycle(h, symmetric)
     solve_bytes = cyc_bytes * cycles
     true_rel = float(out["relres"])
     line = {
@@ -252,6 +259,11 @@ def run_b200(args):
         used, cap = s.l2_arena_bytes()
         line["config"]["l2_persisting_window_bytes"] = int(used)
     s.close()
+    line["config"]["level0_transfers"] = ("factorised: plain P_0 / R_0, smoothing factors applied on the fly (amgb_options.factor_level0); "
+                                          "bytes_per_cycle counts that form") if fact0 else "explicit Pbar_0 / Rbar_0"
+    if fact0 and ((not args.no_async and sv == H.MULTADD) or not args.no_cpu_baseline):
+        # the asynchronous solver and the reference's own code take the explicit products (src/SMEM_Setup.cpp:1173-1254)
+        h.build_transfers(H.MULTADD, args.smooth_weight, num_pre=1, num_post=args.num_post)
     if not is_async and not args.no_async and sv == H.MULTADD:
         # the asynchronous member of BASELINE.json configs[1] on the same problem (persistent cooperative kernel),
         # reported beside the synchronous headline: smallest correction count (multiple of 5) that reaches 1e-9
@@ -387,6 +399,8 @@ def main():
                     help="multi-GPU: levels with fewer owned rows per rank are replicated, not partitioned")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-async", action="store_true", help="skip the asynchronous solve reported beside the headline")
+    ap.add_argument("--no-factor-level0", action="store_true",
+                    help="upload the explicit products Pbar_0 / Rbar_0 instead of applying the level-0 smoothing factors on the fly")
     ap.add_argument("--cpu-port", action="store_true", help="time the oracle port instead of oracle/_ref")
     ap.add_argument("--cpu-sample-cycles", type=int, default=3)
     ap.add_argument("--cpu-threads", type=int, default=0)

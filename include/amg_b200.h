@@ -53,6 +53,10 @@ typedef struct {
    int l2_persist;              /* 1: pin the coarse hierarchy in L2 with an access-policy window */
    int use_stream;              /* 1: CSR-stream kernel (row blocks staged through shared memory with 128-bit
                                    loads) for every matrix not stored as sliced ELL; 0: vector-per-row CSR */
+   int factor_level0;           /* 1 (synchronous Multadd with the symmetrised smoother only): P_0 / R_0 are uploaded PLAIN and the
+                                   smoothing factors are applied on the fly, Pbar_0 e = (I - w D^-1 A_0)(P_0 e), Rbar_0 r = R_0 (r - w A_0 D^-1 r):
+                                   the level-0 smoother and Rbar_0 then share ONE pass over A_0.  Same operator, rounding-level
+                                   differences; the explicit products (src/SMEM_Setup.cpp:1173-1254) are what 0 uses */
    int coarse_solve;            /* 0: SMEM convention, the coarsest level contributes nothing to Multadd/AFACx (the reference's
                                    hypre_GaussElimSolve result is never used there); 1: DMEM convention, direct solve
                                    on the coarsest level (src/DMEM_Add.cpp:262-264, src/DMEM_Mult.cpp:393) applied as a dense inverse */
