@@ -549,7 +549,6 @@ int amgb_setup(amgb_ctx *c)
                   (o.smoother == AMGB_SMOOTH_JACOBI || o.smoother == AMGB_SMOOTH_L1_JACOBI);
    if (o.factor_level0 && !(o.solver == AMGB_SOLVER_MULTADD && c->symmetric))
       return amgb_fail(c, AMGB_EINVAL, "factor_level0 applies to synchronous Multadd with the symmetrised (L1-)Jacobi smoother");
-   if (o.factor_level0 && c->dist) return amgb_fail(c, AMGB_EINVAL, "factor_level0 is not wired into the partitioned path");
    int rc;
    c->ws.assign(L, nullptr); c->dow.assign(L, nullptr); c->l1.assign(L, nullptr); c->inv_l1.assign(L, nullptr);
    c->r.assign(L, nullptr); c->e.assign(L, nullptr); c->t.assign(L, nullptr); c->w.assign(L, nullptr);

@@ -39,6 +39,7 @@ struct DistState {
    std::vector<DistLevel> lv;
    std::vector<double *> ws, r, e;   // level layout
    double *u = nullptr, *f = nullptr;   // u: level-0 layout; f: owned rows
+   double *t0 = nullptr, *v0 = nullptr;  // level-0 layout: scratch of the factorised level-0 transfers (factor_level0)
    // halo exchange on its own stream, overlapped with the interior launch units of the SpMV that needs it
    cudaStream_t comm_stream = nullptr;
    cudaEvent_t ev_x = nullptr, ev_h = nullptr;
@@ -195,16 +196,24 @@ static int dist_cycle(amgb_ctx *c)
    const bool bpx = c->opt.solver == AMGB_SOLVER_BPX;                   // SYNC_BPX of DMEM_SyncAddCycle (src/DMEM_Mult.cpp:346-349)
    const bool direct = c->opt.coarse_solve && c->Ainv.rp != nullptr;   // DMEM: direct solve on the (replicated) coarsest level
    const int top = (direct || bpx) ? L : L - 1;                         // levels that contribute a correction
+   // level-0 transfers in factorised form (see enq_cycle in context.cu): plain P_0 / R_0 uploaded
+   const bool fact0 = c->opt.factor_level0 && c->symmetric && top >= 2;
+   const int off0 = d->lv[0].off();
    for (int l = 0; l < top - 1; l++) {
       const DistLevel &nx = d->lv[l + 1];
       const bool gather = d->lv[l].distributed && !nx.distributed;
       double *out = d->r[l + 1] + (gather ? nx.row_start : nx.off());
-      if ((rc = dist_spmv(c, c->R[l], false, l, d->r[l], out, epi(1.0, 0.0, nullptr), false))) return rc;
+      if (fact0 && l == 0) {
+         // t_0 = r_0 - A_0 diag(w/d) r_0 (ghosts of r_0), then r_1 = R_0 t_0 (ghosts of t_0)
+         if ((rc = dist_spmv(c, c->A[0], true, 0, d->r[0], d->t0 + off0, epi(-1.0, 1.0, d->r[0] + off0), false))) return rc;
+         if ((rc = dist_spmv(c, c->R[0], false, 0, d->t0, out, epi(1.0, 0.0, nullptr), false))) return rc;
+      } else if ((rc = dist_spmv(c, c->R[l], false, l, d->r[l], out, epi(1.0, 0.0, nullptr), false))) return rc;
       if (gather && (rc = allgather_level(c, l + 1, d->r[l + 1]))) return rc;
    }
    if (top == L - 1 && (rc = halo(c, L - 2, d->r[L - 2]))) return rc;
    if (direct) enq_spmv(c, c->Ainv, false, d->r[L - 1], d->e[L - 1], epi(1.0, 0.0, nullptr), false);
    for (int l = 0; l < (direct ? L - 1 : top); l++) {
+      if (fact0 && l == 0) continue;                  // e_0 is folded into the last launch of the cycle
       const DistLevel &lv = d->lv[l];
       const double *rown = d->r[l] + lv.off();
       const double *ws = d->ws[l] + lv.off();
@@ -218,7 +227,14 @@ static int dist_cycle(amgb_ctx *c)
       if ((rc = dist_spmv(c, c->P[l], false, l + 1, d->e[l + 1], eo, epi(1.0, 1.0, eo), false))) return rc;
    }
    double *uo = d->u + d->lv[0].off();
-   if (top >= 2) {
+   if (fact0) {
+      // v = P_0 e_1 (ghosts of e_1);  u += v + (w/d) o (r_0 + t_0 - A_0 v) (ghosts of v)
+      if ((rc = dist_spmv(c, c->P[0], false, 1, d->e[1], d->v0 + off0, epi(1.0, 0.0, nullptr), false))) return rc;
+      SpmvEpilogue fe = epi(-1.0, 1.0, d->r[0] + off0, 1.0, uo, d->ws[0] + off0);
+      fe.b2 = d->t0 + off0; fe.beta2 = 1.0;
+      fe.xs = d->v0 + off0; fe.xself = 1.0;
+      if ((rc = dist_spmv(c, c->A[0], false, 0, d->v0, uo, fe, false))) return rc;
+   } else if (top >= 2) {
       if ((rc = dist_spmv(c, c->P[0], false, 1, d->e[1], uo, epi(1.0, 1.0, d->e[0] + d->lv[0].off(), 1.0, uo), false))) return rc;
    } else {
       c->launches += launch_add(c->cfg, c->stream, c->A[0].nrows, d->e[0] + d->lv[0].off(), uo);
@@ -342,6 +358,10 @@ int amgb_dist_setup(amgb_ctx *c)
    CUDA_OK(c, cudaEventCreateWithFlags(&d->ev_h, cudaEventDisableTiming));
    if (const char *ov = getenv("AMGB_DIST_OVERLAP")) d->overlap = atoi(ov) != 0;
    if ((rc = amgb_dev_alloc_bytes(c, (void **)&d->u, sizeof(double) * (size_t)d->lv[0].n_ext(), true))) return rc;
+   if (c->opt.factor_level0) {
+      if ((rc = amgb_dev_alloc_bytes(c, (void **)&d->t0, sizeof(double) * (size_t)d->lv[0].n_ext(), true))) return rc;
+      if ((rc = amgb_dev_alloc_bytes(c, (void **)&d->v0, sizeof(double) * (size_t)d->lv[0].n_ext(), true))) return rc;
+   }
    if ((rc = amgb_dev_alloc_bytes(c, (void **)&d->f, sizeof(double) * (size_t)std::max(1, c->A[0].nrows), true))) return rc;
    CUDA_OK(c, cudaStreamSynchronize(c->stream));
    d->halo_bytes = 0; d->collectives = 0;

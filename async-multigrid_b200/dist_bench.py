@@ -65,6 +65,11 @@ class _PlanFromDisk:
         self.info = meta["info"]
 
 
+def _fact0(args):
+    """level-0 transfers in factorised form (amgb_options.factor_level0): symmetrised Jacobi only"""
+    return not getattr(args, "no_factor_level0", False) and args.num_post > 0
+
+
 def _build_and_scatter(args, world, d):
     """rank 0: global problem -> plan -> per-rank blocks on /dev/shm (freed level by level)"""
     t0 = time.time()
@@ -72,11 +77,13 @@ def _build_and_scatter(args, world, d):
     H.set_host_threads(os.cpu_count() or 1)      # the other ranks idle at the barrier meanwhile
     A = H.laplacian("7pt", n, n, n * world)
     h = H.amg_setup(A, theta=args.theta)
-    h.build_transfers(H.MULTADD, args.smooth_weight, num_pre=1, num_post=args.num_post)
+    fact0 = _fact0(args)
+    h.build_transfers(H.MULTADD, args.smooth_weight, num_pre=1, num_post=args.num_post, factor_level0=fact0)
     b = H.rand_rhs(A.nrows)
     info = {"levels": h.num_levels, "n": [int(x) for x in h.n], "nnz_A": [int(a.nnz) for a in h.A],
             "operator_complexity": round(h.operator_complexity(), 3),
-            "bytes_per_cycle": int(H.bytes_sync_multadd_cycle(h, args.num_post > 0)), "host_setup_s": round(time.time() - t0, 1)}
+            "bytes_per_cycle": int(H.bytes_sync_multadd_cycle_factored(h) if fact0 else H.bytes_sync_multadd_cycle(h, args.num_post > 0)),
+            "host_setup_s": round(time.time() - t0, 1)}
     _log("[bench] global hierarchy: %d levels, n=%s, host setup %.1fs" % (h.num_levels, h.n, time.time() - t0))
     starts, num_dist, halos = PT.plan_layouts(h, world, plane=n * n, min_rows_per_rank=args.min_rows_per_rank)
     layouts = [PT.rank_layouts(h, world, r, starts, num_dist, halos) for r in range(world)]
@@ -137,7 +144,8 @@ def run(args, rank, world, local):
     uid = [S.dist_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     t0 = time.time()
-    s = S.DistSolver(plan, uid[0], args.smooth_weight, num_pre=1, num_post=args.num_post, use_sell=not args.no_sell, device=local)
+    s = S.DistSolver(plan, uid[0], args.smooth_weight, num_pre=1, num_post=args.num_post, use_sell=not args.no_sell,
+                     factor_level0=_fact0(args), device=local)
     _log("[bench] rank %d: upload + device setup %.1fs, owned rows per level %s" % (rank, time.time() - t0, [x.n_owned for x in plan.layouts]))
     dist.barrier()
     if rank == 0:
@@ -196,7 +204,8 @@ def run(args, rank, world, local):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "3D 7-pt Laplacian %dx%dx%d (n=%d) in %d z-slabs of %d^3 rows, sync Multadd, smoother j w=%.2f, tol 1e-9"
                        % (args.n, args.n, args.n * world, n0, world, args.n, args.smooth_weight),
-                       "levels": info["levels"], "distributed_levels": plan.num_dist, "operator_complexity": info["operator_complexity"],
+                       "levels": info["levels"], "distributed_levels": plan.num_dist,
+                       "level0_transfers": "factorised (amgb_options.factor_level0)" if _fact0(args) else "explicit Pbar_0 / Rbar_0", "operator_complexity": info["operator_complexity"],
                        "cycles_to_tol": int(cycles), "final_relres": float(hist[-1]), "rows_per_s": n0 / solve_s,
                        "l2": "per-GPU inputs exceed the 126 MB L2; no explicit flush",
                        "exchange": "NCCL send/recv halo with row-neighbours per SpMV input, all-gather of the first replicated level, all-reduce of the norm",

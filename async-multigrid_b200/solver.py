@@ -335,7 +335,7 @@ class DistSolver:
     partition.RankPlan; `uid` the 128-byte id from dist_unique_id() of rank 0."""
 
     def __init__(self, plan, uid, smooth_weight=1.0, num_pre=1, num_post=1, use_sell=True, use_stream=True,
-                 coarse_solve=False, solver=H.MULTADD, device=0):
+                 coarse_solve=False, solver=H.MULTADD, factor_level0=False, device=0):
         self.L = load_library()
         self.plan = plan
         self.ctx = C.c_void_p()
@@ -349,6 +349,7 @@ class DistSolver:
         o.num_pre_smooth_sweeps, o.num_post_smooth_sweeps = num_pre, num_post
         o.use_sell, o.use_stream = int(use_sell), int(use_stream)
         o.coarse_solve = int(coarse_solve)
+        o.factor_level0 = int(factor_level0)
         self._ck(self.L.amgb_set_options(self.ctx, C.byref(o)))
         nl = plan.num_levels
         self._ck(self.L.amgb_set_num_levels(self.ctx, nl))

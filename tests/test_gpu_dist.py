@@ -41,6 +41,20 @@ def test_single_rank_communicator_matches_oracle(post, direct):
     s.close()
 
 
+def test_single_rank_factorised_level0_matches_oracle():
+    w = 0.9
+    h, b = _setup("7pt", 20, w)
+    _, want, _ = O.Problem(h, H.MULTADD, H.JACOBI, w).solve_sync(b, 1e-9, 100)       # explicit products
+    hf = H.Hierarchy(h.A, h.P_plain)
+    hf.cpts = h.cpts
+    hf.build_transfers(H.MULTADD, w, factor_level0=True)
+    s = amg.DistSolver(PT.RankPlan(hf, 1, 0), amg.solver.dist_unique_id(), w, factor_level0=True)
+    s.set_rhs(b)
+    hist, _ = s.solve_sync(1e-9, 100)
+    assert len(hist) == len(want) and np.max(np.abs(hist - want)) <= HIST_TOL
+    s.close()
+
+
 def test_single_rank_bpx_matches_oracle():
     """SYNC_BPX in the partitioned path (plain P, R = P^T, one Jacobi sweep on every level incl. the coarsest)"""
     w = 0.6
@@ -64,7 +78,7 @@ def _worker(rank, world, port, uid_q, res_q):
     w = 0.9
     A = H2.laplacian("7pt", 32)
     h = H2.amg_setup(A)
-    h.build_transfers(H2.MULTADD, w)
+    h.build_transfers(H2.MULTADD, w, factor_level0=True)      # plain P_0 / R_0: the factorised form adds two halo exchanges
     b = H2.rand_rhs(A.nrows)
     plan = PT2.RankPlan(h, world, rank, plane=32 * 32, min_rows_per_rank=256)
     if rank == 0:
@@ -73,7 +87,7 @@ def _worker(rank, world, port, uid_q, res_q):
             uid_q.put(uid)
     else:
         uid = uid_q.get(timeout=120)
-    s = amg2.DistSolver(plan, uid, w, device=rank)
+    s = amg2.DistSolver(plan, uid, w, factor_level0=True, device=rank)
     l0 = plan.layouts[0]
     s.set_rhs(b[l0.row_start:l0.row_start + l0.n_owned])
     hist, secs = s.solve_sync(1e-9, 100)

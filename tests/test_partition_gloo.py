@@ -122,7 +122,7 @@ def test_bench_plan_roundtrip_through_disk(tmp_path):
     DB._build_and_scatter(args, world, d)
     A = H.laplacian("7pt", 12, 12, 12 * world)
     h = H.amg_setup(A)
-    h.build_transfers(H.MULTADD, 0.9)
+    h.build_transfers(H.MULTADD, 0.9, factor_level0=True)      # the bench's multi-GPU leg uploads plain P_0 / R_0
     b = H.rand_rhs(A.nrows)
     for rank in range(world):
         got = DB._PlanFromDisk(d, rank, world)
