@@ -367,6 +367,12 @@ static int async_prepare(amgb_ctx *c)
    return AMGB_OK;
 }
 
+void amgb_async_teardown(amgb_ctx *c)
+{
+   delete c->async_host;
+   c->async_host = nullptr;
+}
+
 extern "C" int amgb_solve_async(amgb_ctx *c, int num_cycles, int converge_type, int *corrections, double *relres,
                                 double *solve_seconds)
 {

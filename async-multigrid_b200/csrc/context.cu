@@ -143,6 +143,7 @@ int amgb_destroy(amgb_ctx *c)
    cudaStreamSynchronize(c->stream);
    amgb_dist_teardown(c);
    for (double *p : c->peer_u) cudaIpcCloseMemHandle(p);
+   amgb_async_teardown(c);
    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
    for (void *p : c->allocs) cudaFree(p);
    if (c->h_scalars) cudaFreeHost(c->h_scalars);

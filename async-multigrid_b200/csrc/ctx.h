@@ -64,6 +64,7 @@ int amgb_fail(amgb_ctx *c, int code, const char *fmt, ...);
 // input vector is not partitioned (nothing to overlap)
 bool amgb_dist_owned_cols(const amgb_ctx *c, int kind, int level, int *c0, int *c1);
 void amgb_dist_teardown(amgb_ctx *c);
+void amgb_async_teardown(amgb_ctx *c);   // frees the host copy of the persistent kernel's parameter block
 int amgb_dist_diag_offset(const amgb_ctx *c, int level);          // position of the diagonal in a local row block
 bool amgb_dist_level_distributed(const amgb_ctx *c, int level);
 
