@@ -86,3 +86,17 @@ def test_byte_model_matches_baseline_table():
         nnz = 117047296
     assert abs(H.bytes_spmv(M, False) / 1e9 - 1.7401) < 1e-3
     assert abs(H.bytes_spmv(M, True) / 1e9 - 1.8743) < 1e-3
+
+
+def test_algorithmic_byte_model_matches_survey_table():
+    """SURVEY.md 8d / BASELINE.md 3: bytes of y = Ax and r = b - Ax for the headline matrices"""
+    import types
+    from async_multigrid_b200 import hierarchy as H
+
+    def m(n, nnz):
+        return types.SimpleNamespace(nrows=n, ncols=n, nnz=nnz)
+    assert H.bytes_spmv(m(16777216, 117047296), False) == 1740111876          # 7-pt 256^3: 1.7401 GB
+    assert H.bytes_spmv(m(16777216, 117047296), True) == 1874329604           #             1.8743 GB
+    assert H.bytes_spmv(m(16777216, 449455096), False) == 5729005476          # 27-pt 256^3: 5.7290 GB
+    assert abs(H.bytes_spmv(m(134217728, 937951232), True) / 1e9 - 15.013) < 1e-3   # 7-pt 512^3
+    assert H.bytes_spmv(m(262144, 1308672), True) == 23044100                 # 5-pt 512^2: 23.04 MB
