@@ -59,7 +59,7 @@ def build_cuda(force=False, verbose=False):
     if not force and _newer(CUDA_LIB, deps):
         return CUDA_LIB
     inc, lib = _nccl_dirs()
-    cmd = [NVCC, "-O3", "-std=c++17", "-lineinfo", "-shared", "-Xcompiler", "-fPIC,-fopenmp",
+    cmd = [NVCC, "--threads", "0", "-O3", "-std=c++17", "-lineinfo", "-shared", "-Xcompiler", "-fPIC,-fopenmp",
            "-rdc=false", "-I", os.path.join(ROOT, "include"), "-I", CSRC] + ARCH
     if verbose:
         cmd += ["-Xptxas", "-v"]
