@@ -39,6 +39,7 @@ struct DistState {
    std::vector<DistLevel> lv;
    std::vector<double *> ws, r, e;   // level layout
    double *u = nullptr, *f = nullptr;   // u: level-0 layout; f: owned rows
+   double *ecyc = nullptr, *dacc = nullptr;   // owned rows: cycle output and the accelerated increment (DMEM_ChebyUpdate)
    double *t0 = nullptr, *v0 = nullptr;  // level-0 layout: scratch of the factorised level-0 transfers (factor_level0)
    // halo exchange on its own stream, overlapped with the interior launch units of the SpMV that needs it
    cudaStream_t comm_stream = nullptr;
@@ -187,12 +188,16 @@ static int dist_residual(amgb_ctx *c)
 // one synchronous Multadd cycle on r[0]; u += B r   (SMEM_Sync_Add_Vcycle semantics, src/SEQ_AMG.cpp:110-235;
 // DMEM analogue DMEM_SyncAddCycle, src/DMEM_Mult.cpp:322-450, with the SMEM convention that the coarsest
 // level contributes nothing)
-static int dist_cycle(amgb_ctx *c)
+// tgt: owned rows of a level-0 vector; accumulate: tgt += B r, else tgt = B r
+static int dist_cycle(amgb_ctx *c, double *tgt, bool accumulate)
 {
    DistState *d = c->dist;
    const int L = c->L;
    int rc;
-   if (L == 1) return AMGB_OK;
+   if (L == 1) {
+      if (!accumulate) CUDA_OK(c, cudaMemsetAsync(tgt, 0, sizeof(double) * c->A[0].nrows, c->stream));
+      return AMGB_OK;
+   }
    const bool bpx = c->opt.solver == AMGB_SOLVER_BPX;                   // SYNC_BPX of DMEM_SyncAddCycle (src/DMEM_Mult.cpp:346-349)
    const bool direct = c->opt.coarse_solve && c->Ainv.rp != nullptr;   // DMEM: direct solve on the (replicated) coarsest level
    const int top = (direct || bpx) ? L : L - 1;                         // levels that contribute a correction
@@ -226,18 +231,21 @@ static int dist_cycle(amgb_ctx *c)
       double *eo = d->e[l] + d->lv[l].off();
       if ((rc = dist_spmv(c, c->P[l], false, l + 1, d->e[l + 1], eo, epi(1.0, 1.0, eo), false))) return rc;
    }
-   double *uo = d->u + d->lv[0].off();
+   double *uo = tgt;
+   const double *cacc = accumulate ? tgt : nullptr;
    if (fact0) {
       // v = P_0 e_1 (ghosts of e_1);  u += v + (w/d) o (r_0 + t_0 - A_0 v) (ghosts of v)
       if ((rc = dist_spmv(c, c->P[0], false, 1, d->e[1], d->v0 + off0, epi(1.0, 0.0, nullptr), false))) return rc;
-      SpmvEpilogue fe = epi(-1.0, 1.0, d->r[0] + off0, 1.0, uo, d->ws[0] + off0);
+      SpmvEpilogue fe = epi(-1.0, 1.0, d->r[0] + off0, 1.0, cacc, d->ws[0] + off0);
       fe.b2 = d->t0 + off0; fe.beta2 = 1.0;
       fe.xs = d->v0 + off0; fe.xself = 1.0;
       if ((rc = dist_spmv(c, c->A[0], false, 0, d->v0, uo, fe, false))) return rc;
    } else if (top >= 2) {
-      if ((rc = dist_spmv(c, c->P[0], false, 1, d->e[1], uo, epi(1.0, 1.0, d->e[0] + d->lv[0].off(), 1.0, uo), false))) return rc;
-   } else {
+      if ((rc = dist_spmv(c, c->P[0], false, 1, d->e[1], uo, epi(1.0, 1.0, d->e[0] + d->lv[0].off(), 1.0, cacc), false))) return rc;
+   } else if (accumulate) {
       c->launches += launch_add(c->cfg, c->stream, c->A[0].nrows, d->e[0] + d->lv[0].off(), uo);
+   } else {
+      CUDA_OK(c, cudaMemcpyAsync(uo, d->e[0] + d->lv[0].off(), sizeof(double) * c->A[0].nrows, cudaMemcpyDeviceToDevice, c->stream));
    }
    return AMGB_OK;
 }
@@ -396,12 +404,28 @@ int amgb_dist_get_solution(amgb_ctx *c, double *u_owned)
 // global norm; stop test -- the same on every rank (the norm is all-reduced), so all ranks leave together.
 int amgb_dist_solve_sync(amgb_ctx *c, double tol, int max_cycles, double *hist, int *n_cycles, double *solve_seconds)
 {
+   return amgb_dist_solve_sync_accel(c, tol, max_cycles, 0, 1.0, 1.0, hist, n_cycles, solve_seconds);
+}
+
+// accel 1 / 2: DMEM_ChebyUpdate (src/DMEM_Misc.cpp:612-666) applied to the accumulated correction in
+// DMEM_SyncAddCorrect (src/DMEM_Add.cpp:706-711): cycle 0: d = e; then d = (omega-1) d + omega*delta*e; x += d, with
+// omega from the Chebyshev recurrence c_{k+1} = 2 mu c_k - c_{k-1} (accel 1) or fixed 2/(1+sqrt(1-mu^-2)) (accel 2).
+int amgb_dist_solve_sync_accel(amgb_ctx *c, double tol, int max_cycles, int accel, double mu, double delta, double *hist,
+                               int *n_cycles, double *solve_seconds)
+{
    NEED_READY(c);
 #ifdef AMG_HAVE_NCCL
    DistState *d = c->dist;
    if (!d || !d->ready) return amgb_fail(c, AMGB_ESTATE, "amgb_dist_setup not called");
-   if (max_cycles < 0) return amgb_fail(c, AMGB_EINVAL, "max_cycles < 0");
+   if (max_cycles < 0 || accel < 0 || accel > 2) return amgb_fail(c, AMGB_EINVAL, "bad arguments");
    int rc;
+   const int nown = c->A[0].nrows;
+   double *uo = d->u + d->lv[0].off();
+   if (accel && !d->ecyc) {
+      if ((rc = amgb_dev_alloc_bytes(c, (void **)&d->ecyc, sizeof(double) * (size_t)std::max(1, nown), true))) return rc;
+      if ((rc = amgb_dev_alloc_bytes(c, (void **)&d->dacc, sizeof(double) * (size_t)std::max(1, nown), true))) return rc;
+   }
+   double c_prev = 1.0, c_cur = mu;
    CUDA_OK(c, cudaMemsetAsync(d->u, 0, sizeof(double) * (size_t)d->lv[0].n_ext(), c->stream));
    if ((rc = dist_residual(c))) return rc;
    double ss;
@@ -411,7 +435,24 @@ int amgb_dist_solve_sync(amgb_ctx *c, double tol, int max_cycles, double *hist, 
    int done = 0;
    CUDA_OK(c, cudaEventRecord(c->ev0, c->stream));
    for (int k = 1; k <= max_cycles; k++) {
-      if ((rc = dist_cycle(c))) return rc;
+      if (!accel) {
+         if ((rc = dist_cycle(c, uo, true))) return rc;
+      } else {
+         if ((rc = dist_cycle(c, d->ecyc, false))) return rc;
+         if (k == 1) c->launches += launch_axpby(c->cfg, c->stream, nown, 1.0, d->ecyc, 0.0, d->dacc, nullptr);
+         else {
+            double omega;
+            if (accel == 2) omega = 2.0 / (1.0 + sqrt(1.0 - 1.0 / (mu * mu)));
+            else {
+               const double c_temp = c_cur;
+               c_cur = 2.0 * mu * c_cur - c_prev;
+               c_prev = c_temp;
+               omega = 2.0 * mu * c_prev / c_cur;
+            }
+            c->launches += launch_axpby(c->cfg, c->stream, nown, omega * delta, d->ecyc, omega - 1.0, d->dacc, nullptr);
+         }
+         c->launches += launch_add(c->cfg, c->stream, nown, d->dacc, uo);
+      }
       if ((rc = dist_residual(c))) return rc;
       if ((rc = amgb_fetch_scalar(c, &ss))) return rc;
       done = k;
@@ -429,7 +470,7 @@ int amgb_dist_solve_sync(amgb_ctx *c, double tol, int max_cycles, double *hist, 
    CUDA_OK(c, cudaGetLastError());
    return AMGB_OK;
 #else
-   (void)tol; (void)max_cycles; (void)hist; (void)n_cycles; (void)solve_seconds;
+   (void)tol; (void)max_cycles; (void)accel; (void)mu; (void)delta; (void)hist; (void)n_cycles; (void)solve_seconds;
    return amgb_fail(c, AMGB_ENCCL, "library built without NCCL");
 #endif
 }

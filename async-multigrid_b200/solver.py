@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "amgb_spgemv", "amgb_spgemv_transpose", "amgb_smooth", "amgb_norm2", "amgb_cycle", "amgb_eigs_power", "amgb_solve_sync", "amgb_solve_async",
     "amgb_smem_solve", "amgb_time_residual", "amgb_level_storage", "amgb_time_spmv", "amgb_stream_stats", "amgb_l2_arena_bytes",
     "amgb_dist_unique_id", "amgb_dist_init", "amgb_dist_set_level", "amgb_dist_setup", "amgb_dist_set_rhs",
-    "amgb_dist_get_solution", "amgb_dist_solve_sync", "amgb_dist_stats",
+    "amgb_dist_get_solution", "amgb_dist_solve_sync", "amgb_dist_solve_sync_accel", "amgb_dist_stats",
     "amgb_ipc_export_solution", "amgb_ipc_open_peers", "amgb_async_dist_correct", "amgb_residual_norm", "amgb_stream_synchronize",
 ]
 
@@ -94,6 +94,7 @@ def load_library():
     L.amgb_dist_set_rhs.argtypes = [C.c_void_p, DP]
     L.amgb_dist_get_solution.argtypes = [C.c_void_p, DP]
     L.amgb_dist_solve_sync.argtypes = [C.c_void_p, C.c_double, C.c_int, DP, IP, DP]
+    L.amgb_dist_solve_sync_accel.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, DP, IP, DP]
     L.amgb_dist_stats.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     _lib = L
     return L
@@ -388,10 +389,11 @@ class DistSolver:
         self._ck(self.L.amgb_dist_get_solution(self.ctx, _dp(u)))
         return u
 
-    def solve_sync(self, tol=1e-9, max_cycles=100):
+    def solve_sync(self, tol=1e-9, max_cycles=100, accel=0, mu=1.0, delta=1.0):
+        """accel: 0 none, 1 Chebyshev, 2 second-order Richardson (DMEM_ChebyUpdate)"""
         hist = np.zeros(max_cycles + 1)
         n, secs = C.c_int(0), C.c_double(0)
-        self._ck(self.L.amgb_dist_solve_sync(self.ctx, tol, max_cycles, _dp(hist), C.byref(n), C.byref(secs)))
+        self._ck(self.L.amgb_dist_solve_sync_accel(self.ctx, tol, max_cycles, accel, mu, delta, _dp(hist), C.byref(n), C.byref(secs)))
         return hist[:n.value + 1], secs.value
 
     def stats(self):

@@ -173,6 +173,11 @@ int amgb_dist_get_solution(amgb_ctx *ctx, double *u_owned);
 /* x0 = 0; cycles until ||r||/||r0|| < tol (global norms) or max_cycles; identical history on every rank */
 int amgb_dist_solve_sync(amgb_ctx *ctx, double tol, int max_cycles, double *relres_hist, int *n_cycles,
                          double *solve_seconds);
+/* the same with DMEM's acceleration of the accumulated correction (DMEM_ChebyUpdate, src/DMEM_Misc.cpp:612-666, applied in
+ * DMEM_SyncAddCorrect src/DMEM_Add.cpp:706-711): accel 0 none, 1 Chebyshev, 2 second-order Richardson; mu, delta from
+ * ChebySetup (src/DMEM_Setup.cpp:1901-1914) */
+int amgb_dist_solve_sync_accel(amgb_ctx *ctx, double tol, int max_cycles, int accel, double mu, double delta,
+                               double *relres_hist, int *n_cycles, double *solve_seconds);
 int amgb_dist_stats(amgb_ctx *ctx, long long *halo_bytes_sent, long long *nccl_ops);
 
 /* ---- asynchronous additive solve across GPUs (DMEM async Multadd; one process per GPU) --------------------------

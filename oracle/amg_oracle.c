@@ -520,6 +520,55 @@ int orc_solve_async_sequential(const orc_problem *pb, const double *f, double *u
    return 0;
 }
 
+/* DMEM's accelerated synchronous additive solve: DMEM_SyncAddCorrect + DMEM_ChebyUpdate
+ * (src/DMEM_Add.cpp:647-716, src/DMEM_Misc.cpp:612-666, ChebySetup src/DMEM_Setup.cpp:1901-1914).  Per cycle e = B r
+ * (all grids' corrections accumulated), then cycle 0: d = e; later cycles: d = (omega-1) d + omega*delta*e with
+ * omega = 2/(1+sqrt(1-mu^-2)) (accel 2, Richardson) or omega = 2 mu c_k / c_{k+1}, c_{k+1} = 2 mu c_k - c_{k-1},
+ * c_0 = 1, c_1 = mu (accel 1, Chebyshev); x += d.  accel 0: x += e. */
+int orc_solve_sync_dmem(const orc_problem *pb, const double *f, double *u, double tol, int num_cycles,
+                        int accel, double mu, double delta, double *relres)
+{
+   const int n0 = pb->A[0].nrows;
+   orc_work *w = work_alloc(pb);
+   double *r = w->r[0];
+   double *e = (double *)calloc((size_t)n0, sizeof(double)), *d = (double *)calloc((size_t)n0, sizeof(double));
+   double c_prev = 1.0, c_cur = mu;
+   orc_residual(&pb->A[0], f, u, r);
+   const double r0 = orc_norm2(r, n0);
+   relres[0] = 1.0;
+   int done = 0;
+   for (int k = 0; k < num_cycles; k++) {
+      memset(e, 0, sizeof(double) * (size_t)n0);
+      if (pb->solver == ORC_BPX) orc_bpx_cycle(pb, w, e);
+      else orc_add_vcycle(pb, w, e, NULL);
+      if (accel == 0) {
+         for (int i = 0; i < n0; i++) u[i] += e[i];
+      } else {
+         if (k == 0) memcpy(d, e, sizeof(double) * (size_t)n0);
+         else {
+            double omega;
+            if (accel == 2) omega = 2.0 / (1.0 + sqrt(1.0 - pow(mu, -2.0)));
+            else {
+               const double c_temp = c_cur;
+               c_cur = 2.0 * mu * c_cur - c_prev;
+               c_prev = c_temp;
+               omega = 2.0 * mu * c_prev / c_cur;
+            }
+            for (int i = 0; i < n0; i++) d[i] = (omega - 1.0) * d[i] + omega * delta * e[i];
+         }
+         for (int i = 0; i < n0; i++) u[i] += d[i];
+      }
+      orc_residual(&pb->A[0], f, u, r);
+      const double rn = orc_norm2(r, n0);
+      relres[k + 1] = rn / r0;
+      done = k + 1;
+      if (rn / r0 < tol) break;
+   }
+   free(e); free(d);
+   work_free(w);
+   return done;
+}
+
 /* EigsPower (src/SMEM_Cheby.cpp:410-518): extreme eigenvalues of B*A by power iteration, B = one application of
  * the selected cycle from a zero guess (the reference hard-wires its hypre-vector BPXCycle for every solver other
  * than MULT; here B is the cycle `pb` names, identical for BPX).  Start vector all ones; `iters` normalise /

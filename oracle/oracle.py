@@ -59,6 +59,8 @@ def lib():
         L.orc_symmetric_jacobi.argtypes = [C.POINTER(OrcCSR), DP, DP, DP, DP, C.c_double, C.c_int, C.c_int]
         L.orc_symmetric_l1_jacobi.argtypes = [C.POINTER(OrcCSR), DP, DP, DP, DP, DP, C.c_int, C.c_int]
         L.orc_solve_async_sequential.argtypes = [C.POINTER(OrcProblem), DP, DP, C.c_int, IP, DP]
+        L.orc_solve_sync_dmem.restype = C.c_int
+        L.orc_solve_sync_dmem.argtypes = [C.POINTER(OrcProblem), DP, DP, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, DP]
         L.orc_eigs_power.argtypes = [C.POINTER(OrcProblem), C.c_int, DP, DP]
         L.orc_eigs_power.restype = None
         _lib = L
@@ -124,6 +126,13 @@ class Problem:
         u = np.zeros(self.h.n[0])
         lib().orc_cycle(C.byref(self.c), dptr(np.ascontiguousarray(r)), dptr(u))
         return u
+
+    def solve_sync_dmem(self, f, tol=1e-9, num_cycles=100, accel=0, mu=1.0, delta=1.0):
+        """DMEM_SyncAddCorrect + DMEM_ChebyUpdate: accel 0 none, 1 Chebyshev, 2 second-order Richardson"""
+        u = np.zeros(self.h.n[0])
+        hist = np.zeros(num_cycles + 1)
+        k = lib().orc_solve_sync_dmem(C.byref(self.c), dptr(np.ascontiguousarray(f)), dptr(u), tol, num_cycles, accel, mu, delta, dptr(hist))
+        return u, hist[:k + 1]
 
     def eigs_power(self, iters=20):
         """(alpha, beta) = (eig_min, eig_max) of B*A as EigsPower estimates them"""

@@ -55,6 +55,23 @@ def test_single_rank_factorised_level0_matches_oracle():
     s.close()
 
 
+@pytest.mark.parametrize("accel", [1, 2])
+def test_single_rank_dmem_acceleration_matches_oracle(accel):
+    """DMEM_ChebyUpdate on the accumulated correction (Chebyshev / second-order Richardson)"""
+    w = 0.9
+    h, b = _setup("7pt", 20, w)
+    pb = O.Problem(h, H.MULTADD, H.JACOBI, w)
+    alpha, beta = pb.eigs_power(20)
+    mu, delta = (beta + alpha) / (beta - alpha), 2.0 / (beta + alpha)
+    _, want = pb.solve_sync_dmem(b, 1e-9, 100, accel, mu, delta)
+    assert len(want) - 1 < 27                                   # the acceleration pays (27 cycles without)
+    s = amg.DistSolver(PT.RankPlan(h, 1, 0), amg.solver.dist_unique_id(), w)
+    s.set_rhs(b)
+    hist, _ = s.solve_sync(1e-9, 100, accel=accel, mu=mu, delta=delta)
+    assert len(hist) == len(want) and np.max(np.abs(hist - want)) <= HIST_TOL
+    s.close()
+
+
 def test_single_rank_bpx_matches_oracle():
     """SYNC_BPX in the partitioned path (plain P, R = P^T, one Jacobi sweep on every level incl. the coarsest)"""
     w = 0.6
