@@ -53,6 +53,8 @@ def host_lib():
         L.amgh_csr_free.restype = None
         L.amgh_smooth_transfer.argtypes = [C.POINTER(_CSR), C.POINTER(_CSR), C.c_int, C.c_double,
                                            C.c_int, C.c_int, C.POINTER(_CSR), C.POINTER(_CSR)]
+        L.amgh_read_binary_triplets.argtypes = [C.c_char_p, C.c_int, C.POINTER(_CSR)]
+        L.amgh_write_binary_triplets.argtypes = [C.POINTER(_CSR), C.c_char_p, C.c_int]
         _lib = L
     return _lib
 
@@ -143,6 +145,25 @@ def laplacian(problem, nx, ny=None, nz=None):
     if rc != 0:
         raise ValueError("problem too large for int32 CSR")
     return _take(out)
+
+
+def read_matrix(path, symm_flag=1):
+    """`-problem file`: the reference's binary triplet format (ReadBinary_fread_HypreParCSR, src/Misc.cpp:800-915;
+    SMEM_Setup calls it with symm_flag = 1, src/SMEM_Setup.cpp:1646-1650).  Diag-first CSR."""
+    out = _CSR()
+    rc = host_lib().amgh_read_binary_triplets(os.fsencode(path), C.c_int(int(symm_flag)), C.byref(out))
+    if rc != 0:
+        raise IOError({1: "cannot open matrix file %r", 2: "matrix file %r is not in the 16-byte triplet format",
+                       3: "matrix file %r has an index outside 1..num_rows"}.get(rc, "cannot read %r") % path)
+    return _take(out)
+
+
+def write_matrix(m, path, lower_only=True):
+    """the matching writer (PrintCSRMatrix, bin_file = 1, src/Misc.cpp:752-798); lower_only: one triangle, the
+    form the SMEM reader mirrors"""
+    cs = m._as_c()
+    if host_lib().amgh_write_binary_triplets(C.byref(cs), os.fsencode(path), C.c_int(1 if lower_only else 0)) != 0:
+        raise IOError("cannot write %r" % path)
 
 
 def rand_rhs(n, lo=-1.0, hi=1.0, seed=0):

@@ -478,6 +478,79 @@ void amgh_rand_fill(double *b, long n, double lo, double hi, unsigned seed)
    for (long k = 0; k < n; k++) b[k] = lo + (hi - lo) * ((double)rand() / RAND_MAX);
 }
 
+// ---- matrix files (`-problem file`) -----------------------------------------------------------------
+// Binary triplet format of the reference (reader ReadBinary_fread_HypreParCSR src/Misc.cpp:800-915, called with
+// symm_flag = 1 by SMEM_Setup src/SMEM_Setup.cpp:1646-1650; writer PrintCSRMatrix src/Misc.cpp:752-798): 16-byte
+// records {int32 i, int32 j, double val}; record 0 carries the number of rows in `i`; every following record is one
+// entry with 1-based row / column.  symm_flag != 0: the file holds one triangle and every off-diagonal entry is
+// mirrored.  Entries keep the order of the file inside their row (a mirrored entry is appended to its row when the
+// original is met); the diagonal is then moved to the front, as hypre's IJ assembly does for the diag block and as
+// the solve phase requires (src/SMEM_Smooth.cpp:385-386).  Returns 0, or 1 file / 2 format / 3 index errors
+// (the reference prints and exit(1)s, src/SMEM_Setup.cpp:1652-1654).
+int amgh_read_binary_triplets(const char *path, int symm_flag, amgh_csr *out)
+{
+   struct Rec { int i, j; double v; };
+   static_assert(sizeof(Rec) == 16, "triplet record size");
+   FILE *fp = fopen(path, "rb");
+   if (!fp) return 1;
+   fseek(fp, 0, SEEK_END);
+   const long bytes = ftell(fp);
+   rewind(fp);
+   if (bytes < 16 || bytes % 16) { fclose(fp); return 2; }
+   const long nrec = bytes / 16;
+   std::vector<Rec> rec((size_t)nrec);
+   if (fread(rec.data(), 16, (size_t)nrec, fp) != (size_t)nrec) { fclose(fp); return 2; }
+   fclose(fp);
+   const int n = rec[0].i;
+   if (n < 0) return 2;
+   std::vector<int> cnt((size_t)n + 1, 0);
+   for (long k = 1; k < nrec; k++) {
+      const int r = rec[k].i, c = rec[k].j;
+      if (r < 1 || r > n || c < 1 || c > n) return 3;
+      cnt[r]++;
+      if (symm_flag && r != c) cnt[c]++;
+   }
+   long tot = 0;
+   for (int r = 1; r <= n; r++) tot += cnt[r];
+   if (tot > 2147483000L) return 2;
+   for (int r = 0; r < n; r++) cnt[r + 1] += cnt[r];
+   csr_alloc(out, n, n, cnt[n]);
+   memcpy(out->i, cnt.data(), sizeof(int) * ((size_t)n + 1));
+   std::vector<int> fill(cnt.begin(), cnt.end() - 1);
+   for (long k = 1; k < nrec; k++) {
+      const int r = rec[k].i - 1, c = rec[k].j - 1;
+      int d = fill[r]++;
+      out->j[d] = c; out->data[d] = rec[k].v;
+      if (symm_flag && r != c) { d = fill[c]++; out->j[d] = r; out->data[d] = rec[k].v; }
+   }
+   diag_first(out);
+   return 0;
+}
+
+// the matching writer: header record {nrows, ncols, -}, then one record per entry, rows ascending
+// (PrintCSRMatrix with bin_file = 1, src/Misc.cpp:752-798).  lower_only != 0 writes the entries with col <= row
+// only -- the form the SMEM reader (symm_flag = 1) expects for a symmetric matrix.
+int amgh_write_binary_triplets(const amgh_csr *A, const char *path, int lower_only)
+{
+   struct Rec { int i, j; double v; };
+   FILE *fp = fopen(path, "wb");
+   if (!fp) return 1;
+   Rec h; h.i = A->nrows; h.j = A->ncols; h.v = 0.0;
+   long kept = 0;
+   for (int r = 0; r < A->nrows; r++)
+      for (int p = A->i[r]; p < A->i[r + 1]; p++) if (!lower_only || A->j[p] <= r) kept++;
+   memcpy(&h.v, &kept, sizeof(long) < sizeof(double) ? sizeof(long) : sizeof(double));
+   fwrite(&h, 16, 1, fp);
+   for (int r = 0; r < A->nrows; r++)
+      for (int p = A->i[r]; p < A->i[r + 1]; p++) {
+         if (lower_only && A->j[p] > r) continue;
+         Rec e; e.i = r + 1; e.j = A->j[p] + 1; e.v = A->data[p];
+         fwrite(&e, 16, 1, fp);
+      }
+   fclose(fp);
+   return 0;
+}
+
 int amgh_transpose(const amgh_csr *A, amgh_csr *AT) { transpose(*A, AT); return 0; }
 int amgh_spgemm(const amgh_csr *A, const amgh_csr *B, amgh_csr *C) { spgemm(*A, *B, C); return 0; }
 int amgh_diag_first(amgh_csr *A) { diag_first(A); return 0; }

@@ -220,8 +220,26 @@ def ref_lib():
         L.ref_matvec.argtypes = [C.POINTER(OrcCSR), DP, DP]
         L.ref_seq_symmetric_jacobi.argtypes = [C.POINTER(OrcCSR), DP, DP, C.c_double, C.c_int]
         L.ref_seq_jacobi.argtypes = [C.POINTER(OrcCSR), DP, DP, C.c_double, C.c_int, C.c_int]
+        L.ref_read_matrix.restype = C.c_int
+        L.ref_read_matrix.argtypes = [C.c_char_p, C.c_int, IP, IP, C.POINTER(IP), C.POINTER(IP), C.POINTER(DP)]
+        L.ref_free.argtypes = [C.c_void_p]
         _ref = L
     return _ref
+
+
+def ref_read_matrix(path, symm_flag=1):
+    """the reference's own reader (ReadBinary_fread_HypreParCSR, src/Misc.cpp:800-915) -> (indptr, indices, data)"""
+    L = ref_lib()
+    n, nnz = C.c_int(), C.c_int()
+    ri, rj, rd = IP(), IP(), DP()
+    if L.ref_read_matrix(os.fsencode(path), symm_flag, C.byref(n), C.byref(nnz), C.byref(ri), C.byref(rj), C.byref(rd)) != 0:
+        raise IOError(path)
+    ip = np.ctypeslib.as_array(ri, shape=(n.value + 1,)).copy()
+    ix = np.ctypeslib.as_array(rj, shape=(max(nnz.value, 1),))[:nnz.value].copy()
+    dv = np.ctypeslib.as_array(rd, shape=(max(nnz.value, 1),))[:nnz.value].copy()
+    for q in (ri, rj, rd):
+        L.ref_free(C.cast(q, C.c_void_p))
+    return ip, ix, dv
 
 
 class RefSolver:

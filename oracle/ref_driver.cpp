@@ -59,12 +59,63 @@ HYPRE_Int hypre_GaussElimSolve(hypre_ParAMGData *, HYPRE_Int, HYPRE_Int) { retur
 HYPRE_Int HYPRE_BoomerAMGSetPrintLevel(HYPRE_Solver, HYPRE_Int) { return 0; }
 HYPRE_Int HYPRE_BoomerAMGSetMaxIter(HYPRE_Solver, HYPRE_Int) { return 0; }
 HYPRE_Int hypre_ParVectorSetConstantValues(hypre_ParVector *, HYPRE_Complex) { return 0; }
-HYPRE_Int HYPRE_IJMatrixCreate(MPI_Comm, HYPRE_BigInt, HYPRE_BigInt, HYPRE_BigInt, HYPRE_BigInt, HYPRE_IJMatrix *) { return 1; }
-HYPRE_Int HYPRE_IJMatrixSetObjectType(HYPRE_IJMatrix, HYPRE_Int) { return 1; }
-HYPRE_Int HYPRE_IJMatrixInitialize(HYPRE_IJMatrix) { return 1; }
-HYPRE_Int HYPRE_IJMatrixSetValues(HYPRE_IJMatrix, HYPRE_Int, HYPRE_Int *, const HYPRE_BigInt *, const HYPRE_BigInt *, const HYPRE_Complex *) { return 1; }
-HYPRE_Int HYPRE_IJMatrixAssemble(HYPRE_IJMatrix) { return 1; }
-HYPRE_Int HYPRE_IJMatrixGetObject(HYPRE_IJMatrix, void **) { return 1; }
+// HYPRE_IJMatrix as far as ReadBinary_fread_HypreParCSR (src/Misc.cpp:800-915) uses it: rows are set one at a time
+// and the assembled object is a ParCSR matrix whose (only) diag block is CSR.  As in hypre's IJ assembly the
+// diagonal entry is moved to the front of its row; the other entries keep the order they were set in.
+struct StubIJ {
+   int n = 0;
+   std::vector<std::vector<int>> cols;
+   std::vector<std::vector<double>> vals;
+   hypre_CSRMatrix csr;
+   hypre_ParCSRMatrix par;
+};
+HYPRE_Int HYPRE_IJMatrixCreate(MPI_Comm, HYPRE_BigInt ilower, HYPRE_BigInt iupper, HYPRE_BigInt, HYPRE_BigInt, HYPRE_IJMatrix *m)
+{
+   StubIJ *ij = new StubIJ();
+   ij->n = iupper - ilower + 1;
+   ij->cols.resize(ij->n); ij->vals.resize(ij->n);
+   *m = ij;
+   return 0;
+}
+HYPRE_Int HYPRE_IJMatrixSetObjectType(HYPRE_IJMatrix, HYPRE_Int) { return 0; }
+HYPRE_Int HYPRE_IJMatrixInitialize(HYPRE_IJMatrix) { return 0; }
+HYPRE_Int HYPRE_IJMatrixSetValues(HYPRE_IJMatrix m, HYPRE_Int nrows, HYPRE_Int *ncols, const HYPRE_BigInt *rows, const HYPRE_BigInt *cols,
+                                  const HYPRE_Complex *values)
+{
+   StubIJ *ij = (StubIJ *)m;
+   int pos = 0;
+   for (int r = 0; r < nrows; r++)
+      for (int k = 0; k < ncols[r]; k++, pos++) { ij->cols[rows[r]].push_back(cols[pos]); ij->vals[rows[r]].push_back(values[pos]); }
+   return 0;
+}
+HYPRE_Int HYPRE_IJMatrixAssemble(HYPRE_IJMatrix m)
+{
+   StubIJ *ij = (StubIJ *)m;
+   size_t nnz = 0;
+   for (auto &c : ij->cols) nnz += c.size();
+   hypre_CSRMatrix &A = ij->csr;
+   A.num_rows = A.num_cols = ij->n; A.num_nonzeros = (int)nnz; A.rownnz = nullptr; A.num_rownnz = ij->n;
+   A.i = (int *)malloc(sizeof(int) * ((size_t)ij->n + 1));
+   A.j = (int *)malloc(sizeof(int) * std::max<size_t>(nnz, 1));
+   A.data = (double *)malloc(sizeof(double) * std::max<size_t>(nnz, 1));
+   A.i[0] = 0;
+   for (int r = 0; r < ij->n; r++) {
+      int d = A.i[r];
+      const int len = (int)ij->cols[r].size();
+      for (int k = 0; k < len; k++) { A.j[d + k] = ij->cols[r][k]; A.data[d + k] = ij->vals[r][k]; }
+      for (int k = 0; k < len; k++)
+         if (A.j[d + k] == r) {
+            const int jt = A.j[d + k]; const double vt = A.data[d + k];
+            for (int q = k; q > 0; q--) { A.j[d + q] = A.j[d + q - 1]; A.data[d + q] = A.data[d + q - 1]; }
+            A.j[d] = jt; A.data[d] = vt;
+            break;
+         }
+      A.i[r + 1] = d + len;
+   }
+   ij->par.diag = &ij->csr; ij->par.global_num_rows = ij->n;
+   return 0;
+}
+HYPRE_Int HYPRE_IJMatrixGetObject(HYPRE_IJMatrix m, void **object) { *object = &((StubIJ *)m)->par; return 0; }
 
 // referenced by SMEM_Solve.cpp (async with one thread) but defined in a TU that is compiled too
 // (SEQ_AMG.cpp); nothing else is missing.
@@ -376,5 +427,20 @@ void ref_seq_jacobi(const RefCSR *A, double *f, double *u, double w, int sweeps,
    std::vector<double> up(A->nrows);
    SEQ_Jacobi(&ad, &m, f, u, up.data(), sweeps, 0);
 }
+
+// The reference's own matrix-file reader (`-problem file`, src/SMEM_Setup.cpp:1646-1650 -> ReadBinary_fread_HypreParCSR,
+// src/Misc.cpp:800-915) on `path`; the caller frees the three arrays with ref_free.
+int ref_read_matrix(const char *path, int symm_flag, int *nrows, int *nnz, int **ri, int **rj, double **rdata)
+{
+   FILE *fp = fopen(path, "rb");
+   if (!fp) return 1;
+   hypre_ParCSRMatrix *par = nullptr;
+   ReadBinary_fread_HypreParCSR(fp, &par, symm_flag, 0);
+   fclose(fp);
+   hypre_CSRMatrix *A = hypre_ParCSRMatrixDiag(par);
+   *nrows = A->num_rows; *nnz = A->num_nonzeros; *ri = A->i; *rj = A->j; *rdata = A->data;
+   return 0;
+}
+void ref_free(void *p) { free(p); }
 int ref_max_threads(void) { return omp_get_max_threads(); }
 }

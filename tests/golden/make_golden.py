@@ -95,5 +95,37 @@ def main():
         print(name, {k: (v.shape if hasattr(v, "shape") else v) for k, v in d.items() if "hist" in k})
 
 
+def matrix_file_golden():
+    """A small file in the reference's binary triplet format and what the reference's own reader
+    (ReadBinary_fread_HypreParCSR, src/Misc.cpp:800-915, compiled in oracle/_ref) makes of it, for both settings of
+    symm_flag.  The records are shuffled so that the in-row order (file order, mirrored entries appended) is pinned."""
+    import tempfile
+    rng = np.random.default_rng(7)
+    A = H.laplacian("7pt", 5, 4, 3).to_scipy().tocoo()
+    vals = A.data * (1.0 + 0.01 * np.minimum(A.row, A.col)) + 0.001 * np.maximum(A.row, A.col)   # symmetric, distinct values
+    keep = A.col <= A.row
+    rec = np.zeros(1 + int(keep.sum()), dtype=[("i", "<i4"), ("j", "<i4"), ("v", "<f8")])
+    rec[0] = (A.shape[0], A.shape[1], 0.0)
+    order = rng.permutation(int(keep.sum()))
+    rec["i"][1:] = A.row[keep][order] + 1
+    rec["j"][1:] = A.col[keep][order] + 1
+    rec["v"][1:] = vals[keep][order]
+    d = {"file_bytes": np.frombuffer(rec.tobytes(), dtype=np.uint8)}
+    with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as fp:
+        fp.write(rec.tobytes())
+        path = fp.name
+    for flag in (0, 1):
+        ip, ix, dv = O.ref_read_matrix(path, flag)
+        d["symm%d_indptr" % flag], d["symm%d_indices" % flag], d["symm%d_data" % flag] = ip, ix, dv
+    os.unlink(path)
+    np.savez_compressed(os.path.join(OUT, "matrix_file.npz"), **d)
+    print("matrix_file", rec.shape, d["symm1_indptr"][-1])
+
+
 if __name__ == "__main__":
-    main()
+    if "--matrix-file-only" not in sys.argv:
+        main()
+    else:
+        from oracle import build as obuild
+        amg.build.build_host(); obuild.build_ref()
+    matrix_file_golden()
