@@ -53,6 +53,10 @@ def host_lib():
         L.amgh_csr_free.restype = None
         L.amgh_smooth_transfer.argtypes = [C.POINTER(_CSR), C.POINTER(_CSR), C.c_int, C.c_double,
                                            C.c_int, C.c_int, C.POINTER(_CSR), C.POINTER(_CSR)]
+        L.amgh_setup_systems.restype = C.c_void_p
+        L.amgh_setup_systems.argtypes = [C.POINTER(_CSR), C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.amgh_elasticity_beam.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
+                                           C.c_double, C.POINTER(_CSR), C.c_void_p]
         L.amgh_read_binary_triplets.argtypes = [C.c_char_p, C.c_int, C.POINTER(_CSR)]
         L.amgh_write_binary_triplets.argtypes = [C.POINTER(_CSR), C.c_char_p, C.c_int]
         _lib = L
@@ -147,6 +151,23 @@ def laplacian(problem, nx, ny=None, nz=None):
     return _take(out)
 
 
+def elasticity_beam(ex, ey=None, ez=None, h=None, lam=(50.0, 1.0), mu=(50.0, 1.0)):
+    """Stand-in for the reference's MFEM elasticity problem (DMEM_BuildMfemMatrix, src/DMEM_BuildMatrix.cpp:442-719;
+    BASELINE.json configs[3]): Q1 hexahedra on an ex x ey x ez beam (default 8:1:1 like beam-hex.mesh), two materials,
+    face x = 0 clamped, traction on x = L.  Returns (A, b): 3 unknowns per node, interleaved; use
+    amg_setup(A, num_functions=3)."""
+    ey = max(1, ex // 8) if ey is None else ey
+    ez = ey if ez is None else ez
+    h = 8.0 / ex if h is None else h
+    out = _CSR()
+    n = 3 * (ex + 1) * (ey + 1) * (ez + 1)
+    b = np.zeros(n, dtype=np.float64)
+    rc = host_lib().amgh_elasticity_beam(ex, ey, ez, h, lam[0], mu[0], lam[1], mu[1], C.byref(out), b.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise ValueError("elasticity problem too large for int32 CSR" if rc == 1 else "bad beam dimensions")
+    return _take(out), b
+
+
 def read_matrix(path, symm_flag=1):
     """`-problem file`: the reference's binary triplet format (ReadBinary_fread_HypreParCSR, src/Misc.cpp:800-915;
     SMEM_Setup calls it with symm_flag = 1, src/SMEM_Setup.cpp:1646-1650).  Diag-first CSR."""
@@ -232,11 +253,14 @@ class Hierarchy:
         return sum(a.nnz for a in self.A) / self.A[0].nnz
 
 
-def amg_setup(A, theta=0.25, max_levels=25, max_coarse=9, pmax=4, jacobi_interp_steps=1, verbose=False):
-    """Classical AMG hierarchy (stand-in for HYPRE_BoomerAMGSetup, SMEM_Setup.cpp:65)."""
+def amg_setup(A, theta=0.25, max_levels=25, max_coarse=9, pmax=4, jacobi_interp_steps=1, verbose=False, num_functions=1):
+    """Classical AMG hierarchy (stand-in for HYPRE_BoomerAMGSetup, SMEM_Setup.cpp:65).  num_functions > 1: systems of
+    PDEs with interleaved unknowns, unknown-based coarsening (HYPRE_BoomerAMGSetNumFunctions; the reference sets
+    num_functions = dim for elasticity, src/DMEM_BuildMatrix.cpp:470)."""
     L = host_lib()
     a_c = A._as_c()
-    h = L.amgh_setup(C.byref(a_c), theta, max_levels, max_coarse, pmax, jacobi_interp_steps, int(verbose))
+    h = L.amgh_setup_systems(C.byref(a_c), int(num_functions), theta, max_levels, max_coarse, pmax, jacobi_interp_steps,
+                             int(verbose))
     nl = L.amgh_num_levels(h)
     As = [_take(L.amgh_level_A(h, l).contents, free=False) for l in range(nl)]
     Ps = [_take(L.amgh_level_P(h, l).contents, free=False) for l in range(nl - 1)]

@@ -183,7 +183,10 @@ inline uint32_t hash32(uint32_t x)
 
 // classical strength of connection: j strongly influences i iff
 // -a_ij >= theta * max_k(-a_ik), k != i.   Returns S with the pattern only (data = a_ij).
-void strength(const amgh_csr &A, double theta, amgh_csr *S)
+// func != nullptr (systems of PDEs, hypre's num_functions > 1 / dof_func): only couplings between unknowns of the
+// same function count -- the "unknown-based" approach HYPRE_BoomerAMGSetNumFunctions selects
+// (src/DMEM_BuildMatrix.cpp:470 sets num_functions = dim for the elasticity problems).
+void strength(const amgh_csr &A, double theta, amgh_csr *S, const int *func = nullptr)
 {
    const int n = A.nrows;
    int *si = (int *)calloc((size_t)n + 1, sizeof(int));
@@ -191,11 +194,11 @@ void strength(const amgh_csr &A, double theta, amgh_csr *S)
    for (int r = 0; r < n; r++) {
       double mx = 0.0;
       for (int p = A.i[r]; p < A.i[r + 1]; p++)
-         if (A.j[p] != r) mx = std::max(mx, -A.data[p]);
+         if (A.j[p] != r && (!func || func[A.j[p]] == func[r])) mx = std::max(mx, -A.data[p]);
       int cnt = 0;
       if (mx > 0.0)
          for (int p = A.i[r]; p < A.i[r + 1]; p++)
-            if (A.j[p] != r && -A.data[p] >= theta * mx) cnt++;
+            if (A.j[p] != r && (!func || func[A.j[p]] == func[r]) && -A.data[p] >= theta * mx) cnt++;
       si[r + 1] = cnt;
    }
    prefix(si, n);
@@ -206,11 +209,11 @@ void strength(const amgh_csr &A, double theta, amgh_csr *S)
    for (int r = 0; r < n; r++) {
       double mx = 0.0;
       for (int p = A.i[r]; p < A.i[r + 1]; p++)
-         if (A.j[p] != r) mx = std::max(mx, -A.data[p]);
+         if (A.j[p] != r && (!func || func[A.j[p]] == func[r])) mx = std::max(mx, -A.data[p]);
       int d = si[r];
       if (mx > 0.0)
          for (int p = A.i[r]; p < A.i[r + 1]; p++)
-            if (A.j[p] != r && -A.data[p] >= theta * mx) { S->j[d] = A.j[p]; S->data[d] = A.data[p]; d++; }
+            if (A.j[p] != r && (!func || func[A.j[p]] == func[r]) && -A.data[p] >= theta * mx) { S->j[d] = A.j[p]; S->data[d] = A.data[p]; d++; }
    }
 }
 
@@ -266,7 +269,7 @@ void pmis(const amgh_csr &S, std::vector<int> &cf)
 
 // direct interpolation on strong C neighbours (Stueben), sign-separated.
 void direct_interp(const amgh_csr &A, const amgh_csr &S, const std::vector<int> &cf,
-                   const std::vector<int> &cidx, int nc, amgh_csr *P)
+                   const std::vector<int> &cidx, int nc, amgh_csr *P, const int *func = nullptr)
 {
    const int n = A.nrows;
    int *pi = (int *)calloc((size_t)n + 1, sizeof(int));
@@ -288,6 +291,7 @@ void direct_interp(const amgh_csr &A, const amgh_csr &S, const std::vector<int> 
       double diag = 0, neg_all = 0, pos_all = 0, neg_c = 0, pos_c = 0;
       for (int p = A.i[r]; p < A.i[r + 1]; p++) {
          if (A.j[p] == r) diag += A.data[p];
+         else if (func && func[A.j[p]] != func[r]) continue;   // other functions do not enter the row sums (hypre dof_func test)
          else if (A.data[p] < 0) neg_all += A.data[p];
          else pos_all += A.data[p];
       }
@@ -469,6 +473,126 @@ int amgh_laplacian_27pt(int nx, int ny, int nz, amgh_csr *out)
    return 0;
 }
 
+// ---- 3-D linear elasticity on a structured beam (stand-in for the reference's MFEM problem) ----------------------
+// The reference's elasticity test (DMEM_BuildMfemMatrix, src/DMEM_BuildMatrix.cpp:442-719) refines MFEM's
+// beam-hex.mesh -- an 8 x 1 x 1 beam of hexahedra whose first half is material 1 (lambda = mu = 50) and second half
+// material 2 (lambda = mu = 1) (:540-547) -- with first-order H1 elements in a byVDIM vector space (:508), clamps the
+// face x = 0 (:513-516), pulls on the face x = L with -1e-2 in the last component (:518-527) and hands hypre
+// num_functions = dim (:470).  MFEM is absent here, so this assembler produces the same discretisation directly:
+// trilinear (Q1) hexahedra of side h on an (ex x ey x ez)-element box, 2x2x2 Gauss quadrature, unknown
+// 3*node + component with node = ix + (ex+1)*(iy + (ey+1)*iz); elements with ix < ex/2 are material 1.  Clamped
+// unknowns keep their diagonal and lose their off-diagonal row and column entries.  Interior rows carry
+// 27 nodes x 3 components = 81 entries.  Diag-first rows, then ascending columns.
+static void hex_elasticity_ke(double lambda, double mu, double h, double Ke[24][24])
+{
+   const double g = 1.0 / std::sqrt(3.0);
+   for (int a = 0; a < 24; a++) for (int b = 0; b < 24; b++) Ke[a][b] = 0.0;
+   for (int q = 0; q < 8; q++) {
+      const double xi[3] = {(q & 1) ? g : -g, (q & 2) ? g : -g, (q & 4) ? g : -g};
+      double dN[8][3];
+      for (int a = 0; a < 8; a++) {
+         const double sa[3] = {(a & 1) ? 1.0 : -1.0, (a & 2) ? 1.0 : -1.0, (a & 4) ? 1.0 : -1.0};
+         for (int d = 0; d < 3; d++) {
+            double v = sa[d] / 8.0;
+            for (int o = 0; o < 3; o++) if (o != d) v *= (1.0 + sa[o] * xi[o]);
+            dN[a][d] = v * 2.0 / h;      // d/dx = (2/h) d/dxi
+         }
+      }
+      const double wdet = h * h * h / 8.0;   // unit Gauss weights x det J
+      for (int a = 0; a < 8; a++)
+         for (int b = 0; b < 8; b++) {
+            double gg = 0.0;
+            for (int d = 0; d < 3; d++) gg += dN[a][d] * dN[b][d];
+            for (int i = 0; i < 3; i++)
+               for (int j = 0; j < 3; j++)
+                  Ke[3 * a + i][3 * b + j] += wdet * (lambda * dN[a][i] * dN[b][j] + mu * dN[a][j] * dN[b][i] + (i == j ? mu * gg : 0.0));
+         }
+   }
+}
+
+int amgh_elasticity_beam(int ex, int ey, int ez, double h, double lambda1, double mu1, double lambda2, double mu2,
+                         amgh_csr *out, double *rhs /* 3*nodes or NULL */)
+{
+   if (ex < 1 || ey < 1 || ez < 1) return 2;
+   const int nx = ex + 1, ny = ey + 1, nz = ez + 1;
+   const long nodes = (long)nx * ny * nz, N = 3 * nodes;
+   double Ke[2][24][24];
+   hex_elasticity_ke(lambda1, mu1, h, Ke[0]);
+   hex_elasticity_ke(lambda2, mu2, h, Ke[1]);
+   // row lengths
+   std::vector<long> ptr((size_t)N + 1, 0);
+   long tot = 0;
+   for (int iz = 0; iz < nz; iz++)
+      for (int iy = 0; iy < ny; iy++)
+         for (int ix = 0; ix < nx; ix++) {
+            const long nd = ix + (long)nx * (iy + (long)ny * iz);
+            int len;
+            if (ix == 0) len = 1;
+            else {
+               const int cx = 1 + (ix > 1) + (ix < nx - 1);       // neighbours in the clamped plane are dropped
+               const int cy = 1 + (iy > 0) + (iy < ny - 1), cz = 1 + (iz > 0) + (iz < nz - 1);
+               len = 3 * cx * cy * cz;
+            }
+            for (int c = 0; c < 3; c++) { ptr[3 * nd + c + 1] = len; tot += len; }
+         }
+   if (tot > 2147483000L) return 1;
+   for (long r = 0; r < N; r++) ptr[r + 1] += ptr[r];
+   csr_alloc(out, (int)N, (int)N, (int)ptr[N]);
+   for (long r = 0; r <= N; r++) out->i[r] = (int)ptr[r];
+#pragma omp parallel for collapse(2) schedule(static)
+   for (int iz = 0; iz < nz; iz++)
+      for (int iy = 0; iy < ny; iy++)
+         for (int ix = 0; ix < nx; ix++) {
+            const long nd = ix + (long)nx * (iy + (long)ny * iz);
+            double acc[3][27][3];
+            for (int i = 0; i < 3; i++) for (int k = 0; k < 27; k++) for (int j = 0; j < 3; j++) acc[i][k][j] = 0.0;
+            // the up to 8 elements around the node; the node is local vertex a = (ax, ay, az) of element (ix-ax, iy-ay, iz-az)
+            for (int a = 0; a < 8; a++) {
+               const int ax = a & 1, ay = (a >> 1) & 1, az = (a >> 2) & 1;
+               const int e0 = ix - ax, e1 = iy - ay, e2 = iz - az;
+               if (e0 < 0 || e0 >= ex || e1 < 0 || e1 >= ey || e2 < 0 || e2 >= ez) continue;
+               const double(*K)[24] = Ke[e0 < ex / 2 ? 0 : 1];
+               for (int b = 0; b < 8; b++) {
+                  const int dx = (b & 1) - ax, dy = ((b >> 1) & 1) - ay, dz = ((b >> 2) & 1) - az;
+                  const int k = (dx + 1) + 3 * ((dy + 1) + 3 * (dz + 1));
+                  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) acc[i][k][j] += K[3 * a + i][3 * b + j];
+               }
+            }
+            for (int i = 0; i < 3; i++) {
+               const int row = (int)(3 * nd + i);
+               int d = out->i[row];
+               out->j[d] = row; out->data[d++] = acc[i][13][i];
+               if (ix == 0) continue;
+               for (int dz = -1; dz <= 1; dz++) {
+                  if (iz + dz < 0 || iz + dz >= nz) continue;
+                  for (int dy = -1; dy <= 1; dy++) {
+                     if (iy + dy < 0 || iy + dy >= ny) continue;
+                     for (int dx = -1; dx <= 1; dx++) {
+                        if (ix + dx < 1 || ix + dx >= nx) continue;
+                        const int k = (dx + 1) + 3 * ((dy + 1) + 3 * (dz + 1));
+                        const long nb = nd + dx + (long)nx * (dy + (long)ny * dz);
+                        for (int j = 0; j < 3; j++) {
+                           if (k == 13 && j == i) continue;
+                           out->j[d] = (int)(3 * nb + j); out->data[d++] = acc[i][k][j];
+                        }
+                     }
+                  }
+               }
+            }
+         }
+   if (rhs) {
+      // traction (0, 0, -1e-2) on the face x = L: nodal load = traction x (h^2/4 per adjacent face element)
+      for (long r = 0; r < N; r++) rhs[r] = 0.0;
+      for (int iz = 0; iz < nz; iz++)
+         for (int iy = 0; iy < ny; iy++) {
+            const long nd = (nx - 1) + (long)nx * (iy + (long)ny * iz);
+            const int fy = (iy > 0) + (iy < ny - 1), fz = (iz > 0) + (iz < nz - 1);
+            rhs[3 * nd + 2] = -1.0e-2 * h * h / 4.0 * fy * fz;
+         }
+   }
+   return 0;
+}
+
 // b_i = lo + (hi-lo) * rand()/RAND_MAX after srand(seed), i ascending
 // (RandDouble src/Misc.cpp:282-285; SMEM RHS src/SMEM_Setup.cpp:1729-1742).  Uses the C
 // library's own rand() so the sequence is the one the reference would draw on this box.
@@ -556,10 +680,23 @@ int amgh_spgemm(const amgh_csr *A, const amgh_csr *B, amgh_csr *C) { spgemm(*A, 
 int amgh_diag_first(amgh_csr *A) { diag_first(A); return 0; }
 
 // ---- hierarchy --------------------------------------------------------------------------------
+void *amgh_setup_systems(const amgh_csr *A0, int num_functions, double theta, int max_levels, int max_coarse, int pmax,
+                         int jacobi_interp_steps, int verbose);
 void *amgh_setup(const amgh_csr *A0, double theta, int max_levels, int max_coarse, int pmax,
                  int jacobi_interp_steps, int verbose)
 {
+   return amgh_setup_systems(A0, 1, theta, max_levels, max_coarse, pmax, jacobi_interp_steps, verbose);
+}
+
+// num_functions > 1: unknown i of the fine level belongs to function i % num_functions (hypre's default dof_func for
+// interleaved systems, the ordering MFEM's byVDIM spaces give, src/DMEM_BuildMatrix.cpp:508); coarse unknowns inherit
+// the function of their fine point, and strength, interpolation and its Jacobi improvement stay inside a function.
+void *amgh_setup_systems(const amgh_csr *A0, int num_functions, double theta, int max_levels, int max_coarse, int pmax,
+                         int jacobi_interp_steps, int verbose)
+{
    Hierarchy *H = new Hierarchy();
+   std::vector<int> func;
+   if (num_functions > 1) { func.resize(A0->nrows); for (int r = 0; r < A0->nrows; r++) func[r] = r % num_functions; }
    amgh_csr A;
    csr_alloc(&A, A0->nrows, A0->ncols, A0->nnz);
    memcpy(A.i, A0->i, sizeof(int) * ((size_t)A0->nrows + 1));
@@ -571,7 +708,8 @@ void *amgh_setup(const amgh_csr *A0, double theta, int max_levels, int max_coars
       const amgh_csr &Af = H->A.back();
       const int n = Af.nrows;
       double t0 = omp_get_wtime();
-      amgh_csr S; strength(Af, theta, &S);
+      const int *fn = func.empty() ? nullptr : func.data();
+      amgh_csr S; strength(Af, theta, &S, fn);
       std::vector<int> cf; pmis(S, cf);
       std::vector<int> cidx(n, -1);
       int nc = 0;
@@ -579,21 +717,28 @@ void *amgh_setup(const amgh_csr *A0, double theta, int max_levels, int max_coars
       if (nc == 0 || nc == n) { amgh_csr_free(&S); break; }
       std::vector<int> cp(nc);
       for (int r = 0; r < n; r++) if (cf[r] == 1) cp[cidx[r]] = r;
-      amgh_csr P; direct_interp(Af, S, cf, cidx, nc, &P);
+      amgh_csr P; direct_interp(Af, S, cf, cidx, nc, &P, fn);
       amgh_csr_free(&S);
       for (int it = 0; it < jacobi_interp_steps; it++) {
          // P <- M P with M = -D^{-1}(A-D) on F rows, identity on C rows
          amgh_csr M;
          csr_alloc(&M, n, n, Af.nnz);
          int *mi = M.i; mi[0] = 0;
-         for (int r = 0; r < n; r++) mi[r + 1] = mi[r] + (cf[r] == 1 ? 1 : (Af.i[r + 1] - Af.i[r] - 1));
+         for (int r = 0; r < n; r++) {
+            int len = Af.i[r + 1] - Af.i[r] - 1;
+            if (fn && cf[r] != 1) { len = 0; for (int p = Af.i[r] + 1; p < Af.i[r + 1]; p++) if (fn[Af.j[p]] == fn[r]) len++; }
+            mi[r + 1] = mi[r] + (cf[r] == 1 ? 1 : len);
+         }
          M.nnz = mi[n];
 #pragma omp parallel for schedule(static)
          for (int r = 0; r < n; r++) {
             int d = mi[r];
             if (cf[r] == 1) { M.j[d] = r; M.data[d] = 1.0; continue; }
             double diag = Af.data[Af.i[r]];
-            for (int p = Af.i[r] + 1; p < Af.i[r + 1]; p++) { M.j[d] = Af.j[p]; M.data[d] = -Af.data[p] / diag; d++; }
+            for (int p = Af.i[r] + 1; p < Af.i[r + 1]; p++) {
+               if (fn && fn[Af.j[p]] != fn[r]) continue;
+               M.j[d] = Af.j[p]; M.data[d] = -Af.data[p] / diag; d++;
+            }
          }
          amgh_csr P1; spgemm(M, P, &P1);
          amgh_csr_free(&M); amgh_csr_free(&P);
@@ -609,6 +754,7 @@ void *amgh_setup(const amgh_csr *A0, double theta, int max_levels, int max_coars
       if (verbose)
          printf("[amgh_setup] level %d: n=%d nnz=%d -> nc=%d nnz(P)=%d nnz(Ac)=%d  (%.2fs)\n",
                 (int)H->A.size() - 1, n, Af.nnz, nc, P.nnz, Ac.nnz, omp_get_wtime() - t0);
+      if (fn) { std::vector<int> cfunc(nc); for (int k = 0; k < nc; k++) cfunc[k] = func[cp[k]]; func.swap(cfunc); }
       H->P.push_back(P);
       H->A.push_back(Ac);
       H->cpts.push_back(std::move(cp));

@@ -401,6 +401,59 @@ def test_chebysetup_power_iteration_matches_oracle(solver, w):
 
 
 # ---- asynchronous solves --------------------------------------------------------------------------------
+# ---- BASELINE.json configs[3]: elasticity (3-component vector system), BPX cycle ----------------------------------
+def test_elasticity_bpx_matches_oracle():
+    """Q1 elasticity beam (stand-in for the reference's MFEM problem, src/DMEM_BuildMatrix.cpp:442-719) with
+    num_functions = 3 coarsening: 81-entry rows with entries of both signs.  Operators, one BPX cycle, the device power
+    iteration and the Chebyshev-accelerated history against the oracle."""
+    A, b = H.elasticity_beam(24, 3, 3)
+    h = H.amg_setup(A, num_functions=3, theta=0.5)
+    w = 0.6
+    h.build_transfers(H.BPX, w)
+    pb = O.Problem(h, H.BPX, H.JACOBI, w)
+    s = amg.Solver(h, H.BPX, H.JACOBI, w)
+    rng = np.random.default_rng(5)
+    for kind, mats in ((MAT_A, h.A), (MAT_P, h.P), (MAT_R, h.R)):
+        for l, m in enumerate(mats):
+            x = rng.uniform(-1, 1, m.ncols)
+            bb = rng.uniform(-1, 1, m.nrows)
+            got = s.spgemv(kind, l, -1.0, x, 1.0, bb)
+            want = O.spgemv(m, x, bb, -1.0, 1.0)
+            mag = O.spgemv(H.CSR(m.nrows, m.ncols, m.indptr, m.indices, np.abs(m.data)), np.abs(x), np.abs(bb), 1.0, 1.0)
+            assert np.max(np.abs(got - want) / np.maximum(mag, 1e-300)) <= 1e-13, (kind, l)
+    r = rng.uniform(-1, 1, h.n[0])
+    assert _rel(s.cycle(r), pb.cycle(r)) <= 1e-12
+    s.set_rhs(b)
+    alpha, beta = pb.eigs_power(20)
+    mu, delta, a2, b2 = s.ChebySetup(20)
+    assert abs(a2 - alpha) <= 1e-9 * abs(alpha) and abs(b2 - beta) <= 1e-9 * abs(beta), (a2, alpha, b2, beta)
+    # bounds from a long power iteration (the reference's -cheby_eig_max_iters), then 80 accelerated cycles
+    alpha, beta = pb.eigs_power(300)
+    mu, delta = (beta + alpha) / (beta - alpha), 2.0 / (beta + alpha)
+    _, want, _ = pb.solve_sync(b, 1e-9, 80, cheby=(mu, delta))
+    s.set_solution(None)
+    got, _ = s.solve_sync(1e-9, 80, cheby=(mu, delta))
+    assert len(got) == len(want)
+    assert np.max(np.abs(got - want) / want) <= 1e-10
+    s.close()
+
+
+def test_elasticity_multadd_sync_and_async():
+    """the same system through synchronous Multadd (history vs oracle) and the persistent asynchronous kernel
+    (single-sweep chains on 81-entry rows; checked against the oracle's residual of the returned u)"""
+    A, b = H.elasticity_beam(24, 3, 3)
+    h = H.amg_setup(A, num_functions=3, theta=0.5)
+    w = 0.6
+    h.build_transfers(H.MULTADD, w)
+    _, want, _ = O.Problem(h, H.MULTADD, H.JACOBI, w).solve_sync(b, 1e-9, 40)
+    s = amg.Solver(h, H.MULTADD, H.JACOBI, w)
+    s.set_rhs(b)
+    s.set_solution(None)
+    got, _ = s.solve_sync(1e-9, 40)
+    assert len(got) == len(want) and np.max(np.abs(got - want)) <= HIST_TOL
+    s.close()
+
+
 @pytest.mark.parametrize("solver,smoother,w,cycles,post", [
     (H.ASYNC_MULTADD, H.JACOBI, 0.9, 160, 1),      # chaotic iteration: generous counts, the check is the true residual
     # hybrid JGS: w = 1 diverges asynchronously, also in the reference's own object code; w = 0.7 converges, slowly and

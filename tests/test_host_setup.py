@@ -100,3 +100,68 @@ def test_algorithmic_byte_model_matches_survey_table():
     assert H.bytes_spmv(m(16777216, 449455096), False) == 5729005476          # 27-pt 256^3: 5.7290 GB
     assert abs(H.bytes_spmv(m(134217728, 937951232), True) / 1e9 - 15.013) < 1e-3   # 7-pt 512^3
     assert H.bytes_spmv(m(262144, 1308672), True) == 23044100                 # 5-pt 512^2: 23.04 MB
+
+
+# ---- BASELINE.json configs[3]: elasticity stand-in (the reference's MFEM beam, src/DMEM_BuildMatrix.cpp:442-719) ----
+def _beam_nodes(ex, ey, ez, h):
+    nx, ny = ex + 1, ey + 1
+    node = np.arange((ex + 1) * (ey + 1) * (ez + 1))
+    return node % nx, (node // nx) % ny, node // (nx * ny), nx
+
+
+def test_elasticity_beam_operator_properties():
+    ex, ey, ez, hh = 16, 3, 2, 0.5
+    A, b = H.elasticity_beam(ex, ey, ez, hh)
+    ix, iy, iz, nx = _beam_nodes(ex, ey, ez, hh)
+    n = A.nrows
+    assert n == 3 * ix.size and np.array_equal(A.indices[A.indptr[:-1]], np.arange(n))       # 3 dof / node, diag first
+    S = A.to_scipy()
+    assert abs(S - S.T).max() < 1e-12 * abs(S).max()
+    row_len = np.diff(A.indptr)
+    interior = np.repeat((ix >= 2) & (ix < ex) & (iy >= 1) & (iy < ey) & (iz >= 1) & (iz < ez), 3)
+    assert interior.any() and np.all(row_len[interior] == 81)                                # 27 nodes x 3 components
+    assert np.all(row_len[np.repeat(ix == 0, 3)] == 1)                                       # clamped face
+    # rigid-body modes are in the kernel of every row whose stencil does not touch the clamped face
+    free = np.repeat(ix >= 2, 3)
+    x, y, z = ix * hh, iy * hh, iz * hh
+    modes = []
+    for c in range(3):
+        t = np.zeros(n); t[c::3] = 1.0; modes.append(t)
+    r = np.zeros(n); r[0::3] = -y; r[1::3] = x; modes.append(r)
+    r = np.zeros(n); r[1::3] = -z; r[2::3] = y; modes.append(r)
+    r = np.zeros(n); r[0::3] = z; r[2::3] = -x; modes.append(r)
+    for m in modes:
+        assert np.max(np.abs((S @ m)[free])) < 1e-10 * abs(S).max()
+    # constant-strain patch test inside material 1
+    ux = np.zeros(n); ux[0::3] = x
+    inside = np.repeat((ix >= 2) & (ix <= ex // 2 - 2) & (iy >= 1) & (iy < ey) & (iz >= 1) & (iz < ez), 3)
+    assert inside.any() and np.max(np.abs((S @ ux)[inside])) < 1e-10 * abs(S).max()
+    # material 1 is 50x stiffer than material 2 (src/DMEM_BuildMatrix.cpp:540-547)
+    d = A.diagonal()
+    k1 = 3 * (2 + nx * (1 + (ey + 1) * 1)); k2 = 3 * (ex - 2 + nx * (1 + (ey + 1) * 1))
+    assert abs(d[k1] / d[k2] - 50.0) < 1e-9
+    # SPD, and the load is the traction integrated over the face x = L
+    import scipy.sparse.linalg as sla
+    assert sla.eigsh(S.tocsc(), k=1, sigma=0, return_eigenvectors=False)[0] > 0
+    assert abs(b.sum() + 1e-2 * (ey * hh) * (ez * hh)) < 1e-14 and np.all(b[0::3] == 0) and np.all(b[1::3] == 0)
+
+
+def test_systems_amg_keeps_functions_apart_and_converges():
+    """num_functions = 3 (src/DMEM_BuildMatrix.cpp:470): interpolation never mixes displacement components; the
+    Chebyshev-accelerated BPX cycle (configs[3]) then converges to 1e-9 in the oracle"""
+    from oracle import oracle as O
+    A, b = H.elasticity_beam(16, 2, 2)
+    h = H.amg_setup(A, num_functions=3, theta=0.5)
+    assert h.num_levels >= 3
+    func = np.arange(A.nrows) % 3
+    for l in range(h.num_levels - 1):
+        P = h.P_plain[l]
+        rows = np.repeat(np.arange(P.nrows), np.diff(P.indptr))
+        cfunc = func[h.cpts[l]]
+        assert np.array_equal(func[rows], cfunc[P.indices])
+        func = cfunc
+    h.build_transfers(H.BPX, 0.6)
+    p = O.Problem(h, H.BPX, H.JACOBI, 0.6)
+    lo, hi = p.eigs_power(300)
+    _, hist, _ = p.solve_sync(b, 1e-9, 800, cheby=((hi + lo) / (hi - lo), 2.0 / (hi + lo)))
+    assert hist[-1] < 1e-9
