@@ -37,7 +37,8 @@ struct DistState {
    ncclComm_t comm = nullptr;
 #endif
    std::vector<DistLevel> lv;
-   std::vector<double *> ws, r, e;   // level layout
+   std::vector<double *> ws, r, e;   // level layout (ws = w/d, or 1/l1 for the L1-Jacobi smoother)
+   std::vector<double *> t, w;       // level layout: AFACx scratch (coarse-grid correction / its prolongation, fine residual)
    double *u = nullptr, *f = nullptr;   // u: level-0 layout; f: owned rows
    double *ecyc = nullptr, *dacc = nullptr;   // owned rows: cycle output and the accelerated increment (DMEM_ChebyUpdate)
    double *t0 = nullptr, *v0 = nullptr;  // level-0 layout: scratch of the factorised level-0 transfers (factor_level0)
@@ -199,12 +200,14 @@ static int dist_cycle(amgb_ctx *c, double *tgt, bool accumulate)
       return AMGB_OK;
    }
    const bool bpx = c->opt.solver == AMGB_SOLVER_BPX;                   // SYNC_BPX of DMEM_SyncAddCycle (src/DMEM_Mult.cpp:346-349)
+   const bool afacx = c->opt.solver == AMGB_SOLVER_AFACX;               // SYNC_AFACX (DMEM_SyncAFACCycle, src/DMEM_Mult.cpp:452-612)
    const bool direct = c->opt.coarse_solve && c->Ainv.rp != nullptr;   // DMEM: direct solve on the (replicated) coarsest level
    const int top = (direct || bpx) ? L : L - 1;                         // levels that contribute a correction
+   const int last_r = afacx ? L - 1 : top - 1;                          // AFACx level L-2 smooths r_{L-1} on its coarse side
    // level-0 transfers in factorised form (see enq_cycle in context.cu): plain P_0 / R_0 uploaded
    const bool fact0 = c->opt.factor_level0 && c->symmetric && top >= 2;
    const int off0 = d->lv[0].off();
-   for (int l = 0; l < top - 1; l++) {
+   for (int l = 0; l < last_r; l++) {
       const DistLevel &nx = d->lv[l + 1];
       const bool gather = d->lv[l].distributed && !nx.distributed;
       double *out = d->r[l + 1] + (gather ? nx.row_start : nx.off());
@@ -215,14 +218,22 @@ static int dist_cycle(amgb_ctx *c, double *tgt, bool accumulate)
       } else if ((rc = dist_spmv(c, c->R[l], false, l, d->r[l], out, epi(1.0, 0.0, nullptr), false))) return rc;
       if (gather && (rc = allgather_level(c, l + 1, d->r[l + 1]))) return rc;
    }
-   if (top == L - 1 && (rc = halo(c, L - 2, d->r[L - 2]))) return rc;
+   if (top == L - 1 && c->symmetric && (rc = halo(c, L - 2, d->r[L - 2]))) return rc;   // (the other smoothers read owned entries only)
    if (direct) enq_spmv(c, c->Ainv, false, d->r[L - 1], d->e[L - 1], epi(1.0, 0.0, nullptr), false);
    for (int l = 0; l < (direct ? L - 1 : top); l++) {
       if (fact0 && l == 0) continue;                  // e_0 is folded into the last launch of the cycle
       const DistLevel &lv = d->lv[l];
       const double *rown = d->r[l] + lv.off();
       const double *ws = d->ws[l] + lv.off();
-      if (c->symmetric)   // e = (w/d) o (2 r - (A diag(w/d)) r)
+      if (afacx) {
+         // src/SEQ_AMG.cpp:172-208 with one sweep on either side: u_c = s_{l+1} o r_{l+1};  e = P_l u_c (ghosts of u_c);
+         // r_f = r_l - A_l e (ghosts of e);  u_f = s_l o r_f
+         const DistLevel &nx = d->lv[l + 1];
+         c->launches += launch_scale(c->cfg, c->stream, c->A[l + 1].nrows, d->ws[l + 1] + nx.off(), d->r[l + 1] + nx.off(), d->t[l + 1] + nx.off());
+         if ((rc = dist_spmv(c, c->P[l], false, l + 1, d->t[l + 1], d->w[l] + lv.off(), epi(1.0, 0.0, nullptr), false))) return rc;
+         if ((rc = dist_spmv(c, c->A[l], false, l, d->w[l], d->t[l] + lv.off(), epi(-1.0, 1.0, rown), false))) return rc;
+         c->launches += launch_scale(c->cfg, c->stream, c->A[l].nrows, ws, d->t[l] + lv.off(), d->e[l] + lv.off());
+      } else if (c->symmetric)   // e = (w/d) o (2 r - (A diag(w/d)) r)
          enq_spmv(c, c->A[l], true, d->r[l], d->e[l] + lv.off(), epi(-1.0, 2.0, rown, 0.0, nullptr, ws), false);
       else
          c->launches += launch_scale(c->cfg, c->stream, c->A[l].nrows, ws, rown, d->e[l] + lv.off());
@@ -321,10 +332,16 @@ int amgb_dist_setup(amgb_ctx *c)
    if (d->ready) return amgb_fail(c, AMGB_ESTATE, "amgb_dist_setup already done");
    const int L = c->L;
    const amgb_options &o = c->opt;
-   if ((o.solver != AMGB_SOLVER_MULTADD && o.solver != AMGB_SOLVER_BPX) || o.smoother != AMGB_SMOOTH_JACOBI)
-      return amgb_fail(c, AMGB_EINVAL, "the partitioned path implements synchronous Multadd and BPX with weighted Jacobi");
+   if ((o.solver != AMGB_SOLVER_MULTADD && o.solver != AMGB_SOLVER_BPX && o.solver != AMGB_SOLVER_AFACX) ||
+       (o.smoother != AMGB_SMOOTH_JACOBI && o.smoother != AMGB_SMOOTH_L1_JACOBI))
+      return amgb_fail(c, AMGB_EINVAL, "the partitioned path implements synchronous Multadd, AFACx and BPX with weighted or L1 Jacobi");
    if (o.solver == AMGB_SOLVER_BPX && o.num_pre_smooth_sweeps != 1)
       return amgb_fail(c, AMGB_EINVAL, "partitioned BPX runs one Jacobi sweep per level");
+   if (o.solver == AMGB_SOLVER_AFACX && (o.num_fine_smooth_sweeps != 1 || o.num_coarse_smooth_sweeps != 1 || o.coarse_solve))
+      return amgb_fail(c, AMGB_EINVAL, "partitioned AFACx runs one fine and one coarse sweep per level, SMEM coarsest-level convention");
+   if (o.solver == AMGB_SOLVER_MULTADD && o.num_fine_smooth_sweeps != 1)
+      return amgb_fail(c, AMGB_EINVAL, "partitioned Multadd runs one smoothing sweep per level");
+   const bool l1s = o.smoother == AMGB_SMOOTH_L1_JACOBI;
    if ((int)d->lv.size() != L) return amgb_fail(c, AMGB_ESTATE, "level layouts missing");
    int rc;
    for (int l = 0; l < L; l++) {
@@ -341,15 +358,20 @@ int amgb_dist_setup(amgb_ctx *c)
       }
    }
    d->ws.assign(L, nullptr); d->r.assign(L, nullptr); d->e.assign(L, nullptr);
+   d->t.assign(L, nullptr); d->w.assign(L, nullptr);
    for (int l = 0; l < L; l++) {
       const DistLevel &lv = d->lv[l];
       const size_t bytes = sizeof(double) * (size_t)lv.n_ext();
       if ((rc = amgb_dev_alloc_bytes(c, (void **)&d->ws[l], bytes, true))) return rc;
       if ((rc = amgb_dev_alloc_bytes(c, (void **)&d->r[l], bytes, true))) return rc;
       if ((rc = amgb_dev_alloc_bytes(c, (void **)&d->e[l], bytes, true))) return rc;
-      // w/d of the owned rows, ghosts from the neighbours, then the column-scaled values of the one-pass
+      if (o.solver == AMGB_SOLVER_AFACX) {
+         if ((rc = amgb_dev_alloc_bytes(c, (void **)&d->t[l], bytes, true))) return rc;
+         if ((rc = amgb_dev_alloc_bytes(c, (void **)&d->w[l], bytes, true))) return rc;
+      }
+      // w/d (1/l1 for L1-Jacobi; the row sums of a local row block are the global ones) of the owned rows, ghosts from the neighbours, then the column-scaled values of the one-pass
       // symmetrised smoother (on replicated levels amgb_setup already did this)
-      CUDA_OK(c, cudaMemcpyAsync(d->ws[l] + lv.off(), c->ws[l], sizeof(double) * c->A[l].nrows, cudaMemcpyDeviceToDevice, c->stream));
+      CUDA_OK(c, cudaMemcpyAsync(d->ws[l] + lv.off(), l1s ? c->inv_l1[l] : c->ws[l], sizeof(double) * c->A[l].nrows, cudaMemcpyDeviceToDevice, c->stream));
       if (lv.distributed) {
          if ((rc = halo(c, l, d->ws[l]))) return rc;
          c->launches += launch_colscale(c->stream, c->A[l].nnz, c->A[l].ci, c->A[l].va, d->ws[l], const_cast<double *>(c->A[l].sval));

@@ -186,19 +186,24 @@ class DistEmulator:
     """Runs the plan with numpy kernels; communication through a `comm` object with
     sendrecv(send_lo, send_hi, n_lo, n_hi) -> (from_lo, from_hi), allgatherv(x, counts) and allreduce_sum(v)."""
 
-    def __init__(self, plan, comm, smooth_weight):
+    def __init__(self, plan, comm, smooth_weight, solver=H.MULTADD, smoother=H.JACOBI, symmetric=True):
         import scipy.sparse as sp
         self.pl, self.comm, self.w = plan, comm, smooth_weight
+        self.solver, self.smoother = solver, smoother
+        self.symmetric = bool(symmetric) and solver == H.MULTADD
         self.sp = sp
         self.A = [m.to_scipy() for m in plan.A]
         self.P = [m.to_scipy() for m in plan.P]
         self.R = [m.to_scipy() for m in plan.R]
-        # omega/d in the level's vector layout (ghosts filled by one halo exchange at setup)
+        # omega/d (1/l1 for L1-Jacobi: the row sums of a local row block are the global ones) in the level's vector
+        # layout (ghosts filled by one halo exchange at setup)
         self.ws = []
         for l, lay in enumerate(plan.layouts):
-            d = plan.A[l].data[plan.A[l].indptr[:-1]]
             v = self.new_vec(l)
-            self.owned(l, v)[:] = smooth_weight / d
+            if smoother == H.L1_JACOBI:
+                self.owned(l, v)[:] = 1.0 / np.add.reduceat(np.abs(plan.A[l].data), plan.A[l].indptr[:-1])
+            else:
+                self.owned(l, v)[:] = smooth_weight / plan.A[l].data[plan.A[l].indptr[:-1]]
             self.halo(l, v)
             self.ws.append(v)
 
@@ -219,20 +224,30 @@ class DistEmulator:
         v[lay.halo_lo + lay.n_owned:] = hi
 
     def smooth_symmetric(self, l, r):
-        """e = (w/d) o (2 r - A ((w/d) o r)) on the owned rows; r must have valid ghosts"""
+        """e = s o (2 r - A (s o r)) on the owned rows, s = w/d or 1/l1; r must have valid ghosts"""
         ws = self.ws[l]
         t = self.A[l] @ (ws * r)
         e = self.new_vec(l)
         self.owned(l, e)[:] = self.owned(l, ws) * (2.0 * self.owned(l, r) - t)
         return e
 
+    def smooth_plain(self, l, r):
+        """one (L1-)Jacobi sweep from a zero guess: e = s o r on the owned rows"""
+        e = self.new_vec(l)
+        self.owned(l, e)[:] = self.owned(l, self.ws[l]) * self.owned(l, r)
+        return e
+
     def cycle(self, r0):
-        """one synchronous Multadd cycle (symmetrised Jacobi) on the residual r0 (level-0 layout, owned part
-        valid); returns the correction in level-0 layout (owned part valid)"""
+        """one synchronous additive cycle -- Multadd (symmetrised or plain Jacobi), AFACx or BPX, one sweep per level --
+        on the residual r0 (level-0 layout, owned part valid); returns the correction in level-0 layout (owned part
+        valid).  Mirrors dist_cycle of csrc/dist.cu."""
         pl = self.pl
         L = pl.num_levels
+        afacx, bpx = self.solver == H.AFACX, self.solver == H.BPX
+        top = L if bpx else L - 1                   # levels that contribute a correction
+        last_r = L - 1 if afacx else top - 1        # coarsest residual the cycle reads
         r = [r0] + [None] * (L - 1)
-        for l in range(L - 2):
+        for l in range(last_r):
             self.halo(l, r[l])
             nxt = pl.layouts[l + 1]
             y = self.R[l] @ r[l]
@@ -242,10 +257,25 @@ class DistEmulator:
             else:
                 v[:] = self.comm.allgatherv(y, pl.all_counts[l + 1])
             r[l + 1] = v
-        if L >= 2:
+        if self.symmetric and L >= 2:
             self.halo(L - 2, r[L - 2])
-        e = [self.smooth_symmetric(l, r[l]) for l in range(L - 1)]
-        for l in range(L - 3, -1, -1):
+        if afacx:
+            # src/SEQ_AMG.cpp:172-208: u_c = S_{l+1} r_{l+1}; e = P_l u_c; r_f = r_l - A_l e; u_f = S_l r_f
+            e = []
+            for l in range(L - 1):
+                uc = self.smooth_plain(l + 1, r[l + 1])
+                self.halo(l + 1, uc)
+                t = self.new_vec(l)
+                self.owned(l, t)[:] = self.P[l] @ uc
+                self.halo(l, t)
+                rf = self.new_vec(l)
+                self.owned(l, rf)[:] = self.owned(l, r[l]) - self.A[l] @ t
+                e.append(self.smooth_plain(l, rf))
+        elif self.symmetric:
+            e = [self.smooth_symmetric(l, r[l]) for l in range(top)]
+        else:
+            e = [self.smooth_plain(l, r[l]) for l in range(top)]
+        for l in range(top - 2, -1, -1):
             self.halo(l + 1, e[l + 1])
             self.owned(l, e[l])[:] += self.P[l] @ e[l + 1]
         return e[0]

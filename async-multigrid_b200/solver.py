@@ -24,7 +24,7 @@ ABI_SYMBOLS = [
     "amgb_set_num_levels", "amgb_set_matrix", "amgb_set_options", "amgb_setup",
     "amgb_set_rhs", "amgb_set_solution", "amgb_get_solution", "amgb_get_residual",
     "amgb_spgemv", "amgb_spgemv_transpose", "amgb_smooth", "amgb_norm2", "amgb_cycle", "amgb_eigs_power", "amgb_solve_sync", "amgb_solve_async",
-    "amgb_smem_solve", "amgb_time_residual", "amgb_level_storage", "amgb_time_spmv", "amgb_stream_stats", "amgb_l2_arena_bytes",
+    "amgb_async_groups", "amgb_smem_solve", "amgb_time_residual", "amgb_level_storage", "amgb_time_spmv", "amgb_stream_stats", "amgb_l2_arena_bytes",
     "amgb_dist_unique_id", "amgb_dist_init", "amgb_dist_set_level", "amgb_dist_setup", "amgb_dist_set_rhs",
     "amgb_dist_get_solution", "amgb_dist_solve_sync", "amgb_dist_solve_sync_accel", "amgb_dist_stats",
     "amgb_ipc_export_solution", "amgb_ipc_open_peers", "amgb_async_dist_correct", "amgb_residual_norm", "amgb_stream_synchronize",
@@ -332,11 +332,12 @@ def dist_unique_id():
 
 
 class DistSolver:
-    """One rank of the row-partitioned synchronous Multadd solve (DMEM_Add replacement).  `plan` is a
+    """One rank of the row-partitioned synchronous solve -- Multadd, AFACx or BPX with weighted / L1 Jacobi (DMEM_Add /
+    DMEM_SyncAdd replacement).  `plan` is a
     partition.RankPlan; `uid` the 128-byte id from dist_unique_id() of rank 0."""
 
     def __init__(self, plan, uid, smooth_weight=1.0, num_pre=1, num_post=1, use_sell=True, use_stream=True,
-                 coarse_solve=False, solver=H.MULTADD, factor_level0=False, device=0):
+                 coarse_solve=False, solver=H.MULTADD, factor_level0=False, device=0, smoother=H.JACOBI):
         self.L = load_library()
         self.plan = plan
         self.ctx = C.c_void_p()
@@ -346,7 +347,7 @@ class DistSolver:
         self._ck(self.L.amgb_dist_init(self.ctx, uid, plan.rank, plan.nranks))
         o = Options()
         self.L.amgb_default_options(C.byref(o))
-        o.solver, o.smoother, o.smooth_weight = solver, H.JACOBI, smooth_weight
+        o.solver, o.smoother, o.smooth_weight = solver, smoother, smooth_weight
         o.num_pre_smooth_sweeps, o.num_post_smooth_sweeps = num_pre, num_post
         o.use_sell, o.use_stream = int(use_sell), int(use_stream)
         o.coarse_solve = int(coarse_solve)

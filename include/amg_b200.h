@@ -131,6 +131,11 @@ int amgb_eigs_power(amgb_ctx *ctx, int iters, double *eig_min, double *eig_max);
 int amgb_solve_async(amgb_ctx *ctx, int num_cycles, int converge_type, int *corrections_per_level,
                      double *relres, double *solve_seconds);
 
+/* CTA groups of the persistent kernel, sized by the reference's work model (PartitionLevels / BALANCED_THREADS,
+ * src/SMEM_Setup.cpp:770-868,1083-1160): cta_begin[num_levels + 1], *grid = total CTAs.  Valid after the first
+ * amgb_solve_async. */
+int amgb_async_groups(amgb_ctx *ctx, int *cta_begin, int *grid);
+
 /* Drop-in for one whole SMEM_Solve call with HOST buffers (what SMEM_Main's run loop would call,
  * src/SMEM_Main.cpp:694-757): uploads f, zeroes u (InitSolve), runs the sync or async solve named
  * by opt.solver, downloads u. */
@@ -151,7 +156,7 @@ int amgb_l2_arena_bytes(amgb_ctx *ctx, long long *used, long long *capacity);
 
 /* ---- multi-GPU (DMEM replacement; one process per GPU) ------------------------------------
  * Replaces DMEM_Add / DMEM_SyncAdd (src/DMEM_Add.cpp:20-178, src/DMEM_Mult.cpp:263-450) for the synchronous
- * Multadd cycle: hypre's ParCSR halo exchange and DMEM_Comm (src/DMEM_Comm.cpp:81-382) become NCCL
+ * Multadd, AFACx (DMEM_SyncAFACCycle, src/DMEM_Mult.cpp:452-612) and BPX cycles with weighted or L1 Jacobi, one sweep per level: hypre's ParCSR halo exchange and DMEM_Comm (src/DMEM_Comm.cpp:81-382) become NCCL
  * send/recv between row-neighbours, the residual norm an ncclAllReduce (src/DMEM_Misc.cpp:398-433).
  * Call order: amgb_create, amgb_dist_init, amgb_set_options, amgb_set_num_levels, amgb_dist_set_level for
  * EVERY level, then the amgb_set_matrix calls (LOCAL row blocks whose column

@@ -88,14 +88,32 @@ def test_single_rank_bpx_matches_oracle():
     s.close()
 
 
-def _worker(rank, world, port, uid_q, res_q):
+@pytest.mark.parametrize("solver,smoother,w,post", [(H.AFACX, H.JACOBI, 0.6, 1), (H.AFACX, H.L1_JACOBI, 0.9, 1),
+                                                     (H.MULTADD, H.L1_JACOBI, 0.9, 1), (H.MULTADD, H.L1_JACOBI, 0.9, 0)])
+def test_single_rank_afacx_and_l1_match_oracle(solver, smoother, w, post):
+    """SYNC_AFACX (DMEM_SyncAFACCycle, src/DMEM_Mult.cpp:452-612; meaning src/SEQ_AMG.cpp:172-208) and the L1-Jacobi
+    smoother in the partitioned path"""
+    A = H.laplacian("7pt", 18)
+    h = H.amg_setup(A)
+    h.build_transfers(solver, w, smooth_interp_type=smoother, num_pre=1, num_post=post)
+    b = H.rand_rhs(A.nrows)
+    s = amg.DistSolver(PT.RankPlan(h, 1, 0), amg.solver.dist_unique_id(), w, num_pre=1, num_post=post, solver=solver, smoother=smoother)
+    s.set_rhs(b)
+    hist, _ = s.solve_sync(1e-9, 100)
+    _, want, _ = O.Problem(h, solver, smoother, w, num_pre=1, num_post=post).solve_sync(b, 1e-9, 100)
+    assert len(hist) == len(want) and hist[-1] < 1e-9
+    assert np.max(np.abs(hist - want)) <= HIST_TOL
+    s.close()
+
+
+def _worker(rank, world, port, uid_q, res_q, solver=H.MULTADD, w=0.9):
     sys.path.insert(0, ROOT)
     import async_multigrid_b200 as amg2
     from async_multigrid_b200 import hierarchy as H2, partition as PT2
-    w = 0.9
     A = H2.laplacian("7pt", 32)
     h = H2.amg_setup(A)
-    h.build_transfers(H2.MULTADD, w, factor_level0=True)      # plain P_0 / R_0: the factorised form adds two halo exchanges
+    fact = solver == H2.MULTADD
+    h.build_transfers(solver, w, factor_level0=fact)      # Multadd: plain P_0 / R_0, the factorised form adds two halo exchanges
     b = H2.rand_rhs(A.nrows)
     plan = PT2.RankPlan(h, world, rank, plane=32 * 32, min_rows_per_rank=256)
     if rank == 0:
@@ -104,7 +122,7 @@ def _worker(rank, world, port, uid_q, res_q):
             uid_q.put(uid)
     else:
         uid = uid_q.get(timeout=120)
-    s = amg2.DistSolver(plan, uid, w, factor_level0=True, device=rank)
+    s = amg2.DistSolver(plan, uid, w, factor_level0=fact, device=rank, solver=solver)
     l0 = plan.layouts[0]
     s.set_rhs(b[l0.row_start:l0.row_start + l0.n_owned])
     hist, secs = s.solve_sync(1e-9, 100)
@@ -114,22 +132,26 @@ def _worker(rank, world, port, uid_q, res_q):
     s.close()
 
 
-def test_two_gpus_match_global_oracle():
+@pytest.mark.parametrize("solver,w", [(H.MULTADD, 0.9), (H.AFACX, 0.6)])
+def test_two_gpus_match_global_oracle(solver, w):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     uid_q, res_q = ctx.Queue(), ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, 0, uid_q, res_q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, 0, uid_q, res_q, solver, w)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted([res_q.get(timeout=300) for _ in range(2)], key=lambda x: x[0])
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    h, b = _setup("7pt", 32, 0.9)
-    _, want, _ = O.Problem(h, H.MULTADD, H.JACOBI, 0.9).solve_sync(b, 1e-9, 100)
+    A = H.laplacian("7pt", 32)
+    h = H.amg_setup(A)
+    h.build_transfers(solver, w)
+    b = H.rand_rhs(A.nrows)
+    _, want, _ = O.Problem(h, solver, H.JACOBI, w).solve_sync(b, 1e-9, 100)
     u = np.concatenate([r[2] for r in res])
     for rank, hist, _, _, num_dist, hb in res:
         assert num_dist >= 2 and hb > 0

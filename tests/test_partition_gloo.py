@@ -20,7 +20,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, prob, n, min_rows, q):
+def _worker(rank, world, port, prob, n, min_rows, q, solver=2, smoother=0, w=0.9, post=1):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     os.environ["OMP_NUM_THREADS"] = "1"
@@ -30,40 +30,48 @@ def _worker(rank, world, port, prob, n, min_rows, q):
     from oracle import oracle as O
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        w = 0.9
         A = H.laplacian(prob, n)
         h = H.amg_setup(A)
-        h.build_transfers(H.MULTADD, w)
+        h.build_transfers(solver, w, smooth_interp_type=smoother, num_pre=1, num_post=post)
         b = H.rand_rhs(A.nrows)
         plane = n * n if prob != "5pt" else n
         plan = PT.RankPlan(h, world, rank, plane=plane, min_rows_per_rank=min_rows)
         lay0 = plan.layouts[0]
-        em = PT.DistEmulator(plan, PT.TorchComm(), w)
+        em = PT.DistEmulator(plan, PT.TorchComm(), w, solver, smoother, symmetric=post > 0)
         # one cycle on the right-hand side vs the global oracle
         r0 = em.new_vec(0)
         em.owned(0, r0)[:] = b[lay0.row_start:lay0.row_start + lay0.n_owned]
         c = em.owned(0, em.cycle(r0))
-        pb = O.Problem(h, H.MULTADD, H.JACOBI, w)
+        pb = O.Problem(h, solver, smoother, w, num_pre=1, num_post=post)
         want = pb.cycle(b)[lay0.row_start:lay0.row_start + lay0.n_owned]
         err_cycle = float(np.max(np.abs(c - want)) / np.max(np.abs(want)))
         # whole solve: history vs the global oracle
-        u, hist = em.solve(b[lay0.row_start:lay0.row_start + lay0.n_owned], 1e-9, 100)
-        _, want_hist, _ = pb.solve_sync(b, 1e-9, 100)
+        ncyc = 10 if solver == H.BPX else 100              # BPX alone does not converge: compare the first cycles
+        u, hist = em.solve(b[lay0.row_start:lay0.row_start + lay0.n_owned], 1e-9, ncyc)
+        _, want_hist, _ = pb.solve_sync(b, 1e-9, ncyc)
         ok_len = len(hist) == len(want_hist)
-        err_hist = float(np.max(np.abs(hist - want_hist))) if ok_len else 1.0
+        err_hist = float(np.max(np.abs(hist - want_hist) / np.maximum(want_hist, 1.0))) if ok_len else 1.0
         q.put((rank, plan.num_dist, err_cycle, err_hist, ok_len, [l.n_owned for l in plan.layouts],
                [(l.halo_lo, l.halo_hi) for l in plan.layouts]))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,prob,n,min_rows", [(2, "7pt", 16, 64), (3, "7pt", 18, 32), (2, "5pt", 48, 100)])
-def test_distributed_plan_reproduces_global_cycle(world, prob, n, min_rows):
+# (solver, smoother, weight, post sweeps): Multadd symmetrised / plain / L1, AFACx (DMEM_SyncAFACCycle), BPX
+VARIANTS = {"multadd": (2, 0, 0.9, 1), "multadd_plain": (2, 0, 0.9, 0), "multadd_l1": (2, 6, 0.9, 1),
+            "afacx": (1, 0, 0.6, 1), "afacx_l1": (1, 6, 0.9, 1), "bpx": (3, 0, 0.6, 1)}
+
+
+@pytest.mark.parametrize("world,prob,n,min_rows,variant", [
+    (2, "7pt", 16, 64, "multadd"), (3, "7pt", 18, 32, "multadd"), (2, "5pt", 48, 100, "multadd"),
+    (2, "7pt", 16, 64, "afacx"), (3, "7pt", 18, 32, "afacx_l1"), (2, "7pt", 16, 64, "multadd_l1"),
+    (2, "7pt", 16, 64, "multadd_plain"), (2, "5pt", 48, 100, "bpx")])
+def test_distributed_plan_reproduces_global_cycle(world, prob, n, min_rows, variant):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, prob, n, min_rows, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, prob, n, min_rows, q) + VARIANTS[variant]) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=240) for _ in range(world)]
