@@ -48,6 +48,11 @@ struct DistState {
    double *partials3 = nullptr;          // 3 x npartials: interior / low boundary / high boundary launches
    bool overlap = true;
    bool ready = false;
+   // asynchronous fine-grid smoother across GPUs (DMEM_AsyncSmooth): the neighbours' level-0 solution vectors mapped
+   // through CUDA IPC, and where in them this rank's boundary entries belong (their ghost slots)
+   double *nbr_lo = nullptr, *nbr_hi = nullptr;   // rank-1 / rank+1
+   long nbr_lo_off = 0;                            // first ghost_hi entry of rank-1 ( = its halo_lo + n_owned )
+   double *sm_scratch = nullptr;
    long long halo_bytes = 0, collectives = 0;
 };
 
@@ -57,6 +62,8 @@ void amgb_dist_teardown(amgb_ctx *c)
 #ifdef AMG_HAVE_NCCL
       if (c->dist->comm) ncclCommDestroy(c->dist->comm);
 #endif
+      if (c->dist->nbr_lo) cudaIpcCloseMemHandle(c->dist->nbr_lo);
+      if (c->dist->nbr_hi) cudaIpcCloseMemHandle(c->dist->nbr_hi);
       if (c->dist->comm_stream) cudaStreamDestroy(c->dist->comm_stream);
       if (c->dist->ev_x) cudaEventDestroy(c->dist->ev_x);
       if (c->dist->ev_h) cudaEventDestroy(c->dist->ev_h);
@@ -88,14 +95,6 @@ bool amgb_dist_level_distributed(const amgb_ctx *c, int level)
    return c->dist && level < (int)c->dist->lv.size() && c->dist->lv[level].set && c->dist->lv[level].distributed;
 }
 
-#ifdef AMG_HAVE_NCCL
-#define NCCL_OK(c, call)                                                                                    \
-   do {                                                                                                     \
-      ncclResult_t r__ = (call);                                                                            \
-      if (r__ != ncclSuccess)                                                                               \
-         return amgb_fail((c), AMGB_ENCCL, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, ncclGetErrorString(r__)); \
-   } while (0)
-
 static inline SpmvEpilogue epi(double alpha, double beta, const double *b, double gamma = 0.0, const double *cc = nullptr,
                                const double *rs = nullptr)
 {
@@ -103,6 +102,14 @@ static inline SpmvEpilogue epi(double alpha, double beta, const double *b, doubl
    e.alpha = alpha; e.beta = beta; e.gamma = gamma; e.b = b; e.c = cc; e.rs = rs;
    return e;
 }
+
+#ifdef AMG_HAVE_NCCL
+#define NCCL_OK(c, call)                                                                                    \
+   do {                                                                                                     \
+      ncclResult_t r__ = (call);                                                                            \
+      if (r__ != ncclSuccess)                                                                               \
+         return amgb_fail((c), AMGB_ENCCL, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, ncclGetErrorString(r__)); \
+   } while (0)
 
 // ghosts of v (level layout) <- neighbours' boundary entries
 static int halo(amgb_ctx *c, int l, double *v, cudaStream_t st = nullptr)
@@ -495,6 +502,112 @@ int amgb_dist_solve_sync_accel(amgb_ctx *c, double tol, int max_cycles, int acce
    (void)tol; (void)max_cycles; (void)accel; (void)mu; (void)delta; (void)hist; (void)n_cycles; (void)solve_seconds;
    return amgb_fail(c, AMGB_ENCCL, "library built without NCCL");
 #endif
+}
+
+// ---- asynchronous fine-grid smoother across GPUs --------------------------------------------------------------------
+// DMEM_AsyncSmooth (src/DMEM_Smooth.cpp:16-313; solver option of DMEM_Add, src/DMEM_Add.cpp:88-95) with the ASYNC_JACOBI /
+// ASYNC_L1_JACOBI smoothers: every rank relaxes its rows of the fine system over and over, u = r ./ s, x += u, and ships
+// the new boundary values to its neighbours without ever waiting for theirs -- it simply uses whatever ghost values have
+// arrived (the reference keeps the residual incrementally, r -= A_diag e, r -= A_offd x_ghost as messages land,
+// :226-262; that is r = b - A [x_own | x_ghost] with the ghosts of the moment).  The reference's MPI_Isend / Test engine
+// (DMEM_Comm.cpp:81-382, finestIntra_outsideSend / Recv) becomes plain stores over NVLink: the neighbours' solution
+// vectors are mapped through CUDA IPC and this rank writes its boundary entries straight into their ghost slots.
+// Stop rule: the reference's LOCAL one -- every rank stops after `sweeps` own relaxations (AsyncSmoothCheckConverge :340-349).
+int amgb_dist_ipc_export_solution(amgb_ctx *c, unsigned char handle64[64])
+{
+   NEED_READY(c);
+   if (!c->dist || !c->dist->ready) return amgb_fail(c, AMGB_ESTATE, "amgb_dist_setup not called");
+   cudaIpcMemHandle_t h;
+   CUDA_OK(c, cudaIpcGetMemHandle(&h, c->dist->u));
+   memcpy(handle64, &h, 64);
+   return AMGB_OK;
+}
+
+// handle_lo / handle_hi: the exported handles of rank-1 / rank+1 (NULL at the ends of the chain, or for a neighbour that
+// lives in this very process); lo_ghost_offset = index of rank-1's first ghost_hi entry in ITS level-0 vector
+// (its halo_lo + its n_owned).  rank+1's ghost_lo entries start at index 0 of its vector.
+int amgb_dist_ipc_open_neighbours(amgb_ctx *c, const unsigned char *handle_lo, long long lo_ghost_offset, const unsigned char *handle_hi)
+{
+   NEED_READY(c);
+   DistState *d = c->dist;
+   if (!d || !d->ready) return amgb_fail(c, AMGB_ESTATE, "amgb_dist_setup not called");
+   if (d->nbr_lo || d->nbr_hi) return amgb_fail(c, AMGB_ESTATE, "neighbours already mapped");
+   if ((handle_lo && d->rank == 0) || (handle_hi && d->rank == d->nranks - 1) || lo_ghost_offset < 0)
+      return amgb_fail(c, AMGB_EINVAL, "no such neighbour");
+   cudaIpcMemHandle_t h;
+   void *ptr = nullptr;
+   if (handle_lo) {
+      memcpy(&h, handle_lo, 64);
+      CUDA_OK(c, cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+      d->nbr_lo = (double *)ptr;
+      d->nbr_lo_off = (long)lo_ghost_offset;
+   }
+   if (handle_hi) {
+      memcpy(&h, handle_hi, 64);
+      CUDA_OK(c, cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+      d->nbr_hi = (double *)ptr;
+   }
+   return AMGB_OK;
+}
+
+// `sweeps` relaxations of this rank's rows of A_0 x = f from the resident x (amgb_dist_solve_sync leaves its solution there;
+// amgb_dist_set_rhs + a fresh context start from x = 0), enqueued on the context's stream; returns without waiting for
+// the GPU.  Every sweep: x_own <- x_own + s o (f - A_0 [ghost_lo | x_own | ghost_hi]), then the boundary entries go to
+// the neighbours' ghost slots.  With one rank this is `sweeps` sweeps of (L1-)Jacobi.
+int amgb_dist_async_smooth(amgb_ctx *c, int sweeps)
+{
+   NEED_READY(c);
+   DistState *d = c->dist;
+   if (!d || !d->ready) return amgb_fail(c, AMGB_ESTATE, "amgb_dist_setup not called");
+   if (sweeps < 0) return amgb_fail(c, AMGB_EINVAL, "sweeps < 0");
+   const DistLevel &L0 = d->lv[0];
+   if (L0.distributed && ((d->rank > 0 && L0.send_lo && !d->nbr_lo) || (d->rank < d->nranks - 1 && L0.send_hi && !d->nbr_hi)))
+      return amgb_fail(c, AMGB_ESTATE, "amgb_dist_ipc_open_neighbours not called");
+   const int nown = c->A[0].nrows;
+   int rc;
+   if (!d->sm_scratch && (rc = amgb_dev_alloc_bytes(c, (void **)&d->sm_scratch, sizeof(double) * (size_t)std::max(1, nown), true))) return rc;
+   double *uo = d->u + L0.off();
+   const double *so = d->ws[0] + L0.off();
+   for (int k = 0; k < sweeps; k++) {
+      enq_spmv(c, c->A[0], false, d->u, d->sm_scratch, epi(-1.0, 1.0, d->f, 1.0, uo, so), false);
+      CUDA_OK(c, cudaMemcpyAsync(uo, d->sm_scratch, sizeof(double) * (size_t)nown, cudaMemcpyDeviceToDevice, c->stream));
+      if (d->nbr_lo && L0.send_lo)
+         CUDA_OK(c, cudaMemcpyAsync(d->nbr_lo + d->nbr_lo_off, uo, sizeof(double) * (size_t)L0.send_lo, cudaMemcpyDefault, c->stream));
+      if (d->nbr_hi && L0.send_hi)
+         CUDA_OK(c, cudaMemcpyAsync(d->nbr_hi, uo + L0.n_owned - L0.send_hi, sizeof(double) * (size_t)L0.send_hi, cudaMemcpyDefault, c->stream));
+      d->halo_bytes += 8LL * ((d->nbr_lo ? L0.send_lo : 0) + (d->nbr_hi ? L0.send_hi : 0));
+   }
+   CUDA_OK(c, cudaGetLastError());
+   return AMGB_OK;
+}
+
+// global ||f - A_0 x||_2 of the resident vectors: a synchronised halo exchange, the residual and an all-reduce (collective)
+int amgb_dist_residual_norm(amgb_ctx *c, double *norm)
+{
+   NEED_READY(c);
+#ifdef AMG_HAVE_NCCL
+   DistState *d = c->dist;
+   if (!d || !d->ready) return amgb_fail(c, AMGB_ESTATE, "amgb_dist_setup not called");
+   if (!norm) return amgb_fail(c, AMGB_EINVAL, "null output");
+   int rc;
+   if ((rc = dist_residual(c))) return rc;
+   double ss;
+   if ((rc = amgb_fetch_scalar(c, &ss))) return rc;
+   *norm = sqrt(ss);
+   return AMGB_OK;
+#else
+   (void)norm;
+   return amgb_fail(c, AMGB_ENCCL, "library built without NCCL");
+#endif
+}
+
+int amgb_dist_zero_solution(amgb_ctx *c)
+{
+   NEED_READY(c);
+   if (!c->dist || !c->dist->ready) return amgb_fail(c, AMGB_ESTATE, "amgb_dist_setup not called");
+   CUDA_OK(c, cudaMemsetAsync(c->dist->u, 0, sizeof(double) * (size_t)c->dist->lv[0].n_ext(), c->stream));
+   CUDA_OK(c, cudaStreamSynchronize(c->stream));
+   return AMGB_OK;
 }
 
 // halo bytes sent and NCCL operations enqueued by this rank since amgb_dist_setup

@@ -148,7 +148,7 @@ class RankPlan:
         self.nranks, self.rank = nranks, rank
         self.num_levels = h.num_levels
         starts, num_dist, halos = plan if plan is not None else plan_layouts(h, nranks, plane, min_rows_per_rank)
-        self.starts, self.num_dist = starts, num_dist
+        self.starts, self.num_dist, self.halos = starts, num_dist, halos
         self.layouts = rank_layouts(h, nranks, rank, starts, num_dist, halos)
         self.all_counts = [np.diff(s).astype(np.int64) for s in starts]
         L = h.num_levels

@@ -27,6 +27,8 @@ ABI_SYMBOLS = [
     "amgb_async_groups", "amgb_smem_solve", "amgb_time_residual", "amgb_level_storage", "amgb_time_spmv", "amgb_stream_stats", "amgb_l2_arena_bytes",
     "amgb_dist_unique_id", "amgb_dist_init", "amgb_dist_set_level", "amgb_dist_setup", "amgb_dist_set_rhs",
     "amgb_dist_get_solution", "amgb_dist_solve_sync", "amgb_dist_solve_sync_accel", "amgb_dist_stats",
+    "amgb_dist_ipc_export_solution", "amgb_dist_ipc_open_neighbours", "amgb_dist_async_smooth", "amgb_dist_residual_norm",
+    "amgb_dist_zero_solution",
     "amgb_ipc_export_solution", "amgb_ipc_open_peers", "amgb_async_dist_correct", "amgb_residual_norm", "amgb_stream_synchronize",
 ]
 
@@ -96,6 +98,11 @@ def load_library():
     L.amgb_dist_solve_sync.argtypes = [C.c_void_p, C.c_double, C.c_int, DP, IP, DP]
     L.amgb_dist_solve_sync_accel.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, DP, IP, DP]
     L.amgb_dist_stats.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+    L.amgb_dist_ipc_export_solution.argtypes = [C.c_void_p, C.c_char_p]
+    L.amgb_dist_ipc_open_neighbours.argtypes = [C.c_void_p, C.c_char_p, C.c_longlong, C.c_char_p]
+    L.amgb_dist_async_smooth.argtypes = [C.c_void_p, C.c_int]
+    L.amgb_dist_residual_norm.argtypes = [C.c_void_p, DP]
+    L.amgb_dist_zero_solution.argtypes = [C.c_void_p]
     _lib = L
     return L
 
@@ -401,3 +408,33 @@ class DistSolver:
         hb, ops = C.c_longlong(0), C.c_longlong(0)
         self._ck(self.L.amgb_dist_stats(self.ctx, C.byref(hb), C.byref(ops)))
         return hb.value, ops.value
+
+    # ---- DMEM_AsyncSmooth: asynchronous (L1-)Jacobi on the fine grid across GPUs (src/DMEM_Smooth.cpp:16-313) ----
+    def ipc_export_solution(self):
+        buf = C.create_string_buffer(64)
+        self._ck(self.L.amgb_dist_ipc_export_solution(self.ctx, buf))
+        return buf.raw
+
+    def ipc_open_neighbours(self, handle_lo, handle_hi):
+        """handles exported by rank-1 / rank+1 (None where there is no such rank)"""
+        off = 0
+        if handle_lo is not None:
+            lo, _ = self.plan.halos[0][self.plan.rank - 1]
+            off = int(lo) + int(self.plan.all_counts[0][self.plan.rank - 1])
+        self._ck(self.L.amgb_dist_ipc_open_neighbours(self.ctx, handle_lo, off, handle_hi))
+
+    def DMEM_AsyncSmooth(self, sweeps):
+        """enqueue `sweeps` own relaxations; returns without waiting for the GPU or for any peer"""
+        self._ck(self.L.amgb_dist_async_smooth(self.ctx, int(sweeps)))
+
+    def zero_solution(self):
+        self._ck(self.L.amgb_dist_zero_solution(self.ctx))
+
+    def synchronize(self):
+        self._ck(self.L.amgb_stream_synchronize(self.ctx))
+
+    def residual_norm(self):
+        """global ||f - A_0 x||_2 (collective)"""
+        v = C.c_double(0)
+        self._ck(self.L.amgb_dist_residual_norm(self.ctx, C.byref(v)))
+        return v.value

@@ -185,6 +185,22 @@ int amgb_dist_solve_sync_accel(amgb_ctx *ctx, double tol, int max_cycles, int ac
                                double *relres_hist, int *n_cycles, double *solve_seconds);
 int amgb_dist_stats(amgb_ctx *ctx, long long *halo_bytes_sent, long long *nccl_ops);
 
+/* ---- asynchronous fine-grid smoother across GPUs: DMEM_AsyncSmooth (src/DMEM_Smooth.cpp:16-313) with the ASYNC_JACOBI /
+ * ASYNC_L1_JACOBI smoothers, the `-smoother async_j` solver of DMEM_Add (src/DMEM_Add.cpp:88-95).  Every rank relaxes its
+ * rows of A_0 x = f again and again, x_own += s o (f - A_0 [ghosts | x_own]), with whatever ghost values have arrived, and
+ * writes its new boundary entries straight into the neighbours' ghost slots (their level-0 vectors mapped through CUDA IPC:
+ * stores over NVLink replace finestIntra_outsideSend / Recv and DMEM_Comm's Isend / Test engine).  Nobody waits.
+ * amgb_dist_ipc_export_solution: 64-byte handle of this rank's level-0 vector.  amgb_dist_ipc_open_neighbours: the handles
+ * of rank-1 / rank+1 (NULL where there is none); lo_ghost_offset = rank-1's halo_lo + n_owned (index of its first ghost_hi
+ * entry).  amgb_dist_async_smooth enqueues `sweeps` relaxations (LOCAL stop rule, AsyncSmoothCheckConverge :340-349) and
+ * returns without synchronising.  amgb_dist_residual_norm: global ||f - A_0 x||_2 (collective; synchronises). */
+int amgb_dist_ipc_export_solution(amgb_ctx *ctx, unsigned char handle64[64]);
+int amgb_dist_ipc_open_neighbours(amgb_ctx *ctx, const unsigned char *handle_lo, long long lo_ghost_offset,
+                                  const unsigned char *handle_hi);
+int amgb_dist_async_smooth(amgb_ctx *ctx, int sweeps);
+int amgb_dist_residual_norm(amgb_ctx *ctx, double *norm);
+int amgb_dist_zero_solution(amgb_ctx *ctx);
+
 /* ---- asynchronous additive solve across GPUs (DMEM async Multadd; one process per GPU) --------------------------
  * The reference assigns ranks to grids (src/DMEM_Setup.cpp:1638-1759): every grid's rank group holds the hierarchy
  * down to its level and full-length fine vectors, runs its own chain on a private residual and sends fine-level
