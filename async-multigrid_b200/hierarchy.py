@@ -20,6 +20,7 @@ ASYNC_GAUSS_SEIDEL = 5
 L1_JACOBI = 6
 MULT, AFACX, MULTADD, BPX = 0, 1, 2, 3
 ASYNC_AFACX, ASYNC_MULTADD = 5, 6
+IMPLICIT_EXTENDED_SYSTEM_BPX = 16   # `-solver iebpx` (src/Main.hpp:76, src/SMEM_ExtendedSystem.cpp)
 
 
 class _CSR(C.Structure):

@@ -600,5 +600,117 @@ void orc_eigs_power(const orc_problem *pb, int iters, double *eig_min, double *e
    free(u); free(e); free(f);
 }
 
+/* ---- implicit extended-system BPX solver (`-solver iebpx`), synchronous ----------------------------------------------
+ * SMEM_ExtendedSystemSolve with IMPLICIT_EXTENDED_SYSTEM_BPX, src/SMEM_ExtendedSystem.cpp:9-836 (+ ExtendedSystemImplicitMatVec
+ * :838-907).  Chebyshev-accelerated Jacobi on Griebel's semi-definite "generating system"  AA xx = bb  whose unknowns are the
+ * per-level vectors u_0 .. u_{L-1}; block (k,l) of AA is  A_k P^{k<-l}  for l >= k  and  R^{k<-l} A_l  for l < k  (never
+ * formed).  R = P^T, plain P (src/SMEM_Setup.cpp:262-274).  The solution of A x = f is x = sum_l P^{0<-l} u_l.
+ *   set-up (:112-136): f_{l+1} = R_l f_l; r0_ext = sqrt(sum_l |f_l|^2); y_l = 0; u_l = delta f_l / a_ii (the raw diagonal);
+ *                      e_l = A_l u_l
+ *   every iteration (:392-636), omega_0 = 2:
+ *     phase 1 (all levels from the same u, e):  z1_{L-1} = u_{L-1}, z1_k = P_k z1_{k+1} + u_k;
+ *                                               z2_0 = 0, z2_{k+1} = R_k (z2_k + e_k)
+ *     phase 2 (per level k):  z = A_k z1_k + z2_k;  r_k = f_k - z;  s = r_k ./ scale_k  (scale = a_ii/w, or the L1 norms);
+ *                             u_k <- y_k + omega (delta s + u_k - y_k),  y_k <- old u_k;  e_k = A_k u_k
+ *     omega <- 1 / (1 - omega / (2 mu)^2);  stop when the iteration counter reaches num_cycles, or -- from the second
+ *     iteration on -- when sqrt(sum_k |r_k|^2) / r0_ext < tol (:636-658; the counter starts at 1 and the loop is skipped
+ *     altogether for num_cycles <= 1, :271).
+ *   finish (:777-817): extended residual of the final iterate, x = sum_l P^{0<-l} u_l, r = f - A_0 x.
+ * ext_hist[it] (it >= 1) = sqrt(sum_k |r_k|^2)/r0_ext as measured in iteration it (the residual of the iterate that ENTERS
+ * the iteration); returns the final value of the reference's loc_iters (= grid.local_num_correct). */
+int orc_solve_iebpx(const orc_problem *pb, const double *f, double *x_out, double tol, int num_cycles, double mu, double delta,
+                    double *ext_hist, double *ext_relres, double *relres)
+{
+   const int L = pb->num_levels;
+   double **fl = (double **)malloc(sizeof(double *) * L), **u = (double **)malloc(sizeof(double *) * L);
+   double **y = (double **)malloc(sizeof(double *) * L), **e = (double **)malloc(sizeof(double *) * L);
+   double **z1 = (double **)malloc(sizeof(double *) * L), **z2 = (double **)malloc(sizeof(double *) * L);
+   double **z = (double **)malloc(sizeof(double *) * L), **t = (double **)malloc(sizeof(double *) * L);
+   for (int l = 0; l < L; l++) {
+      const size_t n = (size_t)pb->A[l].nrows;
+      fl[l] = (double *)calloc(n, sizeof(double)); u[l] = (double *)calloc(n, sizeof(double));
+      y[l] = (double *)calloc(n, sizeof(double)); e[l] = (double *)calloc(n, sizeof(double));
+      z1[l] = (double *)calloc(n, sizeof(double)); z2[l] = (double *)calloc(n, sizeof(double));
+      z[l] = (double *)calloc(n, sizeof(double)); t[l] = (double *)calloc(n, sizeof(double));
+   }
+   const int n0 = pb->A[0].nrows;
+   memcpy(fl[0], f, sizeof(double) * (size_t)n0);
+   double ss = 0.0;
+   for (int i = 0; i < n0; i++) ss += f[i] * f[i];
+   const double r0 = sqrt(ss);
+   for (int l = 0; l < L - 1; l++) {
+      orc_matvec(&pb->R[l], fl[l], fl[l + 1], 0, pb->R[l].nrows);
+      for (int i = 0; i < pb->A[l + 1].nrows; i++) ss += fl[l + 1][i] * fl[l + 1][i];
+   }
+   const double r0_ext = sqrt(ss);
+   for (int l = 0; l < L; l++) {
+      const orc_csr *A = &pb->A[l];
+      for (int i = 0; i < A->nrows; i++) u[l][i] = delta * fl[l][i] / A->data[A->i[i]];
+      orc_matvec(A, u[l], e[l], 0, A->nrows);
+   }
+   double omega = 2.0;
+   const double mu22 = (2.0 * mu) * (2.0 * mu);
+   int it = 1;
+   /* phases 1 of the loop and of the final ExtendedSystemImplicitMatVec are the same computation */
+#define ORC_EXT_PHASE1()                                                                         \
+   do {                                                                                          \
+      memcpy(z1[L - 1], u[L - 1], sizeof(double) * (size_t)pb->A[L - 1].nrows);                 \
+      for (int k = L - 2; k >= 0; k--) {                                                         \
+         orc_matvec(&pb->P[k], z1[k + 1], z1[k], 0, pb->P[k].nrows);                            \
+         for (int i = 0; i < pb->A[k].nrows; i++) z1[k][i] += u[k][i];                          \
+      }                                                                                          \
+      memset(z2[0], 0, sizeof(double) * (size_t)n0);                                            \
+      for (int k = 0; k < L - 1; k++) {                                                          \
+         for (int i = 0; i < pb->A[k].nrows; i++) t[k][i] = z2[k][i] + e[k][i];                 \
+         orc_matvec(&pb->R[k], t[k], z2[k + 1], 0, pb->R[k].nrows);                             \
+      }                                                                                          \
+   } while (0)
+   if (num_cycles > 1)
+      for (;;) {
+         ORC_EXT_PHASE1();
+         double rs = 0.0;
+         for (int k = 0; k < L; k++) {
+            const orc_csr *A = &pb->A[k];
+            orc_matvec(A, z1[k], z[k], 0, A->nrows);
+            for (int i = 0; i < A->nrows; i++) {
+               z[k][i] += z2[k][i];
+               const double r = fl[k][i] - z[k][i];
+               const double scale = (pb->smoother == ORC_L1_JACOBI) ? pb->l1[k][i] : A->data[A->i[i]] / pb->smooth_weight;
+               const double us = r / scale;
+               const double up = u[k][i];
+               u[k][i] = y[k][i] + omega * (delta * us + u[k][i] - y[k][i]);
+               y[k][i] = up;
+               rs += r * r;
+            }
+            orc_matvec(A, u[k], e[k], 0, A->nrows);
+         }
+         if (ext_hist) ext_hist[it] = sqrt(rs) / r0_ext;
+         const int measured = it > 1;                /* check_resnorm_flag && loc_iters > 1 (:618) */
+         omega = 1.0 / (1.0 - omega / mu22);
+         it++;
+         if (it == num_cycles) break;
+         if (measured && sqrt(rs) / r0_ext < tol) break;
+      }
+   ORC_EXT_PHASE1();
+   ss = 0.0;
+   for (int k = 0; k < L; k++) {
+      const orc_csr *A = &pb->A[k];
+      orc_matvec(A, z1[k], z[k], 0, A->nrows);
+      for (int i = 0; i < A->nrows; i++) { const double r = fl[k][i] - (z[k][i] + z2[k][i]); ss += r * r; }
+   }
+   if (ext_relres) *ext_relres = sqrt(ss) / r0_ext;
+   for (int k = L - 2; k >= 0; k--) {
+      orc_matvec(&pb->P[k], u[k + 1], e[k], 0, pb->P[k].nrows);
+      for (int i = 0; i < pb->A[k].nrows; i++) u[k][i] += e[k][i];
+   }
+   memcpy(x_out, u[0], sizeof(double) * (size_t)n0);
+   orc_residual(&pb->A[0], f, u[0], z[0]);
+   if (relres) *relres = orc_norm2(z[0], n0) / r0;
+   for (int l = 0; l < L; l++) { free(fl[l]); free(u[l]); free(y[l]); free(e[l]); free(z1[l]); free(z2[l]); free(z[l]); free(t[l]); }
+   free(fl); free(u); free(y); free(e); free(z1); free(z2); free(z); free(t);
+   return it;
+}
+#undef ORC_EXT_PHASE1
+
 int orc_max_threads(void) { return omp_get_max_threads(); }
 void orc_set_threads(int t) { omp_set_num_threads(t); }

@@ -140,6 +140,17 @@ class Problem:
         lib().orc_eigs_power(C.byref(self.c), iters, C.byref(a), C.byref(b))
         return a.value, b.value
 
+    def solve_iebpx(self, f, tol=1e-9, num_cycles=100, mu=1.0, delta=1.0):
+        """implicit extended-system BPX (`-solver iebpx`, src/SMEM_ExtendedSystem.cpp) -> dict(x, iters = the reference's
+        loc_iters, ext_hist[1..iters-1], ext_relres, relres)"""
+        x = np.zeros(self.h.n[0])
+        hist = np.zeros(max(num_cycles, 2) + 1)
+        er, rr = C.c_double(0), C.c_double(0)
+        lib().orc_solve_iebpx.restype = C.c_int
+        it = lib().orc_solve_iebpx(C.byref(self.c), dptr(np.ascontiguousarray(f)), dptr(x), C.c_double(tol), int(num_cycles),
+                                   C.c_double(mu), C.c_double(delta), dptr(hist), C.byref(er), C.byref(rr))
+        return dict(x=x, iters=it, ext_hist=hist[:it], ext_relres=er.value, relres=rr.value)
+
     def solve_async_sequential(self, f, num_cycles):
         u = np.zeros(self.h.n[0])
         counts = np.zeros(self.h.num_levels, dtype=np.int32)
@@ -295,6 +306,15 @@ class RefSolver:
         k = self.L.ref_solve(self.handle, num_cycles, tol, async_type, 1 if cheby else 0, mu, delta, precond,
                              dptr(u), dptr(hist), iptr(corr), C.byref(secs), C.byref(rr))
         return dict(u=u, hist=hist[:k + 1], cycles=k, corrections=corr, seconds=secs.value, relres=rr.value)
+
+    def solve_iebpx(self, num_cycles, tol=1e-9, mu=1.0, delta=1.0):
+        """SMEM_ExtendedSystemSolve, IMPLICIT_EXTENDED_SYSTEM_BPX, synchronous (handle created with solver = 16)"""
+        u = np.zeros(self.h.n[0])
+        er, rr = C.c_double(0), C.c_double(0)
+        self.L.ref_solve_iebpx.restype = C.c_int
+        self.L.ref_solve_iebpx.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, DP, DP, DP]
+        it = self.L.ref_solve_iebpx(self.handle, num_cycles, tol, mu, delta, dptr(u), C.byref(er), C.byref(rr))
+        return dict(x=u, iters=it, ext_relres=er.value, relres=rr.value)
 
     def solve_sync_det(self, num_cycles, tol=1e-9):
         """race-free run of the reference's grouped additive cycle (see ref_driver.cpp)"""

@@ -18,6 +18,7 @@
 #include "SMEM_MatVec.hpp"
 #include "SEQ_Smooth.hpp"
 #include "SMEM_Sync_AMG.hpp"
+#include "SMEM_ExtendedSystem.hpp"
 #include <cstdarg>
 
 static AllData *g_all = nullptr;
@@ -59,6 +60,11 @@ HYPRE_Int hypre_GaussElimSolve(hypre_ParAMGData *, HYPRE_Int, HYPRE_Int) { retur
 HYPRE_Int HYPRE_BoomerAMGSetPrintLevel(HYPRE_Solver, HYPRE_Int) { return 0; }
 HYPRE_Int HYPRE_BoomerAMGSetMaxIter(HYPRE_Solver, HYPRE_Int) { return 0; }
 HYPRE_Int hypre_ParVectorSetConstantValues(hypre_ParVector *, HYPRE_Complex) { return 0; }
+// referenced by SMEM_ExtendedSystem.cpp on its EXPLICIT_EXTENDED_SYSTEM_BPX branch only, which the driver never takes
+HYPRE_Int hypre_ParCSRMatrixMatvecOutOfPlace(HYPRE_Complex, hypre_ParCSRMatrix *, hypre_ParVector *, HYPRE_Complex, hypre_ParVector *, hypre_ParVector *) { abort(); }
+HYPRE_Int hypre_ParCSRMatrixMatvec(HYPRE_Complex, hypre_ParCSRMatrix *, hypre_ParVector *, HYPRE_Complex, hypre_ParVector *) { abort(); }
+HYPRE_Int hypre_ParVectorCopy(hypre_ParVector *, hypre_ParVector *) { abort(); }
+
 // HYPRE_IJMatrix as far as ReadBinary_fread_HypreParCSR (src/Misc.cpp:800-915) uses it: rows are set one at a time
 // and the assembled object is a ParCSR matrix whose (only) diag block is CSR.  As in hypre's IJ assembly the
 // diagonal entry is moved to the front of its row; the other entries keep the order they were set in.
@@ -217,7 +223,7 @@ void *ref_create(int L, const RefCSR *A, const RefCSR *P, const RefCSR *R, doubl
    // vectors (src/SMEM_Setup.cpp:280-419)
    VectorData *v = &ad->vector;
    HYPRE_Real ***arrs[] = {&v->f, &v->u, &v->u_prev, &v->u_fine, &v->u_fine_prev, &v->u_coarse, &v->u_coarse_prev,
-                           &v->y, &v->r, &v->r_fine, &v->r_coarse, &v->e, &v->z};
+                           &v->y, &v->r, &v->r_fine, &v->r_coarse, &v->e, &v->z, &v->u_smooth};
    for (auto a : arrs) {
       *a = (HYPRE_Real **)calloc(L, sizeof(HYPRE_Real *));
       for (int l = 0; l < L; l++) (*a)[l] = H->vec(A[l].nrows);
@@ -233,7 +239,9 @@ void *ref_create(int L, const RefCSR *A, const RefCSR *P, const RefCSR *R, doubl
                                &lv->y, &lv->r, &lv->r_coarse, &lv->r_fine, &lv->e, &lv->z, &lv->z1, &lv->z2};
          for (auto a : la) {
             *a = (HYPRE_Real **)calloc(L, sizeof(HYPRE_Real *));
-            for (int inner = 0; inner < level + 2 && inner < L; inner++) (*a)[inner] = H->vec(A[inner].nrows);
+            // every inner level for the implicit extended system (InitVectors, src/Misc.cpp:571-577), else level + 2
+            const int inner_end = solver == IMPLICIT_EXTENDED_SYSTEM_BPX ? L : level + 2;
+            for (int inner = 0; inner < inner_end && inner < L; inner++) (*a)[inner] = H->vec(A[inner].nrows);
          }
       }
    }
@@ -307,6 +315,20 @@ void *ref_create(int L, const RefCSR *A, const RefCSR *P, const RefCSR *R, doubl
                   bound(M, (M->num_nonzeros + nlt - 1) / nlt, nlt, st, &th->R_ns[inner][t], &th->R_ne[inner][t]);
                }
             }
+         // row_ns / row_ne: rows dealt round-robin into contiguous parts (src/SMEM_Setup.cpp:982-1005)
+         for (int inner = 0; inner < L; inner++) {
+            const int n = ad->grid.n[inner];
+            std::vector<int> parts(nlt, 0);
+            for (int cnt = 0; cnt < n;)
+               for (int i = 0; i < nlt && cnt < n; i++) { parts[i]++; cnt++; }
+            int disp = 0;
+            for (int i = 0; i < nlt; i++) {
+               const int t = th->level_threads[level][i];
+               th->row_ns[inner][t] = disp;
+               disp += parts[i];
+               th->row_ne[inner][t] = disp;
+            }
+         }
       }
    } else {
       for (int l = 0; l < L; l++) {
@@ -402,6 +424,28 @@ int ref_solve_sync_det(void *h, int num_cycles, double tol, double *u_out, doubl
    omp_destroy_lock(&ad->thread.lock);
    if (u_out) memcpy(u_out, ad->vector.u[0], sizeof(double) * n0);
    return done;
+}
+
+// SMEM_ExtendedSystemSolve (src/SMEM_ExtendedSystem.cpp:9-836) for IMPLICIT_EXTENDED_SYSTEM_BPX, the way SMEM_Main runs it
+// (InitSolve, then the solver: src/SMEM_Main.cpp:724-729).  The handle must have been created with solver = 16 and plain
+// P / R = P^T.  Returns local_num_correct of thread 0 (the final loc_iters).
+int ref_solve_iebpx(void *h, int num_cycles, double tol, double mu, double delta, double *u_out, double *ext_relres, double *relres)
+{
+   RefHandle *H = (RefHandle *)h;
+   AllData *ad = &H->all;
+   if (ad->input.solver != IMPLICIT_EXTENDED_SYSTEM_BPX) return -1;
+   ad->input.num_cycles = num_cycles;
+   ad->input.tol = tol;
+   ad->input.async_flag = 0;
+   ad->input.omp_parfor_flag = 0;
+   ad->cheby.mu = mu; ad->cheby.delta = delta;
+   omp_set_num_threads(ad->input.num_threads);
+   InitSolve(ad);
+   SMEM_ExtendedSystemSolve(ad);
+   if (u_out) memcpy(u_out, ad->vector.u[0], sizeof(double) * ad->grid.n[0]);
+   if (ext_relres) *ext_relres = ad->output.r_norm2_ext_sys / ad->output.r0_norm2_ext_sys;
+   if (relres) *relres = ad->output.r_norm2 / ad->output.r0_norm2;
+   return ad->grid.local_num_correct[0];
 }
 
 void ref_destroy(void *h) { delete (RefHandle *)h; }

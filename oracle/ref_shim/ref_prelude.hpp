@@ -1,14 +1,16 @@
 /* ref_prelude.hpp -- force-included (-include) before every reference translation unit.
  * src/Main.hpp is stale relative to the SMEM sources: the solve phase names
  * matrix.A_diag, L1_HYBRID_JACOBI_GAUSS_SEIDEL and CYCLE_PHASE_DOWN/UP, none of which it
- * declares.  The reference sources are compiled UNMODIFIED; this prelude injects the missing
+ * declares (nor vector.u_smooth, which SMEM_ExtendedSystem.cpp uses).  The reference sources are compiled UNMODIFIED; this prelude injects the missing
  * member through the preprocessor (the token A_diag_ext in the struct body expands to
  * "A_diag_ext; double **A_diag") and supplies the three missing enumerators. */
 #ifndef AMG_REF_PRELUDE_HPP
 #define AMG_REF_PRELUDE_HPP
 #define A_diag_ext A_diag_ext; double **A_diag
+#define z2 z2; HYPRE_Real **u_smooth   /* VectorData::u_smooth: used by src/SMEM_ExtendedSystem.cpp:374, allocated by src/SMEM_Setup.cpp:287 */
 #include "Main.hpp"
 #undef A_diag_ext
+#undef z2
 #define L1_HYBRID_JACOBI_GAUSS_SEIDEL 12
 #define CYCLE_PHASE_DOWN 0
 #define CYCLE_PHASE_UP 1

@@ -122,10 +122,43 @@ def matrix_file_golden():
     print("matrix_file", rec.shape, d["symm1_indptr"][-1])
 
 
+def iebpx_golden():
+    """The reference's implicit extended-system BPX solver (SMEM_ExtendedSystemSolve, src/SMEM_ExtendedSystem.cpp,
+    compiled in oracle/_ref) on the hierarchies of the committed fixtures, one thread per level (deterministic)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import hierarchy_from_golden
+    d = {}
+    for name in ("lap5pt_n32", "lap7pt_n12"):
+        h, g = hierarchy_from_golden(name)
+        b, w = g["b"], 0.8
+        h.build_transfers(H.BPX, w)
+        for sm, tag in ((H.JACOBI, "j"), (H.L1_JACOBI, "l1")):
+            lo, hi = O.Problem(h, H.BPX, sm, w).eigs_power(20)
+            mu, delta = (hi + lo) / (hi - lo), 2.0 / (hi + lo)
+            for nc in (2, 7, 300):
+                rs = O.RefSolver(h, H.IMPLICIT_EXTENDED_SYSTEM_BPX, sm, b, w, one_thread_per_level=True)
+                r = rs.solve_iebpx(nc, 1e-9, mu, delta)
+                rs.close()
+                k = "%s_%s_nc%d_" % (name, tag, nc)
+                d[k + "mu_delta"] = np.asarray([mu, delta])
+                d[k + "iters"] = np.asarray(r["iters"])
+                d[k + "norms"] = np.asarray([r["ext_relres"], r["relres"]])
+                d[k + "x"] = r["x"]
+                print(k, r["iters"], r["ext_relres"], r["relres"])
+    np.savez_compressed(os.path.join(OUT, "iebpx.npz"), **d)
+
+
 if __name__ == "__main__":
+    if "--iebpx-only" in sys.argv:
+        from oracle import build as obuild
+        amg.build.build_host(); obuild.build_oracle(); obuild.build_ref()
+        iebpx_golden()
+        sys.exit(0)
     if "--matrix-file-only" not in sys.argv:
         main()
     else:
         from oracle import build as obuild
         amg.build.build_host(); obuild.build_ref()
     matrix_file_golden()
+    if "--matrix-file-only" not in sys.argv:
+        iebpx_golden()

@@ -124,3 +124,46 @@ def test_hybrid_jgs_block_semantics():
                         res -= D[i, j] * up[j]
                 u[i] = res / D[i, i] if k == 0 else u[i] + res / D[i, i]
     assert np.max(np.abs(got - u)) <= 1e-13
+
+
+# ---- implicit extended-system BPX (`-solver iebpx`, src/SMEM_ExtendedSystem.cpp) ---------------------------------------
+@pytest.mark.parametrize("name", ["lap5pt_n32", "lap7pt_n12"])
+@pytest.mark.parametrize("sm,tag", [(H.JACOBI, "j"), (H.L1_JACOBI, "l1")])
+def test_iebpx_matches_reference_fixture(name, sm, tag):
+    """oracle restatement vs the reference's own object code (tests/golden/iebpx.npz, made by make_golden.py from
+    oracle/_ref): same iteration count at tol 1e-9, same norms, same solution"""
+    import os
+    from conftest import GOLDEN, hierarchy_from_golden
+    g = dict(np.load(os.path.join(GOLDEN, "iebpx.npz")))
+    h, d = hierarchy_from_golden(name)
+    h.build_transfers(H.BPX, 0.8)
+    pb = O.Problem(h, H.BPX, sm, 0.8)
+    for nc in (2, 7, 300):
+        k = "%s_%s_nc%d_" % (name, tag, nc)
+        mu, delta = g[k + "mu_delta"]
+        out = pb.solve_iebpx(d["b"], 1e-9, nc, mu, delta)
+        assert out["iters"] == int(g[k + "iters"])
+        assert abs(out["ext_relres"] - g[k + "norms"][0]) <= 1e-12 * g[k + "norms"][0]
+        assert abs(out["relres"] - g[k + "norms"][1]) <= 1e-12 * g[k + "norms"][1]
+        assert np.max(np.abs(out["x"] - g[k + "x"])) <= 1e-13 * np.max(np.abs(g[k + "x"]))
+    assert out["relres"] < 1e-9                      # the extended-system iterate gives a solution of A x = f
+
+
+def test_iebpx_matches_live_reference():
+    if O.ref_lib() is None:
+        pytest.skip("oracle/_ref not built here")
+    A = H.laplacian("7pt", 10)
+    h = H.amg_setup(A)
+    b = H.rand_rhs(A.nrows)
+    h.build_transfers(H.BPX, 0.7)
+    pb = O.Problem(h, H.BPX, H.JACOBI, 0.7)
+    lo, hi = pb.eigs_power(20)
+    mu, delta = (hi + lo) / (hi - lo), 2.0 / (hi + lo)
+    for nc in (1, 2, 3, 25, 400):
+        want = O.RefSolver(h, H.IMPLICIT_EXTENDED_SYSTEM_BPX, H.JACOBI, b, 0.7, one_thread_per_level=True)
+        r = want.solve_iebpx(nc, 1e-9, mu, delta)
+        want.close()
+        out = pb.solve_iebpx(b, 1e-9, nc, mu, delta)
+        assert out["iters"] == r["iters"]
+        assert np.max(np.abs(out["x"] - r["x"])) <= 1e-13 * np.max(np.abs(r["x"]))
+        assert abs(out["ext_relres"] - r["ext_relres"]) <= 1e-12 * r["ext_relres"]
