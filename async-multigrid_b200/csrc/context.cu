@@ -144,6 +144,7 @@ int amgb_destroy(amgb_ctx *c)
    amgb_dist_teardown(c);
    for (double *p : c->peer_u) cudaIpcCloseMemHandle(p);
    amgb_async_teardown(c);
+   amgb_ext_teardown(c);
    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
    for (void *p : c->allocs) cudaFree(p);
    if (c->h_scalars) cudaFreeHost(c->h_scalars);

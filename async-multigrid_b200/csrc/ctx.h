@@ -6,6 +6,7 @@
 #include <vector>
 
 struct DistState;
+struct ExtState;
 
 struct amgb_ctx {
    int device = 0;
@@ -54,6 +55,8 @@ struct amgb_ctx {
    std::vector<int> async_cta_begin;
    // distributed
    DistState *dist = nullptr;
+   // implicit extended-system BPX solver: per-level vectors (extended.cu)
+   ExtState *ext = nullptr;
    // asynchronous solve across GPUs: IPC-mapped solution vectors of the peer ranks (fp64 reductions over NVLink)
    std::vector<double *> peer_u;
    char err[512] = {0};
@@ -64,6 +67,7 @@ int amgb_fail(amgb_ctx *c, int code, const char *fmt, ...);
 // input vector is not partitioned (nothing to overlap)
 bool amgb_dist_owned_cols(const amgb_ctx *c, int kind, int level, int *c0, int *c1);
 void amgb_dist_teardown(amgb_ctx *c);
+void amgb_ext_teardown(amgb_ctx *c);
 void amgb_async_teardown(amgb_ctx *c);   // frees the host copy of the persistent kernel's parameter block
 int amgb_dist_diag_offset(const amgb_ctx *c, int level);          // position of the diagonal in a local row block
 bool amgb_dist_level_distributed(const amgb_ctx *c, int level);

@@ -24,7 +24,7 @@ ABI_SYMBOLS = [
     "amgb_set_num_levels", "amgb_set_matrix", "amgb_set_options", "amgb_setup",
     "amgb_set_rhs", "amgb_set_solution", "amgb_get_solution", "amgb_get_residual",
     "amgb_spgemv", "amgb_spgemv_transpose", "amgb_smooth", "amgb_norm2", "amgb_cycle", "amgb_eigs_power", "amgb_solve_sync", "amgb_solve_async",
-    "amgb_async_groups", "amgb_smem_solve", "amgb_time_residual", "amgb_level_storage", "amgb_time_spmv", "amgb_stream_stats", "amgb_l2_arena_bytes",
+    "amgb_async_groups", "amgb_solve_extended", "amgb_smem_solve", "amgb_time_residual", "amgb_level_storage", "amgb_time_spmv", "amgb_stream_stats", "amgb_l2_arena_bytes",
     "amgb_dist_unique_id", "amgb_dist_init", "amgb_dist_set_level", "amgb_dist_setup", "amgb_dist_set_rhs",
     "amgb_dist_get_solution", "amgb_dist_solve_sync", "amgb_dist_solve_sync_accel", "amgb_dist_stats",
     "amgb_dist_ipc_export_solution", "amgb_dist_ipc_open_neighbours", "amgb_dist_async_smooth", "amgb_dist_residual_norm",
@@ -77,6 +77,7 @@ def load_library():
     L.amgb_eigs_power.argtypes = [C.c_void_p, C.c_int, DP, DP]
     L.amgb_solve_sync.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, DP, IP, DP]
     L.amgb_solve_async.argtypes = [C.c_void_p, C.c_int, C.c_int, IP, DP, DP]
+    L.amgb_solve_extended.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_double, C.c_double, DP, IP, DP, DP, DP]
     L.amgb_smem_solve.argtypes = [C.c_void_p, DP, DP, C.c_double, C.c_int, DP, IP, IP, DP, DP]
     L.amgb_time_residual.argtypes = [C.c_void_p, C.c_int, DP]
     L.amgb_level_storage.argtypes = [C.c_void_p, C.c_int, C.c_int, IP]
@@ -232,6 +233,18 @@ class Solver:
         c = np.empty(self.n0)
         self._ck(self.L.amgb_cycle(self.ctx, _dp(r), _dp(c)))
         return c
+
+    def SMEM_ExtendedSystemSolve(self, f, tol=1e-9, num_cycles=100, mu=1.0, delta=1.0):
+        """`-solver iebpx` (src/SMEM_ExtendedSystem.cpp): hierarchy built for BPX.  -> dict(x, iters, ext_hist, ext_relres,
+        relres, seconds)"""
+        self.set_rhs(f)
+        hist = np.zeros(max(num_cycles, 2) + 1)
+        it = C.c_int(0)
+        er, rr, secs = C.c_double(0), C.c_double(0), C.c_double(0)
+        self._ck(self.L.amgb_solve_extended(self.ctx, tol, int(num_cycles), mu, delta, _dp(hist), C.byref(it), C.byref(er),
+                                            C.byref(rr), C.byref(secs)))
+        return dict(x=self.get_solution(), iters=it.value, ext_hist=hist[:it.value], ext_relres=er.value, relres=rr.value,
+                    seconds=secs.value)
 
     def ChebySetup(self, iters=20):
         """EigsPower + ChebySetup (src/SMEM_Cheby.cpp:28-60,410-518): returns (mu, delta, alpha, beta)"""

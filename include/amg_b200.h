@@ -33,7 +33,8 @@ enum {
 enum { AMGB_SMOOTH_JACOBI = 0, AMGB_SMOOTH_HYBRID_JGS = 2, AMGB_SMOOTH_SEMI_ASYNC_GS = 4, AMGB_SMOOTH_ASYNC_GS = 5,
        AMGB_SMOOTH_L1_JACOBI = 6 };
 enum { AMGB_SOLVER_MULT = 0, AMGB_SOLVER_AFACX = 1, AMGB_SOLVER_MULTADD = 2, AMGB_SOLVER_BPX = 3,
-       AMGB_SOLVER_ASYNC_AFACX = 5, AMGB_SOLVER_ASYNC_MULTADD = 6 };
+       AMGB_SOLVER_ASYNC_AFACX = 5, AMGB_SOLVER_ASYNC_MULTADD = 6,
+       AMGB_SOLVER_IEBPX = 16 /* IMPLICIT_EXTENDED_SYSTEM_BPX: amgb_solve_extended; hierarchy as for BPX */ };
 enum { AMGB_CONVERGE_LOCAL = 0, AMGB_CONVERGE_GLOBAL = 1 };       /* src/Main.hpp LOCAL/GLOBAL */
 enum { AMGB_MAT_A = 0, AMGB_MAT_P = 1, AMGB_MAT_R = 2 };
 
@@ -135,6 +136,18 @@ int amgb_solve_async(amgb_ctx *ctx, int num_cycles, int converge_type, int *corr
  * src/SMEM_Setup.cpp:770-868,1083-1160): cta_begin[num_levels + 1], *grid = total CTAs.  Valid after the first
  * amgb_solve_async. */
 int amgb_async_groups(amgb_ctx *ctx, int *cta_begin, int *grid);
+
+/* SMEM_ExtendedSystemSolve with IMPLICIT_EXTENDED_SYSTEM_BPX, synchronous (`-solver iebpx`; src/SMEM_ExtendedSystem.cpp:9-836,
+ * finish :777-817, ExtendedSystemImplicitMatVec :838-907) on the resident f: Chebyshev-accelerated (mu, delta from
+ * ChebySetup) weighted / L1 Jacobi on the semi-definite extended ("generating") system over all levels, plain P and
+ * R = P^T as for BPX.  Stops when the reference's iteration counter (which starts at 1; no iteration at all for
+ * num_cycles <= 1) reaches num_cycles or, from the second iteration on, when the extended residual drops below
+ * tol * r0_ext.  ext_hist[it], 1 <= it < *iters (caller provides max(num_cycles,2)+1 doubles, may be NULL) = relative
+ * extended residual measured in iteration it; *iters = the reference's local_num_correct; ext_relres / relres = final
+ * relative residuals of the extended system and of A x = f; the solution x = sum_l P^{0<-l} u_l is left in u
+ * (amgb_get_solution). */
+int amgb_solve_extended(amgb_ctx *ctx, double tol, int num_cycles, double mu, double delta, double *ext_hist, int *iters,
+                        double *ext_relres, double *relres, double *solve_seconds);
 
 /* Drop-in for one whole SMEM_Solve call with HOST buffers (what SMEM_Main's run loop would call,
  * src/SMEM_Main.cpp:694-757): uploads f, zeroes u (InitSolve), runs the sync or async solve named

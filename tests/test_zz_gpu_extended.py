@@ -1,0 +1,63 @@
+"""GPU parity of the implicit extended-system BPX solver (`-solver iebpx`; amgb_solve_extended, csrc/extended.cu) against
+the oracle restatement -- which the reference's own SMEM_ExtendedSystem.cpp object code pins bit-exactly
+(tests/test_oracle_golden.py) -- and against the committed reference fixture tests/golden/iebpx.npz.  fp64; the device
+computes the same chains with fused epilogues and a different summation order: norms agree to 1e-10 relative to r0_ext,
+iteration counts are equal, solutions agree to 1e-11 of their magnitude."""
+import os
+
+import numpy as np
+import pytest
+
+import async_multigrid_b200 as amg
+from async_multigrid_b200 import hierarchy as H
+from conftest import GOLDEN, HIST_TOL, hierarchy_from_golden
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(out, want):
+    assert out["iters"] == want["iters"], (out["iters"], want["iters"])
+    k = want["iters"]
+    assert np.max(np.abs(out["ext_hist"][1:k] - want["ext_hist"][1:k])) <= HIST_TOL if k > 1 else True
+    assert abs(out["ext_relres"] - want["ext_relres"]) <= HIST_TOL
+    assert abs(out["relres"] - want["relres"]) <= HIST_TOL
+    assert np.max(np.abs(out["x"] - want["x"])) <= 1e-11 * np.max(np.abs(want["x"]))
+
+
+@pytest.mark.parametrize("prob,n,sm", [("7pt", 16, H.JACOBI), ("5pt", 48, H.L1_JACOBI), ("27pt", 10, H.JACOBI)])
+def test_iebpx_matches_oracle(prob, n, sm):
+    w = 0.8
+    A = H.laplacian(prob, n)
+    h = H.amg_setup(A)
+    h.build_transfers(H.BPX, w)
+    b = H.rand_rhs(A.nrows)
+    pb = O.Problem(h, H.BPX, sm, w)
+    lo, hi = pb.eigs_power(20)
+    mu, delta = (hi + lo) / (hi - lo), 2.0 / (hi + lo)
+    s = amg.Solver(h, H.BPX, sm, w)
+    for nc in (1, 2, 3, 12, 400):
+        _check(s.SMEM_ExtendedSystemSolve(b, 1e-9, nc, mu, delta), pb.solve_iebpx(b, 1e-9, nc, mu, delta))
+    out = s.SMEM_ExtendedSystemSolve(b, 1e-9, 400, mu, delta)
+    assert out["relres"] < 2e-9 and out["iters"] < 400
+    true = O.norm2(O.spgemv(h.A[0], out["x"], b, -1.0, 1.0)) / O.norm2(b)
+    assert abs(true - out["relres"]) <= 1e-12
+    s.close()
+
+
+@pytest.mark.parametrize("name", ["lap5pt_n32", "lap7pt_n12"])
+def test_iebpx_matches_reference_fixture(name):
+    g = dict(np.load(os.path.join(GOLDEN, "iebpx.npz")))
+    h, d = hierarchy_from_golden(name)
+    h.build_transfers(H.BPX, 0.8)
+    for sm, tag in ((H.JACOBI, "j"), (H.L1_JACOBI, "l1")):
+        s = amg.Solver(h, H.IMPLICIT_EXTENDED_SYSTEM_BPX, sm, 0.8)
+        for nc in (2, 7, 300):
+            k = "%s_%s_nc%d_" % (name, tag, nc)
+            mu, delta = g[k + "mu_delta"]
+            out = s.SMEM_ExtendedSystemSolve(d["b"], 1e-9, nc, mu, delta)
+            assert out["iters"] == int(g[k + "iters"])
+            assert abs(out["ext_relres"] - g[k + "norms"][0]) <= HIST_TOL
+            assert abs(out["relres"] - g[k + "norms"][1]) <= HIST_TOL
+            assert np.max(np.abs(out["x"] - g[k + "x"])) <= 1e-11 * np.max(np.abs(g[k + "x"]))
+        s.close()
