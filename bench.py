@@ -368,7 +368,9 @@ def run_reference(args):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "3D 7-pt Laplacian %d^3 (n=%d, nnz=%d), %s, smoother %s w=%.2f, tol 1e-9, x0=0, b=srand(0) RandDouble(-1,1)"
                    % (args.n, h.n[0], h.A[0].nnz, args.solver, args.smoother, args.smooth_weight),
-                   "levels": h.num_levels, "cycles_to_tol": cycles},
+                   "levels": h.num_levels, "cycles_to_tol": cycles,
+                   **({"note": "the reference arm always solves the 1-GPU-sized problem (%d^3) on the host cores; at --gpus %d the "
+                               "b200 arm solves %d x the rows (weak scaling)" % (args.n, args.gpus, args.gpus)} if args.gpus > 1 else {})},
         "cpu_baseline": cb,
         "e2e": {"value": v, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
