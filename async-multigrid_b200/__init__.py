@@ -10,4 +10,4 @@ Importable as ``importlib.import_module("async-multigrid_b200")`` or through the
   build      in-tree nvcc / g++ builds
 """
 from . import build, hierarchy, partition, solver  # noqa: F401
-from .solver import Solver, DistSolver, AmgError  # noqa: F401
+from .solver import Solver, DistSolver, ExtendedExplicitSolver, AmgError  # noqa: F401

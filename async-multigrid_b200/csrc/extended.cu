@@ -17,6 +17,11 @@
 // and k restrictions, sum over k = L(L-1) SpMVs per iteration); the chains are the same for all groups, so here they are
 // computed once per iteration (2(L-1) SpMVs) and shared.  Everything is a composition of the kernels of kernels.cuh: the
 // prolongation fuses "+ u_k", the residual fuses "f_k - z2_k - A_k z1_k" and its sum of squares.
+//
+// The EXPLICIT form (`-solver eebpx`, EXPLICIT_EXTENDED_SYSTEM_BPX, :84-110,295-365) is the same loop on a ONE-level
+// context whose A_0 is the assembled extended matrix AA (BuildExtendedMatrix, src/SMEM_Setup.cpp:1426-1521; host side:
+// amgh_build_extended_matrix) with smooth_weight = 1 (that branch divides by the raw diagonal): z1 = x, z2 = 0,
+// r = bb - AA x, x <- y + omega (delta r ./ diag + x - y).  solver.ExtendedExplicitSolver drives it.
 #include "ctx.h"
 #include <algorithm>
 #include <cmath>
@@ -132,7 +137,7 @@ extern "C" int amgb_solve_extended(amgb_ctx *c, double tol, int num_cycles, doub
       // u = delta f ./ a_ii: ws = w/d, so f .* ws scaled by delta/w
       c->launches += launch_scale(c->cfg, c->stream, n, c->ws[l], x->f[l], x->u[l]);
       c->launches += launch_axpby(c->cfg, c->stream, n, 0.0, x->f[l], delta / c->opt.smooth_weight, x->u[l], nullptr);
-      enq_spmv(c, c->A[l], false, x->u[l], x->e[l], epi(1.0, 0.0, nullptr), false);
+      if (L > 1) enq_spmv(c, c->A[l], false, x->u[l], x->e[l], epi(1.0, 0.0, nullptr), false);   // e feeds the restriction chain only
    }
    double omega = 2.0;
    const double mu22 = (2.0 * mu) * (2.0 * mu);
@@ -148,7 +153,7 @@ extern "C" int amgb_solve_extended(amgb_ctx *c, double tol, int num_cycles, doub
             c->launches += launch_scale(c->cfg, c->stream, n, rs, x->r[k], x->us[k]);
             // u <- y + omega (delta s + u - y), y <- old u   (k_cheby; its third output goes to scratch)
             c->launches += launch_cheby(c->cfg, c->stream, n, omega, delta, x->us[k], x->u[k], x->y[k], x->s[k]);
-            enq_spmv(c, c->A[k], false, x->u[k], x->e[k], epi(1.0, 0.0, nullptr), false);
+            if (L > 1) enq_spmv(c, c->A[k], false, x->u[k], x->e[k], epi(1.0, 0.0, nullptr), false);
          }
          if ((rc = ext_fetch_sum(c, &ss))) return rc;
          const double rel = sqrt(ss) / r0_ext;

@@ -58,6 +58,8 @@ def host_lib():
         L.amgh_setup_systems.argtypes = [C.POINTER(_CSR), C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.amgh_elasticity_beam.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
                                            C.c_double, C.POINTER(_CSR), C.c_void_p]
+        L.amgh_build_extended_matrix.argtypes = [C.c_int, C.POINTER(_CSR), C.POINTER(_CSR), C.POINTER(_CSR), C.POINTER(_CSR),
+                                                 C.POINTER(C.c_int)]
         L.amgh_read_binary_triplets.argtypes = [C.c_char_p, C.c_int, C.POINTER(_CSR)]
         L.amgh_write_binary_triplets.argtypes = [C.POINTER(_CSR), C.c_char_p, C.c_int]
         _lib = L
@@ -167,6 +169,38 @@ def elasticity_beam(ex, ey=None, ez=None, h=None, lam=(50.0, 1.0), mu=(50.0, 1.0
     if rc != 0:
         raise ValueError("elasticity problem too large for int32 CSR" if rc == 1 else "bad beam dimensions")
     return _take(out), b
+
+
+def extended_system(h, f=None):
+    """Explicit extended system of `-solver eebpx` (BuildExtendedMatrix + the bb assembly of InitAlgebra,
+    src/SMEM_Setup.cpp:1426-1521,505-541) for a hierarchy whose transfers are the plain ones of BPX: returns (AA, disp[, bb])
+    with AA the (sum_l n_l)-square matrix of blocks A_k P^{k<-l} / R^{l<-k} A_k^T (diag-first rows), disp[l] the first row
+    of block l, and bb = (f, R_0 f, R_1 R_0 f, ...)."""
+    L = h.num_levels
+    As = (_CSR * L)(*[a._as_c() for a in h.A])
+    Ps = (_CSR * max(L - 1, 1))(*[p._as_c() for p in h.P])
+    Rs = (_CSR * max(L - 1, 1))(*[r._as_c() for r in h.R])
+    out = _CSR()
+    disp = np.zeros(L + 1, dtype=np.int32)
+    rc = host_lib().amgh_build_extended_matrix(L, As, Ps, Rs, C.byref(out), disp.ctypes.data_as(C.POINTER(C.c_int)))
+    if rc != 0:
+        raise ValueError("extended matrix too large for int32 CSR")
+    AA = _take(out)
+    if f is None:
+        return AA, disp
+    parts = [np.asarray(f, dtype=np.float64)]
+    for l in range(L - 1):
+        parts.append(h.R[l].to_scipy() @ parts[-1])
+    return AA, disp, np.concatenate(parts)
+
+
+def extended_solution(h, disp, xx):
+    """x = sum_l P_0 ... P_{l-1} x_l from the blocks of an extended-system iterate (src/SMEM_ExtendedSystem.cpp:736-759)"""
+    L = h.num_levels
+    v = np.array(xx[disp[L - 1]:disp[L]], dtype=np.float64)
+    for l in range(L - 2, -1, -1):
+        v = xx[disp[l]:disp[l + 1]] + h.P[l].to_scipy() @ v
+    return v
 
 
 def read_matrix(path, symm_flag=1):

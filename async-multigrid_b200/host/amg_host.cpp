@@ -824,6 +824,64 @@ int amgh_smooth_transfer(const amgh_csr *A, const amgh_csr *P, int kind, double 
    return 0;
 }
 
+// ---- explicit extended-system matrix (`-solver eebpx`) ---------------------------------------------------------------
+// BuildExtendedMatrix for EXPLICIT_EXTENDED_SYSTEM_BPX (src/SMEM_Setup.cpp:1426-1521): the (sum_l n_l)-square matrix AA whose
+// block (k,k) is A_k, block (k,l), l > k, is A_k P_k ... P_{l-1} and block (l,k) is R_{l-1} ... R_k A_k^T; disp[l] = first
+// row of block l.  Entries are pushed block by block in the reference's order (level k: A_k, then for every l > k the
+// block (k,l) into the rows of block k and the block (l,k) into the rows of block l), every row is then reversed and its
+// diagonal entry swapped to the front (StdVector_to_CSR, :1372-1424) -- the solver divides by A_data[A_i[i]]
+// (src/SMEM_ExtendedSystem.cpp:108,327).  Inside one pushed block the columns ascend here; hypre_CSRMatrixMultiply's own
+// order (un-vendored) may differ, which only changes the summation order of a row.
+int amgh_build_extended_matrix(int L, const amgh_csr *A, const amgh_csr *P, const amgh_csr *R, amgh_csr *AA, int *disp /* L+1 */)
+{
+   disp[0] = 0;
+   for (int l = 0; l < L; l++) disp[l + 1] = disp[l] + A[l].nrows;
+   const int N = disp[L];
+   std::vector<std::vector<int>> cols((size_t)N);
+   std::vector<std::vector<double>> vals((size_t)N);
+   auto push = [&](const amgh_csr &M, int row0, int col0) {
+#pragma omp parallel for schedule(static)
+      for (int i = 0; i < M.nrows; i++)
+         for (int p = M.i[i]; p < M.i[i + 1]; p++) { cols[(size_t)row0 + i].push_back(col0 + M.j[p]); vals[(size_t)row0 + i].push_back(M.data[p]); }
+   };
+   for (int k = 0; k < L; k++) {
+      push(A[k], disp[k], disp[k]);
+      amgh_csr AP = {0, 0, 0, nullptr, nullptr, nullptr}, RA = {0, 0, 0, nullptr, nullptr, nullptr};
+      bool own = false;
+      const amgh_csr *ap = &A[k];
+      amgh_csr AT; transpose(A[k], &AT);
+      const amgh_csr *ra = &AT;
+      amgh_csr ra_own = AT;
+      for (int l = k + 1; l < L; l++) {
+         amgh_csr Q, M;
+         spgemm(*ap, P[l - 1], &Q);
+         spgemm(R[l - 1], *ra, &M);
+         if (own) amgh_csr_free(&AP);
+         amgh_csr_free(&ra_own);
+         AP = Q; RA = M; ra_own = M; own = true;
+         ap = &AP; ra = &RA;
+         push(AP, disp[k], disp[l]);
+         push(RA, disp[l], disp[k]);
+      }
+      if (own) amgh_csr_free(&AP);
+      amgh_csr_free(&ra_own);
+   }
+   long nnz = 0;
+   for (int i = 0; i < N; i++) nnz += (long)cols[i].size();
+   if (nnz > 2147483000L) return 1;
+   csr_alloc(AA, N, N, (int)nnz);
+   AA->i[0] = 0;
+   for (int i = 0; i < N; i++) AA->i[i + 1] = AA->i[i] + (int)cols[i].size();
+#pragma omp parallel for schedule(static)
+   for (int i = 0; i < N; i++) {
+      const int s = AA->i[i], len = (int)cols[i].size();
+      for (int t = 0; t < len; t++) { AA->j[s + t] = cols[i][len - 1 - t]; AA->data[s + t] = vals[i][len - 1 - t]; }
+      for (int t = 0; t < len; t++)
+         if (AA->j[s + t] == i) { std::swap(AA->j[s], AA->j[s + t]); std::swap(AA->data[s], AA->data[s + t]); break; }
+   }
+   return 0;
+}
+
 // plain R = P^T in the reference's layout (hypre_CSRMatrixTranspose keeps ascending rows)
 int amgh_restriction_from_P(const amgh_csr *P, amgh_csr *R) { transpose(*P, R); return 0; }
 

@@ -451,3 +451,42 @@ class DistSolver:
         v = C.c_double(0)
         self._ck(self.L.amgb_dist_residual_norm(self.ctx, C.byref(v)))
         return v.value
+
+
+class ExtendedExplicitSolver:
+    """`-solver eebpx`: SMEM_ExtendedSystemSolve with EXPLICIT_EXTENDED_SYSTEM_BPX (src/SMEM_ExtendedSystem.cpp:84-110,295-365,
+    finish :736-775).  `h`: hierarchy with the plain transfers of BPX.  The extended matrix AA is assembled on the host
+    (hierarchy.extended_system = BuildExtendedMatrix, src/SMEM_Setup.cpp:1426-1521) and lives in a one-level context; the
+    right-hand side bb = (f, R_0 f, ...) and the final x = sum_l P^{0<-l} x_l are computed on the device through the
+    hierarchy's own context."""
+
+    def __init__(self, h, device=0, **kw):
+        self.h = h
+        self.AA, self.disp = H.extended_system(h)
+        h1 = H.Hierarchy([self.AA], [])
+        h1.P, h1.R = [], []
+        self.ext = Solver(h1, H.IMPLICIT_EXTENDED_SYSTEM_BPX, H.JACOBI, 1.0, device=device, **kw)
+        self.hs = Solver(h, H.BPX, H.JACOBI, 1.0, device=device, **kw)
+
+    def extended_rhs(self, f):
+        parts = [np.ascontiguousarray(f, dtype=np.float64)]
+        for l in range(self.h.num_levels - 1):
+            parts.append(self.hs.spgemv(MAT_R, l, 1.0, parts[-1], 0.0, None))
+        return np.concatenate(parts)
+
+    def SMEM_ExtendedSystemSolve(self, f, tol=1e-9, num_cycles=100, mu=1.0, delta=1.0):
+        """-> dict(x, xx, iters, ext_hist, ext_relres, relres, seconds)"""
+        bb = self.extended_rhs(f)
+        out = self.ext.SMEM_ExtendedSystemSolve(bb, tol, num_cycles, mu, delta)
+        xx, d, L = out["x"], self.disp, self.h.num_levels
+        v = np.ascontiguousarray(xx[d[L - 1]:d[L]])
+        for l in range(L - 2, -1, -1):
+            v = self.hs.spgemv(MAT_P, l, 1.0, v, 1.0, np.ascontiguousarray(xx[d[l]:d[l + 1]]))
+        r = self.hs.spgemv(MAT_A, 0, -1.0, v, 1.0, np.ascontiguousarray(f, dtype=np.float64))
+        rel = self.hs.norm2(r) / self.hs.norm2(np.ascontiguousarray(f, dtype=np.float64))
+        return dict(x=v, xx=xx, iters=out["iters"], ext_hist=out["ext_hist"], ext_relres=out["relres"], relres=rel,
+                    seconds=out["seconds"])
+
+    def close(self):
+        self.ext.close()
+        self.hs.close()

@@ -238,6 +238,27 @@ def ref_lib():
     return _ref
 
 
+def ref_solve_eebpx(h, AA, disp, bb, num_cycles, tol=1e-9, mu=1.0, delta=1.0, num_threads=4):
+    """the reference's SMEM_ExtendedSystemSolve, EXPLICIT_EXTENDED_SYSTEM_BPX branch (object code in oracle/_ref), on an
+    assembled extended matrix -> dict(x, xx, iters, ext_relres, relres)"""
+    L = ref_lib()
+    nl = h.num_levels
+    keep = (list(h.A), list(h.P), AA)
+    A = (OrcCSR * nl)(*[c_csr(a) for a in h.A])
+    P = (OrcCSR * max(nl - 1, 1))(*[c_csr(p) for p in h.P])
+    aa = c_csr(AA)
+    x, xx = np.zeros(h.n[0]), np.zeros(AA.nrows)
+    er, rr = C.c_double(0), C.c_double(0)
+    L.ref_solve_eebpx.restype = C.c_int
+    L.ref_solve_eebpx.argtypes = [C.c_int, C.POINTER(OrcCSR), C.POINTER(OrcCSR), C.POINTER(OrcCSR), IP, DP, C.c_int, C.c_int,
+                                  C.c_double, C.c_double, C.c_double, DP, DP, DP, DP]
+    d = np.ascontiguousarray(disp, dtype=np.int32)
+    it = L.ref_solve_eebpx(nl, A, P, C.byref(aa), iptr(d), dptr(np.ascontiguousarray(bb, dtype=np.float64)), num_threads,
+                           num_cycles, tol, mu, delta, dptr(x), dptr(xx), C.byref(er), C.byref(rr))
+    del keep
+    return dict(x=x, xx=xx, iters=it, ext_relres=er.value, relres=rr.value)
+
+
 def ref_read_matrix(path, symm_flag=1):
     """the reference's own reader (ReadBinary_fread_HypreParCSR, src/Misc.cpp:800-915) -> (indptr, indices, data)"""
     L = ref_lib()

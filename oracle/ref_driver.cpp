@@ -60,10 +60,30 @@ HYPRE_Int hypre_GaussElimSolve(hypre_ParAMGData *, HYPRE_Int, HYPRE_Int) { retur
 HYPRE_Int HYPRE_BoomerAMGSetPrintLevel(HYPRE_Solver, HYPRE_Int) { return 0; }
 HYPRE_Int HYPRE_BoomerAMGSetMaxIter(HYPRE_Solver, HYPRE_Int) { return 0; }
 HYPRE_Int hypre_ParVectorSetConstantValues(hypre_ParVector *, HYPRE_Complex) { return 0; }
-// referenced by SMEM_ExtendedSystem.cpp on its EXPLICIT_EXTENDED_SYSTEM_BPX branch only, which the driver never takes
-HYPRE_Int hypre_ParCSRMatrixMatvecOutOfPlace(HYPRE_Complex, hypre_ParCSRMatrix *, hypre_ParVector *, HYPRE_Complex, hypre_ParVector *, hypre_ParVector *) { abort(); }
-HYPRE_Int hypre_ParCSRMatrixMatvec(HYPRE_Complex, hypre_ParCSRMatrix *, hypre_ParVector *, HYPRE_Complex, hypre_ParVector *) { abort(); }
-HYPRE_Int hypre_ParVectorCopy(hypre_ParVector *, hypre_ParVector *) { abort(); }
+// hypre ParCSR matvecs as far as SMEM_ExtendedSystem.cpp's EXPLICIT_EXTENDED_SYSTEM_BPX branch uses them (one rank: the
+// diag block is the whole matrix): y = alpha A x + beta b  /  y = alpha A x + beta y  /  y = x
+HYPRE_Int hypre_ParCSRMatrixMatvecOutOfPlace(HYPRE_Complex alpha, hypre_ParCSRMatrix *A, hypre_ParVector *x, HYPRE_Complex beta,
+                                             hypre_ParVector *b, hypre_ParVector *y)
+{
+   hypre_CSRMatrix *M = A->diag;
+   const double *xd = x->local_vector->data, *bd = b->local_vector->data;
+   double *yd = y->local_vector->data;
+   for (int i = 0; i < M->num_rows; i++) {
+      double t = 0.0;
+      for (int jj = M->i[i]; jj < M->i[i + 1]; jj++) t += M->data[jj] * xd[M->j[jj]];
+      yd[i] = alpha * t + beta * bd[i];
+   }
+   return 0;
+}
+HYPRE_Int hypre_ParCSRMatrixMatvec(HYPRE_Complex alpha, hypre_ParCSRMatrix *A, hypre_ParVector *x, HYPRE_Complex beta, hypre_ParVector *y)
+{
+   return hypre_ParCSRMatrixMatvecOutOfPlace(alpha, A, x, beta, y, y);
+}
+HYPRE_Int hypre_ParVectorCopy(hypre_ParVector *x, hypre_ParVector *y)
+{
+   memcpy(y->local_vector->data, x->local_vector->data, sizeof(double) * x->local_vector->size);
+   return 0;
+}
 
 // HYPRE_IJMatrix as far as ReadBinary_fread_HypreParCSR (src/Misc.cpp:800-915) uses it: rows are set one at a time
 // and the assembled object is a ParCSR matrix whose (only) diag block is CSR.  As in hypre's IJ assembly the
@@ -446,6 +466,82 @@ int ref_solve_iebpx(void *h, int num_cycles, double tol, double mu, double delta
    if (ext_relres) *ext_relres = ad->output.r_norm2_ext_sys / ad->output.r0_norm2_ext_sys;
    if (relres) *relres = ad->output.r_norm2 / ad->output.r0_norm2;
    return ad->grid.local_num_correct[0];
+}
+
+// SMEM_ExtendedSystemSolve for EXPLICIT_EXTENDED_SYSTEM_BPX (`-solver eebpx`), synchronous, on an assembled extended matrix
+// AA (BuildExtendedMatrix is part of SMEM_Setup.cpp, which needs hypre: the caller assembles AA).  Fills exactly what that
+// branch reads: matrix.AA, vector.xx/bb/rr/zz (src/SMEM_Setup.cpp:505-541), grid.disp, thread.AA_NS/NE (:543-556), and
+// hypre's A / P / U / F arrays + Vtemp for the initial fine residual and the final prolongation sum (:736-775).
+// x0 = 0 (InitVectors).  Returns loc_iters; x_out = fine-level solution, xx_out = the extended iterate.
+int ref_solve_eebpx(int L, const RefCSR *A, const RefCSR *P, const RefCSR *AAin, const int *disp, const double *bb, int num_threads,
+                    int num_cycles, double tol, double mu, double delta, double *x_out, double *xx_out, double *ext_relres, double *relres)
+{
+   AllData all;
+   AllData *ad = &all;
+   memset((void *)&ad->input, 0, sizeof(ad->input));
+   memset((void *)&ad->output, 0, sizeof(ad->output));
+   memset((void *)&ad->matrix, 0, sizeof(ad->matrix));
+   memset((void *)&ad->cheby, 0, sizeof(ad->cheby));
+   ad->input.solver = EXPLICIT_EXTENDED_SYSTEM_BPX;
+   ad->input.num_threads = num_threads;
+   ad->input.num_cycles = num_cycles;
+   ad->input.tol = tol;
+   ad->input.check_resnorm_flag = 1;
+   ad->input.async_flag = 0;
+   ad->input.omp_parfor_flag = 0;
+   ad->input.delay_type = DELAY_NONE;
+   ad->cheby.mu = mu; ad->cheby.delta = delta;
+   ad->grid.num_levels = L;
+   std::vector<int> n(L), dsp(disp, disp + L + 1), lnc(num_threads, 0);
+   for (int l = 0; l < L; l++) n[l] = A[l].nrows;
+   ad->grid.n = n.data(); ad->grid.disp = dsp.data(); ad->grid.local_num_correct = lnc.data();
+   const int N = AAin->nrows;
+   hypre_CSRMatrix AA; fill(&AA, *AAin);
+   ad->matrix.AA = &AA;
+   std::vector<double> xx(N, 0.0), rr(N, 0.0), zz(N, 0.0), b(bb, bb + N);
+   ad->vector.xx = xx.data(); ad->vector.bb = b.data(); ad->vector.rr = rr.data(); ad->vector.zz = zz.data();
+   std::vector<int> ns(num_threads), ne(num_threads);
+   const int per = (AA.num_nonzeros + num_threads - 1) / num_threads;
+   for (int t = 0; t < num_threads; t++) {
+      ns[t] = (t == 0) ? 0 : (int)(hypre_LowerBound(AA.i, AA.i + N, per * t) - AA.i);
+      ne[t] = (t == num_threads - 1) ? N : (int)(hypre_LowerBound(AA.i, AA.i + N, per * (t + 1)) - AA.i);
+   }
+   ad->thread.AA_NS = ns.data(); ad->thread.AA_NE = ne.data();
+   std::vector<double> aw(num_threads, 0.0), vw(num_threads, 0.0), iw(num_threads, 0.0), w4(4 * (size_t)num_threads, 0.0);
+   ad->output.A_matvec_wtime = aw.data(); ad->output.vec_wtime = vw.data(); ad->output.innerprod_wtime = iw.data();
+   ad->output.smooth_wtime = w4.data(); ad->output.residual_wtime = w4.data() + num_threads;
+   ad->output.restrict_wtime = w4.data() + 2 * num_threads; ad->output.prolong_wtime = w4.data() + 3 * num_threads;
+   // hypre side: per-level A, P as ParCSR with one diag block; U / F vectors per level; Vtemp
+   std::vector<hypre_CSRMatrix> hA(L), hP(L);
+   std::vector<hypre_ParCSRMatrix> pA(L), pP(L);
+   std::vector<hypre_ParCSRMatrix *> Aarr(L), Parr(L);
+   std::vector<std::vector<double>> ud(L), fd(L);
+   std::vector<hypre_Vector> uv(L), fv(L);
+   std::vector<hypre_ParVector> up(L), fp(L);
+   std::vector<hypre_ParVector *> Uarr(L), Farr(L);
+   for (int l = 0; l < L; l++) {
+      fill(&hA[l], A[l]); pA[l].diag = &hA[l]; pA[l].global_num_rows = n[l]; Aarr[l] = &pA[l];
+      if (l < L - 1) { fill(&hP[l], P[l]); pP[l].diag = &hP[l]; pP[l].global_num_rows = n[l]; Parr[l] = &pP[l]; }
+      ud[l].assign(n[l], 0.0); fd[l].assign(n[l], 0.0);
+      uv[l].data = ud[l].data(); uv[l].size = n[l]; up[l].local_vector = &uv[l]; Uarr[l] = &up[l];
+      fv[l].data = fd[l].data(); fv[l].size = n[l]; fp[l].local_vector = &fv[l]; Farr[l] = &fp[l];
+   }
+   memcpy(fd[0].data(), bb, sizeof(double) * n[0]);          // F_array[0] = f (bb's first block)
+   std::vector<double> vd(n[0], 0.0);
+   hypre_Vector vv; vv.data = vd.data(); vv.size = n[0];
+   hypre_ParVector vp; vp.local_vector = &vv;
+   hypre_ParAMGData amg;
+   memset(&amg, 0, sizeof(amg));
+   amg.A_array = Aarr.data(); amg.P_array = Parr.data(); amg.R_array = nullptr;
+   amg.U_array = Uarr.data(); amg.F_array = Farr.data(); amg.Vtemp = &vp; amg.Ztemp = &vp;
+   ad->hypre.solver = (HYPRE_Solver)&amg;
+   omp_set_num_threads(num_threads);
+   SMEM_ExtendedSystemSolve(ad);
+   if (x_out) memcpy(x_out, ud[0].data(), sizeof(double) * n[0]);
+   if (xx_out) memcpy(xx_out, xx.data(), sizeof(double) * N);
+   if (ext_relres) *ext_relres = ad->output.r_norm2_ext_sys / ad->output.r0_norm2_ext_sys;
+   if (relres) *relres = ad->output.r_norm2 / ad->output.r0_norm2;
+   return lnc[0];
 }
 
 void ref_destroy(void *h) { delete (RefHandle *)h; }

@@ -136,15 +136,42 @@ def iebpx_golden():
             lo, hi = O.Problem(h, H.BPX, sm, w).eigs_power(20)
             mu, delta = (hi + lo) / (hi - lo), 2.0 / (hi + lo)
             for nc in (2, 7, 300):
-                rs = O.RefSolver(h, H.IMPLICIT_EXTENDED_SYSTEM_BPX, sm, b, w, one_thread_per_level=True)
-                r = rs.solve_iebpx(nc, 1e-9, mu, delta)
-                rs.close()
+                # thread 0 of the reference sums the threads' residual contributions without a barrier
+                # (src/SMEM_ExtendedSystem.cpp:641-648); a stale one delays the tolerance stop by an iteration: keep the
+                # race-free outcome = the smallest count of a few runs
+                r = None
+                for _ in range(5):
+                    rs = O.RefSolver(h, H.IMPLICIT_EXTENDED_SYSTEM_BPX, sm, b, w, one_thread_per_level=True)
+                    t = rs.solve_iebpx(nc, 1e-9, mu, delta)
+                    rs.close()
+                    if r is None or t["iters"] < r["iters"]:
+                        r = t
                 k = "%s_%s_nc%d_" % (name, tag, nc)
                 d[k + "mu_delta"] = np.asarray([mu, delta])
                 d[k + "iters"] = np.asarray(r["iters"])
                 d[k + "norms"] = np.asarray([r["ext_relres"], r["relres"]])
                 d[k + "x"] = r["x"]
                 print(k, r["iters"], r["ext_relres"], r["relres"])
+    # explicit form (`-solver eebpx`): the reference's EXPLICIT branch on the extended matrix assembled by the host side
+    for name in ("lap5pt_n32", "lap7pt_n12"):
+        h, g = hierarchy_from_golden(name)
+        b = g["b"]
+        h.build_transfers(H.BPX, 1.0)
+        AA, disp, bb = H.extended_system(h, b)
+        lo, hi = O.Problem(h, H.BPX, H.JACOBI, 1.0).eigs_power(20)
+        mu, delta = (hi + lo) / (hi - lo), 2.0 / (hi + lo)
+        for nc in (2, 7, 300):
+            r = None
+            for _ in range(5):
+                t = O.ref_solve_eebpx(h, AA, disp, bb, nc, 1e-9, mu, delta, num_threads=4)
+                if r is None or t["iters"] < r["iters"]:
+                    r = t
+            k = "%s_explicit_nc%d_" % (name, nc)
+            d[k + "mu_delta"] = np.asarray([mu, delta])
+            d[k + "iters"] = np.asarray(r["iters"])
+            d[k + "norms"] = np.asarray([r["ext_relres"], r["relres"]])
+            d[k + "x"] = r["x"]
+            print(k, r["iters"], r["ext_relres"], r["relres"])
     np.savez_compressed(os.path.join(OUT, "iebpx.npz"), **d)
 
 

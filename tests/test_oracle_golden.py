@@ -164,6 +164,84 @@ def test_iebpx_matches_live_reference():
         r = want.solve_iebpx(nc, 1e-9, mu, delta)
         want.close()
         out = pb.solve_iebpx(b, 1e-9, nc, mu, delta)
-        assert out["iters"] == r["iters"]
-        assert np.max(np.abs(out["x"] - r["x"])) <= 1e-13 * np.max(np.abs(r["x"]))
-        assert abs(out["ext_relres"] - r["ext_relres"]) <= 1e-12 * r["ext_relres"]
+        # thread 0 of the reference sums the threads' residual contributions without a barrier
+        # (src/SMEM_ExtendedSystem.cpp:641-648): a stale contribution delays the tolerance stop by one iteration
+        assert r["iters"] in (out["iters"], out["iters"] + 1)
+        if r["iters"] == out["iters"]:
+            assert np.max(np.abs(out["x"] - r["x"])) <= 1e-13 * np.max(np.abs(r["x"]))
+            assert abs(out["ext_relres"] - r["ext_relres"]) <= 1e-13 + 1e-9 * r["ext_relres"]
+
+
+# ---- explicit extended-system BPX (`-solver eebpx`): the same loop on the assembled extended matrix -----------------
+def _explicit_oracle(h, AA, disp, bb, b, nc, mu, delta):
+    h1 = H.Hierarchy([AA], [])
+    h1.P, h1.R = [], []
+    out = O.Problem(h1, H.BPX, H.JACOBI, 1.0).solve_iebpx(bb, 1e-9, nc, mu, delta)
+    x = H.extended_solution(h, disp, out["x"])
+    rel = O.norm2(O.spgemv(h.A[0], x, b, -1.0, 1.0)) / O.norm2(b)
+    return dict(x=x, xx=out["x"], iters=out["iters"], ext_relres=out["relres"], relres=rel)
+
+
+def test_extended_matrix_blocks_and_equivalence_with_the_implicit_form():
+    """BuildExtendedMatrix restated on the host: block (k,l) = A_k P_k..P_{l-1}, symmetric, diag first; Jacobi-Chebyshev on it
+    is the same iteration as the implicit form with weight 1"""
+    A = H.laplacian("7pt", 9)
+    h = H.amg_setup(A)
+    h.build_transfers(H.BPX, 1.0)
+    b = H.rand_rhs(A.nrows)
+    AA, disp, bb = H.extended_system(h, b)
+    assert np.array_equal(AA.indices[AA.indptr[:-1]], np.arange(AA.nrows))
+    S = AA.to_scipy().copy()          # (scipy sorts a row's indices in place when slicing: keep AA's diag-first rows intact)
+    As, Ps = [a.to_scipy().copy() for a in h.A], [p.to_scipy().copy() for p in h.P]
+    for k in range(h.num_levels):
+        M = As[k]
+        for l in range(k, h.num_levels):
+            if l > k:
+                M = M @ Ps[l - 1]
+            assert abs(S[disp[k]:disp[k + 1], disp[l]:disp[l + 1]] - M).max() <= 1e-13 * abs(S).max()
+            assert abs(S[disp[l]:disp[l + 1], disp[k]:disp[k + 1]] - M.T).max() <= 1e-13 * abs(S).max()
+    pb = O.Problem(h, H.BPX, H.JACOBI, 1.0)
+    lo, hi = pb.eigs_power(20)
+    mu, delta = (hi + lo) / (hi - lo), 2.0 / (hi + lo)
+    imp = pb.solve_iebpx(b, 1e-9, 300, mu, delta)
+    exp = _explicit_oracle(h, AA, disp, bb, b, 300, mu, delta)
+    assert imp["iters"] == exp["iters"] and imp["relres"] < 1e-9
+    assert np.max(np.abs(imp["x"] - exp["x"])) <= 1e-12 * np.max(np.abs(imp["x"]))
+
+
+@pytest.mark.parametrize("name", ["lap5pt_n32", "lap7pt_n12"])
+def test_eebpx_matches_reference_fixture(name):
+    import os
+    from conftest import GOLDEN, hierarchy_from_golden
+    g = dict(np.load(os.path.join(GOLDEN, "iebpx.npz")))
+    h, d = hierarchy_from_golden(name)
+    h.build_transfers(H.BPX, 1.0)
+    AA, disp, bb = H.extended_system(h, d["b"])
+    for nc in (2, 7, 300):
+        k = "%s_explicit_nc%d_" % (name, nc)
+        mu, delta = g[k + "mu_delta"]
+        out = _explicit_oracle(h, AA, disp, bb, d["b"], nc, mu, delta)
+        assert out["iters"] == int(g[k + "iters"])
+        # (norms of a converged iterate carry the cancellation of f - A x: absolute 1e-13 of the initial residual)
+        assert abs(out["ext_relres"] - g[k + "norms"][0]) <= 1e-13 + 1e-9 * g[k + "norms"][0]
+        assert abs(out["relres"] - g[k + "norms"][1]) <= 1e-13 + 1e-9 * g[k + "norms"][1]
+        assert np.max(np.abs(out["x"] - g[k + "x"])) <= 1e-12 * np.max(np.abs(g[k + "x"]))
+
+
+def test_eebpx_matches_live_reference():
+    if O.ref_lib() is None:
+        pytest.skip("oracle/_ref not built here")
+    A = H.laplacian("5pt", 20)
+    h = H.amg_setup(A)
+    h.build_transfers(H.BPX, 1.0)
+    b = H.rand_rhs(A.nrows)
+    AA, disp, bb = H.extended_system(h, b)
+    lo, hi = O.Problem(h, H.BPX, H.JACOBI, 1.0).eigs_power(20)
+    mu, delta = (hi + lo) / (hi - lo), 2.0 / (hi + lo)
+    for nc, nt in ((1, 1), (2, 4), (9, 3), (300, 4)):
+        r = O.ref_solve_eebpx(h, AA, disp, bb, nc, 1e-9, mu, delta, num_threads=nt)
+        out = _explicit_oracle(h, AA, disp, bb, b, nc, mu, delta)
+        assert r["iters"] in (out["iters"], out["iters"] + 1)       # (the same unsynchronised sum, :641-648)
+        if r["iters"] == out["iters"]:
+            assert np.max(np.abs(out["xx"] - r["xx"])) <= 1e-13 * np.max(np.abs(r["xx"]))
+            assert np.max(np.abs(out["x"] - r["x"])) <= 1e-13 * np.max(np.abs(r["x"]))

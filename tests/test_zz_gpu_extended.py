@@ -61,3 +61,31 @@ def test_iebpx_matches_reference_fixture(name):
             assert abs(out["relres"] - g[k + "norms"][1]) <= HIST_TOL
             assert np.max(np.abs(out["x"] - g[k + "x"])) <= 1e-11 * np.max(np.abs(g[k + "x"]))
         s.close()
+
+
+def test_eebpx_matches_oracle_and_reference_fixture():
+    """explicit form (`-solver eebpx`): the same device loop on a one-level context holding the assembled extended matrix;
+    against the oracle (pinned by the reference's EXPLICIT branch, tests/test_oracle_golden.py) and the reference fixture"""
+    g = dict(np.load(os.path.join(GOLDEN, "iebpx.npz")))
+    name = "lap7pt_n12"
+    h, d = hierarchy_from_golden(name)
+    h.build_transfers(H.BPX, 1.0)
+    b = d["b"]
+    s = amg.ExtendedExplicitSolver(h)
+    bb = s.extended_rhs(b)
+    AA, disp, bb_host = H.extended_system(h, b)
+    assert np.max(np.abs(bb - bb_host)) <= 1e-13 * np.max(np.abs(bb_host))
+    h1 = H.Hierarchy([AA], [])
+    h1.P, h1.R = [], []
+    pb = O.Problem(h1, H.BPX, H.JACOBI, 1.0)
+    for nc in (2, 7, 300):
+        k = "%s_explicit_nc%d_" % (name, nc)
+        mu, delta = g[k + "mu_delta"]
+        out = s.SMEM_ExtendedSystemSolve(b, 1e-9, nc, mu, delta)
+        want = pb.solve_iebpx(bb_host, 1e-9, nc, mu, delta)
+        assert out["iters"] == want["iters"] == int(g[k + "iters"])
+        assert np.max(np.abs(out["xx"] - want["x"])) <= 1e-11 * np.max(np.abs(want["x"]))
+        assert abs(out["ext_relres"] - g[k + "norms"][0]) <= HIST_TOL
+        assert abs(out["relres"] - g[k + "norms"][1]) <= HIST_TOL
+        assert np.max(np.abs(out["x"] - g[k + "x"])) <= 1e-11 * np.max(np.abs(g[k + "x"]))
+    s.close()
