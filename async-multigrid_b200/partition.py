@@ -280,6 +280,18 @@ class DistEmulator:
             self.owned(l, e[l])[:] += self.P[l] @ e[l + 1]
         return e[0]
 
+    def async_smooth_lockstep(self, f_owned, sweeps):
+        """DMEM_AsyncSmooth (src/DMEM_Smooth.cpp:16-313; csrc/dist.cu amgb_dist_async_smooth) in the one interleaving that is
+        reproducible: every rank's boundary values reach its neighbours before their next sweep.  x_own += s o (f - A_0
+        [ghosts | x_own]); this is global (L1-)Jacobi.  Returns the owned part of x."""
+        u = self.new_vec(0)
+        f = np.asarray(f_owned, dtype=np.float64)
+        so = self.owned(0, self.ws[0])
+        for _ in range(sweeps):
+            self.halo(0, u)
+            self.owned(0, u)[:] += so * (f - self.A[0] @ u)
+        return self.owned(0, u).copy()
+
     def solve(self, f_owned, tol, max_cycles):
         l0 = self.pl.layouts[0]
         u = self.new_vec(0)

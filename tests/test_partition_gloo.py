@@ -51,6 +51,17 @@ def _worker(rank, world, port, prob, n, min_rows, q, solver=2, smoother=0, w=0.9
         _, want_hist, _ = pb.solve_sync(b, 1e-9, ncyc)
         ok_len = len(hist) == len(want_hist)
         err_hist = float(np.max(np.abs(hist - want_hist) / np.maximum(want_hist, 1.0))) if ok_len else 1.0
+        # DMEM_AsyncSmooth in lock step = global (L1-)Jacobi; and the slot a rank's low boundary goes to in its lower
+        # neighbour's vector (DistSolver.ipc_open_neighbours) is that neighbour's first ghost_hi entry
+        if solver == H.MULTADD:
+            x = em.async_smooth_lockstep(b[lay0.row_start:lay0.row_start + lay0.n_owned], 12)
+            want_x = O.smooth("l1_jacobi" if smoother == H.L1_JACOBI else "jacobi", h.A[0], b, w, sweeps=12, zero_flag=1,
+                              l1=h.l1_norms()[0])[lay0.row_start:lay0.row_start + lay0.n_owned]
+            assert np.max(np.abs(x - want_x)) <= 1e-13 * np.max(np.abs(want_x))
+            if rank > 0:
+                nb = PT.rank_layouts(h, world, rank - 1, plan.starts, plan.num_dist, plan.halos)[0]
+                assert plan.halos[0][rank - 1][0] + plan.all_counts[0][rank - 1] == nb.halo_lo + nb.n_owned
+                assert nb.halo_hi == lay0.send_lo
         q.put((rank, plan.num_dist, err_cycle, err_hist, ok_len, [l.n_owned for l in plan.layouts],
                [(l.halo_lo, l.halo_hi) for l in plan.layouts]))
     finally:
