@@ -48,6 +48,11 @@ struct DistState {
    double *partials3 = nullptr;          // 3 x npartials: interior / low boundary / high boundary launches
    bool overlap = true;
    bool ready = false;
+   // EXPERIMENTAL (AMGB_DIST_GRAPH=1, off by default; not measured yet): one cycle + residual + norm captured as a CUDA graph,
+   // NCCL operations and the communication stream's fork / join included, replayed per cycle
+   bool use_graph = false;
+   cudaGraphExec_t graph_exec = nullptr;
+   long long graph_kernels = 0, graph_halo_bytes = 0, graph_collectives = 0;
    // asynchronous fine-grid smoother across GPUs (DMEM_AsyncSmooth): the neighbours' level-0 solution vectors mapped
    // through CUDA IPC, and where in them this rank's boundary entries belong (their ghost slots)
    double *nbr_lo = nullptr, *nbr_hi = nullptr;   // rank-1 / rank+1
@@ -62,6 +67,7 @@ void amgb_dist_teardown(amgb_ctx *c)
 #ifdef AMG_HAVE_NCCL
       if (c->dist->comm) ncclCommDestroy(c->dist->comm);
 #endif
+      if (c->dist->graph_exec) cudaGraphExecDestroy(c->dist->graph_exec);
       if (c->dist->nbr_lo) cudaIpcCloseMemHandle(c->dist->nbr_lo);
       if (c->dist->nbr_hi) cudaIpcCloseMemHandle(c->dist->nbr_hi);
       if (c->dist->comm_stream) cudaStreamDestroy(c->dist->comm_stream);
@@ -394,6 +400,7 @@ int amgb_dist_setup(amgb_ctx *c)
    CUDA_OK(c, cudaEventCreateWithFlags(&d->ev_x, cudaEventDisableTiming));
    CUDA_OK(c, cudaEventCreateWithFlags(&d->ev_h, cudaEventDisableTiming));
    if (const char *ov = getenv("AMGB_DIST_OVERLAP")) d->overlap = atoi(ov) != 0;
+   if (const char *gv = getenv("AMGB_DIST_GRAPH")) d->use_graph = atoi(gv) != 0;
    if ((rc = amgb_dev_alloc_bytes(c, (void **)&d->u, sizeof(double) * (size_t)d->lv[0].n_ext(), true))) return rc;
    if (c->opt.factor_level0) {
       if ((rc = amgb_dev_alloc_bytes(c, (void **)&d->t0, sizeof(double) * (size_t)d->lv[0].n_ext(), true))) return rc;
@@ -462,8 +469,36 @@ int amgb_dist_solve_sync_accel(amgb_ctx *c, double tol, int max_cycles, int acce
    const double r0 = sqrt(ss);
    if (hist) hist[0] = 1.0;
    int done = 0;
+   if (d->use_graph && !accel && !d->graph_exec) {
+      // capture u += B r; r = f - A u; ||r||^2 all-reduced; 8-byte D2H.  The halo exchanges run on the communication stream,
+      // which joins the capture through the events dist_spmv records and is joined back before every boundary launch.
+      cudaGraph_t g;
+      const long long l0 = c->launches, h0 = d->halo_bytes, c0 = d->collectives;
+      CUDA_OK(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+      rc = dist_cycle(c, uo, true);
+      if (!rc) rc = dist_residual(c);
+      cudaMemcpyAsync(c->h_scalars, c->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+      cudaError_t ce = cudaStreamEndCapture(c->stream, &g);
+      if (rc) return rc;
+      if (ce != cudaSuccess) return amgb_fail(c, AMGB_ECUDA, "graph capture of the partitioned cycle failed: %s", cudaGetErrorString(ce));
+      d->graph_kernels = c->launches - l0; d->graph_halo_bytes = d->halo_bytes - h0; d->graph_collectives = d->collectives - c0;
+      c->launches = l0; d->halo_bytes = h0; d->collectives = c0;
+      CUDA_OK(c, cudaGraphInstantiate(&d->graph_exec, g, 0));
+      cudaGraphDestroy(g);
+   }
    CUDA_OK(c, cudaEventRecord(c->ev0, c->stream));
    for (int k = 1; k <= max_cycles; k++) {
+      if (d->graph_exec && !accel) {
+         CUDA_OK(c, cudaGraphLaunch(d->graph_exec, c->stream));
+         CUDA_OK(c, cudaStreamSynchronize(c->stream));
+         c->launches += d->graph_kernels; d->halo_bytes += d->graph_halo_bytes; d->collectives += d->graph_collectives;
+         ss = c->h_scalars[0];
+         done = k;
+         const double relg = sqrt(ss) / r0;
+         if (hist) hist[k] = relg;
+         if (relg < tol) break;
+         continue;
+      }
       if (!accel) {
          if ((rc = dist_cycle(c, uo, true))) return rc;
       } else {

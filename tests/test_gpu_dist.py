@@ -347,3 +347,21 @@ def test_async_smooth_two_gpus():
     r400 = O.norm2(O.spgemv(A, O.smooth("jacobi", A, b, 0.9, sweeps=400), b, -1.0, 1.0))
     assert 0.5 * r400 <= true <= 0.1 * O.norm2(b), (r400, true, O.norm2(b))
     assert res[0][4] > 0 and res[1][4] > 0                 # boundary values really went over NVLink
+
+
+@pytest.mark.skipif(os.environ.get("AMGB_EXPERIMENTAL") != "1", reason="experimental path (AMGB_DIST_GRAPH=1), not validated on hardware yet")
+def test_single_rank_graph_captured_cycle_matches_oracle():
+    """the partitioned cycle replayed as a CUDA graph (NCCL calls captured) must give the history of the eager path"""
+    w = 0.9
+    h, b = _setup("7pt", 20, w)
+    _, want, _ = O.Problem(h, H.MULTADD, H.JACOBI, w).solve_sync(b, 1e-9, 100)
+    os.environ["AMGB_DIST_GRAPH"] = "1"
+    try:
+        s = amg.DistSolver(PT.RankPlan(h, 1, 0), amg.solver.dist_unique_id(), w)
+    finally:
+        del os.environ["AMGB_DIST_GRAPH"]
+    s.set_rhs(b)
+    for _ in range(2):                      # second solve replays the instantiated graph
+        hist, _ = s.solve_sync(1e-9, 100)
+        assert len(hist) == len(want) and np.max(np.abs(hist - want)) <= HIST_TOL
+    s.close()
