@@ -24,7 +24,7 @@ ABI_SYMBOLS = [
     "amgb_set_num_levels", "amgb_set_matrix", "amgb_set_options", "amgb_setup",
     "amgb_set_rhs", "amgb_set_solution", "amgb_get_solution", "amgb_get_residual",
     "amgb_spgemv", "amgb_spgemv_transpose", "amgb_smooth", "amgb_norm2", "amgb_cycle", "amgb_eigs_power", "amgb_solve_sync", "amgb_solve_async",
-    "amgb_async_groups", "amgb_solve_extended", "amgb_smem_solve", "amgb_time_residual", "amgb_level_storage", "amgb_time_spmv", "amgb_stream_stats", "amgb_l2_arena_bytes",
+    "amgb_async_groups", "amgb_solve_extended", "amgb_smooth_transfer", "amgb_host_csr_free", "amgb_smem_solve", "amgb_time_residual", "amgb_level_storage", "amgb_time_spmv", "amgb_stream_stats", "amgb_l2_arena_bytes",
     "amgb_dist_unique_id", "amgb_dist_init", "amgb_dist_set_level", "amgb_dist_setup", "amgb_dist_set_rhs",
     "amgb_dist_get_solution", "amgb_dist_solve_sync", "amgb_dist_solve_sync_accel", "amgb_dist_stats",
     "amgb_dist_ipc_export_solution", "amgb_dist_ipc_open_neighbours", "amgb_dist_async_smooth", "amgb_dist_residual_norm",
@@ -39,6 +39,11 @@ class Options(C.Structure):
                 ("num_fine_smooth_sweeps", C.c_int), ("num_coarse_smooth_sweeps", C.c_int),
                 ("jgs_block_rows", C.c_int), ("use_sell", C.c_int), ("l2_persist", C.c_int), ("use_stream", C.c_int),
                 ("factor_level0", C.c_int), ("coarse_solve", C.c_int), ("sell_sigma", C.c_int), ("stream_variant", C.c_int)]
+
+
+class HostCSR(C.Structure):
+    _fields_ = [("nrows", C.c_int), ("ncols", C.c_int), ("nnz", C.c_int),
+                ("row_ptr", IP), ("col_idx", IP), ("values", DP)]
 
 
 _lib = None
@@ -78,6 +83,10 @@ def load_library():
     L.amgb_solve_sync.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, DP, IP, DP]
     L.amgb_solve_async.argtypes = [C.c_void_p, C.c_int, C.c_int, IP, DP, DP]
     L.amgb_solve_extended.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_double, C.c_double, DP, IP, DP, DP, DP]
+    L.amgb_smooth_transfer.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, IP, IP, DP, C.c_int, IP, IP, DP,
+                                       C.POINTER(HostCSR), C.POINTER(HostCSR)]
+    L.amgb_host_csr_free.argtypes = [C.POINTER(HostCSR)]
+    L.amgb_host_csr_free.restype = None
     L.amgb_smem_solve.argtypes = [C.c_void_p, DP, DP, C.c_double, C.c_int, DP, IP, IP, DP, DP]
     L.amgb_time_residual.argtypes = [C.c_void_p, C.c_int, DP]
     L.amgb_level_storage.argtypes = [C.c_void_p, C.c_int, C.c_int, IP]
@@ -451,6 +460,36 @@ class DistSolver:
         v = C.c_double(0)
         self._ck(self.L.amgb_dist_residual_norm(self.ctx, C.byref(v)))
         return v.value
+
+
+def smooth_transfer_device(A, P, smooth_interp_type=H.JACOBI, smooth_weight=1.0, want_P=True, want_R=True, device=0):
+    """EXPERIMENTAL (not yet validated on hardware): SmoothTransfer (src/SMEM_Setup.cpp:1173-1254) on the device --
+    (Pbar, Rbar) = (G P, P^T GT) as hierarchy.CSR in the reference's product layout; None for an output not asked for."""
+    L = load_library()
+    ctx = C.c_void_p()
+    if L.amgb_create(C.byref(ctx), device) != 0:
+        raise AmgError("amgb_create failed: no CUDA device / driver -- there is no CPU fallback")
+    pb, rb = HostCSR(), HostCSR()
+    try:
+        rc = L.amgb_smooth_transfer(ctx, smooth_interp_type, smooth_weight, A.nrows, _ip(A.indptr), _ip(A.indices), _dp(A.data),
+                                    P.ncols, _ip(P.indptr), _ip(P.indices), _dp(P.data),
+                                    C.byref(pb) if want_P else None, C.byref(rb) if want_R else None)
+        if rc != 0:
+            raise AmgError("amg_b200 error %d: %s" % (rc, L.amgb_last_error(ctx).decode()))
+        out = []
+        for want, m in ((want_P, pb), (want_R, rb)):
+            if not want:
+                out.append(None)
+                continue
+            ip = np.ctypeslib.as_array(m.row_ptr, shape=(m.nrows + 1,)).copy()
+            ix = np.ctypeslib.as_array(m.col_idx, shape=(max(m.nnz, 1),))[:m.nnz].copy()
+            dv = np.ctypeslib.as_array(m.values, shape=(max(m.nnz, 1),))[:m.nnz].copy()
+            out.append(H.CSR(m.nrows, m.ncols, ip, ix, dv))
+        return tuple(out)
+    finally:
+        L.amgb_host_csr_free(C.byref(pb))
+        L.amgb_host_csr_free(C.byref(rb))
+        L.amgb_destroy(ctx)
 
 
 class ExtendedExplicitSolver:

@@ -156,6 +156,19 @@ int amgb_smem_solve(amgb_ctx *ctx, const double *f_host, double *u_host, double 
                     double *relres_hist, int *n_cycles, int *corrections_per_level, double *final_relres,
                     double *solve_seconds);
 
+/* ---- setup step next to the path.  EXPERIMENTAL: compiled, not yet validated on hardware. ----------------
+ * SmoothTransfer (src/SMEM_Setup.cpp:1173-1254; its Eigen products :1256-1339) on the device: Pbar = G P and Rbar = P^T GT with
+ * G = I - w D^-1 A (or the L1 form) from the diag-first A_l (n x n) and the plain P_l (n x nc), host CSR in, host CSR out in
+ * the reference's product layout (descending columns, entry with column == row first, :1382-1423).  Either output may be
+ * NULL.  The arrays of an amgb_host_csr are malloc'ed by the library: release them with amgb_host_csr_free.  `ctx` supplies
+ * the device and stream; no hierarchy needs to be defined. */
+typedef struct { int nrows, ncols, nnz; int *row_ptr; int *col_idx; double *values; } amgb_host_csr;
+int amgb_smooth_transfer(amgb_ctx *ctx, int smooth_interp_type /* AMGB_SMOOTH_JACOBI | AMGB_SMOOTH_L1_JACOBI */, double smooth_weight,
+                         int n, const int *A_row_ptr, const int *A_col_idx, const double *A_values,
+                         int nc, const int *P_row_ptr, const int *P_col_idx, const double *P_values,
+                         amgb_host_csr *Pbar, amgb_host_csr *Rbar);
+void amgb_host_csr_free(amgb_host_csr *m);
+
 /* ---- introspection used by bench.py ------------------------------------------------------- */
 /* event-timed duration (ms) of `reps` back-to-back launches of the fine-level residual kernel
  * r = f - A_0 u (the dominant kernel), on the context's stream */

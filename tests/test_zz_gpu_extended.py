@@ -89,3 +89,20 @@ def test_eebpx_matches_oracle_and_reference_fixture():
         assert abs(out["relres"] - g[k + "norms"][1]) <= HIST_TOL
         assert np.max(np.abs(out["x"] - g[k + "x"])) <= 1e-11 * np.max(np.abs(g[k + "x"]))
     s.close()
+
+
+@pytest.mark.skipif(os.environ.get("AMGB_EXPERIMENTAL") != "1", reason="experimental path (device SmoothTransfer), not validated on hardware yet")
+@pytest.mark.parametrize("prob,n,kind", [("7pt", 12, H.JACOBI), ("5pt", 40, H.L1_JACOBI), ("27pt", 8, H.JACOBI)])
+def test_device_smooth_transfer_matches_host(prob, n, kind):
+    """Pbar = G P and Rbar = P^T GT built on the device (expand - sort - compress) against the host
+    restatement of SmoothTransfer: identical pattern and row layout, values to 1e-14"""
+    A = H.laplacian(prob, n)
+    h = H.amg_setup(A)
+    w = 0.9
+    h.build_transfers(H.MULTADD, w, smooth_interp_type=kind)
+    for l in range(h.num_levels - 1):
+        pb, rb = amg.solver.smooth_transfer_device(h.A[l], h.P_plain[l], kind, w)
+        for got, want in ((pb, h.P[l]), (rb, h.R[l])):
+            assert got.shape == want.shape and np.array_equal(got.indptr, want.indptr)
+            assert np.array_equal(got.indices, want.indices)
+            assert np.max(np.abs(got.data - want.data)) <= 1e-14 * np.max(np.abs(want.data))
