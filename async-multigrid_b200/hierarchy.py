@@ -60,6 +60,7 @@ def host_lib():
                                            C.c_double, C.POINTER(_CSR), C.c_void_p]
         L.amgh_build_extended_matrix.argtypes = [C.c_int, C.POINTER(_CSR), C.POINTER(_CSR), C.POINTER(_CSR), C.POINTER(_CSR),
                                                  C.POINTER(C.c_int)]
+        L.amgh_permute.argtypes = [C.POINTER(_CSR), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.POINTER(_CSR)]
         L.amgh_read_binary_triplets.argtypes = [C.c_char_p, C.c_int, C.POINTER(_CSR)]
         L.amgh_write_binary_triplets.argtypes = [C.POINTER(_CSR), C.c_char_p, C.c_int]
         _lib = L
@@ -308,6 +309,61 @@ def amg_setup(A, theta=0.25, max_levels=25, max_coarse=9, pmax=4, jacobi_interp_
     hh = Hierarchy(As, Ps)
     hh.cpts = cpts
     return hh
+
+
+# ---------------------------------------------------------------------------------------------
+# data-layout experiment: tiled ordering of the unknowns (fewer distinct cache lines per x gather of the Galerkin /
+# transfer operators, profiles/README.md section 3).  The hierarchy is built in the reference's natural ordering and then
+# permuted consistently on every level, so it is the SAME hierarchy: same cycle counts, same history up to summation order.
+# ---------------------------------------------------------------------------------------------
+def tiled_permutation(nx, ny, nz, tile):
+    """new_of_old for a structured nx x ny x nz grid in natural ordering: unknowns numbered tile by tile (tile^3 blocks in
+    x-fastest order, x-fastest inside a tile)"""
+    ix, iy, iz = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    ix, iy, iz = (a.transpose(2, 1, 0).ravel() for a in (ix, iy, iz))          # natural order: x fastest
+    tx, ty, tz = ix // tile, iy // tile, iz // tile
+    ntx, nty = -(-nx // tile), -(-ny // tile)
+    key = (((tz * nty + ty) * ntx + tx).astype(np.int64) * tile ** 3 +
+           ((iz % tile) * tile + (iy % tile)) * tile + (ix % tile))
+    order = np.argsort(key, kind="stable")            # order[new] = old
+    new_of_old = np.empty(order.size, dtype=np.int32)
+    new_of_old[order] = np.arange(order.size, dtype=np.int32)
+    return new_of_old
+
+
+def _permute(m, new_row, new_col, diag_first):
+    out = _CSR()
+    mc = m._as_c()
+    nr = np.ascontiguousarray(new_row, dtype=np.int32)
+    ncl = np.ascontiguousarray(new_col, dtype=np.int32)
+    rc = host_lib().amgh_permute(C.byref(mc), nr.ctypes.data_as(C.POINTER(C.c_int)), ncl.ctypes.data_as(C.POINTER(C.c_int)),
+                                 int(diag_first), C.byref(out))
+    if rc != 0:
+        raise ValueError("not a permutation")
+    return _take(out)
+
+
+def reorder_hierarchy(h, new_of_old0):
+    """(hierarchy with every level renumbered, [new_of_old per level]): level 0 by `new_of_old0`, every coarser level by the
+    new index of its points' fine parents (so coarse points keep following their fine points, as cpts requires)"""
+    if h.cpts is None:
+        raise ValueError("hierarchy has no coarse-point map")
+    perms = [np.ascontiguousarray(new_of_old0, dtype=np.int32)]
+    for l in range(h.num_levels - 1):
+        parent_new = perms[l][h.cpts[l]]
+        order = np.argsort(parent_new, kind="stable")
+        p = np.empty(order.size, dtype=np.int32)
+        p[order] = np.arange(order.size, dtype=np.int32)
+        perms.append(p)
+    A = [_permute(h.A[l], perms[l], perms[l], True) for l in range(h.num_levels)]
+    P = [_permute(h.P_plain[l], perms[l], perms[l + 1], False) for l in range(h.num_levels - 1)]
+    out = Hierarchy(A, P)
+    out.cpts = []
+    for l in range(h.num_levels - 1):
+        c = np.empty(h.n[l + 1], dtype=np.int32)
+        c[perms[l + 1]] = perms[l][h.cpts[l]]
+        out.cpts.append(c)
+    return out, perms
 
 
 # ---------------------------------------------------------------------------------------------

@@ -882,6 +882,37 @@ int amgh_build_extended_matrix(int L, const amgh_csr *A, const amgh_csr *P, cons
    return 0;
 }
 
+// ---- symmetric / rectangular permutation of a CSR matrix (data-layout experiment: tiled ordering of the unknowns) ----
+// out(new_row[r], new_col[c]) = A(r, c).  Rows come out with ascending columns; diag_first != 0 (square matrices) then
+// moves a_ii to the front, the layout the solve phase requires (src/SMEM_Smooth.cpp:385-386).
+int amgh_permute(const amgh_csr *A, const int *new_row, const int *new_col, int diag_first_flag, amgh_csr *out)
+{
+   const int n = A->nrows;
+   std::vector<int> old_of_new((size_t)n);
+   for (int r = 0; r < n; r++) {
+      if (new_row[r] < 0 || new_row[r] >= n) return 1;
+      old_of_new[new_row[r]] = r;
+   }
+   csr_alloc(out, n, A->ncols, A->nnz);
+   out->i[0] = 0;
+   for (int r = 0; r < n; r++) { const int o = old_of_new[r]; out->i[r + 1] = out->i[r] + (A->i[o + 1] - A->i[o]); }
+#pragma omp parallel
+   {
+      std::vector<std::pair<int, double>> row;
+#pragma omp for schedule(static)
+      for (int r = 0; r < n; r++) {
+         const int o = old_of_new[r];
+         row.clear();
+         for (int p = A->i[o]; p < A->i[o + 1]; p++) row.emplace_back(new_col[A->j[p]], A->data[p]);
+         std::sort(row.begin(), row.end(), [](const std::pair<int, double> &a, const std::pair<int, double> &b) { return a.first < b.first; });
+         int d = out->i[r];
+         for (auto &e : row) { out->j[d] = e.first; out->data[d] = e.second; d++; }
+      }
+   }
+   if (diag_first_flag) diag_first(out);
+   return 0;
+}
+
 // plain R = P^T in the reference's layout (hypre_CSRMatrixTranspose keeps ascending rows)
 int amgh_restriction_from_P(const amgh_csr *P, amgh_csr *R) { transpose(*P, R); return 0; }
 
