@@ -165,3 +165,27 @@ def test_systems_amg_keeps_functions_apart_and_converges():
     lo, hi = p.eigs_power(300)
     _, hist, _ = p.solve_sync(b, 1e-9, 800, cheby=((hi + lo) / (hi - lo), 2.0 / (hi + lo)))
     assert hist[-1] < 1e-9
+
+
+def test_tiled_renumbering_is_the_same_hierarchy():
+    """hierarchy.reorder_hierarchy: every level renumbered tile by tile; the oracle's solve of the permuted problem is the
+    permuted solve (same cycle count, history to rounding)"""
+    from oracle import oracle as O
+    n = 12
+    A = H.laplacian("7pt", n)
+    h = H.amg_setup(A)
+    b = H.rand_rhs(A.nrows)
+    p0 = H.tiled_permutation(n, n, n, 4)
+    assert np.array_equal(np.sort(p0), np.arange(n ** 3))
+    h2, perms = H.reorder_hierarchy(h, p0)
+    assert all(np.all(np.diff(c) > 0) for c in h2.cpts)                                   # coarse points still follow their fine points
+    for l in range(h.num_levels):
+        assert np.array_equal(h2.A[l].indices[h2.A[l].indptr[:-1]], np.arange(h.n[l]))   # diag first
+    h.build_transfers(H.MULTADD, 0.9)
+    h2.build_transfers(H.MULTADD, 0.9)
+    b2 = np.empty_like(b)
+    b2[p0] = b
+    u, hist, _ = O.Problem(h, H.MULTADD, H.JACOBI, 0.9).solve_sync(b, 1e-9, 100)
+    u2, hist2, _ = O.Problem(h2, H.MULTADD, H.JACOBI, 0.9).solve_sync(b2, 1e-9, 100)
+    assert len(hist) == len(hist2) and np.max(np.abs(hist - hist2)) <= 1e-13
+    assert np.max(np.abs(u2[p0] - u)) <= 1e-12 * np.max(np.abs(u))
