@@ -13,117 +13,13 @@
 // (CheckConverge, src/Misc.cpp:418-442) and every group sees it at its next barrier (:323-337).
 #include "ctx.h"
 #include "kernels.cuh"
+#include "async_team.cuh"
 #include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <vector>
 
 namespace {
-
-constexpr int kABlock = 256;
-
-struct Team {
-   int tid, size;          // thread index / thread count within the level's CTA group
-   int cta, nctas;         // CTA index / count within the group
-   unsigned int *count;
-   volatile unsigned int *gen;
-   unsigned char *smem;    // AMGB_TEAM_SMEM bytes of shared memory (CSR-stream staging)
-};
-
-// barrier among the CTAs of one group (the reference's SMEM_LevelBarrier)
-__device__ __forceinline__ void group_barrier(const Team &tm)
-{
-   __syncthreads();
-   if (tm.nctas > 1) {
-      if (threadIdx.x == 0) {
-         __threadfence();
-         const unsigned int g = *tm.gen;
-         const unsigned int prev = atomicAdd(tm.count, 1u);
-         if (prev == (unsigned int)tm.nctas - 1u) {
-            atomicExch(tm.count, 0u);
-            __threadfence();
-            atomicAdd((unsigned int *)tm.gen, 1u);
-         } else {
-            while (*tm.gen == g) __nanosleep(32);
-         }
-         __threadfence();
-      }
-      __syncthreads();
-   }
-}
-
-__device__ __forceinline__ SpmvEpilogue mk(double alpha, double beta, const double *b, double gamma = 0.0,
-                                           const double *c = nullptr, const double *rs = nullptr)
-{
-   SpmvEpilogue e;
-   e.alpha = alpha; e.beta = beta; e.gamma = gamma; e.b = b; e.c = c; e.rs = rs;
-   return e;
-}
-
-// e = S_l f from a zero guess (the dispatch of SMEM_Smooth, src/SMEM_Solve.cpp:264-323), ends with
-// a group barrier.  s1: scratch vector of level l.
-__device__ void team_smooth_zero(const AsyncParams &p, const Team &tm, int l, const double *f, double *e,
-                                 double *s1, int sweeps, bool symmetric)
-{
-   const DevCSR &A = p.A[l];
-   const int n = A.nrows;
-   if (p.smoother == AMGB_SMOOTH_ASYNC_GS || p.smoother == AMGB_SMOOTH_SEMI_ASYNC_GS) {
-      for (int i = tm.tid; i < n; i += tm.size) st_cg(e + i, 0.0);
-      group_barrier(tm);
-      if (p.smoother == AMGB_SMOOTH_ASYNC_GS) {
-         async_gs_team<false>(A, f, e, p.jgs_block_rows, sweeps, tm.tid, tm.size);
-         group_barrier(tm);
-      } else {
-         for (int k = 0; k < sweeps; k++) {
-            async_gs_team<false>(A, f, e, p.jgs_block_rows, 1, tm.tid, tm.size);
-            group_barrier(tm);
-         }
-      }
-      return;
-   }
-   if (p.smoother == AMGB_SMOOTH_HYBRID_JGS) {
-      auto sweep = [&](const double *uprev, bool zero) {
-         double *su = reinterpret_cast<double *>(tm.smem);
-         switch (p.jgs_lpb[l]) {   // sub-warp per block (see hybrid_jgs_subwarp_team); 0: block longer than the staging slice
-            case 4: hybrid_jgs_subwarp_team<false, 4>(A, f, e, uprev, nullptr, p.jgs_block_rows, zero, tm.tid, tm.size, su); break;
-            case 8: hybrid_jgs_subwarp_team<false, 8>(A, f, e, uprev, nullptr, p.jgs_block_rows, zero, tm.tid, tm.size, su); break;
-            case 16: hybrid_jgs_subwarp_team<false, 16>(A, f, e, uprev, nullptr, p.jgs_block_rows, zero, tm.tid, tm.size, su); break;
-            case 32: hybrid_jgs_subwarp_team<false, 32>(A, f, e, uprev, nullptr, p.jgs_block_rows, zero, tm.tid, tm.size, su); break;
-            default: hybrid_jgs_team<false>(A, f, e, uprev, nullptr, p.jgs_block_rows, zero, tm.tid, tm.size);
-         }
-      };
-      sweep(nullptr, true);
-      group_barrier(tm);
-      for (int k = 1; k < sweeps; k++) {
-         for (int i = tm.tid; i < n; i += tm.size) s1[i] = ld_cg(e + i);
-         group_barrier(tm);
-         sweep(s1, false);
-         group_barrier(tm);
-      }
-      return;
-   }
-   const double *rs = (p.smoother == AMGB_SMOOTH_L1_JACOBI) ? p.inv_l1[l] : p.ws[l];
-   if (symmetric) {
-      spmv_team<false, true>(A, f, e, mk(-1.0, 2.0, f, 0.0, nullptr, rs), tm.tid, tm.size, false, tm.smem);
-      group_barrier(tm);
-      for (int k = 1; k < sweeps; k++) {
-         spmv_team<false, false>(A, e, s1, mk(-1.0, 1.0, f), tm.tid, tm.size, false, tm.smem);
-         group_barrier(tm);
-         spmv_team<false, true>(A, s1, e, mk(-1.0, 2.0, s1, 0.0, nullptr, rs), tm.tid, tm.size, false, tm.smem);
-         group_barrier(tm);
-      }
-      return;
-   }
-   double *cur = ((sweeps - 1) & 1) ? s1 : e;
-   double *oth = (cur == e) ? s1 : e;
-   for (int i = tm.tid; i < n; i += tm.size) cur[i] = __ldg(rs + i) * ld_cg(f + i);
-   group_barrier(tm);
-   for (int k = 1; k < sweeps; k++) {
-      spmv_team<false, false>(A, cur, oth, mk(-1.0, 1.0, f, 1.0, cur, rs), tm.tid, tm.size, false, tm.smem);
-      group_barrier(tm);
-      double *tmp = cur; cur = oth; oth = tmp;
-   }
-}
 
 __global__ void __launch_bounds__(kABlock, 3) k_async_amg(const AsyncParams *__restrict__ pp)
 {
@@ -267,6 +163,8 @@ static int async_prepare(amgb_ctx *c)
    const int L = c->L;
    const amgb_options &o = c->opt;
    const bool multadd = o.solver == AMGB_SOLVER_ASYNC_MULTADD || o.solver == AMGB_SOLVER_MULTADD;
+   // factorised level-0 transfers (EXPERIMENTAL, k_async_amg_fact0 in async_fact0.cu): plain P_0 / R_0 were uploaded
+   const bool fact0 = o.factor_level0 && multadd && c->symmetric && L >= 3;
    AsyncParams hp;
    memset(&hp, 0, sizeof(hp));
    hp.num_levels = L;
@@ -300,6 +198,7 @@ static int async_prepare(amgb_ctx *c)
          }
       }
       if ((rc = amgb_dev_alloc_bytes(c, (void **)&hp.g[q].u_local, sizeof(double) * (size_t)n0, true))) return rc;
+      if (fact0 && q >= 1 && (rc = amgb_dev_alloc_bytes(c, (void **)&hp.t0[q], sizeof(double) * (size_t)n0, true))) return rc;
    }
    // CTA groups proportional to the reference's work model (ComputeWork, src/SMEM_Setup.cpp:1083-1160)
    std::vector<double> work(L, 0.0);
@@ -308,6 +207,7 @@ static int async_prepare(amgb_ctx *c)
       double w = (double)c->A[0].nnz + n0;
       const int coarsest = multadd ? k : k + 1;
       for (int l = 0; l < coarsest && l < L - 1; l++) w += multadd ? (double)c->R[l].nnz : (k < L - 1 ? (double)l * c->R[l].nnz : 0.0);
+      if (fact0 && k >= 1) w += 2.0 * c->A[0].nnz;      // the two extra passes over A_0 of the factorised level-0 transfers
       if (k == L - 1) w += c->A[k].nnz;
       else if (multadd) w += c->symmetric ? (double)o.num_fine_smooth_sweeps * (c->A[k].nnz + c->A[k].nrows) : (double)c->A[k].nrows;
       else w += (double)(o.num_coarse_smooth_sweeps - 1) * c->A[k + 1].nnz + c->P[k].nnz + c->A[k].nnz +
@@ -319,7 +219,7 @@ static int async_prepare(amgb_ctx *c)
       work[k] = w;
       tot += w;
    }
-   int grid = async_max_grid(kABlock);
+   int grid = fact0 ? async_max_grid_fact0(kABlock) : async_max_grid(kABlock);
    if (grid < L) return amgb_fail(c, AMGB_ECUDA, "cooperative grid %d smaller than the number of levels %d", grid, L);
    std::vector<int> ctas(L, 1);
    int left = grid - L;
@@ -402,8 +302,11 @@ extern "C" int amgb_solve_async(amgb_ctx *c, int num_cycles, int converge_type, 
    CUDA_OK(c, cudaMemsetAsync((void *)hp.converge_flag, 0, sizeof(int) * 4, c->stream));
    CUDA_OK(c, cudaMemcpyAsync(c->async_params_dev, &hp, sizeof(AsyncParams), cudaMemcpyHostToDevice, c->stream));
    CUDA_OK(c, cudaEventRecord(c->ev0, c->stream));
-   int lr = launch_async(c->cfg, c->stream, (const AsyncParams *)c->async_params_dev, c->async_grid, kABlock,
-                         c->window_valid ? &c->window : nullptr);
+   const bool fact0 = L > 1 && hp.t0[1] != nullptr;
+   int lr = fact0 ? launch_async_fact0(c->cfg, c->stream, (const AsyncParams *)c->async_params_dev, c->async_grid, kABlock,
+                                       c->window_valid ? &c->window : nullptr)
+                  : launch_async(c->cfg, c->stream, (const AsyncParams *)c->async_params_dev, c->async_grid, kABlock,
+                                 c->window_valid ? &c->window : nullptr);
    if (lr < 0) return amgb_fail(c, AMGB_ECUDA, "cooperative launch failed: %s", cudaGetErrorString((cudaError_t)(-lr)));
    c->launches += 1;
    CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));

@@ -549,8 +549,9 @@ int amgb_setup(amgb_ctx *c)
    const bool multadd = o.solver == AMGB_SOLVER_MULTADD || o.solver == AMGB_SOLVER_ASYNC_MULTADD;
    c->symmetric = multadd && o.num_pre_smooth_sweeps > 0 && o.num_post_smooth_sweeps > 0 &&
                   (o.smoother == AMGB_SMOOTH_JACOBI || o.smoother == AMGB_SMOOTH_L1_JACOBI);
-   if (o.factor_level0 && !(o.solver == AMGB_SOLVER_MULTADD && c->symmetric))
-      return amgb_fail(c, AMGB_EINVAL, "factor_level0 applies to synchronous Multadd with the symmetrised (L1-)Jacobi smoother");
+   // (ASYNC_MULTADD: experimental, see k_async_amg<true> in async.cu)
+   if (o.factor_level0 && !((o.solver == AMGB_SOLVER_MULTADD || o.solver == AMGB_SOLVER_ASYNC_MULTADD) && c->symmetric))
+      return amgb_fail(c, AMGB_EINVAL, "factor_level0 applies to Multadd with the symmetrised (L1-)Jacobi smoother");
    int rc;
    c->ws.assign(L, nullptr); c->dow.assign(L, nullptr); c->l1.assign(L, nullptr); c->inv_l1.assign(L, nullptr);
    c->r.assign(L, nullptr); c->e.assign(L, nullptr); c->t.assign(L, nullptr); c->w.assign(L, nullptr);

@@ -90,7 +90,13 @@ struct AsyncParams {
    int *num_correct;                        // [L] local_num_correct
    int *group_stop;                         // [L] the group root's stop decision (GLOBAL rule)
    volatile int *converge_flag;             // thread.converge_flag
+   // (appended last so that the offsets the round-1 kernel reads stay what they were)
+   double *t0[AMGB_MAX_LEVELS];             // per group: level-0 scratch of the factorised level-0 transfers (k_async_amg_fact0)
 };
 int launch_async(const LaunchCfg &cfg, cudaStream_t st, const AsyncParams *params_dev, int grid, int block,
                  const cudaAccessPolicyWindow *window);
 int async_max_grid(int block);
+// experimental copy with the level-0 transfers in factorised form (async_fact0.cu)
+int launch_async_fact0(const LaunchCfg &cfg, cudaStream_t st, const AsyncParams *params_dev, int grid, int block,
+                       const cudaAccessPolicyWindow *window);
+int async_max_grid_fact0(int block);

@@ -106,3 +106,25 @@ def test_device_smooth_transfer_matches_host(prob, n, kind):
             assert got.shape == want.shape and np.array_equal(got.indptr, want.indptr)
             assert np.array_equal(got.indices, want.indices)
             assert np.max(np.abs(got.data - want.data)) <= 1e-14 * np.max(np.abs(want.data))
+
+
+@pytest.mark.skipif(os.environ.get("AMGB_EXPERIMENTAL") != "1", reason="experimental path (factorised level-0 transfers in the persistent kernel), not validated on hardware yet")
+def test_async_factorised_level0_reaches_tolerance():
+    """k_async_amg_fact0: plain P_0 / R_0 with the smoothing factors applied on the fly inside the persistent kernel; with a
+    two-group hierarchy the chaotic iteration is sequential and must equal the explicit-product kernel to rounding"""
+    w = 0.9
+    A = H.laplacian("7pt", 24)
+    h = H.amg_setup(A)
+    b = H.rand_rhs(A.nrows)
+    h.build_transfers(H.MULTADD, w)
+    s = amg.Solver(h, H.ASYNC_MULTADD, H.JACOBI, w)
+    ref = s.SMEM_Solve(b, 1e-9, 120)
+    s.close()
+    hf = H.Hierarchy(h.A, h.P_plain)
+    hf.cpts = h.cpts
+    hf.build_transfers(H.MULTADD, w, factor_level0=True)
+    s = amg.Solver(hf, H.ASYNC_MULTADD, H.JACOBI, w, factor_level0=True)
+    out = s.SMEM_Solve(b, 1e-9, 120)
+    s.close()
+    true = O.norm2(O.spgemv(h.A[0], out["u"], b, -1.0, 1.0)) / O.norm2(b)
+    assert true < 1e-9 and abs(true - out["relres"]) <= 1e-12, (true, ref["relres"])
