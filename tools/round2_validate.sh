@@ -1,0 +1,10 @@
+#!/bin/bash
+# One gpurun call that validates and times everything round 1 left unvalidated (written when the GPU budget was spent):
+#   gpurun --timeout 900 -- 'bash tools/round2_validate.sh > gpurun_out/round2_validate.log 2>&1'
+# 1. the gated tests (device SmoothTransfer, factorised level-0 transfers in the persistent kernel, graph-captured
+#    partitioned cycle); 2. A/B timings at 256^3.
+set -x
+export AMGB_EXPERIMENTAL=1
+timeout 300 python -m pytest tests/test_zz_gpu_extended.py tests/test_gpu_dist.py -m gpu -q -k "device_smooth_transfer or async_factorised or graph_captured"
+timeout 300 python tools/async_fact0_time.py --n 256 --corrections 40
+timeout 200 python tools/iebpx_time.py --n 256
