@@ -60,6 +60,7 @@ def host_lib():
                                            C.c_double, C.POINTER(_CSR), C.c_void_p]
         L.amgh_build_extended_matrix.argtypes = [C.c_int, C.POINTER(_CSR), C.POINTER(_CSR), C.POINTER(_CSR), C.POINTER(_CSR),
                                                  C.POINTER(C.c_int)]
+        L.amgh_difconv_7pt.argtypes = [C.c_int] * 3 + [C.c_double] * 6 + [C.c_int, C.POINTER(_CSR)]
         L.amgh_permute.argtypes = [C.POINTER(_CSR), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.POINTER(_CSR)]
         L.amgh_read_binary_triplets.argtypes = [C.c_char_p, C.c_int, C.POINTER(_CSR)]
         L.amgh_write_binary_triplets.argtypes = [C.POINTER(_CSR), C.c_char_p, C.c_int]
@@ -150,6 +151,18 @@ def laplacian(problem, nx, ny=None, nz=None):
         rc = L.amgh_laplacian_27pt(C.c_int(nx), C.c_int(ny), C.c_int(nz), C.byref(out))
     else:
         raise ValueError("unknown problem %r" % problem)
+    if rc != 0:
+        raise ValueError("problem too large for int32 CSR")
+    return _take(out)
+
+
+def difconv(nx, ny=None, nz=None, c=(1.0, 1.0, 1.0), a=(1.0, 1.0, 1.0), atype=-1):
+    """`-problem difconv`: 3-D 7-point convection-diffusion stencil (src/BuildHypreMatrix.cpp:104-245; reference defaults
+    c = a = 1, atype = -1 = centred, src/SMEM_Main.cpp:47-53).  Nonsymmetric; diag-first CSR, natural ordering."""
+    ny = nx if ny is None else ny
+    nz = nx if nz is None else nz
+    out = _CSR()
+    rc = host_lib().amgh_difconv_7pt(nx, ny, nz, c[0], c[1], c[2], a[0], a[1], a[2], int(atype), C.byref(out))
     if rc != 0:
         raise ValueError("problem too large for int32 CSR")
     return _take(out)

@@ -428,6 +428,63 @@ int amgh_laplacian_7pt(int nx, int ny, int nz, amgh_csr *out)
    return 0;
 }
 
+// 3-D convection-diffusion, 7-point (`-problem difconv`): -c.Laplace(u) + a.grad(u) on the unit cube, h = 1/(n+1), with the
+// stencil coefficients exactly as the caller of hypre's GenerateDifConv computes them (src/BuildHypreMatrix.cpp:104-245):
+// atype 0 forward, 1 backward, 3 upwind (per direction: backward when c and a have the same sign), otherwise centred
+// differences for the convection term.  values[1..3] multiply the x-1 / y-1 / z-1 neighbours, values[4..6] the x+1 / y+1 /
+// z+1 ones (hypre par_difconv.c; un-vendored, restated).  NONSYMMETRIC for a != 0.  Diag first, then ascending columns.
+int amgh_difconv_7pt(int nx, int ny, int nz, double cx, double cy, double cz, double ax, double ay, double az, int atype, amgh_csr *out)
+{
+   const long N = (long)nx * ny * nz;
+   if (N * 7 > 2147483000L) return 1;
+   const double hx = 1.0 / (nx + 1), hy = 1.0 / (ny + 1), hz = 1.0 / (nz + 1);
+   const double c[3] = {cx, cy, cz}, a[3] = {ax, ay, az}, h[3] = {hx, hy, hz};
+   const int dim[3] = {nx, ny, nz};
+   double v[7] = {0, 0, 0, 0, 0, 0, 0};
+   auto sgn = [](double x) { return x > 0 ? 1 : (x < 0 ? -1 : 0); };
+   for (int d = 0; d < 3; d++) {
+      const double diff = c[d] / (h[d] * h[d]);
+      int scheme = atype;                       // 0 forward, 1 backward, else centred
+      if (atype == 3) scheme = (sgn(c[d]) * sgn(a[d]) == 1) ? 1 : 0;
+      if (scheme == 0) {
+         v[1 + d] = -diff; v[4 + d] = -diff + a[d] / h[d];
+         if (dim[d] > 1) v[0] += 2.0 * diff - a[d] / h[d];
+      } else if (scheme == 1) {
+         v[1 + d] = -diff - a[d] / h[d]; v[4 + d] = -diff;
+         if (dim[d] > 1) v[0] += 2.0 * diff + a[d] / h[d];
+      } else {
+         v[1 + d] = -diff - a[d] / (2.0 * h[d]); v[4 + d] = -diff + a[d] / (2.0 * h[d]);
+         if (dim[d] > 1) v[0] += 2.0 * diff;
+      }
+   }
+   std::vector<int> ptr((size_t)N + 1);
+   ptr[0] = 0;
+   for (int z = 0; z < nz; z++)
+      for (int y = 0; y < ny; y++)
+         for (int x = 0; x < nx; x++) {
+            const long r = x + (long)nx * (y + (long)ny * z);
+            ptr[r + 1] = 1 + (x > 0) + (x < nx - 1) + (y > 0) + (y < ny - 1) + (z > 0) + (z < nz - 1);
+         }
+   for (long r = 0; r < N; r++) ptr[r + 1] += ptr[r];
+   csr_alloc(out, (int)N, (int)N, ptr[N]);
+   memcpy(out->i, ptr.data(), sizeof(int) * ((size_t)N + 1));
+#pragma omp parallel for collapse(2) schedule(static)
+   for (int z = 0; z < nz; z++)
+      for (int y = 0; y < ny; y++)
+         for (int x = 0; x < nx; x++) {
+            const int r = x + nx * (y + ny * z);
+            int d = out->i[r];
+            out->j[d] = r; out->data[d++] = v[0];
+            if (z > 0) { out->j[d] = r - nx * ny; out->data[d++] = v[3]; }
+            if (y > 0) { out->j[d] = r - nx; out->data[d++] = v[2]; }
+            if (x > 0) { out->j[d] = r - 1; out->data[d++] = v[1]; }
+            if (x < nx - 1) { out->j[d] = r + 1; out->data[d++] = v[4]; }
+            if (y < ny - 1) { out->j[d] = r + nx; out->data[d++] = v[5]; }
+            if (z < nz - 1) { out->j[d] = r + nx * ny; out->data[d++] = v[6]; }
+         }
+   return 0;
+}
+
 // 3-D 27-point: diag 26 (8 / 2 for degenerate dims), off -1  (src/BuildHypreMatrix.cpp:277-286)
 int amgh_laplacian_27pt(int nx, int ny, int nz, amgh_csr *out)
 {

@@ -245,3 +245,25 @@ def test_eebpx_matches_live_reference():
         if r["iters"] == out["iters"]:
             assert np.max(np.abs(out["xx"] - r["xx"])) <= 1e-13 * np.max(np.abs(r["xx"]))
             assert np.max(np.abs(out["x"] - r["x"])) <= 1e-13 * np.max(np.abs(r["x"]))
+
+
+# ---- nonsymmetric operators: `-problem difconv` (src/BuildHypreMatrix.cpp:104-245) ---------------------------------------
+@pytest.mark.parametrize("a,atype", [((40.0, -20.0, 10.0), 3), ((10.0, 10.0, 10.0), 0), ((5.0, 5.0, 5.0), -1)])
+def test_nonsymmetric_difconv_history_matches_live_reference(a, atype):
+    """convection-diffusion stencils (upwind / forward / centred): the oracle's synchronous Multadd history against the
+    reference's object code on a NONSYMMETRIC hierarchy (R-bar = P^T GT scales A's columns, src/SMEM_Setup.cpp:1209-1253)"""
+    if O.ref_lib() is None:
+        pytest.skip("oracle/_ref not built here")
+    A = H.difconv(12, a=a, atype=atype)
+    S = A.to_scipy().copy()
+    assert abs(S - S.T).max() > 1.0                                  # really nonsymmetric
+    assert abs(S[12 * 12 * 5 + 12 * 5 + 5].sum()) < 1e-10 * abs(S).max()   # interior row sums vanish (pure derivatives)
+    h = H.amg_setup(A)
+    b = H.rand_rhs(A.nrows)
+    h.build_transfers(H.MULTADD, 0.9)
+    _, hist, _ = O.Problem(h, H.MULTADD, H.JACOBI, 0.9).solve_sync(b, 1e-9, 100)
+    rs = O.RefSolver(h, H.MULTADD, H.JACOBI, b, 0.9, one_thread_per_level=True)
+    out = rs.solve_sync_det(100, 1e-9)
+    rs.close()
+    assert len(hist) == len(out["hist"]) and hist[-1] < 1e-9
+    assert np.max(np.abs(hist - out["hist"])) <= HIST_TOL

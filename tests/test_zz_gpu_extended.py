@@ -128,3 +128,18 @@ def test_async_factorised_level0_reaches_tolerance():
     s.close()
     true = O.norm2(O.spgemv(h.A[0], out["u"], b, -1.0, 1.0)) / O.norm2(b)
     assert true < 1e-9 and abs(true - out["relres"]) <= 1e-12, (true, ref["relres"])
+
+
+@pytest.mark.skipif(os.environ.get("AMGB_EXPERIMENTAL") != "1", reason="nonsymmetric operators on the device: test written after the GPU budget was spent")
+@pytest.mark.parametrize("a,atype", [((40.0, -20.0, 10.0), 3), ((10.0, 10.0, 10.0), 0)])
+def test_nonsymmetric_difconv_matches_oracle(a, atype):
+    """`-problem difconv` (nonsymmetric 7-point convection-diffusion): operators and the synchronous Multadd history"""
+    A = H.difconv(14, a=a, atype=atype)
+    h = H.amg_setup(A)
+    b = H.rand_rhs(A.nrows)
+    h.build_transfers(H.MULTADD, 0.9)
+    _, want, _ = O.Problem(h, H.MULTADD, H.JACOBI, 0.9).solve_sync(b, 1e-9, 100)
+    s = amg.Solver(h, H.MULTADD, H.JACOBI, 0.9)
+    got = s.SMEM_Solve(b, 1e-9, 100)["hist"]
+    assert len(got) == len(want) and np.max(np.abs(got - want)) <= HIST_TOL
+    s.close()
