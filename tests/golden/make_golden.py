@@ -175,7 +175,36 @@ def iebpx_golden():
     np.savez_compressed(os.path.join(OUT, "iebpx.npz"), **d)
 
 
+def hybrid_jgs_golden():
+    """Multadd with the hybrid Jacobi / Gauss-Seidel smoother (SMEM_Sync_HybridJacobiGaussSeidel, src/SMEM_Smooth.cpp:533-586;
+    -num_post_smooth_sweeps 0) through the reference's object code with SEVERAL threads per level: a thread's row range is
+    its Gauss-Seidel block, so the block lists are stored with the history."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import hierarchy_from_golden
+    d = {}
+    for name in ("lap5pt_n32", "lap7pt_n12"):
+        h, g = hierarchy_from_golden(name)
+        b, w = g["b"], 0.9
+        h.build_transfers(H.MULTADD, w, num_pre=1, num_post=0)
+        for nt in (h.num_levels, 16):
+            rs = O.RefSolver(h, H.MULTADD, H.HYBRID_JACOBI_GAUSS_SEIDEL, b, w, num_pre=1, num_post=0, num_threads=nt,
+                             one_thread_per_level=(nt == h.num_levels))
+            tpl = np.asarray(rs.threads_per_level, dtype=np.int32)
+            out = rs.solve_sync_det(80, 1e-9)
+            rs.close()
+            k = "%s_nt%d_" % (name, 16 if nt == 16 else 0)
+            d[k + "threads_per_level"] = tpl
+            d[k + "hist"] = out["hist"]
+            print(k, tpl, len(out["hist"]) - 1, out["hist"][-1])
+    np.savez_compressed(os.path.join(OUT, "hybrid_jgs.npz"), **d)
+
+
 if __name__ == "__main__":
+    if "--hybrid-jgs-only" in sys.argv:
+        from oracle import build as obuild
+        amg.build.build_host(); obuild.build_oracle(); obuild.build_ref()
+        hybrid_jgs_golden()
+        sys.exit(0)
     if "--iebpx-only" in sys.argv:
         from oracle import build as obuild
         amg.build.build_host(); obuild.build_oracle(); obuild.build_ref()
@@ -189,3 +218,4 @@ if __name__ == "__main__":
     matrix_file_golden()
     if "--matrix-file-only" not in sys.argv:
         iebpx_golden()
+        hybrid_jgs_golden()

@@ -267,3 +267,22 @@ def test_nonsymmetric_difconv_history_matches_live_reference(a, atype):
     rs.close()
     assert len(hist) == len(out["hist"]) and hist[-1] < 1e-9
     assert np.max(np.abs(hist - out["hist"])) <= HIST_TOL
+
+
+# ---- hybrid Jacobi / Gauss-Seidel pinned by the reference's object code (block = a thread's row range) ---------------------
+@pytest.mark.parametrize("name", ["lap5pt_n32", "lap7pt_n12"])
+@pytest.mark.parametrize("tag", ["nt0", "nt16"])
+def test_hybrid_jgs_history_matches_reference_fixture(name, tag):
+    """SMEM_Sync_HybridJacobiGaussSeidel inside Multadd (-num_post_smooth_sweeps 0) with one and with several threads per
+    level: the oracle replays the reference's blocks (the nnz-balanced thread ranges, src/SMEM_Setup.cpp:945-979)"""
+    import os
+    from conftest import GOLDEN, hierarchy_from_golden
+    g = dict(np.load(os.path.join(GOLDEN, "hybrid_jgs.npz")))
+    h, d = hierarchy_from_golden(name)
+    h.build_transfers(H.MULTADD, 0.9, num_pre=1, num_post=0)
+    tpl = g["%s_%s_threads_per_level" % (name, tag)]
+    blocks = [H.nnz_balanced_bounds(h.A[l].indptr, int(tpl[l])) for l in range(h.num_levels)]
+    _, hist, _ = O.Problem(h, H.MULTADD, H.HYBRID_JACOBI_GAUSS_SEIDEL, 0.9, num_pre=1, num_post=0,
+                           jgs_blocks=blocks).solve_sync(d["b"], 1e-9, 80)
+    _close_hist(hist, g["%s_%s_hist" % (name, tag)])
+    assert hist[-1] < 1e-9
