@@ -199,7 +199,33 @@ def hybrid_jgs_golden():
     np.savez_compressed(os.path.join(OUT, "hybrid_jgs.npz"), **d)
 
 
+def cheby_golden():
+    """SMEM_Solve with -cheby (Chebyshev acceleration of the BPX cycle, src/SMEM_Solve.cpp:169-188, precond_flag = 1) through
+    the reference's object code, 4 threads (omp-for cycle: deterministic)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import hierarchy_from_golden
+    d = {}
+    for name in ("lap5pt_n32", "lap7pt_n12"):
+        h, g = hierarchy_from_golden(name)
+        b, w = g["b"], 0.8
+        h.build_transfers(H.BPX, w)
+        lo, hi = O.Problem(h, H.BPX, H.JACOBI, w).eigs_power(20)
+        mu, delta = (hi + lo) / (hi - lo), 2.0 / (hi + lo)
+        rs = O.RefSolver(h, H.BPX, H.JACOBI, b, w, num_threads=4)
+        out = rs.solve(200, 1e-9, async_type=0, cheby=(mu, delta), precond=1)
+        rs.close()
+        d[name + "_mu_delta"] = np.asarray([mu, delta])
+        d[name + "_hist"] = out["hist"]
+        print(name, len(out["hist"]) - 1, out["hist"][-1])
+    np.savez_compressed(os.path.join(OUT, "cheby_bpx.npz"), **d)
+
+
 if __name__ == "__main__":
+    if "--cheby-only" in sys.argv:
+        from oracle import build as obuild
+        amg.build.build_host(); obuild.build_oracle(); obuild.build_ref()
+        cheby_golden()
+        sys.exit(0)
     if "--hybrid-jgs-only" in sys.argv:
         from oracle import build as obuild
         amg.build.build_host(); obuild.build_oracle(); obuild.build_ref()
@@ -219,3 +245,4 @@ if __name__ == "__main__":
     if "--matrix-file-only" not in sys.argv:
         iebpx_golden()
         hybrid_jgs_golden()
+        cheby_golden()

@@ -286,3 +286,17 @@ def test_hybrid_jgs_history_matches_reference_fixture(name, tag):
                            jgs_blocks=blocks).solve_sync(d["b"], 1e-9, 80)
     _close_hist(hist, g["%s_%s_hist" % (name, tag)])
     assert hist[-1] < 1e-9
+
+
+@pytest.mark.parametrize("name", ["lap5pt_n32", "lap7pt_n12"])
+def test_chebyshev_accelerated_bpx_matches_reference_fixture(name):
+    """the -cheby branch of SMEM_Solve (src/SMEM_Solve.cpp:169-188) around the BPX cycle, from the reference's object code"""
+    import os
+    from conftest import GOLDEN, hierarchy_from_golden
+    g = dict(np.load(os.path.join(GOLDEN, "cheby_bpx.npz")))
+    h, d = hierarchy_from_golden(name)
+    h.build_transfers(H.BPX, 0.8)
+    mu, delta = g[name + "_mu_delta"]
+    _, hist, _ = O.Problem(h, H.BPX, H.JACOBI, 0.8).solve_sync(d["b"], 1e-9, 200, cheby=(mu, delta))
+    _close_hist(hist, g[name + "_hist"])
+    assert hist[-1] < 1e-9
