@@ -143,3 +143,18 @@ def test_nonsymmetric_difconv_matches_oracle(a, atype):
     got = s.SMEM_Solve(b, 1e-9, 100)["hist"]
     assert len(got) == len(want) and np.max(np.abs(got - want)) <= HIST_TOL
     s.close()
+
+
+@pytest.mark.skipif(os.environ.get("AMGB_EXPERIMENTAL") != "1", reason="test written after the GPU budget was spent")
+@pytest.mark.parametrize("name", ["lap5pt_n32", "lap7pt_n12"])
+def test_hybrid_jgs_single_block_matches_reference_fixture(name):
+    """hybrid Jacobi / Gauss-Seidel against the reference's OWN object code: with one thread per level the reference's block
+    is the whole level (pure Gauss-Seidel); jgs_block_rows >= n_0 gives the device the same single block"""
+    g = dict(np.load(os.path.join(GOLDEN, "hybrid_jgs.npz")))
+    h, d = hierarchy_from_golden(name)
+    h.build_transfers(H.MULTADD, 0.9, num_pre=1, num_post=0)
+    s = amg.Solver(h, H.MULTADD, H.HYBRID_JACOBI_GAUSS_SEIDEL, 0.9, num_pre=1, num_post=0, jgs_block_rows=h.n[0])
+    got = s.SMEM_Solve(d["b"], 1e-9, 80)["hist"]
+    want = g["%s_nt0_hist" % name]
+    assert len(got) == len(want) and np.max(np.abs(got - want)) <= HIST_TOL
+    s.close()
