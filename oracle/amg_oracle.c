@@ -7,8 +7,9 @@
  *
  * Parity status: PINNED against the reference's own object code -- oracle/_ref compiles the
  * unmodified reference translation units SMEM_MatVec.cpp, SMEM_Smooth.cpp, SMEM_Sync_AMG.cpp,
- * SMEM_Async_AMG.cpp, SMEM_Solve.cpp, SEQ_*.cpp against a hypre stub shim and
- * tests/test_oracle_vs_ref.py compares both on the same inputs; the outputs are also
+ * SMEM_Async_AMG.cpp, SMEM_ExtendedSystem.cpp, SMEM_Solve.cpp, SEQ_*.cpp, Misc.cpp, DMEM_Mult.cpp, DMEM_Misc.cpp (the DMEM
+ * files for ONE rank) against a hypre / MPI stub shim and
+ * tests/test_oracle_golden.py compares both on the same inputs; the outputs are also
  * committed as fixtures under tests/golden/.  The reference ships no golden vectors of its
  * own.  The hierarchy (A_l, P_l) is an INPUT here -- hypre's setup is an
  * un-vendored third-party dependency and is not restated.

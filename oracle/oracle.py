@@ -259,6 +259,37 @@ def ref_solve_eebpx(h, AA, disp, bb, num_cycles, tol=1e-9, mu=1.0, delta=1.0, nu
     return dict(x=x, xx=xx, iters=it, ext_relres=er.value, relres=rr.value)
 
 
+def ref_dmem_sync_add(h, b, smooth_weight, symmetrised=True, num_cycles=100, tol=1e-9):
+    """the reference's DMEM_SyncAdd / DMEM_SyncAddCycle object code (src/DMEM_Mult.cpp:263-450) on one rank, Multadd with the
+    DMEM conventions (direct solve on the coarsest level); h.P / h.R are the smoothed transfers.  -> (x, hist)"""
+    L = ref_lib()
+    nl = h.num_levels
+    Rt = [_pkg.hierarchy.CSR.from_scipy(r.to_scipy().T.tocsr()) for r in h.R]     # hypre applies R_array transposed
+    keep = (list(h.A), list(h.P), Rt)
+    A = (OrcCSR * nl)(*[c_csr(a) for a in h.A])
+    P = (OrcCSR * max(nl - 1, 1))(*[c_csr(p) for p in h.P])
+    R = (OrcCSR * max(nl - 1, 1))(*[c_csr(r) for r in Rt])
+    x, hist = np.zeros(h.n[0]), np.zeros(num_cycles + 1)
+    L.ref_dmem_sync_add.restype = C.c_int
+    L.ref_dmem_sync_add.argtypes = [C.c_int, C.POINTER(OrcCSR), C.POINTER(OrcCSR), C.POINTER(OrcCSR), C.c_double, C.c_int, DP,
+                                    C.c_int, C.c_double, DP, DP]
+    k = L.ref_dmem_sync_add(nl, A, P, R, smooth_weight, int(symmetrised), dptr(np.ascontiguousarray(b, dtype=np.float64)),
+                            num_cycles, tol, dptr(x), dptr(hist))
+    del keep
+    return x, hist[:k + 1]
+
+
+def ref_dmem_cheby_update(d, u, cycle, mu, delta, c, c_prev, accel_type=1):
+    """DMEM_ChebyUpdate (src/DMEM_Misc.cpp:612-666), synchronous branch, in place on copies -> (d, u, c, c_prev)"""
+    L = ref_lib()
+    d, u = np.array(d, dtype=np.float64), np.array(u, dtype=np.float64)
+    cc, cp = C.c_double(c), C.c_double(c_prev)
+    L.ref_dmem_cheby_update.restype = None
+    L.ref_dmem_cheby_update.argtypes = [C.c_int, DP, DP, C.c_int, C.c_double, C.c_double, C.c_int, DP, DP]
+    L.ref_dmem_cheby_update(len(d), dptr(d), dptr(u), cycle, mu, delta, accel_type, C.byref(cc), C.byref(cp))
+    return d, u, cc.value, cp.value
+
+
 def ref_read_matrix(path, symm_flag=1):
     """the reference's own reader (ReadBinary_fread_HypreParCSR, src/Misc.cpp:800-915) -> (indptr, indices, data)"""
     L = ref_lib()

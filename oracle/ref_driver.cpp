@@ -19,6 +19,9 @@
 #include "SEQ_Smooth.hpp"
 #include "SMEM_Sync_AMG.hpp"
 #include "SMEM_ExtendedSystem.hpp"
+#include "DMEM_Main.hpp"
+#include "DMEM_Mult.hpp"
+#include "DMEM_Misc.hpp"
 #include <cstdarg>
 
 static AllData *g_all = nullptr;
@@ -56,10 +59,79 @@ HYPRE_Int hypre_CSRMatrixGetLoadBalancedPartitionBegin(hypre_CSRMatrix *A) { ret
 HYPRE_Int hypre_CSRMatrixGetLoadBalancedPartitionEnd(hypre_CSRMatrix *A) { return lb_boundary(A, omp_get_thread_num() + 1); }
 // SMEM additive cycles call this on hypre's own F/U arrays, which the cycle never reads
 // (SURVEY.md 5.9c): a no-op reproduces the reference result exactly.
-HYPRE_Int hypre_GaussElimSolve(hypre_ParAMGData *, HYPRE_Int, HYPRE_Int) { return 0; }
+// DMEM convention (driver flag functional_gauss_elim): U_array[level] = A_array[level]^{-1} F_array[level] by dense Gaussian
+// elimination with partial pivoting (hypre_GaussElimSetup / Solve, relax types 9 / 99; un-vendored, restated).
+HYPRE_Int hypre_GaussElimSolve(hypre_ParAMGData *amg, HYPRE_Int level, HYPRE_Int)
+{
+   if (!amg || !amg->functional_gauss_elim) return 0;
+   hypre_CSRMatrix *A = amg->A_array[level]->diag;
+   const int n = A->num_rows;
+   std::vector<double> M((size_t)n * (n + 1), 0.0);
+   const double *f = amg->F_array[level]->local_vector->data;
+   double *u = amg->U_array[level]->local_vector->data;
+   for (int i = 0; i < n; i++) {
+      for (int jj = A->i[i]; jj < A->i[i + 1]; jj++) M[(size_t)i * (n + 1) + A->j[jj]] += A->data[jj];
+      M[(size_t)i * (n + 1) + n] = f[i];
+   }
+   for (int k = 0; k < n; k++) {
+      int piv = k;
+      for (int i = k + 1; i < n; i++) if (fabs(M[(size_t)i * (n + 1) + k]) > fabs(M[(size_t)piv * (n + 1) + k])) piv = i;
+      if (piv != k) for (int j = 0; j <= n; j++) std::swap(M[(size_t)k * (n + 1) + j], M[(size_t)piv * (n + 1) + j]);
+      for (int i = k + 1; i < n; i++) {
+         const double fct = M[(size_t)i * (n + 1) + k] / M[(size_t)k * (n + 1) + k];
+         if (fct != 0.0) for (int j = k; j <= n; j++) M[(size_t)i * (n + 1) + j] -= fct * M[(size_t)k * (n + 1) + j];
+      }
+   }
+   for (int i = n - 1; i >= 0; i--) {
+      double t = M[(size_t)i * (n + 1) + n];
+      for (int j = i + 1; j < n; j++) t -= M[(size_t)i * (n + 1) + j] * u[j];
+      u[i] = t / M[(size_t)i * (n + 1) + i];
+   }
+   return 0;
+}
 HYPRE_Int HYPRE_BoomerAMGSetPrintLevel(HYPRE_Solver, HYPRE_Int) { return 0; }
 HYPRE_Int HYPRE_BoomerAMGSetMaxIter(HYPRE_Solver, HYPRE_Int) { return 0; }
-HYPRE_Int hypre_ParVectorSetConstantValues(hypre_ParVector *, HYPRE_Complex) { return 0; }
+HYPRE_Int hypre_ParVectorSetConstantValues(hypre_ParVector *v, HYPRE_Complex value)
+{
+   if (v && v->local_vector && v->local_vector->data)
+      for (int i = 0; i < v->local_vector->size; i++) v->local_vector->data[i] = value;
+   return 0;
+}
+// single-rank hypre vector / matrix operations named by the DMEM translation units (dmem_stub.h)
+HYPRE_Int vecop_machine = HYPRE_MEMORY_HOST;            // src/DMEM_Main.cpp:10
+HYPRE_Int hypre_ParCSRMatrixMatvecT(HYPRE_Complex alpha, hypre_ParCSRMatrix *A, hypre_ParVector *x, HYPRE_Complex beta, hypre_ParVector *y)
+{
+   hypre_CSRMatrix *M = A->diag;
+   const double *xd = x->local_vector->data;
+   double *yd = y->local_vector->data;
+   for (int j = 0; j < M->num_cols; j++) yd[j] *= beta;
+   for (int i = 0; i < M->num_rows; i++)
+      for (int jj = M->i[i]; jj < M->i[i + 1]; jj++) yd[M->j[jj]] += alpha * M->data[jj] * xd[i];
+   return 0;
+}
+HYPRE_Int hypre_BoomerAMGRelax(hypre_ParCSRMatrix *, hypre_ParVector *, HYPRE_Int *, HYPRE_Int, HYPRE_Int, HYPRE_Real, HYPRE_Real, HYPRE_Real *,
+                               hypre_ParVector *, hypre_ParVector *, hypre_ParVector *) { abort(); }
+HYPRE_Real hypre_SeqVectorInnerProd(hypre_Vector *x, hypre_Vector *y)
+{
+   double s = 0.0;
+   for (int i = 0; i < x->size; i++) s += x->data[i] * y->data[i];
+   return s;
+}
+HYPRE_Real hypre_ParVectorInnerProd(hypre_ParVector *x, hypre_ParVector *y) { return hypre_SeqVectorInnerProd(x->local_vector, y->local_vector); }
+HYPRE_Int hypre_ParVectorScale(HYPRE_Complex alpha, hypre_ParVector *y)
+{
+   for (int i = 0; i < y->local_vector->size; i++) y->local_vector->data[i] *= alpha;
+   return 0;
+}
+HYPRE_Int hypre_ParVectorAxpy(HYPRE_Complex alpha, hypre_ParVector *x, hypre_ParVector *y)
+{
+   for (int i = 0; i < y->local_vector->size; i++) y->local_vector->data[i] += alpha * x->local_vector->data[i];
+   return 0;
+}
+hypre_ParVector *hypre_ParVectorCreate(MPI_Comm, HYPRE_BigInt, HYPRE_BigInt *) { abort(); }
+HYPRE_Int hypre_ParVectorInitialize(hypre_ParVector *) { abort(); }
+HYPRE_Int hypre_ParVectorDestroy(hypre_ParVector *) { abort(); }
+HYPRE_Int hypre_ParVectorSetPartitioningOwner(hypre_ParVector *, HYPRE_Int) { abort(); }
 // hypre ParCSR matvecs as far as SMEM_ExtendedSystem.cpp's EXPLICIT_EXTENDED_SYSTEM_BPX branch uses them (one rank: the
 // diag block is the whole matrix): y = alpha A x + beta b  /  y = alpha A x + beta y  /  y = x
 HYPRE_Int hypre_ParCSRMatrixMatvecOutOfPlace(HYPRE_Complex alpha, hypre_ParCSRMatrix *A, hypre_ParVector *x, HYPRE_Complex beta,
@@ -542,6 +614,90 @@ int ref_solve_eebpx(int L, const RefCSR *A, const RefCSR *P, const RefCSR *AAin,
    if (ext_relres) *ext_relres = ad->output.r_norm2_ext_sys / ad->output.r0_norm2_ext_sys;
    if (relres) *relres = ad->output.r_norm2 / ad->output.r0_norm2;
    return lnc[0];
+}
+
+// ---- DMEM: the synchronous additive solve on all ranks, ONE rank -------------------------------------------------------
+// DMEM_SyncAdd (src/DMEM_Mult.cpp:263-319) = DMEM_SyncAddCycle (:322-450) + residual + norm per cycle, the reference's
+// object code.  hypre's solver object is filled the way DMEM_Setup leaves it for this path: A_array, P_array (the smoothed
+// interpolants), R_array applied TRANSPOSED (hypre_ParCSRMatrixMatvecT; Rt[l] is n_l x n_{l+1}), add_rlx_wt = omega,
+// simple = -1 for the symmetrised smoother (src/DMEM_Setup.cpp:465-483), GridRelaxType[1] = 0 (Jacobi), and a direct solve
+// on the coarsest level.  x0 = 0, r = b.  hist[k] = ||b - A x_k|| / ||b||.  Returns the cycles done.
+int ref_dmem_sync_add(int L, const RefCSR *A, const RefCSR *P, const RefCSR *Rt, double smooth_weight, int symmetrised,
+                      const double *b, int num_cycles, double tol, double *x_out, double *hist)
+{
+   DMEM_AllData *dm = new DMEM_AllData();
+   std::vector<hypre_CSRMatrix> hA(L), hP(L), hR(L);
+   std::vector<hypre_ParCSRMatrix> pA(L), pP(L), pR(L);
+   std::vector<hypre_ParCSRMatrix *> Aarr(L), Parr(L), Rarr(L);
+   std::vector<std::vector<double>> ud(L), fd(L);
+   std::vector<hypre_Vector> uv(L), fv(L);
+   std::vector<hypre_ParVector> up(L), fp(L);
+   std::vector<hypre_ParVector *> Uarr(L), Farr(L);
+   std::vector<double *> l1(L, nullptr);
+   for (int l = 0; l < L; l++) {
+      fill(&hA[l], A[l]); memset(&pA[l], 0, sizeof(pA[l])); pA[l].diag = &hA[l]; pA[l].global_num_rows = A[l].nrows; Aarr[l] = &pA[l];
+      if (l < L - 1) {
+         fill(&hP[l], P[l]); memset(&pP[l], 0, sizeof(pP[l])); pP[l].diag = &hP[l]; pP[l].global_num_rows = P[l].nrows; Parr[l] = &pP[l];
+         fill(&hR[l], Rt[l]); memset(&pR[l], 0, sizeof(pR[l])); pR[l].diag = &hR[l]; pR[l].global_num_rows = Rt[l].nrows; Rarr[l] = &pR[l];
+      }
+      ud[l].assign(A[l].nrows, 0.0); fd[l].assign(A[l].nrows, 0.0);
+      uv[l].data = ud[l].data(); uv[l].size = A[l].nrows; up[l].local_vector = &uv[l]; Uarr[l] = &up[l];
+      fv[l].data = fd[l].data(); fv[l].size = A[l].nrows; fp[l].local_vector = &fv[l]; Farr[l] = &fp[l];
+   }
+   const int n0 = A[0].nrows;
+   std::vector<double> vt(n0, 0.0), xv(n0, 0.0), rv(b, b + n0), bv(b, b + n0), ev(n0, 0.0);
+   hypre_Vector hv[5];
+   hypre_ParVector pv[5];
+   double *ptrs[5] = {vt.data(), xv.data(), rv.data(), bv.data(), ev.data()};
+   for (int k = 0; k < 5; k++) { hv[k].data = ptrs[k]; hv[k].size = n0; pv[k].local_vector = &hv[k]; }
+   hypre_ParAMGData amg;
+   memset(&amg, 0, sizeof(amg));
+   int relax_type[4] = {0, 0, 0, 0};
+   amg.A_array = Aarr.data(); amg.P_array = Parr.data(); amg.R_array = Rarr.data(); amg.P_array_afacj = Parr.data();
+   amg.F_array = Farr.data(); amg.U_array = Uarr.data(); amg.Vtemp = &pv[0]; amg.Ztemp = &pv[0];
+   amg.l1_norms = l1.data(); amg.num_levels = L; amg.grid_relax_type = relax_type; amg.add_rlx_wt = smooth_weight;
+   amg.simple = symmetrised ? -1 : 0; amg.functional_gauss_elim = 1;
+   dm->hypre.solver = (HYPRE_Solver)&amg;
+   dm->input.solver = SYNC_MULTADD;
+   dm->input.tol = tol;
+   dm->input.num_cycles = 1;                               // one cycle per call: the history is collected here
+   dm->vector_fine.x = &pv[1]; dm->vector_fine.r = &pv[2]; dm->vector_fine.b = &pv[3]; dm->vector_fine.e = &pv[4];
+   double r0 = 0.0;
+   for (int i = 0; i < n0; i++) r0 += b[i] * b[i];
+   r0 = sqrt(r0);
+   dm->output.r0_norm2 = r0;
+   if (hist) hist[0] = 1.0;
+   int done = 0;
+   for (int k = 1; k <= num_cycles; k++) {
+      DMEM_SyncAdd(dm);                                    // cycle + residual into vector_fine.r (+ its norm, discarded)
+      double rn = 0.0;
+      for (int i = 0; i < n0; i++) rn += rv[i] * rv[i];
+      done = k;
+      if (hist) hist[k] = sqrt(rn) / r0;
+      if (sqrt(rn) / r0 < tol) break;
+   }
+   if (x_out) memcpy(x_out, xv.data(), sizeof(double) * n0);
+   delete dm;
+   return done;
+}
+
+// DMEM_ChebyUpdate (src/DMEM_Misc.cpp:612-666), synchronous branch: d and u of length n, `cycle` = iter.cycle; c / c_prev are
+// the recurrence state (in / out)
+void ref_dmem_cheby_update(int n, double *d, double *u, int cycle, double mu, double delta, int accel_type, double *c, double *c_prev)
+{
+   DMEM_AllData *dm = new DMEM_AllData();
+   hypre_Vector dv, uv;
+   hypre_ParVector dp, upv;
+   dv.data = d; dv.size = n; dp.local_vector = &dv;
+   uv.data = u; uv.size = n; upv.local_vector = &uv;
+   dm->cheby.mu = mu; dm->cheby.delta = delta; dm->cheby.c = *c; dm->cheby.c_prev = *c_prev;
+   dm->iter.cycle = cycle;
+   dm->input.accel_type = accel_type;
+   dm->input.solver = SYNC_MULTADD;
+   dm->input.async_flag = 0;
+   DMEM_ChebyUpdate(dm, &dp, &upv, n);
+   *c = dm->cheby.c; *c_prev = dm->cheby.c_prev;
+   delete dm;
 }
 
 void ref_destroy(void *h) { delete (RefHandle *)h; }

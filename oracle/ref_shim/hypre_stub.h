@@ -39,7 +39,9 @@ typedef struct { HYPRE_Real *data; HYPRE_Int size; } hypre_Vector;
 #define hypre_VectorSize(v) ((v)->size)
 typedef struct { hypre_Vector *local_vector; } hypre_ParVector;
 #define hypre_ParVectorLocalVector(v) ((v)->local_vector)
-typedef struct { hypre_CSRMatrix *diag; HYPRE_Int global_num_rows; } hypre_ParCSRMatrix;
+typedef struct { hypre_CSRMatrix *diag; HYPRE_Int global_num_rows;
+                 /* named by the DMEM translation units only (dmem_stub.h); never read on the driver's single-rank paths */
+                 hypre_CSRMatrix *offd; HYPRE_BigInt *row_starts; HYPRE_BigInt *col_map_offd; MPI_Comm comm; } hypre_ParCSRMatrix;
 #define hypre_ParCSRMatrixDiag(m) ((m)->diag)
 #define hypre_ParCSRMatrixNumRows(m) ((m)->global_num_rows)
 typedef struct {
@@ -47,6 +49,10 @@ typedef struct {
    hypre_ParVector **F_array, **U_array;
    hypre_ParVector *Vtemp, *Ztemp;
    HYPRE_Real **l1_norms;
+   /* DMEM side (src/DMEM_Mult.cpp): */
+   HYPRE_Int num_levels; HYPRE_Int *grid_relax_type; HYPRE_Real add_rlx_wt; HYPRE_Int simple; HYPRE_Real *relax_weight;
+   hypre_ParCSRMatrix **P_array_afacj;
+   HYPRE_Int functional_gauss_elim;   /* driver flag: hypre_GaussElimSolve really solves (DMEM convention) */
 } hypre_ParAMGData;
 #define hypre_ParAMGDataAArray(d) ((d)->A_array)
 #define hypre_ParAMGDataPArray(d) ((d)->P_array)
@@ -85,4 +91,5 @@ HYPRE_Int HYPRE_IJMatrixInitialize(HYPRE_IJMatrix matrix);
 HYPRE_Int HYPRE_IJMatrixSetValues(HYPRE_IJMatrix matrix, HYPRE_Int nrows, HYPRE_Int *ncols, const HYPRE_BigInt *rows, const HYPRE_BigInt *cols, const HYPRE_Complex *values);
 HYPRE_Int HYPRE_IJMatrixAssemble(HYPRE_IJMatrix matrix);
 HYPRE_Int HYPRE_IJMatrixGetObject(HYPRE_IJMatrix matrix, void **object);
+#include "dmem_stub.h"
 #endif

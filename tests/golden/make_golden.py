@@ -220,7 +220,57 @@ def cheby_golden():
     np.savez_compressed(os.path.join(OUT, "cheby_bpx.npz"), **d)
 
 
+def _dmem_accel_with_reference_update(h, pb, b, mu, delta, ref_accel_code, num_cycles=100, tol=1e-9):
+    """DMEM_SyncAddCorrect's loop (src/DMEM_Add.cpp:706-711) with the reference's DMEM_ChebyUpdate object code applied to the
+    cycle output"""
+    S = h.A[0].to_scipy().copy()
+    x, d, r = np.zeros_like(b), np.zeros_like(b), b.copy()
+    c, cp, hist = mu, 1.0, [1.0]
+    for k in range(num_cycles):
+        e = pb.cycle(r)
+        d, _, c, cp = O.ref_dmem_cheby_update(d, e, k, mu, delta, c, cp, accel_type=ref_accel_code)
+        x = x + d
+        r = b - S @ x
+        hist.append(np.linalg.norm(r) / np.linalg.norm(b))
+        if hist[-1] < tol:
+            break
+    return np.asarray(hist)
+
+
+def dmem_golden():
+    """DMEM_SyncAdd / DMEM_SyncAddCycle (src/DMEM_Mult.cpp:263-450) and DMEM_ChebyUpdate (src/DMEM_Misc.cpp:612-666) through
+    the reference's object code on one rank (MPI of one process, oracle/ref_shim/dmem_stub.h)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import hierarchy_from_golden
+    d = {}
+    for name in ("lap5pt_n32", "lap7pt_n12"):
+        h, g = hierarchy_from_golden(name)
+        b, w = g["b"], 0.9
+        for tag, sym, post in (("sym", True, 1), ("plain", False, 0)):
+            h.build_transfers(H.MULTADD, w, num_pre=1, num_post=post)
+            x, hist = O.ref_dmem_sync_add(h, b, w, symmetrised=sym, num_cycles=100, tol=1e-9)
+            d["%s_%s_hist" % (name, tag)] = hist
+            d["%s_%s_x" % (name, tag)] = x
+            print(name, tag, len(hist) - 1, hist[-1])
+        h.build_transfers(H.MULTADD, w)
+        pb = O.Problem(h, H.MULTADD, H.JACOBI, w, coarse_solve=1)
+        lo, hi = pb.eigs_power(20)
+        mu, delta = (hi + lo) / (hi - lo), 2.0 / (hi + lo)
+        d[name + "_mu_delta"] = np.asarray([mu, delta])
+        # in the reference's (stale) src/Main.hpp:79-81 CHEBY_ACCEL == RICHARD_ACCEL == 1, so accel_type 1 takes the Richardson
+        # branch of DMEM_ChebyUpdate; any other non-zero value reaches the Chebyshev recurrence
+        d[name + "_richardson_hist"] = _dmem_accel_with_reference_update(h, pb, b, mu, delta, 1)
+        d[name + "_chebyshev_hist"] = _dmem_accel_with_reference_update(h, pb, b, mu, delta, 2)
+        print(name, "accel", len(d[name + "_richardson_hist"]) - 1, len(d[name + "_chebyshev_hist"]) - 1)
+    np.savez_compressed(os.path.join(OUT, "dmem.npz"), **d)
+
+
 if __name__ == "__main__":
+    if "--dmem-only" in sys.argv:
+        from oracle import build as obuild
+        amg.build.build_host(); obuild.build_oracle(); obuild.build_ref()
+        dmem_golden()
+        sys.exit(0)
     if "--cheby-only" in sys.argv:
         from oracle import build as obuild
         amg.build.build_host(); obuild.build_oracle(); obuild.build_ref()
@@ -246,3 +296,4 @@ if __name__ == "__main__":
         iebpx_golden()
         hybrid_jgs_golden()
         cheby_golden()
+        dmem_golden()

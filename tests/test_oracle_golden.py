@@ -300,3 +300,42 @@ def test_chebyshev_accelerated_bpx_matches_reference_fixture(name):
     _, hist, _ = O.Problem(h, H.BPX, H.JACOBI, 0.8).solve_sync(d["b"], 1e-9, 200, cheby=(mu, delta))
     _close_hist(hist, g[name + "_hist"])
     assert hist[-1] < 1e-9
+
+
+# ---- DMEM: synchronous Multadd on all ranks and the acceleration of the accumulated correction -----------------------------
+@pytest.mark.parametrize("name", ["lap5pt_n32", "lap7pt_n12"])
+def test_dmem_sync_add_matches_reference_fixture(name):
+    """DMEM_SyncAdd / DMEM_SyncAddCycle (src/DMEM_Mult.cpp:263-450; direct solve on the coarsest level, symmetrised and plain
+    smoother) and DMEM_ChebyUpdate (src/DMEM_Misc.cpp:612-666; Richardson and Chebyshev branches) from the reference's object
+    code compiled for one rank (tests/golden/dmem.npz) against the oracle's restatement"""
+    import os
+    from conftest import GOLDEN, hierarchy_from_golden
+    g = dict(np.load(os.path.join(GOLDEN, "dmem.npz")))
+    h, d = hierarchy_from_golden(name)
+    b, w = d["b"], 0.9
+    for tag, post in (("sym", 1), ("plain", 0)):
+        h.build_transfers(H.MULTADD, w, num_pre=1, num_post=post)
+        u, hist = O.Problem(h, H.MULTADD, H.JACOBI, w, num_pre=1, num_post=post, coarse_solve=1).solve_sync_dmem(b, 1e-9, 100)
+        _close_hist(hist, g["%s_%s_hist" % (name, tag)])
+        assert np.max(np.abs(u - g["%s_%s_x" % (name, tag)])) <= 1e-12 * np.max(np.abs(u))
+    h.build_transfers(H.MULTADD, w)
+    pb = O.Problem(h, H.MULTADD, H.JACOBI, w, coarse_solve=1)
+    mu, delta = g[name + "_mu_delta"]
+    _, hist = pb.solve_sync_dmem(b, 1e-9, 100, 2, mu, delta)             # ours: 2 = second-order Richardson
+    _close_hist(hist, g[name + "_richardson_hist"])
+    _, hist = pb.solve_sync_dmem(b, 1e-9, 100, 1, mu, delta)             # ours: 1 = Chebyshev recurrence
+    _close_hist(hist, g[name + "_chebyshev_hist"])
+
+
+def test_dmem_sync_add_matches_live_reference():
+    if O.ref_lib() is None:
+        pytest.skip("oracle/_ref not built here")
+    A = H.laplacian("7pt", 11)
+    h = H.amg_setup(A)
+    b = H.rand_rhs(A.nrows)
+    for sym, post in ((True, 1), (False, 0)):
+        h.build_transfers(H.MULTADD, 0.8, num_pre=1, num_post=post)
+        u, hist = O.Problem(h, H.MULTADD, H.JACOBI, 0.8, num_pre=1, num_post=post, coarse_solve=1).solve_sync_dmem(b, 1e-9, 100)
+        x, rh = O.ref_dmem_sync_add(h, b, 0.8, symmetrised=sym, num_cycles=100, tol=1e-9)
+        _close_hist(hist, rh)
+        assert np.max(np.abs(u - x)) <= 1e-12 * np.max(np.abs(x))
