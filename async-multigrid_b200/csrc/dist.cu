@@ -213,7 +213,7 @@ static int dist_cycle(amgb_ctx *c, double *tgt, bool accumulate)
       return AMGB_OK;
    }
    const bool bpx = c->opt.solver == AMGB_SOLVER_BPX;                   // SYNC_BPX of DMEM_SyncAddCycle (src/DMEM_Mult.cpp:346-349)
-   const bool afacx = c->opt.solver == AMGB_SOLVER_AFACX;               // SYNC_AFACX (DMEM_SyncAFACCycle, src/DMEM_Mult.cpp:452-612)
+   const bool afacx = c->opt.solver == AMGB_SOLVER_AFACX;               // AFACx with the SMEM / SEQ meaning (src/SEQ_AMG.cpp:172-208), row-partitioned
    const bool direct = c->opt.coarse_solve && c->Ainv.rp != nullptr;   // DMEM: direct solve on the (replicated) coarsest level
    const int top = (direct || bpx) ? L : L - 1;                         // levels that contribute a correction
    const int last_r = afacx ? L - 1 : top - 1;                          // AFACx level L-2 smooths r_{L-1} on its coarse side

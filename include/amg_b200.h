@@ -182,7 +182,7 @@ int amgb_l2_arena_bytes(amgb_ctx *ctx, long long *used, long long *capacity);
 
 /* ---- multi-GPU (DMEM replacement; one process per GPU) ------------------------------------
  * Replaces DMEM_Add / DMEM_SyncAdd (src/DMEM_Add.cpp:20-178, src/DMEM_Mult.cpp:263-450) for the synchronous
- * Multadd, AFACx (DMEM_SyncAFACCycle, src/DMEM_Mult.cpp:452-612) and BPX cycles with weighted or L1 Jacobi, one sweep per level: hypre's ParCSR halo exchange and DMEM_Comm (src/DMEM_Comm.cpp:81-382) become NCCL
+ * Multadd and BPX cycles, and AFACx with the SMEM meaning (src/SEQ_AMG.cpp:172-208), with weighted or L1 Jacobi, one sweep per level: hypre's ParCSR halo exchange and DMEM_Comm (src/DMEM_Comm.cpp:81-382) become NCCL
  * send/recv between row-neighbours, the residual norm an ncclAllReduce (src/DMEM_Misc.cpp:398-433).
  * Call order: amgb_create, amgb_dist_init, amgb_set_options, amgb_set_num_levels, amgb_dist_set_level for
  * EVERY level, then the amgb_set_matrix calls (LOCAL row blocks whose column

@@ -91,7 +91,7 @@ def test_single_rank_bpx_matches_oracle():
 @pytest.mark.parametrize("solver,smoother,w,post", [(H.AFACX, H.JACOBI, 0.6, 1), (H.AFACX, H.L1_JACOBI, 0.9, 1),
                                                      (H.MULTADD, H.L1_JACOBI, 0.9, 1), (H.MULTADD, H.L1_JACOBI, 0.9, 0)])
 def test_single_rank_afacx_and_l1_match_oracle(solver, smoother, w, post):
-    """SYNC_AFACX (DMEM_SyncAFACCycle, src/DMEM_Mult.cpp:452-612; meaning src/SEQ_AMG.cpp:172-208) and the L1-Jacobi
+    """AFACx with the SMEM / SEQ meaning (src/SEQ_AMG.cpp:172-208) in the row-partitioned path, and the L1-Jacobi
     smoother in the partitioned path"""
     A = H.laplacian("7pt", 18)
     h = H.amg_setup(A)

@@ -68,7 +68,7 @@ def _worker(rank, world, port, prob, n, min_rows, q, solver=2, smoother=0, w=0.9
         dist.destroy_process_group()
 
 
-# (solver, smoother, weight, post sweeps): Multadd symmetrised / plain / L1, AFACx (DMEM_SyncAFACCycle), BPX
+# (solver, smoother, weight, post sweeps): Multadd symmetrised / plain / L1, AFACx (src/SEQ_AMG.cpp:172-208), BPX
 VARIANTS = {"multadd": (2, 0, 0.9, 1), "multadd_plain": (2, 0, 0.9, 0), "multadd_l1": (2, 6, 0.9, 1),
             "afacx": (1, 0, 0.6, 1), "afacx_l1": (1, 6, 0.9, 1), "bpx": (3, 0, 0.6, 1)}
 
