@@ -494,8 +494,10 @@ int orc_solve_sync(const orc_problem *pb, const double *f, double *u, double tol
 
 /* Sequential model of the asynchronous additive solve with no staleness: every level applies
  * its chain to the residual of the CURRENT shared u, one level after the other (the
- * num_threads-independent limit of src/SMEM_Async_AMG.cpp:79-352 when groups never overlap).
- * Used only to sanity-check the async GPU path's convergence; counts[l] = corrections. */
+ * num_threads-independent limit of src/SMEM_Async_AMG.cpp:79-352 when groups never overlap; with coarse_solve it is
+ * DMEM_Add's asynchronous loop, src/DMEM_Add.cpp:101-130, grid after grid -- AddCycle :180-329 + DMEM_AddSmooth
+ * src/DMEM_Smooth.cpp:574-638 -- which the reference's object code pins, tests/test_oracle_golden.py).
+ * counts[l] = corrections. */
 int orc_solve_async_sequential(const orc_problem *pb, const double *f, double *u, int num_cycles,
                                int *counts, double *final_relres)
 {
@@ -509,6 +511,9 @@ int orc_solve_async_sequential(const orc_problem *pb, const double *f, double *u
          if (q < L - 1) {
             memset(w->e[q], 0, sizeof(double) * (size_t)pb->A[q].nrows);
             orc_smooth(pb, q, w->r[q], w->e[q], w->y[q], w->s[q], pb->fine_sweeps);
+         } else if (pb->coarse_solve && L > 1) {
+            /* DMEM: the last grid solves directly (AddCycle, src/DMEM_Add.cpp:262-264) */
+            orc_dense_solve(&pb->A[q], w->r[q], w->e[q]);
          } else memset(w->e[q], 0, sizeof(double) * (size_t)pb->A[q].nrows);
          for (int inner = q; inner > 0; inner--)
             orc_matvec(&pb->P[inner - 1], w->e[inner], w->e[inner - 1], 0, pb->P[inner - 1].nrows);

@@ -279,6 +279,26 @@ def ref_dmem_sync_add(h, b, smooth_weight, symmetrised=True, num_cycles=100, tol
     return x, hist[:k + 1]
 
 
+def ref_dmem_add_cycles(h, b, smooth_weight, symmetrised=True, rounds=10):
+    """AddCycle + DMEM_AddSmooth (src/DMEM_Add.cpp:180-329, src/DMEM_Smooth.cpp:574-638), the reference's object code, grid
+    after grid on one rank -> (x, hist per round)"""
+    L = ref_lib()
+    nl = h.num_levels
+    Rt = [_pkg.hierarchy.CSR.from_scipy(r.to_scipy().T.tocsr()) for r in h.R]
+    keep = (list(h.A), list(h.P), Rt)
+    A = (OrcCSR * nl)(*[c_csr(a) for a in h.A])
+    P = (OrcCSR * max(nl - 1, 1))(*[c_csr(p) for p in h.P])
+    R = (OrcCSR * max(nl - 1, 1))(*[c_csr(r) for r in Rt])
+    x, hist = np.zeros(h.n[0]), np.zeros(rounds + 1)
+    L.ref_dmem_add_cycles.restype = C.c_int
+    L.ref_dmem_add_cycles.argtypes = [C.c_int, C.POINTER(OrcCSR), C.POINTER(OrcCSR), C.POINTER(OrcCSR), C.c_double, C.c_int, DP,
+                                      C.c_int, DP, DP]
+    L.ref_dmem_add_cycles(nl, A, P, R, smooth_weight, int(symmetrised), dptr(np.ascontiguousarray(b, dtype=np.float64)), rounds,
+                          dptr(x), dptr(hist))
+    del keep
+    return x, hist
+
+
 def ref_dmem_cheby_update(d, u, cycle, mu, delta, c, c_prev, accel_type=1):
     """DMEM_ChebyUpdate (src/DMEM_Misc.cpp:612-666), synchronous branch, in place on copies -> (d, u, c, c_prev)"""
     L = ref_lib()

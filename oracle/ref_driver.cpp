@@ -22,6 +22,10 @@
 #include "DMEM_Main.hpp"
 #include "DMEM_Mult.hpp"
 #include "DMEM_Misc.hpp"
+#include "DMEM_Comm.hpp"
+#include "DMEM_Add.hpp"
+#include "DMEM_Smooth.hpp"
+void AddCycle(DMEM_AllData *dmem_all_data);     // defined (non-static) in src/DMEM_Add.cpp:180, declared only inside that file
 #include <cstdarg>
 
 static AllData *g_all = nullptr;
@@ -128,6 +132,22 @@ HYPRE_Int hypre_ParVectorAxpy(HYPRE_Complex alpha, hypre_ParVector *x, hypre_Par
    for (int i = 0; i < y->local_vector->size; i++) y->local_vector->data[i] += alpha * x->local_vector->data[i];
    return 0;
 }
+HYPRE_Int hypre_CSRMatrixMatvec(HYPRE_Complex alpha, hypre_CSRMatrix *A, hypre_Vector *x, HYPRE_Complex beta, hypre_Vector *y)
+{
+   for (int i = 0; i < A->num_rows; i++) {
+      double t = 0.0;
+      for (int jj = A->i[i]; jj < A->i[i + 1]; jj++) t += A->data[jj] * x->data[A->j[jj]];
+      y->data[i] = alpha * t + beta * y->data[i];
+   }
+   return 0;
+}
+// DMEM_Comm's message engine (src/DMEM_Comm.cpp; needs hypre's seq_mv.h and real MPI): one rank has no peer, the driver
+// never reaches it
+int SendRecv(DMEM_AllData *, DMEM_CommData *, HYPRE_Real *, int) { abort(); }
+void CompleteRecv(DMEM_AllData *, DMEM_CommData *, HYPRE_Real *, int) { abort(); }
+void CompleteInFlight(DMEM_AllData *, DMEM_CommData *) { abort(); }
+void CheckInFlight(DMEM_AllData *, DMEM_CommData *, int) { abort(); }
+void DMEM_ResetAllCommData(DMEM_AllData *) { abort(); }
 hypre_ParVector *hypre_ParVectorCreate(MPI_Comm, HYPRE_BigInt, HYPRE_BigInt *) { abort(); }
 HYPRE_Int hypre_ParVectorInitialize(hypre_ParVector *) { abort(); }
 HYPRE_Int hypre_ParVectorDestroy(hypre_ParVector *) { abort(); }
@@ -698,6 +718,90 @@ void ref_dmem_cheby_update(int n, double *d, double *u, int cycle, double mu, do
    DMEM_ChebyUpdate(dm, &dp, &upv, n);
    *c = dm->cheby.c; *c_prev = dm->cheby.c_prev;
    delete dm;
+}
+
+// AddCycle (src/DMEM_Add.cpp:180-329) + DMEM_AddSmooth (src/DMEM_Smooth.cpp:574-638), the reference's object code, for every
+// grid k in turn on ONE rank: r = b - A x, grid k's chain (restrict k times with R_array applied transposed, smooth with
+// wJacobi_scale = d/omega -- symmetrised when simple_jacobi_flag = -1 -- or the direct solve on the last grid, prolong k
+// times), x += U_array[0].  That is DMEM_Add's asynchronous loop (:101-130) when the grids never overlap.  `rounds` passes
+// over all grids; hist[round] = ||b - A x|| / ||b||.
+int ref_dmem_add_cycles(int L, const RefCSR *A, const RefCSR *P, const RefCSR *Rt, double smooth_weight, int symmetrised,
+                        const double *b, int rounds, double *x_out, double *hist)
+{
+   DMEM_AllData *dm = new DMEM_AllData();
+   std::vector<hypre_CSRMatrix> hA(L), hP(L), hR(L);
+   std::vector<hypre_ParCSRMatrix> pA(L), pP(L), pR(L);
+   std::vector<hypre_ParCSRMatrix *> Aarr(L), Parr(L), Rarr(L);
+   std::vector<std::vector<double>> ud(L), fd(L), sc(L), ssc(L);
+   std::vector<hypre_Vector> uv(L), fv(L);
+   std::vector<hypre_ParVector> up(L), fp(L);
+   std::vector<hypre_ParVector *> Uarr(L), Farr(L);
+   std::vector<double *> scp(L), sscp(L);
+   for (int l = 0; l < L; l++) {
+      fill(&hA[l], A[l]); memset(&pA[l], 0, sizeof(pA[l])); pA[l].diag = &hA[l]; pA[l].global_num_rows = A[l].nrows; Aarr[l] = &pA[l];
+      if (l < L - 1) {
+         fill(&hP[l], P[l]); memset(&pP[l], 0, sizeof(pP[l])); pP[l].diag = &hP[l]; pP[l].global_num_rows = P[l].nrows; Parr[l] = &pP[l];
+         fill(&hR[l], Rt[l]); memset(&pR[l], 0, sizeof(pR[l])); pR[l].diag = &hR[l]; pR[l].global_num_rows = Rt[l].nrows; Rarr[l] = &pR[l];
+      }
+      const int n = A[l].nrows;
+      ud[l].assign(n, 0.0); fd[l].assign(n, 0.0); sc[l].resize(n); ssc[l].resize(n);
+      for (int i = 0; i < n; i++) {            // src/DMEM_Setup.cpp:465-483
+         const double d = A[l].data[A[l].i[i]];
+         sc[l][i] = d == 0.0 ? 1.0 : d / smooth_weight;
+         ssc[l][i] = -sc[l][i];
+      }
+      scp[l] = sc[l].data(); sscp[l] = ssc[l].data();
+      uv[l].data = ud[l].data(); uv[l].size = n; up[l].local_vector = &uv[l]; Uarr[l] = &up[l];
+      fv[l].data = fd[l].data(); fv[l].size = n; fp[l].local_vector = &fv[l]; Farr[l] = &fp[l];
+   }
+   const int n0 = A[0].nrows;
+   std::vector<double> vt(n0, 0.0), x(n0, 0.0);
+   hypre_Vector hv; hv.data = vt.data(); hv.size = n0;
+   hypre_ParVector pvt; pvt.local_vector = &hv;
+   hypre_ParAMGData amg;
+   memset(&amg, 0, sizeof(amg));
+   amg.A_array = Aarr.data(); amg.P_array = Parr.data(); amg.R_array = Rarr.data();
+   amg.F_array = Farr.data(); amg.U_array = Uarr.data(); amg.Vtemp = &pvt; amg.Ztemp = &pvt;
+   amg.num_levels = L; amg.functional_gauss_elim = 1;
+   dm->hypre.solver_gridk = (HYPRE_Solver)&amg;
+   dm->grid.num_levels = L;
+   dm->input.solver = MULTADD;
+   dm->input.smoother = JACOBI;
+   dm->input.coarsest_mult_level = 0;
+   dm->input.num_interpolants = ONE_INTERPOLANT + 1;          // anything but ONE_INTERPOLANT: level-by-level transfers
+   dm->input.async_flag = 0;
+   dm->input.simple_jacobi_flag = symmetrised ? -1 : 0;
+   dm->matrix.wJacobi_scale_gridk = scp.data();
+   dm->matrix.symmwJacobi_scale_gridk = sscp.data();
+   dm->output.level_wtime.assign(L + 1, 0.0);
+   double r0 = 0.0;
+   for (int i = 0; i < n0; i++) r0 += b[i] * b[i];
+   r0 = sqrt(r0);
+   if (hist) hist[0] = 1.0;
+   hypre_CSRMatrix *A0 = &hA[0];
+   auto residual = [&](double *r) {
+      double s = 0.0;
+      for (int i = 0; i < n0; i++) {
+         double t = 0.0;
+         for (int jj = A0->i[i]; jj < A0->i[i + 1]; jj++) t += A0->data[jj] * x[A0->j[jj]];
+         r[i] = b[i] - t;
+         s += r[i] * r[i];
+      }
+      return sqrt(s);
+   };
+   double rn = residual(fd[0].data());
+   for (int k = 1; k <= rounds; k++) {
+      for (int grid = 0; grid < L; grid++) {
+         dm->grid.my_grid = grid;
+         AddCycle(dm);
+         for (int i = 0; i < n0; i++) x[i] += ud[0][i];
+         rn = residual(fd[0].data());
+      }
+      if (hist) hist[k] = rn / r0;
+   }
+   if (x_out) memcpy(x_out, x.data(), sizeof(double) * n0);
+   delete dm;
+   return rounds;
 }
 
 void ref_destroy(void *h) { delete (RefHandle *)h; }

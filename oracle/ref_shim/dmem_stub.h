@@ -25,6 +25,10 @@ static inline int MPI_Comm_size(MPI_Comm, int *s) { *s = 1; return 0; }
 static inline int hypre_MPI_Comm_rank(MPI_Comm, int *r) { *r = 0; return 0; }
 static inline double MPI_Wtime(void) { return omp_get_wtime(); }
 static inline int MPI_Barrier(MPI_Comm) { return 0; }
+#define MPI_STATUSES_IGNORE ((MPI_Status *)0)
+/* never reached on one rank (no neighbour, no other grid): */
+static inline int hypre_MPI_Waitall(int, MPI_Request *, MPI_Status *) { return 0; }
+static inline int hypre_MPI_Irecv(void *, int, MPI_Datatype, int, int, MPI_Comm, MPI_Request *) { return 0; }
 static inline size_t amg_ref_mpi_size(MPI_Datatype t) { return t == MPI_INT ? sizeof(int) : sizeof(double); }
 static inline int MPI_Reduce(const void *s, void *r, int n, MPI_Datatype t, MPI_Op, int, MPI_Comm) { memcpy(r, s, n * amg_ref_mpi_size(t)); return 0; }
 static inline int hypre_MPI_Allreduce(void *s, void *r, int n, MPI_Datatype t, MPI_Op, MPI_Comm) { memcpy(r, s, n * amg_ref_mpi_size(t)); return 0; }
@@ -47,6 +51,7 @@ static inline int hypre_MPI_Allreduce(void *s, void *r, int n, MPI_Datatype t, M
 #define hypre_ParCSRMatrixNumNonzeros(m) ((m)->diag->num_nonzeros)
 #define hypre_ParCSRMatrixSetNumNonzeros(m) (0)
 
+HYPRE_Int hypre_CSRMatrixMatvec(HYPRE_Complex alpha, hypre_CSRMatrix *A, hypre_Vector *x, HYPRE_Complex beta, hypre_Vector *y);
 HYPRE_Int hypre_ParCSRMatrixMatvecT(HYPRE_Complex alpha, hypre_ParCSRMatrix *A, hypre_ParVector *x, HYPRE_Complex beta, hypre_ParVector *y);
 HYPRE_Int hypre_BoomerAMGRelax(hypre_ParCSRMatrix *A, hypre_ParVector *f, HYPRE_Int *cf_marker, HYPRE_Int relax_type, HYPRE_Int relax_points,
                                HYPRE_Real relax_weight, HYPRE_Real omega, HYPRE_Real *l1_norms, hypre_ParVector *u, hypre_ParVector *Vtemp,

@@ -262,6 +262,10 @@ def dmem_golden():
         d[name + "_richardson_hist"] = _dmem_accel_with_reference_update(h, pb, b, mu, delta, 1)
         d[name + "_chebyshev_hist"] = _dmem_accel_with_reference_update(h, pb, b, mu, delta, 2)
         print(name, "accel", len(d[name + "_richardson_hist"]) - 1, len(d[name + "_chebyshev_hist"]) - 1)
+        # AddCycle + DMEM_AddSmooth, grid after grid on one rank (DMEM_Add's asynchronous loop without overlap)
+        x, hist = O.ref_dmem_add_cycles(h, b, w, symmetrised=True, rounds=12)
+        d[name + "_addcycle_hist"] = hist
+        d[name + "_addcycle_x"] = x
     np.savez_compressed(os.path.join(OUT, "dmem.npz"), **d)
 
 

@@ -327,6 +327,20 @@ def test_dmem_sync_add_matches_reference_fixture(name):
     _close_hist(hist, g[name + "_chebyshev_hist"])
 
 
+@pytest.mark.parametrize("name", ["lap5pt_n32", "lap7pt_n12"])
+def test_dmem_addcycle_matches_reference_fixture(name):
+    """AddCycle (src/DMEM_Add.cpp:180-329) + DMEM_AddSmooth (src/DMEM_Smooth.cpp:574-638) from the reference's object code, every
+    grid in turn on one rank = the oracle's sequential model of the asynchronous solve with the DMEM coarse solve"""
+    import os
+    from conftest import GOLDEN, hierarchy_from_golden
+    g = dict(np.load(os.path.join(GOLDEN, "dmem.npz")))
+    h, d = hierarchy_from_golden(name)
+    h.build_transfers(H.MULTADD, 0.9)
+    u, counts, rel = O.Problem(h, H.MULTADD, H.JACOBI, 0.9, coarse_solve=1).solve_async_sequential(d["b"], 12)
+    assert abs(rel - g[name + "_addcycle_hist"][-1]) <= HIST_TOL and list(counts) == [12] * h.num_levels
+    assert np.max(np.abs(u - g[name + "_addcycle_x"])) <= 1e-12 * np.max(np.abs(u))
+
+
 def test_dmem_sync_add_matches_live_reference():
     if O.ref_lib() is None:
         pytest.skip("oracle/_ref not built here")
