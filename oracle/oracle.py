@@ -299,6 +299,20 @@ def ref_dmem_add_cycles(h, b, smooth_weight, symmetrised=True, rounds=10):
     return x, hist
 
 
+def ref_dmem_async_smooth(A, b, smooth_weight, num_cycles, l1=None):
+    """DMEM_AsyncSmooth (src/DMEM_Smooth.cpp:16-313), the reference's object code, on one rank (no neighbour): ASYNC_JACOBI, or
+    ASYNC_L1_JACOBI when l1 is given -> (x, r as the reference maintains it incrementally, relaxations done)"""
+    L = ref_lib()
+    a = c_csr(A)
+    x, r = np.zeros(A.nrows), np.zeros(A.nrows)
+    l1a = np.ascontiguousarray(l1 if l1 is not None else np.ones(A.nrows), dtype=np.float64)
+    L.ref_dmem_async_smooth.restype = C.c_int
+    L.ref_dmem_async_smooth.argtypes = [C.POINTER(OrcCSR), DP, C.c_double, DP, C.c_int, C.c_int, DP, DP]
+    k = L.ref_dmem_async_smooth(C.byref(a), dptr(np.ascontiguousarray(b, dtype=np.float64)), smooth_weight, dptr(l1a),
+                                10 if l1 is not None else 8, num_cycles, dptr(x), dptr(r))
+    return x, r, k
+
+
 def ref_dmem_cheby_update(d, u, cycle, mu, delta, c, c_prev, accel_type=1):
     """DMEM_ChebyUpdate (src/DMEM_Misc.cpp:612-666), synchronous branch, in place on copies -> (d, u, c, c_prev)"""
     L = ref_lib()

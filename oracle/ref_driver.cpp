@@ -143,7 +143,9 @@ HYPRE_Int hypre_CSRMatrixMatvec(HYPRE_Complex alpha, hypre_CSRMatrix *A, hypre_V
 }
 // DMEM_Comm's message engine (src/DMEM_Comm.cpp; needs hypre's seq_mv.h and real MPI): one rank has no peer, the driver
 // never reaches it
-int SendRecv(DMEM_AllData *, DMEM_CommData *, HYPRE_Real *, int) { abort(); }
+// SendRecv with NO peer in the list (one rank): the loop over comm_data->procs never runs and the function returns its initial
+// return_flag = 0 (src/DMEM_Comm.cpp:92,95,347); with a peer it would need the real engine
+int SendRecv(DMEM_AllData *, DMEM_CommData *comm_data, HYPRE_Real *, int) { if (!comm_data->procs.empty()) abort(); return 0; }
 void CompleteRecv(DMEM_AllData *, DMEM_CommData *, HYPRE_Real *, int) { abort(); }
 void CompleteInFlight(DMEM_AllData *, DMEM_CommData *) { abort(); }
 void CheckInFlight(DMEM_AllData *, DMEM_CommData *, int) { abort(); }
@@ -802,6 +804,56 @@ int ref_dmem_add_cycles(int L, const RefCSR *A, const RefCSR *P, const RefCSR *R
    if (x_out) memcpy(x_out, x.data(), sizeof(double) * n0);
    delete dm;
    return rounds;
+}
+
+// DMEM_AsyncSmooth (src/DMEM_Smooth.cpp:16-313), the reference's object code, on ONE rank: the asynchronous fine-grid smoother
+// with no neighbour and no other grid to hear from -- u = r ./ s, x += u, r -= A_diag u, `num_cycles` relaxations (LOCAL rule,
+// AsyncSmoothCheckConverge :340-349).  smoother: ASYNC_JACOBI (8) with s = d / omega, ASYNC_L1_JACOBI (10) with s = l1.
+int ref_dmem_async_smooth(const RefCSR *A, const double *b, double smooth_weight, const double *l1, int smoother, int num_cycles,
+                          double *x_out, double *r_out)
+{
+   DMEM_AllData *dm = new DMEM_AllData();
+   const int n = A->nrows;
+   hypre_CSRMatrix hA, hOffd;
+   fill(&hA, *A);
+   std::vector<int> offd_i((size_t)n + 1, 0);
+   memset(&hOffd, 0, sizeof(hOffd));
+   hOffd.i = offd_i.data(); hOffd.num_rows = n; hOffd.num_cols = 0; hOffd.num_nonzeros = 0;
+   hypre_ParCSRMatrix pA;
+   memset(&pA, 0, sizeof(pA));
+   pA.diag = &hA; pA.offd = &hOffd; pA.global_num_rows = n;
+   hypre_ParCSRMatrix *Aarr[1] = {&pA};
+   std::vector<double> u(n, 0.0), f(n, 0.0), vt(n, 0.0), x(n, 0.0), r(b, b + n), bb(b, b + n), e(n, 0.0), d(n, 0.0), scale(n), ghost(1, 0.0);
+   for (int i = 0; i < n; i++) scale[i] = (smoother == ASYNC_L1_JACOBI) ? l1[i] : A->data[A->i[i]] / smooth_weight;
+   double *ptrs[8] = {u.data(), f.data(), vt.data(), x.data(), r.data(), bb.data(), e.data(), d.data()};
+   hypre_Vector hv[8];
+   hypre_ParVector pv[8];
+   for (int k = 0; k < 8; k++) { hv[k].data = ptrs[k]; hv[k].size = n; pv[k].local_vector = &hv[k]; }
+   hypre_Vector gv[2];
+   for (int k = 0; k < 2; k++) { gv[k].data = ghost.data(); gv[k].size = 0; }
+   hypre_ParVector *Uarr[1] = {&pv[0]}, *Farr[1] = {&pv[1]};
+   hypre_ParAMGData amg;
+   memset(&amg, 0, sizeof(amg));
+   amg.A_array = Aarr; amg.U_array = Uarr; amg.F_array = Farr; amg.Vtemp = &pv[2]; amg.Ztemp = &pv[2]; amg.num_levels = 1;
+   dm->hypre.solver_gridk = (HYPRE_Solver)&amg;
+   dm->vector_gridk.x = &pv[3]; dm->vector_gridk.r = &pv[4]; dm->vector_gridk.b = &pv[5]; dm->vector_gridk.e = &pv[6];
+   dm->vector_gridk.d = &pv[7]; dm->vector_gridk.x_ghost = &gv[0]; dm->vector_gridk.x_ghost_prev = &gv[1];
+   double *sp[1] = {scale.data()};
+   dm->matrix.wJacobi_scale_gridk = sp;
+   dm->matrix.L1_row_norm_gridk = sp;
+   dm->input.smoother = smoother;
+   dm->input.smooth_weight = smooth_weight;
+   dm->input.converge_test_type = LOCAL_CONVERGE;
+   dm->input.num_cycles = num_cycles;
+   dm->input.accel_type = NO_ACCEL;
+   dm->input.async_flag = 1;
+   dm->iter.cycle = 0; dm->iter.relax = 0;
+   DMEM_AsyncSmooth(dm, 0);
+   const int relax = dm->iter.relax;
+   if (x_out) memcpy(x_out, x.data(), sizeof(double) * n);
+   if (r_out) memcpy(r_out, r.data(), sizeof(double) * n);
+   delete dm;
+   return relax;
 }
 
 void ref_destroy(void *h) { delete (RefHandle *)h; }

@@ -266,6 +266,10 @@ def dmem_golden():
         x, hist = O.ref_dmem_add_cycles(h, b, w, symmetrised=True, rounds=12)
         d[name + "_addcycle_hist"] = hist
         d[name + "_addcycle_x"] = x
+        # DMEM_AsyncSmooth on one rank: 17 relaxations of the fine system, weighted and L1 Jacobi
+        l1 = h.l1_norms()[0]
+        d[name + "_asyncsmooth_j_x"] = O.ref_dmem_async_smooth(h.A[0], b, w, 17)[0]
+        d[name + "_asyncsmooth_l1_x"] = O.ref_dmem_async_smooth(h.A[0], b, w, 17, l1=l1)[0]
     np.savez_compressed(os.path.join(OUT, "dmem.npz"), **d)
 
 

@@ -341,6 +341,20 @@ def test_dmem_addcycle_matches_reference_fixture(name):
     assert np.max(np.abs(u - g[name + "_addcycle_x"])) <= 1e-12 * np.max(np.abs(u))
 
 
+@pytest.mark.parametrize("name", ["lap5pt_n32", "lap7pt_n12"])
+def test_dmem_async_smooth_matches_reference_fixture(name):
+    """DMEM_AsyncSmooth (src/DMEM_Smooth.cpp:16-313) from the reference's object code on one rank: u = r ./ s, x += u,
+    r -= A_diag u, `num_cycles` relaxations -- exactly that many (L1-)Jacobi sweeps of the oracle"""
+    import os
+    from conftest import GOLDEN, hierarchy_from_golden
+    g = dict(np.load(os.path.join(GOLDEN, "dmem.npz")))
+    h, d = hierarchy_from_golden(name)
+    want = O.smooth("jacobi", h.A[0], d["b"], 0.9, sweeps=17, zero_flag=1)
+    assert np.max(np.abs(want - g[name + "_asyncsmooth_j_x"])) <= 1e-13 * np.max(np.abs(want))
+    want = O.smooth("l1_jacobi", h.A[0], d["b"], 0.9, sweeps=17, zero_flag=1, l1=h.l1_norms()[0])
+    assert np.max(np.abs(want - g[name + "_asyncsmooth_l1_x"])) <= 1e-13 * np.max(np.abs(want))
+
+
 def test_dmem_sync_add_matches_live_reference():
     if O.ref_lib() is None:
         pytest.skip("oracle/_ref not built here")
