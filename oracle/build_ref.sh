@@ -10,7 +10,7 @@ REF=/root/reference/src
 OUT="$HERE/_ref"
 mkdir -p "$OUT"
 CXX="g++ -O3 -fopenmp -fPIC -w -I$HERE/ref_shim -I$REF -include $HERE/ref_shim/ref_prelude.hpp"
-for f in SMEM_MatVec SMEM_Smooth SMEM_Sync_AMG SMEM_Async_AMG SMEM_ExtendedSystem SEQ_MatVec SEQ_Smooth SEQ_AMG Misc DMEM_Mult DMEM_Misc DMEM_Add DMEM_Smooth; do
+for f in SMEM_MatVec SMEM_Smooth SMEM_Sync_AMG SMEM_Async_AMG SMEM_ExtendedSystem SMEM_Cheby SEQ_MatVec SEQ_Smooth SEQ_AMG Misc DMEM_Mult DMEM_Misc DMEM_Add DMEM_Smooth; do
    $CXX -c "$REF/$f.cpp" -o "$OUT/$f.o"
 done
 # SMEM_Solve.cpp: its printf (residual history, src/SMEM_Solve.cpp:95-103,232-239) goes to the hook

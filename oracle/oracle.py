@@ -313,6 +313,27 @@ def ref_dmem_async_smooth(A, b, smooth_weight, num_cycles, l1=None):
     return x, r, k
 
 
+def ref_cheby_setup(h, b, smoother, smooth_weight, iters=20, num_sweeps=1, num_threads=1):
+    """ChebySetup -> EigsPower -> BPXCycle (src/SMEM_Cheby.cpp:28-60,410-518,520-645), the reference's object code, on the plain
+    interpolants h.P (hypre's R_array is P_array, applied transposed) -> dict(alpha, beta, mu, delta, f_after)"""
+    L = ref_lib()
+    nl = h.num_levels
+    l1arrs = h.l1_norms()
+    keep = (list(h.A), list(h.P), l1arrs)
+    A = (OrcCSR * nl)(*[c_csr(a) for a in h.A])
+    P = (OrcCSR * max(nl - 1, 1))(*[c_csr(p) for p in h.P])
+    l1 = (DP * nl)(*[dptr(a) for a in l1arrs])
+    out, fa = np.zeros(4), np.zeros(h.n[0])
+    L.ref_cheby_setup.restype = C.c_int
+    L.ref_cheby_setup.argtypes = [C.c_int, C.POINTER(OrcCSR), C.POINTER(OrcCSR), C.POINTER(DP), C.c_int, C.c_double, C.c_int,
+                                  C.c_int, C.c_int, DP, DP, DP]
+    rc = L.ref_cheby_setup(nl, A, P, l1, smoother, smooth_weight, num_sweeps, iters, num_threads,
+                           dptr(np.ascontiguousarray(b, dtype=np.float64)), dptr(out), dptr(fa))
+    del keep
+    assert rc == 0
+    return dict(alpha=out[0], beta=out[1], mu=out[2], delta=out[3], f_after=fa)
+
+
 def ref_dmem_cheby_update(d, u, cycle, mu, delta, c, c_prev, accel_type=1):
     """DMEM_ChebyUpdate (src/DMEM_Misc.cpp:612-666), synchronous branch, in place on copies -> (d, u, c, c_prev)"""
     L = ref_lib()

@@ -25,6 +25,7 @@
 #include "DMEM_Comm.hpp"
 #include "DMEM_Add.hpp"
 #include "DMEM_Smooth.hpp"
+#include "SMEM_Cheby.hpp"
 void AddCycle(DMEM_AllData *dmem_all_data);     // defined (non-static) in src/DMEM_Add.cpp:180, declared only inside that file
 #include <cstdarg>
 
@@ -854,6 +855,73 @@ int ref_dmem_async_smooth(const RefCSR *A, const double *b, double smooth_weight
    if (r_out) memcpy(r_out, r.data(), sizeof(double) * n);
    delete dm;
    return relax;
+}
+
+// ChebySetup -> EigsPower -> BPXCycle (src/SMEM_Cheby.cpp:28-60,410-518,520-645), the reference's object code: power iteration on
+// B A with B = its hypre-vector BPX cycle (restriction by hypre_ParCSRMatrixMatvecT with R_array = P_array, as hypre keeps
+// it; (L1-)Jacobi / hybrid sweeps from zero with diag_scale = a_ii / omega or the L1 norms on EVERY level; prolongation with
+// beta = 1).  out[4] = alpha (eig_min), beta (eig_max), mu, delta; f_after (may be null) receives F_array[0] as EigsPower
+// leaves it (it restores the right-hand side it saved in vector.y[0], :512-516).
+int ref_cheby_setup(int L, const RefCSR *A, const RefCSR *P, double *const *l1, int smoother, double smooth_weight, int num_sweeps,
+                    int iters, int num_threads, const double *f0, double *out, double *f_after)
+{
+   AllData *ad = new AllData();
+   memset((void *)&ad->input, 0, sizeof(ad->input));
+   memset((void *)&ad->matrix, 0, sizeof(ad->matrix));
+   memset((void *)&ad->cheby, 0, sizeof(ad->cheby));
+   std::vector<hypre_CSRMatrix> hA(L), hP(L);
+   std::vector<hypre_ParCSRMatrix> pA(L), pP(L);
+   std::vector<hypre_ParCSRMatrix *> Aarr(L), Parr(L);
+   std::vector<std::vector<double>> ud(L), fd(L), dow(L);
+   std::vector<hypre_Vector> uv(L), fv(L);
+   std::vector<hypre_ParVector> up(L), fp(L);
+   std::vector<hypre_ParVector *> Uarr(L), Farr(L);
+   std::vector<double *> dowp(L);
+   for (int l = 0; l < L; l++) {
+      fill(&hA[l], A[l]); memset(&pA[l], 0, sizeof(pA[l])); pA[l].diag = &hA[l]; pA[l].global_num_rows = A[l].nrows; Aarr[l] = &pA[l];
+      if (l < L - 1) { fill(&hP[l], P[l]); memset(&pP[l], 0, sizeof(pP[l])); pP[l].diag = &hP[l]; pP[l].global_num_rows = P[l].nrows; Parr[l] = &pP[l]; }
+      const int n = A[l].nrows;
+      ud[l].assign(n, 0.0); fd[l].assign(n, 0.0); dow[l].resize(n);
+      for (int i = 0; i < n; i++) dow[l][i] = A[l].data[A[l].i[i]] / smooth_weight;      // src/SMEM_Setup.cpp:233-238
+      dowp[l] = dow[l].data();
+      uv[l].data = ud[l].data(); uv[l].size = n; up[l].local_vector = &uv[l]; Uarr[l] = &up[l];
+      fv[l].data = fd[l].data(); fv[l].size = n; fp[l].local_vector = &fv[l]; Farr[l] = &fp[l];
+   }
+   const int n0 = A[0].nrows;
+   memcpy(fd[0].data(), f0, sizeof(double) * n0);
+   std::vector<double> vt(n0, 0.0), e0(n0, 0.0), y0(n0, 0.0);
+   hypre_Vector hv; hv.data = vt.data(); hv.size = n0;
+   hypre_ParVector pvt; pvt.local_vector = &hv;
+   hypre_ParAMGData amg;
+   memset(&amg, 0, sizeof(amg));
+   HYPRE_Int relax_types[4] = {0, 0, 0, 0};
+   amg.A_array = Aarr.data(); amg.P_array = Parr.data(); amg.R_array = Parr.data();
+   amg.F_array = Farr.data(); amg.U_array = Uarr.data(); amg.Vtemp = &pvt; amg.Ztemp = &pvt;
+   amg.num_levels = L; amg.l1_norms = (HYPRE_Real **)l1; amg.grid_relax_type = relax_types;
+   ad->hypre.solver = (HYPRE_Solver)&amg;
+   ad->hypre.print_level = 0;
+   ad->grid.num_levels = L;
+   ad->input.solver = BPX;
+   ad->input.smoother = smoother;
+   ad->input.smooth_weight = smooth_weight;
+   ad->input.num_pre_smooth_sweeps = num_sweeps;
+   ad->input.num_threads = num_threads;
+   ad->input.cheby_eig_type = CHEBY_EIG_POWER;
+   ad->input.cheby_eig_max_iters = iters;
+   ad->input.format_output_flag = 1;
+   ad->input.num_cycles = 1;
+   ad->matrix.A_diag = dowp.data();
+   double *ep[1] = {e0.data()}, *yp[1] = {y0.data()};
+   ad->vector.e = ep; ad->vector.y = yp;
+   const int saved = omp_get_max_threads();
+   omp_set_num_threads(num_threads);
+   ChebySetup(ad);
+   omp_set_num_threads(saved);
+   out[0] = ad->cheby.alpha; out[1] = ad->cheby.beta; out[2] = ad->cheby.mu; out[3] = ad->cheby.delta;
+   if (f_after) memcpy(f_after, fd[0].data(), sizeof(double) * n0);
+   const int ok = (ad->cheby.omega != nullptr);
+   delete ad;
+   return ok ? 0 : 1;
 }
 
 void ref_destroy(void *h) { delete (RefHandle *)h; }

@@ -273,7 +273,31 @@ def dmem_golden():
     np.savez_compressed(os.path.join(OUT, "dmem.npz"), **d)
 
 
+def cheby_setup_golden():
+    """ChebySetup -> EigsPower -> BPXCycle (src/SMEM_Cheby.cpp:28-60,410-518,520-645) through the reference's object code
+    (SMEM_Cheby.cpp compiled unmodified against SLEPc / LOBPCG stand-ins that are never reached): the eigenvalue bounds of
+    B A and the Chebyshev scalars mu, delta for weighted Jacobi, L1 Jacobi and the hybrid smoother (4 threads = 4 blocks)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import hierarchy_from_golden
+    d = {}
+    for name in ("lap5pt_n32", "lap7pt_n12"):
+        h, g = hierarchy_from_golden(name)
+        h.build_transfers(H.BPX, 0.8)
+        for tag, sm, w, nt in (("j", H.JACOBI, 0.8, 4), ("l1", H.L1_JACOBI, 0.8, 4), ("hjgs", H.HYBRID_JACOBI_GAUSS_SEIDEL, 1.0, 4)):
+            for iters in (3, 20):
+                r = O.ref_cheby_setup(h, g["b"], sm, w, iters, 1, nt)
+                assert np.array_equal(r["f_after"], g["b"])
+                d["%s_%s_it%d" % (name, tag, iters)] = np.asarray([r["alpha"], r["beta"], r["mu"], r["delta"]])
+                print(name, tag, iters, d["%s_%s_it%d" % (name, tag, iters)])
+    np.savez_compressed(os.path.join(OUT, "cheby_setup.npz"), **d)
+
+
 if __name__ == "__main__":
+    if "--cheby-setup-only" in sys.argv:
+        from oracle import build as obuild
+        amg.build.build_host(); obuild.build_oracle(); obuild.build_ref()
+        cheby_setup_golden()
+        sys.exit(0)
     if "--dmem-only" in sys.argv:
         from oracle import build as obuild
         amg.build.build_host(); obuild.build_oracle(); obuild.build_ref()
@@ -304,4 +328,5 @@ if __name__ == "__main__":
         iebpx_golden()
         hybrid_jgs_golden()
         cheby_golden()
+        cheby_setup_golden()
         dmem_golden()

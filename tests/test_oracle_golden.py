@@ -302,6 +302,49 @@ def test_chebyshev_accelerated_bpx_matches_reference_fixture(name):
     assert hist[-1] < 1e-9
 
 
+# ---- ChebySetup / EigsPower / BPXCycle (src/SMEM_Cheby.cpp), SURVEY.md row a17 ------------------------------------------------
+_CHEBY_SETUP_CASES = (("j", H.JACOBI, 0.8), ("l1", H.L1_JACOBI, 0.8), ("hjgs", H.HYBRID_JACOBI_GAUSS_SEIDEL, 1.0))
+
+
+def _oracle_cheby_setup(h, sm, w, iters, nthreads):
+    blocks = [H.nnz_balanced_bounds(a.indptr, nthreads) for a in h.A]       # BPXCycle's block = hypre's load-balanced range
+    lo, hi = O.Problem(h, H.BPX, sm, w, jgs_blocks=blocks).eigs_power(iters)
+    return np.asarray([lo, hi, (hi + lo) / (hi - lo), 2.0 / (hi + lo)])
+
+
+@pytest.mark.parametrize("name", ["lap5pt_n32", "lap7pt_n12"])
+def test_cheby_setup_matches_reference_fixture(name):
+    """orc_eigs_power + the mu / delta formulas against ChebySetup -> EigsPower -> BPXCycle of the reference's object code
+    (tests/golden/cheby_setup.npz): eigenvalue bounds and Chebyshev scalars to 1e-12 relative"""
+    import os
+    from conftest import GOLDEN, hierarchy_from_golden
+    g = dict(np.load(os.path.join(GOLDEN, "cheby_setup.npz")))
+    h, d = hierarchy_from_golden(name)
+    h.build_transfers(H.BPX, 0.8)
+    for tag, sm, w in _CHEBY_SETUP_CASES:
+        for iters in (3, 20):
+            want = g["%s_%s_it%d" % (name, tag, iters)]
+            got = _oracle_cheby_setup(h, sm, w, iters, 4)
+            assert np.max(np.abs(got - want) / np.abs(want)) <= 1e-12, (tag, iters, got, want)
+
+
+def test_cheby_setup_matches_live_reference():
+    if O.ref_lib() is None:
+        pytest.skip("oracle/_ref not built here")
+    for prob, n in (("7pt", 9), ("27pt", 7)):
+        A = H.laplacian(prob, n)
+        h = H.amg_setup(A)
+        b = H.rand_rhs(A.nrows)
+        h.build_transfers(H.BPX, 0.7)
+        for tag, sm, w in _CHEBY_SETUP_CASES:
+            for iters, nt in ((2, 1), (7, 3), (20, 4)):
+                r = O.ref_cheby_setup(h, b, sm, w, iters, 1, nt)
+                assert np.array_equal(r["f_after"], b)                       # EigsPower restores the right-hand side
+                want = np.asarray([r["alpha"], r["beta"], r["mu"], r["delta"]])
+                got = _oracle_cheby_setup(h, sm, w, iters, nt)
+                assert np.max(np.abs(got - want) / np.abs(want)) <= 1e-12, (prob, tag, iters, nt)
+
+
 # ---- DMEM: synchronous Multadd on all ranks and the acceleration of the accumulated correction -----------------------------
 @pytest.mark.parametrize("name", ["lap5pt_n32", "lap7pt_n12"])
 def test_dmem_sync_add_matches_reference_fixture(name):
