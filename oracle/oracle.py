@@ -168,6 +168,26 @@ def spgemv(m, x, b, alpha, beta):
     return y
 
 
+def matvecT(m, x):
+    """y = A^T x, sequential scatter (src/SEQ_MatVec.cpp:26-45)"""
+    y = np.zeros(m.ncols)
+    s = c_csr(m)
+    lib().orc_matvecT.argtypes = [C.POINTER(OrcCSR), DP, DP]
+    lib().orc_matvecT(C.byref(s), dptr(np.ascontiguousarray(x, dtype=np.float64)), dptr(y))
+    return y
+
+
+def ref_parfor_matvec_t(m, x, num_threads=4):
+    """SMEM_Sync_Parfor_MatVecT (src/SMEM_MatVec.cpp:27-58), the reference's object code"""
+    L = ref_lib()
+    y = np.zeros(m.ncols)
+    s = c_csr(m)
+    L.ref_parfor_matvec_t.restype = None
+    L.ref_parfor_matvec_t.argtypes = [C.POINTER(OrcCSR), DP, DP, C.c_int]
+    L.ref_parfor_matvec_t(C.byref(s), dptr(np.ascontiguousarray(x, dtype=np.float64)), dptr(y), num_threads)
+    return y
+
+
 def norm2(x):
     x = np.ascontiguousarray(x)
     return lib().orc_norm2(dptr(x), len(x))

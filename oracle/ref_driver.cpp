@@ -932,6 +932,21 @@ void ref_matvec(const RefCSR *A, double *x, double *y)
    hypre_CSRMatrix m; fill(&m, *A);
    SMEM_MatVec(nullptr, &m, x, y, 0, A->nrows);
 }
+// SMEM_Sync_Parfor_MatVecT (src/SMEM_MatVec.cpp:27-58; the -no_construct_R restriction): scatter into per-thread copies of y,
+// then the copies are summed in thread order.
+void ref_parfor_matvec_t(const RefCSR *A, double *x, double *y, int num_threads)
+{
+   hypre_CSRMatrix m; fill(&m, *A);
+   AllData *ad = new AllData();
+   ad->input.num_threads = num_threads;
+   std::vector<double> ye((size_t)num_threads * A->ncols, 0.0);
+   double *yep = ye.data();
+   #pragma omp parallel num_threads(num_threads)
+   {
+      SMEM_Sync_Parfor_MatVecT(ad, &m, x, y, yep);
+   }
+   delete ad;
+}
 void ref_seq_symmetric_jacobi(const RefCSR *A, double *f, double *u, double w, int sweeps)
 {
    hypre_CSRMatrix m; fill(&m, *A);

@@ -302,6 +302,25 @@ def test_chebyshev_accelerated_bpx_matches_reference_fixture(name):
     assert hist[-1] < 1e-9
 
 
+def test_transpose_matvec_matches_live_reference():
+    """-no_construct_R: SMEM_Sync_Parfor_MatVecT of the reference's object code = the oracle's scatter form
+    (bit-identical with one thread; per-thread partial sums otherwise) = the explicit R = P^T product the default path uses"""
+    if O.ref_lib() is None:
+        pytest.skip("oracle/_ref not built here")
+    A = H.laplacian("7pt", 11)
+    h = H.amg_setup(A)
+    h.build_transfers(H.AFACX, 0.9)                      # plain P, R = P^T
+    rng = np.random.default_rng(11)
+    for l in range(h.num_levels - 1):
+        x = rng.uniform(-1, 1, h.n[l])
+        seq = O.matvecT(h.P[l], x)
+        assert np.array_equal(O.ref_parfor_matvec_t(h.P[l], x, 1), seq)
+        mag = np.maximum(O.matvecT(H.CSR(h.P[l].nrows, h.P[l].ncols, h.P[l].indptr, h.P[l].indices, np.abs(h.P[l].data)), np.abs(x)), 1e-300)
+        for nt in (3, 8):
+            assert np.max(np.abs(O.ref_parfor_matvec_t(h.P[l], x, nt) - seq) / mag) <= 4e-16
+        assert np.max(np.abs(O.spgemv(h.R[l], x, None, 1.0, 0.0) - seq) / mag) <= 4e-16
+
+
 # ---- ChebySetup / EigsPower / BPXCycle (src/SMEM_Cheby.cpp), SURVEY.md row a17 ------------------------------------------------
 _CHEBY_SETUP_CASES = (("j", H.JACOBI, 0.8), ("l1", H.L1_JACOBI, 0.8), ("hjgs", H.HYBRID_JACOBI_GAUSS_SEIDEL, 1.0))
 
