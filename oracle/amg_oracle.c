@@ -337,35 +337,43 @@ static void work_free(orc_work *w)
 /* One additive cycle applied to residual w->r[0]; adds every level's correction into u.
  * Multadd / AFACx: src/SEQ_AMG.cpp:110-235 (sequential specification of
  * src/SMEM_Sync_AMG.cpp:408-621).  levels_done[l]++ mirrors local_num_correct. */
+/* The correction of ONE level from the restricted residuals w->r[level] (and w->r[level + 1] for AFACx) into w->e[level]:
+ * shared by the synchronous cycle (src/SEQ_AMG.cpp:110-235) and the asynchronous chain (src/SMEM_Async_AMG.cpp:109-207). */
+static void orc_level_correction(const orc_problem *pb, orc_work *w, int level)
+{
+   const int L = pb->num_levels;
+   double *uf = w->uc[level]; /* u_fine of this level */
+   if (level == L - 1 && pb->coarse_solve && L > 1) {
+      orc_dense_solve(&pb->A[level], w->r[level], w->e[level]);
+   } else if (level == L - 1) {
+      /* coarsest: solve commented out / result unused -> contributes 0 */
+      memset(w->e[level], 0, sizeof(double) * (size_t)pb->A[level].nrows);
+   } else if (pb->solver == ORC_MULTADD) {
+      memset(w->e[level], 0, sizeof(double) * (size_t)pb->A[level].nrows);
+      orc_smooth(pb, level, w->r[level], w->e[level], w->y[level], w->s[level], pb->fine_sweeps);
+   } else { /* AFACx: src/SEQ_AMG.cpp:172-208, src/SMEM_Async_AMG.cpp:153-206 */
+      int c = level + 1;
+      double *ucoarse = w->rf[c];
+      memset(ucoarse, 0, sizeof(double) * (size_t)pb->A[c].nrows);
+      orc_smooth(pb, c, w->r[c], ucoarse, w->y[c], w->s[c], pb->coarse_sweeps);
+      orc_matvec(&pb->P[level], ucoarse, w->e[level], 0, pb->P[level].nrows);
+      /* r_fine = r - A e */
+      orc_spgemv(&pb->A[level], w->e[level], w->r[level], -1.0, 1.0, w->y[level]);
+      double *rfine = (double *)malloc(sizeof(double) * (size_t)pb->A[level].nrows);
+      memcpy(rfine, w->y[level], sizeof(double) * (size_t)pb->A[level].nrows);
+      memset(uf, 0, sizeof(double) * (size_t)pb->A[level].nrows);
+      orc_smooth(pb, level, rfine, uf, w->y[level], w->s[level], pb->fine_sweeps);
+      memcpy(w->e[level], uf, sizeof(double) * (size_t)pb->A[level].nrows);
+      free(rfine);
+   }
+}
+
 static void orc_add_vcycle(const orc_problem *pb, orc_work *w, double *u, int *levels_done)
 {
    const int L = pb->num_levels;
    for (int l = 0; l < L - 1; l++) orc_matvec(&pb->R[l], w->r[l], w->r[l + 1], 0, pb->R[l].nrows);
    for (int level = 0; level < L; level++) {
-      double *uf = w->uc[level]; /* u_fine of this level */
-      if (level == L - 1 && pb->coarse_solve && L > 1) {
-         orc_dense_solve(&pb->A[level], w->r[level], w->e[level]);
-      } else if (level == L - 1) {
-         /* coarsest: solve commented out / result unused -> contributes 0 */
-         memset(w->e[level], 0, sizeof(double) * (size_t)pb->A[level].nrows);
-      } else if (pb->solver == ORC_MULTADD) {
-         memset(w->e[level], 0, sizeof(double) * (size_t)pb->A[level].nrows);
-         orc_smooth(pb, level, w->r[level], w->e[level], w->y[level], w->s[level], pb->fine_sweeps);
-      } else { /* AFACx: src/SEQ_AMG.cpp:172-208 */
-         int c = level + 1;
-         double *ucoarse = w->rf[c];
-         memset(ucoarse, 0, sizeof(double) * (size_t)pb->A[c].nrows);
-         orc_smooth(pb, c, w->r[c], ucoarse, w->y[c], w->s[c], pb->coarse_sweeps);
-         orc_matvec(&pb->P[level], ucoarse, w->e[level], 0, pb->P[level].nrows);
-         /* r_fine = r - A e */
-         orc_spgemv(&pb->A[level], w->e[level], w->r[level], -1.0, 1.0, w->y[level]);
-         double *rfine = (double *)malloc(sizeof(double) * (size_t)pb->A[level].nrows);
-         memcpy(rfine, w->y[level], sizeof(double) * (size_t)pb->A[level].nrows);
-         memset(uf, 0, sizeof(double) * (size_t)pb->A[level].nrows);
-         orc_smooth(pb, level, rfine, uf, w->y[level], w->s[level], pb->fine_sweeps);
-         memcpy(w->e[level], uf, sizeof(double) * (size_t)pb->A[level].nrows);
-         free(rfine);
-      }
+      orc_level_correction(pb, w, level);
       if (levels_done) levels_done[level]++;
       /* prolong this level's correction to level 0 (src/SEQ_AMG.cpp:213-228) */
       for (int inner = level; inner > 0; inner--)
@@ -507,14 +515,12 @@ int orc_solve_async_sequential(const orc_problem *pb, const double *f, double *u
    const double r0 = orc_norm2(w->r[0], n0);
    for (int k = 0; k < num_cycles; k++)
       for (int q = 0; q < L; q++) {
-         for (int l = 0; l < q && l < L - 1; l++) orc_matvec(&pb->R[l], w->r[l], w->r[l + 1], 0, pb->R[l].nrows);
-         if (q < L - 1) {
-            memset(w->e[q], 0, sizeof(double) * (size_t)pb->A[q].nrows);
-            orc_smooth(pb, q, w->r[q], w->e[q], w->y[q], w->s[q], pb->fine_sweeps);
-         } else if (pb->coarse_solve && L > 1) {
-            /* DMEM: the last grid solves directly (AddCycle, src/DMEM_Add.cpp:262-264) */
-            orc_dense_solve(&pb->A[q], w->r[q], w->e[q]);
-         } else memset(w->e[q], 0, sizeof(double) * (size_t)pb->A[q].nrows);
+         /* restriction chain: down to the group's level (Multadd) or one level further (AFACx), :84-108 */
+         const int coarsest = pb->solver == ORC_MULTADD ? q : q + 1;
+         for (int l = 0; l < coarsest && l < L - 1; l++) orc_matvec(&pb->R[l], w->r[l], w->r[l + 1], 0, pb->R[l].nrows);
+         /* the level's correction: Multadd smoother / AFACx two-stage correction; the last level contributes 0 in SMEM and
+          * solves directly in DMEM (AddCycle, src/DMEM_Add.cpp:262-264) */
+         orc_level_correction(pb, w, q);
          for (int inner = q; inner > 0; inner--)
             orc_matvec(&pb->P[inner - 1], w->e[inner], w->e[inner - 1], 0, pb->P[inner - 1].nrows);
          for (int i = 0; i < n0; i++) u[i] += w->e[0][i];

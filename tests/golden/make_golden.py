@@ -292,7 +292,38 @@ def cheby_setup_golden():
     np.savez_compressed(os.path.join(OUT, "cheby_setup.npz"), **d)
 
 
+ASYNC_CASES = (("multadd", H.ASYNC_MULTADD, H.MULTADD, 0.9, 1), ("afacx", H.ASYNC_AFACX, H.AFACX, 0.6, 1), ("afacx2", H.ASYNC_AFACX, H.AFACX, 0.6, 2))
+
+
+def async_golden():
+    """SMEM_Async_Add_AMG (src/SMEM_Async_AMG.cpp:7-437) through the reference's object code on the first TWO levels of the
+    committed hierarchies, one thread per level: a single working group, so the asynchronous iteration is deterministic
+    (the coarsest group adds exactly zero).  Multadd (symmetrised Jacobi) and AFACx (1 and 2 sweeps)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import hierarchy_from_golden
+    d = {}
+    for name in ("lap5pt_n32", "lap7pt_n12"):
+        hf, g = hierarchy_from_golden(name)
+        h = H.Hierarchy(hf.A[:2], hf.P_plain[:1])
+        for tag, solver, base, w, sweeps in ASYNC_CASES:
+            h.build_transfers(base, w)
+            for K in (1, 7, 30):
+                rs = O.RefSolver(h, solver, H.JACOBI, g["b"], w, one_thread_per_level=True, fine_sweeps=sweeps, coarse_sweeps=sweeps)
+                out = rs.solve(K, 1e-9, async_type=0)
+                rs.close()
+                assert list(out["corrections"]) == [K, K]
+                d["%s_%s_k%d_u" % (name, tag, K)] = out["u"]
+                d["%s_%s_k%d_relres" % (name, tag, K)] = np.asarray(out["relres"])
+                print(name, tag, K, out["relres"])
+    np.savez_compressed(os.path.join(OUT, "async_two_level.npz"), **d)
+
+
 if __name__ == "__main__":
+    if "--async-only" in sys.argv:
+        from oracle import build as obuild
+        amg.build.build_host(); obuild.build_oracle(); obuild.build_ref()
+        async_golden()
+        sys.exit(0)
     if "--cheby-setup-only" in sys.argv:
         from oracle import build as obuild
         amg.build.build_host(); obuild.build_oracle(); obuild.build_ref()
@@ -329,4 +360,5 @@ if __name__ == "__main__":
         hybrid_jgs_golden()
         cheby_golden()
         cheby_setup_golden()
+        async_golden()
         dmem_golden()

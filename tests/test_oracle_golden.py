@@ -321,6 +321,50 @@ def test_transpose_matvec_matches_live_reference():
         assert np.max(np.abs(O.spgemv(h.R[l], x, None, 1.0, 0.0) - seq) / mag) <= 4e-16
 
 
+# ---- SMEM_Async_Add_AMG (src/SMEM_Async_AMG.cpp), SURVEY.md row a15 -----------------------------------------------------------
+_ASYNC_CASES = (("multadd", H.ASYNC_MULTADD, H.MULTADD, 0.9, 1), ("afacx", H.ASYNC_AFACX, H.AFACX, 0.6, 1), ("afacx2", H.ASYNC_AFACX, H.AFACX, 0.6, 2))
+
+
+@pytest.mark.parametrize("name", ["lap5pt_n32", "lap7pt_n12"])
+def test_async_single_group_matches_reference_fixture(name):
+    """the asynchronous solver of the reference's object code on a two-level hierarchy (one working group: deterministic)
+    against the oracle's sequential model, Multadd and AFACx chains (tests/golden/async_two_level.npz)"""
+    import os
+    from conftest import GOLDEN, hierarchy_from_golden
+    g = dict(np.load(os.path.join(GOLDEN, "async_two_level.npz")))
+    hf, d = hierarchy_from_golden(name)
+    h = H.Hierarchy(hf.A[:2], hf.P_plain[:1])
+    for tag, solver, base, w, sweeps in _ASYNC_CASES:
+        h.build_transfers(base, w)
+        pb = O.Problem(h, base, H.JACOBI, w, fine_sweeps=sweeps, coarse_sweeps=sweeps)
+        for K in (1, 7, 30):
+            u, counts, rel = pb.solve_async_sequential(d["b"], K)
+            want = g["%s_%s_k%d_u" % (name, tag, K)]
+            assert list(counts) == [K, K]
+            assert np.max(np.abs(u - want)) <= 1e-14 * np.max(np.abs(want)), (tag, K)
+            assert abs(rel - float(g["%s_%s_k%d_relres" % (name, tag, K)])) <= 1e-13
+
+
+def test_async_single_group_matches_live_reference():
+    if O.ref_lib() is None:
+        pytest.skip("oracle/_ref not built here")
+    if O.ref_lib().ref_max_threads() < 2:
+        pytest.skip("needs two cores (one spinning thread per level)")
+    A = H.laplacian("27pt", 8)
+    h = H.amg_setup(A, max_levels=2)
+    b = H.rand_rhs(A.nrows)
+    for tag, solver, base, w, sweeps in _ASYNC_CASES:
+        h.build_transfers(base, w)
+        for K in (2, 11):
+            rs = O.RefSolver(h, solver, H.JACOBI, b, w, one_thread_per_level=True, fine_sweeps=sweeps, coarse_sweeps=sweeps)
+            out = rs.solve(K, 1e-9, async_type=0)
+            rs.close()
+            u, counts, rel = O.Problem(h, base, H.JACOBI, w, fine_sweeps=sweeps, coarse_sweeps=sweeps).solve_async_sequential(b, K)
+            assert list(out["corrections"]) == list(counts) == [K, K]
+            assert np.max(np.abs(u - out["u"])) <= 1e-14 * np.max(np.abs(u)), (tag, K)
+            assert abs(rel - out["relres"]) <= 1e-13
+
+
 # ---- ChebySetup / EigsPower / BPXCycle (src/SMEM_Cheby.cpp), SURVEY.md row a17 ------------------------------------------------
 _CHEBY_SETUP_CASES = (("j", H.JACOBI, 0.8), ("l1", H.L1_JACOBI, 0.8), ("hjgs", H.HYBRID_JACOBI_GAUSS_SEIDEL, 1.0))
 
