@@ -20,7 +20,20 @@ ASYNC_GAUSS_SEIDEL = 5
 L1_JACOBI = 6
 MULT, AFACX, MULTADD, BPX = 0, 1, 2, 3
 ASYNC_AFACX, ASYNC_MULTADD = 5, 6
+PAR_BPX = 17                        # `-solver par_bpx` (src/Main.hpp:77): see par_bpx_equivalent
 IMPLICIT_EXTENDED_SYSTEM_BPX = 16   # `-solver iebpx` (src/Main.hpp:76, src/SMEM_ExtendedSystem.cpp)
+
+
+def par_bpx_equivalent(smoother, smooth_weight):
+    """`-solver par_bpx` (SMEM_Sync_Parfor_BPXcycle's PAR_BPX branch, src/SMEM_Sync_AMG.cpp:183-236) is BPX on the concatenated level
+    vectors with ONE Jacobi loop over all levels, xx = w * rr / A_diag_ext.  A_diag_ext already holds a_ii / w
+    (src/SMEM_Setup.cpp:451-460), so the weight is applied twice: the cycle equals BPX with weighted Jacobi and weight w^2
+    (the reference's object code confirms it, tests/test_oracle_golden.py).  With the L1 smoother the step is w / l1 -- a
+    weighted L1 Jacobi that no other solver of the reference has; it is not offered on the device.
+    -> (solver, smoother, smooth_weight) to hand to Solver / amgb_options."""
+    if smoother in (L1_JACOBI,):
+        raise ValueError("par_bpx with the L1 smoother (step w / l1, src/SMEM_Sync_AMG.cpp:207-212) has no device equivalent")
+    return BPX, JACOBI, smooth_weight * smooth_weight
 
 
 class _CSR(C.Structure):

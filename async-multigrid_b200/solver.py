@@ -142,6 +142,8 @@ class Solver:
         rc = self.L.amgb_create(C.byref(self.ctx), device)
         if rc != 0:
             raise AmgError("amgb_create failed (%d): no CUDA device / driver -- there is no CPU fallback" % rc)
+        if solver == H.PAR_BPX:          # same cycle as BPX with the weight applied twice (hierarchy.par_bpx_equivalent)
+            solver, smoother, smooth_weight = H.par_bpx_equivalent(smoother, smooth_weight)
         o = Options()
         self.L.amgb_default_options(C.byref(o))
         o.solver, o.smoother, o.smooth_weight = solver, smoother, smooth_weight

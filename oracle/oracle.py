@@ -86,14 +86,14 @@ class Problem:
     """Keeps the numpy arrays alive and exposes an orc_problem for the C side."""
 
     def __init__(self, h, solver, smoother, smooth_weight=1.0, num_pre=1, num_post=1,
-                 fine_sweeps=1, coarse_sweeps=1, jgs_blocks=None, jgs_parfor_scale=0, coarse_solve=0):
+                 fine_sweeps=1, coarse_sweeps=1, jgs_blocks=None, jgs_parfor_scale=0, coarse_solve=0, l1_scale=1.0):
         L = h.num_levels
         self.h = h
         self._keep = (list(h.A), list(h.P), list(h.R))   # the C structs borrow these arrays
         self._A = (OrcCSR * L)(*[c_csr(a) for a in h.A])
         self._P = (OrcCSR * max(L - 1, 1))(*[c_csr(p) for p in h.P])
         self._R = (OrcCSR * max(L - 1, 1))(*[c_csr(r) for r in h.R])
-        self._l1arrs = h.l1_norms()
+        self._l1arrs = [np.ascontiguousarray(a * l1_scale) for a in h.l1_norms()]     # l1_scale = 1 / w: the step w / l1 of PAR_BPX
         self._l1 = (DP * L)(*[dptr(a) for a in self._l1arrs])
         if jgs_blocks is None:
             jgs_blocks = [np.asarray([0, a.nrows], dtype=np.int32) for a in h.A]

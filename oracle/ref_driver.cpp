@@ -334,6 +334,19 @@ void *ref_create(int L, const RefCSR *A, const RefCSR *P, const RefCSR *R, doubl
    H->amg.F_array = H->Farr.data(); H->amg.U_array = H->Uarr.data();
    H->amg.Vtemp = &H->pv[2]; H->amg.Ztemp = &H->pv[2]; H->amg.l1_norms = (HYPRE_Real **)l1;
    ad->hypre.solver = (HYPRE_Solver)&H->amg;
+   if (solver == PAR_BPX) {
+      // src/SMEM_Setup.cpp:426-462: the level vectors concatenated, and the smoother's scale array over all levels
+      ad->grid.disp = (int *)malloc((L + 1) * sizeof(int));
+      ad->grid.N = 0; ad->grid.disp[0] = 0;
+      for (int l = 0; l < L; l++) { ad->grid.disp[l + 1] = ad->grid.disp[l] + A[l].nrows; ad->grid.N += A[l].nrows; }
+      ad->vector.xx = H->vec(ad->grid.N);
+      ad->vector.rr = H->vec(ad->grid.N);
+      double *ext = H->vec(ad->grid.N);
+      const bool l1s = smoother == L1_JACOBI || smoother == L1_HYBRID_JACOBI_GAUSS_SEIDEL;
+      for (int l = 0, k = 0; l < L; l++)
+         for (int i = 0; i < A[l].nrows; i++, k++) ext[k] = l1s ? l1[l][i] : A[l].data[A[l].i[i]] / smooth_weight;
+      if (l1s) ad->matrix.L1_row_norm_ext = ext; else ad->matrix.A_diag_ext = ext;
+   }
 
    // vectors (src/SMEM_Setup.cpp:280-419)
    VectorData *v = &ad->vector;

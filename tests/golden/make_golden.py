@@ -318,7 +318,31 @@ def async_golden():
     np.savez_compressed(os.path.join(OUT, "async_two_level.npz"), **d)
 
 
+def par_bpx_golden():
+    """`-solver par_bpx` (PAR_BPX branch of SMEM_Sync_Parfor_BPXcycle, src/SMEM_Sync_AMG.cpp:183-236) through SMEM_Solve of the
+    reference's object code, 4 threads, 12 cycles, weight 0.6: weighted Jacobi (the weight ends up squared) and L1 (step w / l1)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import hierarchy_from_golden
+    d = {}
+    for name in ("lap5pt_n32", "lap7pt_n12"):
+        h, g = hierarchy_from_golden(name)
+        h.build_transfers(H.BPX, 0.6)
+        for tag, sm in (("j", H.JACOBI), ("l1", H.L1_JACOBI)):
+            rs = O.RefSolver(h, H.PAR_BPX, sm, g["b"], 0.6, num_threads=4)
+            out = rs.solve(12, 1e-30, async_type=0)
+            rs.close()
+            d["%s_%s_hist" % (name, tag)] = out["hist"]
+            d["%s_%s_u" % (name, tag)] = out["u"]
+            print(name, tag, out["hist"][-1])
+    np.savez_compressed(os.path.join(OUT, "par_bpx.npz"), **d)
+
+
 if __name__ == "__main__":
+    if "--par-bpx-only" in sys.argv:
+        from oracle import build as obuild
+        amg.build.build_host(); obuild.build_oracle(); obuild.build_ref()
+        par_bpx_golden()
+        sys.exit(0)
     if "--async-only" in sys.argv:
         from oracle import build as obuild
         amg.build.build_host(); obuild.build_oracle(); obuild.build_ref()
@@ -360,5 +384,6 @@ if __name__ == "__main__":
         hybrid_jgs_golden()
         cheby_golden()
         cheby_setup_golden()
+        par_bpx_golden()
         async_golden()
         dmem_golden()

@@ -321,6 +321,52 @@ def test_transpose_matvec_matches_live_reference():
         assert np.max(np.abs(O.spgemv(h.R[l], x, None, 1.0, 0.0) - seq) / mag) <= 4e-16
 
 
+@pytest.mark.parametrize("name", ["lap5pt_n32", "lap7pt_n12"])
+def test_par_bpx_matches_reference_fixture(name):
+    """`-solver par_bpx` from the reference's object code (tests/golden/par_bpx.npz): BPX with the Jacobi weight applied twice
+    (xx = w rr / (a_ii / w), src/SMEM_Sync_AMG.cpp:213-218 with src/SMEM_Setup.cpp:451-460), and with the step w / l1 for L1"""
+    import os
+    from conftest import GOLDEN, hierarchy_from_golden
+    g = dict(np.load(os.path.join(GOLDEN, "par_bpx.npz")))
+    h, d = hierarchy_from_golden(name)
+    h.build_transfers(H.BPX, 0.6)
+    sv, sm, w2 = H.par_bpx_equivalent(H.JACOBI, 0.6)
+    assert (sv, sm) == (H.BPX, H.JACOBI) and abs(w2 - 0.36) < 1e-15
+    u, hist, _ = O.Problem(h, sv, sm, w2).solve_sync(d["b"], 1e-30, 12)
+    want = g[name + "_j_hist"]
+    assert len(hist) == len(want) and np.max(np.abs(hist - want) / want) <= 1e-10
+    assert np.max(np.abs(u - g[name + "_j_u"])) <= 1e-12 * np.max(np.abs(u))
+    u, hist, _ = O.Problem(h, H.BPX, H.L1_JACOBI, 0.6, l1_scale=1.0 / 0.6).solve_sync(d["b"], 1e-30, 12)
+    want = g[name + "_l1_hist"]
+    assert len(hist) == len(want) and np.max(np.abs(hist - want) / want) <= 1e-10
+    with pytest.raises(ValueError):
+        H.par_bpx_equivalent(H.L1_JACOBI, 0.6)
+
+
+def test_async_gauss_seidel_smoothers_match_live_reference():
+    """SMEM_Async_GaussSeidel / SMEM_SemiAsync_GaussSeidel (src/SMEM_Smooth.cpp:445-502) inside Multadd, the
+    reference's object code with one thread per level: the chaotic sweep over a single row range IS Gauss-Seidel = the oracle's
+    hybrid smoother with one block"""
+    if O.ref_lib() is None:
+        pytest.skip("oracle/_ref not built here")
+    A = H.laplacian("7pt", 10)
+    h = H.amg_setup(A)
+    if h.num_levels > O.ref_lib().ref_max_threads():
+        pytest.skip("more levels than cores: the reference's spin barriers would oversubscribe")
+    b = H.rand_rhs(A.nrows)
+    h.build_transfers(H.MULTADD, 0.9, num_pre=1, num_post=0)
+    blocks = [np.asarray([0, a.nrows], dtype=np.int32) for a in h.A]
+    for sm in (H.ASYNC_GAUSS_SEIDEL, H.SEMI_ASYNC_GAUSS_SEIDEL):
+        for sweeps in (1, 2):
+            _, want, _ = O.Problem(h, H.MULTADD, H.HYBRID_JACOBI_GAUSS_SEIDEL, 0.9, num_pre=1, num_post=0, jgs_blocks=blocks,
+                                   fine_sweeps=sweeps).solve_sync(b, 1e-9, 60)
+            rs = O.RefSolver(h, H.MULTADD, sm, b, 0.9, num_pre=1, num_post=0, one_thread_per_level=True, fine_sweeps=sweeps)
+            out = rs.solve_sync_det(60, 1e-9)
+            rs.close()
+            _close_hist(want, out["hist"])
+            assert want[-1] < 1e-9
+
+
 # ---- SMEM_Async_Add_AMG (src/SMEM_Async_AMG.cpp), SURVEY.md row a15 -----------------------------------------------------------
 _ASYNC_CASES = (("multadd", H.ASYNC_MULTADD, H.MULTADD, 0.9, 1), ("afacx", H.ASYNC_AFACX, H.AFACX, 0.6, 1), ("afacx2", H.ASYNC_AFACX, H.AFACX, 0.6, 2))
 

@@ -189,3 +189,18 @@ def test_async_single_group_matches_reference_fixture(name, tag, solver, base, w
 @pytest.mark.parametrize("name", ["lap5pt_n32", "lap7pt_n12"])
 def test_async_afacx_two_sweeps_matches_reference_fixture(name):
     _async_fixture_case(name, "afacx2", H.ASYNC_AFACX, H.AFACX, 0.6, 2)
+
+
+@pytest.mark.parametrize("name", ["lap5pt_n32", "lap7pt_n12"])
+def test_par_bpx_matches_reference_fixture(name):
+    """`-solver par_bpx` against the reference's own object code (tests/golden/par_bpx.npz): Solver(PAR_BPX) runs BPX with the
+    Jacobi weight applied twice (hierarchy.par_bpx_equivalent)"""
+    g = dict(np.load(os.path.join(GOLDEN, "par_bpx.npz")))
+    h, d = hierarchy_from_golden(name)
+    h.build_transfers(H.BPX, 0.6)
+    s = amg.Solver(h, H.PAR_BPX, H.JACOBI, 0.6)
+    out = s.SMEM_Solve(d["b"], 1e-30, 12)
+    s.close()
+    want = g[name + "_j_hist"]
+    assert len(out["hist"]) == len(want) and np.max(np.abs(out["hist"] - want) / want) <= 1e-10
+    assert np.max(np.abs(out["u"] - g[name + "_j_u"])) <= 1e-11 * np.max(np.abs(out["u"]))
