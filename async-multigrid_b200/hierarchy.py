@@ -28,7 +28,7 @@ def par_bpx_equivalent(smoother, smooth_weight):
     """`-solver par_bpx` (SMEM_Sync_Parfor_BPXcycle's PAR_BPX branch, src/SMEM_Sync_AMG.cpp:183-236) is BPX on the concatenated level
     vectors with ONE Jacobi loop over all levels, xx = w * rr / A_diag_ext.  A_diag_ext already holds a_ii / w
     (src/SMEM_Setup.cpp:451-460), so the weight is applied twice: the cycle equals BPX with weighted Jacobi and weight w^2
-    (the reference's object code confirms it, tests/test_oracle_golden.py).  With the L1 smoother the step is w / l1 -- a
+    (confirmed against the reference's object code by the CPU test suite).  With the L1 smoother the step is w / l1 -- a
     weighted L1 Jacobi that no other solver of the reference has; it is not offered on the device.
     -> (solver, smoother, smooth_weight) to hand to Solver / amgb_options."""
     if smoother in (L1_JACOBI,):
