@@ -815,8 +815,12 @@ void enq_vcycle(amgb_ctx *c)
    }
    {
       const int cl = L - 1;
-      enq_jacobi_sweeps(c, cl, cl == 0 ? c->f : c->r[cl], cl == 0 ? c->u : c->e[cl],
-                        o.num_pre_smooth_sweeps + o.num_post_smooth_sweeps, c->t[cl]);
+      // DMEM's comparator (DMEM_MultCycle, src/DMEM_Mult.cpp:207): direct solve on the coarsest level
+      if (o.coarse_solve && cl > 0 && c->Ainv.rp != nullptr)
+         enq_spmv(c, c->Ainv, false, c->r[cl], c->e[cl], epi(1.0, 0.0, nullptr), false);
+      else
+         enq_jacobi_sweeps(c, cl, cl == 0 ? c->f : c->r[cl], cl == 0 ? c->u : c->e[cl],
+                           o.num_pre_smooth_sweeps + o.num_post_smooth_sweeps, c->t[cl]);
    }
    for (int l = L - 2; l >= 0; l--) {
       const double *fl = l == 0 ? c->f : c->r[l];

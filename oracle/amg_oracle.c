@@ -407,7 +407,10 @@ static void orc_bpx_cycle(const orc_problem *pb, orc_work *w, double *u)
  * u is level 0's solution (in/out), f its right-hand side.  w->e[l] (l >= 1) are the level solutions, w->r[l]
  * (l >= 1) the level right-hand sides.  Quirks mirrored: zero_flags is 1 on levels 1..L-2 on the way down (the
  * first sweep overwrites u_l), 0 on level 0 and on the way up; the coarsest level's zero flag is never raised, so its
- * num_pre + num_post sweeps start from whatever the previous cycle left in u_{L-1} (0 on the first cycle). */
+ * num_pre + num_post sweeps start from whatever the previous cycle left in u_{L-1} (0 on the first cycle).
+ * coarse_solve = 1: DMEM's comparator (DMEM_Mult / DMEM_MultCycle, src/DMEM_Mult.cpp:13-261, Jacobi branch `smoother == 0`): the same
+ * V(1,1) with a direct solve on the coarsest level; the reference applies it to the residual from a zero guess and adds the
+ * result to x, which is the same affine map. */
 static void orc_mult_vcycle(const orc_problem *pb, orc_work *w, const double *f, double *u)
 {
    const int L = pb->num_levels;
@@ -424,7 +427,9 @@ static void orc_mult_vcycle(const orc_problem *pb, orc_work *w, const double *f,
       const int c = L - 1;
       const double *fc = c == 0 ? f : w->r[c];
       double *ucs = c == 0 ? u : w->e[c];
-      if (pb->smoother == ORC_L1_JACOBI) orc_l1_jacobi(&pb->A[c], fc, ucs, w->y[c], pb->l1[c], pb->num_pre + pb->num_post, 0);
+      /* DMEM convention (DMEM_MultCycle, src/DMEM_Mult.cpp:207: hypre_GaussElimSolve on the coarsest level) */
+      if (pb->coarse_solve && L > 1) orc_dense_solve(&pb->A[c], fc, ucs);
+      else if (pb->smoother == ORC_L1_JACOBI) orc_l1_jacobi(&pb->A[c], fc, ucs, w->y[c], pb->l1[c], pb->num_pre + pb->num_post, 0);
       else orc_jacobi(&pb->A[c], fc, ucs, w->y[c], om, pb->num_pre + pb->num_post, 0);
    }
    for (int l = L - 2; l >= 0; l--) {

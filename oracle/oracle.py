@@ -299,6 +299,26 @@ def ref_dmem_sync_add(h, b, smooth_weight, symmetrised=True, num_cycles=100, tol
     return x, hist[:k + 1]
 
 
+def ref_dmem_mult(h, b, smooth_weight, num_cycles=100, tol=1e-9):
+    """the reference's DMEM_Mult / DMEM_MultCycle object code (src/DMEM_Mult.cpp:13-261) on one rank: multiplicative V(1,1),
+    weighted Jacobi, direct solve on the coarsest level; h.P / h.R plain.  -> (x, hist)"""
+    L = ref_lib()
+    nl = h.num_levels
+    Rt = [_pkg.hierarchy.CSR.from_scipy(r.to_scipy().T.tocsr()) for r in h.R]     # hypre applies R_array transposed
+    keep = (list(h.A), list(h.P), Rt)
+    A = (OrcCSR * nl)(*[c_csr(a) for a in h.A])
+    P = (OrcCSR * max(nl - 1, 1))(*[c_csr(p) for p in h.P])
+    R = (OrcCSR * max(nl - 1, 1))(*[c_csr(r) for r in Rt])
+    x, hist = np.zeros(h.n[0]), np.zeros(num_cycles + 1)
+    L.ref_dmem_mult.restype = C.c_int
+    L.ref_dmem_mult.argtypes = [C.c_int, C.POINTER(OrcCSR), C.POINTER(OrcCSR), C.POINTER(OrcCSR), C.c_double, DP, C.c_int, C.c_double,
+                                DP, DP]
+    k = L.ref_dmem_mult(nl, A, P, R, smooth_weight, dptr(np.ascontiguousarray(b, dtype=np.float64)), num_cycles, tol, dptr(x),
+                        dptr(hist))
+    del keep
+    return x, hist[:k + 1]
+
+
 def ref_dmem_add_cycles(h, b, smooth_weight, symmetrised=True, rounds=10):
     """AddCycle + DMEM_AddSmooth (src/DMEM_Add.cpp:180-329, src/DMEM_Smooth.cpp:574-638), the reference's object code, grid
     after grid on one rank -> (x, hist per round)"""

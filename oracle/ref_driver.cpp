@@ -717,6 +717,74 @@ int ref_dmem_sync_add(int L, const RefCSR *A, const RefCSR *P, const RefCSR *Rt,
    return done;
 }
 
+// DMEM_Mult / DMEM_MultCycle (src/DMEM_Mult.cpp:13-261), the reference's object code on one rank: the multiplicative V(1,1)
+// comparator of the DMEM driver, Jacobi branch (grid_relax_type[1] == 0: u += relax_weight v / a_ii before the restriction and
+// after the prolongation), hypre_GaussElimSolve on the coarsest level, R_array applied transposed.  One cycle per call of
+// DMEM_Mult (it re-reads x and b on entry); DMEM_MultCycle repoints F_array[0] / U_array[0] at its arguments, so they are
+// pointed back at hypre's own vectors before every call.
+int ref_dmem_mult(int L, const RefCSR *A, const RefCSR *P, const RefCSR *Rt, double smooth_weight, const double *b, int num_cycles,
+                  double tol, double *x_out, double *hist)
+{
+   DMEM_AllData *dm = new DMEM_AllData();
+   std::vector<hypre_CSRMatrix> hA(L), hP(L), hR(L);
+   std::vector<hypre_ParCSRMatrix> pA(L), pP(L), pR(L);
+   std::vector<hypre_ParCSRMatrix *> Aarr(L), Parr(L), Rarr(L);
+   std::vector<std::vector<double>> ud(L), fd(L);
+   std::vector<hypre_Vector> uv(L), fv(L);
+   std::vector<hypre_ParVector> up(L), fp(L);
+   std::vector<hypre_ParVector *> Uarr(L), Farr(L);
+   std::vector<double> rw(L, smooth_weight);
+   for (int l = 0; l < L; l++) {
+      fill(&hA[l], A[l]); memset(&pA[l], 0, sizeof(pA[l])); pA[l].diag = &hA[l]; pA[l].global_num_rows = A[l].nrows; Aarr[l] = &pA[l];
+      if (l < L - 1) {
+         fill(&hP[l], P[l]); memset(&pP[l], 0, sizeof(pP[l])); pP[l].diag = &hP[l]; pP[l].global_num_rows = P[l].nrows; Parr[l] = &pP[l];
+         fill(&hR[l], Rt[l]); memset(&pR[l], 0, sizeof(pR[l])); pR[l].diag = &hR[l]; pR[l].global_num_rows = Rt[l].nrows; Rarr[l] = &pR[l];
+      }
+      ud[l].assign(A[l].nrows, 0.0); fd[l].assign(A[l].nrows, 0.0);
+      uv[l].data = ud[l].data(); uv[l].size = A[l].nrows; up[l].local_vector = &uv[l]; Uarr[l] = &up[l];
+      fv[l].data = fd[l].data(); fv[l].size = A[l].nrows; fp[l].local_vector = &fv[l]; Farr[l] = &fp[l];
+   }
+   const int n0 = A[0].nrows;
+   std::vector<double> vt(n0, 0.0), xv(n0, 0.0), rv(b, b + n0), bv(b, b + n0), ev(n0, 0.0), dv(n0, 0.0);
+   hypre_Vector hv[6];
+   hypre_ParVector pv[6];
+   double *ptrs[6] = {vt.data(), xv.data(), rv.data(), bv.data(), ev.data(), dv.data()};
+   for (int k = 0; k < 6; k++) { hv[k].data = ptrs[k]; hv[k].size = n0; pv[k].local_vector = &hv[k]; }
+   hypre_ParAMGData amg;
+   memset(&amg, 0, sizeof(amg));
+   int relax_type[4] = {0, 0, 0, 0};
+   amg.A_array = Aarr.data(); amg.P_array = Parr.data(); amg.R_array = Rarr.data();
+   amg.F_array = Farr.data(); amg.U_array = Uarr.data(); amg.Vtemp = &pv[0]; amg.Ztemp = &pv[0];
+   amg.num_levels = L; amg.grid_relax_type = relax_type; amg.relax_weight = rw.data(); amg.functional_gauss_elim = 1;
+   dm->hypre.solver = (HYPRE_Solver)&amg;
+   dm->matrix.A_fine = &pA[0];
+   dm->input.solver = MULT;
+   dm->input.tol = tol;
+   dm->input.num_cycles = 1;
+   dm->input.accel_type = NO_ACCEL;
+   dm->input.delay_flag = 0;
+   dm->vector_fine.x = &pv[1]; dm->vector_fine.r = &pv[2]; dm->vector_fine.b = &pv[3]; dm->vector_fine.e = &pv[4];
+   dm->vector_fine.d = &pv[5];
+   double r0 = 0.0;
+   for (int i = 0; i < n0; i++) r0 += b[i] * b[i];
+   r0 = sqrt(r0);
+   dm->output.r0_norm2 = r0;
+   if (hist) hist[0] = 1.0;
+   int done = 0;
+   for (int k = 1; k <= num_cycles; k++) {
+      Uarr[0] = &up[0]; Farr[0] = &fp[0]; Aarr[0] = &pA[0];
+      DMEM_Mult(dm);
+      double rn = 0.0;
+      for (int i = 0; i < n0; i++) rn += rv[i] * rv[i];
+      done = k;
+      if (hist) hist[k] = sqrt(rn) / r0;
+      if (sqrt(rn) / r0 < tol) break;
+   }
+   if (x_out) memcpy(x_out, xv.data(), sizeof(double) * n0);
+   delete dm;
+   return done;
+}
+
 // DMEM_ChebyUpdate (src/DMEM_Misc.cpp:612-666), synchronous branch: d and u of length n, `cycle` = iter.cycle; c / c_prev are
 // the recurrence state (in / out)
 void ref_dmem_cheby_update(int n, double *d, double *u, int cycle, double mu, double delta, int accel_type, double *c, double *c_prev)

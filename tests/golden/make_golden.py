@@ -337,7 +337,27 @@ def par_bpx_golden():
     np.savez_compressed(os.path.join(OUT, "par_bpx.npz"), **d)
 
 
+def dmem_mult_golden():
+    """DMEM_Mult / DMEM_MultCycle (src/DMEM_Mult.cpp:13-261; the DMEM driver's multiplicative comparator: V(1,1), weighted Jacobi,
+    direct solve on the coarsest level) through the reference's object code on one rank"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import hierarchy_from_golden
+    d = {}
+    for name in ("lap5pt_n32", "lap7pt_n12"):
+        h, g = hierarchy_from_golden(name)
+        h.build_transfers(H.MULT, 0.8)
+        x, hist = O.ref_dmem_mult(h, g["b"], 0.8, 100, 1e-9)
+        d[name + "_hist"], d[name + "_x"] = hist, x
+        print(name, len(hist) - 1, hist[-1])
+    np.savez_compressed(os.path.join(OUT, "dmem_mult.npz"), **d)
+
+
 if __name__ == "__main__":
+    if "--dmem-mult-only" in sys.argv:
+        from oracle import build as obuild
+        amg.build.build_host(); obuild.build_oracle(); obuild.build_ref()
+        dmem_mult_golden()
+        sys.exit(0)
     if "--par-bpx-only" in sys.argv:
         from oracle import build as obuild
         amg.build.build_host(); obuild.build_oracle(); obuild.build_ref()
@@ -385,5 +405,6 @@ if __name__ == "__main__":
         cheby_golden()
         cheby_setup_golden()
         par_bpx_golden()
+        dmem_mult_golden()
         async_golden()
         dmem_golden()

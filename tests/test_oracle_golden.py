@@ -507,6 +507,35 @@ def test_dmem_async_smooth_matches_reference_fixture(name):
     assert np.max(np.abs(want - g[name + "_asyncsmooth_l1_x"])) <= 1e-13 * np.max(np.abs(want))
 
 
+@pytest.mark.parametrize("name", ["lap5pt_n32", "lap7pt_n12"])
+def test_dmem_mult_matches_reference_fixture(name):
+    """DMEM_Mult / DMEM_MultCycle (src/DMEM_Mult.cpp:13-261), the DMEM driver's multiplicative comparator, from the reference's
+    object code on one rank (tests/golden/dmem_mult.npz) against the oracle's V-cycle with the direct coarse solve"""
+    import os
+    from conftest import GOLDEN, hierarchy_from_golden
+    g = dict(np.load(os.path.join(GOLDEN, "dmem_mult.npz")))
+    h, d = hierarchy_from_golden(name)
+    h.build_transfers(H.MULT, 0.8)
+    u, hist, _ = O.Problem(h, H.MULT, H.JACOBI, 0.8, coarse_solve=1).solve_sync(d["b"], 1e-9, 100)
+    _close_hist(hist, g[name + "_hist"])
+    assert hist[-1] < 1e-9
+    assert np.max(np.abs(u - g[name + "_x"])) <= 1e-12 * np.max(np.abs(u))
+
+
+def test_dmem_mult_matches_live_reference():
+    if O.ref_lib() is None:
+        pytest.skip("oracle/_ref not built here")
+    A = H.laplacian("27pt", 8)
+    h = H.amg_setup(A)
+    b = H.rand_rhs(A.nrows)
+    for w in (0.6, 0.9):
+        h.build_transfers(H.MULT, w)
+        x, want = O.ref_dmem_mult(h, b, w, 80, 1e-9)
+        u, hist, _ = O.Problem(h, H.MULT, H.JACOBI, w, coarse_solve=1).solve_sync(b, 1e-9, 80)
+        _close_hist(hist, want)
+        assert np.max(np.abs(u - x)) <= 1e-12 * np.max(np.abs(u))
+
+
 def test_dmem_sync_add_matches_live_reference():
     if O.ref_lib() is None:
         pytest.skip("oracle/_ref not built here")

@@ -204,3 +204,18 @@ def test_par_bpx_matches_reference_fixture(name):
     want = g[name + "_j_hist"]
     assert len(out["hist"]) == len(want) and np.max(np.abs(out["hist"] - want) / want) <= 1e-10
     assert np.max(np.abs(out["u"] - g[name + "_j_u"])) <= 1e-11 * np.max(np.abs(out["u"]))
+
+
+@pytest.mark.parametrize("name", ["lap5pt_n32", "lap7pt_n12"])
+def test_dmem_mult_matches_reference_fixture(name):
+    """DMEM's multiplicative comparator (DMEM_Mult / DMEM_MultCycle object code, tests/golden/dmem_mult.npz): the device V(1,1)
+    cycle with coarse_solve = 1 (dense inverse of the coarsest operator applied as one SpMV)"""
+    g = dict(np.load(os.path.join(GOLDEN, "dmem_mult.npz")))
+    h, d = hierarchy_from_golden(name)
+    h.build_transfers(H.MULT, 0.8)
+    s = amg.Solver(h, H.MULT, H.JACOBI, 0.8, coarse_solve=True)
+    out = s.SMEM_Solve(d["b"], 1e-9, 100)
+    s.close()
+    want = g[name + "_hist"]
+    assert len(out["hist"]) == len(want) and np.max(np.abs(out["hist"] - want)) <= HIST_TOL
+    assert np.max(np.abs(out["u"] - g[name + "_x"])) <= 1e-11 * np.max(np.abs(out["u"]))
