@@ -16,6 +16,7 @@
 #include "async_team.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(kABlock, 3) k_async_amg(const AsyncParams *__r
       const int coarsest = idle ? 0 : (multadd ? q : q + 1);
       for (int l = 0; l < coarsest; l++) {
          if (l < L - 1) {
-            spmv_team<false, false>(p.R[l], v.r[l], v.r[l + 1], mk(1.0, 0.0, nullptr), tm.tid, tm.size, false, tm.smem);
+            AMGB_TEAM_SPMV(false, p.R[l], v.r[l], v.r[l + 1], mk(1.0, 0.0, nullptr), tm);
             group_barrier(tm);
          }
       }
@@ -67,15 +68,15 @@ __global__ void __launch_bounds__(kABlock, 3) k_async_amg(const AsyncParams *__r
          // AFACx (:153-206): u_c = S_{q+1} r_{q+1}; e = P u_c; r_f = r_q - A_q e; u_f = S_q r_f
          const int cl = q + 1;
          team_smooth_zero(p, tm, cl, v.r[cl], v.t[cl], v.w[cl], p.coarse_sweeps, false);
-         spmv_team<false, false>(p.P[q], v.t[cl], v.t[q], mk(1.0, 0.0, nullptr), tm.tid, tm.size, false, tm.smem);
+         AMGB_TEAM_SPMV(false, p.P[q], v.t[cl], v.t[q], mk(1.0, 0.0, nullptr), tm);
          group_barrier(tm);
-         spmv_team<false, false>(p.A[q], v.t[q], v.w[q], mk(-1.0, 1.0, v.r[q]), tm.tid, tm.size, false, tm.smem);
+         AMGB_TEAM_SPMV(false, p.A[q], v.t[q], v.w[q], mk(-1.0, 1.0, v.r[q]), tm);
          group_barrier(tm);
          team_smooth_zero(p, tm, q, v.w[q], v.e[q], v.t[q], p.fine_sweeps, false);
       }
       // ---- prolongation chain (:211-224)
       for (int l = idle ? -1 : q - 1; l >= 0; l--) {
-         spmv_team<false, false>(p.P[l], v.e[l + 1], v.e[l], mk(1.0, 0.0, nullptr), tm.tid, tm.size, false, tm.smem);
+         AMGB_TEAM_SPMV(false, p.P[l], v.e[l + 1], v.e[l], mk(1.0, 0.0, nullptr), tm);
          group_barrier(tm);
       }
       // ---- u += e (atomic), private copy (:285-301)
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(kABlock, 3) k_async_amg(const AsyncParams *__r
       __syncthreads();
       const int stop = s_stop;
       // ---- private residual from the private copy (:338-351)
-      if (!idle) spmv_team<false, false>(p.A[0], v.u_local, v.r[0], mk(-1.0, 1.0, p.f), tm.tid, tm.size, false, tm.smem);
+      if (!idle) AMGB_TEAM_SPMV(false, p.A[0], v.u_local, v.r[0], mk(-1.0, 1.0, p.f), tm);
       group_barrier(tm);
       if (stop) break;
    }
@@ -154,6 +155,15 @@ int launch_async(const LaunchCfg &, cudaStream_t st, const AsyncParams *params_d
    cfg.numAttrs = na;
    cudaError_t e = cudaLaunchKernelEx(&cfg, k_async_amg, params_dev);
    return e == cudaSuccess ? 1 : -(int)e;
+}
+
+#ifndef AMGB_ASYNC_KERNEL_ONLY   // (async_ni.cu re-includes this file for the kernel and its two launch helpers only)
+// EXPERIMENTAL switch AMGB_ASYNC_NOINLINE=1: run k_async_amg_ni (async_ni.cu), the same kernel with every SpMV behind a
+// non-inlined call (code size 60 616 -> a few thousand instructions, profiles/README.md section 9)
+static bool async_noinline()
+{
+   const char *e = getenv("AMGB_ASYNC_NOINLINE");
+   return e && atoi(e) != 0;
 }
 
 // ---- host side: build the parameter block once, run ---------------------------------------------
@@ -219,7 +229,7 @@ static int async_prepare(amgb_ctx *c)
       work[k] = w;
       tot += w;
    }
-   int grid = fact0 ? async_max_grid_fact0(kABlock) : async_max_grid(kABlock);
+   int grid = fact0 ? async_max_grid_fact0(kABlock) : (async_noinline() ? async_max_grid_ni(kABlock) : async_max_grid(kABlock));
    if (grid < L) return amgb_fail(c, AMGB_ECUDA, "cooperative grid %d smaller than the number of levels %d", grid, L);
    std::vector<int> ctas(L, 1);
    int left = grid - L;
@@ -305,8 +315,8 @@ extern "C" int amgb_solve_async(amgb_ctx *c, int num_cycles, int converge_type, 
    const bool fact0 = L > 1 && hp.t0[1] != nullptr;
    int lr = fact0 ? launch_async_fact0(c->cfg, c->stream, (const AsyncParams *)c->async_params_dev, c->async_grid, kABlock,
                                        c->window_valid ? &c->window : nullptr)
-                  : launch_async(c->cfg, c->stream, (const AsyncParams *)c->async_params_dev, c->async_grid, kABlock,
-                                 c->window_valid ? &c->window : nullptr);
+                  : (async_noinline() ? launch_async_ni : launch_async)(c->cfg, c->stream, (const AsyncParams *)c->async_params_dev,
+                                                                        c->async_grid, kABlock, c->window_valid ? &c->window : nullptr);
    if (lr < 0) return amgb_fail(c, AMGB_ECUDA, "cooperative launch failed: %s", cudaGetErrorString((cudaError_t)(-lr)));
    c->launches += 1;
    CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));
@@ -336,3 +346,4 @@ extern "C" int amgb_async_groups(amgb_ctx *c, int *cta_begin /* num_levels+1 */,
    if (grid) *grid = c->async_grid;
    return AMGB_OK;
 }
+#endif   // AMGB_ASYNC_KERNEL_ONLY

@@ -4,6 +4,12 @@
 #include "ctx.h"
 #include "kernels.cuh"
 
+// every SpMV of the persistent kernels goes through this macro: the default expands to the inlined spmv_team (the measured
+// round-1 kernels); async_ni.cu redefines it to a non-inlined call to keep the kernel's code inside the instruction cache
+#ifndef AMGB_TEAM_SPMV
+#define AMGB_TEAM_SPMV(SVAL, M, x, y, e, tm) spmv_team<false, SVAL>(M, x, y, e, (tm).tid, (tm).size, false, (tm).smem)
+#endif
+
 namespace {
 
 constexpr int kABlock = 256;
@@ -90,12 +96,12 @@ __device__ void team_smooth_zero(const AsyncParams &p, const Team &tm, int l, co
    }
    const double *rs = (p.smoother == AMGB_SMOOTH_L1_JACOBI) ? p.inv_l1[l] : p.ws[l];
    if (symmetric) {
-      spmv_team<false, true>(A, f, e, mk(-1.0, 2.0, f, 0.0, nullptr, rs), tm.tid, tm.size, false, tm.smem);
+      AMGB_TEAM_SPMV(true, A, f, e, mk(-1.0, 2.0, f, 0.0, nullptr, rs), tm);
       group_barrier(tm);
       for (int k = 1; k < sweeps; k++) {
-         spmv_team<false, false>(A, e, s1, mk(-1.0, 1.0, f), tm.tid, tm.size, false, tm.smem);
+         AMGB_TEAM_SPMV(false, A, e, s1, mk(-1.0, 1.0, f), tm);
          group_barrier(tm);
-         spmv_team<false, true>(A, s1, e, mk(-1.0, 2.0, s1, 0.0, nullptr, rs), tm.tid, tm.size, false, tm.smem);
+         AMGB_TEAM_SPMV(true, A, s1, e, mk(-1.0, 2.0, s1, 0.0, nullptr, rs), tm);
          group_barrier(tm);
       }
       return;
@@ -105,7 +111,7 @@ __device__ void team_smooth_zero(const AsyncParams &p, const Team &tm, int l, co
    for (int i = tm.tid; i < n; i += tm.size) cur[i] = __ldg(rs + i) * ld_cg(f + i);
    group_barrier(tm);
    for (int k = 1; k < sweeps; k++) {
-      spmv_team<false, false>(A, cur, oth, mk(-1.0, 1.0, f, 1.0, cur, rs), tm.tid, tm.size, false, tm.smem);
+      AMGB_TEAM_SPMV(false, A, cur, oth, mk(-1.0, 1.0, f, 1.0, cur, rs), tm);
       group_barrier(tm);
       double *tmp = cur; cur = oth; oth = tmp;
    }

@@ -100,3 +100,7 @@ int async_max_grid(int block);
 int launch_async_fact0(const LaunchCfg &cfg, cudaStream_t st, const AsyncParams *params_dev, int grid, int block,
                        const cudaAccessPolicyWindow *window);
 int async_max_grid_fact0(int block);
+// experimental copy with every SpMV behind a non-inlined call (async_ni.cu; AMGB_ASYNC_NOINLINE=1)
+int launch_async_ni(const LaunchCfg &cfg, cudaStream_t st, const AsyncParams *params_dev, int grid, int block,
+                    const cudaAccessPolicyWindow *window);
+int async_max_grid_ni(int block);

@@ -1,5 +1,6 @@
 """A/B of the persistent asynchronous kernel: explicit level-0 products (k_async_amg, the measured round-1 kernel) against the
-factorised level-0 transfers (k_async_amg_fact0, experimental).  python tools/async_fact0_time.py --n 256 --corrections 40"""
+factorised level-0 transfers (k_async_amg_fact0, experimental) and against the same kernel with non-inlined SpMV calls
+(k_async_amg_ni, AMGB_ASYNC_NOINLINE=1, experimental: code size).  python tools/async_fact0_time.py --n 256 --corrections 40"""
 import argparse
 import json
 import os
@@ -23,7 +24,8 @@ def main():
     h = H.amg_setup(A)
     b = H.rand_rhs(A.nrows)
     out = {"n": a.n, "rows": h.n, "corrections": a.corrections}
-    for tag, fact in (("explicit", False), ("factorised", True)):
+    for tag, fact in (("explicit", False), ("explicit_noinline", False), ("factorised", True)):
+        os.environ["AMGB_ASYNC_NOINLINE"] = "1" if tag == "explicit_noinline" else "0"
         hh = H.Hierarchy(h.A, h.P_plain)
         hh.cpts = h.cpts
         hh.build_transfers(H.MULTADD, a.w, factor_level0=fact)
