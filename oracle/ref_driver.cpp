@@ -263,6 +263,11 @@ static void fill(hypre_CSRMatrix *m, const RefCSR &s)
    m->rownnz = nullptr; m->num_rownnz = s.nrows;
 }
 
+// ONE_LEVEL thread partition for the next ref_create whatever the solver: reaches SMEM_Sync_Parfor_AFACx_Vcycle
+// (src/SMEM_Sync_AMG.cpp:296-406), which SMEM_Main.cpp:641-649 never selects for AFACX (it always takes ALL_LEVELS)
+static int g_force_one_level = 0;
+extern "C" void ref_force_one_level(int v) { g_force_one_level = v; }
+
 extern "C" {
 
 // threads_per_level[L]: BALANCED_THREADS result (caller).  thread_part_type is chosen as
@@ -300,7 +305,7 @@ void *ref_create(int L, const RefCSR *A, const RefCSR *P, const RefCSR *R, doubl
    ad->input.construct_R_flag = 1;
    ad->input.print_reshist_flag = 1;
    ad->input.format_output_flag = 1;
-   ad->input.thread_part_type = (solver == MULT || solver == BPX || solver == PAR_BPX) ? ONE_LEVEL : ALL_LEVELS;
+   ad->input.thread_part_type = (g_force_one_level || solver == MULT || solver == BPX || solver == PAR_BPX) ? ONE_LEVEL : ALL_LEVELS;
    ad->cheby.mu = 1.0; ad->cheby.delta = 1.0;
 
    ad->grid.num_levels = L;

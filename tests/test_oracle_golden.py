@@ -343,6 +343,28 @@ def test_par_bpx_matches_reference_fixture(name):
         H.par_bpx_equivalent(H.L1_JACOBI, 0.6)
 
 
+def test_parfor_afacx_cycle_matches_live_reference():
+    """SMEM_Sync_Parfor_AFACx_Vcycle (src/SMEM_Sync_AMG.cpp:296-406): the omp-for form of AFACx, which the
+    reference's driver never selects (AFACX always gets the ALL_LEVELS partition, src/SMEM_Main.cpp:641-649) -- reached here by
+    forcing ONE_LEVEL in the object-code driver; 4 threads, deterministic; equals the oracle's AFACx history"""
+    if O.ref_lib() is None:
+        pytest.skip("oracle/_ref not built here")
+    A = H.laplacian("7pt", 10)
+    h = H.amg_setup(A)
+    b = H.rand_rhs(A.nrows)
+    h.build_transfers(H.AFACX, 0.6)
+    O.ref_lib().ref_force_one_level(1)
+    try:
+        for sweeps in (1, 2):
+            rs = O.RefSolver(h, H.AFACX, H.JACOBI, b, 0.6, num_threads=4, fine_sweeps=sweeps, coarse_sweeps=sweeps)
+            out = rs.solve(40, 1e-9, async_type=0)
+            rs.close()
+            _, hist, _ = O.Problem(h, H.AFACX, H.JACOBI, 0.6, fine_sweeps=sweeps, coarse_sweeps=sweeps).solve_sync(b, 1e-9, 40)
+            _close_hist(hist, out["hist"])
+    finally:
+        O.ref_lib().ref_force_one_level(0)
+
+
 def test_async_gauss_seidel_smoothers_match_live_reference():
     """SMEM_Async_GaussSeidel / SMEM_SemiAsync_GaussSeidel (src/SMEM_Smooth.cpp:445-502) inside Multadd, the
     reference's object code with one thread per level: the chaotic sweep over a single row range IS Gauss-Seidel = the oracle's
