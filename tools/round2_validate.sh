@@ -8,3 +8,8 @@ export AMGB_EXPERIMENTAL=1
 timeout 300 python -m pytest tests/test_zz_gpu_extended.py tests/test_gpu_dist.py -m gpu -q -k "device_smooth_transfer or async_factorised or graph_captured or nonsymmetric or hybrid_jgs_single_block or async_noinline or afacx_two_sweeps"
 timeout 300 python tools/async_fact0_time.py --n 256 --corrections 40
 timeout 200 python tools/iebpx_time.py --n 256
+# 3. one ncu capture of the persistent asynchronous kernel (never captured in round 1): is it starved for instructions?
+#    (60 616 SASS instructions, profiles/README.md section 9) -- read smsp__warp_issue_stalled_no_instruction*, 
+#    l1tex__data_pipe_lsu_wavefronts*, dram__bytes_* from the report here with `ncu -i ... --page raw --csv`
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:k_async_amg -c 2 -f -o gpurun_out/prof_r2_async \
+   python tools/async_fact0_time.py --n 128 --corrections 10 --reps 1 > gpurun_out/prof_r2_async.log 2>&1 || true
