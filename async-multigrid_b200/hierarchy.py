@@ -256,6 +256,63 @@ def rand_rhs(n, lo=-1.0, hi=1.0, seed=0):
     return b
 
 
+def rand_rhs_dmem(row_starts):
+    """DMEM RHS: EVERY rank seeds srand(0) and draws its local rows from RandDouble(-.5, .5)
+    (src/DMEM_Setup.cpp:1293,1351), so the global b is the same glibc sequence repeated per rank and depends on the number of
+    ranks.  row_starts: the P + 1 row offsets of the partition."""
+    parts = [rand_rhs(int(row_starts[p + 1] - row_starts[p]), -0.5, 0.5, 0) for p in range(len(row_starts) - 1)]
+    return np.concatenate(parts) if parts else np.empty(0)
+
+
+def max_eig_estimate_cg(A, iters=20, seed=1):
+    """Largest / smallest eigenvalue estimate of D^-1/2 A D^-1/2 (= those of D^-1 A) from `iters` CG steps: the Lanczos
+    tridiagonal of the CG coefficients, as hypre_ParCSRMaxEigEstimateCG(A, scale = 1, max_iter, ...) computes them (hypre
+    par_relax_more.c; hypre is un-vendored, so this follows the published algorithm: right-hand side 0, random start vector,
+    T_jj = 1/alpha_j + beta_{j-1}/alpha_{j-1}, T_j,j+1 = sqrt(beta_j)/alpha_j).  The start vector comes from a
+    Park-Miller generator like hypre_Rand's; PARITY UNPINNED -- the estimate depends on it in the third digit.
+    -> (max_eig, min_eig)"""
+    S = A.to_scipy().tocsr()
+    n = S.shape[0]
+    d = np.asarray(A.diagonal(), dtype=np.float64)
+    ds = 1.0 / np.sqrt(np.abs(d))
+    x = np.empty(n)
+    st = int(seed) % 2147483647 or 1
+    for i in range(n):                       # minimal-standard LCG: a = 16807, m = 2^31 - 1, value 2 s / m - 1
+        st = (16807 * st) % 2147483647
+        x[i] = 2.0 * st / 2147483647.0 - 1.0
+    r = -(ds * (S @ (ds * x)))                # r = 0 - B x
+    p = r.copy()
+    gamma = float(r @ r)
+    diag, off = [], []
+    alpha_old, beta = 1.0, 0.0
+    for j in range(iters):
+        if gamma == 0.0:
+            break
+        s_ = ds * (S @ (ds * p))
+        sdotp = float(s_ @ p)
+        if sdotp == 0.0:
+            break
+        alpha = gamma / sdotp
+        diag.append(1.0 / alpha + (beta / alpha_old if j > 0 else 0.0))
+        x += alpha * p
+        r -= alpha * s_
+        gamma_old, gamma = gamma, float(r @ r)
+        beta = gamma / gamma_old
+        off.append(np.sqrt(beta) / alpha)
+        p = r + beta * p
+        alpha_old = alpha
+    k = len(diag)
+    T = np.diag(diag) + np.diag(off[:k - 1], 1) + np.diag(off[:k - 1], -1)
+    ev = np.linalg.eigvalsh(T)
+    return float(ev[-1]), float(ev[0])
+
+
+def dmem_default_smooth_weight(A, iters=20):
+    """DMEM's default Jacobi weight: 1 / lambda_max(D^-1 A) from 20 CG steps (src/DMEM_Setup.cpp:77-87,
+    -eig_CG_max_iters; off when -smooth_weight is given, src/DMEM_Main.cpp:443-447)"""
+    return 1.0 / max_eig_estimate_cg(A, iters)[0]
+
+
 class Hierarchy:
     """Per-level A (diag-first), P (plain), and the transfer operators the selected cycle
     uses: for MULTADD P̄ = G P and R̄ = Pᵀ GT (SMEM_Setup.cpp:244-260,1173-1254); for

@@ -189,3 +189,23 @@ def test_tiled_renumbering_is_the_same_hierarchy():
     u2, hist2, _ = O.Problem(h2, H.MULTADD, H.JACOBI, 0.9).solve_sync(b2, 1e-9, 100)
     assert len(hist) == len(hist2) and np.max(np.abs(hist - hist2)) <= 1e-13
     assert np.max(np.abs(u2[p0] - u)) <= 1e-12 * np.max(np.abs(u))
+
+
+def test_dmem_driver_defaults_rhs_and_jacobi_weight():
+    """host side of the DMEM driver's defaults (SURVEY.md 5.9j,k): per-rank srand(0) right-hand side and the Jacobi weight
+    1 / lambda_max(D^-1 A) from 20 CG steps (hypre's estimator restated from its published algorithm -- parity unpinned)"""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as sla
+    b = H.rand_rhs_dmem([0, 5, 9, 9, 12])
+    one = H.rand_rhs(5, -0.5, 0.5)
+    assert np.array_equal(b[:5], one) and np.array_equal(b[5:9], one[:4]) and np.array_equal(b[9:], one[:3])
+    assert np.all(np.abs(b) <= 0.5)
+    for prob, n in (("7pt", 10), ("5pt", 24), ("27pt", 7)):
+        A = H.laplacian(prob, n)
+        hi, lo = H.max_eig_estimate_cg(A, 20)
+        d = A.diagonal()
+        B = sp.diags(1 / np.sqrt(d)) @ A.to_scipy().tocsr() @ sp.diags(1 / np.sqrt(d))
+        true = sla.eigsh(B, k=1, which="LA", return_eigenvectors=False)[0]
+        assert lo > 0 and hi <= true * (1 + 1e-12) and hi >= 0.97 * true          # Ritz values lie inside the spectrum
+        w = H.dmem_default_smooth_weight(A)
+        assert abs(w - 1.0 / hi) < 1e-15 and 0.4 < w < 1.0
