@@ -511,13 +511,20 @@ int orc_solve_sync(const orc_problem *pb, const double *f, double *u, double tol
  * DMEM_Add's asynchronous loop, src/DMEM_Add.cpp:101-130, grid after grid -- AddCycle :180-329 + DMEM_AddSmooth
  * src/DMEM_Smooth.cpp:574-638 -- which the reference's object code pins, tests/test_oracle_golden.py).
  * counts[l] = corrections. */
-int orc_solve_async_sequential(const orc_problem *pb, const double *f, double *u, int num_cycles,
-                               int *counts, double *final_relres)
+static int async_sequential(const orc_problem *pb, const double *f, double *u, int num_cycles, int *counts, double *final_relres,
+                            int read_res)
 {
    const int L = pb->num_levels, n0 = pb->A[0].nrows;
    orc_work *w = work_alloc(pb);
    orc_residual(&pb->A[0], f, u, w->r[0]);
    const double r0 = orc_norm2(w->r[0], n0);
+   /* -read_type res: per-level accumulators of the corrections (level_vector[q].f[0]) */
+   double **facc = NULL, *ye = NULL;
+   if (read_res) {
+      facc = (double **)malloc(sizeof(double *) * L);
+      for (int q = 0; q < L; q++) facc[q] = (double *)calloc((size_t)n0, sizeof(double));
+      ye = (double *)malloc(sizeof(double) * (size_t)n0);
+   }
    for (int k = 0; k < num_cycles; k++)
       for (int q = 0; q < L; q++) {
          /* restriction chain: down to the group's level (Multadd) or one level further (AFACx), :84-108 */
@@ -528,13 +535,42 @@ int orc_solve_async_sequential(const orc_problem *pb, const double *f, double *u
          orc_level_correction(pb, w, q);
          for (int inner = q; inner > 0; inner--)
             orc_matvec(&pb->P[inner - 1], w->e[inner], w->e[inner - 1], 0, pb->P[inner - 1].nrows);
-         for (int i = 0; i < n0; i++) u[i] += w->e[0][i];
          counts[q]++;
-         orc_residual(&pb->A[0], f, u, w->r[0]);
+         if (read_res) {
+            /* :227-236, :288-293: y = A_0 e; f_q += e; r -= y (the shared residual is maintained incrementally and u is
+             * assembled only at the end) */
+            orc_matvec(&pb->A[0], w->e[0], ye, 0, n0);
+            for (int i = 0; i < n0; i++) { facc[q][i] += w->e[0][i]; w->r[0][i] -= ye[i]; }
+         } else {
+            for (int i = 0; i < n0; i++) u[i] += w->e[0][i];
+            orc_residual(&pb->A[0], f, u, w->r[0]);
+         }
       }
+   if (read_res) {
+      /* :416-426: u += sum over the levels of their accumulated corrections, level after level */
+      for (int q = 0; q < L; q++) {
+         for (int i = 0; i < n0; i++) u[i] += facc[q][i];
+         free(facc[q]);
+      }
+      free(facc); free(ye);
+      orc_residual(&pb->A[0], f, u, w->r[0]);      /* SMEM_Solve's final residual, src/SMEM_Solve.cpp:82-91 */
+   }
    *final_relres = orc_norm2(w->r[0], n0) / r0;
    work_free(w);
    return 0;
+}
+
+int orc_solve_async_sequential(const orc_problem *pb, const double *f, double *u, int num_cycles,
+                               int *counts, double *final_relres)
+{
+   return async_sequential(pb, f, u, num_cycles, counts, final_relres, 0);
+}
+
+/* the same with `-read_type res` (READ_RES, FULL_ASYNC, local residual computation): src/SMEM_Async_AMG.cpp:227-236,285-296,416-426 */
+int orc_solve_async_sequential_res(const orc_problem *pb, const double *f, double *u, int num_cycles,
+                                   int *counts, double *final_relres)
+{
+   return async_sequential(pb, f, u, num_cycles, counts, final_relres, 1);
 }
 
 /* DMEM's accelerated synchronous additive solve: DMEM_SyncAddCorrect + DMEM_ChebyUpdate

@@ -151,12 +151,14 @@ class Problem:
                                    C.c_double(mu), C.c_double(delta), dptr(hist), C.byref(er), C.byref(rr))
         return dict(x=x, iters=it, ext_hist=hist[:it], ext_relres=er.value, relres=rr.value)
 
-    def solve_async_sequential(self, f, num_cycles):
+    def solve_async_sequential(self, f, num_cycles, read_res=False):
+        """read_res: `-read_type res` (the shared residual is updated incrementally, u is assembled at the end)"""
         u = np.zeros(self.h.n[0])
         counts = np.zeros(self.h.num_levels, dtype=np.int32)
         rr = C.c_double(0)
-        lib().orc_solve_async_sequential(C.byref(self.c), dptr(np.ascontiguousarray(f)), dptr(u), num_cycles,
-                                         iptr(counts), C.byref(rr))
+        fn = lib().orc_solve_async_sequential_res if read_res else lib().orc_solve_async_sequential
+        fn.argtypes = [C.POINTER(OrcProblem), DP, DP, C.c_int, IP, DP]
+        fn(C.byref(self.c), dptr(np.ascontiguousarray(f)), dptr(u), num_cycles, iptr(counts), C.byref(rr))
         return u, counts, rr.value
 
 

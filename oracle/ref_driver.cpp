@@ -267,6 +267,9 @@ static void fill(hypre_CSRMatrix *m, const RefCSR &s)
 // (src/SMEM_Sync_AMG.cpp:296-406), which SMEM_Main.cpp:641-649 never selects for AFACX (it always takes ALL_LEVELS)
 static int g_force_one_level = 0;
 extern "C" void ref_force_one_level(int v) { g_force_one_level = v; }
+// -read_type for the next ref_create (READ_SOL is the reference's default, src/SMEM_Main.cpp:93)
+static int g_read_type = READ_SOL;
+extern "C" void ref_set_read_type(int v) { g_read_type = v; }
 
 extern "C" {
 
@@ -300,7 +303,7 @@ void *ref_create(int L, const RefCSR *A, const RefCSR *P, const RefCSR *R, doubl
    ad->input.smoother = smoother;
    ad->input.smooth_interp_type = JACOBI;
    ad->input.solver = solver;
-   ad->input.read_type = READ_SOL;
+   ad->input.read_type = g_read_type;
    ad->input.delay_type = DELAY_NONE;
    ad->input.construct_R_flag = 1;
    ad->input.print_reshist_flag = 1;

@@ -433,6 +433,35 @@ def test_async_single_group_matches_live_reference():
             assert abs(rel - out["relres"]) <= 1e-13
 
 
+def test_async_read_res_mode_matches_live_reference():
+    """`-read_type res` of SMEM_Async_Add_AMG (src/SMEM_Async_AMG.cpp:227-236,285-296,416-426): the shared residual is updated
+    incrementally (r -= A_0 e) and u is assembled from the per-level accumulators at the end -- bit for bit on two levels"""
+    if O.ref_lib() is None:
+        pytest.skip("oracle/_ref not built here")
+    if O.ref_lib().ref_max_threads() < 2:
+        pytest.skip("needs two cores (one spinning thread per level)")
+    A = H.laplacian("7pt", 10)
+    h = H.amg_setup(A, max_levels=2)
+    b = H.rand_rhs(A.nrows)
+    O.ref_lib().ref_set_read_type(1)
+    try:
+        for tag, solver, base, w, sweeps in _ASYNC_CASES:
+            h.build_transfers(base, w)
+            for K in (1, 3, 20):
+                rs = O.RefSolver(h, solver, H.JACOBI, b, w, one_thread_per_level=True, fine_sweeps=sweeps, coarse_sweeps=sweeps)
+                out = rs.solve(K, 1e-9, async_type=0)
+                rs.close()
+                pb = O.Problem(h, base, H.JACOBI, w, fine_sweeps=sweeps, coarse_sweeps=sweeps)
+                u, counts, rel = pb.solve_async_sequential(b, K, read_res=True)
+                assert list(out["corrections"]) == list(counts) == [K, K]
+                assert np.max(np.abs(u - out["u"])) <= 1e-14 * np.max(np.abs(u)), (tag, K)
+                assert abs(rel - out["relres"]) <= 1e-13
+                u2, _, _ = pb.solve_async_sequential(b, K)          # READ_SOL: the same iterate up to rounding
+                assert np.max(np.abs(u - u2)) <= 1e-12 * np.max(np.abs(u))
+    finally:
+        O.ref_lib().ref_set_read_type(0)
+
+
 # ---- ChebySetup / EigsPower / BPXCycle (src/SMEM_Cheby.cpp), SURVEY.md row a17 ------------------------------------------------
 _CHEBY_SETUP_CASES = (("j", H.JACOBI, 0.8), ("l1", H.L1_JACOBI, 0.8), ("hjgs", H.HYBRID_JACOBI_GAUSS_SEIDEL, 1.0))
 
