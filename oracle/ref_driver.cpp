@@ -1066,5 +1066,5 @@ int ref_read_matrix(const char *path, int symm_flag, int *nrows, int *nnz, int *
    return 0;
 }
 void ref_free(void *p) { free(p); }
-int ref_max_threads(void) { return omp_get_max_threads(); }
+int ref_max_threads(void) { return omp_get_num_procs(); }   // (omp_get_max_threads follows the last omp_set_num_threads of a solve)
 }
