@@ -13,6 +13,8 @@ CXX="g++ -O3 -fopenmp -fPIC -w -I$HERE/ref_shim -I$REF -include $HERE/ref_shim/r
 for f in SMEM_MatVec SMEM_Smooth SMEM_Sync_AMG SMEM_Async_AMG SMEM_ExtendedSystem SMEM_Cheby SEQ_MatVec SEQ_Smooth SEQ_AMG Misc DMEM_Mult DMEM_Misc DMEM_Add DMEM_Smooth; do
    $CXX -c "$REF/$f.cpp" -o "$OUT/$f.o"
 done
+# SMEM_Setup.cpp (SmoothTransfer, the thread partition, the work model): Eigen is un-vendored -- oracle/ref_shim/eigen_stub stands in
+$CXX -I"$HERE/ref_shim/eigen_stub" -c "$REF/SMEM_Setup.cpp" -o "$OUT/SMEM_Setup.o"
 # SMEM_Solve.cpp: its printf (residual history, src/SMEM_Solve.cpp:95-103,232-239) goes to the hook
 $CXX -c "$HERE/ref_shim/wrap_SMEM_Solve.cpp" -o "$OUT/SMEM_Solve.o"
 $CXX -c "$HERE/ref_driver.cpp" -o "$OUT/ref_driver.o"

@@ -376,6 +376,34 @@ def ref_cheby_setup(h, b, smoother, smooth_weight, iters=20, num_sweeps=1, num_t
     return dict(alpha=out[0], beta=out[1], mu=out[2], delta=out[3], f_after=fa)
 
 
+def ref_smooth_transfer(A, P, smooth_weight, smooth_interp_type=0, num_pre=1, num_post=1, num_threads=2):
+    """SmoothTransfer (src/SMEM_Setup.cpp:1173-1254, + EigenMatMat / CSR_Transpose / StdVector_to_CSR), the reference's object code
+    compiled against an Eigen stand-in, for one level -> (Pbar or None, Rbar or None) as hierarchy.CSR"""
+    L = ref_lib()
+    hier = _pkg.hierarchy
+    a, p = c_csr(A), c_csr(P)
+    l1 = np.ascontiguousarray(np.add.reduceat(np.abs(A.data), A.indptr[:-1]) if A.nnz else np.zeros(A.nrows))
+    oP, oR = OrcCSR(), OrcCSR()
+    L.ref_smooth_transfer.restype = C.c_int
+    L.ref_smooth_transfer.argtypes = [C.POINTER(OrcCSR), C.POINTER(OrcCSR), DP, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.POINTER(OrcCSR), C.POINTER(OrcCSR)]
+    L.ref_smooth_transfer(C.byref(a), C.byref(p), dptr(l1), smooth_weight, smooth_interp_type, num_pre, num_post, num_threads,
+                          C.byref(oP), C.byref(oR))
+    L.ref_free.argtypes = [C.c_void_p]
+
+    def take(o):
+        if o.nrows < 0:
+            return None
+        n, nnz = o.nrows, o.nnz
+        ip = np.ctypeslib.as_array(o.i, shape=(n + 1,)).copy()
+        ix = np.ctypeslib.as_array(o.j, shape=(nnz,)).copy()
+        va = np.ctypeslib.as_array(o.data, shape=(nnz,)).copy()
+        for ptr in (o.i, o.j, o.data):
+            L.ref_free(C.cast(ptr, C.c_void_p))
+        return hier.CSR(n, o.ncols, ip, ix, va)
+    return take(oP), take(oR)
+
+
 def ref_dmem_cheby_update(d, u, cycle, mu, delta, c, c_prev, accel_type=1):
     """DMEM_ChebyUpdate (src/DMEM_Misc.cpp:612-666), synchronous branch, in place on copies -> (d, u, c, c_prev)"""
     L = ref_lib()

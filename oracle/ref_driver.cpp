@@ -243,6 +243,36 @@ HYPRE_Int HYPRE_IJMatrixGetObject(HYPRE_IJMatrix m, void **object) { *object = &
 
 struct RefCSR { int nrows, ncols, nnz; int *i; int *j; double *data; };
 
+// hypre csr_matop.c: hypre_CSRMatrixTranspose (published algorithm: count the columns, prefix sum, scatter rows in order), as
+// far as src/SMEM_Setup.cpp:253,268 uses it (explicit R = P^T for the solvers with plain transfers).  A row of AT lists the
+// rows of A in ascending order.
+HYPRE_Int hypre_CSRMatrixTranspose(hypre_CSRMatrix *A, hypre_CSRMatrix **AT, HYPRE_Int data)
+{
+   const int m = A->num_rows, n = A->num_cols, nnz = A->i[m];
+   hypre_CSRMatrix *T = (hypre_CSRMatrix *)calloc(1, sizeof(hypre_CSRMatrix));
+   T->num_rows = n; T->num_cols = m; T->num_nonzeros = nnz; T->num_rownnz = n;
+   T->i = (HYPRE_Int *)calloc((size_t)n + 1, sizeof(HYPRE_Int));
+   T->j = (HYPRE_Int *)calloc((size_t)nnz, sizeof(HYPRE_Int));
+   T->data = data ? (HYPRE_Real *)calloc((size_t)nnz, sizeof(HYPRE_Real)) : nullptr;
+   for (int p = 0; p < nnz; p++) T->i[A->j[p] + 1]++;
+   for (int c = 0; c < n; c++) T->i[c + 1] += T->i[c];
+   std::vector<int> next(T->i, T->i + n);
+   for (int r = 0; r < m; r++)
+      for (int p = A->i[r]; p < A->i[r + 1]; p++) {
+         const int q = next[A->j[p]]++;
+         T->j[q] = r;
+         if (data) T->data[q] = A->data[p];
+      }
+   *AT = T;
+   return 0;
+}
+
+// named by SMEM_BuildMatrix (src/SMEM_Setup.cpp:1600-1660), which the driver never calls; src/Laplacian.cpp does not compile here (its 3-D
+// half needs hypre's GenerateLaplacian)
+void Laplacian_2D_5pt(HYPRE_IJMatrix *, int) { abort(); }
+// src/SMEM_Setup.cpp (compiled unmodified against oracle/ref_shim/eigen_stub: Eigen is un-vendored)
+void SmoothTransfer(AllData *all_data, hypre_CSRMatrix *P, hypre_CSRMatrix *R, int level);
+
 struct RefHandle {
    AllData all;
    std::vector<hypre_CSRMatrix> A, P, R;
@@ -1011,6 +1041,40 @@ int ref_cheby_setup(int L, const RefCSR *A, const RefCSR *P, double *const *l1, 
    const int ok = (ad->cheby.omega != nullptr);
    delete ad;
    return ok ? 0 : 1;
+}
+
+// SmoothTransfer (src/SMEM_Setup.cpp:1173-1254: G = I - w D^-1 A / GT = I - w A D^-1 on A's pattern, or their L1 forms; Pbar = G P,
+// Rbar = P^T GT through EigenMatMat :1256-1339 and the row layout of StdVector_to_CSR :1372-1424), the reference's object code,
+// for ONE level: A (diag first), plain P (hypre's R_array is P as well).  out_P / out_R borrow arrays the reference malloc'ed
+// (ref_free them); an output the reference leaves untouched (sweeps == 0) comes back with nrows = -1.
+int ref_smooth_transfer(const RefCSR *A, const RefCSR *P, double *l1, double smooth_weight, int smooth_interp_type, int num_pre,
+                        int num_post, int num_threads, RefCSR *out_P, RefCSR *out_R)
+{
+   AllData *ad = new AllData();
+   memset((void *)&ad->input, 0, sizeof(ad->input));
+   memset((void *)&ad->matrix, 0, sizeof(ad->matrix));
+   hypre_CSRMatrix hA, hP;
+   fill(&hA, *A); fill(&hP, *P);
+   hypre_CSRMatrix *Aarr[1] = {&hA};
+   hypre_CSRMatrix *Parr[1] = {(hypre_CSRMatrix *)calloc(1, sizeof(hypre_CSRMatrix))};
+   hypre_CSRMatrix *Rarr[1] = {(hypre_CSRMatrix *)calloc(1, sizeof(hypre_CSRMatrix))};
+   double *l1arr[1] = {l1};
+   ad->matrix.A = Aarr; ad->matrix.P = Parr; ad->matrix.R = Rarr; ad->matrix.L1_row_norm = l1arr;
+   ad->input.smooth_weight = smooth_weight;
+   ad->input.smooth_interp_type = smooth_interp_type;
+   ad->input.num_pre_smooth_sweeps = num_pre;
+   ad->input.num_post_smooth_sweeps = num_post;
+   ad->input.num_threads = num_threads;
+   Parr[0]->num_rows = -1; Rarr[0]->num_rows = -1;
+   omp_set_num_threads(num_threads);
+   SmoothTransfer(ad, &hP, &hP, 0);
+   auto give = [](hypre_CSRMatrix *m, RefCSR *o) {
+      o->nrows = m->num_rows; o->ncols = m->num_cols; o->nnz = m->num_nonzeros; o->i = m->i; o->j = m->j; o->data = m->data;
+      free(m);
+   };
+   give(Parr[0], out_P); give(Rarr[0], out_R);
+   delete ad;
+   return 0;
 }
 
 void ref_destroy(void *h) { delete (RefHandle *)h; }

@@ -1,0 +1,23 @@
+/* BuildHypreMatrix.hpp -- TEST INFRASTRUCTURE.  src/SMEM_Setup.cpp:10 includes a header of this name which the reference repository
+ * does not contain.  This stand-in declares what that translation unit names beyond oracle/ref_shim/hypre_stub.h:
+ * hypre's set-up interface (HYPRE_BoomerAMG*, HYPRE_IJVector*: un-vendored, never reached by the driver -- they abort) and
+ * hypre_CSRMatrixTranspose (functional, oracle/ref_driver.cpp).  Only SmoothTransfer / EigenMatMat / CSR_Transpose /
+ * StdVector_to_CSR / ComputeWork / PartitionLevels / PartitionGrids of SMEM_Setup.cpp are ever called. */
+#ifndef AMG_REF_SETUP_STUB_H
+#define AMG_REF_SETUP_STUB_H
+#include <stdlib.h>
+#define AMG_REF_NEVER3(name) template <class... T> static inline int name(T...) { abort(); return 0; }
+AMG_REF_NEVER3(HYPRE_BoomerAMGCreate) AMG_REF_NEVER3(HYPRE_BoomerAMGSetup) AMG_REF_NEVER3(HYPRE_BoomerAMGSetStrongThreshold)
+AMG_REF_NEVER3(HYPRE_BoomerAMGSetSimple) AMG_REF_NEVER3(HYPRE_BoomerAMGSetRestriction) AMG_REF_NEVER3(HYPRE_BoomerAMGSetRelaxWt)
+AMG_REF_NEVER3(HYPRE_BoomerAMGSetRelaxType) AMG_REF_NEVER3(HYPRE_BoomerAMGSetPostInterpType) AMG_REF_NEVER3(HYPRE_BoomerAMGSetPMaxElmts)
+AMG_REF_NEVER3(HYPRE_BoomerAMGSetNumSweeps) AMG_REF_NEVER3(HYPRE_BoomerAMGSetNumFunctions) AMG_REF_NEVER3(HYPRE_BoomerAMGSetMeasureType)
+AMG_REF_NEVER3(HYPRE_BoomerAMGSetMaxRowSum) AMG_REF_NEVER3(HYPRE_BoomerAMGSetMaxLevels) AMG_REF_NEVER3(HYPRE_BoomerAMGSetInterpType)
+AMG_REF_NEVER3(HYPRE_BoomerAMGSetCycleRelaxType) AMG_REF_NEVER3(HYPRE_BoomerAMGSetCoarsenType) AMG_REF_NEVER3(HYPRE_BoomerAMGSetAggNumLevels)
+AMG_REF_NEVER3(HYPRE_BoomerAMGSetAdditive) AMG_REF_NEVER3(HYPRE_BoomerAMGSetAddRelaxWt) AMG_REF_NEVER3(HYPRE_BoomerAMGSetAddRelaxType)
+AMG_REF_NEVER3(HYPRE_IJVectorCreate) AMG_REF_NEVER3(HYPRE_IJVectorSetObjectType) AMG_REF_NEVER3(HYPRE_IJVectorInitialize)
+AMG_REF_NEVER3(HYPRE_IJVectorSetValues) AMG_REF_NEVER3(HYPRE_IJVectorAssemble) AMG_REF_NEVER3(HYPRE_IJVectorGetObject)
+AMG_REF_NEVER3(BuildHypreMatrix) AMG_REF_NEVER3(hypre_GaussElimSetup) AMG_REF_NEVER3(MPI_Finalize)
+template <class... T> static inline hypre_CSRMatrix *hypre_CSRMatrixCreate(T...) { abort(); return 0; }
+template <class... T> static inline hypre_CSRMatrix *hypre_CSRMatrixMultiply(T...) { abort(); return 0; }
+HYPRE_Int hypre_CSRMatrixTranspose(hypre_CSRMatrix *A, hypre_CSRMatrix **AT, HYPRE_Int data);
+#endif

@@ -352,7 +352,39 @@ def dmem_mult_golden():
     np.savez_compressed(os.path.join(OUT, "dmem_mult.npz"), **d)
 
 
+def smooth_transfer_golden():
+    """SmoothTransfer (src/SMEM_Setup.cpp:1173-1254; EigenMatMat, CSR_Transpose, StdVector_to_CSR) through the reference's object
+    code (SMEM_Setup.cpp compiled unmodified against the Eigen stand-in oracle/ref_shim/eigen_stub) on every level of the
+    committed hierarchies: Pbar = G P, Rbar = P^T GT with the Jacobi (w = 0.9) and the L1 smoothing factors"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import hierarchy_from_golden
+    d = {}
+    for name in ("lap5pt_n32", "lap7pt_n12"):
+        h, g = hierarchy_from_golden(name)
+        for tag, kind in (("j", H.JACOBI), ("l1", H.L1_JACOBI)):
+            for l in range(h.num_levels - 1):
+                Pb, Rb = O.ref_smooth_transfer(h.A[l], h.P_plain[l], 0.9, kind, 1, 1)
+                for mn, m in (("P", Pb), ("R", Rb)):
+                    k = "%s_%s_%s%d_" % (name, tag, mn, l)
+                    kp = "%s_%s%d_" % (name, mn, l)                         # the pattern does not depend on the smoothing factor
+                    d[kp + "shape"] = np.asarray([m.nrows, m.ncols])
+                    d[kp + "indptr"], d[kp + "indices"] = m.indptr.astype(np.int32), m.indices.astype(np.int16 if m.ncols < 32768 else np.int32)
+                    if m.nnz > 2000:  # the big levels: keep the pattern and the row / column sums of the values (fixture size)
+                        S = m.to_scipy()
+                        d[k + "rowsum"] = np.asarray(S.sum(axis=1)).ravel()
+                        d[k + "colsum"] = np.asarray(S.sum(axis=0)).ravel()
+                    else:
+                        d[k + "data"] = m.data
+        print(name, h.num_levels)
+    np.savez_compressed(os.path.join(OUT, "smooth_transfer.npz"), **d)
+
+
 if __name__ == "__main__":
+    if "--smooth-transfer-only" in sys.argv:
+        from oracle import build as obuild
+        amg.build.build_host(); obuild.build_oracle(); obuild.build_ref()
+        smooth_transfer_golden()
+        sys.exit(0)
     if "--dmem-mult-only" in sys.argv:
         from oracle import build as obuild
         amg.build.build_host(); obuild.build_oracle(); obuild.build_ref()
@@ -404,6 +436,7 @@ if __name__ == "__main__":
         hybrid_jgs_golden()
         cheby_golden()
         cheby_setup_golden()
+        smooth_transfer_golden()
         par_bpx_golden()
         dmem_mult_golden()
         async_golden()

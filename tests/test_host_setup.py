@@ -1,5 +1,6 @@
 """CPU: the host-side input provider (hierarchy.py + host/amg_host.cpp) against scipy."""
 import numpy as np
+import pytest
 import scipy.sparse as sp
 
 from async_multigrid_b200 import hierarchy as H
@@ -209,3 +210,51 @@ def test_dmem_driver_defaults_rhs_and_jacobi_weight():
         assert lo > 0 and hi <= true * (1 + 1e-12) and hi >= 0.97 * true          # Ritz values lie inside the spectrum
         w = H.dmem_default_smooth_weight(A)
         assert abs(w - 1.0 / hi) < 1e-15 and 0.4 < w < 1.0
+
+
+# ---- SmoothTransfer against the reference's own object code ---------------------------------------------
+def _same_matrix(mine, ip, ix, va, tol):
+    assert np.array_equal(mine.indptr, ip) and np.array_equal(mine.indices, ix)        # same pattern AND the same row layout
+    assert np.max(np.abs(mine.data - va)) <= tol * max(1.0, np.max(np.abs(va)))
+
+
+@pytest.mark.parametrize("name", ["lap5pt_n32", "lap7pt_n12"])
+def test_smooth_transfer_matches_reference_fixture(name):
+    """amgh_smooth_transfer (the host input provider's Pbar = G P, Rbar = P^T GT) against SmoothTransfer of the reference
+    (tests/golden/smooth_transfer.npz: src/SMEM_Setup.cpp compiled unmodified, Eigen replaced by a stand-in): identical
+    pattern and row layout (columns descending, diagonal swapped to the front), values to 1e-15"""
+    import os
+    from conftest import GOLDEN, hierarchy_from_golden
+    g = dict(np.load(os.path.join(GOLDEN, "smooth_transfer.npz")))
+    h, d = hierarchy_from_golden(name)
+    for tag, kind in (("j", H.JACOBI), ("l1", H.L1_JACOBI)):
+        h.build_transfers(H.MULTADD, 0.9, smooth_interp_type=kind)
+        for l in range(h.num_levels - 1):
+            for mn, mine in (("P", h.P[l]), ("R", h.R[l])):
+                k = "%s_%s_%s%d_" % (name, tag, mn, l)
+                kp = "%s_%s%d_" % (name, mn, l)
+                assert list(g[kp + "shape"]) == [mine.nrows, mine.ncols]
+                assert np.array_equal(mine.indptr, g[kp + "indptr"]) and np.array_equal(mine.indices, g[kp + "indices"])
+                if k + "data" in g:
+                    _same_matrix(mine, g[kp + "indptr"], g[kp + "indices"], g[k + "data"], 1e-15)
+                else:                   # big levels: pattern + row / column sums of the values (fixture size)
+                    S = mine.to_scipy()
+                    assert np.max(np.abs(np.asarray(S.sum(axis=1)).ravel() - g[k + "rowsum"])) <= 1e-14
+                    assert np.max(np.abs(np.asarray(S.sum(axis=0)).ravel() - g[k + "colsum"])) <= 1e-14
+
+
+def test_smooth_transfer_matches_live_reference():
+    from oracle import oracle as O
+    if O.ref_lib() is None:
+        pytest.skip("oracle/_ref not built here")
+    for A in (H.laplacian("27pt", 6), H.difconv(8, a=(40.0, -20.0, 10.0), atype=3)):     # symmetric and nonsymmetric operators
+        h = H.amg_setup(A)
+        for w, kind, pre, post in ((0.8, H.JACOBI, 1, 1), (0.8, H.L1_JACOBI, 1, 1), (0.8, H.JACOBI, 1, 0), (0.8, H.JACOBI, 0, 1)):
+            h.build_transfers(H.MULTADD, w, smooth_interp_type=kind, num_pre=pre, num_post=post)
+            for l in range(h.num_levels - 1):
+                Pb, Rb = O.ref_smooth_transfer(h.A[l], h.P_plain[l], w, kind, pre, post)
+                assert (Pb is None) == (post == 0) and (Rb is None) == (pre == 0)
+                if Pb is not None:
+                    _same_matrix(h.P[l], Pb.indptr, Pb.indices, Pb.data, 1e-15)
+                if Rb is not None:
+                    _same_matrix(h.R[l], Rb.indptr, Rb.indices, Rb.data, 1e-15)
