@@ -404,6 +404,26 @@ def ref_smooth_transfer(A, P, smooth_weight, smooth_interp_type=0, num_pre=1, nu
     return take(oP), take(oR)
 
 
+def ref_work_partition(h, solver, num_threads, num_pre=1, num_post=1, fine_sweeps=1, coarse_sweeps=1):
+    """ComputeWork + PartitionLevels (BALANCED_THREADS) + PartitionGrids of the reference's object code (src/SMEM_Setup.cpp:590-1170)
+    -> dict(level_work, frac, threads_per_level, A_ns, A_ne [L x num_threads, -1 = not set])"""
+    L = ref_lib()
+    nl = h.num_levels
+    keep = (list(h.A), list(h.P), list(h.R))
+    A = (OrcCSR * nl)(*[c_csr(a) for a in h.A])
+    P = (OrcCSR * max(nl - 1, 1))(*[c_csr(p) for p in h.P])
+    R = (OrcCSR * max(nl - 1, 1))(*[c_csr(r) for r in h.R])
+    lw, fr, tpl = np.zeros(nl, dtype=np.int32), np.zeros(nl), np.zeros(nl, dtype=np.int32)
+    ns, ne = np.zeros(nl * num_threads, dtype=np.int32), np.zeros(nl * num_threads, dtype=np.int32)
+    L.ref_work_partition.restype = C.c_int
+    L.ref_work_partition.argtypes = [C.c_int, C.POINTER(OrcCSR), C.POINTER(OrcCSR), C.POINTER(OrcCSR), C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_int, C.c_int, IP, DP, IP, IP, IP]
+    L.ref_work_partition(nl, A, P, R, solver, num_pre, num_post, fine_sweeps, coarse_sweeps, num_threads, iptr(lw), dptr(fr), iptr(tpl),
+                         iptr(ns), iptr(ne))
+    del keep
+    return dict(level_work=lw, frac=fr, threads_per_level=tpl, A_ns=ns.reshape(nl, num_threads), A_ne=ne.reshape(nl, num_threads))
+
+
 def ref_dmem_cheby_update(d, u, cycle, mu, delta, c, c_prev, accel_type=1):
     """DMEM_ChebyUpdate (src/DMEM_Misc.cpp:612-666), synchronous branch, in place on copies -> (d, u, c, c_prev)"""
     L = ref_lib()

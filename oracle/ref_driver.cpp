@@ -272,6 +272,9 @@ HYPRE_Int hypre_CSRMatrixTranspose(hypre_CSRMatrix *A, hypre_CSRMatrix **AT, HYP
 void Laplacian_2D_5pt(HYPRE_IJMatrix *, int) { abort(); }
 // src/SMEM_Setup.cpp (compiled unmodified against oracle/ref_shim/eigen_stub: Eigen is un-vendored)
 void SmoothTransfer(AllData *all_data, hypre_CSRMatrix *P, hypre_CSRMatrix *R, int level);
+void ComputeWork(AllData *all_data);
+void PartitionLevels(AllData *all_data);
+void PartitionGrids(AllData *all_data);
 
 struct RefHandle {
    AllData all;
@@ -1075,6 +1078,56 @@ int ref_smooth_transfer(const RefCSR *A, const RefCSR *P, double *l1, double smo
    give(Parr[0], out_P); give(Rarr[0], out_R);
    delete ad;
    return 0;
+}
+
+// ComputeWork (src/SMEM_Setup.cpp:1038-1170), PartitionLevels with BALANCED_THREADS (:590-868) and PartitionGrids (:895-1036), the
+// reference's object code: the work model that sizes the level groups, the threads dealt to every level, and every thread's
+// nnz-balanced row range of A on every level (= the hybrid smoother's Gauss-Seidel blocks).  Outputs: level_work[L],
+// frac[L], threads_per_level[L], A_ns / A_ne [L * num_threads] (entry [l * num_threads + t]; -1 where the reference leaves
+// the slot unset: thread t is not in a group that reaches it).
+int ref_work_partition(int L, const RefCSR *A, const RefCSR *P, const RefCSR *R, int solver, int num_pre, int num_post, int fine_sweeps,
+                       int coarse_sweeps, int num_threads, int *level_work, double *frac, int *threads_per_level, int *A_ns, int *A_ne)
+{
+   AllData *ad = new AllData();
+   memset((void *)&ad->input, 0, sizeof(ad->input));
+   memset((void *)&ad->matrix, 0, sizeof(ad->matrix));
+   std::vector<hypre_CSRMatrix> hA(L), hP(L), hR(L);
+   std::vector<hypre_CSRMatrix *> Aarr(L), Parr(L), Rarr(L);
+   std::vector<int> n(L);
+   for (int l = 0; l < L; l++) {
+      fill(&hA[l], A[l]); Aarr[l] = &hA[l]; n[l] = A[l].nrows;
+      if (l < L - 1) { fill(&hP[l], P[l]); fill(&hR[l], R[l]); Parr[l] = &hP[l]; Rarr[l] = &hR[l]; }
+   }
+   ad->matrix.A = Aarr.data(); ad->matrix.P = Parr.data(); ad->matrix.R = Rarr.data();
+   ad->grid.num_levels = L; ad->grid.n = n.data();
+   ad->input.solver = solver;
+   ad->input.res_compute_type = LOCAL;
+   ad->input.num_pre_smooth_sweeps = num_pre; ad->input.num_post_smooth_sweeps = num_post;
+   ad->input.num_fine_smooth_sweeps = fine_sweeps; ad->input.num_coarse_smooth_sweeps = coarse_sweeps;
+   ad->input.num_threads = num_threads;
+   ad->input.thread_part_type = ALL_LEVELS;
+   ad->input.thread_part_distr_type = BALANCED_THREADS;
+   ad->input.construct_R_flag = 1;
+   ComputeWork(ad);
+   PartitionLevels(ad);
+   // PartitionGrids deals the rows of every level with `while (count < n) for (i < num_level_threads) ...` (:1003-1011): a level that
+   // BALANCED_THREADS left without a thread makes that loop spin forever -- the reference HANGS there (SURVEY.md 5.9d says "never
+   // corrected"; it never gets that far).  Skip the call in that case and report the thread counts only.
+   bool empty_level = false;
+   for (int l = 0; l < L; l++) empty_level = empty_level || ad->thread.level_threads[l].empty();
+   if (!empty_level) PartitionGrids(ad);
+   for (int l = 0; l < L; l++) {
+      level_work[l] = ad->grid.level_work[l];
+      frac[l] = ad->grid.frac_level_work[l];
+      threads_per_level[l] = (int)ad->thread.level_threads[l].size();
+   }
+   for (int i = 0; i < L * num_threads; i++) A_ns[i] = A_ne[i] = -1;
+   // a thread's range on inner level l is set by the group it belongs to (PartitionGrids writes [inner_level][t])
+   for (int k = 0; k < L && !empty_level; k++)
+      for (int t : ad->thread.level_threads[k])
+         for (int l = 0; l < L; l++) { A_ns[l * num_threads + t] = ad->thread.A_ns[l][t]; A_ne[l * num_threads + t] = ad->thread.A_ne[l][t]; }
+   delete ad;
+   return empty_level ? 1 : 0;
 }
 
 void ref_destroy(void *h) { delete (RefHandle *)h; }

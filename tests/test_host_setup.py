@@ -258,3 +258,33 @@ def test_smooth_transfer_matches_live_reference():
                     _same_matrix(h.P[l], Pb.indptr, Pb.indices, Pb.data, 1e-15)
                 if Rb is not None:
                     _same_matrix(h.R[l], Rb.indptr, Rb.indices, Rb.data, 1e-15)
+
+
+def test_work_model_and_thread_partition_match_live_reference():
+    """ComputeWork, PartitionLevels (BALANCED_THREADS) and PartitionGrids of the reference's object code (src/SMEM_Setup.cpp:590-1170)
+    against hierarchy.compute_work / balanced_threads / nnz_balanced_bounds: the work model that sizes the level groups (threads on
+    the CPU, CTAs in the persistent kernel), the threads per level and every thread's row range (= the hybrid smoother's blocks)"""
+    from oracle import oracle as O
+    if O.ref_lib() is None:
+        pytest.skip("oracle/_ref not built here")
+    A = H.laplacian("7pt", 12)
+    h = H.amg_setup(A)
+    L = h.num_levels
+    for solver, base, pre, post in ((H.MULTADD, H.MULTADD, 1, 1), (H.MULTADD, H.MULTADD, 1, 0), (H.AFACX, H.AFACX, 1, 1),
+                                    (H.ASYNC_MULTADD, H.MULTADD, 1, 1), (H.ASYNC_AFACX, H.AFACX, 1, 1)):
+        h.build_transfers(base, 0.9, num_pre=pre, num_post=post)
+        for nt, sweeps in ((L, 1), (8, 1), (16, 2), (37, 1)):
+            r = O.ref_work_partition(h, solver, nt, pre, post, sweeps, sweeps)
+            work, frac = H.compute_work(h, solver, pre, post, sweeps, sweeps)
+            tpl = H.balanced_threads(frac, nt)
+            assert list(r["level_work"]) == list(work)
+            assert np.array_equal(r["frac"], np.asarray(frac))
+            assert list(r["threads_per_level"]) == list(tpl)
+            if min(tpl) == 0:
+                continue            # the reference hangs in PartitionGrids when a level has no thread (driver comment); nothing to compare
+            t = 0
+            for k in range(L):
+                for l in range(L):
+                    b = H.nnz_balanced_bounds(h.A[l].indptr, tpl[k])
+                    assert list(r["A_ns"][l][t:t + tpl[k]]) == list(b[:-1]) and list(r["A_ne"][l][t:t + tpl[k]]) == list(b[1:])
+                t += tpl[k]
