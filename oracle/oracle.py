@@ -424,6 +424,31 @@ def ref_work_partition(h, solver, num_threads, num_pre=1, num_post=1, fine_sweep
     return dict(level_work=lw, frac=fr, threads_per_level=tpl, A_ns=ns.reshape(nl, num_threads), A_ne=ne.reshape(nl, num_threads))
 
 
+def ref_build_extended_matrix(h):
+    """BuildExtendedMatrix (src/SMEM_Setup.cpp:1426-1521), EXPLICIT_EXTENDED_SYSTEM_BPX, the reference's object code on h.A / h.P /
+    h.R (plain transfers) -> (AA as hierarchy.CSR, disp)"""
+    L = ref_lib()
+    nl = h.num_levels
+    keep = (list(h.A), list(h.P), list(h.R))
+    A = (OrcCSR * nl)(*[c_csr(a) for a in h.A])
+    P = (OrcCSR * max(nl - 1, 1))(*[c_csr(p) for p in h.P])
+    R = (OrcCSR * max(nl - 1, 1))(*[c_csr(r) for r in h.R])
+    o = OrcCSR()
+    disp = np.zeros(nl + 1, dtype=np.int32)
+    L.ref_build_extended_matrix.restype = C.c_int
+    L.ref_build_extended_matrix.argtypes = [C.c_int, C.POINTER(OrcCSR), C.POINTER(OrcCSR), C.POINTER(OrcCSR), C.POINTER(OrcCSR), IP]
+    L.ref_build_extended_matrix(nl, A, P, R, C.byref(o), iptr(disp))
+    del keep
+    L.ref_free.argtypes = [C.c_void_p]
+    n, nnz = o.nrows, o.nnz
+    ip = np.ctypeslib.as_array(o.i, shape=(n + 1,)).copy()
+    ix = np.ctypeslib.as_array(o.j, shape=(nnz,)).copy()
+    va = np.ctypeslib.as_array(o.data, shape=(nnz,)).copy()
+    for ptr in (o.i, o.j, o.data):
+        L.ref_free(C.cast(ptr, C.c_void_p))
+    return _pkg.hierarchy.CSR(n, o.ncols, ip, ix, va), disp
+
+
 def ref_dmem_cheby_update(d, u, cycle, mu, delta, c, c_prev, accel_type=1):
     """DMEM_ChebyUpdate (src/DMEM_Misc.cpp:612-666), synchronous branch, in place on copies -> (d, u, c, c_prev)"""
     L = ref_lib()

@@ -270,6 +270,47 @@ HYPRE_Int hypre_CSRMatrixTranspose(hypre_CSRMatrix *A, hypre_CSRMatrix **AT, HYP
 // named by SMEM_BuildMatrix (src/SMEM_Setup.cpp:1600-1660), which the driver never calls; src/Laplacian.cpp does not compile here (its 3-D
 // half needs hypre's GenerateLaplacian)
 void Laplacian_2D_5pt(HYPRE_IJMatrix *, int) { abort(); }
+// hypre csr_matrix.c / csr_matop.c as far as BuildExtendedMatrix uses them.  hypre_CSRMatrixMultiply (published algorithm, serial
+// path): row by row with a marker array; an entry of C appears where its column is FIRST touched (entries a_ik in stored order,
+// then b_kj in stored order) and later touches accumulate into it; when A's row count equals B's column count the diagonal
+// entry is placed first.  No sorting.
+hypre_CSRMatrix *hypre_CSRMatrixCreate(HYPRE_Int num_rows, HYPRE_Int num_cols, HYPRE_Int num_nonzeros)
+{
+   hypre_CSRMatrix *M = (hypre_CSRMatrix *)calloc(1, sizeof(hypre_CSRMatrix));
+   M->num_rows = num_rows; M->num_cols = num_cols; M->num_nonzeros = num_nonzeros; M->num_rownnz = num_rows;
+   return M;
+}
+hypre_CSRMatrix *hypre_CSRMatrixMultiply(hypre_CSRMatrix *A, hypre_CSRMatrix *B)
+{
+   const int m = A->num_rows, n = B->num_cols;
+   if (A->num_cols != B->num_rows) abort();
+   const bool allsquare = (m == n);
+   std::vector<int> ci, cp((size_t)m + 1, 0), marker((size_t)n, -1);
+   std::vector<double> cv;
+   for (int ic = 0; ic < m; ic++) {
+      const int row_start = (int)ci.size();
+      if (allsquare) { marker[ic] = (int)ci.size(); ci.push_back(ic); cv.push_back(0.0); }
+      for (int ia = A->i[ic]; ia < A->i[ic + 1]; ia++) {
+         const int ja = A->j[ia]; const double a = A->data[ia];
+         for (int ib = B->i[ja]; ib < B->i[ja + 1]; ib++) {
+            const int jb = B->j[ib]; const double b = B->data[ib];
+            if (marker[jb] < row_start) { marker[jb] = (int)ci.size(); ci.push_back(jb); cv.push_back(a * b); }
+            else cv[marker[jb]] += a * b;
+         }
+      }
+      cp[ic + 1] = (int)ci.size();
+   }
+   hypre_CSRMatrix *Cm = hypre_CSRMatrixCreate(m, n, (int)ci.size());
+   Cm->i = (HYPRE_Int *)malloc(sizeof(HYPRE_Int) * ((size_t)m + 1));
+   Cm->j = (HYPRE_Int *)malloc(sizeof(HYPRE_Int) * std::max<size_t>(ci.size(), 1));
+   Cm->data = (HYPRE_Real *)malloc(sizeof(HYPRE_Real) * std::max<size_t>(ci.size(), 1));
+   memcpy(Cm->i, cp.data(), sizeof(int) * ((size_t)m + 1));
+   if (!ci.empty()) { memcpy(Cm->j, ci.data(), sizeof(int) * ci.size()); memcpy(Cm->data, cv.data(), sizeof(double) * cv.size()); }
+   return Cm;
+}
+
+void BuildExtendedMatrix(AllData *all_data, hypre_CSRMatrix **A_array, hypre_CSRMatrix **P_array, hypre_CSRMatrix **R_array,
+                         hypre_CSRMatrix **B_ptr);
 // src/SMEM_Setup.cpp (compiled unmodified against oracle/ref_shim/eigen_stub: Eigen is un-vendored)
 void SmoothTransfer(AllData *all_data, hypre_CSRMatrix *P, hypre_CSRMatrix *R, int level);
 void ComputeWork(AllData *all_data);
@@ -1128,6 +1169,32 @@ int ref_work_partition(int L, const RefCSR *A, const RefCSR *P, const RefCSR *R,
          for (int l = 0; l < L; l++) { A_ns[l * num_threads + t] = ad->thread.A_ns[l][t]; A_ne[l * num_threads + t] = ad->thread.A_ne[l][t]; }
    delete ad;
    return empty_level ? 1 : 0;
+}
+
+// BuildExtendedMatrix (src/SMEM_Setup.cpp:1426-1521), the reference's object code, EXPLICIT_EXTENDED_SYSTEM_BPX: blocks
+// A_k P_k .. P_{l-1} / R_{l-1} .. R_k A_k^T through hypre_CSRMatrixMultiply / Transpose (stand-ins above), row layout by
+// StdVector_to_CSR.  The result borrows arrays the reference calloc'ed (ref_free them).
+int ref_build_extended_matrix(int L, const RefCSR *A, const RefCSR *P, const RefCSR *R, RefCSR *out, int *disp)
+{
+   AllData *ad = new AllData();
+   memset((void *)&ad->input, 0, sizeof(ad->input));
+   std::vector<hypre_CSRMatrix> hA(L), hP(L), hR(L);
+   std::vector<hypre_CSRMatrix *> Aarr(L), Parr(L), Rarr(L);
+   for (int l = 0; l < L; l++) {
+      fill(&hA[l], A[l]); Aarr[l] = &hA[l];
+      if (l < L - 1) { fill(&hP[l], P[l]); fill(&hR[l], R[l]); Parr[l] = &hP[l]; Rarr[l] = &hR[l]; }
+   }
+   ad->grid.num_levels = L;
+   ad->input.solver = EXPLICIT_EXTENDED_SYSTEM_BPX;
+   ad->input.construct_R_flag = 1;
+   ad->input.format_output_flag = 1;
+   hypre_CSRMatrix *B = nullptr;
+   BuildExtendedMatrix(ad, Aarr.data(), Parr.data(), Rarr.data(), &B);
+   out->nrows = B->num_rows; out->ncols = B->num_cols; out->nnz = B->num_nonzeros; out->i = B->i; out->j = B->j; out->data = B->data;
+   for (int l = 0; l <= L; l++) disp[l] = ad->grid.disp[l];
+   free(B);
+   delete ad;
+   return 0;
 }
 
 void ref_destroy(void *h) { delete (RefHandle *)h; }

@@ -1,7 +1,7 @@
 /* BuildHypreMatrix.hpp -- TEST INFRASTRUCTURE.  src/SMEM_Setup.cpp:10 includes a header of this name which the reference repository
  * does not contain.  This stand-in declares what that translation unit names beyond oracle/ref_shim/hypre_stub.h:
  * hypre's set-up interface (HYPRE_BoomerAMG*, HYPRE_IJVector*: un-vendored, never reached by the driver -- they abort) and
- * hypre_CSRMatrixTranspose (functional, oracle/ref_driver.cpp).  Only SmoothTransfer / EigenMatMat / CSR_Transpose /
+ * hypre_CSRMatrixTranspose / Multiply / Create (functional, oracle/ref_driver.cpp).  Only SmoothTransfer / EigenMatMat / CSR_Transpose /
  * StdVector_to_CSR / ComputeWork / PartitionLevels / PartitionGrids of SMEM_Setup.cpp are ever called. */
 #ifndef AMG_REF_SETUP_STUB_H
 #define AMG_REF_SETUP_STUB_H
@@ -17,7 +17,8 @@ AMG_REF_NEVER3(HYPRE_BoomerAMGSetAdditive) AMG_REF_NEVER3(HYPRE_BoomerAMGSetAddR
 AMG_REF_NEVER3(HYPRE_IJVectorCreate) AMG_REF_NEVER3(HYPRE_IJVectorSetObjectType) AMG_REF_NEVER3(HYPRE_IJVectorInitialize)
 AMG_REF_NEVER3(HYPRE_IJVectorSetValues) AMG_REF_NEVER3(HYPRE_IJVectorAssemble) AMG_REF_NEVER3(HYPRE_IJVectorGetObject)
 AMG_REF_NEVER3(BuildHypreMatrix) AMG_REF_NEVER3(hypre_GaussElimSetup) AMG_REF_NEVER3(MPI_Finalize)
-template <class... T> static inline hypre_CSRMatrix *hypre_CSRMatrixCreate(T...) { abort(); return 0; }
-template <class... T> static inline hypre_CSRMatrix *hypre_CSRMatrixMultiply(T...) { abort(); return 0; }
+/* functional single-rank stand-ins (oracle/ref_driver.cpp), used by BuildExtendedMatrix (src/SMEM_Setup.cpp:1426-1521) */
+hypre_CSRMatrix *hypre_CSRMatrixCreate(HYPRE_Int num_rows, HYPRE_Int num_cols, HYPRE_Int num_nonzeros);
+hypre_CSRMatrix *hypre_CSRMatrixMultiply(hypre_CSRMatrix *A, hypre_CSRMatrix *B);
 HYPRE_Int hypre_CSRMatrixTranspose(hypre_CSRMatrix *A, hypre_CSRMatrix **AT, HYPRE_Int data);
 #endif
