@@ -15,6 +15,8 @@ for f in SMEM_MatVec SMEM_Smooth SMEM_Sync_AMG SMEM_Async_AMG SMEM_ExtendedSyste
 done
 # SMEM_Setup.cpp (SmoothTransfer, the thread partition, the work model): Eigen is un-vendored -- oracle/ref_shim/eigen_stub stands in
 $CXX -I"$HERE/ref_shim/eigen_stub" -c "$REF/SMEM_Setup.cpp" -o "$OUT/SMEM_Setup.o"
+# BuildHypreMatrix.cpp (stencil coefficients of -problem 7pt / 27pt / difconv): its own header is missing from the reference; same stand-in
+$CXX -I"$HERE/ref_shim/eigen_stub" -c "$REF/BuildHypreMatrix.cpp" -o "$OUT/BuildHypreMatrix.o"
 # SMEM_Solve.cpp: its printf (residual history, src/SMEM_Solve.cpp:95-103,232-239) goes to the hook
 $CXX -c "$HERE/ref_shim/wrap_SMEM_Solve.cpp" -o "$OUT/SMEM_Solve.o"
 $CXX -c "$HERE/ref_driver.cpp" -o "$OUT/ref_driver.o"

@@ -449,6 +449,17 @@ def ref_build_extended_matrix(h):
     return _pkg.hierarchy.CSR(n, o.ncols, ip, ix, va), disp
 
 
+def ref_stencil_values(test_problem, n, c=(1.0, 1.0, 1.0), a=(0.0, 0.0, 0.0), atype=0):
+    """the stencil coefficients src/BuildHypreMatrix.cpp:100-289 (the reference's object code) hands to hypre's generators:
+    test_problem 1 = 7pt -> [centre, x, y, z]; 2 = 27pt -> [centre, neighbour]; 7 = difconv -> [centre, x-1, y-1, z-1, x+1, y+1, z+1]"""
+    L = ref_lib()
+    out = np.zeros(8)
+    L.ref_stencil_values.restype = C.c_int
+    L.ref_stencil_values.argtypes = [C.c_int] * 4 + [C.c_double] * 6 + [C.c_int, DP]
+    k = L.ref_stencil_values(test_problem, n, n, n, c[0], c[1], c[2], a[0], a[1], a[2], atype, dptr(out))
+    return out[:k]
+
+
 def ref_dmem_cheby_update(d, u, cycle, mu, delta, c, c_prev, accel_type=1):
     """DMEM_ChebyUpdate (src/DMEM_Misc.cpp:612-666), synchronous branch, in place on copies -> (d, u, c, c_prev)"""
     L = ref_lib()

@@ -267,6 +267,39 @@ HYPRE_Int hypre_CSRMatrixTranspose(hypre_CSRMatrix *A, hypre_CSRMatrix **AT, HYP
    return 0;
 }
 
+// hypre's stencil generators (un-vendored), as called by src/BuildHypreMatrix.cpp: these stand-ins RECORD the coefficients the
+// reference computed -- value[0] centre; GenerateLaplacian: [1] x, [2] y, [3] z neighbours; GenerateDifConv: [1] x-1, [2] y-1,
+// [3] z-1, [4] x+1, [5] y+1, [6] z+1 (hypre par_laplace.c / par_difconv.c) -- and build nothing.
+static double g_gen_values[8];
+static int g_gen_count = 0;
+HYPRE_ParCSRMatrix GenerateLaplacian(MPI_Comm, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int,
+                                     HYPRE_Real *value) { memcpy(g_gen_values, value, sizeof(double) * 4); g_gen_count = 4; return nullptr; }
+HYPRE_ParCSRMatrix GenerateLaplacian27pt(MPI_Comm, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int,
+                                         HYPRE_Int, HYPRE_Real *value) { memcpy(g_gen_values, value, sizeof(double) * 2); g_gen_count = 2; return nullptr; }
+HYPRE_ParCSRMatrix GenerateDifConv(MPI_Comm, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int,
+                                   HYPRE_Real *value) { memcpy(g_gen_values, value, sizeof(double) * 7); g_gen_count = 7; return nullptr; }
+HYPRE_ParCSRMatrix GenerateVarDifConv(MPI_Comm, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int,
+                                      HYPRE_Real, HYPRE_ParVector *) { abort(); }
+void BuildHypreMatrix(AllData *all_data, HYPRE_ParCSRMatrix *A_ptr, HYPRE_ParVector *rhs_ptr, MPI_Comm comm, HYPRE_Int nx, HYPRE_Int ny,
+                      HYPRE_Int nz, HYPRE_Real cx, HYPRE_Real cy, HYPRE_Real cz, HYPRE_Real ax, HYPRE_Real ay, HYPRE_Real az, HYPRE_Real eps,
+                      int atype);
+// The stencil coefficients src/BuildHypreMatrix.cpp:100-289 hands to hypre for test_problem = LAPLACE_3D7PT (1), LAPLACE_3D27PT (2)
+// or DIFCONV_3D7PT (7); returns how many values were recorded.
+extern "C" int ref_stencil_values(int test_problem, int nx, int ny, int nz, double cx, double cy, double cz, double ax, double ay, double az,
+                                  int atype, double *out)
+{
+   AllData *ad = new AllData();
+   memset((void *)&ad->input, 0, sizeof(ad->input));
+   ad->input.test_problem = test_problem;
+   HYPRE_ParCSRMatrix A = nullptr;
+   HYPRE_ParVector rhs = nullptr;
+   g_gen_count = 0;
+   BuildHypreMatrix(ad, &A, &rhs, 0, nx, ny, nz, cx, cy, cz, ax, ay, az, 0.0, atype);
+   memcpy(out, g_gen_values, sizeof(double) * g_gen_count);
+   delete ad;
+   return g_gen_count;
+}
+
 // named by SMEM_BuildMatrix (src/SMEM_Setup.cpp:1600-1660), which the driver never calls; src/Laplacian.cpp does not compile here (its 3-D
 // half needs hypre's GenerateLaplacian)
 void Laplacian_2D_5pt(HYPRE_IJMatrix *, int) { abort(); }

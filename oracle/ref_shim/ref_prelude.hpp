@@ -9,7 +9,7 @@
 #define A_diag_ext A_diag_ext; double **A_diag; \
    double difconv_ax, difconv_ay, difconv_az, difconv_cx, difconv_cy, difconv_cz, vardifconv_eps; int difconv_atype   /* MatrixData: src/SMEM_Setup.cpp:1663-1666 */
 #define add_P_max_elmts add_P_max_elmts; HYPRE_Int relax_type                                 /* HypreData: src/SMEM_Setup.cpp:1689-1693 */
-#define smooth_interp_type smooth_interp_type; int simple_jacobi_flag                         /* InputData: src/SMEM_Setup.cpp:1702 */
+#define smooth_interp_type smooth_interp_type; int simple_jacobi_flag; int hypre_memory       /* InputData: src/SMEM_Setup.cpp:1702, src/BuildHypreMatrix.cpp:117 */
 #define z2 z2; HYPRE_Real **u_smooth   /* VectorData::u_smooth: used by src/SMEM_ExtendedSystem.cpp:374, allocated by src/SMEM_Setup.cpp:287 */
 #include "Main.hpp"
 #undef A_diag_ext

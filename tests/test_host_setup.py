@@ -288,3 +288,28 @@ def test_work_model_and_thread_partition_match_live_reference():
                     b = H.nnz_balanced_bounds(h.A[l].indptr, tpl[k])
                     assert list(r["A_ns"][l][t:t + tpl[k]]) == list(b[:-1]) and list(r["A_ne"][l][t:t + tpl[k]]) == list(b[1:])
                 t += tpl[k]
+
+
+def test_stencil_coefficients_match_live_reference():
+    """`-problem 7pt | 27pt | difconv`: the coefficients src/BuildHypreMatrix.cpp:100-289 computes (the reference's object code; hypre's
+    generators, un-vendored, are replaced by recorders) against an interior row of the host generators' matrices"""
+    from oracle import oracle as O
+    if O.ref_lib() is None:
+        pytest.skip("oracle/_ref not built here")
+    n = 8
+    i = (n // 2) * (1 + n + n * n)
+
+    def interior(A):
+        row = A.to_scipy().tocsr().getrow(i).toarray().ravel()
+        return np.array([row[i], row[i - 1], row[i - n], row[i - n * n], row[i + 1], row[i + n], row[i + n * n]])
+    m = interior(H.laplacian("7pt", n))
+    r = O.ref_stencil_values(1, n, (1.0, 1.0, 1.0))                    # SMEM_Main.cpp:199-204: cx = cy = cz = 1, a = 0
+    assert list(r) == [m[0], m[1], m[2], m[3]] and list(m[1:4]) == list(m[4:])
+    row = H.laplacian("27pt", n).to_scipy().tocsr().getrow(i).toarray().ravel()
+    r = O.ref_stencil_values(2, n)
+    assert r[0] == row[i] and np.all(row[np.nonzero(row)[0][np.nonzero(row)[0] != i]] == r[1]) and np.count_nonzero(row) == 27
+    for c, a, atype in (((1.0, 1.0, 1.0), (1.0, 1.0, 1.0), -1), ((1.0, 1.0, 1.0), (40.0, -20.0, 10.0), 3), ((1.0, 2.0, 3.0), (10.0, 10.0, 10.0), 0),
+                        ((1.0, 1.0, 1.0), (5.0, -7.0, 9.0), 1), ((1.0, 1.0, 1.0), (5.0, -7.0, 9.0), 2), ((0.5, 1.0, 2.0), (-3.0, 4.0, -5.0), 3)):
+        r = O.ref_stencil_values(7, n, c, a, atype)
+        m = interior(H.difconv(n, c=c, a=a, atype=atype))
+        assert np.max(np.abs(r - m)) <= 1e-13 * np.max(np.abs(r)), (atype, r, m)
