@@ -41,7 +41,7 @@ def build_ref(force=False):
         return REF_LIB if os.path.exists(REF_LIB) else None
     script = os.path.join(ORACLE, "build_ref.sh")
     shim = os.path.join(ORACLE, "ref_shim")
-    deps = [script, os.path.join(ORACLE, "ref_driver.cpp")] + [os.path.join(shim, f) for f in os.listdir(shim)]
+    deps = [script, os.path.join(ORACLE, "ref_driver.cpp")] + [os.path.join(d, f) for d, _, fs in os.walk(shim) for f in fs]
     if not force and _newer(REF_LIB, deps):
         return REF_LIB
     _run(["bash", script])
