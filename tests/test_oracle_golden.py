@@ -615,6 +615,21 @@ def test_dmem_mult_matches_live_reference():
         assert np.max(np.abs(u - x)) <= 1e-12 * np.max(np.abs(u))
 
 
+def test_dmem_sync_bpx_mapping_matches_live_reference():
+    """DMEM's SYNC_BPX (src/DMEM_Mult.cpp:346-349) is DMEM_SyncAddCycle on the PLAIN interpolants with the direct coarse solve: the
+    reference's object code fed plain P equals the oracle's Multadd with plain transfers, plain Jacobi and coarse_solve = 1"""
+    if O.ref_lib() is None:
+        pytest.skip("oracle/_ref not built here")
+    A = H.laplacian("7pt", 10)
+    h = H.amg_setup(A)
+    b = H.rand_rhs(A.nrows)
+    h.build_transfers(H.BPX, 0.5)
+    x, want = O.ref_dmem_sync_add(h, b, 0.5, symmetrised=False, num_cycles=30, tol=1e-9)
+    u, hist = O.Problem(h, H.MULTADD, H.JACOBI, 0.5, num_pre=1, num_post=0, coarse_solve=1).solve_sync_dmem(b, 1e-9, 30)
+    assert len(hist) == len(want) and np.max(np.abs(hist - want) / want) <= 1e-10      # (not a convergent iteration without acceleration)
+    assert np.max(np.abs(u - x)) <= 1e-10 * np.max(np.abs(x))
+
+
 def test_dmem_sync_add_matches_live_reference():
     if O.ref_lib() is None:
         pytest.skip("oracle/_ref not built here")
