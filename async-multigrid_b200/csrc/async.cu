@@ -289,6 +289,8 @@ extern "C" int amgb_solve_async(amgb_ctx *c, int num_cycles, int converge_type, 
    NEED_READY(c);
    if (num_cycles < 1) return amgb_fail(c, AMGB_EINVAL, "num_cycles < 1");
    if (c->opt.coarse_solve) return amgb_fail(c, AMGB_EINVAL, "coarse_solve (DMEM convention) is implemented for the synchronous cycles");
+   for (int *b : c->jgs_bounds)
+      if (b) return amgb_fail(c, AMGB_EINVAL, "explicit hybrid-JGS block lists are implemented for the synchronous cycles");
    int rc;
    if ((rc = async_prepare(c))) return rc;
    AsyncParams &hp = *c->async_host;

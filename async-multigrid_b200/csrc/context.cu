@@ -165,6 +165,7 @@ int amgb_set_num_levels(amgb_ctx *c, int L)
    c->L = L;
    c->A.resize(L); c->P.resize(L); c->R.resize(L);
    c->hA.resize(L);
+   c->jgs_bounds.assign(L, nullptr); c->jgs_nb.assign(L, 0);
    return AMGB_OK;
 }
 
@@ -664,6 +665,16 @@ void enq_residual(amgb_ctx *c)
    enq_spmv(c, c->A[0], false, c->u, c->r[0], epi(-1.0, 1.0, c->f), true);
 }
 
+
+// one hybrid Jacobi / Gauss-Seidel sweep on level l: the explicit block list when one was given (amgb_set_jgs_blocks), else the
+// uniform blocks of opt.jgs_block_rows
+static int jgs_sweep(amgb_ctx *c, int l, const DevCSR &A, const double *f, double *u, const double *u_prev, const double *scale, bool zero)
+{
+   if (l >= 0 && l < (int)c->jgs_bounds.size() && c->jgs_bounds[l])
+      return launch_hybrid_jgs_list(c->cfg, c->stream, A, f, u, u_prev, scale, c->jgs_bounds[l], c->jgs_nb[l], zero);
+   return launch_hybrid_jgs(c->cfg, c->stream, A, f, u, u_prev, scale, c->opt.jgs_block_rows, zero);
+}
+
 // e = S_l f from a zero initial guess, `sweeps` sweeps; scratch: t[l], w[l] are free to use.
 // Dispatch as SMEM_Smooth (src/SMEM_Solve.cpp:264-377).  parfor: the ONE_LEVEL branch (BPX).
 void enq_smooth_zero(amgb_ctx *c, int l, const double *f, double *e, int sweeps, bool symmetric, bool parfor,
@@ -681,10 +692,10 @@ void enq_smooth_zero(amgb_ctx *c, int l, const double *f, double *e, int sweeps,
    }
    if (sm == AMGB_SMOOTH_HYBRID_JGS) {
       const double *scale = parfor ? c->dow[l] : nullptr;
-      c->launches += launch_hybrid_jgs(c->cfg, c->stream, A, f, e, nullptr, scale, c->opt.jgs_block_rows, true);
+      c->launches += jgs_sweep(c, l, A, f, e, nullptr, scale, true);
       for (int k = 1; k < sweeps; k++) {
          cudaMemcpyAsync(s1, e, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream);
-         c->launches += launch_hybrid_jgs(c->cfg, c->stream, A, f, e, s1, scale, c->opt.jgs_block_rows, false);
+         c->launches += jgs_sweep(c, l, A, f, e, s1, scale, false);
       }
       return;
    }
@@ -840,6 +851,30 @@ int amgb_fetch_scalar(amgb_ctx *c, double *out)
 
 extern "C" {
 
+// Explicit Gauss-Seidel blocks of the hybrid smoother on one level: bounds[0] = 0 < ... < bounds[nblocks] = n_level.  The
+// reference's block is a thread's row range (src/SMEM_Smooth.cpp:567-581 with the nnz-balanced split of src/SMEM_Setup.cpp:954-959),
+// so its results depend on the thread count; with this list the device sweeps the very same blocks.  nblocks = 0 returns to the
+// uniform blocks of opt.jgs_block_rows.  Synchronous cycles and amgb_smooth only.
+int amgb_set_jgs_blocks(amgb_ctx *c, int level, int nblocks, const int *bounds)
+{
+   if (!c || level < 0 || level >= c->L) return amgb_fail(c, AMGB_EINVAL, "bad level");
+   if (nblocks == 0) { c->jgs_bounds[level] = nullptr; c->jgs_nb[level] = 0; return AMGB_OK; }
+   const int n = c->A[level].nrows;
+   if (nblocks < 0 || !bounds || n <= 0) return amgb_fail(c, AMGB_EINVAL, "block list given before the level's matrix, or empty");
+   if (bounds[0] != 0 || bounds[nblocks] != n) return amgb_fail(c, AMGB_EINVAL, "block list must run from 0 to the level's row count %d", n);
+   for (int b = 0; b < nblocks; b++)
+      if (bounds[b + 1] <= bounds[b]) return amgb_fail(c, AMGB_EINVAL, "block list is not increasing at block %d", b);
+   int *dev = nullptr;
+   int rc = amgb_dev_alloc_bytes(c, (void **)&dev, sizeof(int) * ((size_t)nblocks + 1), false);
+   if (rc) return rc;
+   CUDA_OK(c, cudaMemcpyAsync(dev, bounds, sizeof(int) * ((size_t)nblocks + 1), cudaMemcpyHostToDevice, c->stream));
+   CUDA_OK(c, cudaStreamSynchronize(c->stream));
+   c->jgs_bounds[level] = dev;
+   c->jgs_nb[level] = nblocks;
+   if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }     // the captured cycle held the old launches
+   return AMGB_OK;
+}
+
 // ---- per-op entry points (host in / host out) ------------------------------------------------------
 int amgb_spgemv(amgb_ctx *c, int kind, int level, double alpha, const double *x, double beta, const double *b, double *y)
 {
@@ -893,7 +928,7 @@ int amgb_smooth(amgb_ctx *c, int level, int smoother, int symmetric, int sweeps,
             c->launches += launch_async_gs(c->cfg, c->stream, A, c->io_a, cur, c->opt.jgs_block_rows, 1, true);
          } else if (smoother == AMGB_SMOOTH_HYBRID_JGS) {
             CUDA_OK(c, cudaMemcpyAsync(oth, cur, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
-            c->launches += launch_hybrid_jgs(c->cfg, c->stream, A, c->io_a, cur, oth, nullptr, c->opt.jgs_block_rows, false);
+            c->launches += jgs_sweep(c, level, A, c->io_a, cur, oth, nullptr, false);
          } else {
             const double *rs = (smoother == AMGB_SMOOTH_L1_JACOBI) ? c->inv_l1[level] : c->ws[level];
             enq_spmv(c, A, false, cur, oth, epi(-1.0, 1.0, c->io_a, 1.0, cur, rs), false);

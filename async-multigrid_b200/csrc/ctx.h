@@ -18,6 +18,8 @@ struct amgb_ctx {
    bool ready = false;
    bool symmetric = false;
    std::vector<DevCSR> A, P, R;
+   std::vector<int *> jgs_bounds;   // per level: explicit Gauss-Seidel block list of the hybrid smoother (device, nb + 1 ints) or null
+   std::vector<int> jgs_nb;
    DevCSR Ainv;                     // dense inverse of the coarsest operator (coarse_solve), stored as a full CSR
    std::vector<int> hA;
    std::map<const DevCSR *, long> sell_entries;

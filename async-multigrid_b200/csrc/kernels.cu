@@ -109,6 +109,35 @@ __global__ void __launch_bounds__(kBlock) k_push_correction(int n, const double 
    }
 }
 
+// hybrid Jacobi / Gauss-Seidel over an EXPLICIT block list (amgb_set_jgs_blocks): block b = rows [bounds[b], bounds[b+1]), one thread
+// walks one block in row order -- the arithmetic of hybrid_jgs_team (src/SMEM_Smooth.cpp:533-586) with the reference's own blocks
+// (a thread's nnz-balanced row range, src/SMEM_Setup.cpp:954-959).  A parity path: with the reference's few, huge blocks it is
+// as sequential as the reference's threads are.
+__global__ void __launch_bounds__(kBlock) k_hybrid_jgs_list(DevCSR A, const double *f, double *u, const double *u_prev,
+                                                            const double *scale, const int *__restrict__ bounds, int nblocks, int zero_guess)
+{
+   for (int blk = blockIdx.x * kBlock + threadIdx.x; blk < nblocks; blk += gridDim.x * kBlock) {
+      const int ns = bounds[blk], ne = bounds[blk + 1];
+      if (zero_guess)
+         for (int i = ns; i < ne; i++) u[i] = 0.0;
+      for (int i = ns; i < ne; i++) {
+         const int s = A.rp[i], t = A.rp[i + 1];
+         const double d = A.va[s];
+         if (d != 0.0) {
+            double res = f[i];
+            for (int p = s; p < t; p++) {
+               const int ii = A.ci[p];
+               if (ii >= ns && ii < ne) res -= A.va[p] * u[ii];
+               else if (!zero_guess) res -= A.va[p] * u_prev[ii];
+            }
+            const double div = scale ? scale[i] : d;
+            if (zero_guess) u[i] = res / div;
+            else u[i] += res / div;
+         }
+      }
+   }
+}
+
 __global__ void __launch_bounds__(kBlock) k_hybrid_jgs(DevCSR A, const double *f, double *u, const double *u_prev,
                                                         const double *scale, int B, int zero_guess)
 {
@@ -356,6 +385,13 @@ int launch_hybrid_jgs(const LaunchCfg &cfg, cudaStream_t st, const DevCSR &A, co
       return 1;
    }
    k_hybrid_jgs<<<grid_for(cfg, nblocks), kBlock, 0, st>>>(A, f, u, u_prev, scale, block_rows, zero_guess ? 1 : 0);
+   return 1;
+}
+
+int launch_hybrid_jgs_list(const LaunchCfg &cfg, cudaStream_t st, const DevCSR &A, const double *f, double *u,
+                           const double *u_prev, const double *scale, const int *bounds, int nblocks, bool zero_guess)
+{
+   k_hybrid_jgs_list<<<grid_for(cfg, nblocks), kBlock, 0, st>>>(A, f, u, u_prev, scale, bounds, nblocks, zero_guess ? 1 : 0);
    return 1;
 }
 

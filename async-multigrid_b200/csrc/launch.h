@@ -50,6 +50,9 @@ int launch_sumsq(const LaunchCfg &cfg, cudaStream_t st, int n, const double *x, 
 // hybrid JGS sweep
 int launch_hybrid_jgs(const LaunchCfg &cfg, cudaStream_t st, const DevCSR &A, const double *f, double *u,
                       const double *u_prev, const double *scale, int block_rows, bool zero_guess);
+// the same sweep over an explicit block list bounds[0..nblocks] (amgb_set_jgs_blocks: the reference's blocks are thread row ranges)
+int launch_hybrid_jgs_list(const LaunchCfg &cfg, cudaStream_t st, const DevCSR &A, const double *f, double *u,
+                           const double *u_prev, const double *scale, const int *bounds, int nblocks, bool zero_guess);
 // (semi-)asynchronous Gauss-Seidel sweeps on u (in place); y = M^T x
 int launch_async_gs(const LaunchCfg &cfg, cudaStream_t st, const DevCSR &A, const double *f, double *u, int block_rows,
                     int sweeps, bool semi);

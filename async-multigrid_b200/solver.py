@@ -23,7 +23,7 @@ ABI_SYMBOLS = [
     "amgb_default_options", "amgb_create", "amgb_destroy", "amgb_last_error", "amgb_launch_count",
     "amgb_set_num_levels", "amgb_set_matrix", "amgb_set_options", "amgb_setup",
     "amgb_set_rhs", "amgb_set_solution", "amgb_get_solution", "amgb_get_residual",
-    "amgb_spgemv", "amgb_spgemv_transpose", "amgb_smooth", "amgb_norm2", "amgb_cycle", "amgb_eigs_power", "amgb_solve_sync", "amgb_solve_async",
+    "amgb_spgemv", "amgb_spgemv_transpose", "amgb_smooth", "amgb_set_jgs_blocks", "amgb_norm2", "amgb_cycle", "amgb_eigs_power", "amgb_solve_sync", "amgb_solve_async",
     "amgb_async_groups", "amgb_solve_extended", "amgb_smooth_transfer", "amgb_host_csr_free", "amgb_smem_solve", "amgb_time_residual", "amgb_level_storage", "amgb_time_spmv", "amgb_stream_stats", "amgb_l2_arena_bytes",
     "amgb_dist_unique_id", "amgb_dist_init", "amgb_dist_set_level", "amgb_dist_setup", "amgb_dist_set_rhs",
     "amgb_dist_get_solution", "amgb_dist_solve_sync", "amgb_dist_solve_sync_accel", "amgb_dist_stats",
@@ -80,6 +80,7 @@ def load_library():
     L.amgb_norm2.argtypes = [C.c_void_p, DP, C.c_int, DP]
     L.amgb_cycle.argtypes = [C.c_void_p, DP, DP]
     L.amgb_eigs_power.argtypes = [C.c_void_p, C.c_int, DP, DP]
+    L.amgb_set_jgs_blocks.argtypes = [C.c_void_p, C.c_int, C.c_int, IP]
     L.amgb_solve_sync.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, DP, IP, DP]
     L.amgb_solve_async.argtypes = [C.c_void_p, C.c_int, C.c_int, IP, DP, DP]
     L.amgb_solve_extended.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_double, C.c_double, DP, IP, DP, DP, DP]
@@ -135,7 +136,7 @@ class Solver:
 
     def __init__(self, h, solver=H.MULTADD, smoother=H.JACOBI, smooth_weight=1.0, num_pre=1, num_post=1,
                  fine_sweeps=1, coarse_sweeps=1, jgs_block_rows=8, use_sell=True, l2_persist=True, use_stream=True,
-                 stream_variant=None, sell_sigma=None, coarse_solve=False, factor_level0=False, device=0):
+                 stream_variant=None, sell_sigma=None, coarse_solve=False, factor_level0=False, device=0, jgs_blocks=None):
         self.L = load_library()
         self.h = h
         self.ctx = C.c_void_p()
@@ -171,6 +172,18 @@ class Solver:
                 self._set(MAT_R, l, h.R[l])
         self._ck(self.L.amgb_setup(self.ctx))
         self.n0 = h.n[0]
+        if jgs_blocks is not None:
+            for l, b in enumerate(jgs_blocks):
+                self.set_jgs_blocks(l, b)
+
+    def set_jgs_blocks(self, level, bounds):
+        """explicit Gauss-Seidel blocks of the hybrid smoother on `level` (the reference's blocks are thread row ranges,
+        src/SMEM_Setup.cpp:954-959: hierarchy.nnz_balanced_bounds); None / empty: back to uniform jgs_block_rows blocks"""
+        if bounds is None or len(bounds) == 0:
+            self._ck(self.L.amgb_set_jgs_blocks(self.ctx, level, 0, None))
+            return
+        b = np.ascontiguousarray(bounds, dtype=np.int32)
+        self._ck(self.L.amgb_set_jgs_blocks(self.ctx, level, len(b) - 1, _ip(b)))
 
     def _ck(self, rc):
         if rc != 0:

@@ -104,6 +104,12 @@ int amgb_spgemv_transpose(amgb_ctx *ctx, int kind, int level, const double *x, d
  * input when zero_guess != 0).  symmetric != 0 selects SMEM_Sync_Symmetric{,L1}Jacobi. */
 int amgb_smooth(amgb_ctx *ctx, int level, int smoother, int symmetric, int sweeps, int zero_guess,
                 const double *f, double *u);
+/* Explicit Gauss-Seidel block list of the hybrid Jacobi / Gauss-Seidel smoother on one level: bounds[0] = 0 < ... <
+ * bounds[nblocks] = rows of the level.  Replaces the thread row ranges thread.A_ns / A_ne[level][tid] that PartitionGrids
+ * (src/SMEM_Setup.cpp:954-959) hands to SMEM_Sync_HybridJacobiGaussSeidel (src/SMEM_Smooth.cpp:533-586): with the reference's own
+ * ranges the device reproduces a run of the reference with that many threads per level.  nblocks = 0: back to the uniform
+ * blocks of opt.jgs_block_rows.  Call after the level's matrix is uploaded; synchronous cycles and amgb_smooth only. */
+int amgb_set_jgs_blocks(amgb_ctx *ctx, int level, int nblocks, const int *bounds);
 /* sqrt(sum x_i^2) -- Parfor_Norm2 (src/Misc.cpp:296-309) */
 int amgb_norm2(amgb_ctx *ctx, const double *x, int n, double *out);
 

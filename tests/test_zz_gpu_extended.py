@@ -247,3 +247,21 @@ def test_async_noinline_variant_matches_the_measured_kernel():
         assert true < 1e-9 and list(out["corrections"]) == [160] * h.num_levels
     finally:
         os.environ["AMGB_ASYNC_NOINLINE"] = "0"
+
+
+@pytest.mark.skipif(os.environ.get("AMGB_EXPERIMENTAL") != "1", reason="amgb_set_jgs_blocks was written after the GPU budget was spent")
+@pytest.mark.parametrize("name", ["lap5pt_n32", "lap7pt_n12"])
+@pytest.mark.parametrize("tag", ["nt0", "nt16"])
+def test_hybrid_jgs_reference_blocks_match_reference_fixture(name, tag):
+    """hybrid Jacobi / Gauss-Seidel with the reference's OWN Gauss-Seidel blocks (amgb_set_jgs_blocks: the nnz-balanced thread row
+    ranges of a run with one / several threads per level) against the history of the reference's object code"""
+    g = dict(np.load(os.path.join(GOLDEN, "hybrid_jgs.npz")))
+    h, d = hierarchy_from_golden(name)
+    h.build_transfers(H.MULTADD, 0.9, num_pre=1, num_post=0)
+    tpl = g["%s_%s_threads_per_level" % (name, tag)]
+    blocks = [H.nnz_balanced_bounds(h.A[l].indptr, int(tpl[l])) for l in range(h.num_levels)]
+    s = amg.Solver(h, H.MULTADD, H.HYBRID_JACOBI_GAUSS_SEIDEL, 0.9, num_pre=1, num_post=0, jgs_blocks=blocks)
+    got = s.SMEM_Solve(d["b"], 1e-9, 80)["hist"]
+    want = g["%s_%s_hist" % (name, tag)]
+    assert len(got) == len(want) and np.max(np.abs(got - want)) <= HIST_TOL
+    s.close()

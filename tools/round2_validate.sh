@@ -5,7 +5,7 @@
 #    partitioned cycle); 2. A/B timings at 256^3.
 set -x
 export AMGB_EXPERIMENTAL=1
-timeout 300 python -m pytest tests/test_zz_gpu_extended.py tests/test_gpu_dist.py -m gpu -q -k "device_smooth_transfer or async_factorised or graph_captured or nonsymmetric or hybrid_jgs_single_block or async_noinline or afacx_two_sweeps"
+timeout 300 python -m pytest tests/test_zz_gpu_extended.py tests/test_gpu_dist.py -m gpu -q -k "device_smooth_transfer or async_factorised or graph_captured or nonsymmetric or hybrid_jgs_single_block or async_noinline or afacx_two_sweeps or reference_blocks"
 timeout 300 python tools/async_fact0_time.py --n 256 --corrections 40
 timeout 200 python tools/iebpx_time.py --n 256
 # 3. one ncu capture of the persistent asynchronous kernel (never captured in round 1): is it starved for instructions?
