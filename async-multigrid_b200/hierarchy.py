@@ -256,6 +256,33 @@ def rand_rhs(n, lo=-1.0, hi=1.0, seed=0):
     return b
 
 
+def reference_processor_grid(num_procs, nx, ny, nz):
+    """(P, Q, R) the reference's search picks for `num_procs` ranks (src/DMEM_BuildMatrix.cpp:169-240 = src/BuildHypreMatrix.cpp:36-76):
+    1 rank -> (1,1,1); a prime count -> (1, num_procs, 1), y-slabs; otherwise the first (x, y, z) with x*y*z = num_procs when the
+    divisors are tried in ascending order with z fastest -- (1, 1, num_procs), z-slabs, whenever num_procs <= nz.  The partitioned
+    path here uses z-slabs for every count."""
+    if num_procs == 1:
+        return 1, 1, 1
+    divs = [d for d in range(1, num_procs + 1) if num_procs % d == 0]
+    if len(divs) == 2:
+        return 1, num_procs, 1
+    x = y = z = 1
+    done = False
+    for di in divs:
+        for dj in divs:
+            for dk in divs:
+                if dk > nz or done:
+                    break
+                x, y, z = di, dj, dk
+                if x * y * z == num_procs:
+                    done = True
+            if dj > ny or done:
+                break
+        if di > nx or done:
+            break
+    return x, y, z
+
+
 def rand_rhs_dmem(row_starts):
     """DMEM RHS: EVERY rank seeds srand(0) and draws its local rows from RandDouble(-.5, .5)
     (src/DMEM_Setup.cpp:1293,1351), so the global b is the same glibc sequence repeated per rank and depends on the number of

@@ -272,8 +272,11 @@ HYPRE_Int hypre_CSRMatrixTranspose(hypre_CSRMatrix *A, hypre_CSRMatrix **AT, HYP
 // [3] z-1, [4] x+1, [5] y+1, [6] z+1 (hypre par_laplace.c / par_difconv.c) -- and build nothing.
 static double g_gen_values[8];
 static int g_gen_count = 0;
-HYPRE_ParCSRMatrix GenerateLaplacian(MPI_Comm, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int,
-                                     HYPRE_Real *value) { memcpy(g_gen_values, value, sizeof(double) * 4); g_gen_count = 4; return nullptr; }
+static int g_gen_grid[3] = {0, 0, 0};      // the processor grid (P, Q, R) the reference chose (src/BuildHypreMatrix.cpp:36-76)
+int amg_ref_num_procs = 1;
+HYPRE_ParCSRMatrix GenerateLaplacian(MPI_Comm, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int P, HYPRE_Int Q, HYPRE_Int R, HYPRE_Int, HYPRE_Int, HYPRE_Int,
+                                     HYPRE_Real *value)
+{ memcpy(g_gen_values, value, sizeof(double) * 4); g_gen_count = 4; g_gen_grid[0] = P; g_gen_grid[1] = Q; g_gen_grid[2] = R; return nullptr; }
 HYPRE_ParCSRMatrix GenerateLaplacian27pt(MPI_Comm, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int,
                                          HYPRE_Int, HYPRE_Real *value) { memcpy(g_gen_values, value, sizeof(double) * 2); g_gen_count = 2; return nullptr; }
 HYPRE_ParCSRMatrix GenerateDifConv(MPI_Comm, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int, HYPRE_Int,
@@ -298,6 +301,16 @@ extern "C" int ref_stencil_values(int test_problem, int nx, int ny, int nz, doub
    memcpy(out, g_gen_values, sizeof(double) * g_gen_count);
    delete ad;
    return g_gen_count;
+}
+// The processor grid (P, Q, R) the reference's search (src/BuildHypreMatrix.cpp:36-76, the same code as src/DMEM_BuildMatrix.cpp:169-240)
+// picks for `num_procs` ranks on an nx x ny x nz grid.
+extern "C" void ref_processor_grid(int num_procs, int nx, int ny, int nz, int *pqr)
+{
+   double tmp[8];
+   amg_ref_num_procs = num_procs;
+   ref_stencil_values(LAPLACE_3D7PT, nx, ny, nz, 1.0, 1.0, 1.0, 0.0, 0.0, 0.0, 0, tmp);
+   amg_ref_num_procs = 1;
+   pqr[0] = g_gen_grid[0]; pqr[1] = g_gen_grid[1]; pqr[2] = g_gen_grid[2];
 }
 
 // named by SMEM_BuildMatrix (src/SMEM_Setup.cpp:1600-1660), which the driver never calls; src/Laplacian.cpp does not compile here (its 3-D

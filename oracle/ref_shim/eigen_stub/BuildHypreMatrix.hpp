@@ -44,5 +44,6 @@ HYPRE_ParCSRMatrix GenerateVarDifConv(MPI_Comm comm, HYPRE_Int nx, HYPRE_Int ny,
 #ifndef AMG_REF_DMEM_STUB_H
 static inline int hypre_MPI_Comm_rank(MPI_Comm, int *r) { *r = 0; return 0; }
 #endif
-static inline int hypre_MPI_Comm_size(MPI_Comm, int *s) { *s = 1; return 0; }
+extern int amg_ref_num_procs;   /* oracle/ref_driver.cpp: the communicator size BuildHypreMatrix's processor-grid search sees (rank stays 0) */
+static inline int hypre_MPI_Comm_size(MPI_Comm, int *s) { *s = amg_ref_num_procs; return 0; }
 #endif

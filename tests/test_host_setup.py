@@ -313,3 +313,20 @@ def test_stencil_coefficients_match_live_reference():
         r = O.ref_stencil_values(7, n, c, a, atype)
         m = interior(H.difconv(n, c=c, a=a, atype=atype))
         assert np.max(np.abs(r - m)) <= 1e-13 * np.max(np.abs(r)), (atype, r, m)
+
+
+def test_processor_grid_matches_live_reference():
+    """the reference's processor-grid search (src/BuildHypreMatrix.cpp:36-76, object code) against its restatement: y-slabs for a prime
+    number of ranks, z-slabs otherwise"""
+    from oracle import oracle as O
+    if O.ref_lib() is None:
+        pytest.skip("oracle/_ref not built here")
+    for dims in ((512, 512, 512), (16, 16, 4), (8, 8, 8)):
+        for P in (1, 2, 3, 4, 5, 6, 8, 12, 16, 32):
+            want = H.reference_processor_grid(P, *dims)
+            if want[0] * want[1] * want[2] != P or want[0] > dims[0] or want[1] > dims[1] or want[2] > dims[2]:
+                continue        # the reference prints "Invalid number of processors" and exit(1)s for such a count: do not call it
+            g = np.zeros(3, dtype=np.int32)
+            O.ref_lib().ref_processor_grid(P, dims[0], dims[1], dims[2], O.iptr(g))
+            assert tuple(int(v) for v in g) == want, (P, dims)
+    assert H.reference_processor_grid(2, 512, 512, 512) == (1, 2, 1) and H.reference_processor_grid(8, 512, 512, 512) == (1, 1, 8)
