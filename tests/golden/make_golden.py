@@ -3,7 +3,11 @@ object code (oracle/_ref/libref_smem.so, built from /root/reference/src by oracl
 Run in the build container (needs /root/reference); the fixtures are committed so that the GPU
 box -- which has no /root/reference -- can check the oracle and the CUDA path against them.
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py            (everything; `--<name>-only` regenerates one file)
+
+A regeneration moves the histories in the last bits (1e-16: the reference's threaded norm reductions are not run-to-run
+deterministic); the single-thread / one-thread-per-level outputs (async_two_level, cheby_setup, smooth_transfer, dmem_mult) come
+back byte-identical.
 """
 import os
 import sys
