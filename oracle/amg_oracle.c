@@ -479,6 +479,8 @@ int orc_solve_sync(const orc_problem *pb, const double *f, double *u, double tol
           * precond_flag branch), then the three-term recurrence src/SMEM_Solve.cpp:179-187 */
          memset(c, 0, sizeof(double) * (size_t)n0);
          if (pb->solver == ORC_BPX) orc_bpx_cycle(pb, w, c);
+         /* MULT as a preconditioner (src/SMEM_Sync_AMG.cpp:29-36): the V-cycle on the right-hand side r from a zero guess */
+         else if (pb->solver == ORC_MULT) orc_mult_vcycle(pb, w, r, c);
          else orc_add_vcycle(pb, w, c, NULL);
 #pragma omp parallel for schedule(static)
          for (int i = 0; i < n0; i++) {

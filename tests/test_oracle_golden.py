@@ -533,6 +533,26 @@ def test_cheby_setup_matches_live_reference():
                 assert np.max(np.abs(got - want) / np.abs(want)) <= 1e-12, (prob, tag, iters, nt)
 
 
+def test_chebyshev_accelerated_vcycle_matches_live_reference():
+    """-cheby around the multiplicative V-cycle (precond_flag = 1 form of SMEM_Sync_Parfor_Vcycle, src/SMEM_Sync_AMG.cpp:29-36:
+    the cycle on the residual from a zero guess), the reference's object code with 4 threads (omp-for: deterministic).  The device
+    rejects this combination (Chebyshev acceleration is wired for the additive cycles); the oracle restates it."""
+    if O.ref_lib() is None:
+        pytest.skip("oracle/_ref not built here")
+    A = H.laplacian("7pt", 10)
+    h = H.amg_setup(A)
+    b = H.rand_rhs(A.nrows)
+    h.build_transfers(H.MULT, 0.8)
+    for lo, hi in ((0.5, 1.0), (0.3, 1.2)):
+        mu, delta = (hi + lo) / (hi - lo), 2.0 / (hi + lo)
+        rs = O.RefSolver(h, H.MULT, H.JACOBI, b, 0.8, num_threads=4)
+        out = rs.solve(100, 1e-9, async_type=0, cheby=(mu, delta), precond=1)
+        rs.close()
+        _, hist, _ = O.Problem(h, H.MULT, H.JACOBI, 0.8).solve_sync(b, 1e-9, 100, cheby=(mu, delta))
+        _close_hist(hist, out["hist"])
+        assert hist[-1] < 1e-9
+
+
 # ---- DMEM: synchronous Multadd on all ranks and the acceleration of the accumulated correction -----------------------------
 @pytest.mark.parametrize("name", ["lap5pt_n32", "lap7pt_n12"])
 def test_dmem_sync_add_matches_reference_fixture(name):
