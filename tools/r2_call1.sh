@@ -5,8 +5,7 @@ mkdir -p gpurun_out
 export AMGB_EXPERIMENTAL=1
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv
 nproc
-timeout 600 python -m pytest tests -m gpu -q -x --deselect tests/test_gpu_parity.py::test_full_size_256_properties 2>&1 | tail -40
-timeout 600 python -m pytest tests -m gpu -q 2>&1 | tail -40
+timeout 700 python -m pytest tests -m gpu -q -rfEs 2>&1 | tail -80
 timeout 400 python tools/async_fact0_time.py --n 256 --corrections 40 --reps 2
 timeout 300 python tools/iebpx_time.py --n 256
 timeout 300 python tools/cycle_probe.py --n 256 --cycles 36 --time-ops
