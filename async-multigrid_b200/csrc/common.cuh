@@ -25,6 +25,15 @@ struct DevCSR {
    const double *sell_sval = nullptr;
    int sell_base = 0;                // index of the first slice of this view (row-range launches of the multi-GPU path)
    const int *sell_perm = nullptr;   // SELL-C-sigma: slot (32*slice + lane) -> row, -1 for padding slots; nullptr = identity
+   // SELL-U ("uniform slices", sigma = 1 only): a lossless second encoding of a slice whose entries take few distinct
+   // (column - row, value) pairs -- the stencil levels, where every row of a slice carries the same 7 / 27 pairs.  Slice s
+   // owns groups [su_off[s], su_off[s+1]); group g = {delta, lane mask} + value (+ the column-scaled value): lane l adds
+   // value * x[row + delta] when bit l of the mask is set.  24 bytes per group replace 384 bytes per slice column, so the
+   // kernel streams the vectors only.  su_off[s+1] == su_off[s]: the slice is not encoded, the regular arrays are used.
+   const int *su_off = nullptr;      // [slices+1]
+   const int2 *su_dm = nullptr;      // {column - row, lane mask}
+   const double *su_va = nullptr;
+   const double *su_sval = nullptr;
    int lpr = 8;                      // lanes per row chosen for the CSR vector kernel
    // CSR-stream row blocks: CTA b owns rows [blk[b], blk[b+1]) whose entries (<= AMGB_STREAM_CAP,
    // counted from the 4-aligned start) are streamed with 128-bit loads into shared memory and then
@@ -46,18 +55,11 @@ struct DevCSR {
    const double *pva = nullptr;
    const double *psval = nullptr;
    const unsigned char *pos = nullptr;
-   // second block list for the persistent asynchronous kernel: CTA blocks of <= AMGB_STREAM_CAP entries
-   int ncblk = 0;
-   const int4 *cblk = nullptr;
    // multi-GPU: launch units (slices / chunks / rows) [ulo, uhi) read only OWNED entries of the input vector, so
    // they can run while the halo exchange is in flight; the units outside wait for it.  uhi <= ulo: no split.
    int ulo = 0, uhi = 0;
 };
 #define AMGB_STREAM_CAP 2048          // largest row block any variant uses (and the persistent kernel's)
-#define AMGB_TEAM_STAGES 3
-// dynamic shared memory of a CTA of the persistent kernel: per stage CAP values (products overwrite them in
-// place) + CAP column indices, then one mbarrier per stage
-#define AMGB_TEAM_SMEM (AMGB_TEAM_STAGES * AMGB_STREAM_CAP * 12 + 64)
 
 // y_i = gamma*c_i + rs_i * (beta*b_i + alpha * sum_j M_ij x_j)       (rs == nullptr -> 1)
 // covers: MatVec (alpha=1), Residual (alpha=-1,beta=1,b=f), prolong-and-add (beta=1,b=y),
@@ -73,6 +75,14 @@ struct SpmvEpilogue {
    double beta2 = 0.0, xself = 0.0;
    const double *b2 = nullptr;
    const double *xs = nullptr;
+   // persistent asynchronous kernel only (RO == false): the row result is also (or only, y == nullptr) reduced into a vector
+   // that other CTA groups update concurrently, red_i += red_scale * y_i with red.global.add.f64 (the `omp atomic` of
+   // src/SMEM_Async_AMG.cpp:297), the group's private copy red_copy_i = red_i is taken right after (:298), and acc_i += y_i
+   // keeps the group's accumulated correction (-read_type res, :288)
+   double red_scale = 1.0;
+   double *red = nullptr;
+   double *red_copy = nullptr;
+   double *acc = nullptr;
 };
 
 __device__ __forceinline__ double ld_stream(const double *p)
@@ -113,6 +123,14 @@ __device__ __forceinline__ double ld_cg(const double *p)
 {
    double v;
    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
+   return v;
+}
+// L1-cached load on the coherent path (NOT ld.global.nc): see ld_x<false> in kernels.cuh.  Inline PTX so that a
+// `const __restrict__` qualifier cannot turn it into a non-coherent load behind our back.
+__device__ __forceinline__ double ld_ca(const double *p)
+{
+   double v;
+   asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(v) : "l"(p));
    return v;
 }
 __device__ __forceinline__ void st_cg(double *p, double v)
@@ -187,6 +205,23 @@ __device__ __forceinline__ double epilogue_apply(const SpmvEpilogue &e, int row,
    if (e.c) t += e.gamma * (RO ? e.c[row] : ld_cg(e.c + row));
    if (e.xs) t += e.xself * (RO ? e.xs[row] : ld_cg(e.xs + row));
    return t;
+}
+
+// store of a finished row: plain store for the stand-alone kernels; inside the persistent kernel optionally the fused
+// "u += e; u_k = u" of the asynchronous update
+template <bool RO>
+__device__ __forceinline__ void epilogue_store(const SpmvEpilogue &e, double *y, int row, double v)
+{
+   if (!RO) {
+      if (e.red) {
+         red_add_f64(e.red + row, e.red_scale * v);
+         if (e.red_copy) e.red_copy[row] = ld_cg(e.red + row);
+      }
+      if (e.acc) e.acc[row] += v;
+      if (y) y[row] = v;
+   } else {
+      y[row] = v;
+   }
 }
 
 // epilogue with the row operands loaded ahead of the reduction (latency off the critical path)

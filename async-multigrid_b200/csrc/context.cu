@@ -95,6 +95,10 @@ void amgb_default_options(amgb_options *o)
    o->coarse_solve = 0;
    o->stream_variant = 8;
    o->sell_sigma = 128;
+   o->sell_uniform = 1;
+   o->async_type = 0;
+   o->res_compute_type = 0;
+   o->read_type = 0;
 }
 
 int amgb_create(amgb_ctx **out, int device)
@@ -257,6 +261,141 @@ static int build_sell(amgb_ctx *c, DevCSR &M, int nrows, const int *rp, const in
    return AMGB_OK;
 }
 
+// SELL-U: re-encode the slices of a sigma = 1 sliced-ELL matrix whose entries take few distinct (column - row, value,
+// scaled value) triples (see DevCSR::su_off).  Runs at setup time, after the column-scaled values exist, on host copies of
+// the device arrays (chunks of slices, OpenMP over slices).  Lossless: a slice is encoded only if every real entry of its
+// rows falls into a group and no row holds the same column twice; a row's terms are then summed in group order (the order
+// of first appearance in the slice) instead of CSR order.  A slice that would need more than half the bytes of its
+// regular encoding keeps the regular one; a matrix where fewer than half of the slices qualify is left alone.
+struct SuGrp { int delta; unsigned mask; double va, sv; };
+
+// encode slices [s0, s1): ci / va / sv hold the sliced-ELL entries starting at entry offset e0 (= off[s0] for a chunk)
+static void sellu_encode_chunk(int nrows, const int *off, const int *rp, int s0, int s1, size_t e0, const int *ci,
+                               const double *va, const double *sv, std::vector<std::vector<SuGrp>> &gs)
+{
+   gs.assign((size_t)(s1 - s0), std::vector<SuGrp>());
+#pragma omp parallel for schedule(dynamic, 1024)
+   for (int s = s0; s < s1; s++) {
+      const int w = (off[s + 1] - off[s]) / 32;
+      if (w == 0) continue;
+      std::vector<SuGrp> &g = gs[(size_t)(s - s0)];
+      const size_t cap = std::min<size_t>(64, (size_t)w * 32 * 12 / 2 / 24);
+      bool ok = true;
+      for (int l = 0; l < 32 && ok; l++) {
+         const int r = s * 32 + l;
+         if (r >= nrows) break;
+         const int len = rp[r + 1] - rp[r];
+         for (int k = 0; k < len && ok; k++) {
+            const size_t d = (size_t)off[s] - e0 + (size_t)k * 32 + l;
+            const int delta = ci[d] - r;
+            // the same column twice in ONE row is not representable (one mask bit per lane and group; two groups with
+            // the same delta would be, but such a row is malformed anyway): leave the slice alone
+            for (size_t q2 = 0; q2 < g.size(); q2++)
+               if (g[q2].delta == delta && ((g[q2].mask >> l) & 1u)) { ok = false; break; }
+            if (!ok) break;
+            size_t q = 0;
+            for (; q < g.size(); q++)
+               if (g[q].delta == delta && memcmp(&g[q].va, &va[d], 8) == 0 && memcmp(&g[q].sv, &sv[d], 8) == 0) break;
+            if (q == g.size()) {
+               if (g.size() >= cap) { ok = false; break; }
+               g.push_back(SuGrp{delta, 0u, va[d], sv[d]});
+            }
+            g[q].mask |= 1u << l;
+         }
+      }
+      if (!ok) g.clear();
+   }
+}
+
+static int build_sellu(amgb_ctx *c, DevCSR &M)
+{
+   if (!c->opt.use_sell || c->opt.sell_uniform == 0 || M.sell_slices == 0 || M.sell_perm || M.su_off || !M.sell_sval) return AMGB_OK;
+   const int slices = M.sell_slices, nrows = M.nrows;
+   std::vector<int> off((size_t)slices + 1), rp((size_t)nrows + 1);
+   CUDA_OK(c, cudaStreamSynchronize(c->stream));
+   CUDA_OK(c, cudaMemcpy(off.data(), M.sell_off, sizeof(int) * off.size(), cudaMemcpyDeviceToHost));
+   CUDA_OK(c, cudaMemcpy(rp.data(), M.rp, sizeof(int) * rp.size(), cudaMemcpyDeviceToHost));
+   std::vector<int> goff((size_t)slices + 1, 0);
+   const int CH = 262144;                                   // slices per chunk (bounds the host copy)
+   std::vector<SuGrp> all;
+   long encoded = 0;
+   std::vector<int> ci;
+   std::vector<double> va, sv;
+   std::vector<std::vector<SuGrp>> gs;
+   for (int s0 = 0; s0 < slices; s0 += CH) {
+      const int s1 = std::min(slices, s0 + CH);
+      const size_t e0 = (size_t)off[s0], ne = (size_t)off[s1] - e0;
+      ci.resize(ne); va.resize(ne); sv.resize(ne);
+      if (ne) {
+         CUDA_OK(c, cudaMemcpy(ci.data(), M.sell_ci + e0, sizeof(int) * ne, cudaMemcpyDeviceToHost));
+         CUDA_OK(c, cudaMemcpy(va.data(), M.sell_va + e0, sizeof(double) * ne, cudaMemcpyDeviceToHost));
+         CUDA_OK(c, cudaMemcpy(sv.data(), M.sell_sval + e0, sizeof(double) * ne, cudaMemcpyDeviceToHost));
+      }
+      sellu_encode_chunk(nrows, off.data(), rp.data(), s0, s1, e0, ci.data(), va.data(), sv.data(), gs);
+      for (int s = s0; s < s1; s++) {
+         const std::vector<SuGrp> &g = gs[(size_t)(s - s0)];
+         goff[s + 1] = goff[s] + (int)g.size();
+         if (!g.empty()) encoded++;
+         all.insert(all.end(), g.begin(), g.end());
+      }
+   }
+   if (encoded * 2 < slices) return AMGB_OK;
+   std::vector<int2> dm(all.size());
+   std::vector<double> gva(all.size()), gsv(all.size());
+   for (size_t i = 0; i < all.size(); i++) { dm[i] = make_int2(all[i].delta, (int)all[i].mask); gva[i] = all[i].va; gsv[i] = all[i].sv; }
+   int *d_off; int2 *d_dm; double *d_va, *d_sv;
+   int rc;
+   if ((rc = dev_upload(c, &d_off, goff.data(), goff.size()))) return rc;
+   if ((rc = dev_upload(c, &d_dm, dm.data(), dm.size()))) return rc;
+   if ((rc = dev_upload(c, &d_va, gva.data(), gva.size()))) return rc;
+   if ((rc = dev_upload(c, &d_sv, gsv.data(), gsv.size()))) return rc;
+   CUDA_OK(c, cudaStreamSynchronize(c->stream));
+   M.su_off = d_off; M.su_dm = d_dm; M.su_va = d_va; M.su_sval = d_sv;
+   c->sellu_slices += encoded;
+   c->sellu_groups += (long)all.size();
+   return AMGB_OK;
+}
+
+// Host-only probe of the SELL-U encoder for the CPU test suite (no CUDA call): CSR + scaled values in, the sigma = 1 sliced-ELL
+// layout is formed as build_sell does and encoded; out: goff[slices + 1], and per group delta / mask / va / sv (malloc'ed,
+// release with amgb_host_free).  Returns the number of slices.
+int amgb_sellu_encode_host(int nrows, const int *rp, const int *ci, const double *va, const double *sv, int **goff_out,
+                           int **delta_out, unsigned int **mask_out, double **gva_out, double **gsv_out, int *ngroups)
+{
+   const int slices = (nrows + 31) / 32;
+   std::vector<int> off((size_t)slices + 1, 0);
+   for (int s = 0; s < slices; s++) {
+      int w = 0;
+      for (int l = 0; l < 32 && s * 32 + l < nrows; l++) w = std::max(w, rp[s * 32 + l + 1] - rp[s * 32 + l]);
+      off[s + 1] = off[s] + w * 32;
+   }
+   std::vector<int> sci((size_t)off[slices], 0);
+   std::vector<double> sva((size_t)off[slices], 0.0), ssv((size_t)off[slices], 0.0);
+   for (int r = 0; r < nrows; r++)
+      for (int k = 0; k < rp[r + 1] - rp[r]; k++) {
+         const size_t d = (size_t)off[r / 32] + (size_t)k * 32 + (r & 31);
+         sci[d] = ci[rp[r] + k]; sva[d] = va[rp[r] + k]; ssv[d] = sv[rp[r] + k];
+      }
+   std::vector<std::vector<SuGrp>> gs;
+   sellu_encode_chunk(nrows, off.data(), rp, 0, slices, 0, sci.data(), sva.data(), ssv.data(), gs);
+   size_t tot = 0;
+   for (auto &g : gs) tot += g.size();
+   int *goff = (int *)malloc(sizeof(int) * ((size_t)slices + 1));
+   int *dl = (int *)malloc(sizeof(int) * std::max<size_t>(tot, 1));
+   unsigned int *mk = (unsigned int *)malloc(sizeof(unsigned int) * std::max<size_t>(tot, 1));
+   double *gv = (double *)malloc(sizeof(double) * std::max<size_t>(tot, 1));
+   double *gsvp = (double *)malloc(sizeof(double) * std::max<size_t>(tot, 1));
+   size_t q = 0;
+   goff[0] = 0;
+   for (int s = 0; s < slices; s++) {
+      for (auto &x : gs[(size_t)s]) { dl[q] = x.delta; mk[q] = x.mask; gv[q] = x.va; gsvp[q] = x.sv; q++; }
+      goff[s + 1] = (int)q;
+   }
+   *goff_out = goff; *delta_out = dl; *mask_out = mk; *gva_out = gv; *gsv_out = gsvp; *ngroups = (int)tot;
+   return slices;
+}
+void amgb_host_free(void *p) { free(p); }
+
 // Row blocks of the CSR-stream kernel: consecutive rows whose entries, counted from the 4-aligned
 // start of the block, fit AMGB_STREAM_CAP (and at most AMGB_STREAM_CAP rows); a longer row is a
 // block of its own.
@@ -373,24 +512,6 @@ static int build_stream_blocks(amgb_ctx *c, DevCSR &M, int nrows, int ncols, con
       CUDA_OK(c, cudaStreamSynchronize(c->stream));
       M.pci = d_pci; M.pva = d_pva; M.pos = d_pos;
    }
-   const int solver = c->opt.solver;
-   if (solver == AMGB_SOLVER_ASYNC_MULTADD || solver == AMGB_SOLVER_ASYNC_AFACX) {
-      // the persistent kernel streams CTA-sized blocks (bulk copies start 8-entry aligned)
-      std::vector<int4> cb;
-      int rr = 0;
-      while (rr < nrows) {
-         const int start = rr;
-         const long q0 = rp[start] & ~7;
-         while (rr < nrows && rr - start < AMGB_STREAM_CAP && (long)rp[rr + 1] - q0 <= AMGB_STREAM_CAP) rr++;
-         if (rr == start) rr++;
-         cb.push_back(make_int4(start, rr, rp[start], rp[rr]));
-      }
-      int4 *d_cb;
-      if ((rc = dev_upload(c, &d_cb, cb.data(), cb.size()))) return rc;
-      CUDA_OK(c, cudaStreamSynchronize(c->stream));
-      M.ncblk = (int)cb.size();
-      M.cblk = d_cb;
-   }
    c->stream_blocks += nb;
    c->stream_blocks_staged_x += staged;
    return AMGB_OK;
@@ -429,11 +550,8 @@ int amgb_set_matrix(amgb_ctx *c, int kind, int level, int nrows, int ncols, int 
    CUDA_OK(c, cudaStreamSynchronize(c->stream));
    if (c->opt.use_sell && nrows >= 1024) {
       if ((rc = build_sell(c, M, nrows, rp, ci, va, 1, 0.15))) return rc;
-      // (the persistent asynchronous kernel runs few warps per SM: there the TMA-fed CTA blocks are faster
-      //  than any gather-per-lane layout -- 1.6 s vs 3.0 s for the 256^3 solve -- so SELL-C-sigma is skipped)
-      const bool persistent = c->opt.solver == AMGB_SOLVER_ASYNC_MULTADD || c->opt.solver == AMGB_SOLVER_ASYNC_AFACX;
       // small levels stay on the warp-stream kernel: with few slices the one-row-per-lane loop is latency bound
-      if (M.sell_slices == 0 && c->opt.sell_sigma > 1 && !persistent && nrows >= 262144 && (double)nnz / nrows < 96.0) {
+      if (M.sell_slices == 0 && c->opt.sell_sigma > 1 && nrows >= 262144 && (double)nnz / nrows < 96.0) {
          if ((rc = build_sell(c, M, nrows, rp, ci, va, c->opt.sell_sigma, 0.25))) return rc;
       }
    }
@@ -550,7 +668,6 @@ int amgb_setup(amgb_ctx *c)
    const bool multadd = o.solver == AMGB_SOLVER_MULTADD || o.solver == AMGB_SOLVER_ASYNC_MULTADD;
    c->symmetric = multadd && o.num_pre_smooth_sweeps > 0 && o.num_post_smooth_sweeps > 0 &&
                   (o.smoother == AMGB_SMOOTH_JACOBI || o.smoother == AMGB_SMOOTH_L1_JACOBI);
-   // (ASYNC_MULTADD: experimental, see k_async_amg<true> in async.cu)
    if (o.factor_level0 && !((o.solver == AMGB_SOLVER_MULTADD || o.solver == AMGB_SOLVER_ASYNC_MULTADD) && c->symmetric))
       return amgb_fail(c, AMGB_EINVAL, "factor_level0 applies to Multadd with the symmetrised (L1-)Jacobi smoother");
    int rc;
@@ -587,6 +704,7 @@ int amgb_setup(amgb_ctx *c)
          if (!part) c->launches += launch_colscale(c->stream, (int)pe, c->A[l].sell_ci, c->A[l].sell_va, cs, ssv);
          c->A[l].sell_sval = ssv;
       }
+      if (!part && (rc = build_sellu(c, c->A[l]))) return rc;
       if ((rc = dev_zero(c, &c->r[l], n))) return rc;
       if ((rc = dev_zero(c, &c->e[l], n))) return rc;
       if ((rc = dev_zero(c, &c->t[l], n))) return rc;
@@ -642,6 +760,8 @@ int amgb_get_residual(amgb_ctx *c, double *r)
 }
 
 }  // extern "C"
+
+int amgb_build_sellu(amgb_ctx *c, DevCSR &M) { return build_sellu(c, M); }
 
 // ---- enqueue helpers (no host synchronisation) ---------------------------------------------------
 static inline SpmvEpilogue epi(double alpha, double beta, const double *b, double gamma = 0.0, const double *cc = nullptr,
@@ -851,7 +971,7 @@ int amgb_fetch_scalar(amgb_ctx *c, double *out)
 
 extern "C" {
 
-// Explicit Gauss-Seidel blocks of the hybrid smoother on one level: bounds[0] = 0 < ... < bounds[nblocks] = n_level.  The
+// Explicit Gauss-Seidel blocks of the hybrid smoother on one level: bounds[0] = 0 <= ... <= bounds[nblocks] = n_level (an empty block = a thread left without rows).  The
 // reference's block is a thread's row range (src/SMEM_Smooth.cpp:567-581 with the nnz-balanced split of src/SMEM_Setup.cpp:954-959),
 // so its results depend on the thread count; with this list the device sweeps the very same blocks.  nblocks = 0 returns to the
 // uniform blocks of opt.jgs_block_rows.  Synchronous cycles and amgb_smooth only.
@@ -863,7 +983,7 @@ int amgb_set_jgs_blocks(amgb_ctx *c, int level, int nblocks, const int *bounds)
    if (nblocks < 0 || !bounds || n <= 0) return amgb_fail(c, AMGB_EINVAL, "block list given before the level's matrix, or empty");
    if (bounds[0] != 0 || bounds[nblocks] != n) return amgb_fail(c, AMGB_EINVAL, "block list must run from 0 to the level's row count %d", n);
    for (int b = 0; b < nblocks; b++)
-      if (bounds[b + 1] <= bounds[b]) return amgb_fail(c, AMGB_EINVAL, "block list is not increasing at block %d", b);
+      if (bounds[b + 1] < bounds[b]) return amgb_fail(c, AMGB_EINVAL, "block list is decreasing at block %d", b);   // an EMPTY block is a thread without rows (small levels)
    int *dev = nullptr;
    int rc = amgb_dev_alloc_bytes(c, (void **)&dev, sizeof(int) * ((size_t)nblocks + 1), false);
    if (rc) return rc;
@@ -1180,6 +1300,8 @@ int amgb_smem_solve(amgb_ctx *c, const double *f_host, double *u_host, double to
    if (solver == AMGB_SOLVER_ASYNC_MULTADD || solver == AMGB_SOLVER_ASYNC_AFACX) {
       if ((rc = amgb_solve_async(c, num_cycles, AMGB_CONVERGE_LOCAL, corrections, &rel, solve_seconds))) return rc;
       done = num_cycles;
+      // no per-iteration history exists for a chaotic iteration: the two ends only
+      if (hist) { for (int k = 0; k <= num_cycles; k++) hist[k] = 0.0; hist[0] = 1.0; hist[num_cycles] = rel; }
    } else {
       std::vector<double> h((size_t)num_cycles + 1, 0.0);
       if ((rc = amgb_solve_sync(c, tol, num_cycles, 0, 1.0, 1.0, h.data(), &done, solve_seconds))) return rc;
@@ -1251,6 +1373,15 @@ int amgb_l2_arena_bytes(amgb_ctx *c, long long *used, long long *capacity)
    if (!c) return AMGB_EINVAL;
    if (used) *used = (long long)c->arena_used;
    if (capacity) *capacity = (long long)c->arena_size;
+   return AMGB_OK;
+}
+
+// slices stored in the SELL-U encoding and their groups, over the whole hierarchy
+int amgb_sellu_stats(amgb_ctx *c, long long *slices, long long *groups)
+{
+   if (!c) return AMGB_EINVAL;
+   if (slices) *slices = c->sellu_slices;
+   if (groups) *groups = c->sellu_groups;
    return AMGB_OK;
 }
 

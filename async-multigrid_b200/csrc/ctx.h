@@ -39,6 +39,7 @@ struct amgb_ctx {
    long long launches = 0;
    size_t bytes_allocated = 0;
    int host_threads = 1;   // threads for the upload-time layout conversions (set in amgb_create)
+   long sellu_slices = 0, sellu_groups = 0;               // SELL-U: encoded slices / groups over the whole hierarchy
    long stream_blocks = 0, stream_blocks_staged_x = 0;   // CSR-stream row blocks / those with staged x windows
    size_t l2_bytes = 0, max_window = 0, persist_max = 0;
    std::vector<void *> allocs;
@@ -52,9 +53,12 @@ struct amgb_ctx {
    bool alloc_in_arena = false;
    cudaAccessPolicyWindow window = {};
    bool window_valid = false;
-   bool async_ready = false;
-   int async_grid = 0;
+   bool async_ready = false, async_balanced = false, async_heavy = false;
+   int async_grid = 0, async_grid_used = 0, async_first = 0;
    std::vector<int> async_cta_begin;
+   std::vector<double> async_work;          // cost model of every group's program (seeds the CTA groups)
+   std::vector<double *> async_vec;         // [group][vector kind][level] -> device pointer of a group-private vector
+   double *async_r_shared = nullptr;        // shared residual (-res_compute_type global / -read_type res)
    // distributed
    DistState *dist = nullptr;
    // implicit extended-system BPX solver: per-level vectors (extended.cu)
@@ -90,6 +94,7 @@ bool amgb_dist_level_distributed(const amgb_ctx *c, int level);
 
 // helpers exported by context.cu to async.cu / dist.cu
 int amgb_dev_alloc_bytes(amgb_ctx *c, void **p, size_t bytes, bool zero);
+int amgb_build_sellu(amgb_ctx *c, DevCSR &M);   // SELL-U encoding of a sliced-ELL matrix whose scaled values are final
 void enq_spmv(amgb_ctx *c, const DevCSR &M, bool sval, const double *x, double *y, const SpmvEpilogue &e, bool norm);
 void enq_residual(amgb_ctx *c);
 void enq_cycle(amgb_ctx *c, double *target, bool accumulate);

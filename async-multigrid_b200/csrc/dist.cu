@@ -393,6 +393,7 @@ int amgb_dist_setup(amgb_ctx *c)
          if (c->A[l].sell_slices > 0)
             c->launches += launch_colscale(c->stream, (int)c->sell_entries[&c->A[l]], c->A[l].sell_ci, c->A[l].sell_va, d->ws[l],
                                            const_cast<double *>(c->A[l].sell_sval));
+         if ((rc = amgb_build_sellu(c, c->A[l]))) return rc;      // (the scaled values of a partitioned level are final only now)
       }
    }
    if ((rc = amgb_dev_alloc_bytes(c, (void **)&d->partials3, sizeof(double) * 3 * (size_t)c->npartials, true))) return rc;

@@ -304,7 +304,7 @@ int launch_spmv_units(const LaunchCfg &cfg, cudaStream_t st, const DevCSR &M, in
    DevCSR V = M;
    SpmvEpilogue ev = e;
    double *yv = y;
-   if (M.sell_slices > 0) { V.sell_off += u0; V.sell_base += u0; V.sell_slices = u1 - u0; }
+   if (M.sell_slices > 0) { V.sell_off += u0; V.sell_base += u0; V.sell_slices = u1 - u0; if (V.su_off) V.su_off += u0; }
    else if (M.nblk > 0) { V.blk += u0; if (V.blkx) V.blkx += u0; V.nblk = u1 - u0; }
    else {
       V.rp += u0; V.nrows = u1 - u0; yv += u0;

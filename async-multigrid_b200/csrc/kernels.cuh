@@ -11,7 +11,11 @@ template <bool RO>
 __device__ __forceinline__ double ld_x(const double *p)
 {
    if (RO) return __ldg(p);
-   return ld_cg(p);
+   // persistent kernel: a plain (L1-cached, coherent-path) load.  Every group barrier ends with __threadfence(), which on
+   // sm_100 is MEMBAR.SC.GPU + CCTL.IVALL (the SM's L1 is invalidated), so a line cached before the barrier can never
+   // serve a load after it: vectors the group wrote in the previous phase are read fresh, and gathers get L1 reuse.
+   // (__ldg / ld.global.nc would be wrong here: the data changes during the launch.)
+   return ld_ca(p);
 }
 
 // ---- CSR, LPR lanes per row (vector-per-row; LPR = 32 is warp-per-row) --------------------------
@@ -36,7 +40,7 @@ __device__ __forceinline__ double csr_rows_team(const DevCSR &M, const double *_
       acc = subwarp_sum<LPR>(acc);
       if (lane == 0 && ok) {
          double v = epilogue_apply<RO>(e, row, acc);
-         y[row] = v;
+         epilogue_store<RO>(e, y, row, v);
          if (want_sumsq) sumsq += v * v;
       }
    }
@@ -58,14 +62,28 @@ __device__ __forceinline__ double sell_rows_team(const DevCSR &M, const double *
       const int width = (__ldg(M.sell_off + sl + 1) - off) >> 5;
       int row = ((sl + M.sell_base) << 5) + lane;
       if (M.sell_perm) row = __ldg(M.sell_perm + row);
-      const int *__restrict__ cp = M.sell_ci + off + lane;
-      const double *__restrict__ vp = va + off + lane;
       double acc = 0.0;
+      int g0 = 0, g1 = 0;
+      if (M.su_off) { g0 = __ldg(M.su_off + sl); g1 = __ldg(M.su_off + sl + 1); }
+      if (g1 > g0) {
+         // SELL-U slice: a handful of (delta, mask, value) groups shared by the 32 rows; the group records are read at
+         // a warp-uniform address (one broadcast transaction), the x gathers of a group are one or two full lines
+         const double *__restrict__ gv = SVAL ? M.su_sval : M.su_va;
 #pragma unroll 4
-      for (int k = 0; k < width; k++) acc += ld_stream(vp + (k << 5)) * ld_x<RO>(x + ld_stream(cp + (k << 5)));
+         for (int g = g0; g < g1; g++) {
+            const int2 dm = __ldg(M.su_dm + g);
+            const double v = __ldg(gv + g);
+            if ((static_cast<unsigned int>(dm.y) >> lane) & 1u) acc += v * ld_x<RO>(x + row + dm.x);
+         }
+      } else {
+         const int *__restrict__ cp = M.sell_ci + off + lane;
+         const double *__restrict__ vp = va + off + lane;
+#pragma unroll 4
+         for (int k = 0; k < width; k++) acc += ld_stream(vp + (k << 5)) * ld_x<RO>(x + ld_stream(cp + (k << 5)));
+      }
       if (row >= 0 && row < M.nrows) {
          double v = epilogue_apply<RO>(e, row, acc);
-         y[row] = v;
+         epilogue_store<RO>(e, y, row, v);
          if (want_sumsq) sumsq += v * v;
       }
    }
@@ -373,25 +391,6 @@ __device__ __forceinline__ double csr_rows_dispatch(const DevCSR &M, const doubl
    }
 }
 
-
-// dispatch on storage + lanes per row
-// (team_tid, team_size) = (team_cta * 256 + threadIdx.x, team_nctas * 256); smem: AMGB_TEAM_SMEM bytes
-// of 16-byte aligned shared memory
-template <bool RO, bool SVAL>
-__device__ __forceinline__ double spmv_team(const DevCSR &M, const double *x, double *y, const SpmvEpilogue &e,
-                                            int team_tid, int team_size, bool want_sumsq, unsigned char *smem)
-{
-   if (M.sell_slices > 0) return sell_rows_team<RO, SVAL>(M, x, y, e, team_tid, team_size, want_sumsq);
-   // inside the persistent kernel (few resident warps, 80 registers) the TMA-fed CTA blocks win over the
-   // warp chunks of the stand-alone kernels (measured: 1.3 s vs 2.3 s for the 256^3 asynchronous solve)
-   if (M.ncblk > 0)
-      return stream_rows_team<RO, SVAL, 256, AMGB_STREAM_CAP, 0, AMGB_TEAM_STAGES>(M, x, y, e, team_tid >> 8, team_size >> 8, smem,
-                                                                                  want_sumsq, M.cblk, M.ncblk);
-   if (M.nblk > 0 && M.wept > 0 && M.wept <= 8)      // warp chunks: every warp of the team is an independent worker
-      return warp_stream_rows_team<RO, SVAL, 8>(M, x, y, e, team_tid >> 5, team_size >> 5,
-                                                reinterpret_cast<double *>(smem) + ((threadIdx.x >> 5) << 8), want_sumsq);
-   return csr_rows_dispatch<RO, SVAL>(M, x, y, e, team_tid, team_size, want_sumsq);
-}
 
 // ---- hybrid Jacobi / Gauss-Seidel (src/SMEM_Smooth.cpp:533-586) ----------------------------------
 // Gauss-Seidel inside a block of `B` consecutive rows (one thread walks one block in row order),

@@ -2,6 +2,8 @@
 // asynchronous kernel (async.cu).  Every launcher returns the number of kernels it launched.
 #pragma once
 #include "common.cuh"
+#include "amg_b200.h"
+#include <vector>
 
 struct LaunchCfg {
    int num_sms = 148;
@@ -63,47 +65,63 @@ int launch_l1(cudaStream_t st, const DevCSR &A, double *l1, double *inv_l1);
 int launch_colscale(cudaStream_t st, int nnz, const int *ci, const double *va, const double *cs, double *out);
 
 // ---- persistent asynchronous kernel (async.cu) ---------------------------------------------------
+// The kernel is an interpreter: every level's CTA group loops over its own PROGRAM, a short list of operations (SpMV with a
+// fused epilogue, vector ops, smoother sweeps, the correction count / stop test) separated by group barriers.  The host
+// builds the programs from the solver options (async_build_program, pure host code: the CPU test suite interprets the same
+// programs in numpy against the CPU restatement), so Multadd / AFACx, explicit or factorised level-0 transfers, -read_type,
+// -res_compute_type and -async_type are host-side variations of one small kernel.
 #define AMGB_MAX_LEVELS 32
-struct AsyncLevelVecs {           // per CTA group (the reference's level_vector[k], src/SMEM_Setup.cpp:314-341)
-   double *r[AMGB_MAX_LEVELS];    // residual chain r_0 .. r_k
-   double *e[AMGB_MAX_LEVELS];    // correction chain e_k .. e_0
-   double *t[AMGB_MAX_LEVELS];    // scratch (u_prev / AFACx work)
-   double *w[AMGB_MAX_LEVELS];    // scratch (AFACx r_fine)
-   double *u_local;               // the group's private copy of the fine solution
+enum { AOP_SPMV = 0, AOP_SCALE = 1, AOP_COPY = 2, AOP_ZERO = 3, AOP_UPDATE = 4, AOP_COUNT_STOP = 5, AOP_LOCK = 6, AOP_UNLOCK = 7,
+       AOP_JGS = 8, AOP_ASYNC_GS = 9 };
+// vectors a program names: id = kind * 64 + level (group-private unless said otherwise)
+enum { AV_NONE = -1, AV_F = 0 /* shared f */, AV_U = 1 /* shared u */, AV_RS = 2 /* shared residual (GLOBAL / READ_RES) */,
+       AV_R = 3, AV_E = 4, AV_T = 5, AV_W = 6, AV_UL = 7 /* private copy of u */, AV_T0 = 8 /* level-0 scratch */,
+       AV_FACC = 9 /* accumulated corrections (READ_RES) */, AV_WS = 10 /* w/d (read-only) */, AV_INVL1 = 11 /* 1/l1 (read-only) */ };
+#define AV_ID(kind, level) ((kind) * 64 + (level))
+struct AsyncOpSym {                // one operation, symbolic (what the CPU tests interpret)
+   int type;                       // AOP_*
+   int mat_kind, mat_level;        // AOP_SPMV / AOP_JGS / AOP_ASYNC_GS: AMGB_MAT_* and level
+   int sval;                       // AOP_SPMV: the column-scaled values A*diag(w/d)
+   int range;                      // 0: the whole operation is shared by the CTAs of the group; 1: this CTA's slice of the level-0 rows
+                                   //    (rows dealt to ALL CTAs of the grid: -res_compute_type global)
+   int barrier;                    // group barrier after the operation
+   int x, y;                       // input / output vector ids (y = AV_NONE: the result goes to the reduction target only)
+   int b, c, rs, b2, xs;           // epilogue operands: y_i = gamma*c_i + rs_i*(beta*b_i + beta2*b2_i + alpha*(M x)_i) + xself*xs_i
+   int red, red_copy, acc;         // red += red_scale * y_i (fp64 reduction into a SHARED vector), red_copy_i = red_i afterwards; acc_i += y_i
+   int level, sweeps, zero;        // smoother operations: level, sweeps, zero initial guess
+   int locked;                     // AOP_UPDATE: plain read-modify-write (inside the SEMI_ASYNC critical section) instead of reductions
+   double alpha, beta, gamma, beta2, xself, red_scale;
+};
+struct AsyncOp {                   // the same with device pointers
+   int type, mat_kind, mat_level, sval, range, barrier, level, sweeps, zero, locked;
+   const double *x;
+   double *y;
+   SpmvEpilogue e;
 };
 struct AsyncParams {
    int num_levels;
-   int solver;                    // AMGB_SOLVER_ASYNC_MULTADD / ASYNC_AFACX
+   int first_group;                // 0; 1 with -res_compute_type global (level 0 has no group of its own)
    int smoother;
-   int symmetric;
-   int fine_sweeps, coarse_sweeps;
    int jgs_block_rows;
    int jgs_lpb[AMGB_MAX_LEVELS];  // lanes per hybrid-JGS block on every level (4/8/16/32 from the mean row length; 0: one thread per block)
    int num_cycles;
    int converge_type;
    DevCSR A[AMGB_MAX_LEVELS], P[AMGB_MAX_LEVELS], R[AMGB_MAX_LEVELS];
-   const double *ws[AMGB_MAX_LEVELS];       // w/d
-   const double *inv_l1[AMGB_MAX_LEVELS];   // 1/l1
-   AsyncLevelVecs g[AMGB_MAX_LEVELS];
    int cta_begin[AMGB_MAX_LEVELS + 1];      // CTA range of every level's group
-   const double *f;
-   double *u;                               // shared fine solution (atomic adds)
+   const AsyncOp *ops;                      // all programs, group after group
+   int op_begin[AMGB_MAX_LEVELS + 1];       // program of group q: ops[op_begin[q] .. op_begin[q+1])
+   int n0;
+   double *u;                               // shared fine solution
    unsigned int *barrier_count;             // [L] arrive counters
    volatile unsigned int *barrier_gen;      // [L] generations
    int *num_correct;                        // [L] local_num_correct
    int *group_stop;                         // [L] the group root's stop decision (GLOBAL rule)
    volatile int *converge_flag;             // thread.converge_flag
-   // (appended last so that the offsets the round-1 kernel reads stay what they were)
-   double *t0[AMGB_MAX_LEVELS];             // per group: level-0 scratch of the factorised level-0 transfers (k_async_amg_fact0)
+   int *lock;                               // SEMI_ASYNC: the omp lock around "u += e; u_k = u"
+   unsigned long long *group_ns;            // [L] nanoseconds every group spent in the kernel (CTA-group balancing)
 };
-int launch_async(const LaunchCfg &cfg, cudaStream_t st, const AsyncParams *params_dev, int grid, int block,
-                 const cudaAccessPolicyWindow *window);
-int async_max_grid(int block);
-// experimental copy with the level-0 transfers in factorised form (async_fact0.cu)
-int launch_async_fact0(const LaunchCfg &cfg, cudaStream_t st, const AsyncParams *params_dev, int grid, int block,
-                       const cudaAccessPolicyWindow *window);
-int async_max_grid_fact0(int block);
-// experimental copy with every SpMV behind a non-inlined call (async_ni.cu; AMGB_ASYNC_NOINLINE=1)
-int launch_async_ni(const LaunchCfg &cfg, cudaStream_t st, const AsyncParams *params_dev, int grid, int block,
-                    const cudaAccessPolicyWindow *window);
-int async_max_grid_ni(int block);
+// heavy: the instantiation that carries the Gauss-Seidel-type smoothers (more registers, fewer CTAs per SM)
+int launch_async(cudaStream_t st, const AsyncParams *params_dev, int grid, int block, bool heavy, const cudaAccessPolicyWindow *window);
+int async_max_grid(int block, bool heavy);
+// host-only: the program of group q (appended to `ops`); returns AMGB_OK or AMGB_EINVAL for an unsupported combination
+int async_build_program(const amgb_options &o, int L, bool symmetric, bool fact0, int q, std::vector<AsyncOpSym> &ops);

@@ -24,7 +24,8 @@ ABI_SYMBOLS = [
     "amgb_set_num_levels", "amgb_set_matrix", "amgb_set_options", "amgb_setup",
     "amgb_set_rhs", "amgb_set_solution", "amgb_get_solution", "amgb_get_residual",
     "amgb_spgemv", "amgb_spgemv_transpose", "amgb_smooth", "amgb_set_jgs_blocks", "amgb_norm2", "amgb_cycle", "amgb_eigs_power", "amgb_solve_sync", "amgb_solve_async",
-    "amgb_async_groups", "amgb_solve_extended", "amgb_smooth_transfer", "amgb_host_csr_free", "amgb_smem_solve", "amgb_time_residual", "amgb_level_storage", "amgb_time_spmv", "amgb_stream_stats", "amgb_l2_arena_bytes",
+    "amgb_async_groups", "amgb_solve_extended", "amgb_smooth_transfer", "amgb_host_csr_free", "amgb_smem_solve", "amgb_time_residual", "amgb_level_storage", "amgb_time_spmv", "amgb_stream_stats", "amgb_l2_arena_bytes", "amgb_sellu_stats",
+    "amgb_sellu_encode_host", "amgb_host_free", "amgb_async_program", "amgb_async_group_times",
     "amgb_dist_unique_id", "amgb_dist_init", "amgb_dist_set_level", "amgb_dist_setup", "amgb_dist_set_rhs",
     "amgb_dist_get_solution", "amgb_dist_solve_sync", "amgb_dist_solve_sync_accel", "amgb_dist_stats",
     "amgb_dist_ipc_export_solution", "amgb_dist_ipc_open_neighbours", "amgb_dist_async_smooth", "amgb_dist_residual_norm",
@@ -38,7 +39,8 @@ class Options(C.Structure):
                 ("num_pre_smooth_sweeps", C.c_int), ("num_post_smooth_sweeps", C.c_int),
                 ("num_fine_smooth_sweeps", C.c_int), ("num_coarse_smooth_sweeps", C.c_int),
                 ("jgs_block_rows", C.c_int), ("use_sell", C.c_int), ("l2_persist", C.c_int), ("use_stream", C.c_int),
-                ("factor_level0", C.c_int), ("coarse_solve", C.c_int), ("sell_sigma", C.c_int), ("stream_variant", C.c_int)]
+                ("factor_level0", C.c_int), ("coarse_solve", C.c_int), ("sell_sigma", C.c_int), ("stream_variant", C.c_int),
+                ("sell_uniform", C.c_int), ("async_type", C.c_int), ("res_compute_type", C.c_int), ("read_type", C.c_int)]
 
 
 class HostCSR(C.Structure):
@@ -94,7 +96,10 @@ def load_library():
     L.amgb_time_spmv.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, DP]
     L.amgb_stream_stats.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     L.amgb_l2_arena_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+    L.amgb_sellu_stats.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     L.amgb_async_groups.argtypes = [C.c_void_p, IP, IP]
+    L.amgb_async_group_times.argtypes = [C.c_void_p, DP]
+    L.amgb_async_program.argtypes = [C.POINTER(Options), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, IP]
     L.amgb_ipc_export_solution.argtypes = [C.c_void_p, C.c_char_p]
     L.amgb_ipc_open_peers.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
     L.amgb_async_dist_correct.argtypes = [C.c_void_p, C.c_int]
@@ -136,7 +141,8 @@ class Solver:
 
     def __init__(self, h, solver=H.MULTADD, smoother=H.JACOBI, smooth_weight=1.0, num_pre=1, num_post=1,
                  fine_sweeps=1, coarse_sweeps=1, jgs_block_rows=8, use_sell=True, l2_persist=True, use_stream=True,
-                 stream_variant=None, sell_sigma=None, coarse_solve=False, factor_level0=False, device=0, jgs_blocks=None):
+                 stream_variant=None, sell_sigma=None, coarse_solve=False, factor_level0=False, device=0, jgs_blocks=None,
+                 sell_uniform=None, async_type=0, res_compute_type=0, read_type=0):
         self.L = load_library()
         self.h = h
         self.ctx = C.c_void_p()
@@ -162,6 +168,11 @@ class Solver:
             o.sell_sigma = int(sell_sigma)
         elif "AMGB_SELL_SIGMA" in os.environ:
             o.sell_sigma = int(os.environ["AMGB_SELL_SIGMA"])
+        if sell_uniform is not None:
+            o.sell_uniform = int(sell_uniform)
+        elif "AMGB_SELL_UNIFORM" in os.environ:
+            o.sell_uniform = int(os.environ["AMGB_SELL_UNIFORM"])
+        o.async_type, o.res_compute_type, o.read_type = int(async_type), int(res_compute_type), int(read_type)
         self.options = o
         self._ck(self.L.amgb_set_options(self.ctx, C.byref(o)))
         self._ck(self.L.amgb_set_num_levels(self.ctx, h.num_levels))
@@ -353,16 +364,53 @@ class Solver:
         self._ck(self.L.amgb_l2_arena_bytes(self.ctx, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def sellu_stats(self):
+        """(slices stored in the SELL-U encoding, groups) over the whole hierarchy"""
+        a, b = C.c_longlong(0), C.c_longlong(0)
+        self._ck(self.L.amgb_sellu_stats(self.ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def is_sell(self, kind, level):
         v = C.c_int(0)
         self._ck(self.L.amgb_level_storage(self.ctx, kind, level, C.byref(v)))
         return bool(v.value)
+
+    def async_group_times(self):
+        """seconds every level group spent inside the last launch of the persistent kernel"""
+        t = np.zeros(self.h.num_levels)
+        self._ck(self.L.amgb_async_group_times(self.ctx, _dp(t)))
+        return t
 
     def async_groups(self):
         cb = np.zeros(self.h.num_levels + 1, dtype=np.int32)
         g = C.c_int(0)
         self._ck(self.L.amgb_async_groups(self.ctx, _ip(cb), C.byref(g)))
         return cb, g.value
+
+
+class AsyncOpSym(C.Structure):
+    """csrc/launch.h AsyncOpSym: one operation of a level group's program (symbolic)"""
+    _fields_ = [(k, C.c_int) for k in ("type", "mat_kind", "mat_level", "sval", "range", "barrier", "x", "y", "b", "c", "rs", "b2",
+                                       "xs", "red", "red_copy", "acc", "level", "sweeps", "zero", "locked")] + \
+               [(k, C.c_double) for k in ("alpha", "beta", "gamma", "beta2", "xself", "red_scale")]
+
+
+def async_program(num_levels, solver, smoother=H.JACOBI, symmetric=True, factor_level0=False, fine_sweeps=1, coarse_sweeps=1,
+                  async_type=0, res_compute_type=0, read_type=0):
+    """the programs the persistent asynchronous kernel interprets (amgb_async_program; host-only, no GPU needed):
+    list over the level groups of lists of AsyncOpSym"""
+    L = load_library()
+    o = Options()
+    L.amgb_default_options(C.byref(o))
+    o.solver, o.smoother = solver, smoother
+    o.num_fine_smooth_sweeps, o.num_coarse_smooth_sweeps = fine_sweeps, coarse_sweeps
+    o.async_type, o.res_compute_type, o.read_type = async_type, res_compute_type, read_type
+    ops = (AsyncOpSym * 4096)()
+    ob = np.zeros(num_levels + 1, dtype=np.int32)
+    rc = L.amgb_async_program(C.byref(o), num_levels, int(symmetric), int(factor_level0), ops, 4096, _ip(ob))
+    if rc != 0:
+        raise AmgError("amgb_async_program failed (%d): unsupported combination of asynchronous options" % rc)
+    return [[ops[i] for i in range(ob[q], ob[q + 1])] for q in range(num_levels)]
 
 
 def dist_unique_id():
@@ -381,7 +429,7 @@ class DistSolver:
     partition.RankPlan; `uid` the 128-byte id from dist_unique_id() of rank 0."""
 
     def __init__(self, plan, uid, smooth_weight=1.0, num_pre=1, num_post=1, use_sell=True, use_stream=True,
-                 coarse_solve=False, solver=H.MULTADD, factor_level0=False, device=0, smoother=H.JACOBI):
+                 coarse_solve=False, solver=H.MULTADD, factor_level0=False, device=0, smoother=H.JACOBI, sell_uniform=None):
         self.L = load_library()
         self.plan = plan
         self.ctx = C.c_void_p()
@@ -396,6 +444,10 @@ class DistSolver:
         o.use_sell, o.use_stream = int(use_sell), int(use_stream)
         o.coarse_solve = int(coarse_solve)
         o.factor_level0 = int(factor_level0)
+        if sell_uniform is not None:
+            o.sell_uniform = int(sell_uniform)
+        elif "AMGB_SELL_UNIFORM" in os.environ:
+            o.sell_uniform = int(os.environ["AMGB_SELL_UNIFORM"])
         self._ck(self.L.amgb_set_options(self.ctx, C.byref(o)))
         nl = plan.num_levels
         self._ck(self.L.amgb_set_num_levels(self.ctx, nl))

@@ -65,6 +65,17 @@ typedef struct {
    int sell_sigma;              /* > 1: SELL-C-sigma (rows sorted by length inside windows of sigma rows) for the
                                    non-stencil matrices whose padding then stays <= 25 %; 0/1: off */
    int stream_variant;          /* geometry of the CSR-stream kernel (csrc/launch.h kStreamVariants; default 8 = warp-granular, 256-entry chunks) */
+   int sell_uniform;            /* 1 (default): SELL-U, a lossless re-encoding of sliced-ELL slices whose entries take few distinct
+                                   (column - row, value) pairs (constant-coefficient stencil levels): the kernel then streams the vectors
+                                   only.  Same CSR semantics, a row's terms summed in another order; 0: off */
+   /* options of the asynchronous solver (src/SMEM_Main.cpp:66,71,93; -async_type, -res_compute_type, -read_type) */
+   int async_type;              /* 0 FULL_ASYNC (default): u += e with fp64 global reductions; 1 SEMI_ASYNC: a group's
+                                   "u += e; u_k = u" is one critical section (omp lock, src/SMEM_Async_AMG.cpp:238-283) */
+   int res_compute_type;        /* 0 LOCAL (default): every level group recomputes the whole fine residual from its own copy of u;
+                                   1 GLOBAL (async Multadd only, src/SMEM_Main.cpp:650-660): the rows of level 0 are dealt to ALL CTAs,
+                                   which smooth level 0 and recompute the shared residual on their slices (src/SMEM_Async_AMG.cpp:35-70,356-416) */
+   int read_type;               /* 0 READ_SOL (default): groups share the solution u; 1 READ_RES: groups share the residual,
+                                   r -= A_0 e (src/SMEM_Async_AMG.cpp:227-236,285-296), u assembled at the end (:416-426) */
 } amgb_options;
 
 void amgb_default_options(amgb_options *opt);
@@ -104,8 +115,8 @@ int amgb_spgemv_transpose(amgb_ctx *ctx, int kind, int level, const double *x, d
  * input when zero_guess != 0).  symmetric != 0 selects SMEM_Sync_Symmetric{,L1}Jacobi. */
 int amgb_smooth(amgb_ctx *ctx, int level, int smoother, int symmetric, int sweeps, int zero_guess,
                 const double *f, double *u);
-/* Explicit Gauss-Seidel block list of the hybrid Jacobi / Gauss-Seidel smoother on one level: bounds[0] = 0 < ... <
- * bounds[nblocks] = rows of the level.  Replaces the thread row ranges thread.A_ns / A_ne[level][tid] that PartitionGrids
+/* Explicit Gauss-Seidel block list of the hybrid Jacobi / Gauss-Seidel smoother on one level: bounds[0] = 0 <= ... <=
+ * bounds[nblocks] = rows of the level (empty blocks allowed: threads without rows).  Replaces the thread row ranges thread.A_ns / A_ne[level][tid] that PartitionGrids
  * (src/SMEM_Setup.cpp:954-959) hands to SMEM_Sync_HybridJacobiGaussSeidel (src/SMEM_Smooth.cpp:533-586): with the reference's own
  * ranges the device reproduces a run of the reference with that many threads per level.  nblocks = 0: back to the uniform
  * blocks of opt.jgs_block_rows.  Call after the level's matrix is uploaded; synchronous cycles and amgb_smooth only. */
@@ -143,6 +154,15 @@ int amgb_solve_async(amgb_ctx *ctx, int num_cycles, int converge_type, int *corr
  * src/SMEM_Setup.cpp:770-868,1083-1160): cta_begin[num_levels + 1], *grid = total CTAs.  Valid after the first
  * amgb_solve_async. */
 int amgb_async_groups(amgb_ctx *ctx, int *cta_begin, int *grid);
+
+/* seconds every level group spent inside the last launch of the persistent kernel (its root's %globaltimer): the measured
+ * side of the CTA-group balancing (the reference prints per-thread wall times the same way, src/SMEM_Main.cpp:800-870) */
+int amgb_async_group_times(amgb_ctx *ctx, double *seconds /* num_levels */);
+/* Host-only (no CUDA call; the CPU test suite interprets the result against the oracle): the PROGRAMS the persistent kernel
+ * interprets for these options on a hierarchy of num_levels levels -- one list of operations per level group (restriction
+ * chain, smoother, prolongation chain, "u += e; u_k = u", count / stop, residual; csrc/launch.h AsyncOpSym, 128 bytes each).
+ * ops: caller's array of max_ops records; op_begin[num_levels + 1]. */
+int amgb_async_program(const amgb_options *opt, int num_levels, int symmetric, int factor_level0, void *ops, int max_ops, int *op_begin);
 
 /* SMEM_ExtendedSystemSolve with IMPLICIT_EXTENDED_SYSTEM_BPX, synchronous (`-solver iebpx`; src/SMEM_ExtendedSystem.cpp:9-836,
  * finish :777-817, ExtendedSystemImplicitMatVec :838-907) on the resident f: Chebyshev-accelerated (mu, delta from
@@ -184,6 +204,14 @@ int amgb_level_storage(amgb_ctx *ctx, int kind, int level, int *is_sell);
 /* event-timed y = M x for one matrix of the hierarchy (tools/spmv_sweep.py) and CSR-stream block statistics */
 int amgb_time_spmv(amgb_ctx *ctx, int kind, int level, int use_scaled_values, int reps, double *ms_per_launch);
 int amgb_stream_stats(amgb_ctx *ctx, long long *blocks, long long *blocks_with_staged_x);
+/* slices stored in the SELL-U encoding (amgb_options.sell_uniform) and their (delta, mask, value) groups */
+int amgb_sellu_stats(amgb_ctx *ctx, long long *slices, long long *groups);
+/* Host-only probe of the SELL-U encoder (no CUDA call; CPU test suite): CSR + column-scaled values in, per-slice group
+ * offsets and the groups' delta / lane mask / value / scaled value out (malloc'ed: release with amgb_host_free).  Returns
+ * the number of slices. */
+int amgb_sellu_encode_host(int nrows, const int *row_ptr, const int *col_idx, const double *values, const double *scaled_values,
+                           int **group_off, int **delta, unsigned int **mask, double **gvalues, double **gscaled, int *ngroups);
+void amgb_host_free(void *p);
 /* coarse-hierarchy bytes living in the L2-pinned arena (cudaAccessPolicyWindow of the persistent kernel) */
 int amgb_l2_arena_bytes(amgb_ctx *ctx, long long *used, long long *capacity);
 

@@ -53,8 +53,21 @@ def has_gpu():
         return False
 
 
-# tolerance of the synchronous history test: |relres_gpu[k] - relres_ref[k]| <= HIST_TOL where
-# relres = ||r_k|| / ||r_0||  ("within 1e-10 relative", BASELINE.json north_star; relative to r_0:
-# two CPU runs with different summation order already differ by 1e-8 relative to ||r_k|| itself
-# once ||r_k|| ~ 1e-9 ||r_0||)
-HIST_TOL = 1e-10
+# Tolerance of the synchronous history tests, relres[k] = ||r_k|| / ||r_0||:
+#   |relres_gpu[k] - relres_ref[k]| <= HIST_TOL (absolute, i.e. relative to ||r_0||)   for every k, and
+#   |relres_gpu[k] - relres_ref[k]| <= HIST_REL * relres_ref[k]                        for every k (the tail included).
+# BASELINE.json asks for 1e-10; observed on the B200: <= 1e-16 absolute (summation order is the only difference between
+# the CPU loops and the kernels).  The relative bound is what keeps the tail honest: at relres ~ 1e-9 an absolute 1e-13
+# alone would still admit 1e-4 relative.  A rounding-level perturbation 1e-16 |u| of the iterate moves the residual by
+# ~1e-16 cond-ish / relres relative, so the relative bound cannot be pushed to 1e-10 at the tail.
+HIST_TOL = 1e-13
+HIST_REL = 1e-6
+
+
+def assert_hist_close(got, want, what=""):
+    got, want = np.asarray(got), np.asarray(want)
+    assert len(got) == len(want), (what, len(got), len(want))
+    d = np.abs(got - want)
+    assert np.max(d) <= HIST_TOL, (what, "absolute", float(np.max(d)))
+    rel = d / np.maximum(np.abs(want), 1e-300)
+    assert np.max(rel) <= HIST_REL, (what, "relative", float(np.max(rel)), int(np.argmax(rel)))

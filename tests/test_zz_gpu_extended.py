@@ -10,7 +10,7 @@ import pytest
 
 import async_multigrid_b200 as amg
 from async_multigrid_b200 import hierarchy as H
-from conftest import GOLDEN, HIST_TOL, hierarchy_from_golden
+from conftest import GOLDEN, HIST_TOL, assert_hist_close, hierarchy_from_golden
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -91,7 +91,6 @@ def test_eebpx_matches_oracle_and_reference_fixture():
     s.close()
 
 
-@pytest.mark.skipif(os.environ.get("AMGB_EXPERIMENTAL") != "1", reason="experimental path (device SmoothTransfer), not validated on hardware yet")
 @pytest.mark.parametrize("prob,n,kind", [("7pt", 12, H.JACOBI), ("5pt", 40, H.L1_JACOBI), ("27pt", 8, H.JACOBI)])
 def test_device_smooth_transfer_matches_host(prob, n, kind):
     """Pbar = G P and Rbar = P^T GT built on the device (expand - sort - compress) against the host
@@ -108,10 +107,9 @@ def test_device_smooth_transfer_matches_host(prob, n, kind):
             assert np.max(np.abs(got.data - want.data)) <= 1e-14 * np.max(np.abs(want.data))
 
 
-@pytest.mark.skipif(os.environ.get("AMGB_EXPERIMENTAL") != "1", reason="experimental path (factorised level-0 transfers in the persistent kernel), not validated on hardware yet")
 def test_async_factorised_level0_reaches_tolerance():
-    """k_async_amg_fact0: plain P_0 / R_0 with the smoothing factors applied on the fly inside the persistent kernel; with a
-    two-group hierarchy the chaotic iteration is sequential and must equal the explicit-product kernel to rounding"""
+    """factor_level0 with ASYNC_MULTADD: plain P_0 / R_0 with the smoothing factors applied on the fly inside the persistent
+    kernel (the program of csrc/async.cu async_build_program with fact0)"""
     w = 0.9
     A = H.laplacian("7pt", 24)
     h = H.amg_setup(A)
@@ -130,7 +128,6 @@ def test_async_factorised_level0_reaches_tolerance():
     assert true < 1e-9 and abs(true - out["relres"]) <= 1e-12, (true, ref["relres"])
 
 
-@pytest.mark.skipif(os.environ.get("AMGB_EXPERIMENTAL") != "1", reason="nonsymmetric operators on the device: test written after the GPU budget was spent")
 @pytest.mark.parametrize("a,atype", [((40.0, -20.0, 10.0), 3), ((10.0, 10.0, 10.0), 0)])
 def test_nonsymmetric_difconv_matches_oracle(a, atype):
     """`-problem difconv` (nonsymmetric 7-point convection-diffusion): operators and the synchronous Multadd history"""
@@ -141,11 +138,10 @@ def test_nonsymmetric_difconv_matches_oracle(a, atype):
     _, want, _ = O.Problem(h, H.MULTADD, H.JACOBI, 0.9).solve_sync(b, 1e-9, 100)
     s = amg.Solver(h, H.MULTADD, H.JACOBI, 0.9)
     got = s.SMEM_Solve(b, 1e-9, 100)["hist"]
-    assert len(got) == len(want) and np.max(np.abs(got - want)) <= HIST_TOL
+    assert_hist_close(got, want)
     s.close()
 
 
-@pytest.mark.skipif(os.environ.get("AMGB_EXPERIMENTAL") != "1", reason="test written after the GPU budget was spent")
 @pytest.mark.parametrize("name", ["lap5pt_n32", "lap7pt_n12"])
 def test_hybrid_jgs_single_block_matches_reference_fixture(name):
     """hybrid Jacobi / Gauss-Seidel against the reference's OWN object code: with one thread per level the reference's block
@@ -156,7 +152,7 @@ def test_hybrid_jgs_single_block_matches_reference_fixture(name):
     s = amg.Solver(h, H.MULTADD, H.HYBRID_JACOBI_GAUSS_SEIDEL, 0.9, num_pre=1, num_post=0, jgs_block_rows=h.n[0])
     got = s.SMEM_Solve(d["b"], 1e-9, 80)["hist"]
     want = g["%s_nt0_hist" % name]
-    assert len(got) == len(want) and np.max(np.abs(got - want)) <= HIST_TOL
+    assert_hist_close(got, want)
     s.close()
 
 
@@ -185,7 +181,6 @@ def test_async_single_group_matches_reference_fixture(name, tag, solver, base, w
     _async_fixture_case(name, tag, solver, base, w, 1)
 
 
-@pytest.mark.skipif(os.environ.get("AMGB_EXPERIMENTAL") != "1", reason="test written after the GPU budget was spent")
 @pytest.mark.parametrize("name", ["lap5pt_n32", "lap7pt_n12"])
 def test_async_afacx_two_sweeps_matches_reference_fixture(name):
     _async_fixture_case(name, "afacx2", H.ASYNC_AFACX, H.AFACX, 0.6, 2)
@@ -217,39 +212,10 @@ def test_dmem_mult_matches_reference_fixture(name):
     out = s.SMEM_Solve(d["b"], 1e-9, 100)
     s.close()
     want = g[name + "_hist"]
-    assert len(out["hist"]) == len(want) and np.max(np.abs(out["hist"] - want)) <= HIST_TOL
+    assert_hist_close(out["hist"], want)
     assert np.max(np.abs(out["u"] - g[name + "_x"])) <= 1e-11 * np.max(np.abs(out["u"]))
 
 
-@pytest.mark.skipif(os.environ.get("AMGB_EXPERIMENTAL") != "1", reason="experimental kernel variant, written after the GPU budget was spent")
-def test_async_noinline_variant_matches_the_measured_kernel():
-    """k_async_amg_ni (csrc/async_ni.cu, AMGB_ASYNC_NOINLINE=1): same source, SpMVs behind non-inlined calls.  On a two-level
-    hierarchy (deterministic) it must land on the sequential model like the measured kernel; on a full hierarchy it must converge."""
-    os.environ["AMGB_ASYNC_NOINLINE"] = "1"
-    try:
-        A = H.laplacian("5pt", 24)
-        h = H.amg_setup(A, max_levels=2)
-        h.build_transfers(H.MULTADD, 0.9)
-        b = H.rand_rhs(A.nrows)
-        s = amg.Solver(h, H.ASYNC_MULTADD, H.JACOBI, 0.9)
-        out = s.SMEM_Solve(b, 1e-9, 25)
-        s.close()
-        u, counts, rel = O.Problem(h, H.MULTADD, H.JACOBI, 0.9).solve_async_sequential(b, 25)
-        assert np.max(np.abs(out["u"] - u)) <= 1e-11 * np.max(np.abs(u))
-        A = H.laplacian("7pt", 32)
-        h = H.amg_setup(A)
-        h.build_transfers(H.MULTADD, 0.9)
-        b = H.rand_rhs(A.nrows)
-        s = amg.Solver(h, H.ASYNC_MULTADD, H.JACOBI, 0.9)
-        out = s.SMEM_Solve(b, 1e-9, 160)
-        s.close()
-        true = O.norm2(O.spgemv(h.A[0], out["u"], b, -1.0, 1.0)) / O.norm2(b)
-        assert true < 1e-9 and list(out["corrections"]) == [160] * h.num_levels
-    finally:
-        os.environ["AMGB_ASYNC_NOINLINE"] = "0"
-
-
-@pytest.mark.skipif(os.environ.get("AMGB_EXPERIMENTAL") != "1", reason="amgb_set_jgs_blocks was written after the GPU budget was spent")
 @pytest.mark.parametrize("name", ["lap5pt_n32", "lap7pt_n12"])
 @pytest.mark.parametrize("tag", ["nt0", "nt16"])
 def test_hybrid_jgs_reference_blocks_match_reference_fixture(name, tag):
@@ -263,5 +229,120 @@ def test_hybrid_jgs_reference_blocks_match_reference_fixture(name, tag):
     s = amg.Solver(h, H.MULTADD, H.HYBRID_JACOBI_GAUSS_SEIDEL, 0.9, num_pre=1, num_post=0, jgs_blocks=blocks)
     got = s.SMEM_Solve(d["b"], 1e-9, 80)["hist"]
     want = g["%s_%s_hist" % (name, tag)]
-    assert len(got) == len(want) and np.max(np.abs(got - want)) <= HIST_TOL
+    assert_hist_close(got, want)
     s.close()
+
+
+# ---- round 2: the options of the persistent kernel (-read_type res, -res_compute_type global, -async_type semi) and the
+# ---- factorised level-0 transfers, on the device.  The programs themselves are checked on the CPU (tests/test_async_program.py).
+def _two_level(prob="5pt", n=24, w=0.9):
+    A = H.laplacian(prob, n)
+    h = H.amg_setup(A, max_levels=2)
+    h.build_transfers(H.MULTADD, w)
+    return h, H.rand_rhs(A.nrows)
+
+
+def test_async_read_res_single_group_equals_sequential_model():
+    """-read_type res (src/SMEM_Async_AMG.cpp:227-236,285-296,416-426): one working group => deterministic => the oracle's
+    sequential model of that variant (pinned bit for bit by the reference's object code, tests/test_oracle_golden.py)"""
+    h, b = _two_level()
+    for K in (1, 9):
+        s = amg.Solver(h, H.ASYNC_MULTADD, H.JACOBI, 0.9, read_type=1)
+        out = s.SMEM_Solve(b, 1e-9, K)
+        s.close()
+        want, counts, rel = O.Problem(h, H.MULTADD, H.JACOBI, 0.9).solve_async_sequential(b, K, read_res=True)
+        assert list(out["corrections"]) == [K, K]
+        assert np.max(np.abs(out["u"] - want)) <= 1e-11 * np.max(np.abs(want))
+        assert abs(out["relres"] - rel) <= HIST_TOL
+
+
+def test_async_factorised_single_group_equals_sequential_model():
+    A = H.laplacian("7pt", 14)
+    h = H.amg_setup(A, max_levels=2)
+    h.build_transfers(H.MULTADD, 0.9)
+    b = H.rand_rhs(A.nrows)
+    want, counts, rel = O.Problem(h, H.MULTADD, H.JACOBI, 0.9).solve_async_sequential(b, 12)
+    hf = H.Hierarchy(h.A, h.P_plain)
+    hf.build_transfers(H.MULTADD, 0.9, factor_level0=True)
+    s = amg.Solver(hf, H.ASYNC_MULTADD, H.JACOBI, 0.9, factor_level0=True)
+    out = s.SMEM_Solve(b, 1e-9, 12)
+    s.close()
+    assert np.max(np.abs(out["u"] - want)) <= 1e-11 * np.max(np.abs(want))
+
+
+@pytest.mark.parametrize("kw,cycles", [(dict(read_type=1), 160), (dict(async_type=1), 160), (dict(res_compute_type=1), 250),
+                                       (dict(res_compute_type=1, factor_level0=True), 250), (dict(factor_level0=True), 160)])
+def test_async_option_variants_reach_tolerance(kw, cycles):
+    w = 0.9
+    A = H.laplacian("7pt", 32)
+    h = H.amg_setup(A)
+    h.build_transfers(H.MULTADD, w, factor_level0=kw.get("factor_level0", False))
+    b = H.rand_rhs(A.nrows)
+    s = amg.Solver(h, H.ASYNC_MULTADD, H.JACOBI, w, **kw)
+    out = s.SMEM_Solve(b, 1e-9, cycles)
+    first = 1 if kw.get("res_compute_type") else 0
+    assert list(out["corrections"][first:]) == [cycles] * (h.num_levels - first)
+    true = O.norm2(O.spgemv(h.A[0], out["u"], b, -1.0, 1.0)) / O.norm2(b)
+    assert abs(true - out["relres"]) <= 1e-12 * max(1.0, true)
+    assert true < 1e-9, (kw, true)
+    t = s.async_group_times()
+    assert np.all(t[first:] > 0.0)
+    print("async variant", kw, "relres", true, "group seconds", t)
+    s.close()
+
+
+def test_async_global_stop_rule_with_global_residual():
+    w = 0.9
+    A = H.laplacian("7pt", 24)
+    h = H.amg_setup(A)
+    h.build_transfers(H.MULTADD, w)
+    b = H.rand_rhs(A.nrows)
+    s = amg.Solver(h, H.ASYNC_MULTADD, H.JACOBI, w, res_compute_type=1)
+    s.set_rhs(b)
+    s.set_solution(None)
+    corr, rel, secs = s.solve_async(250, amg.solver.CONVERGE_GLOBAL)
+    assert corr[0] == 0 and np.all(corr[1:] >= 250)          # level 0 has no group of its own (finest_level = 1, src/Misc.cpp:428-433)
+    assert rel < 1e-9
+    s.close()
+
+
+def test_async_unsupported_option_combination_is_an_error():
+    A = H.laplacian("7pt", 12)
+    h = H.amg_setup(A)
+    h.build_transfers(H.AFACX, 0.6)
+    b = H.rand_rhs(A.nrows)
+    s = amg.Solver(h, H.ASYNC_AFACX, H.JACOBI, 0.6, res_compute_type=1)
+    with pytest.raises(amg.solver.AmgError):
+        s.SMEM_Solve(b, 1e-9, 5)
+    s.close()
+
+
+# ---- SELL-U (amgb_options.sell_uniform): the stencil levels stream no matrix at all; same operator as the regular encoding
+@pytest.mark.parametrize("prob,n", [("7pt", 20), ("27pt", 12), ("5pt", 70)])
+def test_sell_uniform_encoding_matches_regular_sliced_ell(prob, n):
+    w = 0.9
+    A = H.laplacian(prob, n)
+    h = H.amg_setup(A)
+    h.build_transfers(H.MULTADD, w)
+    b = H.rand_rhs(A.nrows)
+    su = amg.Solver(h, H.MULTADD, H.JACOBI, w, sell_uniform=1)
+    sr = amg.Solver(h, H.MULTADD, H.JACOBI, w, sell_uniform=0)
+    slices, groups = su.sellu_stats()
+    assert slices >= 0.9 * ((A.nrows + 31) // 32) and sr.sellu_stats() == (0, 0)
+    x = np.random.default_rng(0).standard_normal(A.nrows)
+    want = O.spgemv(h.A[0], x, b, -1.0, 1.0)
+    for s in (su, sr):
+        got = s.spgemv(amg.solver.MAT_A, 0, -1.0, x, 1.0, b)
+        assert np.max(np.abs(got - want)) <= 1e-13 * np.max(np.abs(want))
+        e = s.smooth(0, b, sweeps=1, symmetric=True)
+        ew = O.smooth("symmetric_jacobi", h.A[0], b, w)
+        assert np.max(np.abs(e - ew)) <= 1e-13 * np.max(np.abs(ew))
+    su.set_rhs(b)
+    su.set_solution(None)
+    sr.set_rhs(b)
+    sr.set_solution(None)
+    h1, _ = su.solve_sync(1e-9, 100)
+    h2, _ = sr.solve_sync(1e-9, 100)
+    assert_hist_close(h1, h2)
+    su.close()
+    sr.close()
