@@ -608,10 +608,14 @@ def bytes_sync_multadd_cycle_factored(h):
     return tot
 
 
-def bytes_async_chain(h, k, symmetric=True):
+def bytes_async_chain(h, k, symmetric=True, fact0=False):
+    """algorithmic bytes of ONE correction of level k's group.  fact0: h.P[0] / h.R[0] are the plain transfers
+    and the smoothing factors are applied on the fly (two extra passes over A_0 for every group below level 0)"""
     tot = 0
     for l in range(min(k, h.num_levels - 1)):
         tot += bytes_spmv(h.R[l], False) + bytes_spmv(h.P[l], False)
+        if fact0 and l == 0:
+            tot += 2 * bytes_spmv(h.A[0], True)
     if k < h.num_levels - 1:
         tot += (bytes_spmv(h.A[k], False) + 8 * h.n[k]) if symmetric else 24 * h.n[k]
     tot += bytes_spmv(h.A[0], True) + 32 * h.n[0]

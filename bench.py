@@ -102,24 +102,49 @@ SMOOTHERS = {"j": 0, "hybrid_jgs": 2, "L1j": 6}
 
 
 def factor_level0(args):
-    """level-0 transfers in factorised form (amgb_options.factor_level0): synchronous Multadd, symmetrised Jacobi, one GPU"""
-    return (not args.no_factor_level0 and args.solver == "multadd" and args.smoother in ("j", "L1j") and args.num_post > 0
-            and args.impl == "b200" and int(os.environ.get("WORLD_SIZE", "1")) == 1)
+    """level-0 transfers in factorised form (amgb_options.factor_level0): synchronous / asynchronous Multadd, symmetrised Jacobi"""
+    return (not args.no_factor_level0 and args.solver in ("multadd", "async_multadd") and args.smoother in ("j", "L1j")
+            and args.num_post > 0 and args.impl == "b200" and int(os.environ.get("WORLD_SIZE", "1")) == 1)
 
 
-def build_problem(args, H):
+def build_problem(args, H, fact0=None):
     t0 = time.time()
-    A = H.laplacian(args.problem, args.n, args.n, args.nz or args.n)
+    if args.problem == "5pt":
+        A = H.laplacian("5pt", args.n)
+    else:
+        A = H.laplacian(args.problem, args.n, args.n, args.nz or args.n)
     h = H.amg_setup(A, theta=args.theta)
     sv = SOLVERS[args.solver]
     base = H.MULTADD if sv in (H.MULTADD, H.ASYNC_MULTADD) else sv
     if sv == H.ASYNC_AFACX:
         base = H.AFACX
-    h.build_transfers(base, args.smooth_weight, num_pre=1, num_post=args.num_post, factor_level0=factor_level0(args))
+    h.build_transfers(base, args.smooth_weight, num_pre=1, num_post=args.num_post,
+                      factor_level0=factor_level0(args) if fact0 is None else fact0)
     b = H.rand_rhs(A.nrows)
     log("[bench] hierarchy: %d levels, n=%s, nnz(A)=%s, opcx=%.2f, host setup %.1fs" %
         (h.num_levels, h.n, [a.nnz for a in h.A], h.operator_complexity(), time.time() - t0))
     return h, b
+
+
+def workload_string(args, h):
+    """the SAME string in both arms (the driver compares the arms' `config`)"""
+    dims = "%d^2" % args.n if args.problem == "5pt" else ("%d^3" % args.n if not args.nz else "%dx%dx%d" % (args.n, args.n, args.nz))
+    return ("%s %s Laplacian %s (n=%d, nnz=%d), %s%s, smoother %s w=%.2f, tol 1e-9, x0=0, b=srand(0) RandDouble(-1,1)"
+            % ("2D" if args.problem == "5pt" else "3D", args.problem, dims, h.n[0], h.A[0].nnz, args.solver,
+               " + Chebyshev acceleration" if args.cheby else "", args.smoother, args.smooth_weight))
+
+
+def base_config(args, h, cycles):
+    """config keys common to both arms"""
+    return {"workload": workload_string(args, h), "levels": h.num_levels, "operator_complexity": round(h.operator_complexity(), 3),
+            "cycles_to_tol": int(cycles),
+            "hierarchy": "host classical AMG stand-in for hypre BoomerAMG (PMIS, direct interp + 1 Jacobi step, Pmax 4)"}
+
+
+def ref_hist_path(args, h):
+    import hashlib
+    key = hashlib.sha1(workload_string(args, h).encode()).hexdigest()[:16]
+    return os.path.join(os.environ.get("TMPDIR", "/tmp"), "amgb_ref_hist_%s.json" % key)
 
 
 def pinned(n):
@@ -151,7 +176,8 @@ def run_b200(args):
     fact0 = factor_level0(args)
     t0 = time.time()
     s = amg.Solver(h, sv, sm, args.smooth_weight, num_pre=1, num_post=args.num_post, jgs_block_rows=args.jgs_block_rows,
-                   use_sell=not args.no_sell, factor_level0=factor_level0(args))
+                   use_sell=not args.no_sell, factor_level0=fact0, sell_uniform=0 if args.no_sell_uniform else 1,
+                   async_type=args.async_type, res_compute_type=args.res_compute_type, read_type=args.read_type)
     log("[bench] upload + device setup %.1fs" % (time.time() - t0))
     f_t, f_host = pinned(h.n[0])
     u_t, u_host = pinned(h.n[0])
@@ -181,9 +207,9 @@ def run_b200(args):
         s.set_solution(None)
         if is_async:
             corr, rel, secs = s.solve_async(num_cycles)
-            return secs, num_cycles, rel, corr
+            return secs, num_cycles, rel, corr, None
         hist, secs = s.solve_sync(TOL, max_cycles, cheby=cheby)
-        return secs, len(hist) - 1, hist[-1], None
+        return secs, len(hist) - 1, hist[-1], None, hist
 
     def one_solve_e2e():
         if cheby is None:
@@ -201,9 +227,9 @@ def run_b200(args):
     sampler.start()
     launches0 = s.launch_count()
     torch.cuda.synchronize()
-    secs_list, cycles, rel = [], 0, 0.0
+    secs_list, cycles, rel, hist = [], 0, 0.0, None
     for _ in range(args.steps):
-        secs, cycles, rel, corr = one_solve_resident()
+        secs, cycles, rel, corr, hist = one_solve_resident()
         secs_list.append(secs)
     torch.cuda.synchronize()
     launches = s.launch_count() - launches0
@@ -218,73 +244,121 @@ def run_b200(args):
         e2e_list.append(time.perf_counter() - t0)
     e2e_s = float(np.mean(e2e_list))
 
-    # dominant kernel: fine-level residual r = f - A_0 u (k_spmv on A_0), event-timed on the solver's stream
+    # per-kernel picture of one cycle: every large operator event-timed on the solver's stream (y = M x, plain epilogue),
+    # against its ALGORITHMIC bytes (12 nnz + 4 (m+1) + 8 n + 8 m, defined on CSR whatever the storage)
+    kernels = []
+    for l in range(h.num_levels - 1):
+        if h.A[l].nrows < 50000:
+            break
+        for name, kind, sval in (("A%d" % l, 0, False), ("P%d" % l, 1, False), ("R%d" % l, 2, False)):
+            m = (h.A, h.P, h.R)[kind][l]
+            ms = s.time_spmv(kind, l, sval, 20)
+            gbs = H.bytes_spmv(m, False) / (ms * 1e-3) / 1e9
+            kernels.append({"op": "y = %s x" % name, "rows": int(m.nrows), "nnz": int(m.nnz), "ms": round(ms, 4),
+                            "achieved": round(gbs, 1), "frac": round(gbs / peak, 3)})
     res_ms = s.time_residual(50)
     clocks = sampler.stop()
     res_bytes = H.bytes_spmv(h.A[0], True)
-    achieved = res_bytes / (res_ms * 1e-3) / 1e9
+    res_gbs = res_bytes / (res_ms * 1e-3) / 1e9
+    su_slices, su_groups = s.sellu_stats()
     symmetric = sm != H.HYBRID_JACOBI_GAUSS_SEIDEL and args.num_post > 0
     if is_async:
-        cyc_bytes = sum(H.bytes_async_chain(h, k, symmetric) for k in range(h.num_levels))
+        cyc_bytes = sum(H.bytes_async_chain(h, k, symmetric, fact0) for k in range(h.num_levels))
     else:
         cyc_bytes = H.bytes_sync_multadd_cycle_factored(h) if fact0 else H.bytes_sync_multadd_cycle(h, symmetric)
     solve_bytes = cyc_bytes * cycles
+    solve_gbs = solve_bytes / solve_s / 1e9
     true_rel = float(out["relres"])
+    cfg = base_config(args, h, cycles)
     line = {
         "metric": METRIC, "value": solve_s, "unit": "s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": solve_s * 1e3, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "3D %s Laplacian %d^3 (n=%d, nnz=%d), %s, smoother %s w=%.2f, tol 1e-9, x0=0, b=srand(0) RandDouble(-1,1)"
-                   % (args.problem, args.n, h.n[0], h.A[0].nnz, args.solver + (" + Chebyshev acceleration" if args.cheby else ""),
-                      args.smoother, args.smooth_weight),
-                   "levels": h.num_levels, "operator_complexity": round(h.operator_complexity(), 3),
-                   "cycles_to_tol": int(cycles), "final_relres": float(rel),
-                   "l2": "inputs (A_0 alone %.2f GB) exceed the 126 MB L2; no explicit flush" % (12e-9 * h.A[0].nnz),
-                   "hierarchy": "host classical AMG stand-in for hypre BoomerAMG (PMIS, direct interp + 1 Jacobi step, Pmax 4)"},
+        "config": cfg,
+        "details": {"final_relres": float(rel),
+                    "l2": "inputs (A_0 alone %.2f GB as CSR) exceed the 126 MB L2; no explicit flush" % (12e-9 * h.A[0].nnz),
+                    "level0_transfers": ("factorised: plain P_0 / R_0, smoothing factors applied on the fly (amgb_options.factor_level0); "
+                                         "bytes_per_cycle counts that form") if fact0 else "explicit Pbar_0 / Rbar_0",
+                    "sell_uniform": {"slices_encoded": int(su_slices), "groups": int(su_groups),
+                                     "note": "SELL-U: lossless (delta, mask, value) groups replace the column / value streams of the "
+                                             "stencil level; its kernels are flagged `exceeds_csr_roofline` below"}},
         "e2e": {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": int(8 * h.n[0]), "d2h_bytes_per_step": int(8 * h.n[0]),
                 "final_relres": true_rel},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "k_spmv<1,0> sliced-ELL SpGEMV, r = f - A_0 u on the fine level", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "frac_of_8000_spec": achieved / 8000.0,
-                     "peak_source": peak_src, "bytes_per_launch": int(res_bytes), "ms_per_launch": res_ms,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full capture at 256^3
-                     # (profiles/r1_ncu_full_final_kernels.csv: 1.677 GB + 0.115 GB); only valid for the default size
-                     "traffic": 1.792e9 if (args.n == 256 and not args.nz and args.problem == "7pt") else None},
-        "solve_roofline": {"bytes_per_cycle": int(cyc_bytes), "cycles": int(cycles),
-                           "achieved": solve_bytes / solve_s / 1e9, "frac": solve_bytes / solve_s / 1e9 / peak, "unit": "GB/s"},
+        # time-weighted over EVERY kernel of the timed region: algorithmic bytes of all cycles / device seconds of the solve
+        "roofline": {"bound": "hbm", "kernel": "all kernels of the timed solve, time-weighted (algorithmic bytes of %d cycles / device seconds)" % cycles,
+                     "achieved": solve_gbs, "peak": peak, "unit": "GB/s", "frac": solve_gbs / peak, "frac_of_8000_spec": solve_gbs / 8000.0,
+                     "peak_source": peak_src, "bytes_per_cycle": int(cyc_bytes), "cycles": int(cycles),
+                     "traffic": None,      # no ncu pass runs inside bench.py; per-kernel DRAM bytes are in profiles/r2_ncu_*.csv
+                     "kernels": kernels,
+                     "fine_residual": {"kernel": "k_spmv<1,0>, r = f - A_0 u" + (" (SELL-U encoding)" if su_slices else ""),
+                                       "ms_per_launch": res_ms, "bytes_per_launch": int(res_bytes), "achieved": res_gbs,
+                                       "frac": res_gbs / peak,
+                                       "exceeds_csr_roofline": bool(res_gbs > peak),
+                                       "actual_traffic_model_bytes": int(32 * h.n[0]) if su_slices else int(res_bytes)}},
     }
+    if hist is not None:
+        line["details"]["hist_check"] = hist_check(args, h, hist)
     if corr is not None:
-        line["config"]["corrections_per_level"] = [int(x) for x in corr]
+        line["details"]["corrections_per_level"] = [int(x) for x in corr]
+        line["details"]["async_group_seconds"] = [round(float(x), 4) for x in s.async_group_times()]
+        line["details"]["async_cta_groups"] = [int(x) for x in s.async_groups()[0]]
         used, cap = s.l2_arena_bytes()
-        line["config"]["l2_persisting_window_bytes"] = int(used)
+        line["details"]["l2_persisting_window_bytes"] = int(used)
     s.close()
-    line["config"]["level0_transfers"] = ("factorised: plain P_0 / R_0, smoothing factors applied on the fly (amgb_options.factor_level0); "
-                                          "bytes_per_cycle counts that form") if fact0 else "explicit Pbar_0 / Rbar_0"
-    if fact0 and ((not args.no_async and sv == H.MULTADD) or not args.no_cpu_baseline):
-        # the asynchronous solver and the reference's own code take the explicit products (src/SMEM_Setup.cpp:1173-1254)
-        h.build_transfers(H.MULTADD, args.smooth_weight, num_pre=1, num_post=args.num_post)
     if not is_async and not args.no_async and sv == H.MULTADD:
         # the asynchronous member of BASELINE.json configs[1] on the same problem (persistent cooperative kernel),
         # reported beside the synchronous headline: smallest correction count (multiple of 5) that reaches 1e-9
         sa = amg.Solver(h, H.ASYNC_MULTADD, sm, args.smooth_weight, num_pre=1, num_post=args.num_post,
-                        jgs_block_rows=args.jgs_block_rows, use_sell=not args.no_sell)
+                        jgs_block_rows=args.jgs_block_rows, use_sell=not args.no_sell, factor_level0=fact0,
+                        sell_uniform=0 if args.no_sell_uniform else 1)
         res = None
-        for nc in range(30, max_cycles + 1, 5):
+        for nc in range(25, max_cycles + 1, 5):
             out = sa.SMEM_Solve(f_host, TOL, nc, u_out=u_host)
             if out["relres"] < TOL:
                 t0 = time.perf_counter()
                 out = sa.SMEM_Solve(f_host, TOL, nc, u_out=u_host)
+                ab = int(sum(H.bytes_async_chain(h, k, symmetric, fact0) for k in range(h.num_levels)))
                 res = {"solver": "async_multadd", "corrections_per_level": [int(x) for x in out["corrections"]],
                        "value": out["seconds"], "e2e": time.perf_counter() - t0, "unit": "s", "final_relres": float(out["relres"]),
-                       "bytes_per_correction_round": int(sum(H.bytes_async_chain(h, k, symmetric) for k in range(h.num_levels))),
+                       "bytes_per_correction_round": ab,
+                       "roofline": {"achieved": ab * nc / out["seconds"] / 1e9, "frac": ab * nc / out["seconds"] / 1e9 / peak, "unit": "GB/s"},
+                       "group_seconds": [round(float(x), 4) for x in sa.async_group_times()],
+                       "cta_groups": [int(x) for x in sa.async_groups()[0]],
                        "l2_persisting_window_bytes": int(sa.l2_arena_bytes()[0]), "gpu_launches": 1}
                 break
         line["async"] = res
         sa.close()
     if not args.no_cpu_baseline:
+        if fact0:
+            # the reference's own code takes the explicit products (src/SMEM_Setup.cpp:1173-1254)
+            h.build_transfers(H.MULTADD, args.smooth_weight, num_pre=1, num_post=args.num_post)
         line["cpu_baseline"] = cpu_baseline(args, h, b, cycles if not is_async else num_cycles)
+        if hist is not None and "hist" in line["cpu_baseline"]:
+            rh = np.asarray(line["cpu_baseline"].pop("hist"))
+            k = min(len(rh), len(hist))
+            d = np.abs(np.asarray(hist[:k]) - rh[:k])
+            line["details"]["hist_check_sample"] = {"against": "cpu_baseline sample (reference object code, same run)", "cycles_compared": int(k - 1),
+                                                    "max_abs_diff": float(np.max(d)), "max_rel_diff": float(np.max(d / np.maximum(rh[:k], 1e-300)))}
     print(json.dumps(line), flush=True)
+
+
+def hist_check(args, h, hist):
+    """max |hist_gpu - hist_ref| against the FULL solve of the reference arm (bench.py --impl reference writes its history to
+    a temp file; the driver runs that arm first on the same box)"""
+    p = ref_hist_path(args, h)
+    if not os.path.exists(p):
+        return {"against": None, "note": "no history file from `bench.py --impl reference` on this box (%s)" % p}
+    try:
+        ref = np.asarray(json.load(open(p))["hist"], dtype=np.float64)
+    except Exception as e:
+        return {"against": None, "note": "unreadable reference history: %s" % e}
+    k = min(len(ref), len(hist))
+    d = np.abs(np.asarray(hist[:k]) - ref[:k])
+    return {"against": "full solve of the reference arm (oracle/_ref object code), all cycles", "cycles_ref": int(len(ref) - 1),
+            "cycles_gpu": int(len(hist) - 1), "max_abs_diff": float(np.max(d)),
+            "max_rel_diff": float(np.max(d / np.maximum(ref[:k], 1e-300)))}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -305,6 +379,7 @@ def cpu_baseline(args, h, b, cycles_to_tol, sample_cycles=None, full=False):
         sample = args.max_cycles
     use_ref = O.ref_lib() is not None and not args.cpu_port
     t0 = time.time()
+    ref_hist, stock = None, None
     if use_ref:
         # one driver object per process: its setup (allocating and zeroing ~20 GB of per-group vectors) is not the solve phase
         rs = _REF.get("rs")
@@ -323,6 +398,12 @@ def cpu_baseline(args, h, b, cycles_to_tol, sample_cycles=None, full=False):
                 rs.solve_sync_det(sample, 1e-300)
             out = rs.solve_sync_det(sample, TOL if full else 1e-300)
             secs, done, rel = out["seconds"], out["cycles"], out["hist"][-1]      # omp_get_wtime around the cycle loop
+            ref_hist = [float(x) for x in out["hist"]]
+            if not full:
+                # the STOCK loop beside it (SMEM_Solve exactly as shipped: no added barrier, no lock), same sample: shows what the
+                # added barrier + lock cost (its iterates race, SURVEY.md 5.9b, so only its time is used)
+                so = rs.solve(sample, 1e-300, async_type=0)
+                stock = so["seconds"] / max(so["cycles"], 1)
         else:
             out = rs.solve(sample, TOL if full else 1e-300, async_type=0)
             secs, done, rel = out["seconds"], out["cycles"], out["relres"]
@@ -333,15 +414,24 @@ def cpu_baseline(args, h, b, cycles_to_tol, sample_cycles=None, full=False):
         pb = O.Problem(h, base, sm, args.smooth_weight, num_pre=1, num_post=args.num_post, jgs_blocks=[H.uniform_blocks(m, args.jgs_block_rows) for m in h.n])
         _, hist, secs = pb.solve_sync(b, TOL if full else 1e-300, sample)
         done, rel = len(hist) - 1, hist[-1]
+        ref_hist = [float(x) for x in hist]
         kind = "port"
     per_cycle = secs / max(done, 1)
     total = cycles_to_tol if cycles_to_tol else done
     log("[bench] cpu %s: %d cycles in %.2fs (%d threads, wall incl. setup %.1fs), relres after sample %.3e" %
         (kind, done, secs, threads, time.time() - t0, rel))
-    return {"value": per_cycle * total, "unit": "s", "cores": threads, "kind": kind,
-            "sample": "%d cycles of the same %d^3 solve timed (%.3fs, %.4fs/cycle), scaled to the %d cycles of the full solve"
-                      % (done, args.n, secs, per_cycle, total),
-            "seconds_per_cycle": per_cycle, "cycles": int(total), "relres_after_sample": float(rel)}
+    out = {"value": per_cycle * total, "unit": "s", "cores": threads, "kind": kind,
+           "sample": "%d cycles of the same solve timed (%.3fs, %.4fs/cycle), scaled to the %d cycles of the full solve"
+                     % (done, secs, per_cycle, total),
+           "seconds_per_cycle": per_cycle, "cycles": int(total), "relres_after_sample": float(rel)}
+    if kind == "reference" and sv in (H.MULTADD, H.AFACX):
+        out["timed_loop"] = ("SMEM_Solve's k-loop with ONE added omp barrier + the reference's SEMI_ASYNC lock (oracle/ref_driver.cpp "
+                             "ref_solve_sync_det): the stock grouped cycle races on u; cycle / smoother / SpMV are the reference's object code")
+        if stock is not None:
+            out["stock_loop_seconds_per_cycle"] = stock
+    if ref_hist is not None:
+        out["hist"] = ref_hist
+    return out
 
 
 def run_reference(args):
@@ -355,26 +445,35 @@ def run_reference(args):
     # steps: a bounded sample of cycles each
     full = cpu_baseline(args, h, b, None, full=True)
     cycles = int(full["cycles"])
+    if "hist" in full:
+        try:        # the b200 arm (run after this one on the same box) compares its history with this full solve
+            json.dump({"workload": workload_string(args, h), "hist": full["hist"]}, open(ref_hist_path(args, h), "w"))
+        except Exception as e:
+            log("[bench] could not write the reference history: %s" % e)
     for _ in range(max(0, args.warmup - 1)):
         cpu_baseline(args, h, b, cycles)
     vals = [cpu_baseline(args, h, b, cycles) for _ in range(args.steps)]
     v = float(np.mean([x["value"] for x in vals]))
     cb = dict(vals[-1])
+    cb.pop("hist", None)
     cb["value"] = v
     cb["full_solve_seconds_measured_once"] = full["value"]
+    cb["timing"] = ("value = seconds/cycle of a %d-cycle sample (after an untimed pass) x the %d cycles of the full solve; the full solve "
+                    "itself was run once to the tolerance (full_solve_seconds_measured_once)" % (args.cpu_sample_cycles, cycles))
+    cfg = base_config(args, h, cycles)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": v * 1e3, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "3D 7-pt Laplacian %d^3 (n=%d, nnz=%d), %s, smoother %s w=%.2f, tol 1e-9, x0=0, b=srand(0) RandDouble(-1,1)"
-                   % (args.n, h.n[0], h.A[0].nnz, args.solver, args.smoother, args.smooth_weight),
-                   "levels": h.num_levels, "cycles_to_tol": cycles,
-                   **({"note": "the reference arm always solves the 1-GPU-sized problem (%d^3) on the host cores; at --gpus %d the "
-                               "b200 arm solves %d x the rows (weak scaling)" % (args.n, args.gpus, args.gpus)} if args.gpus > 1 else {})},
+        "config": cfg,
         "cpu_baseline": cb,
         "e2e": {"value": v, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if args.gpus > 1:
+        line["same_workload_as_b200_arm"] = False
+        line["note"] = ("the reference arm solves the 1-GPU-sized problem (%d^3) on the host cores; at --gpus %d the b200 arm solves %d x "
+                        "the rows (weak scaling) -- the ratio of the two arms is NOT a same-workload speed-up" % (args.n, args.gpus, args.gpus))
     print(json.dumps(line), flush=True)
 
 
@@ -386,7 +485,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", "--grid", dest="n", type=int, default=256, help="grid points per dimension (per GPU slab)")
     ap.add_argument("--nz", type=int, default=0)
-    ap.add_argument("--problem", default="7pt", choices=["7pt", "27pt"], help="stencil (BASELINE.json configs[1] / configs[2])")
+    ap.add_argument("--problem", default="7pt", choices=["7pt", "27pt", "5pt"],
+                    help="stencil: BASELINE.json configs[1] (7pt) / configs[2] (27pt) / configs[0] (5pt, 2-D n x n)")
     ap.add_argument("--solver", default="multadd", choices=sorted(SOLVERS))
     ap.add_argument("--smoother", default="j", choices=sorted(SMOOTHERS))
     ap.add_argument("--smooth-weight", type=float, default=0.9)
@@ -397,6 +497,10 @@ def main():
     ap.add_argument("--max-cycles", type=int, default=200)
     ap.add_argument("--jgs-block-rows", type=int, default=8)
     ap.add_argument("--no-sell", action="store_true")
+    ap.add_argument("--no-sell-uniform", action="store_true", help="keep the regular sliced-ELL encoding on the stencil levels (no SELL-U)")
+    ap.add_argument("--async-type", type=int, default=0, help="asynchronous solver: 0 full (default), 1 semi (-async_type)")
+    ap.add_argument("--res-compute-type", type=int, default=0, help="asynchronous solver: 0 local (default), 1 global (-res_compute_type)")
+    ap.add_argument("--read-type", type=int, default=0, help="asynchronous solver: 0 sol (default), 1 res (-read_type)")
     ap.add_argument("--min-rows-per-rank", type=int, default=16384,
                     help="multi-GPU: levels with fewer owned rows per rank are replicated, not partitioned")
     ap.add_argument("--no-cpu-baseline", action="store_true")
