@@ -45,19 +45,22 @@ struct OpView {
 };
 
 // thread 0: the view of the operator this CTA works on -- the column-scaled values when asked for, and, for a CTA-slice
-// operation, this CTA's share of the rows, the rows of level 0 being dealt to ALL CTAs of the grid (A_ns_global /
-// A_ne_global, src/SMEM_Setup.cpp:923-939): whole slices of a sliced-ELL operator, else rows
-__device__ __forceinline__ void make_view(OpView &v, const DevCSR &M0)
+// operation, this CTA's share of the rows, the rows of level 0 being dealt to the CTAs of all WORKING groups (the
+// reference deals them to all threads, A_ns_global / A_ne_global, src/SMEM_Setup.cpp:923-939; the idle coarsest group is
+// left out here: it finishes its num_cycles empty iterations at once, and the rows of a group that has stopped are
+// never smoothed or refreshed again): whole slices of a sliced-ELL operator, else rows
+__device__ __forceinline__ void make_view(OpView &v, const DevCSR &M0, int slice_ctas)
 {
    v.M = M0;
    DevCSR &M = v.M;
    if (v.op.sval) { M.va = M0.sval; M.sell_va = M0.sell_sval; M.su_va = M0.su_sval; }
    if (!v.op.range) return;
    const long units = M.sell_slices > 0 ? M.sell_slices : M.nrows;
-   const int u0 = (int)(units * blockIdx.x / gridDim.x), u1 = (int)(units * (blockIdx.x + 1) / gridDim.x);
+   const long cta = min((long)blockIdx.x, (long)slice_ctas);      // (a CTA beyond slice_ctas -- the idle coarsest group -- gets nothing)
+   const int u0 = (int)(units * cta / slice_ctas), u1 = (int)(units * min(cta + 1, (long)slice_ctas) / slice_ctas);
    if (M.sell_slices > 0) {
       M.sell_off += u0; M.sell_base += u0; M.sell_slices = u1 - u0;
-      if (M.su_off) M.su_off += u0;
+      if (M.su_desc) M.su_desc += u0;
    } else {
       SpmvEpilogue &e = v.op.e;
       M.rp += u0; M.nrows = u1 - u0;
@@ -74,10 +77,11 @@ __device__ __forceinline__ void make_view(OpView &v, const DevCSR &M0)
 }
 
 // this CTA's row range when level-0 rows are dealt to all CTAs (matches make_view)
-__device__ __forceinline__ void cta_slice_rows(const DevCSR &M, int *r0, int *r1)
+__device__ __forceinline__ void cta_slice_rows(const DevCSR &M, int slice_ctas, int *r0, int *r1)
 {
    const long units = M.sell_slices > 0 ? M.sell_slices : M.nrows;
-   const long u0 = units * blockIdx.x / gridDim.x, u1 = units * (blockIdx.x + 1) / gridDim.x;
+   const long cta = min((long)blockIdx.x, (long)slice_ctas);
+   const long u0 = units * cta / slice_ctas, u1 = units * min(cta + 1, (long)slice_ctas) / slice_ctas;
    if (M.sell_slices > 0) { *r0 = (int)min((long)M.nrows, u0 * 32); *r1 = (int)min((long)M.nrows, u1 * 32); }
    else { *r0 = (int)u0; *r1 = (int)u1; }
 }
@@ -117,16 +121,17 @@ __global__ void __launch_bounds__(kABlock, HEAVY ? 3 : 6) k_async_amg(const Asyn
          const int type = op.type;
          if (type == AOP_SPMV) {
             if (threadIdx.x == 0)
-               make_view(sv, op.mat_kind == AMGB_MAT_A ? p.A[op.mat_level] : (op.mat_kind == AMGB_MAT_P ? p.P[op.mat_level] : p.R[op.mat_level]));
+               make_view(sv, op.mat_kind == AMGB_MAT_A ? p.A[op.mat_level] : (op.mat_kind == AMGB_MAT_P ? p.P[op.mat_level] : p.R[op.mat_level]), p.slice_ctas);
             __syncthreads();
             const DevCSR &M = sv.M;
             const int t0 = op.range ? (int)threadIdx.x : tm.tid, ts = op.range ? kABlock : tm.size;
-            if (M.sell_slices > 0) sell_rows_team<false, false>(M, op.x, op.y, op.e, t0, ts, false);
+            if (M.sell_slices > 0 && M.su_desc) sell_rows_team<false, false, 4>(M, op.x, op.y, op.e, t0, ts, false);
+            else if (M.sell_slices > 0) sell_rows_team<false, false>(M, op.x, op.y, op.e, t0, ts, false);
             else if (M.nrows > 0) csr_rows_dispatch<false, false>(M, op.x, op.y, op.e, t0, ts, false);
          } else if (type == AOP_SCALE) {
             // y = rs o x (zero-guess Jacobi, src/SMEM_Smooth.cpp:381-389), optionally reduced into the shared u
             int r0 = 0, r1 = p.A[op.level].nrows, step = tm.size, first = tm.tid;
-            if (op.range) { cta_slice_rows(p.A[op.level], &r0, &r1); step = kABlock; first = threadIdx.x; }
+            if (op.range) { cta_slice_rows(p.A[op.level], p.slice_ctas, &r0, &r1); step = kABlock; first = threadIdx.x; }
             for (int k = r0 + first; k < r1; k += step) {
                const double v = __ldg(op.e.rs + k) * ld_cg(op.x + k);
                if (op.e.red) {
@@ -357,8 +362,8 @@ int async_build_program(const amgb_options &o, int L, bool symmetric, bool fact0
    // stop protocol (and, with -res_compute_type global, its share of the level-0 rows)
    const bool idle = (q == L - 1);
    const int rs0 = B.rs_id(0);
-   if (global) {
-      // all CTAs: smooth level 0 on this CTA's rows, u += u_fine (:35-60).  The reference reads the group's copy of the shared
+   if (global && !idle) {
+      // all CTAs of the working groups: smooth level 0 on this CTA's rows, u += u_fine (:35-60).  The reference reads the group's copy of the shared
       // residual; here the shared residual itself (the copy only exists for the chain's sake, and the idle coarsest
       // group has none)
       if (symmetric) {
@@ -425,11 +430,11 @@ int async_build_program(const amgb_options &o, int L, bool symmetric, bool fact0
       }
    }
    B.vec(AOP_COUNT_STOP, 0, AV_NONE, AV_NONE).barrier = 0;
-   if (global) {
-      // ---- all CTAs: residual of this CTA's rows from the shared u into the shared r, then the group's copy (:356-416)
+   if (global && !idle) {
+      // ---- all working CTAs: residual of this CTA's rows from the shared u into the shared r, then the group's copy (:356-416)
       AsyncOpSym &s = B.spmv(AMGB_MAT_A, 0, 0, U, RS, -1.0, 1.0, F);
       s.range = 1;
-      if (!idle) B.vec(AOP_COPY, 0, RS, Rv(0));
+      B.vec(AOP_COPY, 0, RS, Rv(0));
    } else if (!idle && !read_res) {
       // ---- private residual from the private copy (:338-351)
       B.spmv(AMGB_MAT_A, 0, 0, UL, Rv(0), -1.0, 1.0, F);
@@ -447,7 +452,7 @@ static bool async_heavy(const amgb_options &o)
 // reaches in the stand-alone kernels, profiles/README.md): only the RATIOS matter, they seed the CTA-group sizes
 static double op_cost(const DevCSR &M, long sell_entries)
 {
-   if (M.su_off) return (32.0 * M.nrows) / 0.8;
+   if (M.su_desc) return (32.0 * M.nrows) / 0.8;
    if (M.sell_slices > 0) return (12.0 * (double)sell_entries + 16.0 * M.nrows) / (M.sell_perm ? 0.55 : 0.85);
    return (12.0 * M.nnz + 16.0 * M.nrows) / 0.4;
 }
@@ -640,6 +645,7 @@ static void async_assign_groups(amgb_ctx *c, const std::vector<double> &work)
    }
    for (int q = 0; q <= first; q++) hp.cta_begin[q] = 0;
    for (int q = first; q < L; q++) hp.cta_begin[q + 1] = hp.cta_begin[q] + ctas[q];
+   hp.slice_ctas = std::max(1, L > 1 ? hp.cta_begin[L - 1] : hp.cta_begin[L]);      // CTAs of the working groups
    c->async_cta_begin.assign(hp.cta_begin, hp.cta_begin + L + 1);
    c->async_grid_used = hp.cta_begin[L];
 }

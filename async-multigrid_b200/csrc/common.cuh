@@ -27,10 +27,11 @@ struct DevCSR {
    const int *sell_perm = nullptr;   // SELL-C-sigma: slot (32*slice + lane) -> row, -1 for padding slots; nullptr = identity
    // SELL-U ("uniform slices", sigma = 1 only): a lossless second encoding of a slice whose entries take few distinct
    // (column - row, value) pairs -- the stencil levels, where every row of a slice carries the same 7 / 27 pairs.  Slice s
-   // owns groups [su_off[s], su_off[s+1]); group g = {delta, lane mask} + value (+ the column-scaled value): lane l adds
-   // value * x[row + delta] when bit l of the mask is set.  24 bytes per group replace 384 bytes per slice column, so the
-   // kernel streams the vectors only.  su_off[s+1] == su_off[s]: the slice is not encoded, the regular arrays are used.
-   const int *su_off = nullptr;      // [slices+1]
+   // owns groups [su_desc[s].x, su_desc[s].x + su_desc[s].y) of a DEDUPLICATED group table (slices with the same list share
+   // it: a stencil has a few dozen distinct lists, which then live in L1); group g = {delta, lane mask} + value (+ the
+   // column-scaled value): lane l adds value * x[row + delta] when bit l of the mask is set.  The kernel streams the vectors
+   // only.  su_desc[s].y == 0: the slice is not encoded, the regular arrays are used.
+   const int2 *su_desc = nullptr;    // [slices] {first group, number of groups}
    const int2 *su_dm = nullptr;      // {column - row, lane mask}
    const double *su_va = nullptr;
    const double *su_sval = nullptr;

@@ -15,6 +15,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <string>
 #include <vector>
 #include <omp.h>
 
@@ -99,6 +101,7 @@ void amgb_default_options(amgb_options *o)
    o->async_type = 0;
    o->res_compute_type = 0;
    o->read_type = 0;
+   o->lean_storage = 0;
 }
 
 int amgb_create(amgb_ctx **out, int device)
@@ -116,6 +119,7 @@ int amgb_create(amgb_ctx **out, int device)
    cudaGetDeviceProperties(&prop, device);
    c->cfg.num_sms = prop.multiProcessorCount;
    c->cfg.ctas_per_sm = 8;
+   if (const char *sc = getenv("AMGB_SELLU_CTAS")) c->cfg.sellu_ctas = atoi(sc) == 5 ? 5 : 4;
    c->host_threads = std::max(1, std::min(16, omp_get_num_procs()));
    c->l2_bytes = prop.l2CacheSize;
    c->max_window = prop.accessPolicyMaxWindowSize;
@@ -169,6 +173,7 @@ int amgb_set_num_levels(amgb_ctx *c, int L)
    c->L = L;
    c->A.resize(L); c->P.resize(L); c->R.resize(L);
    c->hA.resize(L);
+   c->lean_diag.assign(L, nullptr); c->lean_l1.assign(L, nullptr);
    c->jgs_bounds.assign(L, nullptr); c->jgs_nb.assign(L, 0);
    return AMGB_OK;
 }
@@ -262,7 +267,7 @@ static int build_sell(amgb_ctx *c, DevCSR &M, int nrows, const int *rp, const in
 }
 
 // SELL-U: re-encode the slices of a sigma = 1 sliced-ELL matrix whose entries take few distinct (column - row, value,
-// scaled value) triples (see DevCSR::su_off).  Runs at setup time, after the column-scaled values exist, on host copies of
+// scaled value) triples (see DevCSR::su_desc).  Runs at setup time, after the column-scaled values exist, on host copies of
 // the device arrays (chunks of slices, OpenMP over slices).  Lossless: a slice is encoded only if every real entry of its
 // rows falls into a group and no row holds the same column twice; a row's terms are then summed in group order (the order
 // of first appearance in the slice) instead of CSR order.  A slice that would need more than half the bytes of its
@@ -307,18 +312,36 @@ static void sellu_encode_chunk(int nrows, const int *off, const int *rp, int s0,
    }
 }
 
+// group lists of many slices are identical (a constant-coefficient stencil has one list per boundary pattern): the table
+// keeps one copy of every distinct list, slice s points at it through desc[s] = {first group, count}
+struct SuTable {
+   std::vector<SuGrp> groups;
+   std::map<std::string, int> seen;
+   int2 add(const std::vector<SuGrp> &g)
+   {
+      if (g.empty()) return make_int2(0, 0);
+      std::string key(reinterpret_cast<const char *>(g.data()), g.size() * sizeof(SuGrp));
+      auto it = seen.find(key);
+      if (it != seen.end()) return make_int2(it->second, (int)g.size());
+      const int first = (int)groups.size();
+      groups.insert(groups.end(), g.begin(), g.end());
+      seen.emplace(std::move(key), first);
+      return make_int2(first, (int)g.size());
+   }
+};
+
 static int build_sellu(amgb_ctx *c, DevCSR &M)
 {
-   if (!c->opt.use_sell || c->opt.sell_uniform == 0 || M.sell_slices == 0 || M.sell_perm || M.su_off || !M.sell_sval) return AMGB_OK;
+   if (!c->opt.use_sell || c->opt.sell_uniform == 0 || M.sell_slices == 0 || M.sell_perm || M.su_desc || !M.sell_sval) return AMGB_OK;
    const int slices = M.sell_slices, nrows = M.nrows;
    std::vector<int> off((size_t)slices + 1), rp((size_t)nrows + 1);
    CUDA_OK(c, cudaStreamSynchronize(c->stream));
    CUDA_OK(c, cudaMemcpy(off.data(), M.sell_off, sizeof(int) * off.size(), cudaMemcpyDeviceToHost));
    CUDA_OK(c, cudaMemcpy(rp.data(), M.rp, sizeof(int) * rp.size(), cudaMemcpyDeviceToHost));
-   std::vector<int> goff((size_t)slices + 1, 0);
+   std::vector<int2> desc((size_t)slices, make_int2(0, 0));
    const int CH = 262144;                                   // slices per chunk (bounds the host copy)
-   std::vector<SuGrp> all;
-   long encoded = 0;
+   SuTable tab;
+   long encoded = 0, listed = 0;
    std::vector<int> ci;
    std::vector<double> va, sv;
    std::vector<std::vector<SuGrp>> gs;
@@ -334,32 +357,35 @@ static int build_sellu(amgb_ctx *c, DevCSR &M)
       sellu_encode_chunk(nrows, off.data(), rp.data(), s0, s1, e0, ci.data(), va.data(), sv.data(), gs);
       for (int s = s0; s < s1; s++) {
          const std::vector<SuGrp> &g = gs[(size_t)(s - s0)];
-         goff[s + 1] = goff[s] + (int)g.size();
-         if (!g.empty()) encoded++;
-         all.insert(all.end(), g.begin(), g.end());
+         desc[s] = tab.add(g);
+         if (!g.empty()) { encoded++; listed += (long)g.size(); }
       }
+      // a matrix whose lists do not repeat (variable coefficients) would only trade one stream for another: give up early
+      if (s1 >= std::min(slices, 65536) && (double)tab.groups.size() > 0.5 * (double)listed && tab.groups.size() > 4096) return AMGB_OK;
    }
    if (encoded * 2 < slices) return AMGB_OK;
+   const std::vector<SuGrp> &all = tab.groups;
    std::vector<int2> dm(all.size());
    std::vector<double> gva(all.size()), gsv(all.size());
    for (size_t i = 0; i < all.size(); i++) { dm[i] = make_int2(all[i].delta, (int)all[i].mask); gva[i] = all[i].va; gsv[i] = all[i].sv; }
-   int *d_off; int2 *d_dm; double *d_va, *d_sv;
+   int2 *d_desc, *d_dm; double *d_va, *d_sv;
    int rc;
-   if ((rc = dev_upload(c, &d_off, goff.data(), goff.size()))) return rc;
+   if ((rc = dev_upload(c, &d_desc, desc.data(), desc.size()))) return rc;
    if ((rc = dev_upload(c, &d_dm, dm.data(), dm.size()))) return rc;
    if ((rc = dev_upload(c, &d_va, gva.data(), gva.size()))) return rc;
    if ((rc = dev_upload(c, &d_sv, gsv.data(), gsv.size()))) return rc;
    CUDA_OK(c, cudaStreamSynchronize(c->stream));
-   M.su_off = d_off; M.su_dm = d_dm; M.su_va = d_va; M.su_sval = d_sv;
+   M.su_desc = d_desc; M.su_dm = d_dm; M.su_va = d_va; M.su_sval = d_sv;
    c->sellu_slices += encoded;
    c->sellu_groups += (long)all.size();
    return AMGB_OK;
 }
 
 // Host-only probe of the SELL-U encoder for the CPU test suite (no CUDA call): CSR + scaled values in, the sigma = 1 sliced-ELL
-// layout is formed as build_sell does and encoded; out: goff[slices + 1], and per group delta / mask / va / sv (malloc'ed,
-// release with amgb_host_free).  Returns the number of slices.
-int amgb_sellu_encode_host(int nrows, const int *rp, const int *ci, const double *va, const double *sv, int **goff_out,
+// layout is formed as build_sell does, encoded and deduplicated exactly as build_sellu does; out: per slice the first group
+// and the group count (two ints per slice, count 0 = not encoded) and per group of the deduplicated table delta / mask / va / sv
+// (malloc'ed, release with amgb_host_free).  Returns the number of slices.
+int amgb_sellu_encode_host(int nrows, const int *rp, const int *ci, const double *va, const double *sv, int **desc_out,
                            int **delta_out, unsigned int **mask_out, double **gva_out, double **gsv_out, int *ngroups)
 {
    const int slices = (nrows + 31) / 32;
@@ -378,20 +404,19 @@ int amgb_sellu_encode_host(int nrows, const int *rp, const int *ci, const double
       }
    std::vector<std::vector<SuGrp>> gs;
    sellu_encode_chunk(nrows, off.data(), rp, 0, slices, 0, sci.data(), sva.data(), ssv.data(), gs);
-   size_t tot = 0;
-   for (auto &g : gs) tot += g.size();
-   int *goff = (int *)malloc(sizeof(int) * ((size_t)slices + 1));
+   SuTable tab;
+   int *desc = (int *)malloc(sizeof(int) * 2 * std::max<size_t>((size_t)slices, 1));
+   for (int s = 0; s < slices; s++) {
+      const int2 d = tab.add(gs[(size_t)s]);
+      desc[2 * s] = d.x; desc[2 * s + 1] = d.y;
+   }
+   const size_t tot = tab.groups.size();
    int *dl = (int *)malloc(sizeof(int) * std::max<size_t>(tot, 1));
    unsigned int *mk = (unsigned int *)malloc(sizeof(unsigned int) * std::max<size_t>(tot, 1));
    double *gv = (double *)malloc(sizeof(double) * std::max<size_t>(tot, 1));
    double *gsvp = (double *)malloc(sizeof(double) * std::max<size_t>(tot, 1));
-   size_t q = 0;
-   goff[0] = 0;
-   for (int s = 0; s < slices; s++) {
-      for (auto &x : gs[(size_t)s]) { dl[q] = x.delta; mk[q] = x.mask; gv[q] = x.va; gsvp[q] = x.sv; q++; }
-      goff[s + 1] = (int)q;
-   }
-   *goff_out = goff; *delta_out = dl; *mask_out = mk; *gva_out = gv; *gsv_out = gsvp; *ngroups = (int)tot;
+   for (size_t q = 0; q < tot; q++) { dl[q] = tab.groups[q].delta; mk[q] = tab.groups[q].mask; gv[q] = tab.groups[q].va; gsvp[q] = tab.groups[q].sv; }
+   *desc_out = desc; *delta_out = dl; *mask_out = mk; *gva_out = gv; *gsv_out = gsvp; *ngroups = (int)tot;
    return slices;
 }
 void amgb_host_free(void *p) { free(p); }
@@ -520,9 +545,9 @@ static int build_stream_blocks(amgb_ctx *c, DevCSR &M, int nrows, int ncols, con
 int amgb_set_matrix(amgb_ctx *c, int kind, int level, int nrows, int ncols, int nnz,
                     const int *rp, const int *ci, const double *va)
 {
+   if (!c || !rp || (nnz > 0 && (!ci || !va))) return amgb_fail(c, AMGB_EINVAL, "null matrix arrays");
    // layout conversion below is OpenMP-parallel; launchers such as torchrun export OMP_NUM_THREADS=1
    if (omp_get_max_threads() < c->host_threads) omp_set_num_threads(c->host_threads);
-   if (!c || !rp || (nnz > 0 && (!ci || !va))) return amgb_fail(c, AMGB_EINVAL, "null matrix arrays");
    if (c->L == 0) return amgb_fail(c, AMGB_ESTATE, "call amgb_set_num_levels first");
    if (level < 0 || level >= c->L || (kind != AMGB_MAT_A && level >= c->L - 1 && c->L > 1))
       return amgb_fail(c, AMGB_EINVAL, "level %d out of range for kind %d", level, kind);
@@ -542,10 +567,8 @@ int amgb_set_matrix(amgb_ctx *c, int kind, int level, int nrows, int ncols, int 
    c->alloc_in_arena = c->opt.l2_persist && level >= 2 && (size_t)nnz * 40 + (size_t)nrows * 16 + 65536 <= c->arena_size - c->arena_used;
    struct ArenaOff { amgb_ctx *c; ~ArenaOff() { c->alloc_in_arena = false; } } arena_off{c};
    if ((rc = dev_upload(c, &d_rp, rp, (size_t)nrows + 1))) return rc;
-   if ((rc = dev_upload(c, &d_ci, ci, (size_t)nnz))) return rc;
-   if ((rc = dev_upload(c, &d_va, va, (size_t)nnz))) return rc;
    M.nrows = nrows; M.ncols = ncols; M.nnz = nnz;
-   M.rp = d_rp; M.ci = d_ci; M.va = d_va;
+   M.rp = d_rp;
    M.lpr = pick_lpr(nrows, nnz);
    CUDA_OK(c, cudaStreamSynchronize(c->stream));
    if (c->opt.use_sell && nrows >= 1024) {
@@ -555,6 +578,34 @@ int amgb_set_matrix(amgb_ctx *c, int kind, int level, int nrows, int ncols, int 
          if ((rc = build_sell(c, M, nrows, rp, ci, va, c->opt.sell_sigma, 0.25))) return rc;
       }
    }
+   // lean storage (amgb_options.lean_storage): a matrix that lives in sliced ELL keeps NO second copy in CSR -- only the row
+   // pointer stays (the SELL-U encoder and the long-row test read it).  The CSR arrays are what the Gauss-Seidel-type
+   // smoothers, the transposed product and the set-up kernels (diagonal, l1 norms) read, so lean storage is limited to
+   // the (L1-)Jacobi family and the diagonal / l1 norms of an A_l are formed here, on the host, instead.
+   const bool jac = c->opt.smoother == AMGB_SMOOTH_JACOBI || c->opt.smoother == AMGB_SMOOTH_L1_JACOBI;
+   const bool lean = c->opt.lean_storage && jac && M.sell_slices > 0;
+   d_ci = nullptr; d_va = nullptr;
+   if (!lean) {
+      if ((rc = dev_upload(c, &d_ci, ci, (size_t)nnz))) return rc;
+      if ((rc = dev_upload(c, &d_va, va, (size_t)nnz))) return rc;
+      CUDA_OK(c, cudaStreamSynchronize(c->stream));
+   } else if (kind == AMGB_MAT_A) {
+      std::vector<double> hd((size_t)nrows), hl((size_t)nrows);
+#pragma omp parallel for schedule(static)
+      for (int r = 0; r < nrows; r++) {
+         double sabs = 0.0;
+         for (int p = rp[r]; p < rp[r + 1]; p++) sabs += fabs(va[p]);
+         hl[r] = sabs;
+         hd[r] = rp[r + 1] > rp[r] ? va[rp[r]] : 0.0;
+      }
+      double *dd = nullptr, *dl = nullptr;
+      if ((rc = dev_upload(c, &dd, hd.data(), hd.size()))) return rc;
+      if ((rc = dev_upload(c, &dl, hl.data(), hl.size()))) return rc;
+      CUDA_OK(c, cudaStreamSynchronize(c->stream));
+      c->lean_diag[level] = dd;
+      c->lean_l1[level] = dl;
+   }
+   M.ci = d_ci; M.va = d_va;
    // long rows (restrictions on coarse levels: 150-300 entries) are served best by one warp per row; everything
    // shorter goes through the stream kernel (measured per matrix with tools/spmv_sweep.py, profiles/)
    const bool long_rows = nrows > 0 && (double)nnz / nrows >= 96.0;
@@ -681,15 +732,22 @@ int amgb_setup(amgb_ctx *c)
       if ((rc = dev_alloc(c, &c->dow[l], n))) return rc;
       if ((rc = dev_alloc(c, &c->l1[l], n))) return rc;
       if ((rc = dev_alloc(c, &c->inv_l1[l], n))) return rc;
-      c->launches += launch_diag_scale(c->stream, c->A[l], o.smooth_weight, c->ws[l], c->dow[l]);
-      c->launches += launch_l1(c->stream, c->A[l], c->l1[l], c->inv_l1[l]);
+      const bool lean = c->A[l].va == nullptr && c->A[l].nnz > 0;     // lean storage: sliced ELL only, diagonal / l1 came from the host
+      if (lean) {
+         c->launches += launch_diag_scale_vec(c->stream, n, c->lean_diag[l], c->lean_l1[l], o.smooth_weight, c->ws[l], c->dow[l], c->l1[l], c->inv_l1[l]);
+      } else {
+         c->launches += launch_diag_scale(c->stream, c->A[l], o.smooth_weight, c->ws[l], c->dow[l]);
+         c->launches += launch_l1(c->stream, c->A[l], c->l1[l], c->inv_l1[l]);
+      }
       // column-scaled copy of A's values for the one-pass symmetrised smoother
       double *sv = nullptr;
-      if ((rc = dev_alloc(c, &sv, (size_t)c->A[l].nnz))) return rc;
       const double *cs = (o.smoother == AMGB_SMOOTH_L1_JACOBI) ? c->inv_l1[l] : c->ws[l];
       // (a partitioned level's columns are in the rank's extended numbering: amgb_dist_setup fills sval there)
       const bool part = amgb_dist_level_distributed(c, l);
-      if (!part) c->launches += launch_colscale(c->stream, c->A[l].nnz, c->A[l].ci, c->A[l].va, cs, sv);
+      if (!lean) {
+         if ((rc = dev_alloc(c, &sv, (size_t)c->A[l].nnz))) return rc;
+         if (!part) c->launches += launch_colscale(c->stream, c->A[l].nnz, c->A[l].ci, c->A[l].va, cs, sv);
+      }
       c->A[l].sval = sv;
       if (c->A[l].pos) {   // scaled values of the column-sorted chunk copy
          double *psv = nullptr;
@@ -716,6 +774,11 @@ int amgb_setup(amgb_ctx *c)
    if ((rc = dev_zero(c, &c->cvec, n0))) return rc;
    if ((rc = dev_zero(c, &c->u_outer, n0))) return rc;
    if ((rc = dev_zero(c, &c->y_outer, n0))) return rc;
+   for (int l = 0; l < L; l++) {            // (a partitioned level's matrices have more columns than rows: ghosts)
+      maxn = std::max(maxn, c->A[l].ncols);
+      if (l < L - 1) maxn = std::max(maxn, std::max(std::max(c->P[l].ncols, c->P[l].nrows), std::max(c->R[l].ncols, c->R[l].nrows)));
+   }
+   c->io_len = maxn;
    if ((rc = dev_zero(c, &c->io_a, maxn))) return rc;
    if ((rc = dev_zero(c, &c->io_b, maxn))) return rc;
    if ((rc = dev_zero(c, &c->io_c, maxn))) return rc;
@@ -1002,6 +1065,7 @@ int amgb_spgemv(amgb_ctx *c, int kind, int level, double alpha, const double *x,
    if (level < 0 || level >= c->L || (kind != AMGB_MAT_A && level >= c->L - 1)) return amgb_fail(c, AMGB_EINVAL, "bad level");
    const DevCSR &M = kind == AMGB_MAT_A ? c->A[level] : (kind == AMGB_MAT_P ? c->P[level] : c->R[level]);
    if (!x || !y || (beta != 0.0 && !b)) return amgb_fail(c, AMGB_EINVAL, "null vector");
+   if (M.nrows > c->io_len || M.ncols > c->io_len) return amgb_fail(c, AMGB_EINVAL, "matrix larger than the staging vectors");
    CUDA_OK(c, cudaMemcpyAsync(c->io_a, x, sizeof(double) * M.ncols, cudaMemcpyHostToDevice, c->stream));
    if (beta != 0.0) CUDA_OK(c, cudaMemcpyAsync(c->io_b, b, sizeof(double) * M.nrows, cudaMemcpyHostToDevice, c->stream));
    enq_spmv(c, M, false, c->io_a, c->io_c, epi(alpha, beta, beta != 0.0 ? c->io_b : nullptr), false);
@@ -1017,9 +1081,8 @@ int amgb_spgemv_transpose(amgb_ctx *c, int kind, int level, const double *x, dou
    if (level < 0 || level >= c->L || (kind != AMGB_MAT_A && level >= c->L - 1)) return amgb_fail(c, AMGB_EINVAL, "bad level");
    const DevCSR &M = kind == AMGB_MAT_A ? c->A[level] : (kind == AMGB_MAT_P ? c->P[level] : c->R[level]);
    if (!x || !y) return amgb_fail(c, AMGB_EINVAL, "null vector");
-   int maxn = 0;
-   for (auto &a : c->A) maxn = std::max(maxn, a.nrows);
-   if (M.nrows > maxn || M.ncols > maxn) return amgb_fail(c, AMGB_EINVAL, "matrix larger than the staging vectors");
+   if (M.nrows > c->io_len || M.ncols > c->io_len) return amgb_fail(c, AMGB_EINVAL, "matrix larger than the staging vectors");
+   if (!M.ci && M.nnz > 0) return amgb_fail(c, AMGB_EINVAL, "the transposed product reads the CSR arrays, which lean storage does not keep");
    CUDA_OK(c, cudaMemcpyAsync(c->io_a, x, sizeof(double) * M.nrows, cudaMemcpyHostToDevice, c->stream));
    c->launches += launch_spmv_transpose(c->cfg, c->stream, M, c->io_a, c->io_c);
    CUDA_OK(c, cudaMemcpyAsync(y, c->io_c, sizeof(double) * M.ncols, cudaMemcpyDeviceToHost, c->stream));
@@ -1080,10 +1143,17 @@ int amgb_norm2(amgb_ctx *c, const double *x, int n, double *out)
    return AMGB_OK;
 }
 
+static bool has_additive_cycle(const amgb_ctx *c)
+{
+   const int s = c->opt.solver;
+   return s == AMGB_SOLVER_MULTADD || s == AMGB_SOLVER_AFACX || s == AMGB_SOLVER_BPX || s == AMGB_SOLVER_ASYNC_MULTADD || s == AMGB_SOLVER_ASYNC_AFACX;
+}
+
 int amgb_cycle(amgb_ctx *c, const double *r_host, double *c_host)
 {
    NEED_READY(c);
    if (!r_host || !c_host) return amgb_fail(c, AMGB_EINVAL, "null vector");
+   if (!has_additive_cycle(c)) return amgb_fail(c, AMGB_EINVAL, "amgb_cycle applies the additive cycles (Multadd, AFACx, BPX); this context was set up for solver %d", c->opt.solver);
    const int n0 = c->A[0].nrows;
    CUDA_OK(c, cudaMemcpyAsync(c->r[0], r_host, sizeof(double) * n0, cudaMemcpyHostToDevice, c->stream));
    enq_cycle(c, c->cvec, false);
@@ -1177,6 +1247,7 @@ int amgb_eigs_power(amgb_ctx *c, int iters, double *eig_min, double *eig_max)
 {
    NEED_READY(c);
    if (iters < 1 || !eig_min || !eig_max) return amgb_fail(c, AMGB_EINVAL, "bad arguments");
+   if (!has_additive_cycle(c)) return amgb_fail(c, AMGB_EINVAL, "amgb_eigs_power applies the additive cycles (Multadd, AFACx, BPX); this context was set up for solver %d", c->opt.solver);
    const int n0 = c->A[0].nrows;
    double *u = c->u_outer, *e = c->y_outer;
    double lam[2] = {0.0, 0.0};
@@ -1341,7 +1412,7 @@ int amgb_time_spmv(amgb_ctx *c, int kind, int level, int use_sval, int reps, dou
    if (level < 0 || level >= c->L || (kind != AMGB_MAT_A && level >= c->L - 1) || reps < 1 || !ms_per_launch)
       return amgb_fail(c, AMGB_EINVAL, "bad arguments");
    const DevCSR &M = kind == AMGB_MAT_A ? c->A[level] : (kind == AMGB_MAT_P ? c->P[level] : c->R[level]);
-   if (use_sval && !M.sval) return amgb_fail(c, AMGB_EINVAL, "no scaled values for this matrix");
+   if (use_sval && !M.sval && !M.sell_sval) return amgb_fail(c, AMGB_EINVAL, "no scaled values for this matrix");
    const double *x = kind == AMGB_MAT_A ? c->r[level] : (kind == AMGB_MAT_P ? c->e[level + 1] : c->r[level]);
    double *y = kind == AMGB_MAT_A ? c->e[level] : (kind == AMGB_MAT_P ? c->t[level] : c->t[level + 1]);
    int grid;

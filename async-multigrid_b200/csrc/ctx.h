@@ -29,6 +29,8 @@ struct amgb_ctx {
    std::vector<double *> ws, dow, l1, inv_l1, r, e, t, w;
    double *f = nullptr, *u = nullptr, *cvec = nullptr, *u_outer = nullptr, *y_outer = nullptr;
    double *io_a = nullptr, *io_b = nullptr, *io_c = nullptr;
+   int io_len = 0;                  // entries of the three staging vectors (largest row / column count of the hierarchy)
+   std::vector<double *> lean_diag, lean_l1;   // lean storage: diagonal and l1 norms of A_l formed on the host at upload
    double *partials = nullptr;
    int npartials = 0;
    double *d_scalars = nullptr;

@@ -48,9 +48,9 @@ struct DistState {
    double *partials3 = nullptr;          // 3 x npartials: interior / low boundary / high boundary launches
    bool overlap = true;
    bool ready = false;
-   // EXPERIMENTAL (AMGB_DIST_GRAPH=1, off by default; not measured yet): one cycle + residual + norm captured as a CUDA graph,
-   // NCCL operations and the communication stream's fork / join included, replayed per cycle
-   bool use_graph = false;
+   // one cycle + residual + norm captured as a CUDA graph, NCCL operations and the communication stream's fork / join
+   // included, replayed per cycle (AMGB_DIST_GRAPH=0 falls back to per-operation launches)
+   bool use_graph = true;
    cudaGraphExec_t graph_exec = nullptr;
    long long graph_kernels = 0, graph_halo_bytes = 0, graph_collectives = 0;
    // asynchronous fine-grid smoother across GPUs (DMEM_AsyncSmooth): the neighbours' level-0 solution vectors mapped
@@ -387,7 +387,8 @@ int amgb_dist_setup(amgb_ctx *c)
       CUDA_OK(c, cudaMemcpyAsync(d->ws[l] + lv.off(), l1s ? c->inv_l1[l] : c->ws[l], sizeof(double) * c->A[l].nrows, cudaMemcpyDeviceToDevice, c->stream));
       if (lv.distributed) {
          if ((rc = halo(c, l, d->ws[l]))) return rc;
-         c->launches += launch_colscale(c->stream, c->A[l].nnz, c->A[l].ci, c->A[l].va, d->ws[l], const_cast<double *>(c->A[l].sval));
+         if (c->A[l].va)      // (lean storage keeps no CSR copy of a sliced-ELL matrix)
+            c->launches += launch_colscale(c->stream, c->A[l].nnz, c->A[l].ci, c->A[l].va, d->ws[l], const_cast<double *>(c->A[l].sval));
          if (c->A[l].pos)
             c->launches += launch_colscale(c->stream, c->A[l].nnz, c->A[l].pci, c->A[l].pva, d->ws[l], const_cast<double *>(c->A[l].psval));
          if (c->A[l].sell_slices > 0)

@@ -12,16 +12,17 @@ namespace {
 
 constexpr int kBlock = 256;
 
-// One kernel per storage scheme (separate register budgets): MODE 0 = vector-per-row CSR,
-// 1 = sliced ELL (stencil levels); the CSR-stream kernel (row blocks through shared memory) is k_spmv_stream.
+// One kernel per storage scheme (separate register budgets): MODE 0 = vector-per-row CSR, 1 = sliced ELL,
+// 2 = sliced ELL with the SELL-U encoding (stencil levels); the CSR-stream kernel (row blocks through shared memory) is k_spmv_stream.
 template <int MODE, bool SVAL>
-__global__ void __launch_bounds__(kBlock) k_spmv(DevCSR M, const double *x, double *y, SpmvEpilogue e, double *partials)
+__global__ void __launch_bounds__(kBlock, MODE == 2 ? 4 : (MODE == 3 ? 5 : 1)) k_spmv(DevCSR M, const double *x, double *y, SpmvEpilogue e, double *partials)
 {
    const int tid = blockIdx.x * kBlock + threadIdx.x;
    const int tsz = gridDim.x * kBlock;
    const bool norm = partials != nullptr;
    double ss;
-   if (MODE == 1) ss = sell_rows_team<true, SVAL>(M, x, y, e, tid, tsz, norm);
+   if (MODE == 2 || MODE == 3) ss = sell_rows_team<true, SVAL, 8>(M, x, y, e, tid, tsz, norm);   // (3: the same at 5 CTAs / SM, 48 registers)
+   else if (MODE == 1) ss = sell_rows_team<true, SVAL>(M, x, y, e, tid, tsz, norm);
    else ss = csr_rows_dispatch<true, SVAL>(M, x, y, e, tid, tsz, norm);
    if (norm) {
       ss = block_sum(ss);
@@ -172,6 +173,19 @@ __global__ void __launch_bounds__(kBlock) k_diag_scale(DevCSR A, double w, doubl
    }
 }
 
+// lean storage: the same scale arrays from the diagonal / l1 norms the host formed at upload
+__global__ void __launch_bounds__(kBlock) k_diag_scale_vec(int n, const double *__restrict__ diag, const double *__restrict__ l1src, double w,
+                                                            double *ws, double *dow, double *l1, double *inv_l1)
+{
+   for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+      const double d = diag[i], s = l1src[i];
+      ws[i] = (d != 0.0) ? w / d : 0.0;
+      dow[i] = d / w;
+      l1[i] = s;
+      inv_l1[i] = (s != 0.0) ? 1.0 / s : 0.0;
+   }
+}
+
 __global__ void __launch_bounds__(kBlock) k_l1(DevCSR A, double *l1, double *inv_l1)
 {
    for (int i = blockIdx.x * kBlock + threadIdx.x; i < A.nrows; i += gridDim.x * kBlock) {
@@ -215,11 +229,12 @@ template <class K>
 static int resident_ctas(K kernel, int block, size_t dyn, int num_sms, int *cache)
 {
    // co-resident CTAs of this kernel on the device: grids are sized to exactly one wave
+   // (the opt-in for more than 48 KB of dynamic shared memory is per device: set it on every call, it is cheap)
+   if (dyn) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
    if (*cache == 0) {
       int v = 0;
-      if (dyn) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, block, dyn) != cudaSuccess || v < 1) v = 1;
-      *cache = v;
+      *cache = std::min(v, 8);      // the per-CTA partial sums of the fused norms are sized for 8 CTAs per SM (LaunchCfg::ctas_per_sm)
    }
    return num_sms * *cache;
 }
@@ -228,7 +243,7 @@ template <int MODE>
 static int launch_spmv_mode(const LaunchCfg &cfg, cudaStream_t st, const DevCSR &M, bool use_sval, const double *x, double *y,
                             const SpmvEpilogue &e, double *partials, long ctas_of_work)
 {
-   static int occ[2] = {0, 0};
+   static int occ[2] = {0, 0};   // (per MODE: a function template has one set of statics per instantiation)
    const int cap = use_sval ? resident_ctas(k_spmv<MODE, true>, kBlock, 0, cfg.num_sms, &occ[1])
                             : resident_ctas(k_spmv<MODE, false>, kBlock, 0, cfg.num_sms, &occ[0]);
    const int grid = (int)std::max(1L, std::min(ctas_of_work, (long)cap));
@@ -269,7 +284,9 @@ int launch_spmv(const LaunchCfg &cfg, cudaStream_t st, const DevCSR &M, bool use
                 const SpmvEpilogue &e, double *partials, int *grid_out)
 {
    int grid;
-   if (M.sell_slices > 0) grid = launch_spmv_mode<1>(cfg, st, M, use_sval, x, y, e, partials, ((long)M.sell_slices * 32 + kBlock - 1) / kBlock);
+   if (M.sell_slices > 0 && M.su_desc && cfg.sellu_ctas == 5) grid = launch_spmv_mode<3>(cfg, st, M, use_sval, x, y, e, partials, ((long)M.sell_slices * 32 + kBlock - 1) / kBlock);
+   else if (M.sell_slices > 0 && M.su_desc) grid = launch_spmv_mode<2>(cfg, st, M, use_sval, x, y, e, partials, ((long)M.sell_slices * 32 + kBlock - 1) / kBlock);
+   else if (M.sell_slices > 0) grid = launch_spmv_mode<1>(cfg, st, M, use_sval, x, y, e, partials, ((long)M.sell_slices * 32 + kBlock - 1) / kBlock);
    else if (M.nblk > 0 && M.wept > 0) {
       if (M.pos) {
          if (M.wept <= 4) grid = launch_wstream<4, true>(cfg, st, M, use_sval, x, y, e, partials);
@@ -304,7 +321,7 @@ int launch_spmv_units(const LaunchCfg &cfg, cudaStream_t st, const DevCSR &M, in
    DevCSR V = M;
    SpmvEpilogue ev = e;
    double *yv = y;
-   if (M.sell_slices > 0) { V.sell_off += u0; V.sell_base += u0; V.sell_slices = u1 - u0; if (V.su_off) V.su_off += u0; }
+   if (M.sell_slices > 0) { V.sell_off += u0; V.sell_base += u0; V.sell_slices = u1 - u0; if (V.su_desc) V.su_desc += u0; }
    else if (M.nblk > 0) { V.blk += u0; if (V.blkx) V.blkx += u0; V.nblk = u1 - u0; }
    else {
       V.rp += u0; V.nrows = u1 - u0; yv += u0;
@@ -416,6 +433,14 @@ int launch_diag_scale(cudaStream_t st, const DevCSR &A, double w, double *ws, do
 {
    LaunchCfg cfg;
    k_diag_scale<<<grid_for(cfg, A.nrows), kBlock, 0, st>>>(A, w, ws, dow);
+   return 1;
+}
+
+int launch_diag_scale_vec(cudaStream_t st, int n, const double *diag, const double *l1src, double w, double *ws, double *dow,
+                          double *l1, double *inv_l1)
+{
+   LaunchCfg cfg;
+   k_diag_scale_vec<<<grid_for(cfg, n), kBlock, 0, st>>>(n, diag, l1src, w, ws, dow, l1, inv_l1);
    return 1;
 }
 

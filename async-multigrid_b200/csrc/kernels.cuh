@@ -48,7 +48,13 @@ __device__ __forceinline__ double csr_rows_team(const DevCSR &M, const double *_
 }
 
 // ---- sliced ELL (C = 32): one thread per row, one warp per slice, coalesced col/val streams -----
-template <bool RO, bool SVAL>
+// SU == 0: the regular encoding only (the Galerkin / transfer operators: this is the round-1 kernel, unchanged).
+// SU  > 0: the matrix carries the SELL-U encoding (DevCSR::su_desc): a slice is a short list of (delta, mask, value) groups
+//          shared by its 32 rows, read SU groups at a time -- all group records first (warp-uniform addresses, and the
+//          lists of a stencil are a few dozen distinct ones, so these are L1 hits), then all x gathers, then the FMAs --
+//          so that one slice costs ONE trip to memory (gathers and the epilogue operands in flight together) instead of
+//          one per dependent load.  The descriptor of the warp's NEXT slice is fetched a slice ahead.
+template <bool RO, bool SVAL, int SU = 0>
 __device__ __forceinline__ double sell_rows_team(const DevCSR &M, const double *__restrict__ x,
                                                  double *y, const SpmvEpilogue &e,
                                                  int team_tid, int team_size, bool want_sumsq)
@@ -57,35 +63,55 @@ __device__ __forceinline__ double sell_rows_team(const DevCSR &M, const double *
    const int nwarp = team_size >> 5;
    const double *__restrict__ va = SVAL ? M.sell_sval : M.sell_va;
    double sumsq = 0.0;
-   for (int sl = team_tid >> 5; sl < M.sell_slices; sl += nwarp) {
-      const int off = __ldg(M.sell_off + sl);
-      const int width = (__ldg(M.sell_off + sl + 1) - off) >> 5;
+   int sl = team_tid >> 5;
+   int2 dsc = make_int2(0, 0);
+   if (SU > 0 && sl < M.sell_slices) dsc = __ldg(M.su_desc + sl);
+   for (; sl < M.sell_slices; sl += nwarp) {
       int row = ((sl + M.sell_base) << 5) + lane;
-      if (M.sell_perm) row = __ldg(M.sell_perm + row);
+      if (SU == 0 && M.sell_perm) row = __ldg(M.sell_perm + row);
       double acc = 0.0;
-      int g0 = 0, g1 = 0;
-      if (M.su_off) { g0 = __ldg(M.su_off + sl); g1 = __ldg(M.su_off + sl + 1); }
-      if (g1 > g0) {
-         // SELL-U slice: a handful of (delta, mask, value) groups shared by the 32 rows; the group records are read at
-         // a warp-uniform address (one broadcast transaction), the x gathers of a group are one or two full lines
+      int2 dnext = make_int2(0, 0);
+      if (SU > 0 && sl + nwarp < M.sell_slices) dnext = __ldg(M.su_desc + sl + nwarp);
+      if (SU > 0 && dsc.y > 0) {
          const double *__restrict__ gv = SVAL ? M.su_sval : M.su_va;
-#pragma unroll 4
-         for (int g = g0; g < g1; g++) {
-            const int2 dm = __ldg(M.su_dm + g);
-            const double v = __ldg(gv + g);
-            if ((static_cast<unsigned int>(dm.y) >> lane) & 1u) acc += v * ld_x<RO>(x + row + dm.x);
+         const bool ok = row < M.nrows;
+         EpiOps ops;
+         ops.b = 0.0; ops.c = 0.0; ops.rs = 1.0;
+         if (RO && ok) ops = epilogue_load<RO>(e, row);       // in flight together with the gathers (the persistent kernel has no registers to spare for it)
+         for (int g = 0; g < dsc.y; g += (SU > 0 ? SU : 1)) {
+            double xv[SU > 0 ? SU : 1];
+            const int2 *__restrict__ dmp = M.su_dm + dsc.x + g;
+            const int left = dsc.y - g;
+            // all gathers of the batch in flight together; the group VALUES are fetched only when the gathers are back (L1
+            // hits), so that nothing but the gathered x occupies registers while the loads are outstanding
+#pragma unroll
+            for (int k = 0; k < SU; k++) {
+               const int2 dm = k < left ? __ldg(dmp + k) : make_int2(0, 0);
+               xv[k] = ((static_cast<unsigned int>(dm.y) >> lane) & 1u) ? ld_x<RO>(x + row + dm.x) : 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < SU; k++)
+               if (k < left) acc += __ldg(gv + dsc.x + g + k) * xv[k];
+         }
+         if (ok) {
+            const double v = RO ? epilogue_finish(e, ops, acc) : epilogue_apply<RO>(e, row, acc);
+            epilogue_store<RO>(e, y, row, v);
+            if (want_sumsq) sumsq += v * v;
          }
       } else {
+         const int off = __ldg(M.sell_off + sl);
+         const int width = (__ldg(M.sell_off + sl + 1) - off) >> 5;
          const int *__restrict__ cp = M.sell_ci + off + lane;
          const double *__restrict__ vp = va + off + lane;
 #pragma unroll 4
          for (int k = 0; k < width; k++) acc += ld_stream(vp + (k << 5)) * ld_x<RO>(x + ld_stream(cp + (k << 5)));
+         if (row >= 0 && row < M.nrows) {
+            double v = epilogue_apply<RO>(e, row, acc);
+            epilogue_store<RO>(e, y, row, v);
+            if (want_sumsq) sumsq += v * v;
+         }
       }
-      if (row >= 0 && row < M.nrows) {
-         double v = epilogue_apply<RO>(e, row, acc);
-         epilogue_store<RO>(e, y, row, v);
-         if (want_sumsq) sumsq += v * v;
-      }
+      dsc = dnext;
    }
    return sumsq;
 }

@@ -9,6 +9,7 @@ struct LaunchCfg {
    int num_sms = 148;
    int ctas_per_sm = 8;
    int stream_variant = 0;
+   int sellu_ctas = 4;          // resident CTAs per SM of the SELL-U kernel: 4 (56 registers) or 5 (48, AMGB_SELLU_CTAS=5)
 };
 
 // geometry of the CSR-stream kernel (kernels.cuh stream_rows_team): threads per CTA, entries per row block,
@@ -62,6 +63,8 @@ int launch_spmv_transpose(const LaunchCfg &cfg, cudaStream_t st, const DevCSR &M
 // setup helpers: ws = w/d (0 where d == 0), l1 = sum |a_ij|, sval = va .* cs[col]
 int launch_diag_scale(cudaStream_t st, const DevCSR &A, double w, double *ws, double *dow);
 int launch_l1(cudaStream_t st, const DevCSR &A, double *l1, double *inv_l1);
+int launch_diag_scale_vec(cudaStream_t st, int n, const double *diag, const double *l1src, double w, double *ws, double *dow,
+                          double *l1, double *inv_l1);
 int launch_colscale(cudaStream_t st, int nnz, const int *ci, const double *va, const double *cs, double *out);
 
 // ---- persistent asynchronous kernel (async.cu) ---------------------------------------------------
@@ -108,6 +111,7 @@ struct AsyncParams {
    int converge_type;
    DevCSR A[AMGB_MAX_LEVELS], P[AMGB_MAX_LEVELS], R[AMGB_MAX_LEVELS];
    int cta_begin[AMGB_MAX_LEVELS + 1];      // CTA range of every level's group
+   int slice_ctas;                          // CTAs that share the level-0 rows of the CTA-slice operations (the working groups')
    const AsyncOp *ops;                      // all programs, group after group
    int op_begin[AMGB_MAX_LEVELS + 1];       // program of group q: ops[op_begin[q] .. op_begin[q+1])
    int n0;

@@ -1,8 +1,9 @@
 """bench.py's multi-GPU leg: the row-partitioned synchronous Multadd solve (DMEM_Add replacement,
 csrc/dist.cu) on N GPUs of one box, one process per GPU (torchrun), NCCL for the data path.
 
-Workload (BASELINE.json configs[4] family): 3-D 7-pt Laplacian on an n x n x (n*N) grid cut into N z-slabs of
-n^3 rows -- per-GPU work is fixed ("weak" scaling; N = 8, n = 256 is the 512^3-sized problem: 134 M rows).
+Workload (BASELINE.json configs[4] family): weak-scaling series with n^3 rows per GPU (grid doubled direction by direction:
+n^3, n x n x 2n, n x 2n x 2n, 2n x 2n x 2n -- N = 8, n = 256 is the 512^3 problem), cut into N z-slabs; and, beside it,
+the STRONG-scaling record of configs[4]: the fixed 512^3 problem on N GPUs, E(P) = t(1) / (P t(P)).
 Rank 0 builds the global hierarchy on the host (as DMEM_Setup's hypre does on all ranks), cuts it into
 per-rank row blocks and hands them over through /dev/shm; the timed region is the solve only.
 """
@@ -70,12 +71,25 @@ def _fact0(args):
     return not getattr(args, "no_factor_level0", False) and args.num_post > 0
 
 
-def _build_and_scatter(args, world, d):
+def weak_dims(n, world):
+    """grid of the weak-scaling series, n^3 rows per GPU: the cube is doubled one direction after the other, z first
+    (1: n^3, 2: n x n x 2n, 4: n x 2n x 2n, 8: 2n x 2n x 2n = the 512^3 problem for n = 256, then z again)"""
+    d = [n, n, n]
+    k, axis = world, 2
+    while k > 1 and k % 2 == 0:
+        d[axis] *= 2
+        axis = (axis - 1) % 3
+        k //= 2
+    d[2] *= k                      # odd remainder: more z-planes
+    return tuple(d)
+
+
+def _build_and_scatter(args, world, d, dims):
     """rank 0: global problem -> plan -> per-rank blocks on /dev/shm (freed level by level)"""
     t0 = time.time()
-    n = args.n
+    nx, ny, nz = dims
     H.set_host_threads(os.cpu_count() or 1)      # the other ranks idle at the barrier meanwhile
-    A = H.laplacian("7pt", n, n, n * world)
+    A = H.laplacian("7pt", nx, ny, nz)
     h = H.amg_setup(A, theta=args.theta)
     fact0 = _fact0(args)
     h.build_transfers(H.MULTADD, args.smooth_weight, num_pre=1, num_post=args.num_post, factor_level0=fact0)
@@ -84,8 +98,8 @@ def _build_and_scatter(args, world, d):
             "operator_complexity": round(h.operator_complexity(), 3),
             "bytes_per_cycle": int(H.bytes_sync_multadd_cycle_factored(h) if fact0 else H.bytes_sync_multadd_cycle(h, args.num_post > 0)),
             "host_setup_s": round(time.time() - t0, 1)}
-    _log("[bench] global hierarchy: %d levels, n=%s, host setup %.1fs" % (h.num_levels, h.n, time.time() - t0))
-    starts, num_dist, halos = PT.plan_layouts(h, world, plane=n * n, min_rows_per_rank=args.min_rows_per_rank)
+    _log("[bench] global hierarchy %dx%dx%d: %d levels, n=%s, host setup %.1fs" % (nx, ny, nz, h.num_levels, h.n, time.time() - t0))
+    starts, num_dist, halos = PT.plan_layouts(h, world, plane=nx * ny, min_rows_per_rank=args.min_rows_per_rank)
     layouts = [PT.rank_layouts(h, world, r, starts, num_dist, halos) for r in range(world)]
     os.makedirs(os.path.join(d, "shared"), exist_ok=True)
     for r in range(world):
@@ -125,28 +139,29 @@ def _build_and_scatter(args, world, d):
     _log("[bench] plan: %d distributed + %d replicated levels, blocks on %s after %.1fs" % (num_dist, L - num_dist, d, time.time() - t0))
 
 
-def run(args, rank, world, local):
+STRONG_T1 = os.path.join(os.environ.get("TMPDIR", "/tmp"), "amgb_strong_t1.json")
+
+
+def _leg(args, rank, world, local, dims, tag, steps, warmup, sampler=None):
+    """one partitioned solve series on the grid `dims` (z-slabs): returns the measurements (valid on every rank)"""
     import torch
     import torch.distributed as dist
-    from bench import ClockSampler, METRIC, TOL, load_peaks
-    torch.cuda.set_device(local)
-    dist.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world)
-    if args.solver != "multadd" or args.smoother != "j":
-        raise SystemExit("bench.py --gpus N>1 runs the synchronous Multadd / weighted-Jacobi path")
-    tag = os.environ.get("MASTER_PORT", "0")
+    from bench import TOL
     base = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
-    d = os.path.join(base, "amgb_plan_%s" % tag)
+    d = os.path.join(base, "amgb_plan_%s_%s" % (os.environ.get("MASTER_PORT", "0"), tag))
     if rank == 0:
         shutil.rmtree(d, ignore_errors=True)
-        _build_and_scatter(args, world, d)
+        _build_and_scatter(args, world, d, dims)
     dist.barrier()
     plan = _PlanFromDisk(d, rank, world)
     uid = [S.dist_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     t0 = time.time()
     s = S.DistSolver(plan, uid[0], args.smooth_weight, num_pre=1, num_post=args.num_post, use_sell=not args.no_sell,
-                     factor_level0=_fact0(args), device=local)
-    _log("[bench] rank %d: upload + device setup %.1fs, owned rows per level %s" % (rank, time.time() - t0, [x.n_owned for x in plan.layouts]))
+                     factor_level0=_fact0(args), device=local, lean_storage=True,
+                     sell_uniform=0 if getattr(args, "no_sell_uniform", False) else 1)
+    upload_s = time.time() - t0
+    _log("[bench] rank %d (%s): upload + device setup %.1fs, owned rows per level %s" % (rank, tag, upload_s, [x.n_owned for x in plan.layouts]))
     dist.barrier()
     if rank == 0:
         shutil.rmtree(d, ignore_errors=True)
@@ -160,15 +175,14 @@ def run(args, rank, world, local):
         torch.cuda.synchronize()
         dist.barrier()
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         hist, secs = s.solve_sync(TOL, args.max_cycles)
-    sampler = ClockSampler(local)
-    if rank == 0:
+    if sampler is not None and rank == 0:
         sampler.start()
     launches0 = s.launch_count()
     sync_all()
     times = []
-    for _ in range(args.steps):
+    for _ in range(steps):
         hist, secs = s.solve_sync(TOL, args.max_cycles)
         times.append(secs)
     sync_all()
@@ -178,7 +192,7 @@ def run(args, rank, world, local):
     solve_s = float(t.item())
     # end to end: host f slice in, host u slice out, per rank; wall clock, max over ranks
     e2e = []
-    for _ in range(args.steps + 1):
+    for _ in range(steps + 1):
         sync_all()
         w0 = time.perf_counter()
         s.set_rhs(f_host)
@@ -191,35 +205,89 @@ def run(args, rank, world, local):
     hb, ops = s.stats()
     hbt = torch.tensor([float(hb)], dtype=torch.float64, device="cuda")
     dist.all_reduce(hbt)
-    clocks = sampler.stop() if rank == 0 else None
-    cycles = len(hist) - 1
+    clocks = sampler.stop() if (sampler is not None and rank == 0) else None
+    out = {"solve_s": solve_s, "e2e_s": e2e_s, "cycles": len(hist) - 1, "final_relres": float(hist[-1]), "launches": int(launches),
+           "halo_bytes": float(hbt.item()), "nccl_ops": int(ops), "info": plan.info, "num_dist": plan.num_dist, "clocks": clocks,
+           "upload_s": round(upload_s, 1), "graph": bool(int(os.environ.get("AMGB_DIST_GRAPH", "1")))}
+    s.close()
+    dist.barrier()
+    return out
+
+
+def run(args, rank, world, local):
+    import torch
+    import torch.distributed as dist
+    from bench import ClockSampler, METRIC, load_peaks
+    torch.cuda.set_device(local)
+    dist.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world)
+    if args.solver != "multadd" or args.smoother != "j":
+        raise SystemExit("bench.py --gpus N>1 runs the synchronous Multadd / weighted-Jacobi path")
+    n = args.n
+    wd = weak_dims(n, world)
+    sn = args.strong_n
+    weak = _leg(args, rank, world, local, wd, "weak", args.steps, args.warmup, ClockSampler(local))
+    strong = None
+    if not args.no_strong:
+        if wd == (sn, sn, sn):
+            strong = dict(weak)            # at this rank count the weak-series grid IS the strong-scaling problem
+            strong["same_run_as_weak"] = True
+        else:
+            strong = _leg(args, rank, world, local, (sn, sn, sn), "strong", min(args.steps, 3), min(args.warmup, 3))
     if rank == 0:
         peak, peak_src = load_peaks()
-        info = plan.info
+        info = weak["info"]
+        cycles = weak["cycles"]
+        solve_s = weak["solve_s"]
         solve_bytes = info["bytes_per_cycle"] * cycles
         n0 = info["n"][0]
         line = {
             "metric": METRIC, "value": solve_s, "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": solve_s * 1e3, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "3D 7-pt Laplacian %dx%dx%d (n=%d) in %d z-slabs of %d^3 rows, sync Multadd, smoother j w=%.2f, tol 1e-9"
-                       % (args.n, args.n, args.n * world, n0, world, args.n, args.smooth_weight),
-                       "levels": info["levels"], "distributed_levels": plan.num_dist,
-                       "level0_transfers": "factorised (amgb_options.factor_level0)" if _fact0(args) else "explicit Pbar_0 / Rbar_0", "operator_complexity": info["operator_complexity"],
-                       "cycles_to_tol": int(cycles), "final_relres": float(hist[-1]), "rows_per_s": n0 / solve_s,
+            "config": {"workload": "3D 7pt Laplacian %dx%dx%d (n=%d) in %d z-slabs of %d rows, sync Multadd, smoother j w=%.2f, tol 1e-9"
+                       % (wd[0], wd[1], wd[2], n0, world, n0 // world, args.smooth_weight),
+                       "levels": info["levels"], "distributed_levels": weak["num_dist"],
+                       "level0_transfers": "factorised (amgb_options.factor_level0)" if _fact0(args) else "explicit Pbar_0 / Rbar_0",
+                       "operator_complexity": info["operator_complexity"],
+                       "cycles_to_tol": int(cycles), "final_relres": weak["final_relres"], "rows_per_s": n0 / solve_s,
                        "l2": "per-GPU inputs exceed the 126 MB L2; no explicit flush",
-                       "exchange": "NCCL send/recv halo with row-neighbours per SpMV input, all-gather of the first replicated level, all-reduce of the norm",
-                       "host_setup_s": info["host_setup_s"]},
-            "e2e": {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": int(8 * n0), "d2h_bytes_per_step": int(8 * n0)},
-            "gpu_launches": int(launches) * world,
-            "clocks": clocks,
+                       "exchange": "NCCL send/recv halo with row-neighbours per SpMV input, all-gather of the first replicated level, all-reduce of the norm; "
+                                   "the whole cycle (kernels + NCCL operations) is one CUDA graph per iteration" if weak["graph"] else
+                                   "NCCL send/recv halo with row-neighbours per SpMV input, all-gather of the first replicated level, all-reduce of the norm",
+                       "coarse_levels": "levels below %d rows per rank are REPLICATED on every GPU after one all-gather and computed redundantly "
+                                        "(instead of agglomerating them onto one GPU: no second exchange on the way up)" % args.min_rows_per_rank,
+                       "host_setup_s": info["host_setup_s"], "upload_s": weak["upload_s"]},
+            "e2e": {"value": weak["e2e_s"], "unit": "s", "h2d_bytes_per_step": int(8 * n0), "d2h_bytes_per_step": int(8 * n0)},
+            "gpu_launches": int(weak["launches"]) * world,
+            "clocks": weak["clocks"],
             "roofline": {"bound": "hbm", "kernel": "whole cycle (all k_spmv launches), aggregate over ranks", "achieved": solve_bytes / solve_s / 1e9,
                          "peak": peak * world, "unit": "GB/s", "frac": solve_bytes / solve_s / 1e9 / (peak * world),
                          "peak_source": peak_src + " x n_gpus", "traffic": None},
-            "comm": {"halo_bytes_sent_all_ranks": float(hbt.item()), "nccl_ops_per_rank": int(ops)},
+            "comm": {"halo_bytes_sent_all_ranks": weak["halo_bytes"], "nccl_ops_per_rank": weak["nccl_ops"]},
         }
+        if strong is not None:
+            si = strong["info"]
+            sb = si["bytes_per_cycle"] * strong["cycles"]
+            rec = {"workload": "3D 7pt Laplacian %d^3 (n=%d) in %d z-slabs, sync Multadd, smoother j w=%.2f, tol 1e-9 (BASELINE.json configs[4] problem)"
+                               % (sn, si["n"][0], world, args.smooth_weight),
+                   "scaling": "strong", "n_gpus": world, "value": strong["solve_s"], "unit": "s", "e2e": strong["e2e_s"],
+                   "cycles_to_tol": int(strong["cycles"]), "ms_per_cycle": strong["solve_s"] * 1e3 / max(strong["cycles"], 1),
+                   "final_relres": strong["final_relres"], "levels": si["levels"], "distributed_levels": strong["num_dist"],
+                   "roofline_frac": sb / strong["solve_s"] / 1e9 / (peak * world), "host_setup_s": si["host_setup_s"],
+                   "upload_s": strong["upload_s"], "same_run_as_weak": bool(strong.get("same_run_as_weak", False))}
+            try:
+                t1 = json.load(open(STRONG_T1))
+                if int(t1.get("n", 0)) == sn:
+                    rec["t1_seconds"] = t1["value"]
+                    rec["t1_cycles"] = t1["cycles"]
+                    rec["parallel_efficiency"] = t1["value"] / (world * strong["solve_s"])
+                    rec["parallel_efficiency_per_cycle"] = (t1["value"] / t1["cycles"]) / (world * strong["solve_s"] / max(strong["cycles"], 1))
+                    rec["efficiency_definition"] = "E(P) = t(1) / (P t(P)) on solve seconds of the same %d^3 problem; t(1) from `bench.py --gpus 1` on this box" % sn
+            except Exception:
+                rec["parallel_efficiency"] = None
+                rec["note"] = "t(1) not found on this box (%s): run `bench.py --gpus 1` first" % STRONG_T1
+            line["strong"] = rec
         print(json.dumps(line), flush=True)
-    s.close()
     dist.barrier()
     dist.destroy_process_group()
 

@@ -40,7 +40,8 @@ class Options(C.Structure):
                 ("num_fine_smooth_sweeps", C.c_int), ("num_coarse_smooth_sweeps", C.c_int),
                 ("jgs_block_rows", C.c_int), ("use_sell", C.c_int), ("l2_persist", C.c_int), ("use_stream", C.c_int),
                 ("factor_level0", C.c_int), ("coarse_solve", C.c_int), ("sell_sigma", C.c_int), ("stream_variant", C.c_int),
-                ("sell_uniform", C.c_int), ("async_type", C.c_int), ("res_compute_type", C.c_int), ("read_type", C.c_int)]
+                ("sell_uniform", C.c_int), ("async_type", C.c_int), ("res_compute_type", C.c_int), ("read_type", C.c_int),
+                ("lean_storage", C.c_int)]
 
 
 class HostCSR(C.Structure):
@@ -142,7 +143,7 @@ class Solver:
     def __init__(self, h, solver=H.MULTADD, smoother=H.JACOBI, smooth_weight=1.0, num_pre=1, num_post=1,
                  fine_sweeps=1, coarse_sweeps=1, jgs_block_rows=8, use_sell=True, l2_persist=True, use_stream=True,
                  stream_variant=None, sell_sigma=None, coarse_solve=False, factor_level0=False, device=0, jgs_blocks=None,
-                 sell_uniform=None, async_type=0, res_compute_type=0, read_type=0):
+                 sell_uniform=None, async_type=0, res_compute_type=0, read_type=0, lean_storage=False):
         self.L = load_library()
         self.h = h
         self.ctx = C.c_void_p()
@@ -173,6 +174,7 @@ class Solver:
         elif "AMGB_SELL_UNIFORM" in os.environ:
             o.sell_uniform = int(os.environ["AMGB_SELL_UNIFORM"])
         o.async_type, o.res_compute_type, o.read_type = int(async_type), int(res_compute_type), int(read_type)
+        o.lean_storage = int(lean_storage)
         self.options = o
         self._ck(self.L.amgb_set_options(self.ctx, C.byref(o)))
         self._ck(self.L.amgb_set_num_levels(self.ctx, h.num_levels))
@@ -429,7 +431,8 @@ class DistSolver:
     partition.RankPlan; `uid` the 128-byte id from dist_unique_id() of rank 0."""
 
     def __init__(self, plan, uid, smooth_weight=1.0, num_pre=1, num_post=1, use_sell=True, use_stream=True,
-                 coarse_solve=False, solver=H.MULTADD, factor_level0=False, device=0, smoother=H.JACOBI, sell_uniform=None):
+                 coarse_solve=False, solver=H.MULTADD, factor_level0=False, device=0, smoother=H.JACOBI, sell_uniform=None,
+                 lean_storage=False):
         self.L = load_library()
         self.plan = plan
         self.ctx = C.c_void_p()
@@ -444,6 +447,7 @@ class DistSolver:
         o.use_sell, o.use_stream = int(use_sell), int(use_stream)
         o.coarse_solve = int(coarse_solve)
         o.factor_level0 = int(factor_level0)
+        o.lean_storage = int(lean_storage)
         if sell_uniform is not None:
             o.sell_uniform = int(sell_uniform)
         elif "AMGB_SELL_UNIFORM" in os.environ:

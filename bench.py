@@ -330,6 +330,8 @@ def run_b200(args):
                 break
         line["async"] = res
         sa.close()
+    if not args.no_strong and sv == H.MULTADD and sm == H.JACOBI and args.problem == "7pt" and not args.cheby:
+        line["strong"] = strong_leg_single(args, amg, H, peak)
     if not args.no_cpu_baseline:
         if fact0:
             # the reference's own code takes the explicit products (src/SMEM_Setup.cpp:1173-1254)
@@ -342,6 +344,66 @@ def run_b200(args):
             line["details"]["hist_check_sample"] = {"against": "cpu_baseline sample (reference object code, same run)", "cycles_compared": int(k - 1),
                                                     "max_abs_diff": float(np.max(d)), "max_rel_diff": float(np.max(d / np.maximum(rh[:k], 1e-300)))}
     print(json.dumps(line), flush=True)
+
+
+def strong_leg_single(args, amg, H, peak):
+    """t(1) of the strong-scaling record (BASELINE.json configs[4]): the 512^3 problem on ONE GPU (lean storage: sliced ELL
+    only), written to a temp file so that the `--gpus N` runs on the same box can form E(P) = t(1) / (P t(P))"""
+    import gc
+    import torch
+    sn = args.strong_n
+    try:
+        import psutil
+        ram = psutil.virtual_memory().available / 2 ** 30
+    except Exception:
+        ram = 1e9
+    need = 110.0 * (sn / 512.0) ** 3
+    if ram < need:
+        return {"skipped": "host has %.0f GiB available; building the %d^3 hierarchy takes about %.0f GiB" % (ram, sn, need)}
+    try:
+        t0 = time.time()
+        A = H.laplacian("7pt", sn)
+        h = H.amg_setup(A, theta=args.theta)
+        h.build_transfers(H.MULTADD, args.smooth_weight, num_pre=1, num_post=args.num_post, factor_level0=True)
+        b = H.rand_rhs(A.nrows)
+        host_s = time.time() - t0
+        log("[bench] strong leg: %d^3 hierarchy %s, host setup %.1fs" % (sn, h.n, host_s))
+        t0 = time.time()
+        s = amg.Solver(h, H.MULTADD, H.JACOBI, args.smooth_weight, num_pre=1, num_post=args.num_post, factor_level0=True,
+                       lean_storage=True, sell_uniform=0 if args.no_sell_uniform else 1)
+        upload_s = time.time() - t0
+        bytes_cycle = H.bytes_sync_multadd_cycle_factored(h)
+        n0, levels = h.n[0], h.num_levels
+        s.set_rhs(b)
+        times, hist = [], None
+        for k in range(1 + min(args.steps, 3)):
+            s.set_solution(None)
+            hist, secs = s.solve_sync(TOL, args.max_cycles)
+            if k > 0:
+                times.append(secs)
+        t0 = time.perf_counter()
+        out = s.SMEM_Solve(b, TOL, args.max_cycles)
+        e2e = time.perf_counter() - t0
+        s.close()
+        del s, h, A, b
+        gc.collect()
+        torch.cuda.empty_cache()
+        v = float(np.mean(times))
+        cycles = len(hist) - 1
+        rec = {"workload": "3D 7pt Laplacian %d^3 (n=%d) on 1 GPU, sync Multadd, smoother j w=%.2f, tol 1e-9 (BASELINE.json configs[4] problem)"
+                           % (sn, n0, args.smooth_weight),
+               "scaling": "strong", "n_gpus": 1, "value": v, "unit": "s", "e2e": e2e, "cycles_to_tol": int(cycles),
+               "ms_per_cycle": v * 1e3 / max(cycles, 1), "final_relres": float(hist[-1]), "levels": levels,
+               "roofline_frac": bytes_cycle * cycles / v / 1e9 / peak, "host_setup_s": round(host_s, 1), "upload_s": round(upload_s, 1),
+               "parallel_efficiency": 1.0, "storage": "lean (sliced ELL only, no CSR copy)"}
+        try:
+            from async_multigrid_b200.dist_bench import STRONG_T1
+            json.dump({"n": sn, "value": v, "cycles": int(cycles)}, open(STRONG_T1, "w"))
+        except Exception as e:
+            rec["note"] = "could not write t(1) for the multi-GPU runs: %s" % e
+        return rec
+    except Exception as e:      # the headline line must survive a failure of this extra leg
+        return {"failed": "%s: %s" % (type(e).__name__, e)}
 
 
 def hist_check(args, h, hist):
@@ -503,6 +565,8 @@ def main():
     ap.add_argument("--read-type", type=int, default=0, help="asynchronous solver: 0 sol (default), 1 res (-read_type)")
     ap.add_argument("--min-rows-per-rank", type=int, default=16384,
                     help="multi-GPU: levels with fewer owned rows per rank are replicated, not partitioned")
+    ap.add_argument("--strong-n", type=int, default=512, help="grid of the strong-scaling record (BASELINE.json configs[4]: 512^3)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling record (512^3 on --gpus N GPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-async", action="store_true", help="skip the asynchronous solve reported beside the headline")
     ap.add_argument("--no-factor-level0", action="store_true",

@@ -76,6 +76,9 @@ typedef struct {
                                    which smooth level 0 and recompute the shared residual on their slices (src/SMEM_Async_AMG.cpp:35-70,356-416) */
    int read_type;               /* 0 READ_SOL (default): groups share the solution u; 1 READ_RES: groups share the residual,
                                    r -= A_0 e (src/SMEM_Async_AMG.cpp:227-236,285-296), u assembled at the end (:416-426) */
+   int lean_storage;            /* 1: a matrix stored as sliced ELL keeps no second (CSR) copy in HBM -- what lets the 512^3 hierarchy
+                                   (2.7 G entries in the A_l alone) fit one 180 GB GPU.  (L1-)Jacobi smoothers only; the transposed
+                                   product is then unavailable for those matrices.  0 (default): both copies */
 } amgb_options;
 
 void amgb_default_options(amgb_options *opt);
@@ -206,11 +209,11 @@ int amgb_time_spmv(amgb_ctx *ctx, int kind, int level, int use_scaled_values, in
 int amgb_stream_stats(amgb_ctx *ctx, long long *blocks, long long *blocks_with_staged_x);
 /* slices stored in the SELL-U encoding (amgb_options.sell_uniform) and their (delta, mask, value) groups */
 int amgb_sellu_stats(amgb_ctx *ctx, long long *slices, long long *groups);
-/* Host-only probe of the SELL-U encoder (no CUDA call; CPU test suite): CSR + column-scaled values in, per-slice group
- * offsets and the groups' delta / lane mask / value / scaled value out (malloc'ed: release with amgb_host_free).  Returns
- * the number of slices. */
+/* Host-only probe of the SELL-U encoder (no CUDA call; CPU test suite): CSR + column-scaled values in; out, per slice, the
+ * first group and the group count (2 ints per slice; count 0 = slice not encoded) into the DEDUPLICATED group table, and the
+ * table's delta / lane mask / value / scaled value (malloc'ed: release with amgb_host_free).  Returns the number of slices. */
 int amgb_sellu_encode_host(int nrows, const int *row_ptr, const int *col_idx, const double *values, const double *scaled_values,
-                           int **group_off, int **delta, unsigned int **mask, double **gvalues, double **gscaled, int *ngroups);
+                           int **slice_desc, int **delta, unsigned int **mask, double **gvalues, double **gscaled, int *ngroups);
 void amgb_host_free(void *p);
 /* coarse-hierarchy bytes living in the L2-pinned arena (cudaAccessPolicyWindow of the persistent kernel) */
 int amgb_l2_arena_bytes(amgb_ctx *ctx, long long *used, long long *capacity);

@@ -43,7 +43,7 @@ class Emulator:
         for q in range(self.L):
             n = 0 if q < first_group else (1 if q == self.L - 1 and self.L > 1 else ctas_per_group)
             self.cta_begin[q + 1] = self.cta_begin[q] + n
-        self.grid = self.cta_begin[-1]
+        self.grid = self.cta_begin[self.L - 1] if self.L > 1 else self.cta_begin[-1]    # (the idle coarsest group owns no rows)
 
     def vec(self, q, vid, level_rows=None):
         if vid < 0:
