@@ -138,8 +138,10 @@ def test_bench_plan_roundtrip_through_disk(tmp_path):
     args = types.SimpleNamespace(n=12, theta=0.25, smooth_weight=0.9, num_post=1, min_rows_per_rank=64)
     world = 2
     d = str(tmp_path / "plan")
-    DB._build_and_scatter(args, world, d)
-    A = H.laplacian("7pt", 12, 12, 12 * world)
+    dims = DB.weak_dims(12, world)
+    assert dims == (12, 12, 24) and DB.weak_dims(256, 8) == (512, 512, 512) and DB.weak_dims(256, 4) == (256, 512, 512)
+    DB._build_and_scatter(args, world, d, dims)
+    A = H.laplacian("7pt", *dims)
     h = H.amg_setup(A)
     h.build_transfers(H.MULTADD, 0.9, factor_level0=True)      # the bench's multi-GPU leg uploads plain P_0 / R_0
     b = H.rand_rhs(A.nrows)
