@@ -719,6 +719,9 @@ int amgb_setup(amgb_ctx *c)
    const bool multadd = o.solver == AMGB_SOLVER_MULTADD || o.solver == AMGB_SOLVER_ASYNC_MULTADD;
    c->symmetric = multadd && o.num_pre_smooth_sweeps > 0 && o.num_post_smooth_sweeps > 0 &&
                   (o.smoother == AMGB_SMOOTH_JACOBI || o.smoother == AMGB_SMOOTH_L1_JACOBI);
+   if (o.smoother == AMGB_SMOOTH_L1_HYBRID_JGS && o.solver != AMGB_SOLVER_BPX)
+      return amgb_fail(c, AMGB_EINVAL, "L1_HYBRID_JACOBI_GAUSS_SEIDEL exists in the Parfor smoother only (BPX); the reference's ALL_LEVELS "
+                                       "dispatcher silently runs weighted Jacobi for it (src/SMEM_Solve.cpp:277-323)");
    if (o.factor_level0 && !((o.solver == AMGB_SOLVER_MULTADD || o.solver == AMGB_SOLVER_ASYNC_MULTADD) && c->symmetric))
       return amgb_fail(c, AMGB_EINVAL, "factor_level0 applies to Multadd with the symmetrised (L1-)Jacobi smoother");
    int rc;
@@ -873,8 +876,9 @@ void enq_smooth_zero(amgb_ctx *c, int l, const double *f, double *e, int sweeps,
       c->launches += launch_async_gs(c->cfg, c->stream, A, f, e, c->opt.jgs_block_rows, sweeps, sm == AMGB_SMOOTH_SEMI_ASYNC_GS);
       return;
    }
-   if (sm == AMGB_SMOOTH_HYBRID_JGS) {
-      const double *scale = parfor ? c->dow[l] : nullptr;
+   if (sm == AMGB_SMOOTH_HYBRID_JGS || sm == AMGB_SMOOTH_L1_HYBRID_JGS) {
+      // Parfor branch (BPX): divisor A_diag = a_ii / w, or the l1 norms for L1_HYBRID_JACOBI_GAUSS_SEIDEL (src/SMEM_Smooth.cpp:253-263)
+      const double *scale = sm == AMGB_SMOOTH_L1_HYBRID_JGS ? c->l1[l] : (parfor ? c->dow[l] : nullptr);
       c->launches += jgs_sweep(c, l, A, f, e, nullptr, scale, true);
       for (int k = 1; k < sweeps; k++) {
          cudaMemcpyAsync(s1, e, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream);

@@ -188,3 +188,151 @@ extern "C" int amgb_solve_extended(amgb_ctx *c, double tol, int num_cycles, doub
    CUDA_OK(c, cudaGetLastError());
    return AMGB_OK;
 }
+
+// ---- asynchronous EXPLICIT extended-system solver (`-solver async_eebpx`) -------------------------------------------------
+// SMEM_ExtendedSystemSolve with EXPLICIT_EXTENDED_SYSTEM_BPX and async_flag = 1 (src/SMEM_ExtendedSystem.cpp:295-365 with the
+// `#pragma omp barrier`s of :330-332,362-364 skipped; stop rule :636-652): every thread relaxes ITS rows of AA x = bb over and
+// over -- r_loc = b - AA x with whatever x the others have written so far, x <- y + omega (delta r ./ diag + x - y), y <- old x,
+// its own omega recurrence -- and nobody waits for anybody.  Here a thread is a CTA of a persistent cooperative launch that
+// owns a contiguous, nnz-balanced row range (thread.AA_NS / AA_NE); x is shared through L2 (the CTA's L1 is invalidated once
+// per sweep by the fence of its leader, so every sweep reads what has reached L2).  Stop: thread 0's sum of the (stale)
+// per-thread residual contributions drops below tol * r0_ext (resnorm_converge_flag), or every thread has done num_cycles
+// sweeps (threads that are done keep relaxing until the last one is: glob_done_iters == num_threads).
+#include "kernels.cuh"
+
+struct ExtAsyncParams {
+   DevCSR A;
+   const double *b;
+   double *x, *y, *r;
+   const double *inv_d;            // 1 / a_ii
+   const int *row_bounds;          // [grid + 1]
+   double delta, mu22, tol2_r0;    // tol^2 * r0_ext^2
+   int num_cycles;
+   double *cta_r2;                 // [grid] residual contribution of every CTA's last sweep
+   volatile int *flag;             // resnorm_converge_flag
+   int *done;                      // glob_done_iters
+   int *iters;                     // [grid] loc_iters of every CTA at exit
+};
+
+namespace {
+constexpr int kEBlock = 256;
+
+__global__ void __launch_bounds__(kEBlock) k_async_eebpx(ExtAsyncParams p)
+{
+   const int cta = blockIdx.x, nct = gridDim.x;
+   const int r0 = p.row_bounds[cta], r1 = p.row_bounds[cta + 1];
+   DevCSR M = p.A;
+   M.rp += r0; M.nrows = r1 - r0;
+   SpmvEpilogue e;
+   e.alpha = -1.0; e.beta = 1.0; e.gamma = 0.0; e.b = p.b + r0; e.c = nullptr; e.rs = nullptr;
+   double omega = 2.0;
+   int loc_iters = 1;
+   __shared__ int s_stop;
+   if (p.num_cycles > 1)
+      for (;;) {
+         // r_loc = b - AA x on this CTA's rows (vector-per-row CSR; x through L1, refreshed by the fence below)
+         csr_rows_dispatch<false, false>(M, p.x, p.r + r0, e, threadIdx.x, kEBlock, false);
+         __syncthreads();
+         double part = 0.0;
+         for (int i = r0 + threadIdx.x; i < r1; i += kEBlock) {
+            const double xo = ld_cg(p.x + i), yo = p.y[i], ri = p.r[i];
+            st_cg(p.x + i, yo + omega * (p.delta * ri * __ldg(p.inv_d + i) + xo - yo));
+            p.y[i] = xo;
+            part += ri * ri;
+         }
+         part = block_sum(part);
+         omega = 1.0 / (1.0 - omega / p.mu22);
+         loc_iters++;
+         if (threadIdx.x == 0) {
+            if (loc_iters > 2) *((volatile double *)(p.cta_r2 + cta)) = part;        // check_resnorm_flag && loc_iters > 1 (before the increment)
+            __threadfence();                                                         // publishes x; invalidates this SM's L1
+            if (cta == 0 && loc_iters > 2) {
+               double s = 0.0;
+               for (int t = 0; t < nct; t++) s += *((volatile double *)(p.cta_r2 + t));
+               if (s < p.tol2_r0) *p.flag = 1;
+            }
+            int stop = *p.flag;
+            if (!stop && loc_iters >= p.num_cycles) {
+               if (loc_iters == p.num_cycles) atomicAdd(p.done, 1);
+               if (*((volatile int *)p.done) == nct) stop = 1;
+            }
+            s_stop = stop;
+         }
+         __syncthreads();
+         if (s_stop) break;
+      }
+   if (threadIdx.x == 0) p.iters[cta] = loc_iters;
+}
+}  // namespace
+
+// One-level context holding the assembled extended matrix AA (smooth_weight = 1), resident f = bb.  Leaves the extended
+// iterate in u (amgb_get_solution); ext_relres = |bb - AA x| / |bb - AA x_0| recomputed after the launch; iters_min / iters_max:
+// fewest / most sweeps any CTA performed.
+extern "C" int amgb_solve_extended_async(amgb_ctx *c, double tol, int num_cycles, double mu, double delta, int *iters_min, int *iters_max,
+                                         double *ext_relres, double *solve_seconds)
+{
+   NEED_READY(c);
+   if (c->L != 1) return amgb_fail(c, AMGB_EINVAL, "the asynchronous extended-system solver runs the EXPLICIT form: a one-level context that holds AA");
+   if (num_cycles < 0 || mu == 0.0) return amgb_fail(c, AMGB_EINVAL, "bad arguments");
+   const DevCSR &A = c->A[0];
+   if (!A.ci || !A.va) return amgb_fail(c, AMGB_EINVAL, "needs the CSR copy of AA (lean_storage = 0)");
+   const int n = A.nrows;
+   int rc;
+   if ((rc = ext_alloc(c))) return rc;
+   ExtState *x = c->ext;
+   // r0_ext and x_0 = delta r ./ diag (the reference starts from xx = 0: :100-106)
+   CUDA_OK(c, cudaMemsetAsync(c->u, 0, sizeof(double) * (size_t)n, c->stream));
+   enq_residual(c);
+   double ss;
+   if ((rc = amgb_fetch_scalar(c, &ss))) return rc;
+   const double r0_ext = sqrt(ss);
+   c->launches += launch_scale(c->cfg, c->stream, n, c->ws[0], c->r[0], c->u);                        // ws = w / d with w = smooth_weight
+   c->launches += launch_axpby(c->cfg, c->stream, n, 0.0, c->r[0], delta / c->opt.smooth_weight, c->u, nullptr);
+   CUDA_OK(c, cudaMemsetAsync(x->y[0], 0, sizeof(double) * (size_t)n, c->stream));
+   // 1 / a_ii
+   c->launches += launch_axpby(c->cfg, c->stream, n, 1.0 / c->opt.smooth_weight, c->ws[0], 0.0, x->us[0], nullptr);
+   // CTAs: one cooperative wave, nnz-balanced contiguous row ranges (hypre_LowerBound on the row pointer, src/SMEM_Setup.cpp:870-893)
+   int dev = 0, sms = 0, per_sm = 0;
+   cudaGetDevice(&dev);
+   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_async_eebpx, kEBlock, 0);
+   int grid = std::max(1, std::min(sms * per_sm, std::max(1, n / 64)));
+   std::vector<int> rp((size_t)n + 1);
+   CUDA_OK(c, cudaMemcpy(rp.data(), A.rp, sizeof(int) * rp.size(), cudaMemcpyDeviceToHost));
+   std::vector<int> bounds((size_t)grid + 1, n);
+   bounds[0] = 0;
+   const long per = ((long)A.nnz + grid - 1) / grid;
+   for (int t = 1; t < grid; t++) bounds[t] = (int)(std::lower_bound(rp.begin(), rp.begin() + n, (int)std::min<long>(per * t, A.nnz)) - rp.begin());
+   for (int t = 1; t <= grid; t++) bounds[t] = std::max(bounds[t], bounds[t - 1]);
+   int *d_bounds = nullptr, *d_misc = nullptr;
+   double *d_r2 = nullptr;
+   if ((rc = amgb_dev_alloc_bytes(c, (void **)&d_bounds, sizeof(int) * bounds.size(), false))) return rc;
+   if ((rc = amgb_dev_alloc_bytes(c, (void **)&d_misc, sizeof(int) * ((size_t)grid + 8), true))) return rc;
+   if ((rc = amgb_dev_alloc_bytes(c, (void **)&d_r2, sizeof(double) * (size_t)grid, false))) return rc;
+   CUDA_OK(c, cudaMemcpyAsync(d_bounds, bounds.data(), sizeof(int) * bounds.size(), cudaMemcpyHostToDevice, c->stream));
+   std::vector<double> big((size_t)grid, 1e300);          // r_norm2_glob[t] = 100 in the reference (:52): "not measured yet"
+   CUDA_OK(c, cudaMemcpyAsync(d_r2, big.data(), sizeof(double) * big.size(), cudaMemcpyHostToDevice, c->stream));
+   ExtAsyncParams p;
+   p.A = A; p.b = c->f; p.x = c->u; p.y = x->y[0]; p.r = x->r[0]; p.inv_d = x->us[0]; p.row_bounds = d_bounds;
+   p.delta = delta; p.mu22 = (2.0 * mu) * (2.0 * mu); p.tol2_r0 = tol * tol * r0_ext * r0_ext; p.num_cycles = num_cycles;
+   p.cta_r2 = d_r2; p.flag = d_misc; p.done = d_misc + 1; p.iters = d_misc + 8;
+   CUDA_OK(c, cudaStreamSynchronize(c->stream));
+   CUDA_OK(c, cudaEventRecord(c->ev0, c->stream));
+   void *args[] = {&p};
+   CUDA_OK(c, cudaLaunchCooperativeKernel((void *)k_async_eebpx, dim3(grid), dim3(kEBlock), args, 0, c->stream));
+   c->launches += 1;
+   CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));
+   CUDA_OK(c, cudaEventSynchronize(c->ev1));
+   float ms = 0;
+   cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+   if (solve_seconds) *solve_seconds = ms * 1e-3;
+   std::vector<int> its((size_t)grid);
+   CUDA_OK(c, cudaMemcpy(its.data(), d_misc + 8, sizeof(int) * (size_t)grid, cudaMemcpyDeviceToHost));
+   if (iters_min) *iters_min = *std::min_element(its.begin(), its.end());
+   if (iters_max) *iters_max = *std::max_element(its.begin(), its.end());
+   enq_residual(c);
+   if ((rc = amgb_fetch_scalar(c, &ss))) return rc;
+   if (ext_relres) *ext_relres = sqrt(ss) / r0_ext;
+   CUDA_OK(c, cudaGetLastError());
+   return AMGB_OK;
+}

@@ -18,6 +18,7 @@ HYBRID_JACOBI_GAUSS_SEIDEL = 2
 SEMI_ASYNC_GAUSS_SEIDEL = 4
 ASYNC_GAUSS_SEIDEL = 5
 L1_JACOBI = 6
+L1_HYBRID_JACOBI_GAUSS_SEIDEL = 12      # Parfor smoother only (BPX): hybrid JGS divided by the l1 norms
 MULT, AFACX, MULTADD, BPX = 0, 1, 2, 3
 ASYNC_AFACX, ASYNC_MULTADD = 5, 6
 PAR_BPX = 17                        # `-solver par_bpx` (src/Main.hpp:77): see par_bpx_equivalent

@@ -24,7 +24,7 @@ ABI_SYMBOLS = [
     "amgb_set_num_levels", "amgb_set_matrix", "amgb_set_options", "amgb_setup",
     "amgb_set_rhs", "amgb_set_solution", "amgb_get_solution", "amgb_get_residual",
     "amgb_spgemv", "amgb_spgemv_transpose", "amgb_smooth", "amgb_set_jgs_blocks", "amgb_norm2", "amgb_cycle", "amgb_eigs_power", "amgb_solve_sync", "amgb_solve_async",
-    "amgb_async_groups", "amgb_solve_extended", "amgb_smooth_transfer", "amgb_host_csr_free", "amgb_smem_solve", "amgb_time_residual", "amgb_level_storage", "amgb_time_spmv", "amgb_stream_stats", "amgb_l2_arena_bytes", "amgb_sellu_stats",
+    "amgb_async_groups", "amgb_solve_extended", "amgb_solve_extended_async", "amgb_smooth_transfer", "amgb_host_csr_free", "amgb_smem_solve", "amgb_time_residual", "amgb_level_storage", "amgb_time_spmv", "amgb_stream_stats", "amgb_l2_arena_bytes", "amgb_sellu_stats",
     "amgb_sellu_encode_host", "amgb_host_free", "amgb_async_program", "amgb_async_group_times",
     "amgb_dist_unique_id", "amgb_dist_init", "amgb_dist_set_level", "amgb_dist_setup", "amgb_dist_set_rhs",
     "amgb_dist_get_solution", "amgb_dist_solve_sync", "amgb_dist_solve_sync_accel", "amgb_dist_stats",
@@ -87,6 +87,7 @@ def load_library():
     L.amgb_solve_sync.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, DP, IP, DP]
     L.amgb_solve_async.argtypes = [C.c_void_p, C.c_int, C.c_int, IP, DP, DP]
     L.amgb_solve_extended.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_double, C.c_double, DP, IP, DP, DP, DP]
+    L.amgb_solve_extended_async.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_double, C.c_double, IP, IP, DP, DP]
     L.amgb_smooth_transfer.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, IP, IP, DP, C.c_int, IP, IP, DP,
                                        C.POINTER(HostCSR), C.POINTER(HostCSR)]
     L.amgb_host_csr_free.argtypes = [C.POINTER(HostCSR)]
@@ -596,6 +597,23 @@ class ExtendedExplicitSolver:
         rel = self.hs.norm2(r) / self.hs.norm2(np.ascontiguousarray(f, dtype=np.float64))
         return dict(x=v, xx=xx, iters=out["iters"], ext_hist=out["ext_hist"], ext_relres=out["relres"], relres=rel,
                     seconds=out["seconds"])
+
+    def SMEM_ExtendedSystemSolve_async(self, f, tol=1e-9, num_cycles=100, mu=1.0, delta=1.0):
+        """`-solver async_eebpx`: the same system relaxed asynchronously (amgb_solve_extended_async) -> dict(x, xx, iters_min,
+        iters_max, ext_relres, relres, seconds)"""
+        bb = self.extended_rhs(f)
+        self.ext.set_rhs(bb)
+        lo, hi = C.c_int(0), C.c_int(0)
+        er, secs = C.c_double(0), C.c_double(0)
+        self.ext._ck(self.ext.L.amgb_solve_extended_async(self.ext.ctx, tol, int(num_cycles), mu, delta, C.byref(lo), C.byref(hi),
+                                                          C.byref(er), C.byref(secs)))
+        xx, d, L = self.ext.get_solution(), self.disp, self.h.num_levels
+        v = np.ascontiguousarray(xx[d[L - 1]:d[L]])
+        for l in range(L - 2, -1, -1):
+            v = self.hs.spgemv(MAT_P, l, 1.0, v, 1.0, np.ascontiguousarray(xx[d[l]:d[l + 1]]))
+        r = self.hs.spgemv(MAT_A, 0, -1.0, v, 1.0, np.ascontiguousarray(f, dtype=np.float64))
+        rel = self.hs.norm2(r) / self.hs.norm2(np.ascontiguousarray(f, dtype=np.float64))
+        return dict(x=v, xx=xx, iters_min=lo.value, iters_max=hi.value, ext_relres=er.value, relres=rel, seconds=secs.value)
 
     def close(self):
         self.ext.close()

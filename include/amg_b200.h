@@ -31,7 +31,9 @@ enum {
 
 /* enumerators keep the reference's numeric values (src/Main.hpp:47-75) */
 enum { AMGB_SMOOTH_JACOBI = 0, AMGB_SMOOTH_HYBRID_JGS = 2, AMGB_SMOOTH_SEMI_ASYNC_GS = 4, AMGB_SMOOTH_ASYNC_GS = 5,
-       AMGB_SMOOTH_L1_JACOBI = 6 };
+       AMGB_SMOOTH_L1_JACOBI = 6,
+       AMGB_SMOOTH_L1_HYBRID_JGS = 12 /* L1_HYBRID_JACOBI_GAUSS_SEIDEL: hybrid JGS divided by the l1 norms; BPX only -- the reference
+                                         reaches it through the Parfor branch alone (src/SMEM_Solve.cpp:324-334, src/SMEM_Smooth.cpp:253-263) */ };
 enum { AMGB_SOLVER_MULT = 0, AMGB_SOLVER_AFACX = 1, AMGB_SOLVER_MULTADD = 2, AMGB_SOLVER_BPX = 3,
        AMGB_SOLVER_ASYNC_AFACX = 5, AMGB_SOLVER_ASYNC_MULTADD = 6,
        AMGB_SOLVER_IEBPX = 16 /* IMPLICIT_EXTENDED_SYSTEM_BPX: amgb_solve_extended; hierarchy as for BPX */ };
@@ -178,6 +180,14 @@ int amgb_async_program(const amgb_options *opt, int num_levels, int symmetric, i
  * (amgb_get_solution). */
 int amgb_solve_extended(amgb_ctx *ctx, double tol, int num_cycles, double mu, double delta, double *ext_hist, int *iters,
                         double *ext_relres, double *relres, double *solve_seconds);
+
+/* The EXPLICIT form run ASYNCHRONOUSLY (`-solver async_eebpx`: EXPLICIT_EXTENDED_SYSTEM_BPX with async_flag = 1,
+ * src/SMEM_ExtendedSystem.cpp:295-365 without its barriers, stop rule :636-652) on a ONE-level context whose A_0 is the assembled
+ * extended matrix AA (smooth_weight = 1) and whose resident f is bb: one persistent cooperative kernel, a CTA = a thread's
+ * contiguous nnz-balanced row range, chaotic Chebyshev-Jacobi relaxations with no barrier between CTAs.  The extended
+ * iterate is left in u; iters_min / iters_max = fewest / most sweeps a CTA did; ext_relres recomputed after the launch. */
+int amgb_solve_extended_async(amgb_ctx *ctx, double tol, int num_cycles, double mu, double delta, int *iters_min, int *iters_max,
+                              double *ext_relres, double *solve_seconds);
 
 /* Drop-in for one whole SMEM_Solve call with HOST buffers (what SMEM_Main's run loop would call,
  * src/SMEM_Main.cpp:694-757): uploads f, zeroes u (InitSolve), runs the sync or async solve named

@@ -37,6 +37,7 @@ typedef struct {
 #define ORC_JACOBI 0
 #define ORC_HYBRID_JGS 2
 #define ORC_L1_JACOBI 6
+#define ORC_L1_HYBRID_JGS 12   /* L1_HYBRID_JACOBI_GAUSS_SEIDEL: Parfor branch only, divisor = l1 norms (src/SMEM_Smooth.cpp:253-263) */
 #define ORC_MULT 0
 #define ORC_AFACX 1
 #define ORC_MULTADD 2
@@ -257,11 +258,14 @@ static void orc_smooth(const orc_problem *pb, int level, const double *f, double
 {
    const orc_csr *A = &pb->A[level];
    const int symm = (pb->solver == ORC_MULTADD) && pb->num_pre > 0 && pb->num_post > 0;
-   if (pb->smoother == ORC_HYBRID_JGS) {
+   if (pb->smoother == ORC_HYBRID_JGS || pb->smoother == ORC_L1_HYBRID_JGS) {
       double *scale = NULL;
-      if (pb->jgs_parfor_scale || pb->solver == ORC_BPX) {
+      if (pb->jgs_parfor_scale || pb->solver == ORC_BPX || pb->smoother == ORC_L1_HYBRID_JGS) {
+         /* SMEM_Sync_Parfor_HybridJacobiGaussSeidel, src/SMEM_Smooth.cpp:253-263: diag_scale = hypre's l1 norms for the L1
+          * variant, A_diag = a_ii / w otherwise (the ALL_LEVELS dispatcher never reaches the L1 variant, src/SMEM_Solve.cpp:277-323) */
          scale = (double *)malloc(sizeof(double) * (size_t)A->nrows);
-         for (int i = 0; i < A->nrows; i++) scale[i] = A->data[A->i[i]] / pb->smooth_weight;
+         for (int i = 0; i < A->nrows; i++)
+            scale[i] = pb->smoother == ORC_L1_HYBRID_JGS ? pb->l1[level][i] : A->data[A->i[i]] / pb->smooth_weight;
       }
       orc_hybrid_jgs(A, f, u, scratch_y, pb->jgs_blocks[level], pb->jgs_nblocks[level], scale, sweeps, 1);
       free(scale);

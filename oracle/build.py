@@ -8,6 +8,7 @@ import sys
 ORACLE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_LIB = os.path.join(ORACLE, "liboracle.so")
 REF_LIB = os.path.join(ORACLE, "_ref", "libref_smem.so")
+REF_B200_LIB = os.path.join(ORACLE, "_ref", "libref_b200.so")     # the same + INTEGRATION.md's binding, linked against libamg_b200.so
 
 
 def _newer(target, sources):
@@ -41,7 +42,8 @@ def build_ref(force=False):
         return REF_LIB if os.path.exists(REF_LIB) else None
     script = os.path.join(ORACLE, "build_ref.sh")
     shim = os.path.join(ORACLE, "ref_shim")
-    deps = [script, os.path.join(ORACLE, "ref_driver.cpp")] + [os.path.join(d, f) for d, _, fs in os.walk(shim) for f in fs]
+    deps = [script, os.path.join(ORACLE, "ref_driver.cpp"), os.path.join(os.path.dirname(ORACLE), "integration", "SMEM_B200.hpp")]
+    deps += [os.path.join(d, f) for d, _, fs in os.walk(shim) for f in fs]
     if not force and _newer(REF_LIB, deps):
         return REF_LIB
     _run(["bash", script])

@@ -25,5 +25,13 @@ g++ -shared -fopenmp -o "$OUT/libref_smem.so" "$OUT"/*.o -Wl,--no-undefined 2> "
    grep -o "undefined reference to \`[^']*'" "$OUT/link.log" | sort -u | head -40
    g++ -shared -fopenmp -o "$OUT/libref_smem.so" "$OUT"/*.o
 }
+# the same objects + the binding of INTEGRATION.md (integration/SMEM_B200.hpp compiled against the reference's Main.hpp), linked
+# against the product library: the reference-side structs drive libamg_b200.so (GPU test only; needs the built product library)
+PKG="$HERE/../async-multigrid_b200"
+if [ -f "$PKG/libamg_b200.so" ]; then
+   $CXX -DREF_WITH_B200 -I"$HERE/../include" -I"$HERE/../integration" -c "$HERE/ref_driver.cpp" -o "$OUT/ref_driver.o"
+   g++ -shared -fopenmp -o "$OUT/libref_b200.so" "$OUT"/*.o -L"$PKG" -lamg_b200 -Wl,-rpath,'$ORIGIN/../../async-multigrid_b200' \
+      && echo "built $OUT/libref_b200.so"
+fi
 rm -f "$OUT"/*.o
 echo "built $OUT/libref_smem.so"

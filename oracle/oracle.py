@@ -226,6 +226,26 @@ def smooth(kind, m, f, w=1.0, sweeps=1, zero_flag=1, u0=None, l1=None, blocks=No
 _ref = None
 
 
+_ref_b200 = None
+
+
+def ref_b200_lib():
+    """oracle/_ref/libref_b200.so: the reference's object code + the binding of INTEGRATION.md (integration/SMEM_B200.hpp),
+    linked against libamg_b200.so -- the reference-side structs drive the product library.  None when absent; loading it
+    needs the CUDA runtime (GPU box)."""
+    global _ref_b200
+    if _ref_b200 is None:
+        path = _build.REF_B200_LIB
+        if not os.path.exists(path):
+            return None
+        L = C.CDLL(path)
+        _declare_ref(L)
+        L.ref_solve_b200.restype = C.c_int
+        L.ref_solve_b200.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, DP, DP, IP, DP]
+        _ref_b200 = L
+    return _ref_b200
+
+
 def ref_lib():
     """None when oracle/_ref is absent (it is built only where /root/reference is mounted and
     travels to the GPU box as a prebuilt file)."""
@@ -240,6 +260,13 @@ def ref_lib():
         if not os.path.exists(path):
             return None
         L = C.CDLL(path)
+        _declare_ref(L)
+        _ref = L
+    return _ref
+
+
+def _declare_ref(L):
+    if True:
         L.ref_create.restype = C.c_void_p
         L.ref_create.argtypes = [C.c_int, C.POINTER(OrcCSR), C.POINTER(OrcCSR), C.POINTER(OrcCSR), C.POINTER(DP),
                                  C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -256,8 +283,6 @@ def ref_lib():
         L.ref_read_matrix.restype = C.c_int
         L.ref_read_matrix.argtypes = [C.c_char_p, C.c_int, IP, IP, C.POINTER(IP), C.POINTER(IP), C.POINTER(DP)]
         L.ref_free.argtypes = [C.c_void_p]
-        _ref = L
-    return _ref
 
 
 def ref_solve_eebpx(h, AA, disp, bb, num_cycles, tol=1e-9, mu=1.0, delta=1.0, num_threads=4):
@@ -491,11 +516,11 @@ class RefSolver:
     for the thread-group-per-level cycles."""
 
     def __init__(self, h, solver, smoother, f, smooth_weight=1.0, num_pre=1, num_post=1,
-                 fine_sweeps=1, coarse_sweeps=1, num_threads=None, one_thread_per_level=False):
+                 fine_sweeps=1, coarse_sweeps=1, num_threads=None, one_thread_per_level=False, lib=None):
         hier = _pkg.hierarchy
         L = h.num_levels
         self.h = h
-        self.L = ref_lib()
+        self.L = ref_lib() if lib is None else lib
         if self.L is None:
             raise RuntimeError("oracle/_ref/libref_smem.so not available")
         if num_threads is None:
@@ -539,6 +564,17 @@ class RefSolver:
         k = self.L.ref_solve(self.handle, num_cycles, tol, async_type, 1 if cheby else 0, mu, delta, precond,
                              dptr(u), dptr(hist), iptr(corr), C.byref(secs), C.byref(rr))
         return dict(u=u, hist=hist[:k + 1], cycles=k, corrections=corr, seconds=secs.value, relres=rr.value)
+
+    def solve_b200(self, num_cycles, tol=1e-9, async_type=0, res_compute_type=0, read_type=0):
+        """(lib = ref_b200_lib()) InitSolve + INTEGRATION.md's SMEM_B200_Upload / SMEM_Solve_B200 on this handle's AllData"""
+        n = self.h.n[0]
+        u = np.zeros(n)
+        hist = np.zeros(num_cycles + 1)
+        corr = np.zeros(self.h.num_levels, dtype=np.int32)
+        rr = C.c_double(0)
+        k = self.L.ref_solve_b200(self.handle, num_cycles, tol, async_type, res_compute_type, read_type, dptr(u), dptr(hist),
+                                  iptr(corr), C.byref(rr))
+        return dict(u=u, hist=hist[:k + 1], cycles=k, corrections=corr, relres=rr.value)
 
     def solve_iebpx(self, num_cycles, tol=1e-9, mu=1.0, delta=1.0):
         """SMEM_ExtendedSystemSolve, IMPLICIT_EXTENDED_SYSTEM_BPX, synchronous (handle created with solver = 16)"""

@@ -682,6 +682,42 @@ int ref_solve_sync_det(void *h, int num_cycles, double tol, double *u_out, doubl
    return done;
 }
 
+#ifdef REF_WITH_B200
+// The binding of INTEGRATION.md (integration/SMEM_B200.hpp, compiled here against the reference's own Main.hpp) driven by the
+// reference-side structs: InitSolve, then SMEM_Solve_B200 instead of SMEM_Solve.  hist: the library's residual history.
+}   // extern "C"
+#ifndef MPI_VERSION
+static int MPI_Finalize() { return 0; }        // (the reference gets MPI through hypre's headers; this build is single-process)
+#endif
+#include "SMEM_B200.hpp"
+extern "C" {
+int ref_solve_b200(void *h, int num_cycles, double tol, int async_type, int res_compute_type, int read_type, double *u_out, double *hist,
+                   int *corrections, double *final_relres)
+{
+   RefHandle *H = (RefHandle *)h;
+   AllData *ad = &H->all;
+   ad->input.num_cycles = num_cycles;
+   ad->input.tol = tol;
+   ad->input.async_type = async_type;
+   ad->input.res_compute_type = res_compute_type;
+   ad->input.read_type = read_type;
+   ad->input.cheby_flag = 0;
+   ad->input.precond_flag = 0;
+   ad->input.print_reshist_flag = 0;
+   InitSolve(ad);
+   SMEM_B200_Upload(ad);
+   SMEM_Solve_B200(ad);
+   const int done = ad->output.num_cycles;
+   if (hist) for (int k = 0; k <= done && k < (int)b200_hist.size(); k++) hist[k] = b200_hist[k];
+   if (u_out) memcpy(u_out, ad->vector.u[0], sizeof(double) * ad->grid.n[0]);
+   if (corrections) for (int l = 0; l < ad->grid.num_levels; l++) corrections[l] = ad->grid.local_num_correct[l];
+   if (final_relres) *final_relres = ad->output.r_norm2 / ad->output.r0_norm2;
+   amgb_destroy(b200);
+   b200 = NULL;
+   return done;
+}
+#endif
+
 // SMEM_ExtendedSystemSolve (src/SMEM_ExtendedSystem.cpp:9-836) for IMPLICIT_EXTENDED_SYSTEM_BPX, the way SMEM_Main runs it
 // (InitSolve, then the solver: src/SMEM_Main.cpp:724-729).  The handle must have been created with solver = 16 and plain
 // P / R = P^T.  Returns local_num_correct of thread 0 (the final loc_iters).

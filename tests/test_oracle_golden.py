@@ -662,3 +662,23 @@ def test_dmem_sync_add_matches_live_reference():
         x, rh = O.ref_dmem_sync_add(h, b, 0.8, symmetrised=sym, num_cycles=100, tol=1e-9)
         _close_hist(hist, rh)
         assert np.max(np.abs(u - x)) <= 1e-12 * np.max(np.abs(x))
+
+
+def test_l1_hybrid_jgs_parfor_smoother_matches_live_reference():
+    """L1_HYBRID_JACOBI_GAUSS_SEIDEL (smoother 12): reachable through the Parfor smoother only (BPX / ONE_LEVEL partition,
+    src/SMEM_Solve.cpp:324-334), where SMEM_Sync_Parfor_HybridJacobiGaussSeidel divides by hypre's l1 norms instead of a_ii / w
+    (src/SMEM_Smooth.cpp:253-263).  One thread = one Gauss-Seidel block per level; BPX is run unaccelerated for a few cycles
+    (it need not converge -- the histories must agree)."""
+    if O.ref_lib() is None:
+        pytest.skip("oracle/_ref not built here")
+    A = H.laplacian("7pt", 9)
+    h = H.amg_setup(A)
+    h.build_transfers(H.BPX, 1.0)
+    b = H.rand_rhs(A.nrows)
+    for sm in (H.L1_HYBRID_JACOBI_GAUSS_SEIDEL, H.HYBRID_JACOBI_GAUSS_SEIDEL):
+        rs = O.RefSolver(h, H.BPX, sm, b, 0.8, num_threads=1)
+        out = rs.solve(6, 1e-300, async_type=0)
+        rs.close()
+        _, hist, _ = O.Problem(h, H.BPX, sm, 0.8).solve_sync(b, 1e-300, 6)
+        assert len(hist) == 7 and np.all(np.isfinite(hist))
+        assert np.max(np.abs(hist - out["hist"]) / np.maximum(np.abs(out["hist"]), 1e-300)) <= 1e-12

@@ -346,3 +346,73 @@ def test_sell_uniform_encoding_matches_regular_sliced_ell(prob, n):
     assert_hist_close(h1, h2)
     su.close()
     sr.close()
+
+
+# ---- INTEGRATION.md's binding, compiled: integration/SMEM_B200.hpp built against the reference's own Main.hpp (oracle/build_ref.sh
+# ---- -> oracle/_ref/libref_b200.so) and driven by the reference-side structs: AllData filled as InitAlgebra does, InitSolve,
+# ---- SMEM_B200_Upload, SMEM_Solve_B200.  The library must land on the history of the reference's own object code.
+@pytest.mark.parametrize("name", ["lap5pt_n32", "lap7pt_n12"])
+def test_reference_structs_drive_the_library(name):
+    lib = O.ref_b200_lib()
+    if lib is None:
+        pytest.skip("oracle/_ref/libref_b200.so not built (needs /root/reference at build time)")
+    h, d = hierarchy_from_golden(name)
+    h.build_transfers(H.MULTADD, 0.9)
+    b = d["b"]
+    rs = O.RefSolver(h, H.MULTADD, H.JACOBI, b, 0.9, lib=lib)
+    want = rs.solve_sync_det(100, 1e-9)                     # the reference's object code, race-free loop
+    got = rs.solve_b200(100, 1e-9)                          # the same AllData through the binding
+    rs.close()
+    assert got["cycles"] == want["cycles"]
+    assert_hist_close(got["hist"], want["hist"])
+    assert np.max(np.abs(got["u"] - want["u"])) <= 1e-11 * np.max(np.abs(want["u"]))
+    assert list(got["corrections"]) == [got["cycles"]] * h.num_levels      # src/SMEM_Solve.cpp:246-248
+    # and the asynchronous solver through the same binding (AllData.input.solver = ASYNC_MULTADD)
+    ra = O.RefSolver(h, H.ASYNC_MULTADD, H.JACOBI, b, 0.9, lib=lib)
+    out = ra.solve_b200(150, 1e-9)
+    ra.close()
+    true = O.norm2(O.spgemv(h.A[0], out["u"], b, -1.0, 1.0)) / O.norm2(b)
+    assert true < 1e-9 and list(out["corrections"]) == [150] * h.num_levels
+
+
+def test_l1_hybrid_jgs_bpx_cycle_matches_oracle():
+    """L1_HYBRID_JACOBI_GAUSS_SEIDEL (smoother 12, Parfor smoother of BPX: hybrid JGS divided by the l1 norms,
+    src/SMEM_Smooth.cpp:253-263); the oracle's restatement is pinned by the reference's object code (tests/test_oracle_golden.py)"""
+    A = H.laplacian("7pt", 14)
+    h = H.amg_setup(A)
+    h.build_transfers(H.BPX, 1.0)
+    b = H.rand_rhs(A.nrows)
+    for rows in (8, 37):
+        blocks = [H.uniform_blocks(n, rows) for n in h.n]
+        want = O.Problem(h, H.BPX, H.L1_HYBRID_JACOBI_GAUSS_SEIDEL, 0.8, jgs_blocks=blocks).cycle(b)
+        s = amg.Solver(h, H.BPX, H.L1_HYBRID_JACOBI_GAUSS_SEIDEL, 0.8, jgs_block_rows=rows)
+        got = s.cycle(b)
+        s.close()
+        assert np.max(np.abs(got - want)) <= 1e-12 * np.max(np.abs(want))
+    h.build_transfers(H.MULTADD, 0.9)
+    with pytest.raises(amg.solver.AmgError):          # the ALL_LEVELS dispatcher never reaches this smoother (src/SMEM_Solve.cpp:277-323)
+        amg.Solver(h, H.MULTADD, H.L1_HYBRID_JACOBI_GAUSS_SEIDEL, 0.9)
+
+
+def test_async_eebpx_converges_to_the_synchronous_solution():
+    """`-solver async_eebpx` (EXPLICIT_EXTENDED_SYSTEM_BPX with async_flag = 1, src/SMEM_ExtendedSystem.cpp:295-365,636-652): chaotic
+    Chebyshev-Jacobi relaxations on the assembled extended system, one persistent cooperative kernel.  With ONE sweep allowed
+    (num_cycles = 2) every CTA performs exactly the first synchronous sweep's arithmetic on the start iterate only where no
+    other CTA has written yet, so the check is the limit: the chaotic iteration must reach the tolerance and land on the
+    solution of A x = f the synchronous form finds."""
+    g = dict(np.load(os.path.join(GOLDEN, "iebpx.npz")))
+    name = "lap7pt_n12"
+    h, d = hierarchy_from_golden(name)
+    h.build_transfers(H.BPX, 1.0)
+    b = d["b"]
+    s = amg.ExtendedExplicitSolver(h)
+    mu, delta = g["%s_explicit_nc300_mu_delta" % name]
+    sync = s.SMEM_ExtendedSystemSolve(b, 1e-9, 300, mu, delta)
+    out = s.SMEM_ExtendedSystemSolve_async(b, 1e-9, 3000, mu, delta)
+    s.close()
+    assert out["iters_min"] >= 2 and out["iters_max"] <= 3000
+    assert out["ext_relres"] < 1e-7, out           # the stop test reads stale per-CTA contributions: looser than the synchronous 1e-9
+    assert out["relres"] < 1e-7, out
+    assert np.max(np.abs(out["x"] - sync["x"])) <= 1e-6 * np.max(np.abs(sync["x"]))
+    print("async eebpx: sweeps per CTA %d..%d, ext relres %.2e, relres %.2e (sync: %d iterations)" %
+          (out["iters_min"], out["iters_max"], out["ext_relres"], out["relres"], sync["iters"]))
