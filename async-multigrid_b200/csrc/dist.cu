@@ -49,8 +49,12 @@ struct DistState {
    bool overlap = true;
    bool ready = false;
    // one cycle + residual + norm captured as a CUDA graph, NCCL operations and the communication stream's fork / join
-   // included, replayed per cycle (AMGB_DIST_GRAPH=0 falls back to per-operation launches)
-   bool use_graph = true;
+   // included, replayed per cycle.  Validated with a single-rank communicator only: with two ranks the replayed graph
+   // DEADLOCKS on the B200 box (round 2, profiles/r2_call4_2gpu.log: both 2-GPU tests and `bench.py --gpus 2` hung until
+   // their timeouts, while the per-operation path of the same build converged in 38 cycles) -- the captured ncclSend /
+   // ncclRecv pairs of the two ranks never meet.  So the graph is the default for ONE rank and off otherwise;
+   // AMGB_DIST_GRAPH=1 / 0 force it.
+   bool use_graph = false;
    cudaGraphExec_t graph_exec = nullptr;
    long long graph_kernels = 0, graph_halo_bytes = 0, graph_collectives = 0;
    // asynchronous fine-grid smoother across GPUs (DMEM_AsyncSmooth): the neighbours' level-0 solution vectors mapped
@@ -402,6 +406,7 @@ int amgb_dist_setup(amgb_ctx *c)
    CUDA_OK(c, cudaEventCreateWithFlags(&d->ev_x, cudaEventDisableTiming));
    CUDA_OK(c, cudaEventCreateWithFlags(&d->ev_h, cudaEventDisableTiming));
    if (const char *ov = getenv("AMGB_DIST_OVERLAP")) d->overlap = atoi(ov) != 0;
+   d->use_graph = d->nranks == 1;
    if (const char *gv = getenv("AMGB_DIST_GRAPH")) d->use_graph = atoi(gv) != 0;
    if ((rc = amgb_dev_alloc_bytes(c, (void **)&d->u, sizeof(double) * (size_t)d->lv[0].n_ext(), true))) return rc;
    if (c->opt.factor_level0) {

@@ -15,7 +15,7 @@ constexpr int kBlock = 256;
 // One kernel per storage scheme (separate register budgets): MODE 0 = vector-per-row CSR, 1 = sliced ELL,
 // 2 = sliced ELL with the SELL-U encoding (stencil levels); the CSR-stream kernel (row blocks through shared memory) is k_spmv_stream.
 template <int MODE, bool SVAL>
-__global__ void __launch_bounds__(kBlock, MODE == 2 ? 4 : (MODE == 3 ? 5 : 1)) k_spmv(DevCSR M, const double *x, double *y, SpmvEpilogue e, double *partials)
+__global__ void __launch_bounds__(kBlock, MODE == 2 ? 3 : (MODE == 3 ? 4 : 1)) k_spmv(DevCSR M, const double *x, double *y, SpmvEpilogue e, double *partials)
 {
    const int tid = blockIdx.x * kBlock + threadIdx.x;
    const int tsz = gridDim.x * kBlock;
@@ -284,7 +284,7 @@ int launch_spmv(const LaunchCfg &cfg, cudaStream_t st, const DevCSR &M, bool use
                 const SpmvEpilogue &e, double *partials, int *grid_out)
 {
    int grid;
-   if (M.sell_slices > 0 && M.su_desc && cfg.sellu_ctas == 5) grid = launch_spmv_mode<3>(cfg, st, M, use_sval, x, y, e, partials, ((long)M.sell_slices * 32 + kBlock - 1) / kBlock);
+   if (M.sell_slices > 0 && M.su_desc && cfg.sellu_ctas == 4) grid = launch_spmv_mode<3>(cfg, st, M, use_sval, x, y, e, partials, ((long)M.sell_slices * 32 + kBlock - 1) / kBlock);
    else if (M.sell_slices > 0 && M.su_desc) grid = launch_spmv_mode<2>(cfg, st, M, use_sval, x, y, e, partials, ((long)M.sell_slices * 32 + kBlock - 1) / kBlock);
    else if (M.sell_slices > 0) grid = launch_spmv_mode<1>(cfg, st, M, use_sval, x, y, e, partials, ((long)M.sell_slices * 32 + kBlock - 1) / kBlock);
    else if (M.nblk > 0 && M.wept > 0) {

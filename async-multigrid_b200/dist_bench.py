@@ -208,7 +208,7 @@ def _leg(args, rank, world, local, dims, tag, steps, warmup, sampler=None):
     clocks = sampler.stop() if (sampler is not None and rank == 0) else None
     out = {"solve_s": solve_s, "e2e_s": e2e_s, "cycles": len(hist) - 1, "final_relres": float(hist[-1]), "launches": int(launches),
            "halo_bytes": float(hbt.item()), "nccl_ops": int(ops), "info": plan.info, "num_dist": plan.num_dist, "clocks": clocks,
-           "upload_s": round(upload_s, 1), "graph": bool(int(os.environ.get("AMGB_DIST_GRAPH", "1")))}
+           "upload_s": round(upload_s, 1), "graph": bool(int(os.environ.get("AMGB_DIST_GRAPH", "1" if world == 1 else "0")))}
     s.close()
     dist.barrier()
     return out

@@ -330,7 +330,14 @@ def run_b200(args):
                 break
         line["async"] = res
         sa.close()
-    if not args.no_strong and sv == H.MULTADD and sm == H.JACOBI and args.problem == "7pt" and not args.cheby:
+    default_leg = sv == H.MULTADD and sm == H.JACOBI and args.problem == "7pt" and not args.cheby
+    extras = set(x for x in args.extras.split(",") if x) if default_leg else set()
+    if extras:
+        try:
+            line["configs"] = extra_configs(args, amg, H, h, b, extras)
+        except Exception as e:      # the headline line must survive a failure of an extra leg
+            line["configs"] = {"failed": "%s: %s" % (type(e).__name__, e)}
+    if not args.no_strong and default_leg:
         line["strong"] = strong_leg_single(args, amg, H, peak)
     if not args.no_cpu_baseline:
         if fact0:
@@ -404,6 +411,112 @@ def strong_leg_single(args, amg, H, peak):
         return rec
     except Exception as e:      # the headline line must survive a failure of this extra leg
         return {"failed": "%s: %s" % (type(e).__name__, e)}
+
+
+def _solve_record(s, f_host, is_async, max_cycles, cheby=None, steps=2):
+    """resident solve(s) of one extra configuration -> dict (value = device seconds of the best of `steps`)"""
+    s.set_rhs(f_host)
+    if is_async:
+        for nc in range(20, max_cycles + 1, 10):
+            out = s.SMEM_Solve(f_host, TOL, nc)
+            if not np.isfinite(out["relres"]) or out["relres"] > 1e6:
+                return {"diverged": True, "corrections_tried": nc, "relres": float(out["relres"])}
+            if out["relres"] < TOL:
+                best = min(s.SMEM_Solve(f_host, TOL, nc)["seconds"] for _ in range(steps))
+                return {"value": best, "unit": "s", "corrections_per_level": int(nc), "final_relres": float(out["relres"])}
+        return {"not_converged": True, "corrections_tried": max_cycles, "relres": float(out["relres"])}
+    best, hist = None, None
+    for _ in range(steps):
+        s.set_solution(None)
+        hist, secs = s.solve_sync(TOL, max_cycles, cheby=cheby)
+        best = secs if best is None else min(best, secs)
+    ok = bool(np.isfinite(hist[-1]) and hist[-1] < TOL)
+    rec = {"value": best, "unit": "s", "cycles": int(len(hist) - 1), "final_relres": float(hist[-1])}
+    if not ok:
+        rec["not_converged"] = True
+    return rec
+
+
+def extra_configs(args, amg, H, h, b, which):
+    """the other members of BASELINE.json `configs` at their stated sizes, as extra keys of the line (device seconds of the solve,
+    hierarchy resident; same stand-in hierarchy provider).  `which`: set of {c1, c2, c3, c4}."""
+    out = {}
+    w = args.smooth_weight
+    if "c1" in which:
+        # configs[0]: SMEM sync Multadd, 2-D 5-point 512 x 512, weighted Jacobi (L2-resident on a B200: not an HBM test)
+        t0 = time.time()
+        A = H.laplacian("5pt", 512)
+        h1 = H.amg_setup(A, theta=args.theta)
+        h1.build_transfers(H.MULTADD, w, factor_level0=True)
+        s = amg.Solver(h1, H.MULTADD, H.JACOBI, w, factor_level0=True)
+        rec = _solve_record(s, H.rand_rhs(A.nrows), False, args.max_cycles, steps=3)
+        s.close()
+        rec.update({"workload": "2D 5pt Laplacian 512^2 (n=%d), sync Multadd, smoother j w=%.2f" % (A.nrows, w), "levels": h1.num_levels,
+                    "host_setup_s": round(time.time() - t0, 1)})
+        out["c1_5pt_512"] = rec
+    if "c2" in which:
+        # configs[1]: async Multadd + AFACx, 7pt 256^3, hybrid JGS smoother.  Hybrid JGS with w = 1 diverges asynchronously in the
+        # reference's own object code too (DESIGN.md section 4); reported: async Multadd with hybrid JGS (pre 1 / post 0, w = 0.7),
+        # sync and async AFACx with weighted Jacobi
+        hh = H.Hierarchy(h.A, h.P_plain)
+        hh.cpts = h.cpts
+        hh.build_transfers(H.MULTADD, 0.7, num_pre=1, num_post=0)
+        s = amg.Solver(hh, H.ASYNC_MULTADD, H.HYBRID_JACOBI_GAUSS_SEIDEL, 0.7, num_pre=1, num_post=0, jgs_block_rows=args.jgs_block_rows)
+        rec = _solve_record(s, b, True, 150)
+        s.close()
+        rec["workload"] = "3D 7pt Laplacian %d^3, ASYNC Multadd, hybrid JGS (blocks of %d rows), w=0.70, pre 1 / post 0" % (args.n, args.jgs_block_rows)
+        out["c2_async_multadd_hybrid_jgs"] = rec
+        hh.build_transfers(H.AFACX, 0.5)
+        for tag, sv, asy in (("c2_afacx", H.AFACX, False), ("c2_async_afacx", H.ASYNC_AFACX, True)):
+            s = amg.Solver(hh, sv, H.JACOBI, 0.5)
+            rec = _solve_record(s, b, asy, 200 if asy else args.max_cycles)
+            s.close()
+            rec["workload"] = "3D 7pt Laplacian %d^3, %s AFACx, smoother j w=0.50" % (args.n, "ASYNC" if asy else "sync")
+            out[tag] = rec
+    if "c3" in which:
+        # configs[2]: 27-point 256^3, Chebyshev-accelerated Multadd, sync vs async (EigsPower on the device supplies mu, delta)
+        t0 = time.time()
+        A = H.laplacian("27pt", args.n)
+        h3 = H.amg_setup(A, theta=args.theta)
+        h3.build_transfers(H.MULTADD, w, factor_level0=True)
+        b3 = H.rand_rhs(A.nrows)
+        host_s = time.time() - t0
+        s = amg.Solver(h3, H.MULTADD, H.JACOBI, w, factor_level0=True, lean_storage=True)
+        plain = _solve_record(s, b3, False, args.max_cycles)
+        s.set_rhs(b3)
+        mu, delta, alpha, beta = s.ChebySetup(args.cheby_eig_max_iters)
+        acc = _solve_record(s, b3, False, args.max_cycles, cheby=(mu, delta))
+        acc["cheby"] = {"eig_min": alpha, "eig_max": beta, "mu": mu, "delta": delta, "power_iterations": args.cheby_eig_max_iters}
+        s.close()
+        sa = amg.Solver(h3, H.ASYNC_MULTADD, H.JACOBI, w, factor_level0=True, lean_storage=True)
+        asy = _solve_record(sa, b3, True, 150)
+        sa.close()
+        wl = "3D 27pt Laplacian %d^3 (n=%d, nnz=%d)" % (args.n, A.nrows, A.nnz)
+        out["c3_27pt"] = {"workload": wl, "levels": h3.num_levels, "host_setup_s": round(host_s, 1), "sync_multadd": plain,
+                          "sync_multadd_chebyshev": acc, "async_multadd": asy}
+    if "c4" in which:
+        # configs[3]: linear elasticity, 3 unknowns per node, ~8 M DOF, BPX (+ Chebyshev acceleration: plain BPX does not converge);
+        # MFEM is absent: Q1 hexahedra on an 8:1:1 two-material beam from the host assembler (DESIGN.md section 7)
+        t0 = time.time()
+        ex = args.elasticity_ex
+        A, rhs = H.elasticity_beam(ex)
+        h4 = H.amg_setup(A, theta=args.theta, num_functions=3)
+        h4.build_transfers(H.BPX, 0.8)
+        host_s = time.time() - t0
+        s = amg.Solver(h4, H.BPX, H.JACOBI, 0.8, lean_storage=True)
+        s.set_rhs(rhs)
+        mu, delta, alpha, beta = s.ChebySetup(args.elasticity_eig_iters)
+        beta *= 1.05
+        mu, delta = (beta + alpha) / (beta - alpha), 2.0 / (beta + alpha)
+        rec = _solve_record(s, rhs, False, args.elasticity_max_cycles, cheby=(mu, delta), steps=1)
+        ms = s.time_spmv(0, 0, False, 10)
+        s.close()
+        rec.update({"workload": "Q1 linear elasticity beam %dx%dx%d elements (n=%d DOF, nnz=%d), BPX + Chebyshev acceleration, smoother j w=0.80"
+                                % (ex, max(1, ex // 8), max(1, ex // 8), A.nrows, A.nnz), "levels": h4.num_levels,
+                    "host_setup_s": round(host_s, 1), "cheby": {"eig_min": alpha, "eig_max": beta, "mu": mu, "delta": delta},
+                    "A0_spmv_ms": ms, "A0_spmv_GBps": H.bytes_spmv(A, False) / (ms * 1e-3) / 1e9})
+        out["c4_elasticity_bpx"] = rec
+    return out
 
 
 def hist_check(args, h, hist):
@@ -565,6 +678,12 @@ def main():
     ap.add_argument("--read-type", type=int, default=0, help="asynchronous solver: 0 sol (default), 1 res (-read_type)")
     ap.add_argument("--min-rows-per-rank", type=int, default=16384,
                     help="multi-GPU: levels with fewer owned rows per rank are replicated, not partitioned")
+    ap.add_argument("--extras", default="c1,c2", help="other members of BASELINE.json `configs` reported as extra keys: c1 (5pt 512^2), "
+                    "c2 (async Multadd hybrid JGS + AFACx at 256^3), c3 (27pt 256^3, Chebyshev, sync vs async), c4 (elasticity ~8 M DOF, BPX); "
+                    "c3 and c4 add minutes of host set-up, so the default runs c1,c2 only")
+    ap.add_argument("--elasticity-ex", type=int, default=560, help="c4: elements along the beam (560 -> 561 x 71 x 71 nodes, 8.5 M DOF)")
+    ap.add_argument("--elasticity-eig-iters", type=int, default=300)
+    ap.add_argument("--elasticity-max-cycles", type=int, default=3000)
     ap.add_argument("--strong-n", type=int, default=512, help="grid of the strong-scaling record (BASELINE.json configs[4]: 512^3)")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling record (512^3 on --gpus N GPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

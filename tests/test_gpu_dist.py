@@ -106,6 +106,25 @@ def test_single_rank_afacx_and_l1_match_oracle(solver, smoother, w, post):
     s.close()
 
 
+_LIVE = []
+
+
+@pytest.fixture(autouse=True)
+def _reap_workers():
+    """whatever a multi-process test leaves running is killed when the test ends (pass or fail)"""
+    yield
+    _reap(_LIVE)
+    del _LIVE[:]
+
+
+def _reap(procs):
+    """a worker that hangs (e.g. a deadlocked collective) must not outlive its test: it would keep spinning on the GPUs"""
+    for p in procs:
+        if p.is_alive():
+            p.kill()
+            p.join(timeout=10)
+
+
 def _worker(rank, world, port, uid_q, res_q, solver=H.MULTADD, w=0.9):
     sys.path.insert(0, ROOT)
     import async_multigrid_b200 as amg2
@@ -143,10 +162,13 @@ def test_two_gpus_match_global_oracle(solver, w):
     procs = [ctx.Process(target=_worker, args=(r, 2, 0, uid_q, res_q, solver, w)) for r in range(2)]
     for p in procs:
         p.start()
-    res = sorted([res_q.get(timeout=300) for _ in range(2)], key=lambda x: x[0])
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    try:
+        res = sorted([res_q.get(timeout=120) for _ in range(2)], key=lambda x: x[0])
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+    finally:
+        _reap(procs)
     A = H.laplacian("7pt", 32)
     h = H.amg_setup(A)
     h.build_transfers(solver, w)
@@ -221,17 +243,18 @@ def test_async_dist_two_gpus_converge():
     q_in = [ctx.Queue() for _ in range(world)]
     q_out, q_res = ctx.Queue(), ctx.Queue()
     procs = [ctx.Process(target=_async_worker, args=(r, world, q_in[r], q_out, q_res)) for r in range(world)]
+    _LIVE.extend(procs)
     for p in procs:
         p.start()
-    handles = dict(q_out.get(timeout=300) for _ in range(world))
+    handles = dict(q_out.get(timeout=150) for _ in range(world))
     for r in range(world):
         q_in[r].put([handles[o] for o in range(world) if o != r])
     for phase, reply in (("ready", "go"), ("done", "all done")):
-        got = [q_out.get(timeout=300) for _ in range(world)]
+        got = [q_out.get(timeout=150) for _ in range(world)]
         assert all(g[1] == phase for g in got)
         for r in range(world):
             q_in[r].put(reply)
-    res = sorted([q_res.get(timeout=300) for _ in range(world)], key=lambda x: x[0])
+    res = sorted([q_res.get(timeout=150) for _ in range(world)], key=lambda x: x[0])
     for r in range(world):
         q_in[r].put("close")
     for p in procs:
@@ -315,24 +338,25 @@ def test_async_smooth_two_gpus():
     q_in = [ctx.Queue() for _ in range(world)]
     q_out, q_res = ctx.Queue(), ctx.Queue()
     procs = [ctx.Process(target=_async_smooth_worker, args=(r, world, q_in[r], q_out, q_res)) for r in range(world)]
+    _LIVE.extend(procs)
     for p in procs:
         p.start()
-    _, tag, uid = q_out.get(timeout=300)
+    _, tag, uid = q_out.get(timeout=150)
     assert tag == "uid"
     for r in range(world):
         q_in[r].put(uid)
     handles = {}
     for _ in range(world):
-        r, tag, hd = q_out.get(timeout=300)
+        r, tag, hd = q_out.get(timeout=150)
         assert tag == "handle"
         handles[r] = hd
     for r in range(world):
         q_in[r].put(handles)
-    got = [q_out.get(timeout=300) for _ in range(world)]
+    got = [q_out.get(timeout=150) for _ in range(world)]
     assert all(g[1] == "done" for g in got)
     for r in range(world):
         q_in[r].put("all done")
-    res = sorted([q_res.get(timeout=300) for _ in range(world)], key=lambda x: x[0])
+    res = sorted([q_res.get(timeout=150) for _ in range(world)], key=lambda x: x[0])
     for r in range(world):
         q_in[r].put("close")
     for p in procs:
