@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#include <omp.h>
 #ifdef AMG_HAVE_NCCL
 #include <nccl.h>
 #endif
@@ -56,6 +57,7 @@ struct DistState {
    // AMGB_DIST_GRAPH=1 / 0 force it.
    bool use_graph = false;
    cudaGraphExec_t graph_exec = nullptr;
+   bool graph_warm = false;              // one cycle has run with per-operation launches (NCCL's lazy connections exist)
    long long graph_kernels = 0, graph_halo_bytes = 0, graph_collectives = 0;
    // asynchronous fine-grid smoother across GPUs (DMEM_AsyncSmooth): the neighbours' level-0 solution vectors mapped
    // through CUDA IPC, and where in them this rank's boundary entries belong (their ghost slots)
@@ -476,7 +478,10 @@ int amgb_dist_solve_sync_accel(amgb_ctx *c, double tol, int max_cycles, int acce
    const double r0 = sqrt(ss);
    if (hist) hist[0] = 1.0;
    int done = 0;
-   if (d->use_graph && !accel && !d->graph_exec) {
+   // (the graph is captured only after ONE cycle has run with per-operation launches -- d->graph_warm: NCCL connects
+   //  peers and algorithms lazily at first use (NCCL_RUNTIME_CONNECT), and the first all-gather of a solve would otherwise
+   //  meet that set-up INSIDE the capture, where its host-side exchange and CUDA calls cannot run)
+   if (d->use_graph && !accel && !d->graph_exec && d->graph_warm) {
       // capture u += B r; r = f - A u; ||r||^2 all-reduced; 8-byte D2H.  The halo exchanges run on the communication stream,
       // which joins the capture through the events dist_spmv records and is joined back before every boundary launch.
       cudaGraph_t g;
@@ -497,7 +502,16 @@ int amgb_dist_solve_sync_accel(amgb_ctx *c, double tol, int max_cycles, int acce
    for (int k = 1; k <= max_cycles; k++) {
       if (d->graph_exec && !accel) {
          CUDA_OK(c, cudaGraphLaunch(d->graph_exec, c->stream));
-         CUDA_OK(c, cudaStreamSynchronize(c->stream));
+         {
+            // a replay that never completes (collectives of two ranks that do not meet) must fail, not hang the job
+            const double t_start = omp_get_wtime();
+            cudaError_t q;
+            while ((q = cudaStreamQuery(c->stream)) == cudaErrorNotReady)
+               if (omp_get_wtime() - t_start > 60.0)
+                  return amgb_fail(c, AMGB_ENCCL, "replay of the captured partitioned cycle did not complete within 60 s (cycle %d): "
+                                                  "set AMGB_DIST_GRAPH=0", k);
+            CUDA_OK(c, q);
+         }
          c->launches += d->graph_kernels; d->halo_bytes += d->graph_halo_bytes; d->collectives += d->graph_collectives;
          ss = c->h_scalars[0];
          done = k;
@@ -530,6 +544,23 @@ int amgb_dist_solve_sync_accel(amgb_ctx *c, double tol, int max_cycles, int acce
       const double rel = sqrt(ss) / r0;
       if (hist) hist[k] = rel;
       if (rel < tol) break;
+      if (d->use_graph && !accel && !d->graph_exec) {
+         // every NCCL operation of a cycle has now run once outside a capture: capture the cycle for the remaining iterations
+         d->graph_warm = true;
+         cudaGraph_t g;
+         const long long l0 = c->launches, h0 = d->halo_bytes, c0 = d->collectives;
+         CUDA_OK(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+         rc = dist_cycle(c, uo, true);
+         if (!rc) rc = dist_residual(c);
+         cudaMemcpyAsync(c->h_scalars, c->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+         cudaError_t ce = cudaStreamEndCapture(c->stream, &g);
+         if (rc) return rc;
+         if (ce != cudaSuccess) return amgb_fail(c, AMGB_ECUDA, "graph capture of the partitioned cycle failed: %s", cudaGetErrorString(ce));
+         d->graph_kernels = c->launches - l0; d->graph_halo_bytes = d->halo_bytes - h0; d->graph_collectives = d->collectives - c0;
+         c->launches = l0; d->halo_bytes = h0; d->collectives = c0;
+         CUDA_OK(c, cudaGraphInstantiate(&d->graph_exec, g, 0));
+         cudaGraphDestroy(g);
+      }
    }
    CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));
    CUDA_OK(c, cudaEventSynchronize(c->ev1));
