@@ -128,6 +128,36 @@ def test_partition_layout_properties():
                     assert plan.A[l].nrows == h.n[l]
 
 
+@pytest.mark.parametrize("world,n", [(4, 8), (8, 8)])
+def test_bench_plan_of_the_weak_series_is_consistent(tmp_path, world, n):
+    """the grids of bench.py's weak series (dist_bench.weak_dims: the cube doubled direction by direction, so ny != nx at 4 ranks
+    and the 512^3-shaped cube at 8) cut into z-slabs: every level's rows are dealt completely, a rank's ghosts are exactly what its
+    neighbours send, and every column of its row blocks lies inside its extended index space"""
+    sys.path.insert(0, ROOT)
+    import async_multigrid_b200 as amg  # noqa: F401
+    from async_multigrid_b200 import hierarchy as H, partition as PT, dist_bench as DB
+    from oracle import oracle as O
+    dims = DB.weak_dims(n, world)
+    assert dims[0] * dims[1] * dims[2] == world * n ** 3
+    A = H.laplacian("7pt", *dims)
+    h = H.amg_setup(A)
+    h.build_transfers(H.MULTADD, 0.9, factor_level0=True)      # what the bench uploads
+    starts, num_dist, halos = PT.plan_layouts(h, world, plane=dims[0] * dims[1], min_rows_per_rank=16)
+    lays = [PT.rank_layouts(h, world, r, starts, num_dist, halos) for r in range(world)]
+    assert num_dist >= 1
+    for l in range(h.num_levels):
+        assert sum(lays[r][l].n_owned for r in range(world)) == h.n[l]
+        for r in range(world):
+            lay = lays[r][l]
+            if lay.distributed:
+                # a rank's ghosts are exactly what its neighbours send
+                assert lay.halo_lo == (lays[r - 1][l].send_hi if r > 0 else 0)
+                assert lay.halo_hi == (lays[r + 1][l].send_lo if r < world - 1 else 0)
+                # and every column of its row block lies inside [ghost_lo | owned | ghost_hi]
+                blk = PT._block(h.A[l], lay.row_start, lay.row_start + lay.n_owned, lay.base, lay.n_ext)
+                assert blk.indices.min() >= 0 and blk.indices.max() < lay.n_ext
+
+
 def test_bench_plan_roundtrip_through_disk(tmp_path):
     """bench.py's multi-GPU leg hands the per-rank blocks over through files: what a rank loads must be what
     RankPlan builds in memory"""
