@@ -47,27 +47,19 @@ __device__ __forceinline__ double csr_rows_team(const DevCSR &M, const double *_
    return sumsq;
 }
 
-// SELL-U fast path: N groups whose deltas / values sit in registers, all lanes active -- N gathers in flight, N FMAs
-template <bool RO, int N, int CAP>
-__device__ __forceinline__ double sellu_fast(const double *__restrict__ xr, const int (&cd)[CAP], const double (&cv)[CAP])
-{
-   double xv[N];
-#pragma unroll
-   for (int k = 0; k < N; k++) xv[k] = ld_x<RO>(xr + cd[k]);
-   double acc = 0.0;
-#pragma unroll
-   for (int k = 0; k < N; k++) acc += cv[k] * xv[k];
-   return acc;
-}
-
 // ---- sliced ELL (C = 32): one thread per row, one warp per slice, coalesced col/val streams -----
-// SU == 0: the regular encoding only (the Galerkin / transfer operators: this is the round-1 kernel, unchanged).
+// SU == 0: the regular encoding only (the Galerkin / transfer operators: round 1's kernel).
 // SU  > 0: the matrix carries the SELL-U encoding (DevCSR::su_desc): a slice is a short list of (delta, mask, value) groups
-//          shared by its 32 rows, read SU groups at a time -- all group records first (warp-uniform addresses, and the
-//          lists of a stencil are a few dozen distinct ones, so these are L1 hits), then all x gathers, then the FMAs --
-//          so that one slice costs ONE trip to memory (gathers and the epilogue operands in flight together) instead of
-//          one per dependent load.  The descriptor of the warp's NEXT slice is fetched a slice ahead.
-template <bool RO, bool SVAL, int SU = 0>
+//          shared by its 32 rows, read SU groups at a time -- the group records (warp-uniform addresses; the lists of a
+//          stencil are a few dozen distinct ones, so these are L1 hits), then all x gathers of the batch in flight, then the
+//          FMAs.  The descriptor of the warp's NEXT slice is fetched a slice ahead.
+// FAST (stand-alone kernels): the warp keeps the DELTAS of the list it met last in registers; consecutive slices of a stencil
+//          share one list, so the common slice -- every lane mask full, at most 8 groups -- costs per group one address, one
+//          gather, one L1-resident value load and one FMA.  What round 2's measurements say about this kernel family
+//          (profiles/README.md R2.3): it is bound by instruction issue and by the number of resident warps, not by HBM --
+//          a variant with every value and the epilogue operands held in registers (80 registers, 3 CTAs/SM) was SLOWER
+//          (0.226 ms against 0.19) than the generic loop at 56 registers; so this path is written for <= 40 registers.
+template <bool RO, bool SVAL, int SU = 0, bool FAST = false>
 __device__ __forceinline__ double sell_rows_team(const DevCSR &M, const double *__restrict__ x,
                                                  double *y, const SpmvEpilogue &e,
                                                  int team_tid, int team_size, bool want_sumsq)
@@ -79,57 +71,43 @@ __device__ __forceinline__ double sell_rows_team(const DevCSR &M, const double *
    int sl = team_tid >> 5;
    int2 dsc = make_int2(0, 0);
    if (SU > 0 && sl < M.sell_slices) dsc = __ldg(M.su_desc + sl);
-   // SU == 8 (stand-alone kernel): the warp keeps the deltas of the group list it met last in registers.  Consecutive slices
-   // of a stencil share one list (the deduplicated table has a few dozen), so the common slice -- all lane masks full -- costs
-   // per group one address, one gather, one (L1-resident) value load and one FMA: ~70 instructions per 32 rows instead of
-   // ~200 for the generic path below, which ncu showed to be issue-bound (profiles/r2_ncu_full_cycle_sellu.csv: 62 % issue
-   // slots busy at 25 % DRAM throughput).
    int cfirst = -1, ccount = 0;
    bool cfull = false;
-   int cd[SU == 8 ? 8 : 1];
-   double cv[SU == 8 ? 8 : 1];
+   int cd[FAST ? 8 : 1];
    for (; sl < M.sell_slices; sl += nwarp) {
       int row = ((sl + M.sell_base) << 5) + lane;
       if (SU == 0 && M.sell_perm) row = __ldg(M.sell_perm + row);
       double acc = 0.0;
       int2 dnext = make_int2(0, 0);
       if (SU > 0 && sl + nwarp < M.sell_slices) dnext = __ldg(M.su_desc + sl + nwarp);
-      if (SU == 8 && dsc.y > 0 && (dsc.x != cfirst || dsc.y != ccount)) {
+      if (FAST && dsc.y > 0 && (dsc.x != cfirst || dsc.y != ccount)) {
          cfirst = dsc.x; ccount = dsc.y;
          unsigned int all = 0xffffffffu;
          if (ccount <= 8) {
-            const double *__restrict__ gv = (SVAL ? M.su_sval : M.su_va) + cfirst;
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                const int2 dm = k < ccount ? __ldg(M.su_dm + cfirst + k) : make_int2(0, -1);
                cd[k] = dm.x;
-               cv[k] = k < ccount ? __ldg(gv + k) : 0.0;
                all &= static_cast<unsigned int>(dm.y);
             }
          } else all = 0u;
          cfull = all == 0xffffffffu;          // every lane takes part in every group (all 32 rows of the slice exist, then)
       }
-      if (SU == 8 && dsc.y > 0 && cfull) {
-         const EpiOps ops = epilogue_load<RO>(e, row);
+      if (FAST && dsc.y > 0 && cfull) {
+         const double *__restrict__ gv = (SVAL ? M.su_sval : M.su_va) + cfirst;
          const double *__restrict__ xr = x + row;
-         if (ccount == 7) acc = sellu_fast<RO, 7, (SU == 8 ? 8 : 1)>(xr, cd, cv);          // 7-point stencils
-         else if (ccount == 5) acc = sellu_fast<RO, 5, (SU == 8 ? 8 : 1)>(xr, cd, cv);     // 5-point
-         else {
-            double xv[8];
+         double xv[8];
 #pragma unroll
-            for (int k = 0; k < 8; k++) xv[k] = k < ccount ? ld_x<RO>(xr + cd[k]) : 0.0;
+         for (int k = 0; k < 8; k++) xv[k] = k < ccount ? ld_x<RO>(xr + cd[k]) : 0.0;
 #pragma unroll
-            for (int k = 0; k < 8; k++) acc += cv[k] * xv[k];
-         }
-         const double v = epilogue_finish(e, ops, acc);
+         for (int k = 0; k < 8; k++)
+            if (k < ccount) acc += __ldg(gv + k) * xv[k];
+         const double v = epilogue_apply<RO>(e, row, acc);
          epilogue_store<RO>(e, y, row, v);
          if (want_sumsq) sumsq += v * v;
       } else if (SU > 0 && dsc.y > 0) {
          const double *__restrict__ gv = SVAL ? M.su_sval : M.su_va;
          const bool ok = row < M.nrows;
-         EpiOps ops;
-         ops.b = 0.0; ops.c = 0.0; ops.rs = 1.0;
-         if (RO && ok) ops = epilogue_load<RO>(e, row);       // in flight together with the gathers (the persistent kernel has no registers to spare for it)
          for (int g = 0; g < dsc.y; g += (SU > 0 ? SU : 1)) {
             double xv[SU > 0 ? SU : 1];
             const int2 *__restrict__ dmp = M.su_dm + dsc.x + g;
@@ -146,7 +124,7 @@ __device__ __forceinline__ double sell_rows_team(const DevCSR &M, const double *
                if (k < left) acc += __ldg(gv + dsc.x + g + k) * xv[k];
          }
          if (ok) {
-            const double v = RO ? epilogue_finish(e, ops, acc) : epilogue_apply<RO>(e, row, acc);
+            const double v = epilogue_apply<RO>(e, row, acc);
             epilogue_store<RO>(e, y, row, v);
             if (want_sumsq) sumsq += v * v;
          }

@@ -9,7 +9,7 @@ struct LaunchCfg {
    int num_sms = 148;
    int ctas_per_sm = 8;
    int stream_variant = 0;
-   int sellu_ctas = 3;          // resident CTAs per SM of the SELL-U kernel: 3 (up to 85 registers) or 4 (64, AMGB_SELLU_CTAS=4)
+   int sellu_ctas = 5;          // resident CTAs per SM of the SELL-U kernel: 5 (48 registers, default), 4 (64) or 6 (40, spills) -- AMGB_SELLU_CTAS
 };
 
 // geometry of the CSR-stream kernel (kernels.cuh stream_rows_team): threads per CTA, entries per row block,
