@@ -119,7 +119,7 @@ int amgb_create(amgb_ctx **out, int device)
    cudaGetDeviceProperties(&prop, device);
    c->cfg.num_sms = prop.multiProcessorCount;
    c->cfg.ctas_per_sm = 8;
-   if (const char *sc = getenv("AMGB_SELLU_CTAS")) c->cfg.sellu_ctas = (atoi(sc) == 4 || atoi(sc) == 6) ? atoi(sc) : 5;
+   if (const char *sc = getenv("AMGB_SELLU_CTAS")) c->cfg.sellu_ctas = (atoi(sc) == 4 || atoi(sc) == 6 || atoi(sc) == 8) ? atoi(sc) : 5;      // 8: the generic batch-of-8 loop
    c->host_threads = std::max(1, std::min(16, omp_get_num_procs()));
    c->l2_bytes = prop.l2CacheSize;
    c->max_window = prop.accessPolicyMaxWindowSize;

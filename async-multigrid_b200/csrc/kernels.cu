@@ -15,13 +15,14 @@ constexpr int kBlock = 256;
 // One kernel per storage scheme (separate register budgets): MODE 0 = vector-per-row CSR, 1 = sliced ELL,
 // 2 (3, 4: other register budgets) = sliced ELL with the SELL-U encoding (stencil levels); the CSR-stream kernel (row blocks through shared memory) is k_spmv_stream.
 template <int MODE, bool SVAL>
-__global__ void __launch_bounds__(kBlock, MODE == 2 ? 5 : (MODE == 3 ? 4 : (MODE == 4 ? 6 : 1))) k_spmv(DevCSR M, const double *x, double *y, SpmvEpilogue e, double *partials)
+__global__ void __launch_bounds__(kBlock, MODE == 2 ? 5 : (MODE == 3 ? 4 : (MODE == 4 ? 6 : (MODE == 5 ? 4 : 1)))) k_spmv(DevCSR M, const double *x, double *y, SpmvEpilogue e, double *partials)
 {
    const int tid = blockIdx.x * kBlock + threadIdx.x;
    const int tsz = gridDim.x * kBlock;
    const bool norm = partials != nullptr;
    double ss;
-   if (MODE >= 2) ss = sell_rows_team<true, SVAL, 4, true>(M, x, y, e, tid, tsz, norm);   // (2 / 3 / 4: the same code at 5 / 4 / 6 CTAs per SM)
+   if (MODE == 5) ss = sell_rows_team<true, SVAL, 8, false>(M, x, y, e, tid, tsz, norm);  // the generic batch-of-8 loop ("v2", 56 registers)
+   else if (MODE >= 2) ss = sell_rows_team<true, SVAL, 4, true>(M, x, y, e, tid, tsz, norm);   // (2 / 3 / 4: the cached-delta path at 5 / 4 / 6 CTAs per SM)
    else if (MODE == 1) ss = sell_rows_team<true, SVAL>(M, x, y, e, tid, tsz, norm);
    else ss = csr_rows_dispatch<true, SVAL>(M, x, y, e, tid, tsz, norm);
    if (norm) {
@@ -286,6 +287,7 @@ int launch_spmv(const LaunchCfg &cfg, cudaStream_t st, const DevCSR &M, bool use
    int grid;
    if (M.sell_slices > 0 && M.su_desc && cfg.sellu_ctas == 4) grid = launch_spmv_mode<3>(cfg, st, M, use_sval, x, y, e, partials, ((long)M.sell_slices * 32 + kBlock - 1) / kBlock);
    else if (M.sell_slices > 0 && M.su_desc && cfg.sellu_ctas == 6) grid = launch_spmv_mode<4>(cfg, st, M, use_sval, x, y, e, partials, ((long)M.sell_slices * 32 + kBlock - 1) / kBlock);
+   else if (M.sell_slices > 0 && M.su_desc && cfg.sellu_ctas == 8) grid = launch_spmv_mode<5>(cfg, st, M, use_sval, x, y, e, partials, ((long)M.sell_slices * 32 + kBlock - 1) / kBlock);
    else if (M.sell_slices > 0 && M.su_desc) grid = launch_spmv_mode<2>(cfg, st, M, use_sval, x, y, e, partials, ((long)M.sell_slices * 32 + kBlock - 1) / kBlock);
    else if (M.sell_slices > 0) grid = launch_spmv_mode<1>(cfg, st, M, use_sval, x, y, e, partials, ((long)M.sell_slices * 32 + kBlock - 1) / kBlock);
    else if (M.nblk > 0 && M.wept > 0) {

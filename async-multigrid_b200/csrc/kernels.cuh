@@ -108,6 +108,10 @@ __device__ __forceinline__ double sell_rows_team(const DevCSR &M, const double *
       } else if (SU > 0 && dsc.y > 0) {
          const double *__restrict__ gv = SVAL ? M.su_sval : M.su_va;
          const bool ok = row < M.nrows;
+         constexpr bool PRELOAD = RO && !FAST;        // (the variant measured as "v2": epilogue operands in flight with the gathers)
+         EpiOps ops;
+         ops.b = 0.0; ops.c = 0.0; ops.rs = 1.0;
+         if (PRELOAD && ok) ops = epilogue_load<RO>(e, row);
          for (int g = 0; g < dsc.y; g += (SU > 0 ? SU : 1)) {
             double xv[SU > 0 ? SU : 1];
             const int2 *__restrict__ dmp = M.su_dm + dsc.x + g;
@@ -124,7 +128,7 @@ __device__ __forceinline__ double sell_rows_team(const DevCSR &M, const double *
                if (k < left) acc += __ldg(gv + dsc.x + g + k) * xv[k];
          }
          if (ok) {
-            const double v = epilogue_apply<RO>(e, row, acc);
+            const double v = PRELOAD ? epilogue_finish(e, ops, acc) : epilogue_apply<RO>(e, row, acc);
             epilogue_store<RO>(e, y, row, v);
             if (want_sumsq) sumsq += v * v;
          }

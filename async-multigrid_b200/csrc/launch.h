@@ -9,7 +9,8 @@ struct LaunchCfg {
    int num_sms = 148;
    int ctas_per_sm = 8;
    int stream_variant = 0;
-   int sellu_ctas = 5;          // resident CTAs per SM of the SELL-U kernel: 5 (48 registers, default), 4 (64) or 6 (40, spills) -- AMGB_SELLU_CTAS
+   int sellu_ctas = 5;          // SELL-U kernel variant (AMGB_SELLU_CTAS): cached-delta path at 5 (48 registers, default), 4 (64) or 6 (40, spills)
+                                // CTAs per SM; 8 = the generic batch-of-8 loop at 4 CTAs per SM (56 registers)
 };
 
 // geometry of the CSR-stream kernel (kernels.cuh stream_rows_team): threads per CTA, entries per row block,

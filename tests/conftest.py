@@ -14,16 +14,34 @@ from async_multigrid_b200 import hierarchy as H  # noqa: E402
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+_CUDA_BUILD_ERROR = None
+
+
 def pytest_configure(config):
+    global _CUDA_BUILD_ERROR
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
     from oracle import build as obuild
     amg.build.build_host()
-    amg.build.build_cuda()
+    try:
+        amg.build.build_cuda()
+    except Exception as e:      # no nvcc on this box: the CPU-only suites (oracle, host set-up, matrix I/O) must still run
+        _CUDA_BUILD_ERROR = e
     obuild.build_oracle()
     try:
         obuild.build_ref()
     except Exception:
         pass
+
+
+def pytest_collection_modifyitems(config, items):
+    """without the built CUDA library the GPU-marked tests cannot run (there is no CPU fallback): skip them loudly, and
+    skip the tests that only need the library to LOAD (C-ABI symbols, host-only probes) as well"""
+    if _CUDA_BUILD_ERROR is None and os.path.exists(amg.build.CUDA_LIB):
+        return
+    why = pytest.mark.skip(reason="libamg_b200.so could not be built here: %s" % (_CUDA_BUILD_ERROR,))
+    for it in items:
+        if "gpu" in it.keywords or it.fspath.basename in ("test_abi.py", "test_sellu_host.py", "test_async_program.py"):
+            it.add_marker(why)
 
 
 def hierarchy_from_golden(name):
