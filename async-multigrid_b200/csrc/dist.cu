@@ -577,6 +577,63 @@ int amgb_dist_solve_sync_accel(amgb_ctx *c, double tol, int max_cycles, int acce
 #endif
 }
 
+// ---- DMEM_PowerMult (src/DMEM_Eig.cpp:10-104): extreme eigenvalues of B*A by power iteration on the partitioned path ----
+// Same iteration as EigsPower: normalise, f = A u, u = B f from a zero guess; eig_max = <v, BAv> after `iters` steps; a second pass
+// deflated with u <- BAv - eig_max v gives eig_min; DMEM's ChebySetup then takes alpha = eig_min, beta = eig_max
+// (src/DMEM_Setup.cpp:1901-1914).  B = the partitioned additive cycle of this context (the reference applies hypre's own
+// BoomerAMGSolve there whatever -solver says -- un-vendored; for the additive solvers the bounds that matter are those of the
+// cycle being accelerated).  u0_owned: this rank's rows of the start vector (the reference draws RandDouble(0,1) - .5 after
+// srand(rank)); NULL = all ones (EigsPower's start vector).  Inner products are all-reduced: every rank gets the same bounds.
+int amgb_dist_eigs_power(amgb_ctx *c, int iters, const double *u0_owned, double *eig_min, double *eig_max)
+{
+   NEED_READY(c);
+#ifdef AMG_HAVE_NCCL
+   DistState *d = c->dist;
+   if (!d || !d->ready) return amgb_fail(c, AMGB_ESTATE, "amgb_dist_setup not called");
+   if (iters < 1 || !eig_min || !eig_max) return amgb_fail(c, AMGB_EINVAL, "bad arguments");
+   int rc;
+   const int nown = c->A[0].nrows, off0 = d->lv[0].off();
+   if (!d->ecyc) {
+      if ((rc = amgb_dev_alloc_bytes(c, (void **)&d->ecyc, sizeof(double) * (size_t)std::max(1, nown), true))) return rc;
+      if ((rc = amgb_dev_alloc_bytes(c, (void **)&d->dacc, sizeof(double) * (size_t)std::max(1, nown), true))) return rc;
+   }
+   double *uo = d->u + off0, *y = d->ecyc;
+   auto global_dot = [&](const double *a, const double *b, double *out) -> int {
+      int grid = 0;
+      c->launches += launch_dot(c->cfg, c->stream, nown, a, b, c->partials, &grid);
+      c->launches += launch_reduce_partials(c->stream, c->partials, grid, c->d_scalars);
+      NCCL_OK(c, ncclAllReduce(c->d_scalars, c->d_scalars, 1, ncclDouble, ncclSum, d->comm, c->stream));
+      d->collectives++;
+      return amgb_fetch_scalar(c, out);
+   };
+   std::vector<double> ones;
+   if (!u0_owned) { ones.assign((size_t)std::max(1, nown), 1.0); u0_owned = ones.data(); }
+   double lam[2] = {0.0, 0.0};
+   for (int pass = 0; pass < 2; pass++) {
+      CUDA_OK(c, cudaMemsetAsync(d->u, 0, sizeof(double) * (size_t)d->lv[0].n_ext(), c->stream));
+      CUDA_OK(c, cudaMemcpyAsync(uo, u0_owned, sizeof(double) * (size_t)nown, cudaMemcpyHostToDevice, c->stream));
+      CUDA_OK(c, cudaStreamSynchronize(c->stream));
+      for (int it = 1;; it++) {
+         double ss;
+         if ((rc = global_dot(uo, uo, &ss))) return rc;
+         c->launches += launch_axpby(c->cfg, c->stream, nown, 1.0 / sqrt(ss), uo, 0.0, uo, y);                      // u /= |u|; y = u
+         if ((rc = dist_spmv(c, c->A[0], false, 0, d->u, d->r[0] + off0, epi(1.0, 0.0, nullptr), false))) return rc;   // f = A u
+         if ((rc = dist_cycle(c, uo, false))) return rc;                                                               // u = B f
+         if (it == iters) break;
+         if (pass == 1) c->launches += launch_axpby(c->cfg, c->stream, nown, -lam[0], y, 1.0, uo, nullptr);
+      }
+      if ((rc = global_dot(y, uo, &lam[pass]))) return rc;
+   }
+   *eig_max = lam[0];
+   *eig_min = lam[1];
+   CUDA_OK(c, cudaGetLastError());
+   return AMGB_OK;
+#else
+   (void)iters; (void)u0_owned; (void)eig_min; (void)eig_max;
+   return amgb_fail(c, AMGB_ENCCL, "library built without NCCL");
+#endif
+}
+
 // ---- asynchronous fine-grid smoother across GPUs --------------------------------------------------------------------
 // DMEM_AsyncSmooth (src/DMEM_Smooth.cpp:16-313; solver option of DMEM_Add, src/DMEM_Add.cpp:88-95) with the ASYNC_JACOBI /
 // ASYNC_L1_JACOBI smoothers: every rank relaxes its rows of the fine system over and over, u = r ./ s, x += u, and ships

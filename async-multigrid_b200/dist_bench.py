@@ -1,9 +1,9 @@
 """bench.py's multi-GPU leg: the row-partitioned synchronous Multadd solve (DMEM_Add replacement,
 csrc/dist.cu) on N GPUs of one box, one process per GPU (torchrun), NCCL for the data path.
 
-Workload (BASELINE.json configs[4] family): weak-scaling series with n^3 rows per GPU (grid doubled direction by direction:
-n^3, n x n x 2n, n x 2n x 2n, 2n x 2n x 2n -- N = 8, n = 256 is the 512^3 problem), cut into N z-slabs; and, beside it,
-the STRONG-scaling record of configs[4]: the fixed 512^3 problem on N GPUs, E(P) = t(1) / (P t(P)).
+Workload (BASELINE.json configs[4] family): weak-scaling series with n^3 rows per GPU (n x n x nN grid, one z-slab of n planes
+per GPU; N = 8, n = 256 has the size of the 512^3 problem: 134 M rows); and, beside it, the STRONG-scaling record of
+configs[4]: the fixed 512^3 problem on N GPUs, E(P) = t(1) / (P t(P)).
 Rank 0 builds the global hierarchy on the host (as DMEM_Setup's hypre does on all ranks), cuts it into
 per-rank row blocks and hands them over through /dev/shm; the timed region is the solve only.
 """
@@ -72,16 +72,10 @@ def _fact0(args):
 
 
 def weak_dims(n, world):
-    """grid of the weak-scaling series, n^3 rows per GPU: the cube is doubled one direction after the other, z first
-    (1: n^3, 2: n x n x 2n, 4: n x 2n x 2n, 8: 2n x 2n x 2n = the 512^3 problem for n = 256, then z again)"""
-    d = [n, n, n]
-    k, axis = world, 2
-    while k > 1 and k % 2 == 0:
-        d[axis] *= 2
-        axis = (axis - 1) % 3
-        k //= 2
-    d[2] *= k                      # odd remainder: more z-planes
-    return tuple(d)
+    """grid of the weak-scaling series, n^3 rows per GPU: n x n x (n * world), one z-slab of n planes per GPU (round 1's series,
+    so the rounds stay comparable; the slab shape -- and with it the halo size and the cycle count, 36 -> 38 -- stays put as N
+    grows, which the cube-doubling alternative does not: 512^3 needs 43 cycles)"""
+    return (n, n, n * world)
 
 
 def _build_and_scatter(args, world, d, dims):

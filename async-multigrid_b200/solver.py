@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "amgb_async_groups", "amgb_solve_extended", "amgb_solve_extended_async", "amgb_smooth_transfer", "amgb_host_csr_free", "amgb_smem_solve", "amgb_time_residual", "amgb_level_storage", "amgb_time_spmv", "amgb_stream_stats", "amgb_l2_arena_bytes", "amgb_sellu_stats",
     "amgb_sellu_encode_host", "amgb_host_free", "amgb_async_program", "amgb_async_group_times",
     "amgb_dist_unique_id", "amgb_dist_init", "amgb_dist_set_level", "amgb_dist_setup", "amgb_dist_set_rhs",
-    "amgb_dist_get_solution", "amgb_dist_solve_sync", "amgb_dist_solve_sync_accel", "amgb_dist_stats",
+    "amgb_dist_get_solution", "amgb_dist_solve_sync", "amgb_dist_solve_sync_accel", "amgb_dist_stats", "amgb_dist_eigs_power",
     "amgb_dist_ipc_export_solution", "amgb_dist_ipc_open_neighbours", "amgb_dist_async_smooth", "amgb_dist_residual_norm",
     "amgb_dist_zero_solution",
     "amgb_ipc_export_solution", "amgb_ipc_open_peers", "amgb_async_dist_correct", "amgb_residual_norm", "amgb_stream_synchronize",
@@ -116,6 +116,7 @@ def load_library():
     L.amgb_dist_solve_sync.argtypes = [C.c_void_p, C.c_double, C.c_int, DP, IP, DP]
     L.amgb_dist_solve_sync_accel.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, DP, IP, DP]
     L.amgb_dist_stats.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+    L.amgb_dist_eigs_power.argtypes = [C.c_void_p, C.c_int, DP, DP, DP]
     L.amgb_dist_ipc_export_solution.argtypes = [C.c_void_p, C.c_char_p]
     L.amgb_dist_ipc_open_neighbours.argtypes = [C.c_void_p, C.c_char_p, C.c_longlong, C.c_char_p]
     L.amgb_dist_async_smooth.argtypes = [C.c_void_p, C.c_int]
@@ -502,6 +503,15 @@ class DistSolver:
         hb, ops = C.c_longlong(0), C.c_longlong(0)
         self._ck(self.L.amgb_dist_stats(self.ctx, C.byref(hb), C.byref(ops)))
         return hb.value, ops.value
+
+    def DMEM_PowerMult(self, iters=20, u0_owned=None):
+        """DMEM_PowerMult + DMEM's ChebySetup (src/DMEM_Eig.cpp:10-104, src/DMEM_Setup.cpp:1901-1914): (mu, delta, alpha, beta) with
+        B = this context's partitioned additive cycle; collective"""
+        a, b = C.c_double(0), C.c_double(0)
+        u0 = None if u0_owned is None else np.ascontiguousarray(u0_owned, dtype=np.float64)
+        self._ck(self.L.amgb_dist_eigs_power(self.ctx, int(iters), None if u0 is None else _dp(u0), C.byref(a), C.byref(b)))
+        alpha, beta = a.value, b.value
+        return (beta + alpha) / (beta - alpha), 2.0 / (beta + alpha), alpha, beta
 
     # ---- DMEM_AsyncSmooth: asynchronous (L1-)Jacobi on the fine grid across GPUs (src/DMEM_Smooth.cpp:16-313) ----
     def ipc_export_solution(self):

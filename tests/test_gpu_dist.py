@@ -72,6 +72,24 @@ def test_single_rank_dmem_acceleration_matches_oracle(accel):
     s.close()
 
 
+@pytest.mark.parametrize("solver,w", [(H.MULTADD, 0.9), (H.BPX, 0.8)])
+def test_single_rank_power_iteration_matches_oracle(solver, w):
+    """DMEM_PowerMult on the partitioned path (amgb_dist_eigs_power): with a one-rank communicator and the all-ones start vector it
+    is EigsPower, whose restatement is pinned by the reference's object code; a given start vector goes through as well"""
+    A = H.laplacian("7pt", 16)
+    h = H.amg_setup(A)
+    h.build_transfers(solver, w)
+    alpha, beta = O.Problem(h, solver, H.JACOBI, w).eigs_power(20)
+    s = amg.DistSolver(PT.RankPlan(h, 1, 0), amg.solver.dist_unique_id(), w, solver=solver)
+    mu, delta, a, bb = s.DMEM_PowerMult(20)
+    assert abs(a - alpha) <= 1e-9 * abs(alpha) and abs(bb - beta) <= 1e-9 * abs(beta)
+    assert abs(mu - (beta + alpha) / (beta - alpha)) <= 1e-8 * mu
+    u0 = H.rand_rhs(h.n[0], 0.0, 1.0, 0) - 0.5                # src/DMEM_Eig.cpp:41: RandDouble(0.0, 1.0) - .5 after srand(rank)
+    _, _, a2, b2 = s.DMEM_PowerMult(20, u0)
+    assert 0.0 < a2 < b2 and abs(b2 - beta) <= 0.2 * beta      # another start vector, the same dominant eigenvalue within the 20-step accuracy
+    s.close()
+
+
 def test_single_rank_bpx_matches_oracle():
     """SYNC_BPX in the partitioned path (plain P, R = P^T, one Jacobi sweep on every level incl. the coarsest)"""
     w = 0.6

@@ -130,15 +130,18 @@ def test_partition_layout_properties():
 
 @pytest.mark.parametrize("world,n", [(4, 8), (8, 8)])
 def test_bench_plan_of_the_weak_series_is_consistent(tmp_path, world, n):
-    """the grids of bench.py's weak series (dist_bench.weak_dims: the cube doubled direction by direction, so ny != nx at 4 ranks
-    and the 512^3-shaped cube at 8) cut into z-slabs: every level's rows are dealt completely, a rank's ghosts are exactly what its
-    neighbours send, and every column of its row blocks lies inside its extended index space"""
+    """the grids of bench.py's two series (dist_bench.weak_dims: n x n x nN; the strong record's cube) cut into z-slabs for 4 and 8
+    ranks: every level's rows are dealt completely, a rank's ghosts are exactly what its neighbours send, and every column of
+    its row blocks lies inside its extended index space"""
     sys.path.insert(0, ROOT)
     import async_multigrid_b200 as amg  # noqa: F401
     from async_multigrid_b200 import hierarchy as H, partition as PT, dist_bench as DB
     from oracle import oracle as O
-    dims = DB.weak_dims(n, world)
-    assert dims[0] * dims[1] * dims[2] == world * n ** 3
+    for dims in (DB.weak_dims(n, world), (2 * n, 2 * n, 2 * n)):
+        _check_plan(H, PT, dims, world)
+
+
+def _check_plan(H, PT, dims, world):
     A = H.laplacian("7pt", *dims)
     h = H.amg_setup(A)
     h.build_transfers(H.MULTADD, 0.9, factor_level0=True)      # what the bench uploads
@@ -169,7 +172,7 @@ def test_bench_plan_roundtrip_through_disk(tmp_path):
     world = 2
     d = str(tmp_path / "plan")
     dims = DB.weak_dims(12, world)
-    assert dims == (12, 12, 24) and DB.weak_dims(256, 8) == (512, 512, 512) and DB.weak_dims(256, 4) == (256, 512, 512)
+    assert dims == (12, 12, 24) and DB.weak_dims(256, 8) == (256, 256, 2048)
     DB._build_and_scatter(args, world, d, dims)
     A = H.laplacian("7pt", *dims)
     h = H.amg_setup(A)
