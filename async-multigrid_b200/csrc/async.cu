@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(kABlock, HEAVY ? 3 : 6) k_async_amg(const Asyn
    const int nops = p.op_begin[q + 1] - p.op_begin[q];
    const unsigned long long t_begin = global_ns();
    int stop = 0;
+   unsigned long long seq = 0;            // exchange steps of this group so far (row-partitioned solve)
 
    while (!stop) {
       for (int i = 0; i < nops; i++) {
@@ -163,6 +164,38 @@ __global__ void __launch_bounds__(kABlock, HEAVY ? 3 : 6) k_async_amg(const Asyn
                   red_add_f64(tgt + k, op.e.red_scale * ev);
                   if (cp) cp[k] = ld_cg(tgt + k);
                }
+            }
+         } else if (type == AOP_PUSH) {
+            // row-partitioned solve: this group's boundary (or owned) entries of a vector go straight into the ghost slots
+            // of the same group's vector on a peer GPU -- plain stores over NVLink, nobody waits for them (dist_async.cu)
+            const int n = op.sweeps;
+            for (int k = tm.tid; k < n; k += tm.size) op.y[k] = ld_cg(op.x + k);
+            __threadfence_system();
+         } else if (type == AOP_SIGNAL) {
+            // exchange step `seq` of this group: once every CTA's stores are fenced and done, the group root publishes the
+            // step number in the peer's flag word (release at system scope)
+            if (op.zero) { group_barrier(tm); seq++; }
+            if (tm.tid == 0 && op.y) {
+               __threadfence_system();
+               *reinterpret_cast<volatile unsigned long long *>(op.y) = seq;
+            }
+         } else if (type == AOP_WAIT) {
+            // ... and waits for the same step from the peer (the same group there runs the same program).  Bounded: a peer that
+            // never arrives (its launch failed) must end this kernel with an error, not hang the GPU.
+            if (tm.tid == 0 && op.x) {
+               const volatile unsigned long long *flag = reinterpret_cast<const volatile unsigned long long *>(op.x);
+               const unsigned long long t_wait = global_ns();
+               while (*flag < seq && p.converge_flag[1] == 0) {      // (after one time-out nobody waits any more: the launch just ends)
+                  __nanosleep(128);
+                  if (global_ns() - t_wait > 30000000000ull) { p.converge_flag[1] = 1; __threadfence(); break; }
+               }
+               __threadfence_system();
+            }
+            if (op.barrier) {
+               // every CTA drops what its SM's L1 holds of the ghost slots (a one-CTA group's barrier has no fence of its own)
+               group_barrier(tm);
+               if (threadIdx.x == 0) __threadfence();
+               __syncthreads();
             }
          } else if (type == AOP_LOCK) {
             if (tm.tid == 0) {
@@ -219,7 +252,7 @@ __global__ void __launch_bounds__(kABlock, HEAVY ? 3 : 6) k_async_amg(const Asyn
          } else if (HEAVY && type == AOP_ASYNC_GS) {
             async_gs_team<false>(p.A[op.level], op.x, op.y, p.jgs_block_rows, op.sweeps, tm.tid, tm.size);
          }
-         if (op.barrier) group_barrier(tm);
+         if (op.barrier && type != AOP_WAIT) group_barrier(tm);
       }
    }
    if (tm.tid == 0) p.group_ns[q] = global_ns() - t_begin;
@@ -342,7 +375,7 @@ struct ProgBuilder {
 
 }  // namespace
 
-int async_build_program(const amgb_options &o, int L, bool symmetric, bool fact0, int q, std::vector<AsyncOpSym> &ops)
+int async_build_program(const amgb_options &o, int L, bool symmetric, bool fact0, int q, std::vector<AsyncOpSym> &ops, bool partitioned)
 {
    const bool multadd = o.solver == AMGB_SOLVER_ASYNC_MULTADD || o.solver == AMGB_SOLVER_MULTADD;
    const bool global = o.res_compute_type != 0, read_res = o.read_type != 0, semi = o.async_type != 0;
@@ -398,9 +431,12 @@ int async_build_program(const amgb_options &o, int L, bool symmetric, bool fact0
       // ---- prolongation chain (:211-224); level 0 factorised: v = P_0 e_1, e_0 = v - (w/d) o (A_0 v)
       for (int l = q - 1; l >= 0; l--) {
          if (fact0 && l == 0) {
-            B.spmv(AMGB_MAT_P, 0, 0, Ev(1), T0, 1.0, 0.0, AV_NONE);
-            AsyncOpSym &s = B.spmv(AMGB_MAT_A, 0, 0, T0, Ev(0), -1.0, 0.0, AV_NONE, 0.0, AV_NONE, rs0);
-            s.xs = T0; s.xself = 1.0;
+            // (row-partitioned solve: the prolongation side gets a scratch vector of its own -- a neighbour GPU that is half
+            //  an iteration ahead or behind must never find the restriction side's t_0 in the ghost slots of v, or vice versa)
+            const int V0 = partitioned ? Wv(0) : T0;
+            B.spmv(AMGB_MAT_P, 0, 0, Ev(1), V0, 1.0, 0.0, AV_NONE);
+            AsyncOpSym &s = B.spmv(AMGB_MAT_A, 0, 0, V0, Ev(0), -1.0, 0.0, AV_NONE, 0.0, AV_NONE, rs0);
+            s.xs = V0; s.xself = 1.0;
          } else B.spmv(AMGB_MAT_P, l, 0, Ev(l + 1), Ev(l), 1.0, 0.0, AV_NONE);
          last = (int)ops.size() - 1;
       }
@@ -450,7 +486,7 @@ static bool async_heavy(const amgb_options &o)
 
 // estimated seconds-equivalent cost of streaming one operator once (bytes over the fraction of the HBM roofline its storage
 // reaches in the stand-alone kernels, profiles/README.md): only the RATIOS matter, they seed the CTA-group sizes
-static double op_cost(const DevCSR &M, long sell_entries)
+double async_op_cost(const DevCSR &M, long sell_entries)
 {
    if (M.su_desc) return (32.0 * M.nrows) / 0.8;
    if (M.sell_slices > 0) return (12.0 * (double)sell_entries + 16.0 * M.nrows) / (M.sell_perm ? 0.55 : 0.85);
@@ -566,7 +602,7 @@ static int async_prepare(amgb_ctx *c)
          if (s.type == AOP_SPMV) {
             const DevCSR &M = s.mat_kind == AMGB_MAT_A ? c->A[s.mat_level] : (s.mat_kind == AMGB_MAT_P ? c->P[s.mat_level] : c->R[s.mat_level]);
             auto it = c->sell_entries.find(&M);
-            w += op_cost(M, it == c->sell_entries.end() ? 0 : it->second) + 24.0 * M.nrows;
+            w += async_op_cost(M, it == c->sell_entries.end() ? 0 : it->second) + 24.0 * M.nrows;
          } else if (s.type == AOP_JGS || s.type == AOP_ASYNC_GS) {
             w += 4.0 * 12.0 * c->A[s.level].nnz * std::max(1, s.sweeps);
          } else if (s.type != AOP_COUNT_STOP && s.type != AOP_LOCK && s.type != AOP_UNLOCK) {
@@ -612,7 +648,7 @@ static int async_prepare(amgb_ctx *c)
 
 // CTA groups proportional to `work` (one CTA per group at least; a group whose work is zero -- the idle coarsest group --
 // keeps exactly one): largest-remainder distribution
-static void async_assign_groups(amgb_ctx *c, const std::vector<double> &work)
+void async_assign_groups(amgb_ctx *c, const std::vector<double> &work)
 {
    AsyncParams &hp = *c->async_host;
    const int L = c->L, first = c->async_first, grid = c->async_grid;

@@ -77,6 +77,9 @@ bool amgb_dist_owned_cols(const amgb_ctx *c, int kind, int level, int *c0, int *
 void amgb_dist_teardown(amgb_ctx *c);
 void amgb_ext_teardown(amgb_ctx *c);
 void amgb_async_teardown(amgb_ctx *c);   // frees the host copy of the persistent kernel's parameter block
+// persistent kernel, host side (async.cu), shared with the row-partitioned solve (dist_async.cu)
+double async_op_cost(const DevCSR &M, long sell_entries);                      // cost-model seed of the CTA groups
+void async_assign_groups(amgb_ctx *c, const std::vector<double> &work);        // CTA groups in proportion to `work`
 int amgb_dist_diag_offset(const amgb_ctx *c, int level);          // position of the diagonal in a local row block
 bool amgb_dist_level_distributed(const amgb_ctx *c, int level);
 

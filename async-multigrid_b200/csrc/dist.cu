@@ -13,63 +13,18 @@
 // contiguous ncclSend/ncclRecv pairs with the immediate neighbours, no packing.  REPLICATED levels (the
 // small coarse tail) hold full vectors and matrices on every rank; the first replicated level's
 // residual is all-gathered, everything coarser is computed redundantly with no communication.
-#include "ctx.h"
+#include "dist.h"
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
 #include <omp.h>
-#ifdef AMG_HAVE_NCCL
-#include <nccl.h>
-#endif
-
-struct DistLevel {
-   int n_global = 0, row_start = 0, n_owned = 0, halo_lo = 0, halo_hi = 0, distributed = 0, send_lo = 0, send_hi = 0;
-   bool set = false;
-   std::vector<int> all_owned;   // n_owned of every rank (all-gather counts)
-   int n_ext() const { return distributed ? halo_lo + n_owned + halo_hi : n_global; }
-   int off() const { return distributed ? halo_lo : 0; }   // position of the first owned entry
-};
-
-struct DistState {
-   int rank = 0, nranks = 1;
-#ifdef AMG_HAVE_NCCL
-   ncclComm_t comm = nullptr;
-#endif
-   std::vector<DistLevel> lv;
-   std::vector<double *> ws, r, e;   // level layout (ws = w/d, or 1/l1 for the L1-Jacobi smoother)
-   std::vector<double *> t, w;       // level layout: AFACx scratch (coarse-grid correction / its prolongation, fine residual)
-   double *u = nullptr, *f = nullptr;   // u: level-0 layout; f: owned rows
-   double *ecyc = nullptr, *dacc = nullptr;   // owned rows: cycle output and the accelerated increment (DMEM_ChebyUpdate)
-   double *t0 = nullptr, *v0 = nullptr;  // level-0 layout: scratch of the factorised level-0 transfers (factor_level0)
-   // halo exchange on its own stream, overlapped with the interior launch units of the SpMV that needs it
-   cudaStream_t comm_stream = nullptr;
-   cudaEvent_t ev_x = nullptr, ev_h = nullptr;
-   double *partials3 = nullptr;          // 3 x npartials: interior / low boundary / high boundary launches
-   bool overlap = true;
-   bool ready = false;
-   // one cycle + residual + norm captured as a CUDA graph, NCCL operations and the communication stream's fork / join
-   // included, replayed per cycle.  Validated with a single-rank communicator only: with two ranks the replayed graph
-   // DEADLOCKS on the B200 box (round 2, profiles/r2_call4_2gpu.log: both 2-GPU tests and `bench.py --gpus 2` hung until
-   // their timeouts, while the per-operation path of the same build converged in 38 cycles) -- the captured ncclSend /
-   // ncclRecv pairs of the two ranks never meet.  So the graph is the default for ONE rank and off otherwise;
-   // AMGB_DIST_GRAPH=1 / 0 force it.
-   bool use_graph = false;
-   cudaGraphExec_t graph_exec = nullptr;
-   bool graph_warm = false;              // one cycle has run with per-operation launches (NCCL's lazy connections exist)
-   long long graph_kernels = 0, graph_halo_bytes = 0, graph_collectives = 0;
-   // asynchronous fine-grid smoother across GPUs (DMEM_AsyncSmooth): the neighbours' level-0 solution vectors mapped
-   // through CUDA IPC, and where in them this rank's boundary entries belong (their ghost slots)
-   double *nbr_lo = nullptr, *nbr_hi = nullptr;   // rank-1 / rank+1
-   long nbr_lo_off = 0;                            // first ghost_hi entry of rank-1 ( = its halo_lo + n_owned )
-   double *sm_scratch = nullptr;
-   long long halo_bytes = 0, collectives = 0;
-};
 
 void amgb_dist_teardown(amgb_ctx *c)
 {
    if (c && c->dist) {
+      amgb_dist_async_teardown(c);
 #ifdef AMG_HAVE_NCCL
       if (c->dist->comm) ncclCommDestroy(c->dist->comm);
 #endif
@@ -116,15 +71,8 @@ static inline SpmvEpilogue epi(double alpha, double beta, const double *b, doubl
 }
 
 #ifdef AMG_HAVE_NCCL
-#define NCCL_OK(c, call)                                                                                    \
-   do {                                                                                                     \
-      ncclResult_t r__ = (call);                                                                            \
-      if (r__ != ncclSuccess)                                                                               \
-         return amgb_fail((c), AMGB_ENCCL, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, ncclGetErrorString(r__)); \
-   } while (0)
-
 // ghosts of v (level layout) <- neighbours' boundary entries
-static int halo(amgb_ctx *c, int l, double *v, cudaStream_t st = nullptr)
+int dist_halo(amgb_ctx *c, int l, double *v, cudaStream_t st)
 {
    DistState *d = c->dist;
    const DistLevel &L = d->lv[l];
@@ -174,13 +122,13 @@ static int dist_spmv(amgb_ctx *c, const DevCSR &M, bool sval, int lin, double *x
    int rc;
    const bool split = d->overlap && d->lv[lin].distributed && M.uhi > M.ulo;
    if (!split) {
-      if ((rc = halo(c, lin, x))) return rc;
+      if ((rc = dist_halo(c, lin, x))) return rc;
       enq_spmv(c, M, sval, x, y, e, norm);
       return AMGB_OK;
    }
    CUDA_OK(c, cudaEventRecord(d->ev_x, c->stream));
    CUDA_OK(c, cudaStreamWaitEvent(d->comm_stream, d->ev_x, 0));
-   if ((rc = halo(c, lin, x, d->comm_stream))) return rc;
+   if ((rc = dist_halo(c, lin, x, d->comm_stream))) return rc;
    CUDA_OK(c, cudaEventRecord(d->ev_h, d->comm_stream));
    const int nu = spmv_units(M), np = c->npartials;
    int g0 = 0, g1 = 0, g2 = 0;
@@ -195,7 +143,7 @@ static int dist_spmv(amgb_ctx *c, const DevCSR &M, bool sval, int lin, double *x
 }
 
 // r_0 = f - A_0 u on the owned rows, d_scalars[0] = global ||r||^2
-static int dist_residual(amgb_ctx *c)
+int dist_residual(amgb_ctx *c)
 {
    DistState *d = c->dist;
    int rc;
@@ -237,7 +185,7 @@ static int dist_cycle(amgb_ctx *c, double *tgt, bool accumulate)
       } else if ((rc = dist_spmv(c, c->R[l], false, l, d->r[l], out, epi(1.0, 0.0, nullptr), false))) return rc;
       if (gather && (rc = allgather_level(c, l + 1, d->r[l + 1]))) return rc;
    }
-   if (top == L - 1 && c->symmetric && (rc = halo(c, L - 2, d->r[L - 2]))) return rc;   // (the other smoothers read owned entries only)
+   if (top == L - 1 && c->symmetric && (rc = dist_halo(c, L - 2, d->r[L - 2]))) return rc;   // (the other smoothers read owned entries only)
    if (direct) enq_spmv(c, c->Ainv, false, d->r[L - 1], d->e[L - 1], epi(1.0, 0.0, nullptr), false);
    for (int l = 0; l < (direct ? L - 1 : top); l++) {
       if (fact0 && l == 0) continue;                  // e_0 is folded into the last launch of the cycle
@@ -392,7 +340,7 @@ int amgb_dist_setup(amgb_ctx *c)
       // symmetrised smoother (on replicated levels amgb_setup already did this)
       CUDA_OK(c, cudaMemcpyAsync(d->ws[l] + lv.off(), l1s ? c->inv_l1[l] : c->ws[l], sizeof(double) * c->A[l].nrows, cudaMemcpyDeviceToDevice, c->stream));
       if (lv.distributed) {
-         if ((rc = halo(c, l, d->ws[l]))) return rc;
+         if ((rc = dist_halo(c, l, d->ws[l]))) return rc;
          if (c->A[l].va)      // (lean storage keeps no CSR copy of a sliced-ELL matrix)
             c->launches += launch_colscale(c->stream, c->A[l].nnz, c->A[l].ci, c->A[l].va, d->ws[l], const_cast<double *>(c->A[l].sval));
          if (c->A[l].pos)

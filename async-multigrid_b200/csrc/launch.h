@@ -76,7 +76,10 @@ int launch_colscale(cudaStream_t st, int nnz, const int *ci, const double *va, c
 // -res_compute_type and -async_type are host-side variations of one small kernel.
 #define AMGB_MAX_LEVELS 32
 enum { AOP_SPMV = 0, AOP_SCALE = 1, AOP_COPY = 2, AOP_ZERO = 3, AOP_UPDATE = 4, AOP_COUNT_STOP = 5, AOP_LOCK = 6, AOP_UNLOCK = 7,
-       AOP_JGS = 8, AOP_ASYNC_GS = 9 };
+       AOP_JGS = 8, AOP_ASYNC_GS = 9,
+       // row-partitioned solve (dist_async.cu): PUSH = boundary / owned entries of a vector into a peer GPU's ghost slots;
+       // SIGNAL = "this group's stores of exchange step s are in place" into a peer's flag word; WAIT = until a peer's flag says s
+       AOP_PUSH = 10, AOP_SIGNAL = 11, AOP_WAIT = 12 };
 // vectors a program names: id = kind * 64 + level (group-private unless said otherwise)
 enum { AV_NONE = -1, AV_F = 0 /* shared f */, AV_U = 1 /* shared u */, AV_RS = 2 /* shared residual (GLOBAL / READ_RES) */,
        AV_R = 3, AV_E = 4, AV_T = 5, AV_W = 6, AV_UL = 7 /* private copy of u */, AV_T0 = 8 /* level-0 scratch */,
@@ -96,7 +99,8 @@ struct AsyncOpSym {                // one operation, symbolic (what the CPU test
    int locked;                     // AOP_UPDATE: plain read-modify-write (inside the SEMI_ASYNC critical section) instead of reductions
    double alpha, beta, gamma, beta2, xself, red_scale;
 };
-struct AsyncOp {                   // the same with device pointers
+struct AsyncOp {                   // the same with device pointers (AOP_PUSH: `sweeps` doubles from x to y, y in a peer's memory;
+                                   // AOP_SIGNAL: y = the peer's flag word, zero = first signal of an exchange step; AOP_WAIT: x = own flag word)
    int type, mat_kind, mat_level, sval, range, barrier, level, sweeps, zero, locked;
    const double *x;
    double *y;
@@ -129,4 +133,31 @@ struct AsyncParams {
 int launch_async(cudaStream_t st, const AsyncParams *params_dev, int grid, int block, bool heavy, const cudaAccessPolicyWindow *window);
 int async_max_grid(int block, bool heavy);
 // host-only: the program of group q (appended to `ops`); returns AMGB_OK or AMGB_EINVAL for an unsupported combination
-int async_build_program(const amgb_options &o, int L, bool symmetric, bool fact0, int q, std::vector<AsyncOpSym> &ops);
+int async_build_program(const amgb_options &o, int L, bool symmetric, bool fact0, int q, std::vector<AsyncOpSym> &ops, bool partitioned = false);
+
+// ---- row-partitioned asynchronous solve (dist_async.cu): the same programs on every GPU's row blocks, with AOP_PUSH
+// operations after every operation whose result a later SpMV reads with ghosts.  Pure host planning, shared by the device
+// path and the CPU test suite's multi-rank interpreter: vectors are SLOTS of one arena per rank (identical slot table on
+// every rank, a slot holds the largest extended length over the ranks), an operand is (slot, element offset).
+struct DistLay { int n_global, row_start, n_owned, halo_lo, halo_hi, distributed, send_lo, send_hi; };   // one (rank, level)
+enum { DROLE_X = 0, DROLE_Y, DROLE_B, DROLE_C, DROLE_RS, DROLE_B2, DROLE_XS, DROLE_RED, DROLE_RED_COPY, DROLE_ACC, DROLE_N };
+enum { DEXT_NONE = -1, DEXT_F = -2 /* rhs, owned rows */, DEXT_U = -3 /* shared solution, level-0 layout */,
+       DEXT_WS0 = -100 /* DEXT_WS0 - l: w/d or 1/l1 of level l, level layout */ };
+struct DistAsyncOp {
+   int type, mat_kind, mat_level, sval, barrier, level;
+   int count, dst_rank;             // AOP_PUSH: `count` doubles from (slot[X], elem[X]) here to (slot[Y], elem[Y]) on dst_rank (-1: nobody there);
+                                    // AOP_SIGNAL: to dst_rank, count = 1 on the first signal of an exchange step; AOP_WAIT: for dst_rank
+   int slot[DROLE_N];               // >= 0: arena slot; DEXT_*
+   long long elem[DROLE_N];         // first element of the operand inside the slot / external vector
+   double alpha, beta, gamma, beta2, xself, red_scale;
+};
+struct DistAsyncPlan {
+   std::vector<DistAsyncOp> ops;           // all groups, group after group
+   std::vector<int> op_begin;              // [L + 1]
+   std::vector<long long> slot_off;        // [num_slots + 1], doubles
+   std::vector<int> slot_group, slot_vec;  // which group's which vector (AV_ID) a slot holds
+   // after the last slot: L x nranks 8-byte flag words, flag[q * nranks + src] = last exchange step of group q that rank src
+   // has completed towards this rank (slot_off.back() is where they start)
+};
+// lay[p * L + l]; returns AMGB_OK or AMGB_EINVAL (unsupported options / inconsistent layouts)
+int dist_async_plan(const amgb_options &o, int L, int nranks, int rank, const DistLay *lay, bool symmetric, bool fact0, DistAsyncPlan &out);

@@ -28,6 +28,7 @@ ABI_SYMBOLS = [
     "amgb_sellu_encode_host", "amgb_host_free", "amgb_async_program", "amgb_async_group_times",
     "amgb_dist_unique_id", "amgb_dist_init", "amgb_dist_set_level", "amgb_dist_setup", "amgb_dist_set_rhs",
     "amgb_dist_get_solution", "amgb_dist_solve_sync", "amgb_dist_solve_sync_accel", "amgb_dist_stats", "amgb_dist_eigs_power",
+    "amgb_dist_solve_async", "amgb_dist_async_groups", "amgb_dist_async_plan",
     "amgb_dist_ipc_export_solution", "amgb_dist_ipc_open_neighbours", "amgb_dist_async_smooth", "amgb_dist_residual_norm",
     "amgb_dist_zero_solution",
     "amgb_ipc_export_solution", "amgb_ipc_open_peers", "amgb_async_dist_correct", "amgb_residual_norm", "amgb_stream_synchronize",
@@ -117,6 +118,10 @@ def load_library():
     L.amgb_dist_solve_sync_accel.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, DP, IP, DP]
     L.amgb_dist_stats.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     L.amgb_dist_eigs_power.argtypes = [C.c_void_p, C.c_int, DP, DP, DP]
+    L.amgb_dist_solve_async.argtypes = [C.c_void_p, C.c_int, IP, DP, DP]
+    L.amgb_dist_async_groups.argtypes = [C.c_void_p, IP, DP]
+    L.amgb_dist_async_plan.argtypes = [C.POINTER(Options), C.c_int, C.c_int, C.c_int, IP, C.c_int, C.c_int, C.c_void_p, C.c_int, IP,
+                                       C.POINTER(C.c_longlong), IP, IP, C.c_int, IP]
     L.amgb_dist_ipc_export_solution.argtypes = [C.c_void_p, C.c_char_p]
     L.amgb_dist_ipc_open_neighbours.argtypes = [C.c_void_p, C.c_char_p, C.c_longlong, C.c_char_p]
     L.amgb_dist_async_smooth.argtypes = [C.c_void_p, C.c_int]
@@ -417,6 +422,42 @@ def async_program(num_levels, solver, smoother=H.JACOBI, symmetric=True, factor_
     return [[ops[i] for i in range(ob[q], ob[q + 1])] for q in range(num_levels)]
 
 
+class DistAsyncOp(C.Structure):
+    """csrc/launch.h DistAsyncOp: one operation of a level group's program on one rank of the row-partitioned asynchronous
+    solve; operands are (slot, elem): slot >= 0 an arena slot, -1 none, -2 f (owned rows), -3 u (level-0 layout),
+    -100 - l the smoother's scale vector of level l (level layout)"""
+    ROLES = ("x", "y", "b", "c", "rs", "b2", "xs", "red", "red_copy", "acc")
+    _fields_ = [(k, C.c_int) for k in ("type", "mat_kind", "mat_level", "sval", "barrier", "level", "count", "dst_rank")] + \
+               [("slot", C.c_int * 10), ("elem", C.c_longlong * 10)] + \
+               [(k, C.c_double) for k in ("alpha", "beta", "gamma", "beta2", "xself", "red_scale")]
+
+
+def dist_async_plan(layouts, rank, solver, smoother=H.JACOBI, symmetric=True, factor_level0=False, fine_sweeps=1, coarse_sweeps=1):
+    """planning of amgb_dist_solve_async for `rank` (host-only).  layouts[p][l]: partition.LevelLayout of rank p.
+    -> (programs: list over the level groups of lists of DistAsyncOp, slot_off (doubles, len num_slots + 1), slot_group, slot_vec)"""
+    L = load_library()
+    o = Options()
+    L.amgb_default_options(C.byref(o))
+    o.solver, o.smoother = solver, smoother
+    o.num_fine_smooth_sweeps, o.num_coarse_smooth_sweeps = fine_sweeps, coarse_sweeps
+    nranks, nl = len(layouts), len(layouts[0])
+    tab = np.zeros((nranks, nl, 8), dtype=np.int32)
+    for p in range(nranks):
+        for l, a in enumerate(layouts[p]):
+            tab[p, l] = (a.n_global, a.row_start, a.n_owned, a.halo_lo, a.halo_hi, int(a.distributed), a.send_lo, a.send_hi)
+    ops = (DistAsyncOp * 8192)()
+    ob = np.zeros(nl + 1, dtype=np.int32)
+    so = np.zeros(1025, dtype=np.int64)
+    sg, sv = np.zeros(1024, dtype=np.int32), np.zeros(1024, dtype=np.int32)
+    ns = C.c_int(0)
+    rc = L.amgb_dist_async_plan(C.byref(o), nl, nranks, rank, _ip(tab), int(symmetric), int(factor_level0), ops, 8192, _ip(ob),
+                                so.ctypes.data_as(C.POINTER(C.c_longlong)), _ip(sg), _ip(sv), 1024, C.byref(ns))
+    if rc != 0:
+        raise AmgError("amgb_dist_async_plan failed (%d): unsupported options or inconsistent layouts" % rc)
+    n = ns.value
+    return [[ops[i] for i in range(ob[q], ob[q + 1])] for q in range(nl)], so[:n + 1].copy(), sg[:n].copy(), sv[:n].copy()
+
+
 def dist_unique_id():
     """128-byte NCCL unique id (rank 0 creates it, everybody receives it through the launcher's channel)"""
     L = load_library()
@@ -512,6 +553,21 @@ class DistSolver:
         self._ck(self.L.amgb_dist_eigs_power(self.ctx, int(iters), None if u0 is None else _dp(u0), C.byref(a), C.byref(b)))
         alpha, beta = a.value, b.value
         return (beta + alpha) / (beta - alpha), 2.0 / (beta + alpha), alpha, beta
+
+    def DMEM_Add_async(self, num_cycles):
+        """DMEM_Add's asynchronous loop on the row-partitioned hierarchy (amgb_dist_solve_async): every level group of every
+        rank performs num_cycles corrections; collective.  -> (corrections per level on this rank, global relres, this rank's
+        kernel seconds)"""
+        cor = np.zeros(self.plan.num_levels, dtype=np.int32)
+        rel, secs = C.c_double(0), C.c_double(0)
+        self._ck(self.L.amgb_dist_solve_async(self.ctx, int(num_cycles), _ip(cor), C.byref(rel), C.byref(secs)))
+        return cor, rel.value, secs.value
+
+    def async_groups(self):
+        cb = np.zeros(self.plan.num_levels + 1, dtype=np.int32)
+        t = np.zeros(self.plan.num_levels)
+        self._ck(self.L.amgb_dist_async_groups(self.ctx, _ip(cb), _dp(t)))
+        return cb, t
 
     # ---- DMEM_AsyncSmooth: asynchronous (L1-)Jacobi on the fine grid across GPUs (src/DMEM_Smooth.cpp:16-313) ----
     def ipc_export_solution(self):

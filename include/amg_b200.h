@@ -264,6 +264,24 @@ int amgb_dist_solve_sync_accel(amgb_ctx *ctx, double tol, int max_cycles, int ac
 int amgb_dist_eigs_power(amgb_ctx *ctx, int iters, const double *u0_owned, double *eig_min, double *eig_max);
 int amgb_dist_stats(amgb_ctx *ctx, long long *halo_bytes_sent, long long *nccl_ops);
 
+/* ---- asynchronous additive solve, ROW-PARTITIONED over the GPUs: DMEM_Add's asynchronous loop (src/DMEM_Add.cpp:101-130)
+ * with DMEM_AddCorrect_LocalRes / DMEM_AddResidual_LocalRes (:391-556) and DMEM_Comm's Isend / Test engine
+ * (src/DMEM_Comm.cpp:81-382).  On a context prepared with amgb_dist_init .. amgb_dist_setup (Multadd or AFACx, weighted / L1
+ * Jacobi) every rank runs ONE persistent kernel on its row blocks: the level groups loop over the single-GPU programs and
+ * store the boundary entries of every vector a later SpMV reads with ghosts straight into the neighbour GPUs' ghost slots
+ * (CUDA IPC over NVLink; the handles and layouts travel through NCCL all-gathers inside the first call); nobody waits for
+ * a peer.  From the resident f and u; LOCAL stop rule: every group of every rank performs num_cycles corrections.
+ * Collective.  corrections[num_levels]: this rank's counts; relres = global ||f - A u|| / ||f - A u_start||; solve_seconds =
+ * this rank's kernel time (the job's time is the maximum over the ranks). */
+int amgb_dist_solve_async(amgb_ctx *ctx, int num_cycles, int *corrections, double *relres, double *solve_seconds);
+int amgb_dist_async_groups(amgb_ctx *ctx, int *cta_begin /* num_levels + 1 */, double *group_seconds /* num_levels */);
+/* host-only probe (no CUDA call) of the planning behind amgb_dist_solve_async, for the CPU test suite's multi-rank
+ * interpreter: layouts = nranks x num_levels x 8 ints (n_global, row_start, n_owned, halo_lo, halo_hi, distributed, send_lo,
+ * send_hi); ops = max_ops records of csrc/launch.h DistAsyncOp; a vector is a slot of the rank's arena, slot_off in doubles */
+int amgb_dist_async_plan(const amgb_options *opt, int num_levels, int nranks, int rank, const int *layouts, int symmetric,
+                         int factor_level0, void *ops, int max_ops, int *op_begin, long long *slot_off, int *slot_group,
+                         int *slot_vec, int max_slots, int *num_slots);
+
 /* ---- asynchronous fine-grid smoother across GPUs: DMEM_AsyncSmooth (src/DMEM_Smooth.cpp:16-313) with the ASYNC_JACOBI /
  * ASYNC_L1_JACOBI smoothers, the `-smoother async_j` solver of DMEM_Add (src/DMEM_Add.cpp:88-95).  Every rank relaxes its
  * rows of A_0 x = f again and again, x_own += s o (f - A_0 [ghosts | x_own]), with whatever ghost values have arrived, and
