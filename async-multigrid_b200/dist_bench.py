@@ -136,7 +136,7 @@ def _build_and_scatter(args, world, d, dims):
 STRONG_T1 = os.path.join(os.environ.get("TMPDIR", "/tmp"), "amgb_strong_t1.json")
 
 
-def _leg(args, rank, world, local, dims, tag, steps, warmup, sampler=None):
+def _leg(args, rank, world, local, dims, tag, steps, warmup, sampler=None, want_async=False):
     """one partitioned solve series on the grid `dims` (z-slabs): returns the measurements (valid on every rank)"""
     import torch
     import torch.distributed as dist
@@ -203,9 +203,54 @@ def _leg(args, rank, world, local, dims, tag, steps, warmup, sampler=None):
     out = {"solve_s": solve_s, "e2e_s": e2e_s, "cycles": len(hist) - 1, "final_relres": float(hist[-1]), "launches": int(launches),
            "halo_bytes": float(hbt.item()), "nccl_ops": int(ops), "info": plan.info, "num_dist": plan.num_dist, "clocks": clocks,
            "upload_s": round(upload_s, 1), "graph": bool(int(os.environ.get("AMGB_DIST_GRAPH", "1" if world == 1 else "0")))}
+    if want_async:
+        out["async"] = _async_on(s, plan, args, world, out["cycles"], min(steps, 3))
     s.close()
     dist.barrier()
     return out
+
+
+def _async_on(s, plan, args, world, sync_cycles, steps):
+    """the ROW-PARTITIONED asynchronous Multadd solve (csrc/dist_async.cu, DMEM_Add's asynchronous loop) on the solver the
+    synchronous leg just used: from x0 = 0, every level group of every rank performs K corrections (LOCAL stop rule); K is
+    the smallest of sync_cycles, +4, +8 ... that reaches the tolerance.  Every rank returns the same record (the ranks
+    fail together or not at all: amgb_dist_solve_async agrees on errors before it returns)."""
+    import torch
+    import torch.distributed as dist
+    from bench import TOL
+
+    def one(K):
+        s.zero_solution()
+        torch.cuda.synchronize()
+        dist.barrier()
+        cor, rel, secs = s.DMEM_Add_async(K)
+        t = torch.tensor([secs], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [int(x) for x in cor], float(rel), float(t.item())
+
+    try:
+        K, tried = int(sync_cycles), []
+        while True:
+            cor, rel, secs = one(K)
+            tried.append({"corrections": K, "relres": rel, "seconds": secs})
+            if rel < TOL or len(tried) >= 5:
+                break
+            K += 4
+        times = []
+        for _ in range(steps):
+            cor, rel, secs = one(K)
+            times.append(secs)
+        cb, gt = s.async_groups()
+        hb, _ = s.stats()
+        return {"solver": "asynchronous Multadd, row-partitioned: one persistent kernel per GPU, level groups exchange boundaries by stores "
+                          "over NVLink with per-group step flags, groups asynchronous to one another (LOCAL stop rule)",
+                "corrections_per_level": cor, "relres": rel, "converged": bool(rel < TOL), "value": float(np.mean(times)), "unit": "s",
+                "timing": "kernel seconds, max over ranks (CUDA events around each rank's launch), mean of %d solves" % steps,
+                "ms_per_correction_round": float(np.mean(times)) * 1e3 / K, "calibration": tried,
+                "cta_groups_rank0": [int(x) for x in np.diff(cb)], "group_seconds_rank0": [round(float(x), 4) for x in gt],
+                "vs_sync_cycles": K / max(sync_cycles, 1)}
+    except S.AmgError as e:
+        return {"error": str(e)[:300]}
 
 
 def run(args, rank, world, local):
@@ -219,14 +264,18 @@ def run(args, rank, world, local):
     n = args.n
     wd = weak_dims(n, world)
     sn = args.strong_n
-    weak = _leg(args, rank, world, local, wd, "weak", args.steps, args.warmup, ClockSampler(local))
+    # the asynchronous solve runs on the strong-scaling problem (512^3, BASELINE.json configs[4]) -- the weak leg when that IS it
+    aleg = getattr(args, "async_leg", "strong")
+    strong_is_weak = wd == (sn, sn, sn)
+    weak = _leg(args, rank, world, local, wd, "weak", args.steps, args.warmup, ClockSampler(local),
+                want_async=aleg == "weak" or (aleg == "strong" and strong_is_weak and not args.no_strong))
     strong = None
     if not args.no_strong:
         if wd == (sn, sn, sn):
             strong = dict(weak)            # at this rank count the weak-series grid IS the strong-scaling problem
             strong["same_run_as_weak"] = True
         else:
-            strong = _leg(args, rank, world, local, (sn, sn, sn), "strong", min(args.steps, 3), min(args.warmup, 3))
+            strong = _leg(args, rank, world, local, (sn, sn, sn), "strong", min(args.steps, 3), min(args.warmup, 3), want_async=aleg == "strong")
     if rank == 0:
         peak, peak_src = load_peaks()
         info = weak["info"]
@@ -280,7 +329,11 @@ def run(args, rank, world, local):
             except Exception:
                 rec["parallel_efficiency"] = None
                 rec["note"] = "t(1) not found on this box (%s): run `bench.py --gpus 1` first" % STRONG_T1
+            if "async" in strong:
+                rec["async"] = strong["async"]
             line["strong"] = rec
+        if "async" in weak and not (strong is not None and strong.get("same_run_as_weak")):
+            line["async"] = weak["async"]
         print(json.dumps(line), flush=True)
     dist.barrier()
     dist.destroy_process_group()

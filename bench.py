@@ -686,6 +686,9 @@ def main():
     ap.add_argument("--elasticity-max-cycles", type=int, default=3000)
     ap.add_argument("--strong-n", type=int, default=512, help="grid of the strong-scaling record (BASELINE.json configs[4]: 512^3)")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling record (512^3 on --gpus N GPUs)")
+    ap.add_argument("--async-leg", default="strong", choices=["strong", "weak", "none"],
+                    help="--gpus N>1: which problem the row-partitioned ASYNCHRONOUS Multadd solve runs on after the synchronous one "
+                         "(strong = the 512^3 problem of BASELINE.json configs[4])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-async", action="store_true", help="skip the asynchronous solve reported beside the headline")
     ap.add_argument("--no-factor-level0", action="store_true",
