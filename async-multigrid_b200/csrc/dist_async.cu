@@ -526,11 +526,19 @@ extern "C" int amgb_dist_solve_async(amgb_ctx *c, int num_cycles, int *correctio
             if ((rc = dist_async_run(c, 3, nullptr, nullptr))) return rc;
             std::vector<unsigned long long> ns(AMGB_MAX_LEVELS);
             CUDA_OK(c, cudaMemcpy(ns.data(), hp.group_ns, sizeof(unsigned long long) * AMGB_MAX_LEVELS, cudaMemcpyDeviceToHost));
-            std::vector<double> work(L, 0.0);
+            std::vector<double> work(AMGB_MAX_LEVELS, 0.0);
             for (int q = 0; q < L; q++) {
                const int nct = hp.cta_begin[q + 1] - hp.cta_begin[q];
                work[q] = c->async_work[q] > 0.0 ? (double)nct * (double)ns[q] : 0.0;
             }
+            // the ranks of one level group move in lock step, so a group is as fast as its slowest rank: every rank deals
+            // its CTAs from the SUM over the ranks (the same split everywhere)
+            static_assert(AMGB_MAX_LEVELS + 8 <= 64, "d_scalars holds 64 doubles");
+            CUDA_OK(c, cudaMemcpyAsync(c->d_scalars + 8, work.data(), sizeof(double) * AMGB_MAX_LEVELS, cudaMemcpyHostToDevice, c->stream));
+            NCCL_OK(c, ncclAllReduce(c->d_scalars + 8, c->d_scalars + 8, AMGB_MAX_LEVELS, ncclDouble, ncclSum, d->comm, c->stream));
+            CUDA_OK(c, cudaMemcpyAsync(work.data(), c->d_scalars + 8, sizeof(double) * AMGB_MAX_LEVELS, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_OK(c, cudaStreamSynchronize(c->stream));
+            work.resize(L);
             async_assign_groups(c, work);
             CUDA_OK(c, cudaMemcpyAsync(d->u, a->u_save, sizeof(double) * next, cudaMemcpyDeviceToDevice, c->stream));
          }
