@@ -42,6 +42,8 @@ CASES = [
     ("5pt", 32, 2, 30, H.MULTADD, H.ASYNC_MULTADD, 1.0, 1, False, H.L1_JACOBI),
     ("7pt", 12, 2, 40, H.AFACX, H.ASYNC_AFACX, 0.6, 1, False, H.JACOBI),
     ("7pt", 12, 2, 10 ** 9, H.MULTADD, H.ASYNC_MULTADD, 0.9, 1, True, H.JACOBI),      # level 0 alone is partitioned
+    ("7pt", 32, 4, 40, H.MULTADD, H.ASYNC_MULTADD, 0.9, 1, True, H.JACOBI),           # ranks with two neighbours, two partitioned levels
+    ("7pt", 16, 8, 40, H.MULTADD, H.ASYNC_MULTADD, 0.9, 1, True, H.JACOBI),           # eight ranks: the gather has seven destinations
 ]
 
 
@@ -107,6 +109,17 @@ def test_random_interleaving_converges_like_one_gpu(ranks, fact0, seed):
         one.append(e1.relres())
     assert em.relres() < 1e-5, em.relres()
     assert em.relres() < 30.0 * max(one), (em.relres(), one)
+
+
+def test_eight_ranks_never_deadlock_under_random_interleaving():
+    """eight ranks, one partitioned level: every iteration of a deep group has one all-to-all exchange step (the gather into
+    the replicated tail) between neighbour-only steps; whatever the interleaving, some group can always advance"""
+    h, b, plane = _problem("7pt", 16, fact0=True)
+    for seed in (11, 12):
+        em = DistAsyncEmulator(h, 8, b, H.ASYNC_MULTADD, H.JACOBI, 0.9, factor_level0=True, plane=plane, min_rows_per_rank=40)
+        em.run_random(30, seed=seed, max_burst=9)
+        assert all(em.count[p] == [30] * h.num_levels for p in range(8))
+        assert em.relres() < 1e-3, em.relres()
 
 
 def test_without_the_exchange_flags_stale_ghosts_cost_orders_of_magnitude():
