@@ -235,6 +235,7 @@ struct DistAsync {
    double *u_save = nullptr;                // level-0 layout: the solution across the balancing launches
    bool ready = false, balanced = false;
    bool peer_timeout = false;               // a level group gave up waiting for a peer's exchange step
+   bool launch_failed = false;              // this rank's cooperative launch failed (message in ctx->err)
    long long pushed_doubles_per_iteration = 0;
 };
 
@@ -473,7 +474,14 @@ static int dist_async_run(amgb_ctx *c, int num_cycles, double *r0_out, double *s
    CUDA_OK(c, cudaEventRecord(c->ev0, c->stream));
    const int lr = launch_async(c->stream, (const AsyncParams *)c->async_params_dev, c->async_grid_used, kABlock, false,
                                c->window_valid ? &c->window : nullptr);
-   if (lr < 0) return amgb_fail(c, AMGB_ECUDA, "cooperative launch failed: %s", cudaGetErrorString((cudaError_t)(-lr)));
+   if (lr < 0) {
+      // (no early return: the peers' kernels are waiting for this rank's exchange steps and will give up after 30 s; the
+      //  failure is reported once the ranks have agreed on it, so that nobody is left alone inside a collective)
+      amgb_fail(c, AMGB_ECUDA, "cooperative launch failed: %s", cudaGetErrorString((cudaError_t)(-lr)));
+      a->peer_timeout = true;
+      a->launch_failed = true;
+      return AMGB_OK;
+   }
    c->launches += 1;
    CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));
    {
@@ -495,6 +503,29 @@ static int dist_async_run(amgb_ctx *c, int num_cycles, double *r0_out, double *s
    return AMGB_OK;
 }
 #endif   // AMG_HAVE_NCCL
+
+#ifdef AMG_HAVE_NCCL
+// every rank learns whether ANY rank's launch failed or timed out waiting for a peer, and all of them fail together
+static int dist_async_agree(amgb_ctx *c)
+{
+   DistState *d = c->dist;
+   DistAsync *a = d->da;
+   const double mine = a->peer_timeout ? 1.0 : 0.0;
+   CUDA_OK(c, cudaMemcpyAsync(c->d_scalars + 2, &mine, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+   NCCL_OK(c, ncclAllReduce(c->d_scalars + 2, c->d_scalars + 2, 1, ncclDouble, ncclMax, d->comm, c->stream));
+   double any = 0.0;
+   CUDA_OK(c, cudaMemcpyAsync(&any, c->d_scalars + 2, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+   CUDA_OK(c, cudaStreamSynchronize(c->stream));
+   const bool was_mine = a->launch_failed;
+   a->peer_timeout = false;
+   a->launch_failed = false;
+   if (any != 0.0) {
+      if (was_mine) return AMGB_ECUDA;                    // (keep this rank's own message: the launch failure)
+      return amgb_fail(c, AMGB_ENCCL, "a level group waited 30 s for a peer GPU's exchange step (a peer's kernel was not running): the solve is void");
+   }
+   return AMGB_OK;
+}
+#endif
 
 // Asynchronous additive solve on the partitioned hierarchy from the resident f and u (amgb_dist_set_rhs; u = 0 after
 // amgb_dist_setup / amgb_dist_zero_solution): every level group of every rank performs num_cycles corrections (LOCAL stop
@@ -524,6 +555,7 @@ extern "C" int amgb_dist_solve_async(amgb_ctx *c, int num_cycles, int *correctio
          CUDA_OK(c, cudaMemcpyAsync(a->u_save, d->u, sizeof(double) * next, cudaMemcpyDeviceToDevice, c->stream));
          for (int it = 0; it < rounds; it++) {
             if ((rc = dist_async_run(c, 3, nullptr, nullptr))) return rc;
+            if ((rc = dist_async_agree(c))) return rc;
             std::vector<unsigned long long> ns(AMGB_MAX_LEVELS);
             CUDA_OK(c, cudaMemcpy(ns.data(), hp.group_ns, sizeof(unsigned long long) * AMGB_MAX_LEVELS, cudaMemcpyDeviceToHost));
             std::vector<double> work(AMGB_MAX_LEVELS, 0.0);
@@ -547,22 +579,12 @@ extern "C" int amgb_dist_solve_async(amgb_ctx *c, int num_cycles, int *correctio
    }
    double r0 = 0.0;
    if ((rc = dist_async_run(c, num_cycles, &r0, solve_seconds))) return rc;
+   if ((rc = dist_async_agree(c))) return rc;
    if ((rc = dist_residual(c))) return rc;
    double ss;
    if ((rc = amgb_fetch_scalar(c, &ss))) return rc;
    if (relres) *relres = r0 > 0.0 ? sqrt(ss) / r0 : 0.0;
    c->r0_norm = r0;
-   {
-      // every rank learns whether ANY rank's groups timed out waiting for a peer, and all of them fail together
-      const double mine = a->peer_timeout ? 1.0 : 0.0;
-      CUDA_OK(c, cudaMemcpyAsync(c->d_scalars + 2, &mine, sizeof(double), cudaMemcpyHostToDevice, c->stream));
-      NCCL_OK(c, ncclAllReduce(c->d_scalars + 2, c->d_scalars + 2, 1, ncclDouble, ncclMax, d->comm, c->stream));
-      double any = 0.0;
-      CUDA_OK(c, cudaMemcpyAsync(&any, c->d_scalars + 2, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-      CUDA_OK(c, cudaStreamSynchronize(c->stream));
-      a->peer_timeout = false;
-      if (any != 0.0) return amgb_fail(c, AMGB_ENCCL, "a level group waited 30 s for a peer GPU's exchange step (a peer's kernel was not running): the solve is void");
-   }
    if (corrections) {
       std::vector<int> h(AMGB_MAX_LEVELS);
       CUDA_OK(c, cudaMemcpy(h.data(), hp.num_correct, sizeof(int) * AMGB_MAX_LEVELS, cudaMemcpyDeviceToHost));

@@ -259,8 +259,8 @@ def _async_on(s, plan, args, world, sync_cycles, steps):
                 "ms_per_correction_round": float(np.mean(times)) * 1e3 / K, "calibration": tried,
                 "cta_groups_rank0": [int(x) for x in np.diff(cb)], "group_seconds_rank0": [round(float(x), 4) for x in gt],
                 "sync_cycles": int(sync_cycles)}
-    except S.AmgError as e:
-        return {"error": str(e)[:300]}
+    except Exception as e:      # (the synchronous records of this line must survive a failure here)
+        return {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
 
 
 def run(args, rank, world, local):
