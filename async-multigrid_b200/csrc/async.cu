@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(kABlock, HEAVY ? 3 : 6) k_async_amg(const Asyn
          const int type = op.type;
          if (type == AOP_SPMV) {
             if (threadIdx.x == 0)
-               make_view(sv, op.mat_kind == AMGB_MAT_A ? p.A[op.mat_level] : (op.mat_kind == AMGB_MAT_P ? p.P[op.mat_level] : p.R[op.mat_level]), p.slice_ctas);
+               make_view(sv, op.mat_kind == AMGB_MAT_A ? p.A[op.mat_level] : (op.mat_kind == AMGB_MAT_P ? p.P[op.mat_level] : (op.mat_kind == AMGB_MAT_R ? p.R[op.mat_level] : p.Ainv)), p.slice_ctas);
             __syncthreads();
             const DevCSR &M = sv.M;
             const int t0 = op.range ? (int)threadIdx.x : tm.tid, ts = op.range ? kABlock : tm.size;
@@ -390,10 +390,14 @@ int async_build_program(const amgb_options &o, int L, bool symmetric, bool fact0
    auto Ev = [](int l) { return AV_ID(AV_E, l); };
    auto Tv = [](int l) { return AV_ID(AV_T, l); };
    auto Wv = [](int l) { return AV_ID(AV_W, l); };
-   // The coarsest level's correction is identically zero in the reference (direct solve commented out, :112-131): its
+   // The coarsest level's correction is identically zero in the SMEM reference (direct solve commented out, :112-131): its
    // restrict / prolong / residual work adds exactly 0.0 to u, so this group only keeps the correction count and the
-   // stop protocol (and, with -res_compute_type global, its share of the level-0 rows)
-   const bool idle = (q == L - 1);
+   // stop protocol.  With amgb_options.coarse_solve (DMEM's convention: AddCycle solves the coarsest grid directly,
+   // src/DMEM_Add.cpp:262-264) it is a working group like the others: e_{L-1} = A_{L-1}^{-1} r_{L-1}.
+   const bool direct = o.coarse_solve != 0 && L > 1;
+   if (direct && global) return AMGB_EINVAL;
+   const bool idle = (q == L - 1) && !direct;
+   const bool coarse_q = direct && q == L - 1;
    const int rs0 = B.rs_id(0);
    if (global && !idle) {
       // all CTAs of the working groups: smooth level 0 on this CTA's rows, u += u_fine (:35-60).  The reference reads the group's copy of the shared
@@ -410,7 +414,7 @@ int async_build_program(const amgb_options &o, int L, bool symmetric, bool fact0
    bool fused_update = false;
    if (!idle) {
       // ---- restriction chain (:93-108); level-0 transfers factorised: t_0 = r_0 - A_0 diag(w/d) r_0, r_1 = R_0 t_0
-      const int coarsest = multadd ? q : q + 1;
+      const int coarsest = (multadd || coarse_q) ? q : q + 1;
       for (int l = 0; l < coarsest && l < L - 1; l++) {
          if (fact0 && l == 0) {
             B.spmv(AMGB_MAT_A, 0, 1, Rv(0), T0, -1.0, 1.0, Rv(0));
@@ -419,7 +423,10 @@ int async_build_program(const amgb_options &o, int L, bool symmetric, bool fact0
       }
       // ---- correction on the group's level (:134-207)
       int last = -1;
-      if (multadd) last = B.smooth_zero(q, Rv(q), Ev(q), Tv(q), o.num_fine_smooth_sweeps, symmetric);
+      if (coarse_q) {
+         B.spmv(AMAT_AINV, q, 0, Rv(q), Ev(q), 1.0, 0.0, AV_NONE);
+         last = (int)ops.size() - 1;
+      } else if (multadd) last = B.smooth_zero(q, Rv(q), Ev(q), Tv(q), o.num_fine_smooth_sweeps, symmetric);
       else {
          // AFACx (:153-206): u_c = S_{q+1} r_{q+1}; e = P u_c; r_f = r_q - A_q e; u_f = S_q r_f
          const int cl = q + 1;
@@ -519,6 +526,7 @@ static int async_prepare(amgb_ctx *c)
       hp.A[l] = c->A[l];
       if (l < L - 1) { hp.P[l] = c->P[l]; hp.R[l] = c->R[l]; }
    }
+   hp.Ainv = c->Ainv;
    int rc;
    // ---- programs (symbolic), then the vectors they name
    std::vector<AsyncOpSym> sym;
@@ -600,7 +608,7 @@ static int async_prepare(amgb_ctx *c)
          const AsyncOpSym &s = sym[i];
          if (s.range) continue;                       // CTA-slice work is the same for every CTA
          if (s.type == AOP_SPMV) {
-            const DevCSR &M = s.mat_kind == AMGB_MAT_A ? c->A[s.mat_level] : (s.mat_kind == AMGB_MAT_P ? c->P[s.mat_level] : c->R[s.mat_level]);
+            const DevCSR &M = s.mat_kind == AMGB_MAT_A ? c->A[s.mat_level] : (s.mat_kind == AMGB_MAT_P ? c->P[s.mat_level] : (s.mat_kind == AMGB_MAT_R ? c->R[s.mat_level] : c->Ainv));
             auto it = c->sell_entries.find(&M);
             w += async_op_cost(M, it == c->sell_entries.end() ? 0 : it->second) + 24.0 * M.nrows;
          } else if (s.type == AOP_JGS || s.type == AOP_ASYNC_GS) {
@@ -745,7 +753,7 @@ extern "C" int amgb_solve_async(amgb_ctx *c, int num_cycles, int converge_type, 
 {
    NEED_READY(c);
    if (num_cycles < 1) return amgb_fail(c, AMGB_EINVAL, "num_cycles < 1");
-   if (c->opt.coarse_solve) return amgb_fail(c, AMGB_EINVAL, "coarse_solve (DMEM convention) is implemented for the synchronous cycles");
+   if (c->opt.coarse_solve && c->L > 1 && !c->Ainv.rp) return amgb_fail(c, AMGB_ESTATE, "coarse_solve: the inverse of the coarsest operator was not built");
    for (int *b : c->jgs_bounds)
       if (b) return amgb_fail(c, AMGB_EINVAL, "explicit hybrid-JGS block lists are implemented for the synchronous cycles");
    int rc;

@@ -66,6 +66,7 @@ int dist_async_plan(const amgb_options &o, int L, int nranks, int rank, const Di
    if (!multadd && !afacx) return AMGB_EINVAL;
    if (o.smoother != AMGB_SMOOTH_JACOBI && o.smoother != AMGB_SMOOTH_L1_JACOBI) return AMGB_EINVAL;
    if (o.res_compute_type || o.read_type || o.async_type) return AMGB_EINVAL;      // the shared-residual variants need a shared r
+   if (o.coarse_solve && L > 1 && lay[(size_t)rank * L + (L - 1)].distributed) return AMGB_EINVAL;   // the direct coarse solve needs the coarsest level whole
    auto LAY = [&](int p, int l) -> const DistLay & { return lay[(size_t)p * L + l]; };
    int num_dist = 0;
    while (num_dist < L && LAY(rank, num_dist).distributed) num_dist++;
@@ -377,7 +378,7 @@ static int dist_async_prepare(amgb_ctx *c)
          t.e.acc = ptr_of(rank, s.slot[DROLE_ACC], s.elem[DROLE_ACC]);
          dev_ops.push_back(t);
          if (s.type == AOP_SPMV) {
-            const DevCSR &M = s.mat_kind == AMGB_MAT_A ? c->A[s.mat_level] : (s.mat_kind == AMGB_MAT_P ? c->P[s.mat_level] : c->R[s.mat_level]);
+            const DevCSR &M = s.mat_kind == AMGB_MAT_A ? c->A[s.mat_level] : (s.mat_kind == AMGB_MAT_P ? c->P[s.mat_level] : (s.mat_kind == AMGB_MAT_R ? c->R[s.mat_level] : c->Ainv));
             auto it = c->sell_entries.find(&M);
             work[q] += async_op_cost(M, it == c->sell_entries.end() ? 0 : it->second) + 24.0 * M.nrows;
          } else if (s.type != AOP_COUNT_STOP) work[q] += 24.0 * c->A[s.level].nrows;
@@ -397,6 +398,7 @@ static int dist_async_prepare(amgb_ctx *c)
       hp.A[l] = c->A[l];
       if (l < L - 1) { hp.P[l] = c->P[l]; hp.R[l] = c->R[l]; }
    }
+   hp.Ainv = c->Ainv;
    AsyncOp *d_ops = nullptr;
    if ((rc = amgb_dev_alloc_bytes(c, (void **)&d_ops, sizeof(AsyncOp) * std::max<size_t>(dev_ops.size(), 1), false))) return rc;
    CUDA_OK(c, cudaMemcpyAsync(d_ops, dev_ops.data(), sizeof(AsyncOp) * dev_ops.size(), cudaMemcpyHostToDevice, c->stream));
@@ -538,7 +540,7 @@ extern "C" int amgb_dist_solve_async(amgb_ctx *c, int num_cycles, int *correctio
    DistState *d = c->dist;
    if (!d || !d->ready) return amgb_fail(c, AMGB_ESTATE, "amgb_dist_setup not called");
    if (num_cycles < 1) return amgb_fail(c, AMGB_EINVAL, "num_cycles < 1");
-   if (c->opt.coarse_solve) return amgb_fail(c, AMGB_EINVAL, "coarse_solve is implemented for the synchronous cycles");
+   if (c->opt.coarse_solve && c->L > 1 && !c->Ainv.rp) return amgb_fail(c, AMGB_ESTATE, "coarse_solve: the inverse of the coarsest operator was not built");
    int rc;
    if ((rc = dist_async_prepare(c))) return rc;
    DistAsync *a = d->da;

@@ -85,6 +85,7 @@ enum { AV_NONE = -1, AV_F = 0 /* shared f */, AV_U = 1 /* shared u */, AV_RS = 2
        AV_R = 3, AV_E = 4, AV_T = 5, AV_W = 6, AV_UL = 7 /* private copy of u */, AV_T0 = 8 /* level-0 scratch */,
        AV_FACC = 9 /* accumulated corrections (READ_RES) */, AV_WS = 10 /* w/d (read-only) */, AV_INVL1 = 11 /* 1/l1 (read-only) */ };
 #define AV_ID(kind, level) ((kind) * 64 + (level))
+#define AMAT_AINV 3                // AsyncOp::mat_kind beside AMGB_MAT_A / P / R: the dense inverse of the coarsest operator (coarse_solve)
 struct AsyncOpSym {                // one operation, symbolic (what the CPU tests interpret)
    int type;                       // AOP_*
    int mat_kind, mat_level;        // AOP_SPMV / AOP_JGS / AOP_ASYNC_GS: AMGB_MAT_* and level
@@ -115,6 +116,7 @@ struct AsyncParams {
    int num_cycles;
    int converge_type;
    DevCSR A[AMGB_MAX_LEVELS], P[AMGB_MAX_LEVELS], R[AMGB_MAX_LEVELS];
+   DevCSR Ainv;                             // coarse_solve: A_{L-1}^{-1} as a full CSR
    int cta_begin[AMGB_MAX_LEVELS + 1];      // CTA range of every level's group
    int slice_ctas;                          // CTAs that share the level-0 rows of the CTA-slice operations (the working groups')
    const AsyncOp *ops;                      // all programs, group after group

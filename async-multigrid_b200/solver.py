@@ -405,7 +405,7 @@ class AsyncOpSym(C.Structure):
 
 
 def async_program(num_levels, solver, smoother=H.JACOBI, symmetric=True, factor_level0=False, fine_sweeps=1, coarse_sweeps=1,
-                  async_type=0, res_compute_type=0, read_type=0):
+                  async_type=0, res_compute_type=0, read_type=0, coarse_solve=False):
     """the programs the persistent asynchronous kernel interprets (amgb_async_program; host-only, no GPU needed):
     list over the level groups of lists of AsyncOpSym"""
     L = load_library()
@@ -414,6 +414,7 @@ def async_program(num_levels, solver, smoother=H.JACOBI, symmetric=True, factor_
     o.solver, o.smoother = solver, smoother
     o.num_fine_smooth_sweeps, o.num_coarse_smooth_sweeps = fine_sweeps, coarse_sweeps
     o.async_type, o.res_compute_type, o.read_type = async_type, res_compute_type, read_type
+    o.coarse_solve = int(coarse_solve)
     ops = (AsyncOpSym * 4096)()
     ob = np.zeros(num_levels + 1, dtype=np.int32)
     rc = L.amgb_async_program(C.byref(o), num_levels, int(symmetric), int(factor_level0), ops, 4096, _ip(ob))
@@ -432,7 +433,8 @@ class DistAsyncOp(C.Structure):
                [(k, C.c_double) for k in ("alpha", "beta", "gamma", "beta2", "xself", "red_scale")]
 
 
-def dist_async_plan(layouts, rank, solver, smoother=H.JACOBI, symmetric=True, factor_level0=False, fine_sweeps=1, coarse_sweeps=1):
+def dist_async_plan(layouts, rank, solver, smoother=H.JACOBI, symmetric=True, factor_level0=False, fine_sweeps=1, coarse_sweeps=1,
+                    coarse_solve=False):
     """planning of amgb_dist_solve_async for `rank` (host-only).  layouts[p][l]: partition.LevelLayout of rank p.
     -> (programs: list over the level groups of lists of DistAsyncOp, slot_off (doubles, len num_slots + 1), slot_group, slot_vec)"""
     L = load_library()
@@ -440,6 +442,7 @@ def dist_async_plan(layouts, rank, solver, smoother=H.JACOBI, symmetric=True, fa
     L.amgb_default_options(C.byref(o))
     o.solver, o.smoother = solver, smoother
     o.num_fine_smooth_sweeps, o.num_coarse_smooth_sweeps = fine_sweeps, coarse_sweeps
+    o.coarse_solve = int(coarse_solve)
     nranks, nl = len(layouts), len(layouts[0])
     tab = np.zeros((nranks, nl, 8), dtype=np.int32)
     for p in range(nranks):

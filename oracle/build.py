@@ -42,7 +42,8 @@ def build_ref(force=False):
         return REF_LIB if os.path.exists(REF_LIB) else None
     script = os.path.join(ORACLE, "build_ref.sh")
     shim = os.path.join(ORACLE, "ref_shim")
-    deps = [script, os.path.join(ORACLE, "ref_driver.cpp"), os.path.join(os.path.dirname(ORACLE), "integration", "SMEM_B200.hpp")]
+    deps = [script, os.path.join(ORACLE, "ref_driver.cpp"), os.path.join(os.path.dirname(ORACLE), "integration", "SMEM_B200.hpp"),
+            os.path.join(os.path.dirname(ORACLE), "integration", "DMEM_B200.hpp")]
     deps += [os.path.join(d, f) for d, _, fs in os.walk(shim) for f in fs]
     if not force and _newer(REF_LIB, deps):
         return REF_LIB

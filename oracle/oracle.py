@@ -326,6 +326,30 @@ def ref_dmem_sync_add(h, b, smooth_weight, symmetrised=True, num_cycles=100, tol
     return x, hist[:k + 1]
 
 
+def ref_dmem_solve_b200(h, b, smooth_weight, symmetrised=True, num_cycles=100, tol=1e-9, async_flag=0):
+    """the DMEM binding of INTEGRATION.md (integration/DMEM_B200.hpp compiled against the reference's DMEM_Main.hpp) on one rank:
+    DMEM_AllData -> DMEM_B200_Upload -> DMEM_Add_B200.  h.P / h.R are the smoothed transfers.  Needs the GPU (libref_b200.so is
+    linked against the product library).  -> dict(x, hist, cycles, corrections, relres)"""
+    L = ref_b200_lib()
+    if L is None:
+        return None
+    nl = h.num_levels
+    keep = (list(h.A), list(h.P), list(h.R))
+    A = (OrcCSR * nl)(*[c_csr(a) for a in h.A])
+    P = (OrcCSR * max(nl - 1, 1))(*[c_csr(p) for p in h.P])
+    R = (OrcCSR * max(nl - 1, 1))(*[c_csr(r) for r in h.R])
+    x, hist = np.zeros(h.n[0]), np.zeros(num_cycles + 1)
+    cor = np.zeros(nl, dtype=np.int32)
+    rel = C.c_double(0)
+    L.ref_dmem_solve_b200.restype = C.c_int
+    L.ref_dmem_solve_b200.argtypes = [C.c_int, C.POINTER(OrcCSR), C.POINTER(OrcCSR), C.POINTER(OrcCSR), C.c_double, C.c_int, DP, C.c_int,
+                                      C.c_double, C.c_int, DP, DP, IP, DP]
+    k = L.ref_dmem_solve_b200(nl, A, P, R, smooth_weight, int(symmetrised), dptr(np.ascontiguousarray(b, dtype=np.float64)), num_cycles,
+                              tol, int(async_flag), dptr(x), dptr(hist), iptr(cor), C.byref(rel))
+    del keep
+    return dict(x=x, hist=hist[:k + 1] if not async_flag else None, cycles=k, corrections=cor, relres=rel.value)
+
+
 def ref_dmem_mult(h, b, smooth_weight, num_cycles=100, tol=1e-9):
     """the reference's DMEM_Mult / DMEM_MultCycle object code (src/DMEM_Mult.cpp:13-261) on one rank: multiplicative V(1,1),
     weighted Jacobi, direct solve on the coarsest level; h.P / h.R plain.  -> (x, hist)"""

@@ -716,6 +716,48 @@ int ref_solve_b200(void *h, int num_cycles, double tol, int async_type, int res_
    b200 = NULL;
    return done;
 }
+
+// The DMEM binding of INTEGRATION.md (integration/DMEM_B200.hpp, compiled here against the reference's own DMEM_Main.hpp) on ONE
+// rank: every level is handed over whole (a one-rank "partition": nothing distributed), DMEM_AllData carries the options the
+// way DMEM_Main's argument parser leaves them, DMEM_Add_B200 runs instead of DMEM_Add's loop.  R: the restriction operators
+// themselves (rows = coarse points), as the library takes them.
+}   // extern "C"
+#include "DMEM_B200.hpp"
+extern "C" {
+int ref_dmem_solve_b200(int L, const RefCSR *A, const RefCSR *P, const RefCSR *R, double smooth_weight, int symmetrised, const double *b,
+                        int num_cycles, double tol, int async_flag, double *x_out, double *hist, int *corrections, double *relres)
+{
+   DMEM_AllData *dm = new DMEM_AllData();
+   dm->grid.num_levels = L;
+   dm->input.solver = async_flag ? ASYNC_MULTADD : MULTADD;
+   dm->input.smoother = JACOBI;
+   dm->input.smooth_weight = smooth_weight;
+   dm->input.simple_jacobi_flag = symmetrised ? -1 : 0;
+   dm->input.async_flag = async_flag;
+   dm->input.num_cycles = num_cycles;
+   dm->input.tol = tol;
+   dm->input.accel_type = 0;
+   dm->cheby.mu = 1.0; dm->cheby.delta = 1.0;
+   std::vector<B200Layout> lay(L);
+   std::vector<B200Csr> bA(L), bP(L), bR(L);
+   std::vector<int> owned(L);
+   for (int l = 0; l < L; l++) {
+      owned[l] = A[l].nrows;
+      lay[l] = B200Layout{A[l].nrows, 0, A[l].nrows, 0, 0, 0, 0, 0, &owned[l]};
+      bA[l] = B200Csr{A[l].nrows, A[l].ncols, A[l].nnz, A[l].i, A[l].j, A[l].data};
+      if (l < L - 1) {
+         bP[l] = B200Csr{P[l].nrows, P[l].ncols, P[l].nnz, P[l].i, P[l].j, P[l].data};
+         bR[l] = B200Csr{R[l].nrows, R[l].ncols, R[l].nnz, R[l].i, R[l].j, R[l].data};
+      }
+   }
+   amgb_ctx *ctx = DMEM_B200_Upload(dm, 0, L, lay.data(), bA.data(), bP.data(), bR.data());
+   const double rr = DMEM_Add_B200(dm, ctx, b, x_out, hist, corrections);
+   if (relres) *relres = rr;
+   const int done = dm->iter.cycle;
+   amgb_destroy(ctx);
+   delete dm;
+   return done;
+}
 #endif
 
 // SMEM_ExtendedSystemSolve (src/SMEM_ExtendedSystem.cpp:9-836) for IMPLICIT_EXTENDED_SYSTEM_BPX, the way SMEM_Main runs it

@@ -25,6 +25,8 @@ static inline int MPI_Comm_size(MPI_Comm, int *s) { *s = 1; return 0; }
 static inline int hypre_MPI_Comm_rank(MPI_Comm, int *r) { *r = 0; return 0; }
 static inline double MPI_Wtime(void) { return omp_get_wtime(); }
 static inline int MPI_Barrier(MPI_Comm) { return 0; }
+#define MPI_BYTE 1
+static inline int MPI_Bcast(void *, int, MPI_Datatype, int, MPI_Comm) { return 0; }     /* one process: the buffer already holds the root's data */
 #define MPI_STATUSES_IGNORE ((MPI_Status *)0)
 /* never reached on one rank (no neighbour, no other grid): */
 static inline int hypre_MPI_Waitall(int, MPI_Request *, MPI_Status *) { return 0; }

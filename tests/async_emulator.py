@@ -78,7 +78,11 @@ class Emulator:
     def run_group_iteration(self, q):
         for op in self.progs[q]:
             if op.type == SPMV:
-                M = (self.A, self.P, self.R)[op.mat_kind][op.mat_level]
+                if op.mat_kind == 3:         # coarse_solve: the dense inverse of the coarsest operator
+                    import scipy.sparse as sp
+                    M = sp.csr_matrix(np.linalg.inv(self.A[op.mat_level].toarray()))
+                else:
+                    M = (self.A, self.P, self.R)[op.mat_kind][op.mat_level]
                 if op.sval:
                     assert op.mat_kind == 0
                     M = self.Asv[op.mat_level]

@@ -23,7 +23,7 @@ V_R, V_UL = 3, 7
 
 class DistAsyncEmulator:
     def __init__(self, h, nranks, f, solver, smoother, w, symmetric=True, factor_level0=False, plane=None, min_rows_per_rank=64,
-                 fine_sweeps=1, coarse_sweeps=1):
+                 fine_sweeps=1, coarse_sweeps=1, coarse_solve=False):
         import scipy.sparse as sp
         self.h, self.P = h, nranks
         self.L = h.num_levels
@@ -33,7 +33,7 @@ class DistAsyncEmulator:
         layouts = [pl.layouts for pl in self.plans]
         self.progs, self.slot_off, self.slot_group, self.slot_vec = [], None, None, None
         for p in range(nranks):
-            pr, so, sg, sv = S.dist_async_plan(layouts, p, solver, smoother, symmetric, factor_level0, fine_sweeps, coarse_sweeps)
+            pr, so, sg, sv = S.dist_async_plan(layouts, p, solver, smoother, symmetric, factor_level0, fine_sweeps, coarse_sweeps, coarse_solve)
             if self.slot_off is None:
                 self.slot_off, self.slot_group, self.slot_vec = so, sg, sv
             else:       # the slot table must be the same on every rank: peers are addressed through it
@@ -56,6 +56,7 @@ class DistAsyncEmulator:
                 wsp.append(gws[l][lay.base:lay.base + lay.n_ext].copy())
             self.ws.append(wsp)
             self.Asv.append([a @ sp.diags(wsp[l]) for l, a in enumerate(self.A[p])])
+        self.Ainv = sp.csr_matrix(np.linalg.inv(h.A[-1].to_scipy().toarray()))
         self.fg = np.asarray(f, dtype=np.float64)
         self.Ag = h.A[0].to_scipy()
         self.f = []
@@ -109,7 +110,10 @@ class DistAsyncEmulator:
     def exec_op(self, p, q, i):
         op = self.progs[p][q][i]
         if op.type == SPMV:
-            M = (self.A, self.Pm, self.R)[op.mat_kind][p][op.mat_level]
+            if op.mat_kind == 3:             # coarse_solve: the dense inverse of the (replicated) coarsest operator
+                M = self.Ainv
+            else:
+                M = (self.A, self.Pm, self.R)[op.mat_kind][p][op.mat_level]
             if op.sval:
                 assert op.mat_kind == 0
                 M = self.Asv[p][op.mat_level]

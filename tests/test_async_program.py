@@ -102,3 +102,44 @@ def test_unsupported_combinations_are_refused():
         S.async_program(3, H.ASYNC_MULTADD, H.JACOBI, symmetric=True, async_type=1, read_type=1)
     with pytest.raises(S.AmgError):
         S.async_program(3, H.ASYNC_AFACX, H.JACOBI, symmetric=False, factor_level0=True)
+
+
+@pytest.mark.parametrize("fact0", [False, True])
+def test_direct_coarse_solve_program_is_the_dmem_sequential_model(fact0):
+    """amgb_options.coarse_solve: the coarsest group solves its level directly (DMEM's AddCycle, src/DMEM_Add.cpp:262-264).  The
+    oracle's sequential model of the DMEM convention (pinned by AddCycle's object code run for every grid in turn,
+    tests/golden/dmem.npz) gives every grid the FRESH fine residual; handing every group that residual before its turn, the
+    programs' chains -- restriction down to the coarsest level, the direct solve, prolongation, update -- must reproduce it"""
+    from async_emulator import V_R, V_UL
+    A, h, b = _multi()
+    w = 0.9
+    h.build_transfers(H.MULTADD, w)
+    K = 6
+    want, counts, rel = O.Problem(h, H.MULTADD, H.JACOBI, w, coarse_solve=1).solve_async_sequential(b, K)
+    hh = h
+    if fact0:
+        hh = H.Hierarchy(h.A, h.P_plain)
+        hh.build_transfers(H.MULTADD, w, factor_level0=True)
+    prog = S.async_program(h.num_levels, H.ASYNC_MULTADD, H.JACOBI, symmetric=True, factor_level0=fact0, coarse_solve=True)
+    assert len(prog[-1]) > 1                                   # the coarsest group works
+    e = Emulator(hh, prog, b, H.JACOBI, w)
+    for _ in range(K):
+        for q in range(h.num_levels):
+            e.vec(q, V_R * 64)[:] = e.f - e.A[0] @ e.u
+            e.vec(q, V_UL * 64)[:] = e.u
+            e.run_group_iteration(q)
+    assert e.count == [K] * h.num_levels
+    assert np.max(np.abs(e.u - want)) <= 1e-12 * np.max(np.abs(want))
+    assert abs(e.relres() - rel) <= 1e-12
+    # ... and with the groups simply taking turns (every group on its own, older residual) the solve converges as with the
+    # SMEM convention (on this grid the coarsest level has a handful of points and contributes little either way)
+    e1 = Emulator(hh, prog, b, H.JACOBI, w)
+    e1.run(12)
+    e0 = Emulator(hh, S.async_program(h.num_levels, H.ASYNC_MULTADD, H.JACOBI, symmetric=True, factor_level0=fact0), b, H.JACOBI, w)
+    e0.run(12)
+    assert e1.relres() < 1e-3 and e1.relres() < 1.5 * e0.relres()
+
+
+def test_direct_coarse_solve_is_refused_with_the_global_residual():
+    with pytest.raises(S.AmgError):
+        S.async_program(4, H.ASYNC_MULTADD, H.JACOBI, symmetric=True, res_compute_type=1, coarse_solve=True)

@@ -138,6 +138,25 @@ def test_without_the_exchange_flags_stale_ghosts_cost_orders_of_magnitude():
     assert min(without) > 10.0 * max(with_flags), (with_flags, without)
 
 
+@pytest.mark.parametrize("ranks,fact0", [(2, True), (3, False)])
+def test_direct_coarse_solve_lockstep_equals_the_single_gpu_programs(ranks, fact0):
+    """DMEM's convention for the coarsest level (direct solve) in the partitioned plans: the coarsest level is replicated, its
+    group restricts through the partitioned levels, gathers, solves, and prolongs back"""
+    h, b, plane = _problem("7pt", 12, fact0=fact0)
+    K = 5
+    ref = Emulator(h, S.async_program(h.num_levels, H.ASYNC_MULTADD, H.JACOBI, symmetric=True, factor_level0=fact0, coarse_solve=True),
+                   b, H.JACOBI, 0.9)
+    want = ref.run(K)
+    em = DistAsyncEmulator(h, ranks, b, H.ASYNC_MULTADD, H.JACOBI, 0.9, factor_level0=fact0, plane=plane, min_rows_per_rank=40,
+                           coarse_solve=True)
+    got = em.run_lockstep(K)
+    assert np.max(np.abs(got - want)) <= 1e-12 * np.max(np.abs(want))
+    em2 = DistAsyncEmulator(h, ranks, b, H.ASYNC_MULTADD, H.JACOBI, 0.9, factor_level0=fact0, plane=plane, min_rows_per_rank=40,
+                            coarse_solve=True)
+    em2.run_random(30, seed=3)
+    assert em2.relres() < 1e-4
+
+
 def test_unsupported_options_are_refused():
     h, b, plane = _problem("7pt", 12)
     with pytest.raises(S.AmgError):

@@ -375,6 +375,57 @@ def test_reference_structs_drive_the_library(name):
     assert true < 1e-9 and list(out["corrections"]) == [150] * h.num_levels
 
 
+@pytest.mark.parametrize("symmetrised,w", [(True, 0.8), (False, 0.5)])
+def test_reference_dmem_structs_drive_the_library(symmetrised, w):
+    """the DMEM binding (integration/DMEM_B200.hpp, compiled against the reference's DMEM_Main.hpp) on one rank: DMEM_AllData ->
+    DMEM_B200_Upload -> DMEM_Add_B200 must land on the history of DMEM_SyncAdd / DMEM_SyncAddCycle's own object code (direct solve
+    on the coarsest level), and its asynchronous branch (amgb_dist_solve_async with the DMEM coarse solve) must converge with
+    every level's corrections counted"""
+    if O.ref_b200_lib() is None:
+        pytest.skip("oracle/_ref/libref_b200.so not built (needs /root/reference at build time)")
+    A = H.laplacian("7pt", 14)
+    h = H.amg_setup(A)
+    h.build_transfers(H.MULTADD, w, num_pre=1, num_post=1 if symmetrised else 0)
+    b = H.rand_rhs(A.nrows)
+    x_ref, hist_ref = O.ref_dmem_sync_add(h, b, w, symmetrised=symmetrised, num_cycles=100, tol=1e-9)     # the reference's object code
+    got = O.ref_dmem_solve_b200(h, b, w, symmetrised=symmetrised, num_cycles=100, tol=1e-9)
+    assert got["cycles"] == len(hist_ref) - 1
+    assert_hist_close(got["hist"], hist_ref)
+    assert np.max(np.abs(got["x"] - x_ref)) <= 1e-11 * np.max(np.abs(x_ref))
+    K = 80
+    out = O.ref_dmem_solve_b200(h, b, w, symmetrised=symmetrised, num_cycles=K, tol=1e-9, async_flag=1)
+    assert list(out["corrections"]) == [K] * h.num_levels
+    true = O.norm2(O.spgemv(h.A[0], out["x"], b, -1.0, 1.0)) / O.norm2(b)
+    # (groups taking turns reach 3e-16 / 1e-8 here; the bound leaves room for what the interleaving of the moment costs)
+    assert abs(true - out["relres"]) <= 1e-12 and true < (1e-6 if symmetrised else 1e-4), true
+
+
+@pytest.mark.parametrize("fact0", [False, True])
+def test_async_solve_with_the_dmem_coarse_solve(fact0):
+    """amgb_options.coarse_solve in the persistent kernel: the coarsest group solves its level directly (AddCycle,
+    src/DMEM_Add.cpp:262-264) instead of idling; the programs are pinned on the CPU (tests/test_async_program.py), here the
+    kernel must reach the tolerance with every group's corrections counted, on one GPU and through the partitioned path"""
+    from async_multigrid_b200 import partition as PT
+    w = 0.9
+    A = H.laplacian("7pt", 20)
+    h = H.amg_setup(A)
+    h.build_transfers(H.MULTADD, w, factor_level0=fact0)
+    b = H.rand_rhs(A.nrows)
+    s = amg.Solver(h, H.ASYNC_MULTADD, H.JACOBI, w, factor_level0=fact0, coarse_solve=True)
+    s.set_rhs(b)
+    s.set_solution(None)
+    cor, rel, _ = s.solve_async(60)
+    u = s.get_solution()
+    true = O.norm2(O.spgemv(h.A[0], u, b, -1.0, 1.0)) / O.norm2(b)
+    assert list(cor) == [60] * h.num_levels and true < 1e-7 and abs(true - rel) <= 1e-12, true
+    s.close()
+    d = amg.DistSolver(PT.RankPlan(h, 1, 0), amg.solver.dist_unique_id(), w, factor_level0=fact0, coarse_solve=True)
+    d.set_rhs(b)
+    cor, rel, _ = d.DMEM_Add_async(60)
+    assert list(cor) == [60] * h.num_levels and rel < 1e-7, rel
+    d.close()
+
+
 def test_l1_hybrid_jgs_bpx_cycle_matches_oracle():
     """L1_HYBRID_JACOBI_GAUSS_SEIDEL (smoother 12, Parfor smoother of BPX: hybrid JGS divided by the l1 norms,
     src/SMEM_Smooth.cpp:253-263); the oracle's restatement is pinned by the reference's object code (tests/test_oracle_golden.py)"""
