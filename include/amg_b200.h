@@ -63,7 +63,9 @@ typedef struct {
    int coarse_solve;            /* 0: SMEM convention, the coarsest level contributes nothing to Multadd/AFACx (the reference's
                                    hypre_GaussElimSolve result is never used there); 1: DMEM convention, direct solve
                                    on the coarsest level (src/DMEM_Add.cpp:262-264, src/DMEM_Mult.cpp:393; with AMGB_SOLVER_MULT: DMEM_MultCycle,
-                                   src/DMEM_Mult.cpp:207, instead of SMEM's pre + post sweeps there) applied as a dense inverse */
+                                   src/DMEM_Mult.cpp:207, instead of SMEM's pre + post sweeps there) applied as a dense inverse; in the
+                                   asynchronous solves (amgb_solve_async, amgb_dist_solve_async) the coarsest level's group then
+                                   works like the others: restrict, solve directly (AddCycle), prolong, update */
    int sell_sigma;              /* > 1: SELL-C-sigma (rows sorted by length inside windows of sigma rows) for the
                                    non-stencil matrices whose padding then stays <= 25 %; 0/1: off */
    int stream_variant;          /* geometry of the CSR-stream kernel (csrc/launch.h kStreamVariants; default 8 = warp-granular, 256-entry chunks) */
