@@ -255,6 +255,7 @@ static int dist_async_prepare(amgb_ctx *c)
 {
    DistState *d = c->dist;
    if (d->da && d->da->ready) return AMGB_OK;
+   if (d->da) return amgb_fail(c, AMGB_ESTATE, "an earlier preparation of the row-partitioned asynchronous solve failed on this context");
    if (c->async_ready) return amgb_fail(c, AMGB_ESTATE, "this context already ran the single-GPU asynchronous solve");
    const int L = c->L, P = d->nranks, rank = d->rank;
    const amgb_options &o = c->opt;
