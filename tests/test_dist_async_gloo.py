@@ -1,5 +1,5 @@
 """The row-partitioned asynchronous solve's plans (csrc/dist_async.cu dist_async_plan) executed by SEPARATE PROCESSES over
-torch.distributed (gloo, world_size 2 and 3): every process interprets only its own rank's programs on its own arena;
+torch.distributed (gloo, world_size 2, 3 and 4): every process interprets only its own rank's programs on its own arena;
 AOP_PUSH becomes a message to the destination rank, AOP_SIGNAL a message carrying the exchange-step number, AOP_WAIT drains
 the source rank's messages until the step has arrived.  That is the device protocol with the NVLink stores replaced by
 messages: a rank sees a peer's boundary values only through the pushes the plan contains, and can only proceed past a wait
@@ -87,7 +87,7 @@ def _worker(rank, world, port, n, min_rows, fact0, K, q_out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n,min_rows,fact0", [(2, 12, 40, True), (3, 12, 40, False), (2, 16, 64, True)])
+@pytest.mark.parametrize("world,n,min_rows,fact0", [(2, 12, 40, True), (3, 12, 40, False), (2, 16, 64, True), (4, 16, 40, True)])
 def test_plans_run_by_separate_processes_equal_the_single_gpu_programs(world, n, min_rows, fact0):
     import torch.multiprocessing as mp
     sys.path.insert(0, os.path.join(ROOT, "tests"))
