@@ -210,10 +210,33 @@ def _leg(args, rank, world, local, dims, tag, steps, warmup, sampler=None, want_
     return out
 
 
+def _calibrate_corrections(one, sync_cycles, tol, max_tries=5):
+    """The LOCAL stop rule takes the correction count as an input (as the reference's -num_cycles): the smallest count that
+    reaches the tolerance, searched from the synchronous solve's cycle count -- downwards in steps of 2 while the solve still
+    converges with a margin (the asynchronous result varies a little from run to run), else upwards in steps of 4.
+    one(K) -> (corrections per level, relres, seconds).  -> (K, [tries])"""
+    K, tried = int(sync_cycles), []
+    cor, rel, secs = one(K)
+    tried.append({"corrections": K, "relres": rel, "seconds": secs})
+    if rel < tol:
+        while K > 4 and len(tried) < max_tries:
+            cor, rel, secs = one(K - 2)
+            tried.append({"corrections": K - 2, "relres": rel, "seconds": secs})
+            if rel >= 0.7 * tol:
+                break
+            K -= 2
+    else:
+        while rel >= tol and len(tried) < max_tries:
+            K += 4
+            cor, rel, secs = one(K)
+            tried.append({"corrections": K, "relres": rel, "seconds": secs})
+    return K, tried
+
+
 def _async_on(s, plan, args, world, sync_cycles, steps):
     """the ROW-PARTITIONED asynchronous Multadd solve (csrc/dist_async.cu, DMEM_Add's asynchronous loop) on the solver the
-    synchronous leg just used: from x0 = 0, every level group of every rank performs K corrections (LOCAL stop rule); K is
-    the smallest of sync_cycles, +4, +8 ... that reaches the tolerance.  Every rank returns the same record (the ranks
+    synchronous leg just used: from x0 = 0, every level group of every rank performs K corrections (LOCAL stop rule); K from
+    _calibrate_corrections.  Every rank returns the same record (the ranks
     fail together or not at all: amgb_dist_solve_async agrees on errors before it returns)."""
     import torch
     import torch.distributed as dist
@@ -229,25 +252,9 @@ def _async_on(s, plan, args, world, sync_cycles, steps):
         return [int(x) for x in cor], float(rel), float(t.item())
 
     try:
-        # the LOCAL stop rule takes the correction count as an input (as the reference's -num_cycles): calibrate it to the
-        # smallest count that reaches the tolerance, starting from the synchronous solve's cycle count, in steps of 2
-        K, tried = int(sync_cycles), []
-        cor, rel, secs = one(K)
-        tried.append({"corrections": K, "relres": rel, "seconds": secs})
-        if rel < TOL:
-            while K > 4 and len(tried) < 5:
-                cor, rel, secs = one(K - 2)
-                tried.append({"corrections": K - 2, "relres": rel, "seconds": secs})
-                if rel >= 0.7 * TOL:      # (a margin: the asynchronous result varies a little from run to run)
-                    break
-                K -= 2
-        else:
-            while rel >= TOL and len(tried) < 5:
-                K += 4
-                cor, rel, secs = one(K)
-                tried.append({"corrections": K, "relres": rel, "seconds": secs})
+        K, tried = _calibrate_corrections(one, int(sync_cycles), TOL)
         times = []
-        for _ in range(steps):
+        for _ in range(max(int(steps), 1)):
             cor, rel, secs = one(K)
             times.append(secs)
         cb, gt = s.async_groups()
@@ -255,7 +262,7 @@ def _async_on(s, plan, args, world, sync_cycles, steps):
         return {"solver": "asynchronous Multadd, row-partitioned: one persistent kernel per GPU, level groups exchange boundaries by stores "
                           "over NVLink with per-group step flags, groups asynchronous to one another (LOCAL stop rule)",
                 "corrections_per_level": cor, "relres": rel, "converged": bool(rel < TOL), "value": float(np.mean(times)), "unit": "s",
-                "timing": "kernel seconds, max over ranks (CUDA events around each rank's launch), mean of %d solves" % steps,
+                "timing": "kernel seconds, max over ranks (CUDA events around each rank's launch), mean of %d solves" % len(times),
                 "ms_per_correction_round": float(np.mean(times)) * 1e3 / K, "calibration": tried,
                 "cta_groups_rank0": [int(x) for x in np.diff(cb)], "group_seconds_rank0": [round(float(x), 4) for x in gt],
                 "sync_cycles": int(sync_cycles)}

@@ -191,3 +191,26 @@ def test_bench_plan_roundtrip_through_disk(tmp_path):
                 assert np.array_equal(mg.indices, mw.indices) and np.array_equal(mg.data, mw.data)
         l0 = want.layouts[0]
         assert np.array_equal(got.b, b[l0.row_start:l0.row_start + l0.n_owned])
+
+
+def test_bench_calibration_of_the_asynchronous_correction_count():
+    """dist_bench._calibrate_corrections (bench.py --gpus N, asynchronous leg): from the synchronous cycle count down in steps of
+    2 while the solve converges with a margin, else up in steps of 4, at most five tries"""
+    sys.path.insert(0, ROOT)
+    import async_multigrid_b200 as amg  # noqa: F401
+    from async_multigrid_b200 import dist_bench as DB
+    calls = []
+
+    def one(K):
+        calls.append(K)
+        return [K] * 3, 0.6 ** K, 0.001 * K
+
+    K, tried = DB._calibrate_corrections(one, 46, 1e-9)
+    assert K == 42 and [t["corrections"] for t in tried] == [46, 44, 42, 40]          # 0.6^40 = 1.3e-9 misses, 0.6^42 = 4.8e-10 < 0.7e-9
+    K, tried = DB._calibrate_corrections(one, 30, 1e-9)
+    assert K == 42 and [t["corrections"] for t in tried] == [30, 34, 38, 42]
+    K, tried = DB._calibrate_corrections(one, 20, 1e-9)
+    assert K == 36 and len(tried) == 5 and tried[-1]["relres"] > 1e-9                   # gives up: the record then says converged = false
+    K, tried = DB._calibrate_corrections(one, 60, 1e-9)
+    assert K == 52 and len(tried) == 5                                                  # never more than five solves
+    assert all(t["seconds"] == 0.001 * t["corrections"] for t in tried)
